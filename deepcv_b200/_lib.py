@@ -1,0 +1,106 @@
+""" ctypes binding of the C ABI declared in `include/deepcv_b200.h` (built in-tree as `deepcv_b200/libdeepcv_b200.so`).
+
+There is no CPU implementation behind these symbols and no fallback here either: if the shared library is missing, or a
+call returns non-zero, a `RuntimeError` is raised with the library's own message.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from pathlib import Path
+
+__all__ = ['lib', 'ConvShape', 'NormParams', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
+           'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
+
+DCV_F32, DCV_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_SIGMOID = 0, 1, 2, 3
+ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05 = 0, 1, 2
+
+
+class ConvShape(Structure):
+    _fields_ = [(n, c_int32) for n in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'stride_h', 'stride_w', 'pad_h', 'pad_w', 'dil_h', 'dil_w', 'p', 'q')]
+
+
+class NormParams(Structure):
+    _fields_ = [('n', c_int32), ('c', c_int32), ('hw', c_int32), ('use_bn', c_int32), ('bn_training', c_int32),
+                ('bn_eps', c_float), ('bn_momentum', c_float),
+                ('bn_weight', c_void_p), ('bn_bias', c_void_p), ('bn_running_mean', c_void_p), ('bn_running_var', c_void_p),
+                ('bn_num_batches_tracked', c_void_p),
+                ('use_gn', c_int32), ('gn_groups', c_int32), ('gn_eps', c_float),
+                ('gn_weight', c_void_p), ('gn_bias', c_void_p)]
+
+
+P = c_void_p
+""" name -> (restype, argtypes); must list every symbol `include/deepcv_b200.h` declares (tests/test_abi.py checks both ways). """
+SYMBOLS = {
+    'dcv_abi_version': (c_int, []),
+    'dcv_last_error': (c_char_p, []),
+    'dcv_device_check': (c_int, []),
+    'dcv_launch_count': (c_uint64, []),
+    'dcv_preprocess_u8': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P]),
+    'dcv_nchw_to_nhwc': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_nhwc_to_nchw': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_cast': (c_int, [P, c_int, P, c_int, c_size_t, P]),
+    'dcv_pack_conv_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_conv2d_fwd': (c_int, [POINTER(ConvShape), P, P, P, P, P, c_int, c_float, c_int, c_int, P]),
+    'dcv_conv2d_dgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, P]),
+    'dcv_conv2d_wgrad_workspace': (c_size_t, [POINTER(ConvShape), c_int, c_int]),
+    'dcv_conv2d_wgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, P]),
+    'dcv_norm_stats': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_norm_saved_floats': (c_size_t, [c_int, c_int, c_int]),
+    'dcv_norm_fwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P]),
+    'dcv_norm_apply_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_norm_bwd_reduce': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_norm_bwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P, P, P, P, P, P]),
+    'dcv_act_norm_bwd_apply': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, P]),
+    'dcv_avgpool2d_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_avgpool2d_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_axpby': (c_int, [P, P, P, c_float, c_float, c_size_t, c_int, P]),
+    'dcv_copy_channels_in': (c_int, [P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
+    'dcv_copy_channels_out': (c_int, [P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
+    'dcv_bilinear_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_bilinear_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_linear_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
+    'dcv_linear_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
+    'dcv_softmax_ce': (c_int, [P, P, P, P, c_int, c_int, P]),
+    'dcv_counter_add': (c_int, [P, c_int32, P]),
+    'dcv_adamw_flat': (c_int, [P, P, P, P, c_size_t, P, c_float, c_float, c_float, c_float, c_float, P, P]),
+}
+
+
+def library_path() -> Path:
+    return Path(os.environ.get('DEEPCV_B200_LIB', Path(__file__).resolve().parent / 'libdeepcv_b200.so'))
+
+
+class _Library:
+    """ Lazy handle: the shared object is loaded on first attribute access so that importing the package (spec parsing,
+    shape inference on `meta` tensors) works in a process that never launches a kernel. """
+
+    def __init__(self):
+        self._cdll = None
+
+    def _load(self):
+        if self._cdll is None:
+            path = library_path()
+            if not path.exists():
+                raise RuntimeError(f'deepcv_b200: CUDA extension "{path}" is missing. Build it with `python -m deepcv_b200.csrc.build` '
+                                   '(or `__graft_entry__.build()`); there is no CPU or PyTorch fallback for this path.')
+            cdll = ctypes.CDLL(str(path))
+            for name, (restype, argtypes) in SYMBOLS.items():
+                fn = getattr(cdll, name)
+                fn.restype, fn.argtypes = restype, argtypes
+            if cdll.dcv_abi_version() != 1:
+                raise RuntimeError(f'deepcv_b200: ABI version mismatch ({cdll.dcv_abi_version()} != 1); rebuild the extension')
+            self._cdll = cdll
+        return self._cdll
+
+    def __getattr__(self, name):
+        return getattr(self._load(), name)
+
+
+lib = _Library()
+
+
+def check(status: int, what: str = '') -> None:
+    if status != 0:
+        msg = lib.dcv_last_error()
+        raise RuntimeError(f'deepcv_b200{": " + what if what else ""}: {msg.decode() if msg else "error " + str(status)}')

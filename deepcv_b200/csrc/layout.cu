@@ -1,0 +1,104 @@
+// Layout / dtype plumbing: NCHW <-> NHWC transposes (tiled through shared memory so both sides stay coalesced),
+// flat casts, and convolution-weight packing for the tensor-core / data-gradient operands.
+#include "common.cuh"
+
+namespace dcv {
+
+// src viewed as [batch][rows][cols] -> dst [batch][cols][rows]
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int rows, int cols, int tiles_r, int tiles_c) {
+  __shared__ float tile[32][33];
+  const int tiles_per_batch = tiles_r * tiles_c;
+  const int b = blockIdx.x / tiles_per_batch;
+  const int t = blockIdx.x - b * tiles_per_batch;
+  const int tr = t / tiles_c, tc = t - tr * tiles_c;
+  const size_t base = (size_t)b * rows * cols;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = tr * 32 + ty + 8 * k, c = tc * 32 + tx;
+    if (r < rows && c < cols) tile[ty + 8 * k][tx] = to_f<TS>(src[base + (size_t)r * cols + c]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = tc * 32 + ty + 8 * k, r = tr * 32 + tx;
+    if (r < rows && c < cols) dst[base + (size_t)c * rows + r] = from_f<TD>(tile[tx][ty + 8 * k]);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) dst[i] = from_f<TD>(to_f<TS>(src[i]));
+}
+
+template <typename TD>
+__global__ void pack_weight_kernel(const float* __restrict__ w, TD* __restrict__ dst, int k, int r, int s, int c, int transpose_flip) {
+  const size_t total = (size_t)k * r * s * c;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i;
+    const int ci = t % c; t /= c;
+    const int si = t % s; t /= s;
+    const int ri = t % r; const int ki = t / r;
+    const size_t o = transpose_flip ? ((((size_t)ci * r + (r - 1 - ri)) * s + (s - 1 - si)) * k + ki) : i;
+    dst[o] = from_f<TD>(w[i]);
+  }
+}
+
+template <typename TS, typename TD>
+static int launch_transpose(const void* src, void* dst, int batch, int rows, int cols, cudaStream_t st) {
+  const int tiles_r = (rows + 31) / 32, tiles_c = (cols + 31) / 32;
+  const size_t blocks = (size_t)batch * tiles_r * tiles_c;
+  DCV_REQUIRE(blocks < (1u << 31), "transpose: too many tiles");
+  transpose_kernel<TS, TD><<<(unsigned)blocks, 256, 0, st>>>((const TS*)src, (TD*)dst, rows, cols, tiles_r, tiles_c);
+  DCV_LAUNCH_CHECK("transpose_kernel");
+  return 0;
+}
+
+static int transpose_dispatch(const void* src, int sd, void* dst, int dd, int batch, int rows, int cols, cudaStream_t st) {
+  DCV_REQUIRE(src && dst && batch > 0 && rows > 0 && cols > 0, "transpose: bad arguments");
+  if (sd == DCV_F32 && dd == DCV_F32) return launch_transpose<float, float>(src, dst, batch, rows, cols, st);
+  if (sd == DCV_F32 && dd == DCV_BF16) return launch_transpose<float, __nv_bfloat16>(src, dst, batch, rows, cols, st);
+  if (sd == DCV_BF16 && dd == DCV_F32) return launch_transpose<__nv_bfloat16, float>(src, dst, batch, rows, cols, st);
+  if (sd == DCV_BF16 && dd == DCV_BF16) return launch_transpose<__nv_bfloat16, __nv_bfloat16>(src, dst, batch, rows, cols, st);
+  DCV_REQUIRE(false, "transpose: unsupported dtypes %d -> %d", sd, dd);
+  return 1;
+}
+
+}  // namespace dcv
+
+extern "C" {
+
+int dcv_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int n, int c, int h, int w, void* stream) {
+  return dcv::transpose_dispatch(src, src_dtype, dst, dst_dtype, n, c, h * w, dcv::as_stream(stream));
+}
+
+int dcv_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int n, int c, int h, int w, void* stream) {
+  return dcv::transpose_dispatch(src, src_dtype, dst, dst_dtype, n, h * w, c, dcv::as_stream(stream));
+}
+
+int dcv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t count, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(src && dst, "cast: null pointer");
+  if (count == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int g = grid_for(count, 256);
+  if (src_dtype == DCV_F32 && dst_dtype == DCV_BF16) cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, count);
+  else if (src_dtype == DCV_BF16 && dst_dtype == DCV_F32) cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, count);
+  else if (src_dtype == DCV_F32 && dst_dtype == DCV_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, count);
+  else if (src_dtype == DCV_BF16 && dst_dtype == DCV_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, count);
+  else DCV_REQUIRE(false, "cast: unsupported dtypes %d -> %d", src_dtype, dst_dtype);
+  DCV_LAUNCH_CHECK("cast_kernel");
+  return 0;
+}
+
+int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, int r, int s, int c, int transpose_flip, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(w_krsc && dst && k > 0 && r > 0 && s > 0 && c > 0, "pack_conv_weight: bad arguments");
+  const size_t total = (size_t)k * r * s * c;
+  DCV_DISPATCH_DTYPE(dst_dtype, T, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w_krsc, (T*)dst, k, r, s, c, transpose_flip)));
+  DCV_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,469 @@
+// BatchNorm / GroupNorm after the activation, restated as ONE affine per (image, channel).
+//
+// Forward:   y = act(conv(x))  --(sum y, sum y^2 per (n,c))-->  finalize  -->  z = A[n][c]*y + B[n][c]
+// Backward:  (sum dz, sum dz*y per (n,c))  -->  finalize  -->  dy = act'(y) * (P[n][c]*dz + Q[n][c]*y + R[n][c])
+//
+// Why this is exact: BatchNorm is a per-channel affine u = alpha_c*y + beta_c whose coefficients depend only on
+// per-channel sums; GroupNorm applied to u is an affine per (n, group) whose mean / variance over u are closed-form in
+// the per-(n,c) sums of y and y^2. The same holds for the adjoint: every reduction BatchNorm-backward and
+// GroupNorm-backward need is bilinear in (dz, y) per (n,c). So the tensor is read once for statistics (or not at all
+// when the convolution epilogue produced them) and once for the apply, instead of the >= 4 passes per block of the
+// module-by-module reference path (meta/nn.py:553). The finalize kernels do the small per-(n,c) algebra in fp64.
+//
+// HBM roofline: apply fwd = 2*E*s bytes, stats = E*s, bwd reduce = 2*E*s, bwd apply = 3*E*s  (E elements, s bytes each).
+#include "common.cuh"
+
+namespace dcv {
+
+// Thread -> (column, row) mapping shared by the streaming kernels: a CTA owns `chunk` pixels of one image and
+// `cols_per_block` 16-byte (or scalar) columns; a thread keeps ONE column for its whole life so per-(n,c) coefficients
+// and partial sums live in registers.
+struct NcGeom {
+  int n, hw, c;
+  int cv;              // columns per pixel (c / VE)
+  int cols_per_block;  // <= 256
+  int rows;            // threads per column
+  int chunk;           // pixels per CTA
+};
+
+template <int VE>
+static NcGeom make_geom(int n, int hw, int c, dim3* grid, int* block) {
+  NcGeom g;
+  g.n = n; g.hw = hw; g.c = c; g.cv = c / VE;
+  g.cols_per_block = g.cv < 256 ? g.cv : 256;
+  g.rows = 256 / g.cols_per_block;
+  if (g.rows < 1) g.rows = 1;
+  *block = g.cols_per_block * g.rows;
+  // aim for >= 4 CTAs per SM overall, at least 4 pixels per thread-row
+  const int col_blocks = (g.cv + g.cols_per_block - 1) / g.cols_per_block;
+  long long want_chunks = (long long)kNumSMs * 4 / ((long long)n * col_blocks) + 1;
+  int chunk = (int)((hw + want_chunks - 1) / want_chunks);
+  const int min_chunk = g.rows * 4;
+  if (chunk < min_chunk) chunk = min_chunk;
+  if (chunk > hw) chunk = hw;
+  g.chunk = chunk;
+  *grid = dim3((hw + chunk - 1) / chunk, n, col_blocks);
+  return g;
+}
+
+template <typename T, int VE> __device__ __forceinline__ void load_vec(const T* p, float* out) {
+  if constexpr (VE == 1) out[0] = to_f<T>(*p);
+  else vec_unpack<T>(*reinterpret_cast<const uint4*>(p), out);
+}
+template <typename T, int VE> __device__ __forceinline__ void store_vec(T* p, const float* in) {
+  if constexpr (VE == 1) *p = from_f<T>(in[0]);
+  else *reinterpret_cast<uint4*>(p) = vec_pack<T>(in);
+}
+
+// Reduces `NV` per-thread values per column element across the `rows` threads that share a column, then one atomicAdd per
+// element into dst[elem * dst_stride + v] (dst_stride >= NV).
+template <int VE, int NV>
+__device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, int colg, float* dst_col0, int dst_stride) {
+  __shared__ float red[256 * 16];  // [row][col][VE*NV] flattened; VE*NV <= 16
+  constexpr int PER = VE * NV;
+  static_assert(PER <= 16, "column_reduce_atomic: too many values per thread");
+  const int t = row * g.cols_per_block + col;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < VE; ++e) red[t * PER + v * VE + e] = acc[v][e];
+  __syncthreads();
+  if (row == 0 && colg < g.cv) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        float s = 0.f;
+        for (int r = 0; r < g.rows; ++r) s += red[(r * g.cols_per_block + col) * PER + v * VE + e];
+        atomicAdd(dst_col0 + (size_t)e * dst_stride + v, s);
+      }
+  }
+}
+
+// ---- statistics: stats[n][c][2] += {sum y, sum y^2}
+template <typename T, int VE>
+__global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, float* __restrict__ stats, const NcGeom g) {
+  const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
+  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
+  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
+  float acc[2][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+  if (colg < g.cv) {
+    const T* base = y + ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
+    for (int p = p0 + row; p < p1; p += g.rows) {
+      float v[VE];
+      load_vec<T, VE>(base + (size_t)p * g.c, v);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
+    }
+  }
+  column_reduce_atomic<VE, 2>(acc, g, col, row, colg, stats + ((size_t)img * g.c + (size_t)colg * VE) * 2, 2);
+}
+
+// ---- forward apply: z = A*y + B
+template <typename T, int VE>
+__global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ z, const NcGeom g) {
+  const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
+  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
+  if (colg >= g.cv) return;
+  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
+  float A[VE], B[VE];
+  const float* abp = ab + ((size_t)img * g.c + (size_t)colg * VE) * 2;
+#pragma unroll
+  for (int e = 0; e < VE; ++e) { A[e] = abp[2 * e]; B[e] = abp[2 * e + 1]; }
+  const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
+  for (int p = p0 + row; p < p1; p += g.rows) {
+    float v[VE];
+    load_vec<T, VE>(y + base + (size_t)p * g.c, v);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
+    store_vec<T, VE>(z + base + (size_t)p * g.c, v);
+  }
+}
+
+// ---- backward reduce: s[n][c][2] += {sum dz, sum dz*y}
+template <typename T, int VE>
+__global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y, float* __restrict__ s, const NcGeom g) {
+  const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
+  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
+  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
+  float acc[2][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+  if (colg < g.cv) {
+    const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
+    for (int p = p0 + row; p < p1; p += g.rows) {
+      float a[VE], b[VE];
+      load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
+      load_vec<T, VE>(y + base + (size_t)p * g.c, b);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
+    }
+  }
+  column_reduce_atomic<VE, 2>(acc, g, col, row, colg, s + ((size_t)img * g.c + (size_t)colg * VE) * 2, 2);
+}
+
+// ---- backward apply: dy = act'(y) * (P*dz + Q*y + R); dbias[c] += sum dy
+template <typename T, int VE>
+__global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ pqr,
+                                                        T* __restrict__ dy, float* __restrict__ dbias, int act, float slope, const NcGeom g) {
+  const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
+  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
+  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
+  float acc[1][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = 0.f;
+  if (colg < g.cv) {
+    float P[VE], Q[VE], R[VE];
+    if (pqr) {
+      const float* pp = pqr + ((size_t)img * g.c + (size_t)colg * VE) * 3;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) { P[e] = pp[3 * e]; Q[e] = pp[3 * e + 1]; R[e] = pp[3 * e + 2]; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VE; ++e) { P[e] = 1.f; Q[e] = 0.f; R[e] = 0.f; }
+    }
+    const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
+    for (int p = p0 + row; p < p1; p += g.rows) {
+      float a[VE], b[VE];
+      load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
+      load_vec<T, VE>(y + base + (size_t)p * g.c, b);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        const float pre = fmaf(P[e], a[e], fmaf(Q[e], b[e], R[e]));
+        a[e] = pre * act_grad_from_output(b[e], act, slope);
+        acc[0][e] += a[e];
+      }
+      store_vec<T, VE>(dy + base + (size_t)p * g.c, a);
+    }
+  }
+  if (dbias) column_reduce_atomic<VE, 1>(acc, g, col, row, colg, dbias + (size_t)colg * VE, 1);
+}
+
+// ---- finalize kernels: one CTA, fp64 algebra on the tiny per-(n,c) arrays -------------------------------------------
+// `saved` layout (floats): [0,2c) BN mean,rstd | [2c,4c) alpha,beta | [4c, 4c+2nG) GN mean,rstd | [.., +2nG) scratch A,B per
+// (n,g) | [.., +2c) scratch U1,U2 per channel.
+__device__ __forceinline__ size_t off_alpha(int c) { return 2 * (size_t)c; }
+__device__ __forceinline__ size_t off_gn(int c) { return 4 * (size_t)c; }
+__device__ __forceinline__ size_t off_ab(int c, int n, int G) { return 4 * (size_t)c + 2 * (size_t)n * G; }
+__device__ __forceinline__ size_t off_u(int c, int n, int G) { return 4 * (size_t)c + 4 * (size_t)n * G; }
+
+__global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, float* __restrict__ ab, float* __restrict__ saved) {
+  const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1;
+  const double hw = (double)prm.hw;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // 1. BatchNorm per channel
+  for (int ch = tid; ch < c; ch += nt) {
+    double alpha = 1.0, beta = 0.0, mean = 0.0, rstd = 1.0;
+    if (prm.use_bn) {
+      double var;
+      if (prm.bn_training) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < n; ++i) { s1 += (double)stats[((size_t)i * c + ch) * 2]; s2 += (double)stats[((size_t)i * c + ch) * 2 + 1]; }
+        const double m = (double)n * hw;
+        mean = s1 / m;
+        var = s2 / m - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (prm.bn_running_mean && prm.bn_running_var) {
+          double mom = (double)prm.bn_momentum;
+          if (mom < 0.0) mom = 1.0 / (double)((prm.bn_num_batches_tracked ? *prm.bn_num_batches_tracked : 0) + 1);
+          const double unbiased = m > 1.0 ? var * m / (m - 1.0) : var;
+          prm.bn_running_mean[ch] = (float)((1.0 - mom) * (double)prm.bn_running_mean[ch] + mom * mean);
+          prm.bn_running_var[ch] = (float)((1.0 - mom) * (double)prm.bn_running_var[ch] + mom * unbiased);
+        }
+      } else {
+        mean = (double)prm.bn_running_mean[ch];
+        var = (double)prm.bn_running_var[ch];
+      }
+      rstd = rsqrt(var + (double)prm.bn_eps);
+      const double gamma = prm.bn_weight ? (double)prm.bn_weight[ch] : 1.0;
+      const double bias = prm.bn_bias ? (double)prm.bn_bias[ch] : 0.0;
+      alpha = gamma * rstd;
+      beta = bias - mean * alpha;
+    }
+    saved[2 * ch] = (float)mean; saved[2 * ch + 1] = (float)rstd;
+    saved[off_alpha(c) + 2 * ch] = (float)alpha; saved[off_alpha(c) + 2 * ch + 1] = (float)beta;
+  }
+  __syncthreads();
+  if (tid == 0 && prm.use_bn && prm.bn_training && prm.bn_num_batches_tracked) *prm.bn_num_batches_tracked += 1;
+  // 2. GroupNorm per (n, group) on u = alpha*y + beta
+  if (prm.use_gn) {
+    const int cg = c / G;
+    const double mg = (double)cg * hw;
+    for (int i = tid; i < n * G; i += nt) {
+      const int img = i / G, grp = i - img * G;
+      double su = 0.0, suu = 0.0;
+      for (int k = 0; k < cg; ++k) {
+        const int ch = grp * cg + k;
+        const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
+        const double sy = (double)stats[((size_t)img * c + ch) * 2], syy = (double)stats[((size_t)img * c + ch) * 2 + 1];
+        su += al * sy + hw * be;
+        suu += al * al * syy + 2.0 * al * be * sy + hw * be * be;
+      }
+      const double mean = su / mg;
+      double var = suu / mg - mean * mean;
+      if (var < 0.0) var = 0.0;
+      saved[off_gn(c) + 2 * (size_t)i] = (float)mean;
+      saved[off_gn(c) + 2 * (size_t)i + 1] = (float)rsqrt(var + (double)prm.gn_eps);
+    }
+    __syncthreads();
+  }
+  // 3. combined affine per (n, c)
+  const int cg = c / G;
+  for (int i = tid; i < n * c; i += nt) {
+    const int img = i / c, ch = i - img * c;
+    double A = (double)saved[off_alpha(c) + 2 * ch], B = (double)saved[off_alpha(c) + 2 * ch + 1];
+    if (prm.use_gn) {
+      const size_t gi = (size_t)img * G + ch / cg;
+      const double mean = (double)saved[off_gn(c) + 2 * gi], rstd = (double)saved[off_gn(c) + 2 * gi + 1];
+      const double a2 = (prm.gn_weight ? (double)prm.gn_weight[ch] : 1.0) * rstd;
+      const double b2 = (prm.gn_bias ? (double)prm.gn_bias[ch] : 0.0) - mean * a2;
+      B = a2 * B + b2;
+      A = a2 * A;
+    }
+    ab[2 * (size_t)i] = (float)A; ab[2 * (size_t)i + 1] = (float)B;
+  }
+}
+
+// D1, D2, D3 of du = D1*dz + D2*y + D3 (GroupNorm adjoint w.r.t. its input u, expressed on (dz, y)).
+__device__ __forceinline__ void gn_adjoint_coeffs(const dcv_norm_params& prm, const float* saved, int img, int ch, int G, double& D1, double& D2, double& D3) {
+  if (!prm.use_gn) { D1 = 1.0; D2 = 0.0; D3 = 0.0; return; }
+  const int c = prm.c, cg = c / G;
+  const size_t gi = (size_t)img * G + ch / cg;
+  const double mean_u = (double)saved[off_gn(c) + 2 * gi], r = (double)saved[off_gn(c) + 2 * gi + 1];
+  const double Ag = (double)saved[off_ab(c, prm.n, G) + 2 * gi], Bg = (double)saved[off_ab(c, prm.n, G) + 2 * gi + 1];
+  const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
+  const double gam = prm.gn_weight ? (double)prm.gn_weight[ch] : 1.0;
+  D1 = r * gam;
+  D2 = -r * Bg * r * al;
+  D3 = -r * Ag - r * Bg * r * (be - mean_u);
+}
+
+__global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, const float* __restrict__ s,
+                                                            float* __restrict__ saved, float* __restrict__ pqr, float* __restrict__ d_bn_w, float* __restrict__ d_bn_b,
+                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b) {
+  const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1, cg = c / G;
+  const double hw = (double)prm.hw;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // 1. GroupNorm group sums A_g = mean_g(gamma*dz), B_g = mean_g(gamma*dz*u_hat)
+  if (prm.use_gn) {
+    const double mg = (double)cg * hw;
+    for (int i = tid; i < n * G; i += nt) {
+      const int img = i / G, grp = i - img * G;
+      const double mean_u = (double)saved[off_gn(c) + 2 * (size_t)i], r = (double)saved[off_gn(c) + 2 * (size_t)i + 1];
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < cg; ++k) {
+        const int ch = grp * cg + k;
+        const double gam = prm.gn_weight ? (double)prm.gn_weight[ch] : 1.0;
+        const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
+        const double s1 = (double)s[((size_t)img * c + ch) * 2], s2 = (double)s[((size_t)img * c + ch) * 2 + 1];
+        a += gam * s1;
+        b += gam * r * (al * s2 + (be - mean_u) * s1);
+      }
+      saved[off_ab(c, n, G) + 2 * (size_t)i] = (float)(a / mg);
+      saved[off_ab(c, n, G) + 2 * (size_t)i + 1] = (float)(b / mg);
+    }
+    __syncthreads();
+  }
+  // 2. per-channel sums over images: BatchNorm adjoint sums U1 = sum du, U2 = sum du*y_hat; parameter gradients
+  for (int ch = tid; ch < c; ch += nt) {
+    const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
+    const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
+    double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
+    for (int img = 0; img < n; ++img) {
+      const size_t i = (size_t)img * c + ch;
+      const double sy = (double)stats[2 * i], syy = (double)stats[2 * i + 1], s1 = (double)s[2 * i], s2 = (double)s[2 * i + 1];
+      double D1, D2, D3;
+      gn_adjoint_coeffs(prm, saved, img, ch, G, D1, D2, D3);
+      u1 += D1 * s1 + D2 * sy + D3 * hw;
+      u2raw += D1 * s2 + D2 * syy + D3 * sy;
+      if (prm.use_gn) {
+        const size_t gi = (size_t)img * G + ch / cg;
+        const double mean_u = (double)saved[off_gn(c) + 2 * gi], r = (double)saved[off_gn(c) + 2 * gi + 1];
+        dgw += r * (al * s2 + (be - mean_u) * s1);
+        dgb += s1;
+      }
+    }
+    const double u2 = rc * (u2raw - mu * u1);
+    saved[off_u(c, n, G) + 2 * ch] = (float)u1;
+    saved[off_u(c, n, G) + 2 * ch + 1] = (float)u2;
+    if (prm.use_bn) { if (d_bn_w) d_bn_w[ch] = (float)u2; if (d_bn_b) d_bn_b[ch] = (float)u1; }
+    if (prm.use_gn) { if (d_gn_w) d_gn_w[ch] = (float)dgw; if (d_gn_b) d_gn_b[ch] = (float)dgb; }
+  }
+  __syncthreads();
+  // 3. P, Q, R per (n, c)
+  const double m = (double)n * hw;
+  for (int i = tid; i < n * c; i += nt) {
+    const int img = i / c, ch = i - img * c;
+    double D1, D2, D3;
+    gn_adjoint_coeffs(prm, saved, img, ch, G, D1, D2, D3);
+    double P = D1, Q = D2, R = D3;
+    if (prm.use_bn) {
+      const double al = (double)saved[off_alpha(c) + 2 * ch];  // gamma * rstd
+      if (prm.bn_training) {
+        const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
+        const double u1 = (double)saved[off_u(c, n, G) + 2 * ch], u2 = (double)saved[off_u(c, n, G) + 2 * ch + 1];
+        P = al * D1;
+        Q = al * (D2 - rc * u2 / m);
+        R = al * (D3 - u1 / m + mu * rc * u2 / m);
+      } else {
+        P = al * D1; Q = al * D2; R = al * D3;
+      }
+    }
+    pqr[3 * (size_t)i] = (float)P; pqr[3 * (size_t)i + 1] = (float)Q; pqr[3 * (size_t)i + 2] = (float)R;
+  }
+}
+
+static bool vec_ok(const void* a, const void* b, const void* d, int c, int ve) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0); };
+  return c % ve == 0 && al(a) && al(b) && al(d);
+}
+
+static int check_nc(const char* name, int n, int hw, int c) {
+  DCV_REQUIRE(n > 0 && hw > 0 && c > 0, "%s: bad shape n=%d hw=%d c=%d", name, n, hw, c);
+  DCV_REQUIRE(n < 65536, "%s: n=%d exceeds grid limit", name, n);
+  return 0;
+}
+
+}  // namespace dcv
+
+extern "C" {
+
+size_t dcv_norm_saved_floats(int n, int c, int groups) {
+  const size_t G = groups > 0 ? groups : 1;
+  return 4 * (size_t)c + 4 * (size_t)n * G + 2 * (size_t)c;
+}
+
+int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(y && stats_nc, "norm_stats: null pointer");
+  if (check_nc("norm_stats", n, hw, c)) return 1;
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(stats_nc, 0, (size_t)n * c * 2 * sizeof(float), st);
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (vec_ok(y, nullptr, nullptr, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); stats_kernel<T, VE><<<grid, block, 0, st>>>((const T*)y, stats_nc, g); }
+    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); stats_kernel<T, 1><<<grid, block, 0, st>>>((const T*)y, stats_nc, g); }
+  });
+  DCV_LAUNCH_CHECK("stats_kernel");
+  return 0;
+}
+
+static int check_norm_params(const dcv_norm_params* prm, const char* name) {
+  using namespace dcv;
+  DCV_REQUIRE(prm, "%s: null params", name);
+  if (check_nc(name, prm->n, prm->hw, prm->c)) return 1;
+  DCV_REQUIRE(!prm->use_gn || (prm->gn_groups > 0 && prm->c % prm->gn_groups == 0), "%s: num_channels=%d not divisible by num_groups=%d", name, prm->c, prm->gn_groups);
+  DCV_REQUIRE(!prm->use_bn || prm->bn_training || (prm->bn_running_mean && prm->bn_running_var), "%s: eval-mode BatchNorm needs running statistics", name);
+  return 0;
+}
+
+int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, float* ab_nc, float* saved, void* stream) {
+  using namespace dcv;
+  if (check_norm_params(prm, "norm_fwd_finalize")) return 1;
+  DCV_REQUIRE(stats_nc && ab_nc && saved, "norm_fwd_finalize: null pointer");
+  fwd_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, ab_nc, saved);
+  DCV_LAUNCH_CHECK("fwd_finalize_kernel");
+  return 0;
+}
+
+int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(y && ab_nc && z, "norm_apply_fwd: null pointer");
+  if (check_nc("norm_apply_fwd", n, hw, c)) return 1;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (vec_ok(y, z, nullptr, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); apply_fwd_kernel<T, VE><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g); }
+    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); apply_fwd_kernel<T, 1><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g); }
+  });
+  DCV_LAUNCH_CHECK("apply_fwd_kernel");
+  return 0;
+}
+
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dz && y && s_nc, "norm_bwd_reduce: null pointer");
+  if (check_nc("norm_bwd_reduce", n, hw, c)) return 1;
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(s_nc, 0, (size_t)n * c * 2 * sizeof(float), st);
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (vec_ok(dz, y, nullptr, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); bwd_reduce_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
+    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); bwd_reduce_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
+  });
+  DCV_LAUNCH_CHECK("bwd_reduce_kernel");
+  return 0;
+}
+
+int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
+                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream) {
+  using namespace dcv;
+  if (check_norm_params(prm, "norm_bwd_finalize")) return 1;
+  DCV_REQUIRE(stats_nc && s_nc && saved && pqr_nc, "norm_bwd_finalize: null pointer");
+  bwd_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias);
+  DCV_LAUNCH_CHECK("bwd_finalize_kernel");
+  return 0;
+}
+
+int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
+                           int n, int hw, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dz && y && dy, "act_norm_bwd_apply: null pointer");
+  if (check_nc("act_norm_bwd_apply", n, hw, c)) return 1;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (vec_ok(dz, y, dy, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); bwd_apply_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, act, slope, g); }
+    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); bwd_apply_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, act, slope, g); }
+  });
+  DCV_LAUNCH_CHECK("bwd_apply_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/*
+ * deepcv_b200.h — C ABI of the B200-native DeepcvModule conv / BatchNorm / augment hot path.
+ *
+ * One shared library (deepcv_b200/libdeepcv_b200.so), plain pointers and sizes only: every pointer below is a DEVICE
+ * pointer unless its name ends in `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default
+ * stream). No call allocates, synchronises or copies to the host: outputs are caller-allocated (the Python host side
+ * hands out torch caching-allocator memory), so every entry point is CUDA-graph capturable.
+ *
+ * Return value: 0 on success, non-zero on failure; `dcv_last_error()` then returns a thread-local message. There is no
+ * CPU implementation behind any entry point: a missing / non-sm_100 GPU is an error, not a fallback.
+ *
+ * Activation tensors are NHWC ("channels last"), `dtype` = DCV_F32 or DCV_BF16. Convolution weights are
+ * [K][R][S][C] (out-channel, kernel-row, kernel-col, in-channel), i.e. the memory of a torch OIHW tensor held in
+ * channels_last format. Each entry point cites the reference call site it stands in for (paths relative to
+ * /root/reference/src/deepcv/).
+ */
+#ifndef DEEPCV_B200_H_
+#define DEEPCV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCV_ABI_VERSION 1
+
+enum dcv_dtype { DCV_F32 = 0, DCV_BF16 = 1 };
+enum dcv_act { DCV_ACT_NONE = 0, DCV_ACT_RELU = 1, DCV_ACT_LEAKY_RELU = 2, DCV_ACT_SIGMOID = 3 };
+enum dcv_conv_algo { DCV_ALGO_AUTO = 0, DCV_ALGO_DIRECT = 1, DCV_ALGO_TCGEN05 = 2 };
+
+/* Geometry of one 2-D convolution: x[n][h][w][c] (*) w[k][r][s][c] -> y[n][p][q][k]. */
+typedef struct dcv_conv_shape {
+  int32_t n, h, w, c;
+  int32_t k, r, s;
+  int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int32_t p, q;
+} dcv_conv_shape;
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+int dcv_abi_version(void);
+const char* dcv_last_error(void);
+/* 0 iff the current CUDA device exists and is compute capability 10.x (B200). */
+int dcv_device_check(void);
+/* Number of kernel launches issued through this library since load (for bench.py's `gpu_launches`). */
+uint64_t dcv_launch_count(void);
+
+/* ---- preprocess / augmentation ---------------------------------------------------------------------------------
+ * Replaces torchvision ToTensor + Normalize applied per sample in PreprocessedDataset.__getitem__
+ * (meta/data/preprocess.py:44-57, recipe conf/base/parameters.yml:197-210) and the flip / crop the augmentation recipe
+ * names (meta/data/augmentation.py:39-44, parameters.yml:152,157): crop (zero pad `pad`, offsets crop_yx[n] = {top,left})
+ * -> horizontal flip (flip[n] != 0) on the uint8 image, then (u8/255 - mean[c]) / std[c] in fp32.
+ * src: uint8 [n][h][w][c]; dst: [n][out_h][out_w][c_out] (NHWC, channels >= c are written as 0) or [n][c][out_h][out_w]
+ * when `nchw_out` != 0 (then c_out must equal c). flip / crop_yx may be NULL (no flip / centred crop at (pad,pad)). */
+int dcv_preprocess_u8(const uint8_t* src, void* dst, int n, int h, int w, int c, int out_h, int out_w, int pad,
+                      const float* mean, const float* std, const uint8_t* flip, const int32_t* crop_yx,
+                      int out_dtype, int c_out, int nchw_out, void* stream);
+
+/* ---- layout / dtype --------------------------------------------------------------------------------------------- */
+/* [n][c][h][w] -> [n][h][w][c] and back, converting dtype on the way (torch.nn.Flatten of parameters.yml:87 is the
+ * NHWC->NCHW direction with h*w*c flattened). */
+int dcv_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int n, int c, int h, int w, void* stream);
+int dcv_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int n, int c, int h, int w, void* stream);
+int dcv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t count, void* stream);
+/* fp32 [K][R][S][C] weights -> `dst_dtype` copy; with `transpose_flip` != 0 writes [C][R-1-r][S-1-s][K] (the operand of
+ * the data-gradient convolution). */
+int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, int r, int s, int c, int transpose_flip, void* stream);
+
+/* ---- convolution (torch.nn.Conv2d built at meta/submodule_creators.py:251, run at meta/nn.py:553) ---------------- */
+/* y = act(conv(x, w) + bias); if stats_nc != NULL also accumulates per-(image, channel) sum(y) and sum(y*y) of the
+ * values written to y into stats_nc[n][k][2] (fp32, caller zeroes it). bias may be NULL. */
+int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,
+                   int act, float slope, int dtype, int algo, void* stream);
+/* dx[n][h][w][c] = sum_{k,r,s} dy[n][p][q][k] * w[k][r][s][c]; `w` as in fwd, `wt` the transpose_flip packing (may be
+ * NULL for the direct algorithm). */
+int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w, const void* wt, void* dx, int dtype, int algo, void* stream);
+/* dw[k][r][s][c] (fp32) = sum_{n,p,q} dy[n][p][q][k] * x[n][..][..][c]. dw is overwritten. `workspace` (fp32, at least
+ * dcv_conv2d_wgrad_workspace(shape) bytes, may be NULL when that is 0) is scratch for split accumulation. */
+size_t dcv_conv2d_wgrad_workspace(const dcv_conv_shape* shape, int dtype, int algo);
+int dcv_conv2d_wgrad(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, void* workspace, int dtype, int algo, void* stream);
+
+/* ---- normalisation (BatchNorm2d / GroupNorm after the activation: meta/nn.py:448-516,553; parameters.yml:10,82) ---
+ * Any {BatchNorm, GroupNorm} stack applied to y collapses to one affine per (image, channel): z = A[n][c]*y + B[n][c],
+ * with A, B closed-form in sum(y), sum(y*y) per (image, channel). */
+typedef struct dcv_norm_params {
+  int32_t n, c, hw;
+  int32_t use_bn, bn_training;       /* bn_training: batch statistics (and running-stat update); else running stats */
+  float bn_eps, bn_momentum;         /* momentum < 0: cumulative moving average using num_batches_tracked */
+  const float* bn_weight; const float* bn_bias;      /* [c] or NULL (affine=False) */
+  float* bn_running_mean; float* bn_running_var;     /* [c] or NULL (track_running_stats=False) */
+  int64_t* bn_num_batches_tracked;                   /* device scalar or NULL */
+  int32_t use_gn, gn_groups;
+  float gn_eps;
+  const float* gn_weight; const float* gn_bias;      /* [c] or NULL */
+} dcv_norm_params;
+
+/* sum(y), sum(y*y) per (image, channel) -> stats_nc[n][c][2] (overwritten). For tensors whose producer did not fuse it. */
+int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dtype, void* stream);
+/* stats_nc -> ab_nc[n][c][2] (A, B) and `saved` (fp32, dcv_norm_saved_floats(n,c,groups) floats: BN mean/rstd [c][2],
+ * BN alpha/beta [c][2], GN mean/rstd [n][groups][2]); updates the running statistics when bn_training. */
+size_t dcv_norm_saved_floats(int n, int c, int groups);
+int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, float* ab_nc, float* saved, void* stream);
+/* z = A*y + B. */
+int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw, int c, int dtype, void* stream);
+/* s_nc[n][c][2] = { sum(dz), sum(dz*y) } (overwritten). */
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream);
+/* -> pqr_nc[n][c][3] with dy_pre_activation = P*dz + Q*y + R, plus parameter gradients (any may be NULL; overwritten).
+ * `saved` is the forward's buffer; its trailing scratch region is written. */
+int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
+                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream);
+/* dy = act'(y) * (P*dz + Q*y + R) (pqr_nc == NULL: P=1,Q=R=0); if dbias_c != NULL accumulates sum over (n,hw) of dy into
+ * dbias_c[c] (fp32, caller zeroes it). `y` is the activation OUTPUT (ReLU / LeakyReLU / Sigmoid / none are recoverable
+ * from it). */
+int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
+                           int n, int hw, int c, int dtype, void* stream);
+
+/* ---- pooling / links (meta/submodule_creators.py:163-176, 272-332; meta/nn.py:416, 665-676) --------------------- */
+/* AvgPool2d(kernel, stride), no padding, floor output size. */
+int dcv_avgpool2d_fwd(const void* x, void* y, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int dtype, void* stream);
+int dcv_avgpool2d_bwd(const void* dy, void* dx, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int dtype, void* stream);
+/* out = alpha*a + beta*b (b may be NULL), elementwise over `count` values: residual sum / mean links. */
+int dcv_axpby(const void* a, const void* b, void* out, float alpha, float beta, size_t count, int dtype, void* stream);
+/* dst[pix][c_off : c_off+c_src] = src[pix][:] (concat = write into a channel slice) and the reverse slice read. */
+int dcv_copy_channels_in(const void* src, void* dst, size_t pixels, int c_src, int c_dst, int c_off, int dtype, void* stream);
+int dcv_copy_channels_out(const void* src, void* dst, size_t pixels, int c_src, int c_off, int c_dst, int dtype, void* stream);
+/* F.interpolate(mode='bilinear', align_corners) forward, and its adjoint accumulated into fp32 dx (caller zeroes). */
+int dcv_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);
+int dcv_bilinear_bwd(const void* dy, float* dx_f32, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);
+
+/* ---- fully connected head (torch.nn.Linear built at meta/submodule_creators.py:268-269) -------------------------- */
+/* y[m][n] = act(sum_k x[m][k]*w[n][k] + bias[n]); w, bias fp32. */
+int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, int m, int n, int k, int act, float slope,
+                   int x_dtype, int y_dtype, void* stream);
+/* dpre = act'(y)*dy; dx = dpre @ w (x_dtype, may be NULL); dw = dpre^T @ x, db = sum_m dpre (fp32, overwritten).
+ * dpre_ws: fp32 [m][n] scratch. */
+int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy, void* dx, float* dw, float* db, float* dpre_ws,
+                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, void* stream);
+
+/* ---- loss / optimiser (classification/image.py:70-71) ------------------------------------------------------------ */
+/* CrossEntropyLoss(reduction='mean') over logits[m][n] (fp32) and int64 targets: loss[0] and dlogits = (softmax - onehot)/m. */
+int dcv_softmax_ce(const float* logits, const int64_t* target, float* loss, float* dlogits, int m, int n, void* stream);
+/* AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, amsgrad=False). `step_dev` is a device int32 holding the
+ * 1-based step number (advance it with dcv_counter_add before the call: graph-replay safe); grads are multiplied by
+ * grad_scale first (1/world_size after a sum all-reduce). lr is read from the device scalar `lr_dev`. */
+int dcv_counter_add(int32_t* counter_dev, int32_t delta, void* stream);
+int dcv_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, const float* lr_dev,
+                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, const int32_t* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPCV_B200_H_ */
