@@ -62,6 +62,7 @@ SYMBOLS = {
     'dcv_linear_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
     'dcv_linear_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
     'dcv_softmax_ce': (c_int, [P, P, P, P, c_int, c_int, P]),
+    'dcv_scale_by_device_scalar': (c_int, [P, P, P, c_size_t, P]),
     'dcv_counter_add': (c_int, [P, c_int32, P]),
     'dcv_adamw_flat': (c_int, [P, P, P, P, c_size_t, P, c_float, c_float, c_float, c_float, c_float, P, P]),
 }

@@ -40,7 +40,7 @@ def build(verbose: bool = False) -> Path:
         objs = list(pool.map(_compile, sources))
     newest = max(o.stat().st_mtime for o in objs)
     if not OUT.exists() or OUT.stat().st_mtime < newest:
-        subprocess.run([NVCC, '-shared', '-o', str(OUT), *map(str, objs), '-cudart', 'static'], check=True)
+        subprocess.run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', str(OUT), *map(str, objs), '-cudart', 'static'], check=True)
     if verbose:
         print(f'built {OUT} from {len(sources)} sources')
     return OUT

@@ -25,6 +25,11 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_
   if (lane == 0) atomicAdd(loss, (lse - row[t]) * inv_m);
 }
 
+__global__ void scale_dev_kernel(const float* __restrict__ src, const float* __restrict__ scale_dev, float* __restrict__ dst, size_t count) {
+  const float sc = *scale_dev;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * sc;
+}
+
 __global__ void counter_add_kernel(int32_t* counter, int32_t delta) { *counter += delta; }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t count,
@@ -56,6 +61,15 @@ int dcv_softmax_ce(const float* logits, const int64_t* target, float* loss, floa
   cudaMemsetAsync(loss, 0, sizeof(float), st);
   softmax_ce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(logits, target, loss, dlogits, m, n);
   DCV_LAUNCH_CHECK("softmax_ce_kernel");
+  return 0;
+}
+
+int dcv_scale_by_device_scalar(const float* src, const float* scale_dev, float* dst, size_t count, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(src && scale_dev && dst, "scale_by_device_scalar: null pointer");
+  if (count == 0) return 0;
+  scale_dev_kernel<<<grid_for(count, 256), 256, 0, as_stream(stream)>>>(src, scale_dev, dst, count);
+  DCV_LAUNCH_CHECK("scale_dev_kernel");
   return 0;
 }
 

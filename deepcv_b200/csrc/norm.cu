@@ -456,6 +456,7 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
   DCV_REQUIRE(dz && y && dy, "act_norm_bwd_apply: null pointer");
   if (check_nc("act_norm_bwd_apply", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
+  if (dbias_c) cudaMemsetAsync(dbias_c, 0, (size_t)c * sizeof(float), st);
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);

@@ -238,6 +238,7 @@ int dcv_bilinear_bwd(const void* dy, float* dx_f32, int n, int h, int w, int c, 
   using namespace dcv;
   DCV_REQUIRE(dy && dx_f32 && n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "bilinear_bwd: bad arguments");
   const float sh = bilinear_scale(h, oh, align_corners), sw = bilinear_scale(w, ow, align_corners);
+  cudaMemsetAsync(dx_f32, 0, (size_t)n * h * w * c * sizeof(float), as_stream(stream));
   DCV_DISPATCH_DTYPE(dtype, T, (bilinear_bwd_kernel<T><<<grid_for((size_t)n * oh * ow * c, 256), 256, 0, as_stream(stream)>>>((const T*)dy, dx_f32, n, h, w, c, oh, ow, align_corners, sh, sw)));
   DCV_LAUNCH_CHECK("bilinear_bwd_kernel");
   return 0;

@@ -1,0 +1,589 @@
+""" Torch-facing operators of the hot path: `torch.autograd.Function`s whose forward and backward are calls into the C ABI
+(`include/deepcv_b200.h`, bound in `deepcv_b200/_lib.py`). PyTorch is used here for device memory (caching allocator),
+the current stream and the autograd graph only; every arithmetic pass is one of the library's CUDA kernels.
+
+Conventions
+  * Image tensors are logically `N x C x H x W` (what the reference's modules see) and physically NHWC
+    (`memory_format=torch.channels_last`); `empty_nhwc` / `as_nhwc` create / obtain that layout.
+  * Activation dtype = dtype of the incoming tensor (float32: parity mode, bfloat16: throughput mode). Parameters, statistics,
+    parameter gradients and losses are float32.
+  * No CPU implementation exists: a non-CUDA tensor raises `RuntimeError` (tensors on the `meta` device are handled by the
+    modules in `deepcv_b200.meta.nn`, for shape inference only).
+"""
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, DCV_BF16, DCV_F32, ConvShape, NormParams, check, lib)
+
+__all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
+           'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count']
+
+_DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f'deepcv_b200: unsupported dtype {t.dtype} (float32 and bfloat16 only)') from None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(f'deepcv_b200: got a tensor on "{t.device}"; this path runs on CUDA (sm_100a) only and has no CPU fallback')
+
+
+def launch_count() -> int:
+    """ Number of kernels launched through the library since it was loaded. """
+    return int(lib.dcv_launch_count())
+
+
+def empty_nhwc(n: int, c: int, h: int, w: int, dtype: torch.dtype, device) -> torch.Tensor:
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def is_nhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+class _ToChannelsLast(torch.autograd.Function):
+    """ contiguous NCHW (any supported dtype) -> NHWC `dtype`, through the tiled transpose kernel. """
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, dtype: torch.dtype):
+        n, c, h, w = x.shape
+        out = empty_nhwc(n, c, h, w, dtype, x.device)
+        check(lib.dcv_nchw_to_nhwc(_ptr(x), _dt(x), _ptr(out), _dt(out), n, c, h, w, _stream()), 'nchw_to_nhwc')
+        ctx.src_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        g = as_nhwc(g)
+        n, c, h, w = g.shape
+        dx = torch.empty((n, c, h, w), dtype=ctx.src_dtype, device=g.device)
+        check(lib.dcv_nhwc_to_nchw(_ptr(g), _dt(g), _ptr(dx), _dt(dx), n, c, h, w, _stream()), 'nhwc_to_nchw')
+        return dx, None
+
+
+class _Cast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, dtype: torch.dtype):
+        out = torch.empty_like(x, dtype=dtype)  # preserves the (dense) strides
+        check(lib.dcv_cast(_ptr(x), _dt(x), _ptr(out), _dt(out), x.numel(), _stream()), 'cast')
+        ctx.src_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        return _cast_raw(_dense_like(g), ctx.src_dtype), None
+
+
+def _dense_like(t: torch.Tensor) -> torch.Tensor:
+    """ A tensor whose memory is dense in either NHWC or plain contiguous order (autograd may hand us expanded gradients). """
+    if t.is_contiguous() or (t.dim() == 4 and is_nhwc(t)):
+        return t
+    return t.contiguous()
+
+
+def _cast_raw(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if x.dtype == dtype:
+        return x
+    out = torch.empty_like(x, dtype=dtype)
+    check(lib.dcv_cast(_ptr(x), _dt(x), _ptr(out), _dt(out), x.numel(), _stream()), 'cast')
+    return out
+
+
+def as_nhwc(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """ `x` as a physically-NHWC tensor of `dtype` (default: unchanged), differentiable. """
+    _require_cuda(x)
+    if x.dim() != 4:
+        raise ValueError(f'deepcv_b200: expected an N x C x H x W tensor, got shape {tuple(x.shape)}')
+    dtype = x.dtype if dtype is None else dtype
+    if is_nhwc(x):
+        return x if x.dtype == dtype else _Cast.apply(x, dtype)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return _ToChannelsLast.apply(x, dtype)
+
+
+def activation_code(act_fn) -> Tuple[int, float]:
+    """ Activation module / type / None -> (DCV_ACT_*, negative slope). Only what the kernels fuse is accepted. """
+    if act_fn is None or act_fn is torch.nn.Identity or isinstance(act_fn, torch.nn.Identity):
+        return ACT_NONE, 0.
+    inst = act_fn() if isinstance(act_fn, type) else act_fn
+    if isinstance(inst, torch.nn.ReLU):
+        return ACT_RELU, 0.
+    if isinstance(inst, torch.nn.LeakyReLU):
+        return ACT_LEAKY_RELU, float(inst.negative_slope)
+    if isinstance(inst, torch.nn.Sigmoid):
+        return ACT_SIGMOID, 0.
+    raise NotImplementedError(f'deepcv_b200: activation "{type(inst).__name__}" is not fused by the sm_100a kernels (ReLU, LeakyReLU, Sigmoid, Identity/None are); '
+                              'there is no PyTorch fallback on this path')
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Convolution block: conv (+bias) -> activation -> [BatchNorm] -> [GroupNorm / InstanceNorm]   (reference: meta/nn.py:553)
+
+class NormConfig:
+    """ What `dcv_norm_params` needs besides tensors: which normalisations follow the activation and their scalars. """
+    __slots__ = ('use_bn', 'bn_eps', 'bn_momentum', 'use_gn', 'gn_groups', 'gn_eps')
+
+    def __init__(self, use_bn=False, bn_eps=1e-5, bn_momentum=0.1, use_gn=False, gn_groups=1, gn_eps=1e-5):
+        self.use_bn, self.bn_eps, self.bn_momentum = bool(use_bn), float(bn_eps), (-1. if bn_momentum is None else float(bn_momentum))
+        self.use_gn, self.gn_groups, self.gn_eps = bool(use_gn), int(gn_groups), float(gn_eps)
+
+    @property
+    def any(self) -> bool:
+        return self.use_bn or self.use_gn
+
+
+def _conv_shape(x: torch.Tensor, weight: torch.Tensor, stride, padding, dilation) -> ConvShape:
+    n, c, h, w = x.shape
+    k, cw, r, s = weight.shape
+    if cw != c:
+        raise RuntimeError(f'deepcv_b200: convolution expects {cw} input channels, got {c} (grouped convolutions are not on this path)')
+    p = (h + 2 * padding[0] - dilation[0] * (r - 1) - 1) // stride[0] + 1
+    q = (w + 2 * padding[1] - dilation[1] * (s - 1) - 1) // stride[1] + 1
+    if p <= 0 or q <= 0:
+        raise RuntimeError(f'deepcv_b200: convolution output would be empty for input {tuple(x.shape)} and kernel {r}x{s}')
+    return ConvShape(n, h, w, c, k, r, s, stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], p, q)
+
+
+def _weight_operand(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """ fp32 OIHW parameter -> [K][R][S][C] tensor of the activation dtype (zero-copy when it already is one). """
+    k, c, r, s = weight.shape
+    if weight.permute(0, 2, 3, 1).is_contiguous():
+        if weight.dtype == dtype:
+            return weight
+        out = torch.empty((k, r, s, c), dtype=dtype, device=weight.device).permute(0, 3, 1, 2)
+        check(lib.dcv_cast(_ptr(weight), _dt(weight), _ptr(out), _dt(out), weight.numel(), _stream()), 'cast(weight)')
+        return out
+    w = weight if weight.is_contiguous() else weight.contiguous()
+    out = torch.empty((k, r, s, c), dtype=dtype, device=weight.device).permute(0, 3, 1, 2)
+    check(lib.dcv_nchw_to_nhwc(_ptr(w), _dt(w), _ptr(out), _dt(out), k, c, r, s, _stream()), 'nchw_to_nhwc(weight)')
+    return out
+
+
+def _norm_params(cfg: NormConfig, n: int, c: int, hw: int, training: bool, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b) -> NormParams:
+    bn_training = bool(training or rm is None or rv is None)  # track_running_stats=False => always batch statistics
+    return NormParams(n, c, hw, int(cfg.use_bn), int(bn_training), cfg.bn_eps, cfg.bn_momentum,
+                      _ptr(bn_w), _ptr(bn_b), _ptr(rm), _ptr(rv), _ptr(nbt),
+                      int(cfg.use_gn), cfg.gn_groups, cfg.gn_eps, _ptr(gn_w), _ptr(gn_b))
+
+
+class _ConvBlock(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out):
+        _require_cuda(x, weight)
+        shape = _conv_shape(x, weight, stride, padding, dilation)
+        n, k, p, q = shape.n, shape.k, shape.p, shape.q
+        dev, st = x.device, _stream()
+        dt = _dt(x)
+        w_op = _weight_operand(weight, x.dtype)
+        y = empty_nhwc(n, k, p, q, x.dtype, dev)
+        stats = torch.empty((n, k, 2), dtype=torch.float32, device=dev) if cfg.any else None
+        check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd')
+        saved = None
+        out = y
+        if cfg.any:
+            groups = cfg.gn_groups if cfg.use_gn else 1
+            saved = torch.empty((int(lib.dcv_norm_saved_floats(n, k, groups)),), dtype=torch.float32, device=dev)
+            ab = torch.empty((n, k, 2), dtype=torch.float32, device=dev)
+            prm = _norm_params(cfg, n, k, p * q, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
+            check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(ab), _ptr(saved), st), 'norm_fwd_finalize')
+            out = empty_nhwc(n, k, p, q, x.dtype, dev)
+            check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, p * q, k, dt, st), 'norm_apply_fwd')
+        ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
+        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv = ctx.saved_tensors
+        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape = ctx.cfg
+        n, k, p, q = shape.n, shape.k, shape.p, shape.q
+        dev, st, dt = y.device, _stream(), _dt(y)
+        dz = as_nhwc(dz.detach(), y.dtype)
+        f32 = dict(dtype=torch.float32, device=dev)
+        targets = grad_out or {}
+        pqr = d_bn_w = d_bn_b = d_gn_w = d_gn_b = None
+        if cfg.any:
+            s_nc = torch.empty((n, k, 2), **f32)
+            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, st), 'norm_bwd_reduce')
+            pqr = torch.empty((n, k, 3), **f32)
+            if cfg.use_bn and bn_w is not None:
+                d_bn_w, d_bn_b = targets.get('bn_w', None), targets.get('bn_b', None)
+                d_bn_w = torch.empty((k,), **f32) if d_bn_w is None else d_bn_w
+                d_bn_b = torch.empty((k,), **f32) if d_bn_b is None else d_bn_b
+            if cfg.use_gn and gn_w is not None:
+                d_gn_w, d_gn_b = targets.get('gn_w', None), targets.get('gn_b', None)
+                d_gn_w = torch.empty((k,), **f32) if d_gn_w is None else d_gn_w
+                d_gn_b = torch.empty((k,), **f32) if d_gn_b is None else d_gn_b
+            prm = _norm_params(cfg, n, k, p * q, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
+            check(lib.dcv_norm_bwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(s_nc), _ptr(saved), _ptr(pqr),
+                                            _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'norm_bwd_finalize')
+        need_dy_pass = cfg.any or act != ACT_NONE or has_bias
+        dy = dz
+        dbias = None
+        if need_dy_pass:
+            dy = empty_nhwc(n, k, p, q, y.dtype, dev)
+            if has_bias:
+                dbias = targets.get('bias', None)
+                dbias = torch.empty((k,), **f32) if dbias is None else dbias
+            check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, st), 'act_norm_bwd_apply')
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = targets.get('weight', None)
+            if dw is None:
+                dw = torch.empty((k, shape.r, shape.s, shape.c), **f32).permute(0, 3, 1, 2)
+            ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+            check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, st), 'conv2d_wgrad')
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_nhwc(n, shape.c, shape.h, shape.w, y.dtype, dev)
+            check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), _ptr(dy), _ptr(w_op), None, _ptr(dx), dt, algo, st), 'conv2d_dgrad')
+
+        def ret(name, g):  # gradients written straight into a caller-provided bucket slice are not handed to autograd again
+            return None if (g is None or name in targets) else g
+        return (dx, ret('weight', dw), ret('bias', dbias) if has_bias else None, ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b),
+                None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def conv_block(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: Sequence[int], padding: Sequence[int], dilation: Sequence[int],
+               act: int = ACT_NONE, slope: float = 0., norm: Optional[NormConfig] = None, training: bool = True,
+               bn_weight=None, bn_bias=None, running_mean=None, running_var=None, num_batches_tracked=None, gn_weight=None, gn_bias=None,
+               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None) -> torch.Tensor:
+    """ act(conv2d(x, weight) + bias) followed by the configured BatchNorm / GroupNorm, as one autograd node.
+    `grad_out` optionally maps 'weight' / 'bias' / 'bn_w' / 'bn_b' / 'gn_w' / 'gn_b' to preallocated fp32 tensors (slices of a
+    flat gradient bucket) that backward fills in place instead of returning new tensors. """
+    x = as_nhwc(x)
+    norm = norm if norm is not None else NormConfig()
+    return _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
+                            tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Average pooling (reference: meta/submodule_creators.py:163-176 -> torch.nn.AvgPool2d)
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, stride):
+        _require_cuda(x)
+        n, c, h, w = x.shape
+        if h < kernel[0] or w < kernel[1]:
+            raise RuntimeError(f'deepcv_b200: average pooling kernel {kernel} larger than input {h}x{w}')
+        p, q = (h - kernel[0]) // stride[0] + 1, (w - kernel[1]) // stride[1] + 1
+        y = empty_nhwc(n, c, p, q, x.dtype, x.device)
+        check(lib.dcv_avgpool2d_fwd(_ptr(x), _ptr(y), n, h, w, c, kernel[0], kernel[1], stride[0], stride[1], _dt(x), _stream()), 'avgpool2d_fwd')
+        ctx.geom = (n, c, h, w, kernel, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, kernel, stride = ctx.geom
+        dy = as_nhwc(dy.detach())
+        dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
+        check(lib.dcv_avgpool2d_bwd(_ptr(dy), _ptr(dx), n, h, w, c, kernel[0], kernel[1], stride[0], stride[1], _dt(dy), _stream()), 'avgpool2d_bwd')
+        return dx, None, None
+
+
+def avg_pool2d(x: torch.Tensor, kernel_size, stride=None) -> torch.Tensor:
+    kernel = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+    stride = kernel if stride is None else ((stride, stride) if isinstance(stride, int) else tuple(stride))
+    return _AvgPool.apply(as_nhwc(x), kernel, stride)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Links (reference: meta/submodule_creators.py:43-65, 272-332; meta/nn.py:665-676)
+
+class _Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow, align_corners):
+        _require_cuda(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, oh, ow, x.dtype, x.device)
+        check(lib.dcv_bilinear_fwd(_ptr(x), _ptr(y), n, h, w, c, oh, ow, int(align_corners), _dt(x), _stream()), 'bilinear_fwd')
+        ctx.geom = (n, c, h, w, oh, ow, int(align_corners))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, oh, ow, align = ctx.geom
+        dy = as_nhwc(dy.detach())
+        dx32 = empty_nhwc(n, c, h, w, torch.float32, dy.device)
+        check(lib.dcv_bilinear_bwd(_ptr(dy), _ptr(dx32), n, h, w, c, oh, ow, align, _dt(dy), _stream()), 'bilinear_bwd')
+        return _cast_raw(dx32, dy.dtype), None, None, None
+
+
+def bilinear_resize(x: torch.Tensor, size: Sequence[int], align_corners: bool = False) -> torch.Tensor:
+    """ `F.interpolate(x, size, mode='bilinear', align_corners)`. An exact 2x reduction with align_corners=False samples at
+    2d+0.5, i.e. it *is* the 2x2 average: that case runs the vectorised pooling kernels. """
+    x = as_nhwc(x)
+    oh, ow = int(size[0]), int(size[1])
+    if not align_corners and x.shape[2] == 2 * oh and x.shape[3] == 2 * ow:
+        return _AvgPool.apply(x, (2, 2), (2, 2))
+    return _Bilinear.apply(x, oh, ow, bool(align_corners))
+
+
+class _Axpby(torch.autograd.Function):
+    """ out = alpha * (a + b) : residual sum (alpha=1) and the two-operand mean (alpha=0.5). """
+
+    @staticmethod
+    def forward(ctx, a, b, alpha):
+        _require_cuda(a, b)
+        out = torch.empty_like(a)
+        check(lib.dcv_axpby(_ptr(a), _ptr(b), _ptr(out), alpha, alpha, a.numel(), _dt(a), _stream()), 'axpby')
+        ctx.alpha = alpha
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.alpha == 1.:
+            return g, g, None
+        g = _dense_like(g.detach())
+        ga = torch.empty_like(g)
+        check(lib.dcv_axpby(_ptr(g), None, _ptr(ga), ctx.alpha, 0., g.numel(), _dt(g), _stream()), 'axpby')
+        return ga, ga, None
+
+
+class _Concat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *tensors):
+        _require_cuda(*tensors)
+        n, _, h, w = tensors[0].shape
+        channels = [t.shape[1] for t in tensors]
+        out = empty_nhwc(n, sum(channels), h, w, tensors[0].dtype, tensors[0].device)
+        off = 0
+        for t, c in zip(tensors, channels):
+            check(lib.dcv_copy_channels_in(_ptr(t), _ptr(out), n * h * w, c, sum(channels), off, _dt(t), _stream()), 'copy_channels_in')
+            off += c
+        ctx.channels = channels
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = as_nhwc(g.detach())
+        n, ctot, h, w = g.shape
+        grads, off = [], 0
+        for i, c in enumerate(ctx.channels):
+            if ctx.needs_input_grad[i]:
+                gi = empty_nhwc(n, c, h, w, g.dtype, g.device)
+                check(lib.dcv_copy_channels_out(_ptr(g), _ptr(gi), n * h * w, ctot, off, c, _dt(g), _stream()), 'copy_channels_out')
+                grads.append(gi)
+            else:
+                grads.append(None)
+            off += c
+        return tuple(grads)
+
+
+def link_reduce(tensors: List[torch.Tensor], reduction: str) -> torch.Tensor:
+    """ 'sum' / 'mean' (elementwise over the list) or 'concat' (channel dim, first tensor first). """
+    if len(tensors) == 1 and reduction in ('sum', 'mean', 'concat'):
+        return tensors[0]
+    dtype = tensors[0].dtype
+    tensors = [as_nhwc(t, dtype) for t in tensors]
+    if reduction == 'concat':
+        if any(t.shape[0] != tensors[0].shape[0] or t.shape[2:] != tensors[0].shape[2:] for t in tensors):
+            raise RuntimeError(f'deepcv_b200: cannot concatenate tensors of shapes {[tuple(t.shape) for t in tensors]} on the channel dim')
+        return _Concat.apply(*tensors)
+    if reduction in ('sum', 'mean'):
+        if any(t.shape != tensors[0].shape for t in tensors):
+            raise RuntimeError(f'deepcv_b200: cannot {reduction} tensors of different shapes {[tuple(t.shape) for t in tensors]}')
+        acc = tensors[0]
+        for t in tensors[1:]:
+            acc = _Axpby.apply(acc, t, 1.)
+        if reduction == 'mean':
+            acc = _Scale.apply(acc, 1. / len(tensors))
+        return acc
+    raise ValueError(f'Error: Invalid "{reduction}" reduction function name. Valid reduction functions are "mean", "sum", "concat" and "none".')
+
+
+class _Scale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, alpha):
+        out = torch.empty_like(a)
+        check(lib.dcv_axpby(_ptr(a), None, _ptr(out), alpha, 0., a.numel(), _dt(a), _stream()), 'axpby')
+        ctx.alpha = alpha
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _dense_like(g.detach())
+        out = torch.empty_like(g)
+        check(lib.dcv_axpby(_ptr(g), None, _ptr(out), ctx.alpha, 0., g.numel(), _dt(g), _stream()), 'axpby')
+        return out, None
+
+
+class _Fork(torch.autograd.Function):
+    """ Two aliases of one tensor whose gradients are summed by `dcv_axpby` (a tensor kept for a later link has two consumers;
+    without this node autograd would add the two gradients with an ATen kernel). """
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None or g2 is None:
+            return g1 if g2 is None else g2
+        g1, g2 = _dense_like(g1.detach()), _dense_like(g2.detach())
+        if g1.stride() != g2.stride() or g1.dtype != g2.dtype:
+            g2 = as_nhwc(g2, g1.dtype) if g1.dim() == 4 else _cast_raw(g2.contiguous(), g1.dtype)
+            g1 = as_nhwc(g1) if g1.dim() == 4 else g1.contiguous()
+        out = torch.empty_like(g1)
+        check(lib.dcv_axpby(_ptr(g1), _ptr(g2), _ptr(out), 1., 1., g1.numel(), _dt(g1), _stream()), 'axpby')
+        return out
+
+
+def fork(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    if not (x.is_cuda and x.requires_grad and torch.is_grad_enabled()):
+        return x, x
+    return _Fork.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Flatten + fully connected head (reference: conf/base/parameters.yml:87-88; meta/submodule_creators.py:268-269)
+
+class _FlattenNCHW(torch.autograd.Function):
+    """ torch.nn.Flatten on the logical N x C x H x W tensor: (C, H, W)-major features from NHWC memory. """
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        n, c, h, w = x.shape
+        out = torch.empty((n, c * h * w), dtype=x.dtype, device=x.device)
+        check(lib.dcv_nhwc_to_nchw(_ptr(x), _dt(x), _ptr(out), _dt(out), n, c, h, w, _stream()), 'nhwc_to_nchw')
+        ctx.shape = (n, c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w = ctx.shape
+        g = g.detach()
+        g = g if g.is_contiguous() else g.contiguous()
+        dx = empty_nhwc(n, c, h, w, g.dtype, g.device)
+        check(lib.dcv_nchw_to_nhwc(_ptr(g), _dt(g), _ptr(dx), _dt(dx), n, c, h, w, _stream()), 'nchw_to_nhwc')
+        return dx
+
+
+def flatten_nchw(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() != 4:
+        return x.flatten(1)  # a view: nothing to compute
+    if x.shape[2] == 1 and x.shape[3] == 1 and is_nhwc(x):
+        return x.reshape(x.shape[0], x.shape[1])  # NHWC with H=W=1 is already (N, C): a view
+    return _FlattenNCHW.apply(as_nhwc(x))
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, slope, grad_out):
+        _require_cuda(x, weight)
+        m, k = x.shape
+        n = weight.shape[0]
+        if weight.shape[1] != k:
+            raise RuntimeError(f'deepcv_b200: linear layer expects {weight.shape[1]} input features, got {k}')
+        w = weight if weight.is_contiguous() else weight.contiguous()
+        y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+        check(lib.dcv_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), m, n, k, act, slope, _dt(x), DCV_F32, _stream()), 'linear_fwd')
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (act, slope, bias is not None, grad_out)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        act, slope, has_bias, grad_out = ctx.cfg
+        targets = grad_out or {}
+        m, k = x.shape
+        n = w.shape[0]
+        dy = _cast_raw(dy.detach().contiguous(), torch.float32)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        dx = torch.empty((m, k), dtype=x.dtype, device=x.device) if ctx.needs_input_grad[0] else None
+        dw = targets.get('weight', None) if ctx.needs_input_grad[1] else None
+        if dw is None and ctx.needs_input_grad[1]:
+            dw = torch.empty((n, k), **f32)
+        db = None
+        if has_bias:
+            db = targets.get('bias', None)
+            db = torch.empty((n,), **f32) if db is None else db
+        dpre = torch.empty((m, n), **f32)
+        check(lib.dcv_linear_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dpre), m, n, k, act, slope, _dt(x), DCV_F32, _stream()), 'linear_bwd')
+        return dx, (None if 'weight' in targets else dw), (None if ('bias' in targets or not has_bias) else db), None, None, None
+
+
+def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE, slope: float = 0., grad_out: Optional[dict] = None) -> torch.Tensor:
+    """ act(x @ weight.T + bias) with fp32 output (logits / losses stay fp32 whatever the activation dtype). """
+    if x.dim() != 2:
+        x = flatten_nchw(x) if x.dim() == 4 else x.reshape(x.shape[0], -1)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return _Linear.apply(x, weight, bias, int(act), float(slope), grad_out)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Loss (reference: classification/image.py:70 — torch.nn.CrossEntropyLoss on the head's outputs)
+
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target):
+        _require_cuda(logits, target)
+        m, n = logits.shape
+        logits = _cast_raw(logits.contiguous(), torch.float32)
+        target = target.contiguous()
+        if target.dtype != torch.int64:
+            raise TypeError(f'deepcv_b200: cross entropy targets must be int64 class indices, got {target.dtype}')
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        check(lib.dcv_softmax_ce(_ptr(logits), _ptr(target), _ptr(loss), _ptr(dlogits), m, n, _stream()), 'softmax_ce')
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dlogits, = ctx.saved_tensors
+        g = _cast_raw(g.detach().contiguous(), torch.float32)
+        out = torch.empty_like(dlogits)
+        check(lib.dcv_scale_by_device_scalar(_ptr(dlogits), _ptr(g), _ptr(out), dlogits.numel(), _stream()), 'scale_by_device_scalar')
+        return out, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """ `torch.nn.CrossEntropyLoss()(logits, target)` (mean reduction, class-index targets). """
+    return _CrossEntropy.apply(logits, target)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Preprocess / augmentation (reference: meta/data/preprocess.py:44-57; conf/base/parameters.yml:197-210; meta/data/augmentation.py:39-44)
+
+def preprocess_u8(img: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, flip: Optional[torch.Tensor] = None, crop_yx: Optional[torch.Tensor] = None,
+                  pad: int = 0, out_hw: Optional[Tuple[int, int]] = None, dtype: torch.dtype = torch.float32, channels_last: bool = True,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ uint8 `N x H x W x C` (device) -> normalised float `N x C x h x w` (NHWC memory unless `channels_last=False`).
+    crop (zero padding `pad`, per-sample `crop_yx[n] = (top, left)`) -> horizontal flip (`flip[n] != 0`) -> (u8/255 - mean)/std. """
+    _require_cuda(img, mean, std, flip, crop_yx)
+    if img.dtype != torch.uint8 or img.dim() != 4 or not img.is_contiguous():
+        raise TypeError(f'deepcv_b200: preprocess_u8 expects a contiguous uint8 N x H x W x C tensor, got {img.dtype} {tuple(img.shape)}')
+    n, h, w, c = img.shape
+    oh, ow = (h, w) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    if flip is not None and (flip.dtype != torch.uint8 or flip.numel() != n):
+        raise TypeError('deepcv_b200: `flip` must be a uint8 tensor with one entry per image')
+    if crop_yx is not None and (crop_yx.dtype != torch.int32 or tuple(crop_yx.shape) != (n, 2) or not crop_yx.is_contiguous()):
+        raise TypeError('deepcv_b200: `crop_yx` must be a contiguous int32 N x 2 tensor')
+    if out is None:
+        out = empty_nhwc(n, c, oh, ow, dtype, img.device) if channels_last else torch.empty((n, c, oh, ow), dtype=dtype, device=img.device)
+    check(lib.dcv_preprocess_u8(_ptr(img), _ptr(out), n, h, w, c, oh, ow, int(pad), _ptr(mean), _ptr(std), _ptr(flip), _ptr(crop_yx),
+                                _dt(out), c, 0 if channels_last else 1, _stream()), 'preprocess_u8')
+    return out

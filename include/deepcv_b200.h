@@ -69,7 +69,7 @@ int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, i
 
 /* ---- convolution (torch.nn.Conv2d built at meta/submodule_creators.py:251, run at meta/nn.py:553) ---------------- */
 /* y = act(conv(x, w) + bias); if stats_nc != NULL also accumulates per-(image, channel) sum(y) and sum(y*y) of the
- * values written to y into stats_nc[n][k][2] (fp32, caller zeroes it). bias may be NULL. */
+ * values written to y into stats_nc[n][k][2] (fp32, overwritten). bias may be NULL. */
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,
                    int act, float slope, int dtype, int algo, void* stream);
 /* dx[n][h][w][c] = sum_{k,r,s} dy[n][p][q][k] * w[k][r][s][c]; `w` as in fwd, `wt` the transpose_flip packing (may be
@@ -110,7 +110,7 @@ int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int h
 int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
                           float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream);
 /* dy = act'(y) * (P*dz + Q*y + R) (pqr_nc == NULL: P=1,Q=R=0); if dbias_c != NULL accumulates sum over (n,hw) of dy into
- * dbias_c[c] (fp32, caller zeroes it). `y` is the activation OUTPUT (ReLU / LeakyReLU / Sigmoid / none are recoverable
+ * dbias_c[c] (fp32, overwritten). `y` is the activation OUTPUT (ReLU / LeakyReLU / Sigmoid / none are recoverable
  * from it). */
 int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
                            int n, int hw, int c, int dtype, void* stream);
@@ -124,7 +124,7 @@ int dcv_axpby(const void* a, const void* b, void* out, float alpha, float beta, 
 /* dst[pix][c_off : c_off+c_src] = src[pix][:] (concat = write into a channel slice) and the reverse slice read. */
 int dcv_copy_channels_in(const void* src, void* dst, size_t pixels, int c_src, int c_dst, int c_off, int dtype, void* stream);
 int dcv_copy_channels_out(const void* src, void* dst, size_t pixels, int c_src, int c_off, int c_dst, int dtype, void* stream);
-/* F.interpolate(mode='bilinear', align_corners) forward, and its adjoint accumulated into fp32 dx (caller zeroes). */
+/* F.interpolate(mode='bilinear', align_corners) forward, and its adjoint written to fp32 dx (overwritten). */
 int dcv_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);
 int dcv_bilinear_bwd(const void* dy, float* dx_f32, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);
 
@@ -140,6 +140,8 @@ int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy,
 /* ---- loss / optimiser (classification/image.py:70-71) ------------------------------------------------------------ */
 /* CrossEntropyLoss(reduction='mean') over logits[m][n] (fp32) and int64 targets: loss[0] and dlogits = (softmax - onehot)/m. */
 int dcv_softmax_ce(const float* logits, const int64_t* target, float* loss, float* dlogits, int m, int n, void* stream);
+/* dst[i] = src[i] * (*scale_dev): chain rule through the loss with the upstream gradient left on the device (no host sync). */
+int dcv_scale_by_device_scalar(const float* src, const float* scale_dev, float* dst, size_t count, void* stream);
 /* AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, amsgrad=False). `step_dev` is a device int32 holding the
  * 1-based step number (advance it with dcv_counter_add before the call: graph-replay safe); grads are multiplied by
  * grad_scale first (1/world_size after a sum all-reduce). lr is read from the device scalar `lr_dev`. */

@@ -1,0 +1,28 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / 'tests' / 'golden'
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200); run with `-m gpu` on the GPU box')
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope='session')
+def default_hp():
+    import copy
+    from deepcv_b200.yaml_config import find_model_spec, load_parameters
+    hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'parameters.yml'), 'image_classifier'))
+    hp['architecture'] = copy.deepcopy(hp['architecture'])
+    hp['architecture'][-1]['fully_connected']['out_features'] = 10
+    return hp

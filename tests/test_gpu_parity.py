@@ -1,0 +1,405 @@
+""" Parity of the sm_100a path against the CPU oracle / stock torch CPU ops and the committed goldens (run on the B200: `pytest -m gpu`).
+
+Tolerances (BASELINE.json north_star): crop/flip geometry and index selection bit-exact; fp32 preprocess values bit-exact (same op order);
+logits and gradients within 1e-4 relative error in fp32 and 2e-2 in bf16, measured as max|a-b| / max|b| per tensor. """
+import copy
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+FP32_TOL, BF16_TOL = 1e-4, 2e-2
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from deepcv_b200._lib import check, lib
+    check(lib.dcv_device_check(), 'device_check')
+    return torch.device('cuda', 0)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+def assert_close(a, b, tol, what=''):
+    e = rel_err(a, b)
+    assert e <= tol, f'{what}: relative error {e:.3e} > {tol:.1e}'
+
+
+# ---- preprocess -----------------------------------------------------------------------------------------------------------------
+
+def test_preprocess_bit_exact_against_torchvision(dev, golden_dir):
+    from deepcv_b200 import ops
+    gold = torch.load(golden_dir / 'torchvision_preprocess.pt')
+    for name in ('cifar', 'imagenet'):
+        g = gold[name]
+        img = g['images'].to(dev)
+        mean, std = torch.tensor(g['mean'], device=dev), torch.tensor(g['std'], device=dev)
+        for channels_last in (True, False):
+            plain = ops.preprocess_u8(img, mean, std, channels_last=channels_last)
+            assert torch.equal(plain.cpu(), g['plain']), (name, channels_last)
+            aug = ops.preprocess_u8(img, mean, std, flip=g['flip'].to(dev), crop_yx=g['crop'].to(dev), pad=g['pad'], channels_last=channels_last)
+            assert torch.equal(aug.cpu(), g['augmented']), (name, channels_last)
+        bf = ops.preprocess_u8(img, mean, std, flip=g['flip'].to(dev), crop_yx=g['crop'].to(dev), pad=g['pad'], dtype=torch.bfloat16)
+        assert torch.equal(bf.cpu(), g['augmented'].to(torch.bfloat16)), name   # round-to-nearest-even of the fp32 value
+    ramp = gold['ramp']
+    out = ops.preprocess_u8(ramp['images'].to(dev), torch.tensor([0.491, 0.482, 0.447], device=dev), torch.tensor([0.247, 0.243, 0.261], device=dev))
+    assert torch.equal(out.cpu(), ramp['plain'])
+
+
+def test_preprocess_index_selection_every_offset(dev, golden_dir):
+    """ Integer source-index map of every output pixel for all 2*9*9 (flip, top, left) at 32x32 / pad 4, against the oracle's map. """
+    from deepcv_b200 import ops
+    from oracle.deepcv_oracle import preprocess_index_map
+    rows = torch.arange(1, 33, dtype=torch.uint8).view(32, 1).expand(32, 32)
+    cols = torch.arange(1, 33, dtype=torch.uint8).view(1, 32).expand(32, 32)
+    img = torch.stack([rows, cols], dim=-1).contiguous()
+    combos = [(f, t, l) for f in (0, 1) for t in range(9) for l in range(9)]
+    batch = img[None].repeat(len(combos), 1, 1, 1).to(dev)
+    flip = torch.tensor([c[0] for c in combos], dtype=torch.uint8, device=dev)
+    crop = torch.tensor([[c[1], c[2]] for c in combos], dtype=torch.int32, device=dev)
+    one, zero = torch.ones(2, device=dev), torch.zeros(2, device=dev)
+    for dtype in (torch.float32, torch.bfloat16):
+        out = ops.preprocess_u8(batch, zero, one, flip=flip, crop_yx=crop, pad=4, dtype=dtype).float().cpu()
+        got = (out * 255).round().to(torch.int32).permute(0, 2, 3, 1).numpy() - 1       # (-1,-1) where the source is zero padding
+        for k, (f, t, l) in enumerate(combos):
+            assert np.array_equal(got[k], preprocess_index_map(32, 32, 32, 32, 4, f, t, l)), (dtype, f, t, l)
+
+
+@pytest.mark.parametrize('n,h,w,c,oh,ow,pad', [(3, 17, 23, 3, 17, 23, 0), (2, 9, 7, 1, 11, 5, 3), (5, 40, 40, 4, 32, 32, 2), (1, 224, 224, 3, 224, 224, 28), (2, 33, 31, 3, 33, 31, 4)])
+def test_preprocess_ragged_shapes(dev, n, h, w, c, oh, ow, pad):
+    from deepcv_b200 import ops
+    from oracle.deepcv_oracle import preprocess_u8
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    img = torch.randint(0, 256, (n, h, w, c), generator=g, dtype=torch.uint8)
+    flip = (torch.rand(n, generator=g) < 0.5).to(torch.uint8)
+    crop = torch.stack([torch.randint(0, h + 2 * pad - oh + 1, (n,), generator=g), torch.randint(0, w + 2 * pad - ow + 1, (n,), generator=g)], 1).to(torch.int32)
+    mean, std = [0.4, 0.5, 0.45, 0.3][:c], [0.2, 0.25, 0.3, 0.22][:c]
+    ref = preprocess_u8(img, mean, std, flip=flip, crop_yx=crop, pad=pad, out_hw=(oh, ow))
+    for channels_last in (True, False):
+        out = ops.preprocess_u8(img.to(dev), torch.tensor(mean, device=dev), torch.tensor(std, device=dev), flip=flip.to(dev), crop_yx=crop.to(dev), pad=pad,
+                                out_hw=(oh, ow), channels_last=channels_last)
+        assert torch.equal(out.cpu(), ref)
+
+
+# ---- convolution block ------------------------------------------------------------------------------------------------------------
+
+CONV_CASES = [
+    # n, c, h, w, k, ksize, stride, pad, dil, act, bn, gn_groups
+    (4, 3, 32, 32, 4, (5, 5), (1, 1), (2, 2), (1, 1), 'relu', True, 4),
+    (4, 4, 16, 16, 16, (3, 3), (1, 1), (1, 1), (1, 1), 'relu', True, 4),
+    (2, 16, 16, 16, 16, (3, 3), (1, 1), (1, 1), (1, 1), 'leaky', True, 0),
+    (2, 3, 33, 29, 8, (7, 7), (2, 2), (3, 3), (1, 1), 'leaky', True, 0),
+    (3, 5, 13, 11, 6, (3, 5), (1, 2), (1, 0), (1, 1), 'none', False, 3),
+    (2, 8, 12, 12, 10, (3, 3), (1, 1), (2, 2), (2, 2), 'sigmoid', False, 0),
+    (2, 32, 14, 14, 24, (1, 1), (1, 1), (0, 0), (1, 1), 'relu', True, 8),
+    (1, 64, 9, 9, 64, (3, 3), (1, 1), (1, 1), (1, 1), 'leaky', True, 0),
+]
+ACTS = {'relu': torch.nn.ReLU, 'leaky': torch.nn.LeakyReLU, 'sigmoid': torch.nn.Sigmoid, 'none': None}
+
+
+def _make_block(c, k, ksize, stride, pad, dil, act, bn, gn, seed):
+    from deepcv_b200.meta import nn as dnn
+    torch.manual_seed(seed)
+    conv = torch.nn.Conv2d(c, k, ksize, stride=stride, padding=pad, dilation=dil)
+    ref_mods = [conv] + ([ACTS[act]()] if ACTS[act] else []) + ([torch.nn.BatchNorm2d(k, eps=1e-5, momentum=0.07359778246238029)] if bn else []) + ([torch.nn.GroupNorm(gn, k)] if gn else [])
+    ref = torch.nn.Sequential(*ref_mods)
+    with torch.no_grad():
+        for m in ref:
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.GroupNorm)):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.3)
+    ours = dnn.FusedLayer(*copy.deepcopy(ref_mods))
+    return ref, ours
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: f'n{c[0]}c{c[1]}h{c[2]}w{c[3]}k{c[4]}r{c[5][0]}s{c[5][1]}_{c[9]}_bn{int(c[10])}gn{c[11]}')
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_conv_block_forward_backward(dev, case, dtype):
+    n, c, h, w, k, ksize, stride, pad, dil, act, bn, gn = case
+    ref, ours = _make_block(c, k, ksize, stride, pad, dil, act, bn, gn, seed=hash(case) % 1000)
+    ours = ours.to(dev)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, c, h, w, generator=g)
+    xq = x.to(dtype).float() if dtype == torch.bfloat16 else x      # same quantised input on both sides
+    x_ref = xq.clone().requires_grad_(True)
+    y_ref = ref(x_ref)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    x_dev = xq.to(dev, dtype).requires_grad_(True)
+    y = ours(x_dev)
+    assert y.dtype == dtype and y.shape == y_ref.shape
+    y.backward(dy.to(dev, dtype))
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert_close(y, y_ref, tol, 'output')
+    assert_close(x_dev.grad, x_ref.grad, tol * (1 if dtype == torch.float32 else 2), 'dx')
+    for (name, p_ref), (_, p) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert p.grad is not None, name
+        assert_close(p.grad, p_ref.grad, tol * (1 if dtype == torch.float32 else 3), f'd{name}')
+    if bn:
+        bn_ref, bn_ours = [m for m in ref if isinstance(m, torch.nn.BatchNorm2d)][0], ours._bn
+        assert_close(bn_ours.running_mean, bn_ref.running_mean, 1e-4 if dtype == torch.float32 else BF16_TOL, 'running_mean')
+        assert_close(bn_ours.running_var, bn_ref.running_var, 1e-4 if dtype == torch.float32 else BF16_TOL, 'running_var')
+        assert int(bn_ours.num_batches_tracked) == 1
+        # eval mode uses the running statistics
+        ref.eval(), ours.eval()
+        assert_close(ours(x_dev.detach()), ref(xq), tol, 'eval output')
+        assert int(bn_ours.num_batches_tracked) == 1
+
+
+def test_instance_norm_is_groupnorm_with_one_channel_groups(dev):
+    from deepcv_b200.meta import nn as dnn
+    torch.manual_seed(3)
+    mods = [torch.nn.Conv2d(3, 6, 3, padding=1), torch.nn.ReLU(), torch.nn.InstanceNorm2d(6, affine=True)]
+    with torch.no_grad():
+        mods[2].weight.uniform_(0.5, 1.5), mods[2].bias.normal_()
+    ref, ours = torch.nn.Sequential(*mods), dnn.FusedLayer(*copy.deepcopy(mods)).to(dev)
+    x = torch.randn(2, 3, 10, 10)
+    assert_close(ours(x.to(dev)), ref(x), FP32_TOL)
+
+
+# ---- pooling, links, head -------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('shape,kernel,stride', [((3, 4, 32, 32), (2, 2), (2, 2)), ((2, 16, 16, 16), (2, 2), (2, 2)), ((2, 24, 7, 7), (7, 7), (7, 7)), ((2, 5, 9, 11), (3, 2), (2, 3))])
+def test_avg_pool(dev, dtype, shape, kernel, stride):
+    from deepcv_b200 import ops
+    x = torch.randn(*shape).to(dtype).float()
+    xr = x.clone().requires_grad_(True)
+    yr = F.avg_pool2d(xr, kernel, stride)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    xd = x.to(dev, dtype).requires_grad_(True)
+    y = ops.avg_pool2d(xd, kernel, stride)
+    y.backward(dy.to(dev, dtype))
+    tol = 1e-6 if dtype == torch.float32 else BF16_TOL
+    assert_close(y, yr, tol), assert_close(xd.grad, xr.grad, tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_links(dev, dtype):
+    from deepcv_b200 import ops
+    tol = 1e-6 if dtype == torch.float32 else BF16_TOL
+    a, b, c = (torch.randn(2, 8, 6, 6).to(dtype).float() for _ in range(3))
+    small = torch.randn(2, 4, 6, 6).to(dtype).float()
+    for reduction, fn in (('sum', lambda ts: ts[0] + ts[1] + ts[2]), ('mean', lambda ts: (ts[0] + ts[1] + ts[2]) / 3), ('concat', lambda ts: torch.cat(ts, 1))):
+        ins = [a, b, small if reduction == 'concat' else c]
+        refs = [t.clone().requires_grad_(True) for t in ins]
+        out_ref = fn(refs)
+        dy = torch.randn_like(out_ref)
+        out_ref.backward(dy)
+        devs = [t.to(dev, dtype).requires_grad_(True) for t in ins]
+        out = ops.link_reduce(devs, reduction)
+        out.backward(dy.to(dev, dtype))
+        assert_close(out, out_ref, tol, reduction)
+        for d, r in zip(devs, refs):
+            assert_close(d.grad, r.grad, tol, reduction + ' grad')
+    with pytest.raises(RuntimeError):
+        ops.link_reduce([a.to(dev), small.to(dev)], 'sum')
+
+
+@pytest.mark.parametrize('in_hw,out_hw,align', [((16, 16), (8, 8), False), ((16, 16), (4, 4), False), ((7, 9), (14, 5), False), ((8, 8), (12, 12), True), ((14, 14), (7, 7), True)])
+def test_bilinear(dev, in_hw, out_hw, align):
+    from deepcv_b200 import ops
+    x = torch.randn(2, 6, *in_hw)
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, size=out_hw, mode='bilinear', align_corners=align)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    xd = x.to(dev).requires_grad_(True)
+    y = ops.bilinear_resize(xd, out_hw, align_corners=align)
+    y.backward(dy.to(dev))
+    assert_close(y, yr, 1e-5), assert_close(xd.grad, xr.grad, 1e-5)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('m,k,n,act', [(8, 1280, 10, 'sigmoid'), (5, 768, 1000, 'none'), (130, 70, 33, 'relu')])
+def test_flatten_linear_cross_entropy(dev, dtype, m, k, n, act):
+    from deepcv_b200 import ops
+    from deepcv_b200.meta import nn as dnn
+    torch.manual_seed(m)
+    c = 5 if k % 5 == 0 else 2
+    hw = k // c
+    h = next(d for d in (8, 7, 6, 5, 4, 3, 2, 1) if hw % d == 0)
+    x = torch.randn(m, c, h, hw // h).to(dtype).float()
+    lin = torch.nn.Linear(k, n)
+    mods = [lin] + ([ACTS[act]()] if ACTS[act] else [])
+    ref, ours = torch.nn.Sequential(*mods), dnn.FusedLayer(*copy.deepcopy(mods)).to(dev)
+    y_t = torch.randint(0, n, (m,))
+    xr = x.clone().requires_grad_(True)
+    loss_ref = F.cross_entropy(ref(xr.flatten(1)), y_t)
+    loss_ref.backward()
+    xd = x.to(dev, dtype).requires_grad_(True)
+    logits = ours(dnn.Flatten()(xd))
+    assert logits.dtype == torch.float32
+    loss = ops.cross_entropy(logits, y_t.to(dev))
+    loss.backward()
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert_close(loss, loss_ref, tol, 'loss'), assert_close(xd.grad, xr.grad, tol, 'dx')
+    assert_close(ours[0].weight.grad, lin.weight.grad, tol, 'dW'), assert_close(ours[0].bias.grad, lin.bias.grad, tol, 'db')
+
+
+# ---- whole networks ---------------------------------------------------------------------------------------------------------------------
+
+def _run_model(model, x, y, loss_fn):
+    model.train()
+    model.zero_grad()
+    logits = model(x)
+    loss = loss_fn(logits, y)
+    loss.backward()
+    return loss, logits
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_default_net_against_golden(dev, golden_dir, default_hp, dtype):
+    """ C1/C2 network (conv -> ReLU -> BatchNorm -> GroupNorm blocks, pooling, dense link with 2x rescale, Flatten, FC + Sigmoid, CE loss). """
+    from deepcv_b200.meta.base_module import DeepcvModule
+    from deepcv_b200.meta.ignite_training import CrossEntropyLoss
+    gold = torch.load(golden_dir / 'oracle_default_net.pt')
+    model = DeepcvModule(gold['input_shape'], default_hp)
+    model.load_state_dict(gold['state'])
+    model = model.to(dev)
+    x = gold['x'].to(dev, dtype)
+    loss, logits = _run_model(model, x, gold['y'].to(dev), CrossEntropyLoss())
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    if dtype == torch.bfloat16:   # compare against the oracle on the same bf16-quantised input
+        from oracle.deepcv_oracle import OracleDeepcvModule, train_step
+        oracle = OracleDeepcvModule(gold['input_shape'], default_hp)
+        oracle.load_state_dict(gold['state'])
+        loss_ref, logits_ref = train_step(oracle, gold['x'].to(dtype).float(), gold['y'])
+        grads_ref = {n: p.grad for n, p in oracle.named_parameters()}
+        state_ref = oracle.state_dict()
+    else:
+        loss_ref, logits_ref, grads_ref, state_ref = gold['loss'], gold['logits'], gold['grads'], gold['state_after']
+    assert abs(float(loss) - float(loss_ref)) <= tol * abs(float(loss_ref))
+    assert_close(logits, logits_ref, tol, 'logits')
+    worst = {}
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        worst[n] = rel_err(p.grad, grads_ref[n])
+    bad = {n: e for n, e in worst.items() if e > tol * (1 if dtype == torch.float32 else 4)}
+    assert not bad, f'gradient parity failures: {bad}'
+    for n, v in model.state_dict().items():
+        if 'running' in n:
+            assert_close(v, state_ref[n], 1e-4 if dtype == torch.float32 else BF16_TOL, n)
+
+
+def _small_resnet_hp():
+    from deepcv_b200.yaml_config import find_model_spec, load_parameters
+    hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'resnet_style.yml'), 'resnet_style_classifier'))
+    hp['architecture'] = copy.deepcopy(hp['architecture'])
+    backbone = hp['architecture'][0]['_nested_deepcvmodule']
+    backbone['architecture'][-1] = {'avg_pooling': {'kernel_size': [2, 2], 'stride': [2, 2]}}   # 64x64 input -> 2x2 final map
+    hp['architecture'][-1]['fully_connected']['out_features'] = 17
+    return hp
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_resnet_style_net_against_oracle(dev, dtype):
+    """ C4 architecture (LeakyReLU + BatchNorm blocks, residual links, dense link with rescale, stride-2 7x7 stem) at 3x64x64. """
+    from deepcv_b200.meta.base_module import DeepcvModule
+    from deepcv_b200.meta.ignite_training import CrossEntropyLoss
+    from oracle.deepcv_oracle import OracleDeepcvModule, train_step
+    hp = _small_resnet_hp()
+    torch.manual_seed(11)
+    oracle = OracleDeepcvModule((3, 64, 64), hp)
+    model = DeepcvModule((3, 64, 64), hp)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 3, 64, 64, generator=g).to(dtype).float()
+    y = torch.randint(0, 17, (4,), generator=g)
+    loss_ref, logits_ref = train_step(oracle, x, y)
+    loss, logits = _run_model(model, x.to(dev, dtype), y.to(dev), CrossEntropyLoss())
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert_close(logits, logits_ref, tol * (1 if dtype == torch.float32 else 2), 'logits')
+    assert abs(float(loss) - loss_ref) <= tol * abs(loss_ref)
+    grads_ref = {n: p.grad for n, p in oracle.named_parameters()}
+    bad = {n: rel_err(p.grad, grads_ref[n]) for n, p in model.named_parameters()}
+    bad = {n: e for n, e in bad.items() if e > tol * (2 if dtype == torch.float32 else 6)}
+    assert not bad, f'gradient parity failures: {bad}'
+
+
+def test_training_steps_flat_adamw_and_graph_replay(dev, golden_dir, default_hp):
+    """ 4 optimisation steps: oracle + torch.optim.AdamW on CPU vs (a) eager process_function with FlatAdamW over flat buffers and
+    (b) the CUDA-graph replayed step — parameters must agree after every step. """
+    from deepcv_b200.meta.base_module import DeepcvModule
+    from deepcv_b200.meta.flat_params import FlatAdamW, flatten_parameters
+    from deepcv_b200.meta.ignite_training import CrossEntropyLoss, Engine, GraphedTrainStep, make_process_function
+    from oracle.deepcv_oracle import OracleDeepcvModule, train_step
+    gold = torch.load(golden_dir / 'oracle_default_net.pt')
+    opts = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    oracle = OracleDeepcvModule(gold['input_shape'], default_hp)
+    oracle.load_state_dict(gold['state'])
+    opt_ref = torch.optim.AdamW(oracle.parameters(), **opts)
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(8, 3, 32, 32, generator=g), torch.randint(0, 10, (8,), generator=g)) for _ in range(4)]
+
+    def build():
+        m = DeepcvModule(gold['input_shape'], default_hp)
+        m.load_state_dict(gold['state'])
+        m = m.to(dev)
+        o = FlatAdamW(m.parameters(), **opts).attach(flatten_parameters(m))
+        return m, o
+    eager, opt_e = build()
+    graphed, opt_g = build()
+    step_fn = make_process_function({}, dev, eager, {'main_loss': CrossEntropyLoss()}, opt_e)
+    engine = Engine(step_fn)
+    state0 = {n: v.clone() for n, v in graphed.state_dict().items()}
+    runner = GraphedTrainStep(graphed, CrossEntropyLoss(), opt_g, batches[0][0].to(dev), batches[0][1].to(dev), warmup_iters=2)
+    # capture ran warm-up steps on the example batch: rewind parameters, statistics and optimizer state
+    with torch.no_grad():
+        graphed.load_state_dict(state0)
+        for v in opt_g.state['flat'].values():
+            v.zero_()
+        opt_g._dev_state['step'].zero_()
+    for i, (x, y) in enumerate(batches):
+        loss_ref, _ = train_step(oracle, x, y, optimizer=opt_ref)
+        out = step_fn(engine, (x.to(dev), y.to(dev)))
+        loss_g = runner.step(x.to(dev), y.to(dev))
+        assert abs(out['main_loss'] - loss_ref) <= 2e-4 * abs(loss_ref), i
+        assert abs(float(loss_g) - loss_ref) <= 2e-4 * abs(loss_ref), i
+        ref_sd = oracle.state_dict()
+        for name, model in (('eager', eager), ('graphed', graphed)):
+            for n, v in model.state_dict().items():
+                if v.dtype.is_floating_point:
+                    assert rel_err(v, ref_sd[n]) <= 5e-4, (i, name, n, rel_err(v, ref_sd[n]))
+    assert int(eager.state_dict()['_child_modules._submodule_0._child_modules._submodule_0.2.num_batches_tracked']) == 4
+
+
+def test_fused_preprocess_module_feeds_model(dev, default_hp):
+    from deepcv_b200.meta.base_module import DeepcvModule
+    from deepcv_b200.meta.data.preprocess import FusedPreprocess
+    from oracle.deepcv_oracle import OracleDeepcvModule, draw_augmentation_params, preprocess_u8
+    torch.manual_seed(2)
+    oracle = OracleDeepcvModule((3, 32, 32), default_hp)
+    model = DeepcvModule((3, 32, 32), default_hp)
+    model.load_state_dict(oracle.state_dict())
+    pre = FusedPreprocess(mean=[0.491, 0.482, 0.447], std=[0.247, 0.243, 0.261], pad=4, flip=True, seed=77)
+    pipeline = torch.nn.Sequential(pre, model).to(dev)
+    img = torch.randint(0, 256, (16, 32, 32, 3), dtype=torch.uint8)
+    flip, crop = draw_augmentation_params(16, 4, 77)      # same host generator, same seed: identical draws
+    pipeline.train(), oracle.train()
+    out = pipeline(img.to(dev))
+    ref = oracle(preprocess_u8(img, pre.mean.tolist(), pre.std.tolist(), flip=flip, crop_yx=crop, pad=4))
+    assert_close(out, ref, FP32_TOL)
+
+
+def test_launch_counter_and_no_silent_fallback(dev):
+    from deepcv_b200 import ops
+    before = ops.launch_count()
+    ops.avg_pool2d(torch.randn(1, 4, 4, 4, device=dev), 2)
+    assert ops.launch_count() > before
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.avg_pool2d(torch.randn(1, 4, 4, 4), 2)
+    with pytest.raises(NotImplementedError):
+        ops.activation_code(torch.nn.GELU)
