@@ -398,7 +398,14 @@ static int launch_wgrad_cfg(WgradArgs a, cudaStream_t st) {
   if (smem < 256 * 16 * sizeof(float)) smem = 256 * 16 * sizeof(float);
   DCV_REQUIRE(smem <= 220 * 1024, "conv2d_wgrad (direct): kernel %dx%d too large for the shared-memory tile", s.r, s.s);
   long long gy = (long long)kNumSMs * 4 / ((long long)tiles * slabs) + 1;
+  // at most 8 images per CTA: bounds the length of each sequential fp32 accumulation chain (the per-CTA partials are then combined by
+  // atomics, i.e. blocked summation), unless that would take more than ~32M atomics
+  const long long elems = (long long)s.k * s.r * s.s * s.c;
+  long long gy_acc = (s.n + 7) / 8;
+  while (gy_acc > gy && elems * gy_acc * tiles > (32ll << 20)) gy_acc /= 2;
+  if (gy_acc > gy) gy = gy_acc;
   if (gy > s.n) gy = s.n;
+  if (gy > 65535) gy = 65535;
   dim3 grid(tiles, (unsigned)gy, (unsigned)slabs);
   auto kern = conv_wgrad_direct_kernel<T, TW, TH>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

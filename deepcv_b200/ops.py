@@ -21,6 +21,7 @@ __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
+_DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -251,6 +252,8 @@ class _ConvBlock(torch.autograd.Function):
             ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
             check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, st), 'conv2d_wgrad')
+        if _DEBUG_CAPTURE is not None:
+            _DEBUG_CAPTURE.append(dict(wshape=wshape, dz=dz.clone(), y=y.clone(), dy=dy.clone(), pqr=None if pqr is None else pqr.clone(), saved=None if saved is None else saved.clone(), dz_ptr=dz.data_ptr(), y_ptr=y.data_ptr(), dy_ptr=dy.data_ptr(), x=x.clone(), dw=None if dw is None else dw.clone()))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(n, shape.c, shape.h, shape.w, y.dtype, dev)

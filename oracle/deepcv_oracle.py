@@ -322,3 +322,60 @@ def resnet_style_spec(num_classes_unused: int = 1000) -> Dict[str, Any]:
     from deepcv_b200.yaml_config import load_parameters, find_model_spec
     from pathlib import Path
     return find_model_spec(load_parameters(Path(__file__).resolve().parent.parent / 'conf' / 'base' / 'resnet_style.yml'), 'resnet_style_classifier')
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# bf16-storage emulation: the oracle's arithmetic stays float32 (the reference CPU path), but every tensor the bf16 device path keeps in
+# HBM as bfloat16 is rounded at the same point: convolution operands (weights), block outputs after the activation (y) and after the
+# normalisations (z), pooling / link outputs, and on the way back the gradients w.r.t. pre-activations (dy) and block inputs (dx).
+# This separates "bf16 storage changes the numbers" (inherent, identical here and on the device) from kernel defects.
+
+class _Round(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fwd: bool, bwd: bool):
+        ctx.bwd = bwd
+        return x.to(torch.bfloat16).to(x.dtype) if fwd else x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).to(g.dtype) if ctx.bwd else g), None, None
+
+
+def _q(x, fwd=True, bwd=False):
+    return _Round.apply(x, fwd, bwd)
+
+
+def emulate_bf16_storage(model: torch.nn.Module) -> torch.nn.Module:
+    """ Patches (in place) the forward of every block of an `OracleDeepcvModule` so that it rounds tensors where the device path stores bf16. """
+    for m in model.modules():
+        if isinstance(m, torch.nn.Sequential) and len(m) > 0 and any(isinstance(c, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)) for c in m):
+            def fwd(x, m=m):
+                op = next(c for c in m if isinstance(c, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)))
+                rest = [c for c in m if c is not op and not isinstance(c, torch.nn.Dropout)]
+                act = [c for c in rest if not isinstance(c, (torch.nn.modules.batchnorm._BatchNorm, torch.nn.GroupNorm))]
+                norms = [c for c in rest if c not in act]
+                x = _q(x, fwd=False, bwd=True)                         # dx is stored bf16
+                if isinstance(op, torch.nn.Linear):
+                    pre = F.linear(x, op.weight, op.bias)              # fp32 weights, fp32 logits
+                    for a in act:
+                        pre = a(pre)
+                    return pre
+                w = _q(op.weight, fwd=True, bwd=False)                 # bf16 convolution operand, fp32 master weight and gradient
+                pre = F.conv2d(x, w, op.bias, op.stride, op.padding, op.dilation, op.groups)
+                pre = _q(pre, fwd=False, bwd=True)                     # dy (gradient w.r.t. the pre-activation) is stored bf16
+                for a in act:
+                    pre = a(pre)
+                y = _q(pre)                                            # y stored bf16; statistics are taken on the stored values
+                if norms:
+                    for nrm in norms:
+                        y = nrm(y)
+                    y = _q(y)                                          # z stored bf16
+                return y
+            m.forward = fwd
+        elif isinstance(m, (torch.nn.AvgPool2d,)):
+            orig = m.forward
+            m.forward = (lambda x, orig=orig: _q(orig(_q(x, fwd=False, bwd=True))))
+        elif isinstance(m, Link):
+            orig_l = m.forward
+            m.forward = (lambda x, referenced_submodules_out, orig_l=orig_l: _q(orig_l(_q(x, fwd=False, bwd=True), OrderedDict((k, _q(v, fwd=False, bwd=True)) for k, v in referenced_submodules_out.items()))))
+    return model

@@ -135,7 +135,13 @@ def oracle_net(model_yaml: str, model_name: str, input_shape, batch: int, classe
     y = torch.randint(0, classes, (batch,), generator=g)
     loss, logits = train_step(model, x, y)
     grads = {n: p.grad.clone() for n, p in model.named_parameters()}
-    return dict(hp_yaml=model_yaml, model_name=model_name, input_shape=tuple(input_shape), classes=classes, seed=seed, state=init_state, x=x, y=y, loss=loss, logits=logits,
+    # the same step in float64: the arbiter for gradients that are analytically (near) zero (SURVEY.md section 8.d parity gates)
+    model64 = OracleDeepcvModule(input_shape, hp)
+    model64.load_state_dict(init_state)
+    model64 = model64.double()
+    loss64, logits64 = train_step(model64, x.double(), y)
+    grads64 = {n: p.grad.clone() for n, p in model64.named_parameters()}
+    return dict(loss64=loss64, logits64=logits64, grads64=grads64, hp_yaml=model_yaml, model_name=model_name, input_shape=tuple(input_shape), classes=classes, seed=seed, state=init_state, x=x, y=y, loss=loss, logits=logits,
                 grads=grads, state_after=copy.deepcopy(model.state_dict()))
 
 
