@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+""" Benchmark of the DeepcvModule conv/BN/augment hot path (BASELINE.json): train images/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cifar|imagenet|preprocess] [--impl reference]
+
+A step = fused uint8 preprocess (normalise / flip / crop) -> forward -> cross-entropy -> backward -> (bucketed NCCL gradient all-reduce when
+N > 1) -> AdamW, on one synthetic batch per GPU (weak scaling). Default workload = BASELINE.json configs[1]: the default CIFAR-10
+`image_classifier` DeepcvModule, bf16 activations, batch 512 per GPU. Prints ONE JSON line (rank 0):
+  value       images/s with the uint8 batches already resident in HBM (a pool of distinct batches larger than L2 is cycled)
+  e2e         same metric through the public API with HOST (pinned) uint8 batches: H2D copy of images / labels / augmentation parameters and
+              D2H read of the loss inside the timed region, every step
+  roofline    the dominant kernel of the step, timed with CUDA events in this process
+  cpu_baseline  the reference CPU path (the oracle: stock torch CPU modules, fp32) timed on this box's host cores on a bounded sample
+`--impl reference` times only that CPU path and prints the same line with "impl": "reference".
+"""
+import argparse
+import copy
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC, UNIT = 'train images/sec', 'images/s'
+CIFAR_MEAN, CIFAR_STD = [0.491, 0.482, 0.447], [0.247, 0.243, 0.261]
+IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cifar', choices=['cifar', 'imagenet', 'preprocess'])
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: 512 cifar, 256 imagenet)')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the bounded CPU baseline sample')
+    return ap.parse_args()
+
+
+def workload_spec(name: str, batch):
+    from deepcv_b200.yaml_config import find_model_spec, load_parameters
+    if name == 'cifar':
+        hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'parameters.yml'), 'image_classifier'))
+        classes, size, mean, std, pad, b = 10, 32, CIFAR_MEAN, CIFAR_STD, 4, 512
+        label = 'deepcv.classification.image default image_classifier DeepcvModule (conf/base/parameters.yml), synthetic CIFAR-10-shaped uint8 3x32x32'
+    else:
+        hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'resnet_style.yml'), 'resnet_style_classifier'))
+        classes, size, mean, std, pad, b = 1000, 224, IMAGENET_MEAN, IMAGENET_STD, 16, 256
+        label = 'ResNet-style DeepcvModule with residual/dense links (conf/base/resnet_style.yml), synthetic ImageNet-shaped uint8 3x224x224'
+    hp['architecture'] = copy.deepcopy(hp['architecture'])
+    hp['architecture'][-1]['fully_connected']['out_features'] = classes
+    return dict(hp=hp, classes=classes, size=size, mean=mean, std=std, pad=pad, batch=batch or b, label=label)
+
+
+class ClockSampler:
+    """ nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). """
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def cpu_reference_run(spec, steps: int, warmup: int, seconds: float, batch: int):
+    """ The reference CPU path: oracle DeepcvModule (stock torch CPU modules, fp32) + torch.optim.AdamW + the ToTensor/Normalize/crop/flip
+    restatement, on host cores. Sweeps thread counts, keeps the best; each step is a bounded sample (`batch` images). """
+    import torch
+    from oracle import deepcv_oracle as O
+    torch.manual_seed(563454)
+    model = O.OracleDeepcvModule((3, spec['size'], spec['size']), spec['hp'])
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    g = torch.Generator().manual_seed(434546)
+    img = torch.randint(0, 256, (batch, spec['size'], spec['size'], 3), generator=g, dtype=torch.uint8)
+    y = torch.randint(0, spec['classes'], (batch,), generator=g)
+    cores = os.cpu_count() or 1
+    best = None
+    candidates = sorted({max(1, cores // 2), cores}) if cores > 2 else [cores]
+    for k in candidates:
+        torch.set_num_threads(k)
+        times = []
+        t_start = time.perf_counter()
+        for i in range(warmup + steps):
+            flip, crop = O.draw_augmentation_params(batch, spec['pad'], 434546 + i)
+            t0 = time.perf_counter()
+            x = O.preprocess_u8(img, spec['mean'], spec['std'], flip=flip, crop_yx=crop, pad=spec['pad'])
+            O.train_step(model, x, y, optimizer=opt)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if time.perf_counter() - t_start > seconds / len(candidates) and len(times) >= 3:
+                break
+        med = statistics.median(times)
+        if best is None or med < best['ms'] / 1e3:
+            best = dict(ms=med * 1e3, threads=k, steps=len(times))
+    return dict(value=batch / (best['ms'] / 1e3), unit=UNIT, cores=best['threads'], kind='port', ms_per_step=best['ms'],
+                sample=f"{best['steps']} timed steps of batch {batch} (fp32, preprocess + forward + backward + AdamW), best of thread counts {candidates} on {cores} host cores; median step")
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    spec = workload_spec('cifar' if args.workload == 'preprocess' else args.workload, args.batch)
+    batch = min(spec['batch'], 512 if args.workload != 'imagenet' else 16)
+    base = cpu_reference_run(spec, max(args.steps, 3), max(args.warmup, 1), seconds=60.0, batch=batch)
+    line = dict(metric=METRIC, value=base['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=base['ms_per_step'], higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=spec['label'], per_step_batch=batch, note='reference CPU path = oracle restatement (the reference package cannot be imported here: SURVEY.md section 8.c)'),
+                cpu_baseline=dict(value=base['value'], unit=UNIT, cores=base['cores'], kind=base['kind'], sample=base['sample']),
+                e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def time_dominant_kernel(batch, size, dev, peaks, dtype_name):
+    """ Roofline of the dominant kernel of the CIFAR step — the direct forward convolution (3->4 channels, 5x5, fused bias + ReLU + per-(n,c)
+    sum / sum-of-squares epilogue), HBM-bound on this network (arithmetic intensity 43-72 FLOP/B). Called through the C ABI
+    with preallocated buffers; algorithmic bytes per launch = read x + write y + read w; timed with CUDA events on the launching stream over
+    launches that walk a working set larger than L2. """
+    import ctypes
+    import torch
+    from deepcv_b200._lib import ACT_RELU, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, check, lib
+    tdt, dt, esize = (torch.bfloat16, DCV_BF16, 2) if dtype_name == 'bf16' else (torch.float32, DCV_F32, 4)
+    n, c, h, w, k = batch, 3, size, size, 4
+    reps = max(4, int(200e6 / (n * h * w * (c + k) * esize)) + 1)
+    xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
+    ys = [torch.empty(n, h, w, k, device=dev, dtype=tdt) for _ in range(reps)]
+    wt = torch.randn(k, 5, 5, c, device=dev).to(tdt)
+    bias = torch.zeros(k, device=dev)
+    stats = torch.empty(n, k, 2, device=dev)
+    shape = ConvShape(n, h, w, c, k, 5, 5, 1, 1, 2, 2, 1, 1, h, w)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def launch(i):
+        check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(wt), P(bias), P(ys[i]), P(stats), ACT_RELU, 0., dt, ALGO_DIRECT, st), 'conv2d_fwd')
+    for i in range(reps):
+        launch(i)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    start.record()
+    for _ in range(iters):
+        for i in range(reps):
+            launch(i)
+    end.record()
+    torch.cuda.synchronize()
+    per_launch_s = start.elapsed_time(end) / 1e3 / (iters * reps)
+    alg_bytes = n * h * w * (c + k) * esize + k * 25 * c * esize
+    achieved = alg_bytes / per_launch_s / 1e9
+    return dict(bound='hbm', kernel='conv_fwd_direct_kernel (3->4 ch, 5x5, bias + ReLU + statistics epilogue; includes its 4 KB statistics memset)', achieved=achieved, peak=peaks['hbm_gbs'],
+                unit='GB/s', frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=per_launch_s * 1e6)
+
+
+def load_peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d['hbm_gbs']), bf16_tflops=float(d['bf16_tflops']), bf16_tflops_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from deepcv_b200 import ops
+    from deepcv_b200._lib import check, lib
+    from deepcv_b200.meta.base_module import DeepcvModule
+    from deepcv_b200.meta.data.preprocess import FusedPreprocess
+    from deepcv_b200.meta.flat_params import FlatAdamW, flatten_parameters
+    from deepcv_b200.meta.ignite_training import CrossEntropyLoss, DataParallelModel, GraphedTrainStep
+
+    rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    check(lib.dcv_device_check(), 'device_check')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks = load_peaks()
+    spec = workload_spec(args.workload, args.batch)
+    batch, size, classes = spec['batch'], spec['size'], spec['classes']
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+
+    torch.manual_seed(563454)   # same initial weights on every rank (DDP broadcasts rank 0's; same seed + broadcast in DataParallelModel)
+    model = DeepcvModule((3, size, size), spec['hp']).to(dev)
+    pre = FusedPreprocess(mean=spec['mean'], std=spec['std'], pad=spec['pad'], flip=True, dtype=dtype, seed=434546 + rank).to(dev)
+    net = DataParallelModel(model) if world > 1 else model
+    flat = flatten_parameters(model)
+    opt = FlatAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1. / world).attach(flat)
+    loss_fn = CrossEntropyLoss()
+
+    # synthetic data: a pool of distinct uint8 batches larger than L2 (126 MB), cycled
+    g = torch.Generator().manual_seed(563454 + rank)
+    batch_bytes = batch * size * size * 3
+    pool_n = max(4, min(256, int(200e6 // batch_bytes) + 1))
+    pool = [torch.randint(0, 256, (batch, size, size, 3), generator=g, dtype=torch.uint8) for _ in range(pool_n)]
+    labels = [torch.randint(0, classes, (batch,), generator=g) for _ in range(pool_n)]
+    pool_dev = [p.to(dev) for p in pool]
+    labels_dev = [l.to(dev) for l in labels]
+    pool_host = [p.pin_memory() for p in pool[:8]]
+    labels_host = [l.pin_memory() for l in labels[:8]]
+
+    launches0 = ops.launch_count()
+    if args.no_graph:
+        class Eager:
+            static_loss = None
+
+            def step(self, x, y):
+                net.train()
+                flip, crop = pre.draw(x.shape[0])
+                xx = pre(x.to(dev, non_blocking=True), flip=flip.to(dev, non_blocking=True), crop_yx=crop.to(dev, non_blocking=True))
+                loss = loss_fn(net(xx), y.to(dev, non_blocking=True))
+                opt.zero_grad()
+                loss.backward()
+                if world > 1:
+                    net.finish_gradient_reduction()
+                opt.step()
+                return loss
+        runner = Eager()
+        runner.step(pool_dev[0], labels_dev[0])
+        launches_per_step = ops.launch_count() - launches0
+    else:
+        runner = GraphedTrainStep(net, loss_fn, opt, pool_dev[0], labels_dev[0], warmup_iters=3, preprocess=pre)
+        launches_per_step = (ops.launch_count() - launches0) // 4   # 3 warm-up steps + 1 captured step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(steps):
+            fn(warmup + i)
+        end.record()
+        barrier()
+        ms = start.elapsed_time(end)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident throughput
+    def step_resident(i):
+        runner.step(pool_dev[i % pool_n], labels_dev[i % pool_n])
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    value = world * batch * args.steps / (ms / 1e3)
+
+    # ---- end to end: host (pinned) uint8 batches in, loss out, every step
+    losses = []
+
+    def step_e2e(i):
+        loss = runner.step(pool_host[i % len(pool_host)], labels_host[i % len(labels_host)])
+        losses.append(loss.item())                         # D2H read of the step's result (and the only host sync)
+    e2e_steps = max(10, args.steps // 2)
+    ms_e2e = timed(step_e2e, e2e_steps, 3)
+    e2e_value = world * batch * e2e_steps / (ms_e2e / 1e3)
+    h2d = batch_bytes + batch * 8 + batch * (1 + 8) + 4    # images + int64 labels + flip (u8) / crop (2 x i32) + learning rate
+    e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / e2e_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    roofline = time_dominant_kernel(batch, size, dev, peaks, args.dtype) if args.workload == 'cifar' else None
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_reference_run(spec, steps=30, warmup=2, seconds=args.cpu_seconds, batch=min(batch, 512 if args.workload == 'cifar' else 8))
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype=args.dtype, data='synthetic',
+                config=dict(workload=spec['label'], per_gpu_batch=batch, global_batch=batch * world, parallelism=f'dp{world}', step='fused u8 preprocess(normalise+flip+crop) + fwd + CE + bwd + '
+                            + ('bucketed NCCL all-reduce + ' if world > 1 else '') + 'AdamW' + ('' if args.no_graph else ', one CUDA graph replay per step'),
+                            l2='inputs cycle through a pool of %d distinct uint8 batches (%.0f MB > 126 MB L2)' % (pool_n, pool_n * batch_bytes / 1e6), final_loss=losses[-1] if losses else None),
+                e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=clocks.summary(), roofline=roofline, cpu_baseline=cpu)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

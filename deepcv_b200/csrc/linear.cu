@@ -87,6 +87,142 @@ __global__ void linear_dpre_kernel(const void* __restrict__ y, const void* __res
   if (db) atomicAdd(db + col, s);
 }
 
+
+// ---- "skinny" head: n <= 32 output features (the 1280 -> 10 classifier of the default net). The generic 64x64 tile above would launch a
+// handful of CTAs; here a warp owns a row of x and keeps all n accumulators in registers (forward / dx), and the weight gradient is a
+// split-M reduction with one thread per input feature.
+template <typename TX> __device__ __forceinline__ float ldx(const TX* p, size_t i) { return to_f<TX>(p[i]); }
+
+template <int NB, typename TX>
+__global__ void __launch_bounds__(256) linear_skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                                                                int m, int n, int k, int act, float slope) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;
+  float acc[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+  const TX* xr = x + (size_t)row * k;
+  int kk = lane;
+  for (; kk + 96 < k; kk += 128) {   // 4 independent k positions per lane and iteration: loads of all four are in flight together
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = ldx<TX>(xr, kk + 32 * u);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j < n) {
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(w + (size_t)j * k + kk + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[j] = fmaf(xv[u], wv[u], acc[j]);
+      }
+    }
+  }
+  for (; kk < k; kk += 32) {
+    const float xv = ldx<TX>(xr, kk);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) if (j < n) acc[j] = fmaf(xv, w[(size_t)j * k + kk], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane < n) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) if (j == lane) v = acc[j];
+    v += bias ? bias[lane] : 0.f;
+    y[(size_t)row * n + lane] = act_apply(v, act, slope);
+  }
+}
+
+// dpre[row][j] = act'(y)*dy (written to dpre_ws) and dx[row][:] = dpre[row][:] @ w
+template <int NB, typename TX>
+__global__ void __launch_bounds__(256) linear_skinny_dx_kernel(const float* __restrict__ w, const float* __restrict__ y, const float* __restrict__ dy, TX* __restrict__ dx,
+                                                               float* __restrict__ dpre_ws, int m, int n, int k, int act, float slope) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;
+  float mine = 0.f;
+  if (lane < n) {
+    const size_t i = (size_t)row * n + lane;
+    mine = dy[i] * act_grad_from_output(y[i], act, slope);
+    dpre_ws[i] = mine;
+  }
+  float d[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) d[j] = __shfl_sync(0xffffffffu, mine, j);
+  if (!dx) return;
+  TX* dxr = dx + (size_t)row * k;
+  int kk = lane;
+  for (; kk + 96 < k; kk += 128) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j < n) {
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(w + (size_t)j * k + kk + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = fmaf(d[j], wv[u], v[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dxr[kk + 32 * u] = from_f<TX>(v[u]);
+  }
+  for (; kk < k; kk += 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) if (j < n) v = fmaf(d[j], w[(size_t)j * k + kk], v);
+    dxr[kk] = from_f<TX>(v);
+  }
+}
+
+// dw[j][kk] += sum over a chunk of rows of dpre[r][j] * x[r][kk]; db[j] += sum dpre[r][j]   (dw, db zeroed by the wrapper)
+template <int NB, typename TX>
+__global__ void __launch_bounds__(256) linear_skinny_dw_kernel(const TX* __restrict__ x, const float* __restrict__ dpre, float* __restrict__ dw, float* __restrict__ db,
+                                                               int m, int n, int k, int rows_per_cta) {
+  __shared__ float s_d[64 * NB];
+  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, m);
+  for (int i = threadIdx.x; i < (r1 - r0) * n; i += blockDim.x) s_d[(i / n) * NB + i % n] = dpre[(size_t)r0 * n + i];
+  __syncthreads();
+  float acc[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+  if (kk < k) {
+    for (int r = r0; r < r1; ++r) {
+      const float xv = ldx<TX>(x, (size_t)r * k + kk);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) if (j < n) acc[j] = fmaf(s_d[(r - r0) * NB + j], xv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) if (j < n) atomicAdd(dw + (size_t)j * k + kk, acc[j]);
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < n) {
+    float sd = 0.f;
+    for (int r = r0; r < r1; ++r) sd += s_d[(r - r0) * NB + threadIdx.x];
+    atomicAdd(db + threadIdx.x, sd);
+  }
+}
+
+template <int NB, typename TX>
+static int skinny_fwd(const void* x, const float* w, const float* bias, float* y, int m, int n, int k, int act, float slope, cudaStream_t st) {
+  linear_skinny_fwd_kernel<NB, TX><<<(m + 3) / 4, 128, 0, st>>>((const TX*)x, w, bias, y, m, n, k, act, slope);
+  DCV_LAUNCH_CHECK("linear_skinny_fwd_kernel");
+  return 0;
+}
+
+template <int NB, typename TX>
+static int skinny_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, float* db, float* dpre, int m, int n, int k, int act, float slope, cudaStream_t st) {
+  linear_skinny_dx_kernel<NB, TX><<<(m + 3) / 4, 128, 0, st>>>(w, y, dy, (TX*)dx, dpre, m, n, k, act, slope);
+  DCV_LAUNCH_CHECK("linear_skinny_dx_kernel");
+  if (dw) {
+    cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), st);
+    const int rows = 32;
+    linear_skinny_dw_kernel<NB, TX><<<dim3((k + 255) / 256, (m + rows - 1) / rows), 256, 0, st>>>((const TX*)x, dpre, dw, db, m, n, k, rows);
+    DCV_LAUNCH_CHECK("linear_skinny_dw_kernel");
+  }
+  return 0;
+}
+
 }  // namespace dcv
 
 extern "C" {
@@ -95,6 +231,14 @@ int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, in
                    int x_dtype, int y_dtype, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(x && w && y && m > 0 && n > 0 && k > 0, "linear_fwd: bad arguments");
+  if (n <= 32 && y_dtype == DCV_F32) {
+    cudaStream_t st = as_stream(stream);
+    DCV_DISPATCH_DTYPE(x_dtype, TX, {
+      if (n <= 8) return skinny_fwd<8, TX>(x, w, bias, (float*)y, m, n, k, act, slope, st);
+      if (n <= 16) return skinny_fwd<16, TX>(x, w, bias, (float*)y, m, n, k, act, slope, st);
+      return skinny_fwd<32, TX>(x, w, bias, (float*)y, m, n, k, act, slope, st);
+    });
+  }
   GemmArgs g{x, w, y, bias, m, n, k, k, 1, 1, k, x_dtype, DCV_F32, y_dtype, act, slope};
   return launch_gemm(g, as_stream(stream));
 }
@@ -105,6 +249,13 @@ int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy,
   DCV_REQUIRE(x && w && y && dy && dpre_ws && m > 0 && n > 0 && k > 0, "linear_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (db) cudaMemsetAsync(db, 0, (size_t)n * sizeof(float), st);
+  if (n <= 32 && y_dtype == DCV_F32) {
+    DCV_DISPATCH_DTYPE(x_dtype, TX, {
+      if (n <= 8) return skinny_bwd<8, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);
+      if (n <= 16) return skinny_bwd<16, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);
+      return skinny_bwd<32, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);
+    });
+  }
   int gy = (m + 31) / 32; if (gy > 64) gy = 64;
   linear_dpre_kernel<<<dim3((n + 127) / 128, gy), 128, 0, st>>>(y, dy, dpre_ws, db, m, n, act, slope, y_dtype);
   DCV_LAUNCH_CHECK("linear_dpre_kernel");

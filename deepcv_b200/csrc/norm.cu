@@ -181,6 +181,12 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz
   if (dbias) column_reduce_atomic<VE, 1>(acc, g, col, row, colg, dbias + (size_t)colg * VE, 1);
 }
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---- finalize kernels: one CTA, fp64 algebra on the tiny per-(n,c) arrays -------------------------------------------
 // `saved` layout (floats): [0,2c) BN mean,rstd | [2c,4c) alpha,beta | [4c, 4c+2nG) GN mean,rstd | [.., +2nG) scratch A,B per
 // (n,g) | [.., +2c) scratch U1,U2 per channel.
@@ -193,19 +199,21 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
   const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1;
   const double hw = (double)prm.hw;
   const int tid = threadIdx.x, nt = blockDim.x;
-  // 1. BatchNorm per channel
-  for (int ch = tid; ch < c; ch += nt) {
+  // 1. BatchNorm per channel: one warp per channel, lanes stride over the images, fp64 warp reduction
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  for (int ch = warp; ch < c; ch += nwarps) {
     double alpha = 1.0, beta = 0.0, mean = 0.0, rstd = 1.0;
     if (prm.use_bn) {
       double var;
       if (prm.bn_training) {
         double s1 = 0.0, s2 = 0.0;
-        for (int i = 0; i < n; ++i) { s1 += (double)stats[((size_t)i * c + ch) * 2]; s2 += (double)stats[((size_t)i * c + ch) * 2 + 1]; }
+        for (int i = lane; i < n; i += 32) { s1 += (double)stats[((size_t)i * c + ch) * 2]; s2 += (double)stats[((size_t)i * c + ch) * 2 + 1]; }
+        s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
         const double m = (double)n * hw;
         mean = s1 / m;
         var = s2 / m - mean * mean;
         if (var < 0.0) var = 0.0;
-        if (prm.bn_running_mean && prm.bn_running_var) {
+        if (lane == 0 && prm.bn_running_mean && prm.bn_running_var) {
           double mom = (double)prm.bn_momentum;
           if (mom < 0.0) mom = 1.0 / (double)((prm.bn_num_batches_tracked ? *prm.bn_num_batches_tracked : 0) + 1);
           const double unbiased = m > 1.0 ? var * m / (m - 1.0) : var;
@@ -222,8 +230,10 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
       alpha = gamma * rstd;
       beta = bias - mean * alpha;
     }
-    saved[2 * ch] = (float)mean; saved[2 * ch + 1] = (float)rstd;
-    saved[off_alpha(c) + 2 * ch] = (float)alpha; saved[off_alpha(c) + 2 * ch + 1] = (float)beta;
+    if (lane == 0) {
+      saved[2 * ch] = (float)mean; saved[2 * ch + 1] = (float)rstd;
+      saved[off_alpha(c) + 2 * ch] = (float)alpha; saved[off_alpha(c) + 2 * ch + 1] = (float)beta;
+    }
   }
   __syncthreads();
   if (tid == 0 && prm.use_bn && prm.bn_training && prm.bn_num_batches_tracked) *prm.bn_num_batches_tracked += 1;
@@ -306,12 +316,14 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
     }
     __syncthreads();
   }
-  // 2. per-channel sums over images: BatchNorm adjoint sums U1 = sum du, U2 = sum du*y_hat; parameter gradients
-  for (int ch = tid; ch < c; ch += nt) {
+  // 2. per-channel sums over images: BatchNorm adjoint sums U1 = sum du, U2 = sum du*y_hat; parameter gradients.
+  //    One warp per channel, lanes stride over the images, fp64 warp reductions.
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  for (int ch = warp; ch < c; ch += nwarps) {
     const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
     const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
     double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
-    for (int img = 0; img < n; ++img) {
+    for (int img = lane; img < n; img += 32) {
       const size_t i = (size_t)img * c + ch;
       const double sy = (double)stats[2 * i], syy = (double)stats[2 * i + 1], s1 = (double)s[2 * i], s2 = (double)s[2 * i + 1];
       double D1, D2, D3;
@@ -325,11 +337,15 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
         dgb += s1;
       }
     }
-    const double u2 = rc * (u2raw - mu * u1);
-    saved[off_u(c, n, G) + 2 * ch] = (float)u1;
-    saved[off_u(c, n, G) + 2 * ch + 1] = (float)u2;
-    if (prm.use_bn) { if (d_bn_w) d_bn_w[ch] = (float)u2; if (d_bn_b) d_bn_b[ch] = (float)u1; }
-    if (prm.use_gn) { if (d_gn_w) d_gn_w[ch] = (float)dgw; if (d_gn_b) d_gn_b[ch] = (float)dgb; }
+    u1 = warp_sum_d(u1); u2raw = warp_sum_d(u2raw);
+    if (prm.use_gn) { dgw = warp_sum_d(dgw); dgb = warp_sum_d(dgb); }
+    if (lane == 0) {
+      const double u2 = rc * (u2raw - mu * u1);
+      saved[off_u(c, n, G) + 2 * ch] = (float)u1;
+      saved[off_u(c, n, G) + 2 * ch + 1] = (float)u2;
+      if (prm.use_bn) { if (d_bn_w) d_bn_w[ch] = (float)u2; if (d_bn_b) d_bn_b[ch] = (float)u1; }
+      if (prm.use_gn) { if (d_gn_w) d_gn_w[ch] = (float)dgw; if (d_gn_b) d_gn_b[ch] = (float)dgb; }
+    }
   }
   __syncthreads();
   // 3. P, Q, R per (n, c)
