@@ -23,6 +23,18 @@ static dcv_conv_shape dgrad_as_fwd(const dcv_conv_shape& s) {
 
 extern "C" {
 
+int dcv_conv2d_tc_supported(const dcv_conv_shape* shape, int dtype, int op) {
+  using namespace dcv;
+  if (!shape) return 0;
+  if (op == 0) return conv_tc_fwd_supported(shape, dtype) ? 1 : 0;
+  if (op == 1) {
+    if (shape->stride_h != 1 || shape->stride_w != 1) return 0;
+    const dcv_conv_shape t = dgrad_as_fwd(*shape);
+    return (t.pad_h >= 0 && t.pad_w >= 0 && conv_tc_fwd_supported(&t, dtype)) ? 1 : 0;
+  }
+  return conv_tc_wgrad_supported(shape, dtype) ? 1 : 0;
+}
+
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,
                    int act, float slope, int dtype, int algo, void* stream) {
   using namespace dcv;

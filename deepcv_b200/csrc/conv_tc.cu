@@ -1,10 +1,337 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution (placeholder until the kernels land: reports "unsupported").
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+// GEMM view of y[n][p][q][k] = sum_{r,s,c} x[n][p+r-pad][q+s-pad][c] * w[k][r][s][c]   (stride 1, dilation 1, NHWC / KRSC):
+//     M = output pixels (128 per tile),  N = output channels (N_TILE = 64 / 128 / 256 per tile),  K = R*S*C walked as (r, s, 64-channel block).
+//   A operand: for one (r, s, channel block) the 128 x 64 im2col slab is ONE 4-D TMA box {64 ch, tw, th, tn} of x whose start
+//     coordinate is shifted by (s - pad, r - pad); TMA zero-fills whatever falls outside the image (the convolution padding) or beyond the
+//     batch. The box lands in shared memory as 128 rows of 128 B, hardware-swizzled (SWIZZLE_128B) = the K-major UMMA operand layout.
+//     (tw, th, tn) with tw*th*tn = 128 is picked per layer to minimise the padded overhang of the P x Q plane.
+//   B operand: weights viewed as the 2-D matrix [K_out][R*S*C]; a 2-D TMA box {64, N_TILE} at column (r*S+s)*C + c0 is the K-major B slab.
+//   D: 128 lanes x N_TILE fp32 columns of tensor memory, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (192 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; also owns the TMEM
+// allocation), warps 2..5 = epilogue (each owns the TMEM lane quarter warp%4: tcgen05.ld -> bias + activation -> bf16 -> 16-byte global stores).
+// Pipelines: shared-memory ring full/empty mbarriers (TMA <-> MMA, released by tcgen05.commit), TMEM full/empty mbarriers (MMA <-> epilogue).
+//
+// The same kernel computes the data gradient (x := dy, w := transposed + flipped weights, pad := R-1-pad). The weight gradient kernel below
+// contracts over pixels instead: dw[k][r][s][c] = sum_pix dy[pix][k] * x[pix + (r,s)][c], with both operands MN-major (channels contiguous).
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
 
 namespace dcv {
-bool conv_tc_fwd_supported(const dcv_conv_shape*, int) { return false; }
+namespace tc {
+
+constexpr int BLOCK_M = 128;   // pixels per tile = UMMA M = TMEM lanes
+constexpr int BLOCK_K = 64;    // channels per k-block: 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B). K-major operands: 8-row groups 1024 B apart (SBO), LBO unused. MN-major operands: rows
+// are K indices (128 B each = 64 MN elements), SBO = 1024 B between 8-row K groups, LBO = byte distance between 64-element MN atoms.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: fp32 accumulate, bf16 A and B, M x N tile, operand majors (0 = K-major, 1 = MN-major).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                 "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+                 "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct FwdParams {
+  int n, h, w, c, k, r, s, pad_h, pad_w, p, q;
+  int tw, th, tn, tiles_w, tiles_h, tiles_n;   // pixel tile geometry
+  int n_tiles_k;                               // K_out / N_TILE
+  int total_tiles;
+  int act; float slope;
+  const float* bias;
+  __nv_bfloat16* y;
+};
+
+template <int N_TILE>
+struct FwdSmem {
+  static constexpr int kStages = N_TILE == 256 ? 4 : 6;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = N_TILE * BLOCK_K * 2;
+  static constexpr size_t kBytes = 1024 /* alignment slack */ + (size_t)kStages * (A_BYTES + B_BYTES) + 256;
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FwdParams prm) {
+  using S = FwdSmem<N_TILE>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base, smem_b = base + kStages * S::A_BYTES;
+  const uint32_t bars = smem_b + kStages * S::B_BYTES;          // 8-byte mbarriers
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (kStages + i); };
+  auto tfull = [&](int i) { return bars + 8u * (2 * kStages + i); };
+  auto tempty = [&](int i) { return bars + 8u * (2 * kStages + 2 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * N_TILE) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int cblocks = prm.c / BLOCK_K;
+  const int num_kb = prm.r * prm.s * cblocks;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        const int nt = tile % prm.n_tiles_k;
+        int pt = tile / prm.n_tiles_k;
+        const int pw = pt % prm.tiles_w; pt /= prm.tiles_w;
+        const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
+        const int q0 = pw * prm.tw, p0 = ph * prm.th, n0 = pn * prm.tn;
+        for (int rr = 0; rr < prm.r; ++rr)
+          for (int ss = 0; ss < prm.s; ++ss)
+            for (int cb = 0; cb < cblocks; ++cb) {
+              mbar_wait(empty(stage), phase ^ 1u);
+              mbar_expect_tx(full(stage), S::A_BYTES + S::B_BYTES);
+              tma_load_4d(smem_a + stage * S::A_BYTES, &map_x, full(stage), cb * BLOCK_K, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
+              tma_load_2d(smem_b + stage * S::B_BYTES, &map_w, full(stage), (rr * prm.s + ss) * prm.c + cb * BLOCK_K, nt * N_TILE);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * N_TILE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_desc(smem_a + stage * S::A_BYTES, 0, 1024);
+          const uint64_t bdesc = make_desc(smem_b + stage * S::B_BYTES, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kb | k) != 0);
+          umma_commit(empty(stage));          // frees the smem slot once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull(as));               // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> bias + activation -> bf16 -> global =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int wl = row % prm.tw, hl = (row / prm.tw) % prm.th, nl = row / (prm.tw * prm.th);
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      const int nt = tile % prm.n_tiles_k;
+      int pt = tile / prm.n_tiles_k;
+      const int pw = pt % prm.tiles_w; pt /= prm.tiles_w;
+      const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
+      const int q = pw * prm.tw + wl, p = ph * prm.th + hl, n = pn * prm.tn + nl;
+      const bool valid = q < prm.q && p < prm.p && n < prm.n;
+      __nv_bfloat16* dst = prm.y + (((size_t)n * prm.p + p) * prm.q + q) * prm.k + (size_t)nt * N_TILE;
+      mbar_wait(tfull(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]);
+            if (prm.bias) a += __ldg(prm.bias + nt * N_TILE + c0 + j);
+            f[j] = act_apply(a, prm.act, prm.slope);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + c0 + j) = vec_pack<__nv_bfloat16>(f + j);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N_TILE) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero fill outside the tensor. dims / box innermost first; strides in bytes for dims 1..rank-1.
+static int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_tiled();
+  DCV_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// (tw, th, tn), powers of two with product 128, minimising the padded overhang of (q, p, n).
+static void pick_pixel_tile(int q, int p, int n, int* tw, int* th, int* tn) {
+  double best = 1e30;
+  for (int a = 1; a <= 128; a *= 2)
+    for (int b = 1; a * b <= 128; b *= 2) {
+      const int c = 128 / (a * b);
+      if (a > 256 || b > 256 || c > 256) continue;
+      const double padded = (double)((q + a - 1) / a * a) * ((p + b - 1) / b * b) * ((n + c - 1) / c * c);
+      // prefer wider rows (longer contiguous global segments per TMA box) on ties
+      const double cost = padded / ((double)q * p * n) - 1e-6 * a;
+      if (cost < best) { best = cost; *tw = a; *th = b; *tn = c; }
+    }
+}
+
+static int num_sms() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = kNumSMs; }
+  return sms;
+}
+
+template <int N_TILE>
+static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const FwdParams& prm, cudaStream_t st) {
+  auto kern = conv_fwd_tc_kernel<N_TILE>;
+  const size_t smem = FwdSmem<N_TILE>::kBytes;
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
+  kern<<<grid, kThreads, smem, st>>>(mx, mw, prm);
+  DCV_LAUNCH_CHECK("conv_fwd_tc_kernel");
+  return 0;
+}
+
+}  // namespace tc
+
+bool conv_tc_fwd_supported(const dcv_conv_shape* s, int dtype) {
+  if (!s || dtype != DCV_BF16) return false;
+  if (s->stride_h != 1 || s->stride_w != 1 || s->dil_h != 1 || s->dil_w != 1) return false;
+  if (s->c % 64 != 0 || s->k % 64 != 0 || s->pad_h < 0 || s->pad_w < 0) return false;
+  if ((long long)s->n * s->p * s->q < 128) return false;
+  return tc::encode_tiled() != nullptr;
+}
+
+int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, float* stats_nc, int act, float slope, cudaStream_t st) {
+  using namespace tc;
+  DCV_REQUIRE(x && w && y, "conv2d_fwd (tcgen05): null pointer");
+  DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0), "conv2d_fwd (tcgen05): pointers must be 16-byte aligned");
+  FwdParams prm{};
+  prm.n = s->n; prm.h = s->h; prm.w = s->w; prm.c = s->c; prm.k = s->k; prm.r = s->r; prm.s = s->s; prm.pad_h = s->pad_h; prm.pad_w = s->pad_w; prm.p = s->p; prm.q = s->q;
+  pick_pixel_tile(s->q, s->p, s->n, &prm.tw, &prm.th, &prm.tn);
+  prm.tiles_w = (s->q + prm.tw - 1) / prm.tw; prm.tiles_h = (s->p + prm.th - 1) / prm.th; prm.tiles_n = (s->n + prm.tn - 1) / prm.tn;
+  const int n_tile = s->k % 256 == 0 ? 256 : (s->k % 128 == 0 ? 128 : 64);
+  prm.n_tiles_k = s->k / n_tile;
+  const long long tiles = (long long)prm.tiles_w * prm.tiles_h * prm.tiles_n * prm.n_tiles_k;
+  DCV_REQUIRE(tiles < (1ll << 31), "conv2d_fwd (tcgen05): too many tiles");
+  prm.total_tiles = (int)tiles;
+  prm.act = act; prm.slope = slope; prm.bias = bias; prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)s->c, (cuuint64_t)s->w, (cuuint64_t)s->h, (cuuint64_t)s->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s->c * 2, (cuuint64_t)s->w * s->c * 2, (cuuint64_t)s->h * s->w * s->c * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)prm.tw, (cuuint32_t)prm.th, (cuuint32_t)prm.tn};
+    if (make_map(&mx, x, 4, dims, strides, box)) return 1;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)s->r * s->s * s->c, (cuuint64_t)s->k};
+    const cuuint64_t strides[1] = {(cuuint64_t)s->r * s->s * s->c * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)n_tile};
+    if (make_map(&mw, w, 2, dims, strides, box)) return 1;
+  }
+  int rc;
+  if (n_tile == 256) rc = launch_fwd<256>(mx, mw, prm, st);
+  else if (n_tile == 128) rc = launch_fwd<128>(mx, mw, prm, st);
+  else rc = launch_fwd<64>(mx, mw, prm, st);
+  if (rc) return rc;
+  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
+  return 0;
+}
+
+// Weight gradient on tensor cores: not built yet (the direct kernel serves it).
 bool conv_tc_wgrad_supported(const dcv_conv_shape*, int) { return false; }
-int conv_fwd_tc(const dcv_conv_shape*, const void*, const void*, const float*, void*, float*, int, float, cudaStream_t) { set_error("tcgen05 convolution not built"); return 1; }
-int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, cudaStream_t) { set_error("tcgen05 convolution not built"); return 1; }
+int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, cudaStream_t) { set_error("tcgen05 weight gradient not built"); return 1; }
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*) { return 0; }
+
 }  // namespace dcv

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, DCV_BF16, DCV_F32, ConvShape, NormParams, check, lib)
+from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, NormParams, check, lib)
 
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count']
@@ -257,7 +257,13 @@ class _ConvBlock(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(n, shape.c, shape.h, shape.w, y.dtype, dev)
-            check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), _ptr(dy), _ptr(w_op), None, _ptr(dx), dt, algo, st), 'conv2d_dgrad')
+            wt = None
+            if algo != ALGO_DIRECT and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 1):
+                # operand of the data-gradient convolution: [C][R-1-r][S-1-s][K] in the activation dtype
+                wt = torch.empty((shape.c, shape.r, shape.s, shape.k), dtype=y.dtype, device=dev)
+                w32 = _cast_raw(w_op, torch.float32) if w_op.dtype != torch.float32 else w_op
+                check(lib.dcv_pack_conv_weight(_ptr(w32), _ptr(wt), dt, shape.k, shape.r, shape.s, shape.c, 1, st), 'pack_conv_weight')
+            check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), _ptr(dy), _ptr(w_op), _ptr(wt), _ptr(dx), dt, algo, st), 'conv2d_dgrad')
 
         def ret(name, g):  # gradients written straight into a caller-provided bucket slice are not handed to autograd again
             return None if (g is None or name in targets) else g

@@ -68,6 +68,9 @@ int dcv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t co
 int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, int r, int s, int c, int transpose_flip, void* stream);
 
 /* ---- convolution (torch.nn.Conv2d built at meta/submodule_creators.py:251, run at meta/nn.py:553) ---------------- */
+/* 1 iff DCV_ALGO_AUTO would run `op` (0 = forward, 1 = data gradient, 2 = weight gradient) of this shape / dtype on the tcgen05 kernels
+ * (bf16, stride 1, dilation 1, c and k multiples of 64); lets the caller skip preparing the `wt` operand otherwise. */
+int dcv_conv2d_tc_supported(const dcv_conv_shape* shape, int dtype, int op);
 /* y = act(conv(x, w) + bias); if stats_nc != NULL also accumulates per-(image, channel) sum(y) and sum(y*y) of the
  * values written to y into stats_nc[n][k][2] (fp32, overwritten). bias may be NULL. */
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,

@@ -184,6 +184,53 @@ def test_conv_block_forward_backward(dev, case, dtype):
         assert int(bn_ours.num_batches_tracked) == 1
 
 
+TC_CASES = [  # n, c, h, w, k, ksize, pad, act, bn
+    (2, 64, 16, 16, 64, (3, 3), (1, 1), 'leaky', True),
+    (4, 128, 14, 14, 256, (3, 3), (1, 1), 'relu', True),
+    (3, 64, 7, 7, 128, (3, 3), (1, 1), 'leaky', False),
+    (5, 64, 12, 20, 64, (1, 1), (0, 0), 'none', False),
+    (2, 256, 9, 11, 512, (3, 3), (1, 1), 'leaky', True),
+    (1, 64, 56, 56, 64, (3, 3), (1, 1), 'leaky', True),
+    (2, 64, 10, 10, 64, (5, 5), (1, 1), 'relu', False),
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES, ids=lambda c: f'n{c[0]}c{c[1]}h{c[2]}w{c[3]}k{c[4]}r{c[5][0]}_{c[7]}_bn{int(c[8])}')
+def test_tcgen05_convolution_matches_direct_and_oracle(dev, case):
+    """ The tcgen05 / TMEM / TMA implicit-GEMM kernels (forward and data gradient) against (a) the direct CUDA-core kernels on the same bf16
+    operands — both accumulate in fp32, so outputs may differ by one bf16 rounding — and (b) the bf16-storage emulation of the torch modules. """
+    from deepcv_b200._lib import ALGO_DIRECT, ALGO_TCGEN05, ConvShape, lib
+    from oracle.deepcv_oracle import emulate_bf16_storage
+    n, c, h, w, k, ksize, pad, act, bn = case
+    ref, tc = _make_block(c, k, ksize, (1, 1), pad, (1, 1), act, bn, 0, seed=7)
+    direct = copy.deepcopy(tc)
+    tc, direct = tc.to(dev), direct.to(dev)
+    direct.algo = ALGO_DIRECT
+    p_, q_ = h + 2 * pad[0] - ksize[0] + 1, w + 2 * pad[1] - ksize[1] + 1
+    import ctypes
+    shape = ConvShape(n, h, w, c, k, ksize[0], ksize[1], 1, 1, pad[0], pad[1], 1, 1, p_, q_)
+    assert lib.dcv_conv2d_tc_supported(ctypes.byref(shape), 1, 0) == 1 and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), 1, 1) == 1
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, c, h, w, generator=g).bfloat16()
+    outs = {}
+    for name, mod in (('tc', tc), ('direct', direct)):
+        xd = x.to(dev).requires_grad_(True)
+        y = mod(xd)
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(4)).bfloat16()
+        y.backward(dy.to(dev))
+        outs[name] = (y.float().cpu(), xd.grad.float().cpu(), {nm: p.grad.float().cpu() for nm, p in mod.named_parameters()})
+    assert_close(outs['tc'][0], outs['direct'][0], 1e-2, 'y tc vs direct')
+    assert_close(outs['tc'][1], outs['direct'][1], 2e-2, 'dx tc vs direct')
+    for nm in outs['tc'][2]:
+        assert_close(outs['tc'][2][nm], outs['direct'][2][nm], 2e-2, f'd{nm} tc vs direct')
+    em = emulate_bf16_storage(ref)
+    xr = x.float().requires_grad_(True)
+    yr = em(xr)
+    yr.backward(dy.float())
+    assert_close(outs['tc'][0], yr, BF16_TOL, 'y vs oracle')
+    assert_close(outs['tc'][1], xr.grad, 2 * BF16_TOL, 'dx vs oracle')
+
+
 def test_instance_norm_is_groupnorm_with_one_channel_groups(dev):
     from deepcv_b200.meta import nn as dnn
     torch.manual_seed(3)
