@@ -329,9 +329,188 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   return 0;
 }
 
-// Weight gradient on tensor cores: not built yet (the direct kernel serves it).
-bool conv_tc_wgrad_supported(const dcv_conv_shape*, int) { return false; }
-int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, cudaStream_t) { set_error("tcgen05 weight gradient not built"); return 1; }
+// ---- weight gradient ---------------------------------------------------------------------------------------------------------------------
+// dw[k][r][s][c] = sum over output pixels of dy[pix][k] * x[pix + (r - pad, s - pad)][c]     (stride 1, dilation 1)
+// GEMM per filter tap: M = 128 output channels k, N = 64 input channels c, K = pixels (128 per step). Both operands are MN-major: a TMA box
+// {64 channels, tw, th, tn} lands as 128 pixel rows x 128 B, i.e. K (pixel) rows of one 64-element MN atom; the k side uses two atoms (LBO apart).
+// A CTA owns (128-k tile, filter row r, 64-c block, pixel split): per pixel tile it loads the dy slab once and the S column-shifted x slabs of
+// its filter row, and accumulates S tap tiles [128 x 64] in tensor memory over all its pixel tiles; the epilogue adds them into dw with fp32 atomics
+// (dw zeroed first; the splits of the pixel range combine there too).
+namespace tc {
+
+struct WgradParams {
+  int n, h, w, c, k, r, s, pad_h, pad_w, p, q;
+  int tw, th, tn, tiles_w, tiles_h, tiles_n, pixel_tiles;
+  int k_tiles, c_tiles, splits;
+  float* dw;
+};
+
+constexpr int WG_SLAB = BLOCK_M * 128;   // one TMA box: 128 pixel rows x 128 B = 16 KB
+constexpr int WG_MAX_S = 3;
+
+template <int S_TAPS>
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams prm) {
+  constexpr int kStages = 2;
+  constexpr int STAGE_BYTES = (2 + S_TAPS) * WG_SLAB;
+  constexpr int TMEM_COLS = S_TAPS * 64 <= 64 ? 64 : (S_TAPS * 64 <= 128 ? 128 : 256);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kStages * STAGE_BYTES;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (kStages + i); };
+  const uint32_t done = bars + 8u * (2 * kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work unit
+  int u = blockIdx.x;
+  const int split = u % prm.splits; u /= prm.splits;
+  const int ct = u % prm.c_tiles; u /= prm.c_tiles;
+  const int rr = u % prm.r; const int kt = u / prm.r;
+  const int my_tiles = split < prm.pixel_tiles ? (prm.pixel_tiles - split + prm.splits - 1) / prm.splits : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        int pt = split + i * prm.splits;
+        const int pw = pt % prm.tiles_w; pt /= prm.tiles_w;
+        const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
+        const int q0 = pw * prm.tw, p0 = ph * prm.th, n0 = pn * prm.tn;
+        mbar_wait(empty(stage), phase ^ 1u);
+        mbar_expect_tx(full(stage), STAGE_BYTES);
+        const uint32_t sb = base + stage * STAGE_BYTES;
+        tma_load_4d(sb, &map_dy, full(stage), kt * 128, q0, p0, n0);
+        tma_load_4d(sb + WG_SLAB, &map_dy, full(stage), kt * 128 + 64, q0, p0, n0);       // zero-filled when k has only 64 channels
+#pragma unroll
+        for (int ss = 0; ss < S_TAPS; ++ss)
+          tma_load_4d(sb + (2 + ss) * WG_SLAB, &map_x, full(stage), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sb = base + stage * STAGE_BYTES;
+#pragma unroll
+        for (int ss = 0; ss < S_TAPS; ++ss) {
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {
+            // MN-major: 16 pixel rows per MMA = 2048 B; SBO = 1024 B between 8-row groups; LBO = one slab between the two 64-channel atoms of k
+            const uint64_t adesc = make_desc(sb + ks * UMMA_K * 128, WG_SLAB, 1024);
+            const uint64_t bdesc = make_desc(sb + (2 + ss) * WG_SLAB + ks * UMMA_K * 128, WG_SLAB, 1024);
+            umma_bf16(tmem_base + (uint32_t)(ss * 64), adesc, bdesc, idesc, (i | ks) != 0);
+          }
+        }
+        umma_commit(empty(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else if (my_tiles > 0) {
+    const int quarter = warp & 3;
+    const int krow = kt * 128 + quarter * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int ss = 0; ss < S_TAPS; ++ss) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ss * 64 + c0, v);
+        if (krow < prm.k) {
+          float* dst = prm.dw + (((size_t)krow * prm.r + rr) * prm.s + ss) * prm.c + ct * 64 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int S_TAPS>
+static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& prm, int grid, cudaStream_t st) {
+  auto kern = conv_wgrad_tc_kernel<S_TAPS>;
+  const size_t smem = 1024 + 2 * (size_t)(2 + S_TAPS) * WG_SLAB + 256;
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  kern<<<grid, kThreads, smem, st>>>(mdy, mx, prm);
+  DCV_LAUNCH_CHECK("conv_wgrad_tc_kernel");
+  return 0;
+}
+
+}  // namespace tc
+
+bool conv_tc_wgrad_supported(const dcv_conv_shape* s, int dtype) {
+  if (!conv_tc_fwd_supported(s, dtype)) return false;
+  return s->s <= tc::WG_MAX_S;
+}
+
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*) { return 0; }
+
+int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float* dw, void* /*workspace*/, cudaStream_t st) {
+  using namespace tc;
+  DCV_REQUIRE(x && dy && dw, "conv2d_wgrad (tcgen05): null pointer");
+  DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0), "conv2d_wgrad (tcgen05): pointers must be 16-byte aligned");
+  WgradParams prm{};
+  prm.n = s->n; prm.h = s->h; prm.w = s->w; prm.c = s->c; prm.k = s->k; prm.r = s->r; prm.s = s->s; prm.pad_h = s->pad_h; prm.pad_w = s->pad_w; prm.p = s->p; prm.q = s->q;
+  pick_pixel_tile(s->q, s->p, s->n, &prm.tw, &prm.th, &prm.tn);
+  prm.tiles_w = (s->q + prm.tw - 1) / prm.tw; prm.tiles_h = (s->p + prm.th - 1) / prm.th; prm.tiles_n = (s->n + prm.tn - 1) / prm.tn;
+  const long long ptiles = (long long)prm.tiles_w * prm.tiles_h * prm.tiles_n;
+  DCV_REQUIRE(ptiles < (1ll << 30), "conv2d_wgrad (tcgen05): too many pixel tiles");
+  prm.pixel_tiles = (int)ptiles;
+  prm.k_tiles = (s->k + 127) / 128; prm.c_tiles = s->c / 64;
+  const int units = prm.k_tiles * s->r * prm.c_tiles;
+  int splits = (2 * num_sms() + units - 1) / units;        // about two waves of CTAs
+  if (splits > prm.pixel_tiles) splits = prm.pixel_tiles;
+  if (splits < 1) splits = 1;
+  prm.splits = splits;
+  prm.dw = dw;
+  cudaMemsetAsync(dw, 0, (size_t)s->k * s->r * s->s * s->c * sizeof(float), st);
+
+  CUtensorMap mdy, mx;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)s->k, (cuuint64_t)s->q, (cuuint64_t)s->p, (cuuint64_t)s->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s->k * 2, (cuuint64_t)s->q * s->k * 2, (cuuint64_t)s->p * s->q * s->k * 2};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)prm.tw, (cuuint32_t)prm.th, (cuuint32_t)prm.tn};
+    if (make_map(&mdy, dy, 4, dims, strides, box)) return 1;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)s->c, (cuuint64_t)s->w, (cuuint64_t)s->h, (cuuint64_t)s->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s->c * 2, (cuuint64_t)s->w * s->c * 2, (cuuint64_t)s->h * s->w * s->c * 2};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)prm.tw, (cuuint32_t)prm.th, (cuuint32_t)prm.tn};
+    if (make_map(&mx, x, 4, dims, strides, box)) return 1;
+  }
+  const int grid = units * splits;
+  if (s->s == 1) return launch_wgrad<1>(mdy, mx, prm, grid, st);
+  if (s->s == 2) return launch_wgrad<2>(mdy, mx, prm, grid, st);
+  return launch_wgrad<3>(mdy, mx, prm, grid, st);
+}
 
 }  // namespace dcv
