@@ -41,6 +41,8 @@ SYMBOLS = {
     'dcv_nhwc_to_nchw': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_cast': (c_int, [P, c_int, P, c_int, c_size_t, P]),
     'dcv_pack_conv_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_im2col': (c_int, [POINTER(ConvShape), P, P, c_int, c_int, P]),
+    'dcv_fill_zero': (c_int, [P, c_size_t, P]),
     'dcv_conv2d_tc_supported': (c_int, [POINTER(ConvShape), c_int, c_int]),
     'dcv_conv2d_fwd': (c_int, [POINTER(ConvShape), P, P, P, P, P, c_int, c_float, c_int, c_int, P]),
     'dcv_conv2d_dgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, P]),

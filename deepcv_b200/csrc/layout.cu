@@ -45,6 +45,36 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, TD* __restrict__
   }
 }
 
+// col[n][p][q][kpad]: entries (r, s, c) of the receptive field of output pixel (p, q) in the order of the [K][R][S][C] weight layout, zero
+// padded from R*S*C to kpad. One thread per 16-byte output vector: the (cached, redundant) gathers are scalar, the 1.2 GB-class store is coalesced.
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, const dcv_conv_shape s, const int kpad) {
+  constexpr int VE = 16 / sizeof(T);
+  const int vec_per_pix = kpad / VE, rsc = s.r * s.s * s.c, sc = s.s * s.c;
+  const size_t total = (size_t)s.n * s.p * s.q * vec_per_pix;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vec_per_pix);
+    size_t t = idx / vec_per_pix;
+    const int oq = (int)(t % s.q); t /= s.q;
+    const int op = (int)(t % s.p); const int img = (int)(t / s.p);
+    const int iy0 = op * s.stride_h - s.pad_h, ix0 = oq * s.stride_w - s.pad_w;
+    const T* xin = x + (size_t)img * s.h * s.w * s.c;
+    float vals[VE];
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      const int kk = v * VE + e;
+      float val = 0.f;
+      if (kk < rsc) {
+        const int rr = kk / sc, rem = kk - rr * sc, ss = rem / s.c, cc = rem - ss * s.c;
+        const int iy = iy0 + rr * s.dil_h, ix = ix0 + ss * s.dil_w;
+        if (iy >= 0 && iy < s.h && ix >= 0 && ix < s.w) val = to_f<T>(xin[((size_t)iy * s.w + ix) * s.c + cc]);
+      }
+      vals[e] = val;
+    }
+    *reinterpret_cast<uint4*>(col + idx * VE) = vec_pack<T>(vals);
+  }
+}
+
 template <typename TS, typename TD>
 static int launch_transpose(const void* src, void* dst, int batch, int rows, int cols, cudaStream_t st) {
   const int tiles_r = (rows + 31) / 32, tiles_c = (cols + 31) / 32;
@@ -89,6 +119,25 @@ int dcv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t co
   else if (src_dtype == DCV_BF16 && dst_dtype == DCV_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, count);
   else DCV_REQUIRE(false, "cast: unsupported dtypes %d -> %d", src_dtype, dst_dtype);
   DCV_LAUNCH_CHECK("cast_kernel");
+  return 0;
+}
+
+int dcv_im2col(const dcv_conv_shape* shape, const void* x, void* col, int kpad, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(shape && x && col, "im2col: null pointer");
+  const int ve = dtype == DCV_BF16 ? 8 : 4;
+  DCV_REQUIRE(kpad >= shape->r * shape->s * shape->c && kpad % ve == 0 && reinterpret_cast<uintptr_t>(col) % 16 == 0, "im2col: kpad=%d must cover r*s*c=%d and be a multiple of %d", kpad,
+              shape->r * shape->s * shape->c, ve);
+  const size_t total = (size_t)shape->n * shape->p * shape->q * (kpad / ve);
+  DCV_DISPATCH_DTYPE(dtype, T, (im2col_kernel<T><<<grid_for(total, 256, kNumSMs * 32), 256, 0, as_stream(stream)>>>((const T*)x, (T*)col, *shape, kpad)));
+  DCV_LAUNCH_CHECK("im2col_kernel");
+  return 0;
+}
+
+int dcv_fill_zero(void* dst, size_t bytes, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dst || bytes == 0, "fill_zero: null pointer");
+  if (bytes && cudaMemsetAsync(dst, 0, bytes, as_stream(stream)) != cudaSuccess) { set_error("fill_zero: cudaMemsetAsync failed"); (void)cudaGetLastError(); return 2; }
   return 0;
 }
 

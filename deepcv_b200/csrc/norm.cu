@@ -195,13 +195,15 @@ __device__ __forceinline__ size_t off_gn(int c) { return 4 * (size_t)c; }
 __device__ __forceinline__ size_t off_ab(int c, int n, int G) { return 4 * (size_t)c + 2 * (size_t)n * G; }
 __device__ __forceinline__ size_t off_u(int c, int n, int G) { return 4 * (size_t)c + 4 * (size_t)n * G; }
 
-__global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, float* __restrict__ ab, float* __restrict__ saved) {
+__global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, float* __restrict__ ab, float* __restrict__ saved, const int cpb) {
   const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1;
   const double hw = (double)prm.hw;
   const int tid = threadIdx.x, nt = blockDim.x;
+  // this CTA owns channels [ch_lo, ch_hi): whole GroupNorm groups (cpb is a multiple of the group size), so every phase below is CTA-local
+  const int ch_lo = blockIdx.x * cpb, ch_hi = min(c, ch_lo + cpb), cl = ch_hi - ch_lo;
   // 1. BatchNorm per channel: one warp per channel, lanes stride over the images, fp64 warp reduction
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  for (int ch = warp; ch < c; ch += nwarps) {
+  for (int ch = ch_lo + warp; ch < ch_hi; ch += nwarps) {
     double alpha = 1.0, beta = 0.0, mean = 0.0, rstd = 1.0;
     if (prm.use_bn) {
       double var;
@@ -236,13 +238,15 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
     }
   }
   __syncthreads();
-  if (tid == 0 && prm.use_bn && prm.bn_training && prm.bn_num_batches_tracked) *prm.bn_num_batches_tracked += 1;
+  if (blockIdx.x == 0 && tid == 0 && prm.use_bn && prm.bn_training && prm.bn_num_batches_tracked) *prm.bn_num_batches_tracked += 1;
   // 2. GroupNorm per (n, group) on u = alpha*y + beta
   if (prm.use_gn) {
     const int cg = c / G;
     const double mg = (double)cg * hw;
-    for (int i = tid; i < n * G; i += nt) {
-      const int img = i / G, grp = i - img * G;
+    const int g_lo = ch_lo / cg, gl = cl / cg;
+    for (int j = tid; j < n * gl; j += nt) {
+      const int img = j / gl, grp = g_lo + (j - img * gl);
+      const size_t i = (size_t)img * G + grp;
       double su = 0.0, suu = 0.0;
       for (int k = 0; k < cg; ++k) {
         const int ch = grp * cg + k;
@@ -261,8 +265,9 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
   }
   // 3. combined affine per (n, c)
   const int cg = c / G;
-  for (int i = tid; i < n * c; i += nt) {
-    const int img = i / c, ch = i - img * c;
+  for (int j = tid; j < n * cl; j += nt) {
+    const int img = j / cl, ch = ch_lo + (j - img * cl);
+    const size_t i = (size_t)img * c + ch;
     double A = (double)saved[off_alpha(c) + 2 * ch], B = (double)saved[off_alpha(c) + 2 * ch + 1];
     if (prm.use_gn) {
       const size_t gi = (size_t)img * G + ch / cg;
@@ -292,15 +297,18 @@ __device__ __forceinline__ void gn_adjoint_coeffs(const dcv_norm_params& prm, co
 
 __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, const float* __restrict__ s,
                                                             float* __restrict__ saved, float* __restrict__ pqr, float* __restrict__ d_bn_w, float* __restrict__ d_bn_b,
-                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b) {
+                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b, const int cpb) {
   const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1, cg = c / G;
   const double hw = (double)prm.hw;
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int ch_lo = blockIdx.x * cpb, ch_hi = min(c, ch_lo + cpb), cl = ch_hi - ch_lo;   // whole groups per CTA (see fwd_finalize_kernel)
   // 1. GroupNorm group sums A_g = mean_g(gamma*dz), B_g = mean_g(gamma*dz*u_hat)
   if (prm.use_gn) {
     const double mg = (double)cg * hw;
-    for (int i = tid; i < n * G; i += nt) {
-      const int img = i / G, grp = i - img * G;
+    const int g_lo = ch_lo / cg, gl = cl / cg;
+    for (int j = tid; j < n * gl; j += nt) {
+      const int img = j / gl, grp = g_lo + (j - img * gl);
+      const size_t i = (size_t)img * G + grp;
       const double mean_u = (double)saved[off_gn(c) + 2 * (size_t)i], r = (double)saved[off_gn(c) + 2 * (size_t)i + 1];
       double a = 0.0, b = 0.0;
       for (int k = 0; k < cg; ++k) {
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
   // 2. per-channel sums over images: BatchNorm adjoint sums U1 = sum du, U2 = sum du*y_hat; parameter gradients.
   //    One warp per channel, lanes stride over the images, fp64 warp reductions.
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  for (int ch = warp; ch < c; ch += nwarps) {
+  for (int ch = ch_lo + warp; ch < ch_hi; ch += nwarps) {
     const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
     const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
     double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
@@ -350,8 +358,9 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
   __syncthreads();
   // 3. P, Q, R per (n, c)
   const double m = (double)n * hw;
-  for (int i = tid; i < n * c; i += nt) {
-    const int img = i / c, ch = i - img * c;
+  for (int j = tid; j < n * cl; j += nt) {
+    const int img = j / cl, ch = ch_lo + (j - img * cl);
+    const size_t i = (size_t)img * c + ch;
     double D1, D2, D3;
     gn_adjoint_coeffs(prm, saved, img, ch, G, D1, D2, D3);
     double P = D1, Q = D2, R = D3;
@@ -407,6 +416,17 @@ int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dty
   return 0;
 }
 
+// Channels per finalize CTA: whole GroupNorm groups, about 4096 (image, channel) items per CTA, at most one CTA per SM.
+static void finalize_grid(const dcv_norm_params* prm, int* cpb, int* blocks) {
+  const int cg = prm->use_gn ? prm->c / prm->gn_groups : 1;
+  int per = 4096 / (prm->n > 0 ? prm->n : 1);
+  if (per < 1) per = 1;
+  per = (per + cg - 1) / cg * cg;
+  while ((prm->c + per - 1) / per > dcv::kNumSMs) per += cg;
+  *cpb = per;
+  *blocks = (prm->c + per - 1) / per;
+}
+
 static int check_norm_params(const dcv_norm_params* prm, const char* name) {
   using namespace dcv;
   DCV_REQUIRE(prm, "%s: null params", name);
@@ -420,7 +440,9 @@ int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, flo
   using namespace dcv;
   if (check_norm_params(prm, "norm_fwd_finalize")) return 1;
   DCV_REQUIRE(stats_nc && ab_nc && saved, "norm_fwd_finalize: null pointer");
-  fwd_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, ab_nc, saved);
+  int cpb, blocks;
+  finalize_grid(prm, &cpb, &blocks);
+  fwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, ab_nc, saved, cpb);
   DCV_LAUNCH_CHECK("fwd_finalize_kernel");
   return 0;
 }
@@ -461,7 +483,9 @@ int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, con
   using namespace dcv;
   if (check_norm_params(prm, "norm_bwd_finalize")) return 1;
   DCV_REQUIRE(stats_nc && s_nc && saved && pqr_nc, "norm_bwd_finalize: null pointer");
-  bwd_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias);
+  int cpb, blocks;
+  finalize_grid(prm, &cpb, &blocks);
+  bwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias, cpb);
   DCV_LAUNCH_CHECK("bwd_finalize_kernel");
   return 0;
 }

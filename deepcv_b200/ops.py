@@ -195,7 +195,26 @@ class _ConvBlock(torch.autograd.Function):
         w_op = _weight_operand(weight, x.dtype)
         y = empty_nhwc(n, k, p, q, x.dtype, dev)
         stats = torch.empty((n, k, 2), dtype=torch.float32, device=dev) if cfg.any else None
-        check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd')
+        # Convolutions the implicit-GEMM tensor-core kernel cannot address directly (few input channels / strides: the 7x7 stride-2 stem) go
+        # through an explicit im2col: conv(x, w) == 1x1 conv of col[n][p][q][kpad] with the weights zero-padded to [K][kpad].
+        rsc = shape.r * shape.s * shape.c
+        gemm_shape = None
+        if (x.dtype == torch.bfloat16 and algo != ALGO_DIRECT and k % 64 == 0 and rsc <= 4096 and n * p * q >= 128
+                and not lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 0)):
+            kpad = (rsc + 63) // 64 * 64
+            gemm_shape = ConvShape(n, p, q, kpad, k, 1, 1, 1, 1, 0, 0, 1, 1, p, q)
+            if not lib.dcv_conv2d_tc_supported(ctypes.byref(gemm_shape), dt, 0):
+                gemm_shape = None
+        if gemm_shape is not None:
+            col = torch.empty((n, p, q, kpad), dtype=x.dtype, device=dev)
+            check(lib.dcv_im2col(ctypes.byref(shape), _ptr(x), _ptr(col), kpad, dt, st), 'im2col')
+            w_col = torch.empty((k, kpad), dtype=x.dtype, device=dev)
+            check(lib.dcv_fill_zero(_ptr(w_col), w_col.numel() * w_col.element_size(), st), 'fill_zero')
+            check(lib.dcv_copy_channels_in(_ptr(w_op), _ptr(w_col), k, rsc, kpad, 0, dt, st), 'copy_channels_in(weight)')
+            check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd(im2col)')
+            x = col   # what the weight gradient needs; the data gradient only needs dy and the weights
+        else:
+            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd')
         saved = None
         out = y
         if cfg.any:
@@ -207,13 +226,13 @@ class _ConvBlock(torch.autograd.Function):
             out = empty_nhwc(n, k, p, q, x.dtype, dev)
             check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, p * q, k, dt, st), 'norm_apply_fwd')
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
-        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape))
+        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape)
         return out
 
     @staticmethod
     def backward(ctx, dz):
         x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv = ctx.saved_tensors
-        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape = ctx.cfg
+        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape, gemm_shape = ctx.cfg
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st, dt = y.device, _stream(), _dt(y)
         dz = as_nhwc(dz.detach(), y.dtype)
@@ -249,9 +268,14 @@ class _ConvBlock(torch.autograd.Function):
             dw = targets.get('weight', None)
             if dw is None:
                 dw = torch.empty((k, shape.r, shape.s, shape.c), **f32).permute(0, 3, 1, 2)
-            ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
-            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
-            check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, st), 'conv2d_wgrad')
+            if gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
+                dw_col = torch.empty((k, gemm_shape.c), **f32)
+                check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, st), 'conv2d_wgrad(im2col)')
+                check(lib.dcv_copy_channels_out(_ptr(dw_col), _ptr(dw), k, gemm_shape.c, 0, shape.r * shape.s * shape.c, DCV_F32, st), 'copy_channels_out(dw)')
+            else:
+                ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, st), 'conv2d_wgrad')
         if _DEBUG_CAPTURE is not None:
             _DEBUG_CAPTURE.append(dict(wshape=wshape, dz=dz.clone(), y=y.clone(), dy=dy.clone(), pqr=None if pqr is None else pqr.clone(), saved=None if saved is None else saved.clone(), dz_ptr=dz.data_ptr(), y_ptr=y.data_ptr(), dy_ptr=dy.data_ptr(), x=x.clone(), dw=None if dw is None else dw.clone()))
         dx = None

@@ -67,6 +67,12 @@ int dcv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t co
  * the data-gradient convolution). */
 int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, int r, int s, int c, int transpose_flip, void* stream);
 
+/* Explicit im2col for convolutions the implicit-GEMM tensor-core kernel cannot address (few input channels, strides — the 7x7/stride-2 stem):
+ * col[n][p][q][kpad] holds the (r, s, c) receptive field of every output pixel in [K][R][S][C] weight order, zero padded to kpad; the convolution is
+ * then the 1x1 convolution of `col` with the weights padded to [K][kpad]. */
+int dcv_im2col(const dcv_conv_shape* shape, const void* x, void* col, int kpad, int dtype, void* stream);
+int dcv_fill_zero(void* dst, size_t bytes, void* stream);
+
 /* ---- convolution (torch.nn.Conv2d built at meta/submodule_creators.py:251, run at meta/nn.py:553) ---------------- */
 /* 1 iff DCV_ALGO_AUTO would run `op` (0 = forward, 1 = data gradient, 2 = weight gradient) of this shape / dtype on the tcgen05 kernels
  * (bf16, stride 1, dilation 1, c and k multiples of 64); lets the caller skip preparing the `wt` operand otherwise. */

@@ -231,6 +231,29 @@ def test_tcgen05_convolution_matches_direct_and_oracle(dev, case):
     assert_close(outs['tc'][1], xr.grad, 2 * BF16_TOL, 'dx vs oracle')
 
 
+@pytest.mark.parametrize('n,c,h,w,k,ks,stride,pad', [(3, 3, 40, 36, 64, 7, 2, 3), (2, 5, 17, 19, 128, 3, 1, 1), (2, 16, 24, 24, 64, 3, 2, 1)])
+def test_im2col_tensor_core_path_matches_direct(dev, n, c, h, w, k, ks, stride, pad):
+    """ Convolutions with few input channels / strides (the 7x7 stride-2 stem) run as explicit im2col + tcgen05 GEMM in bf16 mode: same numbers as
+    the direct kernels on the same operands (forward, weight gradient; the data gradient stays on the direct kernel). """
+    from deepcv_b200._lib import ALGO_DIRECT
+    ref, tc = _make_block(c, k, (ks, ks), (stride, stride), (pad, pad), (1, 1), 'leaky', True, 0, seed=5)
+    direct = copy.deepcopy(tc)
+    tc, direct = tc.to(dev), direct.to(dev)
+    direct.algo = ALGO_DIRECT
+    x = torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(1)).bfloat16()
+    outs = {}
+    for name, mod in (('tc', tc), ('direct', direct)):
+        xd = x.to(dev).requires_grad_(True)
+        y = mod(xd)
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(2)).bfloat16()
+        y.backward(dy.to(dev))
+        outs[name] = (y.float().cpu(), xd.grad.float().cpu(), {nm: p.grad.float().cpu() for nm, p in mod.named_parameters()})
+    assert_close(outs['tc'][0], outs['direct'][0], 1e-2, 'y')
+    assert_close(outs['tc'][1], outs['direct'][1], 2e-2, 'dx')
+    for nm in outs['tc'][2]:
+        assert_close(outs['tc'][2][nm], outs['direct'][2][nm], 2e-2, f'd{nm}')
+
+
 def test_instance_norm_is_groupnorm_with_one_channel_groups(dev):
     from deepcv_b200.meta import nn as dnn
     torch.manual_seed(3)
