@@ -301,9 +301,20 @@ def run_b200(args):
     h2d = batch_bytes + batch * 8 + batch * (1 + 8) + 4    # images + int64 labels + flip (u8) / crop (2 x i32) + learning rate
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / e2e_steps)
 
-    if rank != 0:
+    def shutdown():
+        # A captured CUDA graph that contains NCCL kernels keeps the communicator busy: destroy_process_group() was seen to hang on it.
+        # Release the graph first and leave the process without the collective teardown.
         if world > 1:
-            dist.destroy_process_group()
+            graph = getattr(runner, 'graph', None)
+            if graph is not None:
+                graph.reset()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
     roofline = time_dominant_kernel(batch, size, dev, peaks, args.dtype) if args.workload == 'cifar' else None
     cpu = None
@@ -316,12 +327,14 @@ def run_b200(args):
                             l2='inputs cycle through a pool of %d distinct uint8 batches (%.0f MB > 126 MB L2)' % (pool_n, pool_n * batch_bytes / 1e6), final_loss=losses[-1] if losses else None),
                 e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=clocks.summary(), roofline=roofline, cpu_baseline=cpu)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():
     args = parse_args()
+    if os.environ.get('DCV_BENCH_WATCHDOG'):   # debugging aid: dump all Python stacks and exit if the run is still going after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ['DCV_BENCH_WATCHDOG']), exit=True)
     if args.impl == 'reference':
         run_reference(args)
     else:
