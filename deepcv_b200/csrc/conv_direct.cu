@@ -21,7 +21,15 @@ struct DirectConvArgs {
   int cc;              // input channels per shared-memory chunk
   int in_th, in_tw, in_pitch;
   int tiles_x;
+  int vec4;            // input channels are a multiple of 4 and 4-channel vector loads are aligned
 };
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* v);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* v) { const float4 f = *reinterpret_cast<const float4*>(p); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u); v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+}
 
 template <int BX, int BY, int PX> struct Tile { static constexpr int TW = BX * PX, TH = BY, THREADS = BX * BY; };
 
@@ -153,6 +161,148 @@ __global__ void __launch_bounds__(BX * BY) conv_fwd_direct_kernel(const DirectCo
   }
 }
 
+
+// Stride-1, dilation-1 specialisation with a compile-time filter width S: a thread owns PX *consecutive* output pixels of one row and KC output
+// channels. Per (input channel, filter row) it loads its PX+S-1 input values once (128-bit shared loads, conflict-free when pitch/4 is odd) and
+// slides the S taps over them in registers: S*PX*KC FMAs for (PX+S-1)/4 + S*KC/4 shared loads, i.e. FMA-bound instead of LDS-bound.
+template <typename T, int KC, int BX, int BY, int PX, int S>
+__global__ void __launch_bounds__(BX * BY) conv_fwd_direct_s1_kernel(const DirectConvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const dcv_conv_shape& s = a.s;
+  constexpr int TW = BX * PX, TH = BY, NT = BX * BY, NIN = PX + S - 1, NV = (NIN + 3) / 4;
+  float* s_in = smem;                                                  // [cc][in_th][in_pitch] (+4 floats of slack)
+  float* s_w = smem + (size_t)a.cc * a.in_th * a.in_pitch + 4;         // [r][S][cc][KC]
+  const int tid = threadIdx.x, tx = tid % BX, ty = tid / BX;
+  const int tile = blockIdx.x, tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
+  const int img = blockIdx.y, k0 = blockIdx.z * KC;
+  const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+  const int iy0 = oy0 - s.pad_h, ix0 = ox0 - s.pad_w;
+  const T* xin = reinterpret_cast<const T*>(a.x) + (size_t)img * s.h * s.w * s.c;
+  const T* wgt = reinterpret_cast<const T*>(a.w);
+
+  float acc[PX][KC];
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) acc[p][k] = 0.f;
+
+  for (int c0 = 0; c0 < s.c; c0 += a.cc) {
+    const int ccn = min(a.cc, s.c - c0);
+    __syncthreads();
+    const int plane = a.in_th * a.in_tw;
+    if (a.vec4) {
+      // 4 channels of a pixel per load (8 B of bf16 / 16 B of fp32): one index computation per pixel instead of per element
+      const int groups = ccn >> 2;
+      for (int i = tid; i < plane * groups; i += NT) {
+        const int g4 = i % groups, pix = i / groups;
+        const int iy = pix / a.in_tw, ix = pix - iy * a.in_tw;
+        const int gy = iy0 + iy, gx = ix0 + ix;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < s.h && gx >= 0 && gx < s.w) load4<T>(xin + ((size_t)gy * s.w + gx) * s.c + c0 + 4 * g4, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_in[((4 * g4 + e) * a.in_th + iy) * a.in_pitch + ix] = v[e];
+      }
+    } else {
+      for (int i = tid; i < plane * ccn; i += NT) {
+        const int cc = i % ccn, pix = i / ccn;
+        const int iy = pix / a.in_tw, ix = pix - iy * a.in_tw;
+        const int gy = iy0 + iy, gx = ix0 + ix;
+        float v = 0.f;
+        if (gy >= 0 && gy < s.h && gx >= 0 && gx < s.w) v = to_f<T>(xin[((size_t)gy * s.w + gx) * s.c + c0 + cc]);
+        s_in[(cc * a.in_th + iy) * a.in_pitch + ix] = v;
+      }
+    }
+    const int wcount = s.r * S * ccn * KC;
+    for (int i = tid; i < wcount; i += NT) {
+      const int kk = i % KC;
+      int t = i / KC;
+      const int cc = t % ccn; t /= ccn;
+      const int ss = t % S, rr = t / S;
+      float v = 0.f;
+      if (k0 + kk < s.k) {
+        size_t src;
+        if (!a.transposed) src = (((size_t)(k0 + kk) * s.r + rr) * S + ss) * s.c + c0 + cc;
+        else src = (((size_t)(c0 + cc) * s.r + (s.r - 1 - rr)) * S + (S - 1 - ss)) * s.k + k0 + kk;
+        v = to_f<T>(wgt[src]);
+      }
+      s_w[((rr * S + ss) * a.cc + cc) * KC + kk] = v;
+    }
+    __syncthreads();
+    for (int cc = 0; cc < ccn; ++cc) {
+      const float* pin = s_in + ((size_t)cc * a.in_th + ty) * a.in_pitch + tx * PX;
+      for (int rr = 0; rr < s.r; ++rr) {
+        float in[NV * 4];
+        const float4* prow = reinterpret_cast<const float4*>(pin + rr * a.in_pitch);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { const float4 f = prow[v]; in[4 * v] = f.x; in[4 * v + 1] = f.y; in[4 * v + 2] = f.z; in[4 * v + 3] = f.w; }
+#pragma unroll
+        for (int ss = 0; ss < S; ++ss) {
+          const float* wp = s_w + ((rr * S + ss) * a.cc + cc) * KC;
+          float wv[KC];
+#pragma unroll
+          for (int k = 0; k < KC; k += 4) { const float4 f = *reinterpret_cast<const float4*>(wp + k); wv[k] = f.x; wv[k + 1] = f.y; wv[k + 2] = f.z; wv[k + 3] = f.w; }
+#pragma unroll
+          for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) acc[p][k] = fmaf(in[p + ss], wv[k], acc[p][k]);
+        }
+      }
+    }
+  }
+
+  T* yout = reinterpret_cast<T*>(a.y) + (size_t)img * s.p * s.q * s.k;
+  float ssum[KC], ssq[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) ssum[k] = ssq[k] = 0.f;
+  const int oy = oy0 + ty;
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const int ox = ox0 + tx * PX + p;
+    if (oy < s.p && ox < s.q) {
+      T* dst = yout + ((size_t)oy * s.q + ox) * s.k + k0;
+      float out[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        float v = acc[p][k] + ((a.bias && k0 + k < s.k) ? a.bias[k0 + k] : 0.f);
+        v = act_apply(v, a.act, a.slope);
+        v = to_f<T>(from_f<T>(v));
+        out[k] = v;
+        if (k0 + k < s.k) { ssum[k] += v; ssq[k] = fmaf(v, v, ssq[k]); }
+      }
+      constexpr int VE = 16 / sizeof(T);
+      if (KC % VE == 0 && k0 + KC <= s.k && (s.k % VE == 0) && (reinterpret_cast<uintptr_t>(a.y) % 16 == 0)) {
+#pragma unroll
+        for (int k = 0; k < KC; k += VE) *reinterpret_cast<uint4*>(dst + k) = vec_pack<T>(out + k);
+      } else if (sizeof(T) == 2 && KC % 4 == 0 && k0 + KC <= s.k && (s.k % 4 == 0) && (reinterpret_cast<uintptr_t>(a.y) % 8 == 0)) {
+#pragma unroll
+        for (int k = 0; k < KC; k += 4) {   // 4 bf16 = 8 bytes
+          __nv_bfloat162 lo = __floats2bfloat162_rn(out[k], out[k + 1]), hi = __floats2bfloat162_rn(out[k + 2], out[k + 3]);
+          *reinterpret_cast<uint2*>(dst + k) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) if (k0 + k < s.k) dst[k] = from_f<T>(out[k]);
+      }
+    }
+  }
+  if (a.stats) {
+    __shared__ float s_red[(NT + 31) / 32][KC * 2];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const float v1 = warp_sum(ssum[k]), v2 = warp_sum(ssq[k]);
+      if (lane == 0) { s_red[warp][2 * k] = v1; s_red[warp][2 * k + 1] = v2; }
+    }
+    __syncthreads();
+    if (tid < KC * 2 && k0 + tid / 2 < s.k) {
+      float v = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < (NT + 31) / 32; ++wv) v += s_red[wv][tid];
+      atomicAdd(a.stats + ((size_t)img * s.k + k0) * 2 + tid, v);
+    }
+  }
+}
+
 // Data gradient for strided convolutions (never the hot case: only a strided layer that is not first needs it).
 template <typename T>
 __global__ void conv_dgrad_generic_kernel(const dcv_conv_shape s, const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx) {
@@ -192,6 +342,7 @@ struct WgradArgs {
   const void* x; const void* dy; float* dw;
   int in_th, in_tw, tiles_x;
   int kslabs, cslabs, tap_chunk;
+  int vec_dy, vec_x;   // channel counts are multiples of 4 and the tensors are aligned for 4-channel vector loads
 };
 
 template <typename T, int TW, int TH>
@@ -301,6 +452,136 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const WgradArgs 
   }
 }
 
+
+// Stride-1 / dilation-1 weight gradient with a compile-time filter width S. A thread owns one filter row r, a 4k x 4c register block and ALL S
+// column taps of that row (S*16 accumulators); it walks output rows y (strided over the threads that share the unit) and slides along x keeping the
+// S input columns of row y+r in registers: per pixel 2 shared 128-bit loads (dy, newest input column) feed 16*S FMAs.
+template <typename T, int S, int TW, int TH, int KC, int CC>
+__global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradArgs a) {
+  constexpr int NT = 256, NPIX = TW * TH;   // KC / CC: channel slab widths (4, 8 or 16) = shared-memory pixel strides
+  extern __shared__ __align__(16) float smem[];
+  const dcv_conv_shape& s = a.s;
+  float* s_dy = smem;                 // [NPIX][KC]
+  float* s_x = smem + NPIX * KC;      // [in_th][in_tw][CC]
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x, tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
+  int z = blockIdx.z;
+  const int k0 = (z % a.kslabs) * KC; z /= a.kslabs;
+  const int c0 = z * CC;
+  const int kq_n = (min(KC, s.k - k0) + 3) / 4, cq_n = (min(CC, s.c - c0) + 3) / 4;
+  const int units = s.r * kq_n * cq_n;
+  // L consecutive lanes (a power of two, <= 32) share a unit and split the tile into (row, x-segment) pieces: their partial sums are combined
+  // with warp shuffles at the end, no shared-memory reduction
+  int L = 32;
+  while (L > 1 && units * L > NT) L >>= 1;
+  const int xseg = max(1, min(L / TH, TW / S)), seglen = (TW + xseg - 1) / xseg, nseg = TH * xseg;
+  const int u = tid / L, part = tid % L;
+  const bool active = u < units;
+  const int rr = u / (kq_n * cq_n), kq = (u / cq_n) % kq_n, cq = u % cq_n;
+  const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+  const int iy0 = oy0 - s.pad_h, ix0 = ox0 - s.pad_w;
+  const int in_pix = a.in_th * a.in_tw;
+
+  float acc[S][16];
+#pragma unroll
+  for (int ss = 0; ss < S; ++ss)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[ss][i] = 0.f;
+
+  const T* xall = reinterpret_cast<const T*>(a.x);
+  const T* dyall = reinterpret_cast<const T*>(a.dy);
+  for (int img = blockIdx.y; img < s.n; img += gridDim.y) {
+    __syncthreads();
+    const T* dyp = dyall + (size_t)img * s.p * s.q * s.k;
+    if (a.vec_dy) {   // 4 channels per load
+      for (int i = tid; i < NPIX * (KC / 4); i += NT) {
+        const int g4 = i % (KC / 4), pix = i / (KC / 4);
+        const int oy = oy0 + pix / TW, ox = ox0 + pix % TW;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (oy < s.p && ox < s.q && k0 + 4 * g4 < s.k) load4<T>(dyp + ((size_t)oy * s.q + ox) * s.k + k0 + 4 * g4, v);
+        *reinterpret_cast<float4*>(s_dy + pix * KC + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int i = tid; i < NPIX * KC; i += NT) {
+        const int kk = i % KC, pix = i / KC;
+        const int oy = oy0 + pix / TW, ox = ox0 + pix % TW;
+        float v = 0.f;
+        if (oy < s.p && ox < s.q && k0 + kk < s.k) v = to_f<T>(dyp[((size_t)oy * s.q + ox) * s.k + k0 + kk]);
+        s_dy[i] = v;
+      }
+    }
+    const T* xp = xall + (size_t)img * s.h * s.w * s.c;
+    if (a.vec_x) {
+      for (int i = tid; i < in_pix * (CC / 4); i += NT) {
+        const int g4 = i % (CC / 4), pix = i / (CC / 4);
+        const int gy = iy0 + pix / a.in_tw, gx = ix0 + pix % a.in_tw;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < s.h && gx >= 0 && gx < s.w && c0 + 4 * g4 < s.c) load4<T>(xp + ((size_t)gy * s.w + gx) * s.c + c0 + 4 * g4, v);
+        *reinterpret_cast<float4*>(s_x + pix * CC + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int i = tid; i < in_pix * CC; i += NT) {
+        const int cc = i % CC, pix = i / CC;
+        const int gy = iy0 + pix / a.in_tw, gx = ix0 + pix % a.in_tw;
+        float v = 0.f;
+        if (gy >= 0 && gy < s.h && gx >= 0 && gx < s.w && c0 + cc < s.c) v = to_f<T>(xp[((size_t)gy * s.w + gx) * s.c + c0 + cc]);
+        s_x[i] = v;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int seg = part; seg < nseg; seg += L) {
+        const int y = seg / xseg, xs = seg - y * xseg;
+        const int xbeg = xs * seglen, xend = min(TW, xbeg + seglen);
+        const float* xrow = s_x + (size_t)((y + rr) * a.in_tw) * CC + cq * 4;
+        const float* drow = s_dy + (size_t)(y * TW) * KC + kq * 4;
+        float4 win[S];
+#pragma unroll
+        for (int j = 0; j < S - 1; ++j) win[j] = *reinterpret_cast<const float4*>(xrow + (xbeg + j) * CC);
+        for (int x0 = xbeg; x0 < xend; x0 += S) {
+#pragma unroll
+          for (int j = 0; j < S; ++j) {
+            const int x = x0 + j;
+            if (x < xend) {
+              win[(j + S - 1) % S] = *reinterpret_cast<const float4*>(xrow + (x + S - 1) * CC);
+              const float4 d = *reinterpret_cast<const float4*>(drow + x * KC);
+              const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+              for (int ss = 0; ss < S; ++ss) {
+                const float4 w4 = win[(j + ss) % S];
+                const float xx[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) acc[ss][i * 4 + jj] = fmaf(dd[i], xx[jj], acc[ss][i * 4 + jj]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // combine the L lanes of each unit with shuffles, then one atomic per dw element
+#pragma unroll
+  for (int ss = 0; ss < S; ++ss) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float v = acc[ss][i];
+      for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[ss][i] = v;
+    }
+    if (active && part == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k0 + kq * 4 + i, cc = c0 + cq * 4 + j;
+          if (kk < s.k && cc < s.c) atomicAdd(a.dw + (((size_t)kk * s.r + rr) * S + ss) * s.c + cc, acc[ss][i * 4 + j]);
+        }
+    }
+  }
+}
+
 // ---- host-side launchers ------------------------------------------------------------------------------------------------
 static int check_shape(const dcv_conv_shape* s, const char* name) {
   DCV_REQUIRE(s, "%s: null shape", name);
@@ -337,8 +618,49 @@ static int launch_fwd_cfg(DirectConvArgs a, cudaStream_t st) {
   return 0;
 }
 
+
+template <typename T, int KC, int BX, int BY, int PX, int S>
+static int launch_fwd_s1_cfg(DirectConvArgs a, cudaStream_t st) {
+  const dcv_conv_shape& s = a.s;
+  constexpr int TW = BX * PX, TH = BY;
+  a.in_th = TH + s.r - 1;
+  a.in_tw = TW + S - 1;
+  a.in_pitch = (a.in_tw + 3) / 4 * 4;
+  if ((a.in_pitch / 4) % 2 == 0) a.in_pitch += 4;          // pitch/4 odd: the 128-bit row loads of a quarter warp hit distinct banks
+  int cc = s.c < 16 ? s.c : 16;
+  auto bytes = [&](int c) { return ((size_t)c * a.in_th * a.in_pitch + 4 + (size_t)s.r * S * c * KC) * sizeof(float); };
+  while (cc > 1 && bytes(cc) > 96 * 1024) --cc;
+  a.cc = cc;
+  a.vec4 = (s.c % 4 == 0 && cc % 4 == 0 && reinterpret_cast<uintptr_t>(a.x) % (4 * sizeof(T)) == 0) ? 1 : 0;
+  a.tiles_x = (s.q + TW - 1) / TW;
+  const int tiles = a.tiles_x * ((s.p + TH - 1) / TH);
+  dim3 grid(tiles, s.n, (s.k + KC - 1) / KC);
+  auto kern = conv_fwd_direct_s1_kernel<T, KC, BX, BY, PX, S>;
+  const size_t smem = bytes(cc);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, BX * BY, smem, st>>>(a);
+  DCV_LAUNCH_CHECK("conv_fwd_direct_s1_kernel");
+  return 0;
+}
+
+// Returns -1 when the specialised kernel does not apply (caller falls back to the generic one).
+template <typename T, int KC>
+static int launch_fwd_s1(const DirectConvArgs& a, cudaStream_t st) {
+  const dcv_conv_shape& s = a.s;
+  if (s.stride_h != 1 || s.stride_w != 1 || s.dil_h != 1 || s.dil_w != 1 || s.r > 7) return -1;
+  if (s.q >= 24) {
+    if (s.s == 3) return launch_fwd_s1_cfg<T, KC, 4, 16, 8, 3>(a, st);
+    if (s.s == 5) return launch_fwd_s1_cfg<T, KC, 4, 16, 8, 5>(a, st);
+  } else if (s.q >= 12) {
+    if (s.s == 3) return launch_fwd_s1_cfg<T, KC, 4, 16, 4, 3>(a, st);
+    if (s.s == 5) return launch_fwd_s1_cfg<T, KC, 4, 16, 4, 5>(a, st);
+  }
+  return -1;
+}
+
 template <typename T, int KC>
 static int launch_fwd_kc(const DirectConvArgs& a, cudaStream_t st) {
+  if (KC % 4 == 0) { const int rc = launch_fwd_s1<T, KC>(a, st); if (rc >= 0) return rc; }
   if (a.s.q >= 24) return launch_fwd_cfg<T, KC, 8, 16, 4>(a, st);
   if (a.s.q >= 12) return launch_fwd_cfg<T, KC, 8, 16, 2>(a, st);
   return launch_fwd_cfg<T, KC, 8, 8, 1>(a, st);
@@ -414,6 +736,61 @@ static int launch_wgrad_cfg(WgradArgs a, cudaStream_t st) {
   return 0;
 }
 
+
+template <typename T, int S, int TW, int TH, int KC, int CC>
+static int launch_wgrad_s1_cfg(WgradArgs a, cudaStream_t st) {
+  const dcv_conv_shape& s = a.s;
+  a.in_th = TH + s.r - 1;
+  a.in_tw = TW + S - 1;
+  a.tiles_x = (s.q + TW - 1) / TW;
+  const int tiles = a.tiles_x * ((s.p + TH - 1) / TH);
+  a.kslabs = (s.k + KC - 1) / KC; a.cslabs = (s.c + CC - 1) / CC;
+  const long long slabs = (long long)a.kslabs * a.cslabs;
+  DCV_REQUIRE(slabs < 65536, "conv2d_wgrad (direct): %lld channel slabs exceed the grid limit; use the tcgen05 algorithm", slabs);
+  size_t smem = ((size_t)TW * TH * KC + (size_t)a.in_th * a.in_tw * CC) * sizeof(float);
+  if (smem < 256 * 16 * sizeof(float)) smem = 256 * 16 * sizeof(float);
+  // about 6 CTAs per SM in flight (the staging phase of one CTA hides behind the FMAs of the others), at most 8 images per CTA
+  long long gy = (long long)kNumSMs * 4 / ((long long)tiles * slabs) + 1;
+  const long long elems = (long long)s.k * s.r * s.s * s.c;
+  long long gy_acc = (s.n + 7) / 8;
+  while (gy_acc > gy && elems * gy_acc * tiles > (32ll << 20)) gy_acc /= 2;
+  if (gy_acc > gy) gy = gy_acc;
+  if (gy > s.n) gy = s.n;
+  if (gy > 65535) gy = 65535;
+  a.vec_dy = (s.k % 4 == 0 && reinterpret_cast<uintptr_t>(a.dy) % (4 * sizeof(T)) == 0) ? 1 : 0;
+  a.vec_x = (s.c % 4 == 0 && reinterpret_cast<uintptr_t>(a.x) % (4 * sizeof(T)) == 0) ? 1 : 0;
+  dim3 grid(tiles, (unsigned)gy, (unsigned)slabs);
+  auto kern = conv_wgrad_direct_s1_kernel<T, S, TW, TH, KC, CC>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, 256, smem, st>>>(a);
+  DCV_LAUNCH_CHECK("conv_wgrad_direct_s1_kernel");
+  return 0;
+}
+
+template <typename T, int S, int TW, int TH>
+static int launch_wgrad_s1_slabs(const WgradArgs& a, cudaStream_t st) {
+  const dcv_conv_shape& s = a.s;
+  const bool k4 = s.k <= 4, c4 = s.c <= 4;
+  if (k4 && c4) return launch_wgrad_s1_cfg<T, S, TW, TH, 4, 4>(a, st);
+  if (k4) return launch_wgrad_s1_cfg<T, S, TW, TH, 4, 16>(a, st);
+  if (c4) return launch_wgrad_s1_cfg<T, S, TW, TH, 16, 4>(a, st);
+  return launch_wgrad_s1_cfg<T, S, TW, TH, 16, 16>(a, st);
+}
+
+template <typename T>
+static int launch_wgrad_s1(const WgradArgs& a, cudaStream_t st) {   // -1: not applicable
+  const dcv_conv_shape& s = a.s;
+  if (s.stride_h != 1 || s.stride_w != 1 || s.dil_h != 1 || s.dil_w != 1 || s.r > 7) return -1;
+  if (s.q >= 24) {
+    if (s.s == 3) return launch_wgrad_s1_slabs<T, 3, 32, 16>(a, st);
+    if (s.s == 5) return launch_wgrad_s1_slabs<T, 5, 32, 16>(a, st);
+  } else if (s.q >= 12) {
+    if (s.s == 3) return launch_wgrad_s1_slabs<T, 3, 16, 16>(a, st);
+    if (s.s == 5) return launch_wgrad_s1_slabs<T, 5, 16, 16>(a, st);
+  }
+  return -1;
+}
+
 int conv_wgrad_direct(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, int dtype, cudaStream_t st) {
   if (check_shape(shape, "conv2d_wgrad")) return 1;
   DCV_REQUIRE(x && dy && dw, "conv2d_wgrad: null pointer");
@@ -424,6 +801,7 @@ int conv_wgrad_direct(const dcv_conv_shape* shape, const void* x, const void* dy
   // the 7x7/stride-2 class of layers needs the small tile to fit the input halo in shared memory
   const bool big_halo = ((31 * s.stride_w + (s.s - 1) * s.dil_w + 1) * (15 * s.stride_h + (s.r - 1) * s.dil_h + 1)) > 2200;
   DCV_DISPATCH_DTYPE(dtype, T, {
+    { const int rc = launch_wgrad_s1<T>(a, st); if (rc >= 0) return rc; }
     if (s.q >= 24 && !big_halo) return launch_wgrad_cfg<T, 32, 16>(a, st);
     if (s.q >= 12) return launch_wgrad_cfg<T, 16, 16>(a, st);
     return launch_wgrad_cfg<T, 8, 8>(a, st);

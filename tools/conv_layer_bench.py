@@ -19,12 +19,17 @@ LAYERS = [  # name, c, h, k, ksize
 ]
 
 
+CIFAR_LAYERS = [('c1 3->4 5x5 @32', 3, 32, 4, 5), ('c2 4->4 5x5 @32', 4, 32, 4, 5), ('c4 4->16 3x3 @16', 4, 16, 16, 3), ('c5 16->16 3x3 @16', 16, 16, 16, 3)]
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--net', default='resnet', choices=['resnet', 'cifar'])
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--ops', default='fwd,dgrad,wgrad')
     ap.add_argument('--algo', default='auto')
+    ap.add_argument('--only', default=None, help='substring filter on the layer name')
     args = ap.parse_args()
     algo = ALGO_AUTO if args.algo == 'auto' else ALGO_DIRECT
     peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text()) if (ROOT / 'MEASURED_PEAKS.json').exists() else {'bf16_tflops': 1590.0}
@@ -32,7 +37,9 @@ def main():
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     n = args.batch
-    for name, c, h, k, ks in LAYERS:
+    for name, c, h, k, ks in (LAYERS if args.net == 'resnet' else CIFAR_LAYERS):
+        if args.only and args.only not in name:
+            continue
         pad = ks // 2
         shape = ConvShape(n, h, h, c, k, ks, ks, 1, 1, pad, pad, 1, 1, h, h)
         act_bytes = n * h * h * (c + k) * 2
