@@ -458,11 +458,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const WgradArgs 
 // S input columns of row y+r in registers: per pixel 2 shared 128-bit loads (dy, newest input column) feed 16*S FMAs.
 template <typename T, int S, int TW, int TH, int KC, int CC>
 __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradArgs a) {
-  constexpr int NT = 256, NPIX = TW * TH;   // KC / CC: channel slab widths (4, 8 or 16) = shared-memory pixel strides
+  constexpr int NT = 256, NPIX = TW * TH, TWP = TW + 1;   // TWP: odd row pitch (in pixels) of the staged dy tile => conflict-free 128-bit loads across rows   // KC / CC: channel slab widths (4, 8 or 16) = shared-memory pixel strides
   extern __shared__ __align__(16) float smem[];
   const dcv_conv_shape& s = a.s;
   float* s_dy = smem;                 // [NPIX][KC]
-  float* s_x = smem + NPIX * KC;      // [in_th][in_tw][CC]
+  float* s_x = smem + TH * TWP * KC;  // [in_th][in_tw (odd)][CC]
   const int tid = threadIdx.x;
   const int tile = blockIdx.x, tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
   int z = blockIdx.z;
@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradAr
   const int xseg = max(1, min(L / TH, TW / S)), seglen = (TW + xseg - 1) / xseg, nseg = TH * xseg;
   const int u = tid / L, part = tid % L;
   const bool active = u < units;
+  const bool warp_has_work = ((tid & ~31) / L) < units;   // warp-uniform
   const int rr = u / (kq_n * cq_n), kq = (u / cq_n) % kq_n, cq = u % cq_n;
   const int oy0 = tile_y * TH, ox0 = tile_x * TW;
   const int iy0 = oy0 - s.pad_h, ix0 = ox0 - s.pad_w;
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradAr
         const int oy = oy0 + pix / TW, ox = ox0 + pix % TW;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (oy < s.p && ox < s.q && k0 + 4 * g4 < s.k) load4<T>(dyp + ((size_t)oy * s.q + ox) * s.k + k0 + 4 * g4, v);
-        *reinterpret_cast<float4*>(s_dy + pix * KC + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(s_dy + ((pix / TW) * TWP + pix % TW) * KC + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
       }
     } else {
       for (int i = tid; i < NPIX * KC; i += NT) {
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradAr
         const int oy = oy0 + pix / TW, ox = ox0 + pix % TW;
         float v = 0.f;
         if (oy < s.p && ox < s.q && k0 + kk < s.k) v = to_f<T>(dyp[((size_t)oy * s.q + ox) * s.k + k0 + kk]);
-        s_dy[i] = v;
+        s_dy[((pix / TW) * TWP + pix % TW) * KC + kk] = v;
       }
     }
     const T* xp = xall + (size_t)img * s.h * s.w * s.c;
@@ -531,10 +532,10 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradAr
     __syncthreads();
     if (active) {
       for (int seg = part; seg < nseg; seg += L) {
-        const int y = seg / xseg, xs = seg - y * xseg;
+        const int xs = seg / TH, y = seg - xs * TH;   // consecutive lanes walk rows: with odd row pitches their 16-byte loads hit distinct banks
         const int xbeg = xs * seglen, xend = min(TW, xbeg + seglen);
         const float* xrow = s_x + (size_t)((y + rr) * a.in_tw) * CC + cq * 4;
-        const float* drow = s_dy + (size_t)(y * TW) * KC + kq * 4;
+        const float* drow = s_dy + (size_t)(y * TWP) * KC + kq * 4;
         float4 win[S];
 #pragma unroll
         for (int j = 0; j < S - 1; ++j) win[j] = *reinterpret_cast<const float4*>(xrow + (xbeg + j) * CC);
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradAr
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       float v = acc[ss][i];
-      for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (warp_has_work) for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       acc[ss][i] = v;
     }
     if (active && part == 0) {
@@ -741,14 +742,13 @@ template <typename T, int S, int TW, int TH, int KC, int CC>
 static int launch_wgrad_s1_cfg(WgradArgs a, cudaStream_t st) {
   const dcv_conv_shape& s = a.s;
   a.in_th = TH + s.r - 1;
-  a.in_tw = TW + S - 1;
+  a.in_tw = (TW + S - 1) | 1;        // odd row pitch (see the kernel)
   a.tiles_x = (s.q + TW - 1) / TW;
   const int tiles = a.tiles_x * ((s.p + TH - 1) / TH);
   a.kslabs = (s.k + KC - 1) / KC; a.cslabs = (s.c + CC - 1) / CC;
   const long long slabs = (long long)a.kslabs * a.cslabs;
   DCV_REQUIRE(slabs < 65536, "conv2d_wgrad (direct): %lld channel slabs exceed the grid limit; use the tcgen05 algorithm", slabs);
-  size_t smem = ((size_t)TW * TH * KC + (size_t)a.in_th * a.in_tw * CC) * sizeof(float);
-  if (smem < 256 * 16 * sizeof(float)) smem = 256 * 16 * sizeof(float);
+  size_t smem = ((size_t)(TW + 1) * TH * KC + (size_t)a.in_th * a.in_tw * CC) * sizeof(float);
   // about 6 CTAs per SM in flight (the staging phase of one CTA hides behind the FMAs of the others), at most 8 images per CTA
   long long gy = (long long)kNumSMs * 4 / ((long long)tiles * slabs) + 1;
   const long long elems = (long long)s.k * s.r * s.s * s.c;
