@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
         const int pw = pt % prm.tiles_w; pt /= prm.tiles_w;
         const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
         const int q0 = pw * prm.tw, p0 = ph * prm.th, n0 = pn * prm.tn;
-        int rr = 0, ss = 0, cb = 0;     // k-block cursor: (r, s, channel block), channel block fastest
+        // k-block cursor (r, s, channel block), channel block fastest. Every CTA starts at a different k-block (the accumulation order is free): all
+        // 148 CTAs would otherwise request the same weight slab from the same L2 slice at the same time.
+        const int kstart = (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)num_kb);
+        int cb = kstart % cblocks, ss = (kstart / cblocks) % prm.s, rr = kstart / (cblocks * prm.s);
         for (int kb0 = 0; kb0 < num_kb; kb0 += G) {
           const int cnt = min(G, num_kb - kb0);
           mbar_wait(empty(stage), phase ^ 1u);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
           for (int j = 0; j < cnt; ++j) {
             tma_load_4d(slab_a(stage, j), &map_x, full(stage), cb * BLOCK_K, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
             tma_load_2d(slab_b(stage, j), &map_w, full(stage), (rr * prm.s + ss) * prm.c + cb * BLOCK_K, nt * N_TILE);
-            if (++cb == cblocks) { cb = 0; if (++ss == prm.s) { ss = 0; ++rr; } }
+            if (++cb == cblocks) { cb = 0; if (++ss == prm.s) { ss = 0; if (++rr == prm.r) rr = 0; } }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -603,18 +606,22 @@ struct WgradParams {
 constexpr int WG_SLAB = BLOCK_M * 128;   // one TMA box: 128 pixel rows x 128 B = 16 KB
 constexpr int WG_MAX_S = 3;
 
+constexpr int WG_NA = 3, WG_NB = 6;   // dy-tile slots (2 slabs = 32 KB each) and x-tap slots (16 KB each): 192 KB in flight
+
 template <int S_TAPS>
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams prm) {
-  constexpr int kStages = 2;
-  constexpr int STAGE_BYTES = (2 + S_TAPS) * WG_SLAB;
   constexpr int TMEM_COLS = S_TAPS * 64 <= 64 ? 64 : (S_TAPS * 64 <= 128 ? 128 : 256);
+  constexpr int A_BYTES = 2 * WG_SLAB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + kStages * STAGE_BYTES;
-  auto full = [&](int i) { return bars + 8u * i; };
-  auto empty = [&](int i) { return bars + 8u * (kStages + i); };
-  const uint32_t done = bars + 8u * (2 * kStages);
-  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 1);
+  const uint32_t smem_a = base, smem_b = base + WG_NA * A_BYTES;
+  const uint32_t bars = smem_b + WG_NB * WG_SLAB;
+  auto afull = [&](int i) { return bars + 8u * i; };
+  auto aempty = [&](int i) { return bars + 8u * (WG_NA + i); };
+  auto bfull = [&](int i) { return bars + 8u * (2 * WG_NA + i); };
+  auto bempty = [&](int i) { return bars + 8u * (2 * WG_NA + WG_NB + i); };
+  const uint32_t done = bars + 8u * (2 * WG_NA + 2 * WG_NB);
+  const uint32_t tmem_slot = done + 8u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // work unit
@@ -625,7 +632,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
   const int my_tiles = split < prm.pixel_tiles ? (prm.pixel_tiles - split + prm.splits - 1) / prm.splits : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    for (int i = 0; i < WG_NA; ++i) { mbar_init(afull(i), 1); mbar_init(aempty(i), 1); }
+    for (int i = 0; i < WG_NB; ++i) { mbar_init(bfull(i), 1); mbar_init(bempty(i), 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -640,44 +648,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+    if (lane == 0) {   // ===== producer: per pixel tile one dy tile (A ring) then its S column-shifted x tiles (B ring)
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+      // CTAs of different units walk the same pixel tiles: start each unit at a different tile so that concurrently running CTAs do not all pull the
+      // same lines out of one L2 slice at the same moment (measured 3x slower on the 7x7 maps when they did)
+      const int rot = my_tiles > 0 ? (int)(((unsigned)(blockIdx.x / prm.splits) * 2654435761u) % (unsigned)my_tiles) : 0;
       for (int i = 0; i < my_tiles; ++i) {
-        int pt = split + i * prm.splits;
+        int it = i + rot; if (it >= my_tiles) it -= my_tiles;
+        int pt = split + it * prm.splits;
         const int pw = pt % prm.tiles_w; pt /= prm.tiles_w;
         const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
         const int q0 = pw * prm.tw, p0 = ph * prm.th, n0 = pn * prm.tn;
-        mbar_wait(empty(stage), phase ^ 1u);
-        mbar_expect_tx(full(stage), STAGE_BYTES);
-        const uint32_t sb = base + stage * STAGE_BYTES;
-        tma_load_4d(sb, &map_dy, full(stage), kt * 128, q0, p0, n0);
-        tma_load_4d(sb + WG_SLAB, &map_dy, full(stage), kt * 128 + 64, q0, p0, n0);       // zero-filled when k has only 64 channels
+        mbar_wait(aempty(as), aph ^ 1u);
+        mbar_expect_tx(afull(as), A_BYTES);
+        tma_load_4d(smem_a + as * A_BYTES, &map_dy, afull(as), kt * 128, q0, p0, n0);
+        tma_load_4d(smem_a + as * A_BYTES + WG_SLAB, &map_dy, afull(as), kt * 128 + 64, q0, p0, n0);    // zero-filled when k has only 64 channels
+        if (++as == WG_NA) { as = 0; aph ^= 1u; }
 #pragma unroll
-        for (int ss = 0; ss < S_TAPS; ++ss)
-          tma_load_4d(sb + (2 + ss) * WG_SLAB, &map_x, full(stage), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        for (int ss = 0; ss < S_TAPS; ++ss) {
+          mbar_wait(bempty(bs), bph ^ 1u);
+          mbar_expect_tx(bfull(bs), WG_SLAB);
+          tma_load_4d(smem_b + bs * WG_SLAB, &map_x, bfull(bs), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
+          if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0) {   // ===== MMA issuer
       constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
-      int stage = 0; uint32_t phase = 0;
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(full(stage), phase);
+        mbar_wait(afull(as), aph);
         tc_fence_after();
-        const uint32_t sb = base + stage * STAGE_BYTES;
+        const uint32_t sa = smem_a + as * A_BYTES;
 #pragma unroll
         for (int ss = 0; ss < S_TAPS; ++ss) {
+          mbar_wait(bfull(bs), bph);
+          tc_fence_after();
+          const uint32_t sb = smem_b + bs * WG_SLAB;
 #pragma unroll
           for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {
             // MN-major: 16 pixel rows per MMA = 2048 B; SBO = 1024 B between 8-row groups; LBO = one slab between the two 64-channel atoms of k
-            const uint64_t adesc = make_desc(sb + ks * UMMA_K * 128, WG_SLAB, 1024);
-            const uint64_t bdesc = make_desc(sb + (2 + ss) * WG_SLAB + ks * UMMA_K * 128, WG_SLAB, 1024);
+            const uint64_t adesc = make_desc(sa + ks * UMMA_K * 128, WG_SLAB, 1024);
+            const uint64_t bdesc = make_desc(sb + ks * UMMA_K * 128, WG_SLAB, 1024);
             umma_bf16(tmem_base + (uint32_t)(ss * 64), adesc, bdesc, idesc, (i | ks) != 0);
           }
+          umma_commit(bempty(bs));
+          if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
         }
-        umma_commit(empty(stage));
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        umma_commit(aempty(as));
+        if (++as == WG_NA) { as = 0; aph ^= 1u; }
       }
       umma_commit(done);
     }
@@ -696,7 +716,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
         if (krow < prm.k) {
           float* dst = prm.dw + (((size_t)krow * prm.r + rr) * prm.s + ss) * prm.c + ct * 64 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic operations
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                         "f"(__uint_as_float(v[j + 3])) : "memory");
         }
       }
     }
@@ -712,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
 template <int S_TAPS>
 static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& prm, int grid, cudaStream_t st) {
   auto kern = conv_wgrad_tc_kernel<S_TAPS>;
-  const size_t smem = 1024 + 2 * (size_t)(2 + S_TAPS) * WG_SLAB + 256;
+  const size_t smem = 1024 + (size_t)WG_NA * 2 * WG_SLAB + (size_t)WG_NB * WG_SLAB + 256;
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   kern<<<grid, kThreads, smem, st>>>(mdy, mx, prm);
@@ -742,9 +764,17 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
   prm.pixel_tiles = (int)ptiles;
   prm.k_tiles = (s->k + 127) / 128; prm.c_tiles = s->c / 64;
   const int units = prm.k_tiles * s->r * prm.c_tiles;
-  int splits = (2 * num_sms() + units - 1) / units;        // about two waves of CTAs
-  if (splits > prm.pixel_tiles) splits = prm.pixel_tiles;
-  if (splits < 1) splits = 1;
+  // One CTA per SM fits (192 KB of shared memory): pick the pixel split that minimises (waves of CTAs) x (pixel tiles per CTA + fixed cost) — e.g.
+  // 3 units x 49 splits = 147 CTAs in one wave, never 297 CTAs in two waves plus a one-CTA tail.
+  int splits = 1;
+  long long best_cost = -1;
+  const int max_splits = prm.pixel_tiles < 4 * num_sms() ? prm.pixel_tiles : 4 * num_sms();
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const long long waves = ((long long)units * sp + num_sms() - 1) / num_sms();
+    const long long cost = waves * ((prm.pixel_tiles + sp - 1) / sp + 5);   // + 5: a CTA's prologue + atomic epilogue cost about 5 pixel tiles (measured, 6.8 us vs 1.3 us)
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+  }
+  if (const char* e = getenv("DCV_WGRAD_SPLITS")) { const int v = atoi(e); if (v >= 1 && v <= prm.pixel_tiles) splits = v; }   // tuning aid
   prm.splits = splits;
   prm.dw = dw;
   cudaMemsetAsync(dw, 0, (size_t)s->k * s->r * s->s * s->c * sizeof(float), st);
