@@ -147,6 +147,104 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a)
   }
 }
 
+
+// Streaming path for NHWC output with c_out == c and out_w % 8 == 0 (every shape of the benchmark configs): no shared-memory staging, no block
+// barriers. A thread produces 8 consecutive output pixels: their 8 source pixels are contiguous in the source row (reversed when flipped), so the 8*C
+// source bytes are fetched as 2C+1 aligned 32-bit words (consecutive lanes read consecutive 8*C-byte windows => coalesced) and funnel-shifted to the
+// byte offset the crop asks for. The channel of every element is a compile-time constant; values come from the 256-entry-per-channel table
+// ((v/255 - mean)/std evaluated with IEEE division in torchvision's operation order, R bank-spread replicas). Windows that touch the zero padding
+// take a per-pixel path (only at the crop border).
+template <typename T, int C, int R>
+__global__ void __launch_bounds__(256) preprocess_stream_kernel(const PreprocessArgs a, const size_t total_items) {
+  constexpr int VE = 16 / sizeof(T), NE = 8 * C, NW = 2 * C;
+  __shared__ float lut[C * 256 * R];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int e = tid; e < C * 256; e += blockDim.x) {
+    const int ch = e >> 8, v = e & 255;
+    const float val = ((float)v / 255.0f - a.mean[ch]) / a.stdv[ch];   // ToTensor then Normalize, same op order
+#pragma unroll
+    for (int r = 0; r < R; ++r) lut[e * R + r] = val;
+  }
+  __syncthreads();
+  const int gpr = a.out_w >> 3;
+  const size_t in_row_bytes = (size_t)a.w * C;
+  for (size_t it = (size_t)blockIdx.x * blockDim.x + tid; it < total_items; it += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t row_lin = (uint32_t)(it / gpr);
+    const int gx = (int)(it - (size_t)row_lin * gpr);
+    const int img = a.div_vec_per_row.div(row_lin), i = row_lin - img * a.out_h;        // div_vec_per_row holds out_h here
+    const int top = a.crop_yx ? a.crop_yx[2 * img] : a.pad;
+    const int left = a.crop_yx ? a.crop_yx[2 * img + 1] : a.pad;
+    const bool flip = a.flip ? (a.flip[img] != 0) : false;
+    const int r_src = top + i - a.pad;
+    const int j0 = gx << 3;
+    const int px0 = (flip ? (a.out_w - 8 - j0) : j0) + left - a.pad;                     // first (lowest-address) source pixel of the window
+    uint32_t w[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) w[k] = 0u;
+    if (r_src >= 0 && r_src < a.h) {
+      const uint8_t* row = a.src + ((size_t)img * a.h + r_src) * in_row_bytes;
+      if (px0 >= 0 && px0 + 8 <= a.w) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)px0 * C;
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
+        const int mis = (int)(addr & 3);
+        uint32_t raw[NW + 1];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) raw[k] = __ldg(al + k);
+        raw[NW] = mis ? __ldg(al + NW) : 0u;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(raw[k], raw[k + 1], mis * 8);
+      } else {
+#pragma unroll
+        for (int pxl = 0; pxl < 8; ++pxl) {
+          const int px = px0 + pxl;
+          if (px >= 0 && px < a.w) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              const int kb = pxl * C + ch;
+              w[kb >> 2] |= (uint32_t)row[(size_t)px * C + ch] << (8 * (kb & 3));
+            }
+          }
+        }
+      }
+    }
+    float vals[NE];
+    if (flip) {
+#pragma unroll
+      for (int pxl = 0; pxl < 8; ++pxl)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          const int kb = (7 - pxl) * C + ch;
+          vals[pxl * C + ch] = lut[(ch * 256 + ((w[kb >> 2] >> (8 * (kb & 3))) & 0xffu)) * R + (R == 1 ? 0 : (lane & (R - 1)))];
+        }
+    } else {
+#pragma unroll
+      for (int pxl = 0; pxl < 8; ++pxl)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          const int kb = pxl * C + ch;
+          vals[pxl * C + ch] = lut[(ch * 256 + ((w[kb >> 2] >> (8 * (kb & 3))) & 0xffu)) * R + (R == 1 ? 0 : (lane & (R - 1)))];
+        }
+    }
+    T* dst = reinterpret_cast<T*>(a.dst) + ((size_t)row_lin * a.out_w + j0) * C;
+#pragma unroll
+    for (int v = 0; v < NE / VE; ++v) __stcs(reinterpret_cast<uint4*>(dst + v * VE), vec_pack<T>(vals + v * VE));   // streaming store: written once, read by the next kernel from L2/HBM
+  }
+}
+
+template <typename T, int C>
+static int launch_preprocess_fast(PreprocessArgs a, cudaStream_t st) {
+  constexpr int R = 8;                                           // 256 * C * 8 floats <= 32 KB of static shared memory
+  a.div_vec_per_row = FastDiv(a.out_h);
+  const size_t total_items = (size_t)a.n * a.out_h * (a.out_w >> 3);
+  DCV_REQUIRE((size_t)a.n * a.out_h < (1u << 31), "preprocess_u8: too many rows");
+  size_t blocks = (total_items + 255) / 256;
+  const size_t max_grid = (size_t)kNumSMs * 8;                   // persistent, 8 CTAs of 256 threads per SM (40 registers, 24 KB table): the table is filled once per CTA
+  if (blocks > max_grid) blocks = max_grid;
+  preprocess_stream_kernel<T, C, R><<<(unsigned)blocks, 256, 0, st>>>(a, total_items);
+  DCV_LAUNCH_CHECK("preprocess_stream_kernel");
+  return 0;
+}
+
 // Scalar variant for shapes whose rows are not a whole number of 16-byte vectors.
 template <typename T>
 __global__ void preprocess_scalar_kernel(const PreprocessArgs a) {
@@ -189,6 +287,20 @@ extern "C" int dcv_preprocess_u8(const uint8_t* src, void* dst, int n, int h, in
   const int row_elems = nchw_out ? out_w : out_w * c_out;
   const bool vec_ok = (row_elems % ve == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 4 == 0);
   cudaStream_t st = as_stream(stream);
+  if (vec_ok && !nchw_out && c_out == c && out_w % 8 == 0 && out_w >= 8) {
+    if (out_dtype == DCV_BF16) {
+      if (c == 1) return launch_preprocess_fast<__nv_bfloat16, 1>(a, st);
+      if (c == 2) return launch_preprocess_fast<__nv_bfloat16, 2>(a, st);
+      if (c == 3) return launch_preprocess_fast<__nv_bfloat16, 3>(a, st);
+      return launch_preprocess_fast<__nv_bfloat16, 4>(a, st);
+    }
+    if (out_dtype == DCV_F32) {
+      if (c == 1) return launch_preprocess_fast<float, 1>(a, st);
+      if (c == 2) return launch_preprocess_fast<float, 2>(a, st);
+      if (c == 3) return launch_preprocess_fast<float, 3>(a, st);
+      return launch_preprocess_fast<float, 4>(a, st);
+    }
+  }
   if (!vec_ok) {
     const size_t total = (size_t)n * out_h * out_w * c_out;
     DCV_DISPATCH_DTYPE(out_dtype, T, (preprocess_scalar_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(a)));
