@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a)
 // take a per-pixel path (only at the crop border).
 template <typename T, int C, int R>
 __global__ void __launch_bounds__(256) preprocess_stream_kernel(const PreprocessArgs a, const size_t total_items) {
-  constexpr int VE = 16 / sizeof(T), NE = 8 * C, NW = 2 * C;
-  __shared__ float lut[C * 256 * R];
+  constexpr int VE = 16 / sizeof(T), NE = 8 * C, NW = 2 * C, NL = (8 * C + 30) / 16;   // NL: 128-bit loads covering any alignment of the window
+  extern __shared__ __align__(16) float lut[];   // [C][256][R]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int e = tid; e < C * 256; e += blockDim.x) {
     const int ch = e >> 8, v = e & 255;
@@ -183,16 +183,35 @@ __global__ void __launch_bounds__(256) preprocess_stream_kernel(const Preprocess
     for (int k = 0; k < NW; ++k) w[k] = 0u;
     if (r_src >= 0 && r_src < a.h) {
       const uint8_t* row = a.src + ((size_t)img * a.h + r_src) * in_row_bytes;
-      if (px0 >= 0 && px0 + 8 <= a.w) {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)px0 * C;
-        const uint32_t* al = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
-        const int mis = (int)(addr & 3);
-        uint32_t raw[NW + 1];
+      const size_t win_off = ((size_t)img * a.h + r_src) * in_row_bytes + (size_t)(px0 > 0 ? px0 : 0) * C;
+      if (px0 >= 0 && px0 + 8 <= a.w && (win_off & ~size_t(15)) + 16 * NL <= a.src_total_bytes) {
+        // NL aligned 128-bit loads cover the 8*C-byte window at any byte alignment (the ncu profile of the 32-bit version showed the L1TEX pipe at
+        // 90 %: 6.6 sectors fetched per useful sector); the window is then funnel-shifted out of them. `mw` takes at most two values in a warp.
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(a.src) + win_off;
+        const uint4* al = reinterpret_cast<const uint4*>(addr & ~uintptr_t(15));
+        const int mw = (int)(addr & 15) >> 2, mis = (int)(addr & 3) * 8;
+        uint32_t raw[4 * NL + 1];
 #pragma unroll
-        for (int k = 0; k < NW; ++k) raw[k] = __ldg(al + k);
-        raw[NW] = mis ? __ldg(al + NW) : 0u;
+        for (int k = 0; k < NL; ++k) { const uint4 v4 = __ldg(al + k); raw[4 * k] = v4.x; raw[4 * k + 1] = v4.y; raw[4 * k + 2] = v4.z; raw[4 * k + 3] = v4.w; }
+        raw[4 * NL] = 0u;
+        switch (mw) {
+          case 0:
 #pragma unroll
-        for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(raw[k], raw[k + 1], mis * 8);
+            for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(raw[k], raw[k + 1], mis);
+            break;
+          case 1:
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(raw[k + 1], raw[k + 2], mis);
+            break;
+          case 2:
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(raw[k + 2], raw[k + 3], mis);
+            break;
+          default:
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(raw[k + 3], raw[k + 4], mis);
+            break;
+        }
       } else {
 #pragma unroll
         for (int pxl = 0; pxl < 8; ++pxl) {
@@ -233,14 +252,20 @@ __global__ void __launch_bounds__(256) preprocess_stream_kernel(const Preprocess
 
 template <typename T, int C>
 static int launch_preprocess_fast(PreprocessArgs a, cudaStream_t st) {
-  constexpr int R = 8;                                           // 256 * C * 8 floats <= 32 KB of static shared memory
+  // Table replicas: lane l reads replica l % R, i.e. bank (byte % (32/R)) * R + l % R. ncu on R = 8: 7.6 extra shared wavefronts per lookup and the
+  // L1TEX pipe at 90 %; R = 16 leaves a 2-way conflict only between lanes l and l+16 that look up bytes of the same parity (48 KB for 3 channels).
+  constexpr int R = 16;
   a.div_vec_per_row = FastDiv(a.out_h);
   const size_t total_items = (size_t)a.n * a.out_h * (a.out_w >> 3);
   DCV_REQUIRE((size_t)a.n * a.out_h < (1u << 31), "preprocess_u8: too many rows");
   size_t blocks = (total_items + 255) / 256;
-  const size_t max_grid = (size_t)kNumSMs * 8;                   // persistent, 8 CTAs of 256 threads per SM (40 registers, 24 KB table): the table is filled once per CTA
+  const size_t smem = (size_t)C * 256 * R * sizeof(float);
+  auto kern = preprocess_stream_kernel<T, C, R>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t per_sm = (220 * 1024) / smem < 8 ? (220 * 1024) / smem : 8;
+  const size_t max_grid = (size_t)kNumSMs * per_sm;              // persistent CTAs: the table is filled once per CTA
   if (blocks > max_grid) blocks = max_grid;
-  preprocess_stream_kernel<T, C, R><<<(unsigned)blocks, 256, 0, st>>>(a, total_items);
+  kern<<<(unsigned)blocks, 256, smem, st>>>(a, total_items);
   DCV_LAUNCH_CHECK("preprocess_stream_kernel");
   return 0;
 }

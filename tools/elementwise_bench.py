@@ -17,7 +17,11 @@ from deepcv_b200._lib import ACT_LEAKY_RELU, DCV_BF16, DCV_F32, ConvShape, check
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def timeit(fn, reps, iters=3):
+ITERS = 3
+
+
+def timeit(fn, reps, iters=None):
+    iters = ITERS if iters is None else iters
     fn(0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -34,7 +38,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--what', default='norm,pool,preprocess,im2col')
     ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--sizes', default='32,64,128,224,256,512,1024')
+    ap.add_argument('--iters', type=int, default=3)
     args = ap.parse_args()
+    global ITERS
+    ITERS = args.iters
     peak = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())['hbm_gbs'] if (ROOT / 'MEASURED_PEAKS.json').exists() else 6650.0
     dev = torch.device('cuda')
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -73,7 +81,7 @@ def main():
     if 'preprocess' in what:
         mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
         std = torch.tensor([0.229, 0.224, 0.225], device=dev)
-        for size in (32, 64, 128, 224, 256, 512, 1024):
+        for size in [int(v) for v in args.sizes.split(',')]:
             for out_dt, tdt, es in ((DCV_BF16, torch.bfloat16, 2), (DCV_F32, torch.float32, 4)):
                 n = max(4, int(1024e6 // (size * size * 3 * (1 + es))))
                 n = min(n, 262144)
