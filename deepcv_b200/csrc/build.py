@@ -11,7 +11,7 @@ PKG = CSRC.parent
 OUT = PKG / 'libdeepcv_b200.so'
 OBJ_DIR = CSRC / 'build'
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '--threads', '2']
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '--threads', '2', *os.environ.get('DCV_NVCC_FLAGS', '').split()]
 
 
 def _stamp(src: Path) -> str:

@@ -48,30 +48,34 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, TD* __restrict__
 // col[n][p][q][kpad]: entries (r, s, c) of the receptive field of output pixel (p, q) in the order of the [K][R][S][C] weight layout, zero
 // padded from R*S*C to kpad. One thread per 16-byte output vector: the (cached, redundant) gathers are scalar, the 1.2 GB-class store is coalesced.
 template <typename T>
-__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, const dcv_conv_shape s, const int kpad) {
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, const dcv_conv_shape s, const int kpad, const FastDiv div_vpp, const FastDiv div_q, const FastDiv div_p,
+                              const FastDiv div_sc, const FastDiv div_c) {
   constexpr int VE = 16 / sizeof(T);
   const int vec_per_pix = kpad / VE, rsc = s.r * s.s * s.c, sc = s.s * s.c;
-  const size_t total = (size_t)s.n * s.p * s.q * vec_per_pix;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % vec_per_pix);
-    size_t t = idx / vec_per_pix;
-    const int oq = (int)(t % s.q); t /= s.q;
-    const int op = (int)(t % s.p); const int img = (int)(t / s.p);
+  const uint32_t total = (uint32_t)((size_t)s.n * s.p * s.q * vec_per_pix);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    uint32_t t = div_vpp.div(idx);
+    const int v = (int)(idx - t * vec_per_pix);
+    uint32_t t2 = div_q.div(t);
+    const int oq = (int)(t - t2 * s.q);
+    const int img = (int)div_p.div(t2), op = (int)(t2 - (uint32_t)img * s.p);
     const int iy0 = op * s.stride_h - s.pad_h, ix0 = oq * s.stride_w - s.pad_w;
     const T* xin = x + (size_t)img * s.h * s.w * s.c;
+    // (r, s, c) of the first element by division, of the following ones by carry
+    int kk = v * VE;
+    int rr = (int)div_sc.div((uint32_t)kk), rem = kk - rr * sc, ss = (int)div_c.div((uint32_t)rem), cc = rem - ss * s.c;
     float vals[VE];
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
-      const int kk = v * VE + e;
       float val = 0.f;
-      if (kk < rsc) {
-        const int rr = kk / sc, rem = kk - rr * sc, ss = rem / s.c, cc = rem - ss * s.c;
+      if (kk + e < rsc) {
         const int iy = iy0 + rr * s.dil_h, ix = ix0 + ss * s.dil_w;
-        if (iy >= 0 && iy < s.h && ix >= 0 && ix < s.w) val = to_f<T>(xin[((size_t)iy * s.w + ix) * s.c + cc]);
+        if (iy >= 0 && iy < s.h && ix >= 0 && ix < s.w) val = to_f<T>(__ldg(xin + ((size_t)iy * s.w + ix) * s.c + cc));
       }
       vals[e] = val;
+      if (++cc == s.c) { cc = 0; if (++ss == s.s) { ss = 0; ++rr; } }
     }
-    *reinterpret_cast<uint4*>(col + idx * VE) = vec_pack<T>(vals);
+    __stcs(reinterpret_cast<uint4*>(col + (size_t)idx * VE), vec_pack<T>(vals));
   }
 }
 
@@ -129,7 +133,9 @@ int dcv_im2col(const dcv_conv_shape* shape, const void* x, void* col, int kpad, 
   DCV_REQUIRE(kpad >= shape->r * shape->s * shape->c && kpad % ve == 0 && reinterpret_cast<uintptr_t>(col) % 16 == 0, "im2col: kpad=%d must cover r*s*c=%d and be a multiple of %d", kpad,
               shape->r * shape->s * shape->c, ve);
   const size_t total = (size_t)shape->n * shape->p * shape->q * (kpad / ve);
-  DCV_DISPATCH_DTYPE(dtype, T, (im2col_kernel<T><<<grid_for(total, 256, kNumSMs * 32), 256, 0, as_stream(stream)>>>((const T*)x, (T*)col, *shape, kpad)));
+  DCV_REQUIRE(total < (1ull << 31), "im2col: %zu output vectors exceed the 32-bit index range", total);
+  const FastDiv d_vpp(kpad / ve), d_q(shape->q), d_p(shape->p), d_sc(shape->s * shape->c), d_c(shape->c);
+  DCV_DISPATCH_DTYPE(dtype, T, (im2col_kernel<T><<<grid_for(total, 256, kNumSMs * 32), 256, 0, as_stream(stream)>>>((const T*)x, (T*)col, *shape, kpad, d_vpp, d_q, d_p, d_sc, d_c)));
   DCV_LAUNCH_CHECK("im2col_kernel");
   return 0;
 }

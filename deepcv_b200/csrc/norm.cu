@@ -55,11 +55,13 @@ template <typename T, int VE> __device__ __forceinline__ void store_vec(T* p, co
   else *reinterpret_cast<uint4*>(p) = vec_pack<T>(in);
 }
 
-// Reduces `NV` per-thread values per column element across the `rows` threads that share a column, then one atomicAdd per
-// element into dst[elem * dst_stride + v] (dst_stride >= NV).
+// Reduces `NV` per-thread values per column element across the `rows` threads that share a column, then atomicAdd per element into
+// dst_cta[(colg * VE + e) * dst_stride + v] (dst_stride >= NV; dst_cta = the image's / tensor's base). ALL threads take part in the cross-row sum: the
+// outputs (column, v, e) are spread over the threads and, when there are fewer outputs than threads, the rows are split into slices (one atomic per slice).
+// (A first version let the `row == 0` threads add up all rows serially: 512 dependent shared loads per CTA, ~8 us of tail on a 36 us kernel.)
 template <int VE, int NV>
-__device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, int colg, float* dst_col0, int dst_stride) {
-  __shared__ float red[256 * 16];  // [row][col][VE*NV] flattened; VE*NV <= 16
+__device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, float* dst_cta, int dst_stride) {
+  __shared__ float red[256 * 16];  // [row][col][NV*VE] flattened; VE*NV <= 16
   constexpr int PER = VE * NV;
   static_assert(PER <= 16, "column_reduce_atomic: too many values per thread");
   const int t = row * g.cols_per_block + col;
@@ -68,17 +70,34 @@ __device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcG
 #pragma unroll
     for (int e = 0; e < VE; ++e) red[t * PER + v * VE + e] = acc[v][e];
   __syncthreads();
-  if (row == 0 && colg < g.cv) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        float s = 0.f;
-        for (int r = 0; r < g.rows; ++r) s += red[(r * g.cols_per_block + col) * PER + v * VE + e];
-        atomicAdd(dst_col0 + (size_t)e * dst_stride + v, s);
-      }
+  const int outs = g.cols_per_block * PER, nthr = blockDim.x;
+  const int parts = outs < nthr ? nthr / outs : 1;
+  for (int o = threadIdx.x; o < outs * parts; o += nthr) {
+    const int part = o / outs, oo = o - part * outs;
+    const int cl = oo / PER, k = oo - cl * PER, v = k / VE, e = k - v * VE;
+    const int colg = blockIdx.z * g.cols_per_block + cl;
+    if (colg >= g.cv) continue;
+    float s = 0.f;
+    for (int r = part; r < g.rows; r += parts) s += red[(r * g.cols_per_block + cl) * PER + k];
+    atomicAdd(dst_cta + ((size_t)colg * VE + e) * dst_stride + v, s);
   }
 }
+
+// Raw (not yet unpacked) 16-byte vector or scalar element: lets the streaming loops below issue UNR independent loads before touching any of them.
+template <typename T, int VE> struct Raw { uint4 v; };
+template <typename T> struct Raw<T, 1> { T v; };
+template <typename T, int VE> __device__ __forceinline__ Raw<T, VE> load_raw(const T* p) {
+  Raw<T, VE> r;
+  if constexpr (VE == 1) r.v = *p; else r.v = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+template <typename T, int VE> __device__ __forceinline__ void unpack_raw(const Raw<T, VE>& r, float* out) {
+  if constexpr (VE == 1) out[0] = to_f<T>(r.v); else vec_unpack<T>(r.v, out);
+}
+#ifndef DCV_UNR
+#define DCV_UNR 4
+#endif
+constexpr int UNR = DCV_UNR;   // pixels in flight per thread: the bf16 kernels were latency-bound at ~45 % of HBM with one load per iteration
 
 // ---- statistics: stats[n][c][2] += {sum y, sum y^2}
 template <typename T, int VE>
@@ -91,14 +110,27 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, flo
   for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
   if (colg < g.cv) {
     const T* base = y + ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-    for (int p = p0 + row; p < p1; p += g.rows) {
+    int p = p0 + row;
+    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+      Raw<T, VE> r[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.c);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float v[VE];
+        unpack_raw<T, VE>(r[u], v);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
+      }
+    }
+    for (; p < p1; p += g.rows) {
       float v[VE];
       load_vec<T, VE>(base + (size_t)p * g.c, v);
 #pragma unroll
       for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
     }
   }
-  column_reduce_atomic<VE, 2>(acc, g, col, row, colg, stats + ((size_t)img * g.c + (size_t)colg * VE) * 2, 2);
+  column_reduce_atomic<VE, 2>(acc, g, col, row, stats + (size_t)img * g.c * 2, 2);
 }
 
 // ---- forward apply: z = A*y + B
@@ -113,7 +145,21 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
 #pragma unroll
   for (int e = 0; e < VE; ++e) { A[e] = abp[2 * e]; B[e] = abp[2 * e + 1]; }
   const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-  for (int p = p0 + row; p < p1; p += g.rows) {
+  int p = p0 + row;
+  for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+    Raw<T, VE> r[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.c);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float v[VE];
+      unpack_raw<T, VE>(r[u], v);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
+      store_vec<T, VE>(z + base + (size_t)(p + u * g.rows) * g.c, v);
+    }
+  }
+  for (; p < p1; p += g.rows) {
     float v[VE];
     load_vec<T, VE>(y + base + (size_t)p * g.c, v);
 #pragma unroll
@@ -133,7 +179,20 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
   for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
   if (colg < g.cv) {
     const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-    for (int p = p0 + row; p < p1; p += g.rows) {
+    int p = p0 + row;
+    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+      Raw<T, VE> ra[UNR], rb[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.c); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.c); }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float a[VE], b[VE];
+        unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
+      }
+    }
+    for (; p < p1; p += g.rows) {
       float a[VE], b[VE];
       load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
       load_vec<T, VE>(y + base + (size_t)p * g.c, b);
@@ -141,13 +200,20 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
       for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
     }
   }
-  column_reduce_atomic<VE, 2>(acc, g, col, row, colg, s + ((size_t)img * g.c + (size_t)colg * VE) * 2, 2);
+  column_reduce_atomic<VE, 2>(acc, g, col, row, s + (size_t)img * g.c * 2, 2);
 }
 
-// ---- backward apply: dy = act'(y) * (P*dz + Q*y + R); dbias[c] += sum dy
-template <typename T, int VE>
+// ---- backward apply: dy = act'(y) * (P*dz + Q*y + R); dbias[c] += sum dy. The activation is a template parameter: no per-element switch.
+template <int ACT> __device__ __forceinline__ float act_grad_t(float y, float slope) {
+  if (ACT == DCV_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (ACT == DCV_ACT_LEAKY_RELU) return y > 0.f ? 1.f : slope;
+  if (ACT == DCV_ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+
+template <typename T, int VE, int ACT>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ pqr,
-                                                        T* __restrict__ dy, float* __restrict__ dbias, int act, float slope, const NcGeom g) {
+                                                        T* __restrict__ dy, float* __restrict__ dbias, float slope, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
   const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
@@ -165,20 +231,35 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz
       for (int e = 0; e < VE; ++e) { P[e] = 1.f; Q[e] = 0.f; R[e] = 0.f; }
     }
     const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-    for (int p = p0 + row; p < p1; p += g.rows) {
-      float a[VE], b[VE];
-      load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
-      load_vec<T, VE>(y + base + (size_t)p * g.c, b);
+    auto one = [&](float* a, const float* b, size_t off) {
 #pragma unroll
       for (int e = 0; e < VE; ++e) {
         const float pre = fmaf(P[e], a[e], fmaf(Q[e], b[e], R[e]));
-        a[e] = pre * act_grad_from_output(b[e], act, slope);
+        a[e] = pre * act_grad_t<ACT>(b[e], slope);
         acc[0][e] += a[e];
       }
-      store_vec<T, VE>(dy + base + (size_t)p * g.c, a);
+      store_vec<T, VE>(dy + off, a);
+    };
+    int p = p0 + row;
+    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+      Raw<T, VE> ra[UNR], rb[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.c); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.c); }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float a[VE], b[VE];
+        unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+        one(a, b, base + (size_t)(p + u * g.rows) * g.c);
+      }
+    }
+    for (; p < p1; p += g.rows) {
+      float a[VE], b[VE];
+      load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
+      load_vec<T, VE>(y + base + (size_t)p * g.c, b);
+      one(a, b, base + (size_t)p * g.c);
     }
   }
-  if (dbias) column_reduce_atomic<VE, 1>(acc, g, col, row, colg, dbias + (size_t)colg * VE, 1);
+  if (dbias) column_reduce_atomic<VE, 1>(acc, g, col, row, dbias, 1);
 }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -498,11 +579,19 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
   cudaStream_t st = as_stream(stream);
   if (dbias_c) cudaMemsetAsync(dbias_c, 0, (size_t)c * sizeof(float), st);
   dim3 grid; int block;
-  DCV_DISPATCH_DTYPE(dtype, T, {
-    constexpr int VE = 16 / sizeof(T);
-    if (vec_ok(dz, y, dy, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); bwd_apply_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, act, slope, g); }
-    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); bwd_apply_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, act, slope, g); }
-  });
+#define DCV_BWD_APPLY(ACT_)                                                                                                                                   \
+  DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                              \
+    constexpr int VE = 16 / sizeof(T);                                                                                                                        \
+    if (vec_ok(dz, y, dy, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); bwd_apply_kernel<T, VE, ACT_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g); } \
+    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); bwd_apply_kernel<T, 1, ACT_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g); }                      \
+  })
+  switch (act) {
+    case DCV_ACT_RELU: DCV_BWD_APPLY(DCV_ACT_RELU); break;
+    case DCV_ACT_LEAKY_RELU: DCV_BWD_APPLY(DCV_ACT_LEAKY_RELU); break;
+    case DCV_ACT_SIGMOID: DCV_BWD_APPLY(DCV_ACT_SIGMOID); break;
+    default: DCV_BWD_APPLY(DCV_ACT_NONE); break;
+  }
+#undef DCV_BWD_APPLY
   DCV_LAUNCH_CHECK("bwd_apply_kernel");
   return 0;
 }

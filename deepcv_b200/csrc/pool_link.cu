@@ -62,6 +62,31 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx,
   }
 }
 
+// Non-overlapping windows that tile the input exactly (kernel == stride, h % kh == 0, w % kw == 0: the 2x2/2 pooling of the specs): one thread per
+// OUTPUT-gradient vector reads it once and writes its kh x kw input positions — no per-input-pixel window search, dy is read once instead of kh*kw times.
+template <typename T, int VE>
+__global__ void avgpool_bwd_tiled_kernel(const T* __restrict__ dy, T* __restrict__ dx, int w, int c, int kh, int kw, const FastDiv div_cv, const FastDiv div_q, uint32_t total, int q) {
+  const int cv = c / VE;
+  const float inv = 1.f / (float)(kh * kw);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t t = div_cv.div(idx);
+    const int cc = (int)(idx - t * cv);
+    const uint32_t row = div_q.div(t);           // row = img * p + oy
+    const int ox = (int)(t - row * q);
+    float v[VE];
+    const T* src = dy + (size_t)idx * VE;
+    if constexpr (VE == 1) v[0] = to_f<T>(*src); else vec_unpack<T>(*reinterpret_cast<const uint4*>(src), v);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) v[e] *= inv;
+    T* dst = dx + (((size_t)row * kh) * w + (size_t)ox * kw) * c + (size_t)cc * VE;   // (img*p + oy) * kh == img*h + oy*kh because h == p*kh
+    for (int r = 0; r < kh; ++r)
+      for (int s2 = 0; s2 < kw; ++s2) {
+        T* d = dst + ((size_t)r * w + s2) * c;
+        if constexpr (VE == 1) *d = from_f<T>(v[0]); else *reinterpret_cast<uint4*>(d) = vec_pack<T>(v);
+      }
+  }
+}
+
 template <typename T, int VE>
 __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, float alpha, float beta, size_t nvec) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
@@ -194,6 +219,20 @@ int dcv_avgpool2d_bwd(const void* dy, void* dx, int n, int h, int w, int c, int 
   DCV_REQUIRE(dy && dx, "avgpool2d_bwd: null pointer");
   if (pool_check("avgpool2d_bwd", n, h, w, c, kh, kw, sh, sw, &p, &q)) return 1;
   cudaStream_t st = as_stream(stream);
+  if (kh == sh && kw == sw && h % kh == 0 && w % kw == 0 && (size_t)n * p * q * c < (1ull << 31)) {
+    DCV_DISPATCH_DTYPE(dtype, T, {
+      constexpr int VE = 16 / sizeof(T);
+      if (c % VE == 0 && aligned16(dy) && aligned16(dx)) {
+        const uint32_t total = (uint32_t)((size_t)n * p * q * (c / VE));
+        avgpool_bwd_tiled_kernel<T, VE><<<grid_for(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, w, c, kh, kw, FastDiv(c / VE), FastDiv(q), total, q);
+      } else {
+        const uint32_t total = (uint32_t)((size_t)n * p * q * c);
+        avgpool_bwd_tiled_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>((const T*)dy, (T*)dx, w, c, kh, kw, FastDiv(c), FastDiv(q), total, q);
+      }
+    });
+    DCV_LAUNCH_CHECK("avgpool_bwd_tiled_kernel");
+    return 0;
+  }
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
     if (c % VE == 0 && aligned16(dy) && aligned16(dx)) avgpool_bwd_kernel<T, VE><<<grid_for((size_t)n * h * w * (c / VE), 256), 256, 0, st>>>((const T*)dy, (T*)dx, n, h, w, c, p, q, kh, kw, sh, sw);

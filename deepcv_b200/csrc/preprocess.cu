@@ -17,19 +17,6 @@
 
 namespace dcv {
 
-struct FastDiv {  // n / d for 0 <= n < 2^31, d >= 1
-  uint32_t mul, shr, d;
-  __host__ FastDiv() : mul(0), shr(0), d(1) {}
-  __host__ explicit FastDiv(uint32_t d_) : d(d_) {
-    if (d_ == 1) { mul = 0; shr = 0; return; }
-    uint32_t l = 0;
-    while ((1u << l) < d_) ++l;
-    uint64_t m = ((uint64_t(1) << (31 + l)) + d_ - 1) / d_;  // ceil(2^(31+l) / d)
-    mul = (uint32_t)m; shr = l;                               // valid for n < 2^31
-  }
-  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (uint32_t)(((uint64_t)n * mul) >> 31) >> shr; }
-};
-
 struct PreprocessArgs {
   const uint8_t* src; void* dst;
   int n, h, w, c, out_h, out_w, pad, c_out, nchw_out, rg;   // rg: output rows per group
