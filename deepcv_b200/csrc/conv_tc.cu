@@ -606,7 +606,7 @@ struct WgradParams {
 constexpr int WG_SLAB = BLOCK_M * 128;   // one TMA box: 128 pixel rows x 128 B = 16 KB
 constexpr int WG_MAX_S = 3;
 
-constexpr int WG_NA = 3, WG_NB = 6;   // dy-tile slots (2 slabs = 32 KB each) and x-tap slots (16 KB each): 192 KB in flight
+constexpr int WG_NA = 3, WG_NB = 2;   // dy-tile slots (2 slabs = 32 KB each) and x slots (S_TAPS column-shifted slabs = up to 48 KB each): 192 KB in flight
 
 template <int S_TAPS>
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams prm) {
@@ -614,8 +614,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
   constexpr int A_BYTES = 2 * WG_SLAB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int B_BYTES = S_TAPS * WG_SLAB;
   const uint32_t smem_a = base, smem_b = base + WG_NA * A_BYTES;
-  const uint32_t bars = smem_b + WG_NB * WG_SLAB;
+  const uint32_t bars = smem_b + WG_NB * B_BYTES;
   auto afull = [&](int i) { return bars + 8u * i; };
   auto aempty = [&](int i) { return bars + 8u * (WG_NA + i); };
   auto bfull = [&](int i) { return bars + 8u * (2 * WG_NA + i); };
@@ -664,39 +665,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
         tma_load_4d(smem_a + as * A_BYTES, &map_dy, afull(as), kt * 128, q0, p0, n0);
         tma_load_4d(smem_a + as * A_BYTES + WG_SLAB, &map_dy, afull(as), kt * 128 + 64, q0, p0, n0);    // zero-filled when k has only 64 channels
         if (++as == WG_NA) { as = 0; aph ^= 1u; }
+        mbar_wait(bempty(bs), bph ^ 1u);
+        mbar_expect_tx(bfull(bs), B_BYTES);
 #pragma unroll
-        for (int ss = 0; ss < S_TAPS; ++ss) {
-          mbar_wait(bempty(bs), bph ^ 1u);
-          mbar_expect_tx(bfull(bs), WG_SLAB);
-          tma_load_4d(smem_b + bs * WG_SLAB, &map_x, bfull(bs), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
-          if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
-        }
+        for (int ss = 0; ss < S_TAPS; ++ss) tma_load_4d(smem_b + bs * B_BYTES + ss * WG_SLAB, &map_x, bfull(bs), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
+        if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ===== MMA issuer
-      constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+      // ONE MMA covers all S_TAPS taps: N = S_TAPS x 64, the taps' x slabs being the 64-element MN atoms of B, one slab (LBO) apart. Issuing the taps
+      // separately re-read the dy operand from shared memory once per tap (6 KB per 32 MMA cycles: shared-memory-read bound at 2/3 of the tensor rate).
+      constexpr uint32_t idesc = make_idesc(128, S_TAPS * 64, 1, 1);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         mbar_wait(afull(as), aph);
+        mbar_wait(bfull(bs), bph);
         tc_fence_after();
-        const uint32_t sa = smem_a + as * A_BYTES;
+        const uint32_t sa = smem_a + as * A_BYTES, sb = smem_b + bs * B_BYTES;
 #pragma unroll
-        for (int ss = 0; ss < S_TAPS; ++ss) {
-          mbar_wait(bfull(bs), bph);
-          tc_fence_after();
-          const uint32_t sb = smem_b + bs * WG_SLAB;
-#pragma unroll
-          for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {
-            // MN-major: 16 pixel rows per MMA = 2048 B; SBO = 1024 B between 8-row groups; LBO = one slab between the two 64-channel atoms of k
-            const uint64_t adesc = make_desc(sa + ks * UMMA_K * 128, WG_SLAB, 1024);
-            const uint64_t bdesc = make_desc(sb + ks * UMMA_K * 128, WG_SLAB, 1024);
-            umma_bf16(tmem_base + (uint32_t)(ss * 64), adesc, bdesc, idesc, (i | ks) != 0);
-          }
-          umma_commit(bempty(bs));
-          if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
+        for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {
+          // MN-major: 16 pixel rows per MMA = 2048 B; SBO = 1024 B between 8-row groups; LBO = one slab between 64-channel atoms (of k for A, of the taps for B)
+          const uint64_t adesc = make_desc(sa + ks * UMMA_K * 128, WG_SLAB, 1024);
+          const uint64_t bdesc = make_desc(sb + ks * UMMA_K * 128, WG_SLAB, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | ks) != 0);
         }
+        umma_commit(bempty(bs));
         umma_commit(aempty(as));
+        if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
         if (++as == WG_NA) { as = 0; aph ^= 1u; }
       }
       umma_commit(done);
@@ -734,7 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
 template <int S_TAPS>
 static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& prm, int grid, cudaStream_t st) {
   auto kern = conv_wgrad_tc_kernel<S_TAPS>;
-  const size_t smem = 1024 + (size_t)WG_NA * 2 * WG_SLAB + (size_t)WG_NB * WG_SLAB + 256;
+  const size_t smem = 1024 + (size_t)WG_NA * 2 * WG_SLAB + (size_t)WG_NB * S_TAPS * WG_SLAB + 256;
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   kern<<<grid, kThreads, smem, st>>>(mdy, mx, prm);

@@ -15,34 +15,52 @@
 
 namespace dcv {
 
-// Thread -> (column, row) mapping shared by the streaming kernels: a CTA owns `chunk` pixels of one image and
-// `cols_per_block` 16-byte (or scalar) columns; a thread keeps ONE column for its whole life so per-(n,c) coefficients
-// and partial sums live in registers.
+// Work decomposition shared by the streaming kernels. A tensor is n images of hw pixels of c channels (NHWC). It is walked as "vector rows": one row
+// = `span` contiguous elements = `cv` 16-byte vectors (scalars when the channel count / alignment does not allow vectors). Normally a row is one pixel
+// (span = c); when c is smaller than a vector and divides it (the 4-channel CIFAR layers in bf16) a row packs `pack` pixels (span = c * pack = one
+// vector) and element e of the vector belongs to channel e % c. The n * hwv rows are cut into equal contiguous ranges, one per CTA, with the CTA count
+// fitted to ONE resident wave (ncu on the first version: 768 CTAs on 740 slots = 1.04 waves, SMs idle 40 % of the kernel); a range may cross image
+// boundaries, the per-(image, channel) state is flushed / reloaded there. A thread keeps ONE column for its whole life.
 struct NcGeom {
-  int n, hw, c;
-  int cv;              // columns per pixel (c / VE)
+  int n, c;
+  int hwv;             // vector rows per image
+  int span;            // elements per vector row (c * pack)
+  int pack;            // pixels per vector row
+  int cv;              // vectors per row (span / VE)
   int cols_per_block;  // <= 256
   int rows;            // threads per column
-  int chunk;           // pixels per CTA
+  uint32_t total_rows, rows_per_cta;
 };
 
+static int streaming_ctas_per_sm(const void* kernel) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+  return occ > 4 ? 4 : occ;   // 4 x 256 threads x 4 loads in flight per SM already covers the HBM latency-bandwidth product
+}
+
+// VE = elements per vector (1 = scalar fallback). ctas_per_sm: resident CTAs of the kernel about to be launched.
 template <int VE>
-static NcGeom make_geom(int n, int hw, int c, dim3* grid, int* block) {
+static NcGeom make_geom(int n, int hw, int c, int ctas_per_sm, dim3* grid, int* block, int min_rows_per_thread = 2) {
   NcGeom g;
-  g.n = n; g.hw = hw; g.c = c; g.cv = c / VE;
+  g.n = n; g.c = c; g.pack = 1;
+  if (VE > 1 && c < VE && VE % c == 0 && hw % (VE / c) == 0) g.pack = VE / c;
+  g.hwv = hw / g.pack; g.span = c * g.pack; g.cv = g.span / VE;
   g.cols_per_block = g.cv < 256 ? g.cv : 256;
   g.rows = 256 / g.cols_per_block;
-  if (g.rows < 1) g.rows = 1;
   *block = g.cols_per_block * g.rows;
-  // aim for >= 4 CTAs per SM overall, at least 4 pixels per thread-row
   const int col_blocks = (g.cv + g.cols_per_block - 1) / g.cols_per_block;
-  long long want_chunks = (long long)kNumSMs * 4 / ((long long)n * col_blocks) + 1;
-  int chunk = (int)((hw + want_chunks - 1) / want_chunks);
-  const int min_chunk = g.rows * 4;
-  if (chunk < min_chunk) chunk = min_chunk;
-  if (chunk > hw) chunk = hw;
-  g.chunk = chunk;
-  *grid = dim3((hw + chunk - 1) / chunk, n, col_blocks);
+  g.total_rows = (uint32_t)n * (uint32_t)g.hwv;
+  // one wave at most, and at least `min_rows_per_thread` rows per thread (small tensors: fewer CTAs; the kernel that ends in same-address atomics
+  // asks for 8). A range of several images is cut at image boundaries, so that no CTA pays an extra flush for a partial image.
+  long long ctas = (long long)kNumSMs * ctas_per_sm / col_blocks;
+  const long long by_work = ((long long)g.total_rows + (long long)g.rows * min_rows_per_thread - 1) / ((long long)g.rows * min_rows_per_thread);
+  if (ctas > by_work) ctas = by_work;
+  if (ctas < 1) ctas = 1;
+  uint32_t per = (uint32_t)(((long long)g.total_rows + ctas - 1) / ctas);
+  if (per >= (uint32_t)g.hwv) per = per / g.hwv * g.hwv;
+  else per = (per + g.rows - 1) / g.rows * g.rows;
+  g.rows_per_cta = per;
+  *grid = dim3((g.total_rows + per - 1) / per, 1, col_blocks);
   return g;
 }
 
@@ -55,31 +73,66 @@ template <typename T, int VE> __device__ __forceinline__ void store_vec(T* p, co
   else *reinterpret_cast<uint4*>(p) = vec_pack<T>(in);
 }
 
-// Reduces `NV` per-thread values per column element across the `rows` threads that share a column, then atomicAdd per element into
-// dst_cta[(colg * VE + e) * dst_stride + v] (dst_stride >= NV; dst_cta = the image's / tensor's base). ALL threads take part in the cross-row sum: the
-// outputs (column, v, e) are spread over the threads and, when there are fewer outputs than threads, the rows are split into slices (one atomic per slice).
-// (A first version let the `row == 0` threads add up all rows serially: 512 dependent shared loads per CTA, ~8 us of tail on a 36 us kernel.)
+// Calls f(img, p0, p1) for every image the CTA's row range touches ([p0, p1) = vector rows inside that image). CTA-uniform.
+template <typename F>
+__device__ __forceinline__ void for_each_segment(const NcGeom& g, F&& f) {
+  uint32_t r0 = blockIdx.x * g.rows_per_cta;
+  const uint32_t r1 = min(r0 + g.rows_per_cta, g.total_rows);
+  while (r0 < r1) {
+    const uint32_t img = r0 / (uint32_t)g.hwv;
+    const int p0 = (int)(r0 - img * (uint32_t)g.hwv);
+    const int p1 = (int)min((uint32_t)g.hwv, (uint32_t)p0 + (r1 - r0));
+    f((int)img, p0, p1);
+    r0 += (uint32_t)(p1 - p0);
+  }
+}
+
+// channel of element e of column colg
+__device__ __forceinline__ int chan_of(const NcGeom& g, int colg, int ve, int e) { return g.pack > 1 ? (e & (g.c - 1)) : colg * ve + e; }
+
+// Sums `NV` per-thread values per channel over the CTA (over the `rows` threads that share a column and, in packed mode, over the elements of a
+// vector that belong to the same channel), then ONE atomicAdd per (channel, v) into dst[channel * dst_stride + v]. Two stages so that all threads
+// take part: the outputs x `parts` row slices are spread over the threads, then the slices are folded.
+// (Earlier versions: the row-0 threads summing all rows serially = 512 dependent shared loads; one atomic per slice = 256 atomics per CTA onto 4
+// addresses for the 4-channel layers, 105 us of L2 atomic serialisation.)
 template <int VE, int NV>
-__device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, float* dst_cta, int dst_stride) {
+__device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, float* dst, int dst_stride) {
   __shared__ float red[256 * 16];  // [row][col][NV*VE] flattened; VE*NV <= 16
+  __shared__ float red2[256];
   constexpr int PER = VE * NV;
   static_assert(PER <= 16, "column_reduce_atomic: too many values per thread");
   const int t = row * g.cols_per_block + col;
+  __syncthreads();   // previous use of red / red2
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int e = 0; e < VE; ++e) red[t * PER + v * VE + e] = acc[v][e];
   __syncthreads();
-  const int outs = g.cols_per_block * PER, nthr = blockDim.x;
+  const int epc = g.pack > 1 ? g.c : VE;                  // distinct channels per column
+  const int outs = g.cols_per_block * NV * epc, nthr = blockDim.x;
   const int parts = outs < nthr ? nthr / outs : 1;
   for (int o = threadIdx.x; o < outs * parts; o += nthr) {
     const int part = o / outs, oo = o - part * outs;
-    const int cl = oo / PER, k = oo - cl * PER, v = k / VE, e = k - v * VE;
-    const int colg = blockIdx.z * g.cols_per_block + cl;
-    if (colg >= g.cv) continue;
+    const int cl = oo / (NV * epc), k = oo - cl * (NV * epc), v = k / epc, e0 = k - v * epc;
     float s = 0.f;
-    for (int r = part; r < g.rows; r += parts) s += red[(r * g.cols_per_block + cl) * PER + k];
-    atomicAdd(dst_cta + ((size_t)colg * VE + e) * dst_stride + v, s);
+    for (int r = part; r < g.rows; r += parts)
+      for (int e = e0; e < VE; e += epc) s += red[(r * g.cols_per_block + cl) * PER + v * VE + e];
+    if (parts > 1) red2[o] = s;
+    else {
+      const int colg = blockIdx.z * g.cols_per_block + cl;
+      if (colg < g.cv) atomicAdd(dst + (size_t)chan_of(g, colg, VE, e0) * dst_stride + v, s);
+    }
+  }
+  if (parts > 1) {
+    __syncthreads();
+    if ((int)threadIdx.x < outs) {
+      const int oo = threadIdx.x;
+      const int cl = oo / (NV * epc), k = oo - cl * (NV * epc), v = k / epc, e0 = k - v * epc;
+      float s = 0.f;
+      for (int q = 0; q < parts; ++q) s += red2[q * outs + oo];
+      const int colg = blockIdx.z * g.cols_per_block + cl;
+      if (colg < g.cv) atomicAdd(dst + (size_t)chan_of(g, colg, VE, e0) * dst_stride + v, s);
+    }
   }
 }
 
@@ -97,110 +150,115 @@ template <typename T, int VE> __device__ __forceinline__ void unpack_raw(const R
 #ifndef DCV_UNR
 #define DCV_UNR 4
 #endif
-constexpr int UNR = DCV_UNR;   // pixels in flight per thread: the bf16 kernels were latency-bound at ~45 % of HBM with one load per iteration
+constexpr int UNR = DCV_UNR;   // rows in flight per thread: the bf16 kernels were latency-bound at ~45 % of HBM with one load per iteration
 
 // ---- statistics: stats[n][c][2] += {sum y, sum y^2}
 template <typename T, int VE>
 __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, float* __restrict__ stats, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
-  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
-  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
-  float acc[2][VE];
+  const int colg = blockIdx.z * g.cols_per_block + col;
+  for_each_segment(g, [&](int img, int p0, int p1) {
+    float acc[2][VE];
 #pragma unroll
-  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
-  if (colg < g.cv) {
-    const T* base = y + ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-    int p = p0 + row;
-    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
-      Raw<T, VE> r[UNR];
+    for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+    if (colg < g.cv) {
+      const T* base = y + ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
+      int p = p0 + row;
+      for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+        Raw<T, VE> r[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.c);
+        for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.span);
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < UNR; ++u) {
+          float v[VE];
+          unpack_raw<T, VE>(r[u], v);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
+        }
+      }
+      for (; p < p1; p += g.rows) {
         float v[VE];
-        unpack_raw<T, VE>(r[u], v);
+        load_vec<T, VE>(base + (size_t)p * g.span, v);
 #pragma unroll
         for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
       }
     }
-    for (; p < p1; p += g.rows) {
-      float v[VE];
-      load_vec<T, VE>(base + (size_t)p * g.c, v);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
-    }
-  }
-  column_reduce_atomic<VE, 2>(acc, g, col, row, stats + (size_t)img * g.c * 2, 2);
+    column_reduce_atomic<VE, 2>(acc, g, col, row, stats + (size_t)img * g.c * 2, 2);
+  });
 }
 
 // ---- forward apply: z = A*y + B
 template <typename T, int VE>
 __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ z, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
-  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
+  const int colg = blockIdx.z * g.cols_per_block + col;
   if (colg >= g.cv) return;
-  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
-  float A[VE], B[VE];
-  const float* abp = ab + ((size_t)img * g.c + (size_t)colg * VE) * 2;
+  for_each_segment(g, [&](int img, int p0, int p1) {
+    float A[VE], B[VE];
 #pragma unroll
-  for (int e = 0; e < VE; ++e) { A[e] = abp[2 * e]; B[e] = abp[2 * e + 1]; }
-  const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-  int p = p0 + row;
-  for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
-    Raw<T, VE> r[UNR];
+    for (int e = 0; e < VE; ++e) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(ab) + (size_t)img * g.c + chan_of(g, colg, VE, e));
+      A[e] = t.x; B[e] = t.y;
+    }
+    const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
+    int p = p0 + row;
+    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+      Raw<T, VE> r[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.c);
+      for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
+      for (int u = 0; u < UNR; ++u) {
+        float v[VE];
+        unpack_raw<T, VE>(r[u], v);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
+        store_vec<T, VE>(z + base + (size_t)(p + u * g.rows) * g.span, v);
+      }
+    }
+    for (; p < p1; p += g.rows) {
       float v[VE];
-      unpack_raw<T, VE>(r[u], v);
+      load_vec<T, VE>(y + base + (size_t)p * g.span, v);
 #pragma unroll
       for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
-      store_vec<T, VE>(z + base + (size_t)(p + u * g.rows) * g.c, v);
+      store_vec<T, VE>(z + base + (size_t)p * g.span, v);
     }
-  }
-  for (; p < p1; p += g.rows) {
-    float v[VE];
-    load_vec<T, VE>(y + base + (size_t)p * g.c, v);
-#pragma unroll
-    for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
-    store_vec<T, VE>(z + base + (size_t)p * g.c, v);
-  }
+  });
 }
 
 // ---- backward reduce: s[n][c][2] += {sum dz, sum dz*y}
 template <typename T, int VE>
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y, float* __restrict__ s, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
-  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
-  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
-  float acc[2][VE];
+  const int colg = blockIdx.z * g.cols_per_block + col;
+  for_each_segment(g, [&](int img, int p0, int p1) {
+    float acc[2][VE];
 #pragma unroll
-  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
-  if (colg < g.cv) {
-    const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-    int p = p0 + row;
-    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
-      Raw<T, VE> ra[UNR], rb[UNR];
+    for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+    if (colg < g.cv) {
+      const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
+      int p = p0 + row;
+      for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+        Raw<T, VE> ra[UNR], rb[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.c); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.c); }
+        for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span); }
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < UNR; ++u) {
+          float a[VE], b[VE];
+          unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
+        }
+      }
+      for (; p < p1; p += g.rows) {
         float a[VE], b[VE];
-        unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+        load_vec<T, VE>(dz + base + (size_t)p * g.span, a);
+        load_vec<T, VE>(y + base + (size_t)p * g.span, b);
 #pragma unroll
         for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
       }
     }
-    for (; p < p1; p += g.rows) {
-      float a[VE], b[VE];
-      load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
-      load_vec<T, VE>(y + base + (size_t)p * g.c, b);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
-    }
-  }
-  column_reduce_atomic<VE, 2>(acc, g, col, row, s + (size_t)img * g.c * 2, 2);
+    column_reduce_atomic<VE, 2>(acc, g, col, row, s + (size_t)img * g.c * 2, 2);
+  });
 }
 
 // ---- backward apply: dy = act'(y) * (P*dz + Q*y + R); dbias[c] += sum dy. The activation is a template parameter: no per-element switch.
@@ -215,49 +273,52 @@ template <typename T, int VE, int ACT>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ pqr,
                                                         T* __restrict__ dy, float* __restrict__ dbias, float slope, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
-  const int colg = blockIdx.z * g.cols_per_block + col, img = blockIdx.y;
-  const int p0 = blockIdx.x * g.chunk, p1 = min(p0 + g.chunk, g.hw);
-  float acc[1][VE];
+  const int colg = blockIdx.z * g.cols_per_block + col;
+  float acc[1][VE];   // bias-gradient partial sums, kept over all the CTA's images
 #pragma unroll
   for (int e = 0; e < VE; ++e) acc[0][e] = 0.f;
   if (colg < g.cv) {
-    float P[VE], Q[VE], R[VE];
-    if (pqr) {
-      const float* pp = pqr + ((size_t)img * g.c + (size_t)colg * VE) * 3;
+    for_each_segment(g, [&](int img, int p0, int p1) {
+      float P[VE], Q[VE], R[VE];
+      if (pqr) {
 #pragma unroll
-      for (int e = 0; e < VE; ++e) { P[e] = pp[3 * e]; Q[e] = pp[3 * e + 1]; R[e] = pp[3 * e + 2]; }
-    } else {
+        for (int e = 0; e < VE; ++e) {
+          const float* t = pqr + ((size_t)img * g.c + chan_of(g, colg, VE, e)) * 3;
+          P[e] = __ldg(t); Q[e] = __ldg(t + 1); R[e] = __ldg(t + 2);
+        }
+      } else {
 #pragma unroll
-      for (int e = 0; e < VE; ++e) { P[e] = 1.f; Q[e] = 0.f; R[e] = 0.f; }
-    }
-    const size_t base = ((size_t)img * g.hw) * g.c + (size_t)colg * VE;
-    auto one = [&](float* a, const float* b, size_t off) {
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        const float pre = fmaf(P[e], a[e], fmaf(Q[e], b[e], R[e]));
-        a[e] = pre * act_grad_t<ACT>(b[e], slope);
-        acc[0][e] += a[e];
+        for (int e = 0; e < VE; ++e) { P[e] = 1.f; Q[e] = 0.f; R[e] = 0.f; }
       }
-      store_vec<T, VE>(dy + off, a);
-    };
-    int p = p0 + row;
-    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
-      Raw<T, VE> ra[UNR], rb[UNR];
+      const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
+      auto one = [&](float* a, const float* b, size_t off) {
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.c); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.c); }
+        for (int e = 0; e < VE; ++e) {
+          const float pre = fmaf(P[e], a[e], fmaf(Q[e], b[e], R[e]));
+          a[e] = pre * act_grad_t<ACT>(b[e], slope);
+          acc[0][e] += a[e];
+        }
+        store_vec<T, VE>(dy + off, a);
+      };
+      int p = p0 + row;
+      for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+        Raw<T, VE> ra[UNR], rb[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span); }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          float a[VE], b[VE];
+          unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+          one(a, b, base + (size_t)(p + u * g.rows) * g.span);
+        }
+      }
+      for (; p < p1; p += g.rows) {
         float a[VE], b[VE];
-        unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
-        one(a, b, base + (size_t)(p + u * g.rows) * g.c);
+        load_vec<T, VE>(dz + base + (size_t)p * g.span, a);
+        load_vec<T, VE>(y + base + (size_t)p * g.span, b);
+        one(a, b, base + (size_t)p * g.span);
       }
-    }
-    for (; p < p1; p += g.rows) {
-      float a[VE], b[VE];
-      load_vec<T, VE>(dz + base + (size_t)p * g.c, a);
-      load_vec<T, VE>(y + base + (size_t)p * g.c, b);
-      one(a, b, base + (size_t)p * g.c);
-    }
+    });
   }
   if (dbias) column_reduce_atomic<VE, 1>(acc, g, col, row, dbias, 1);
 }
@@ -461,14 +522,17 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
   }
 }
 
-static bool vec_ok(const void* a, const void* b, const void* d, int c, int ve) {
+// 16-byte vectors are usable when a pixel is a whole number of vectors, or a vector a whole number of pixels (and of an image's pixels)
+static bool vec_ok(const void* a, const void* b, const void* d, int n, int hw, int c, int ve) {
   auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0); };
-  return c % ve == 0 && al(a) && al(b) && al(d);
+  (void)n;
+  const bool shape_ok = c % ve == 0 || (c < ve && ve % c == 0 && hw % (ve / c) == 0);
+  return shape_ok && al(a) && al(b) && al(d);
 }
 
 static int check_nc(const char* name, int n, int hw, int c) {
   DCV_REQUIRE(n > 0 && hw > 0 && c > 0, "%s: bad shape n=%d hw=%d c=%d", name, n, hw, c);
-  DCV_REQUIRE(n < 65536, "%s: n=%d exceeds grid limit", name, n);
+  DCV_REQUIRE((long long)n * hw < (1ll << 31), "%s: n*hw=%lld exceeds the 32-bit row index range", name, (long long)n * hw);
   return 0;
 }
 
@@ -490,8 +554,8 @@ int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dty
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
-    if (vec_ok(y, nullptr, nullptr, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); stats_kernel<T, VE><<<grid, block, 0, st>>>((const T*)y, stats_nc, g); }
-    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); stats_kernel<T, 1><<<grid, block, 0, st>>>((const T*)y, stats_nc, g); }
+    if (vec_ok(y, nullptr, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)stats_kernel<T, VE>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); stats_kernel<T, VE><<<grid, block, 0, st>>>((const T*)y, stats_nc, g); }
+    else { static const int occ = streaming_ctas_per_sm((const void*)stats_kernel<T, 1>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); stats_kernel<T, 1><<<grid, block, 0, st>>>((const T*)y, stats_nc, g); }
   });
   DCV_LAUNCH_CHECK("stats_kernel");
   return 0;
@@ -536,8 +600,8 @@ int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
-    if (vec_ok(y, z, nullptr, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); apply_fwd_kernel<T, VE><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g); }
-    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); apply_fwd_kernel<T, 1><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g); }
+    if (vec_ok(y, z, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)apply_fwd_kernel<T, VE>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); apply_fwd_kernel<T, VE><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g); }
+    else { static const int occ = streaming_ctas_per_sm((const void*)apply_fwd_kernel<T, 1>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); apply_fwd_kernel<T, 1><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g); }
   });
   DCV_LAUNCH_CHECK("apply_fwd_kernel");
   return 0;
@@ -552,8 +616,8 @@ int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int h
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
-    if (vec_ok(dz, y, nullptr, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); bwd_reduce_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
-    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); bwd_reduce_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
+    if (vec_ok(dz, y, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, VE>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
+    else { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, 1>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
   });
   DCV_LAUNCH_CHECK("bwd_reduce_kernel");
   return 0;
@@ -582,8 +646,8 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
 #define DCV_BWD_APPLY(ACT_)                                                                                                                                   \
   DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                              \
     constexpr int VE = 16 / sizeof(T);                                                                                                                        \
-    if (vec_ok(dz, y, dy, c, VE)) { NcGeom g = make_geom<VE>(n, hw, c, &grid, &block); bwd_apply_kernel<T, VE, ACT_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g); } \
-    else { NcGeom g = make_geom<1>(n, hw, c, &grid, &block); bwd_apply_kernel<T, 1, ACT_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g); }                      \
+    if (vec_ok(dz, y, dy, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)bwd_apply_kernel<T, VE, ACT_>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block, dbias_c ? 8 : 2); bwd_apply_kernel<T, VE, ACT_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g); } \
+    else { static const int occ = streaming_ctas_per_sm((const void*)bwd_apply_kernel<T, 1, ACT_>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block, dbias_c ? 8 : 2); bwd_apply_kernel<T, 1, ACT_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g); }                      \
   })
   switch (act) {
     case DCV_ACT_RELU: DCV_BWD_APPLY(DCV_ACT_RELU); break;

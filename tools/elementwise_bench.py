@@ -17,19 +17,30 @@ from deepcv_b200._lib import ACT_LEAKY_RELU, DCV_BF16, DCV_F32, ConvShape, check
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-ITERS = 3
+ITERS = 10
+
+
+WORK_STREAM = None
 
 
 def timeit(fn, reps, iters=None):
+    """ ms per launch. The `reps` launches (distinct buffers, working set > L2) are captured into ONE CUDA graph and the graph is replayed: the
+    kernels are 5-50 us, shorter than a Python + ctypes launch (memset + kernel), so eager launches would time the host, not the device. """
     iters = ITERS if iters is None else iters
     fn(0)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=WORK_STREAM):
         for i in range(reps):
             fn(i)
-    e1.record()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(WORK_STREAM):
+        e0.record()
+        for _ in range(iters):
+            graph.replay()
+        e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / (iters * reps)
 
@@ -39,13 +50,16 @@ def main():
     ap.add_argument('--what', default='norm,pool,preprocess,im2col')
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--sizes', default='32,64,128,224,256,512,1024')
-    ap.add_argument('--iters', type=int, default=3)
+    ap.add_argument('--iters', type=int, default=10)
     args = ap.parse_args()
     global ITERS
     ITERS = args.iters
     peak = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())['hbm_gbs'] if (ROOT / 'MEASURED_PEAKS.json').exists() else 6650.0
     dev = torch.device('cuda')
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    global WORK_STREAM
+    WORK_STREAM = torch.cuda.Stream()
+    torch.cuda.set_stream(WORK_STREAM)
+    st = ctypes.c_void_p(WORK_STREAM.cuda_stream)
     what = args.what.split(',')
 
     def report(name, ms, nbytes):
