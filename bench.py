@@ -147,44 +147,79 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def time_dominant_kernel(batch, size, dev, peaks, dtype_name):
-    """ Roofline of the dominant kernel of the CIFAR step — the direct forward convolution (3->4 channels, 5x5, fused bias + ReLU + per-(n,c)
-    sum / sum-of-squares epilogue), HBM-bound on this network (arithmetic intensity 43-72 FLOP/B). Called through the C ABI
-    with preallocated buffers; algorithmic bytes per launch = read x + write y + read w; timed with CUDA events on the launching stream over
-    launches that walk a working set larger than L2. """
-    import ctypes
+def _graph_time_ms(launch, reps, iters, stream):
+    """ ms per launch: `reps` launches (distinct buffers, working set > L2) captured into one CUDA graph on `stream`, replayed `iters` times between CUDA
+    events recorded on that same stream. Eager Python + ctypes launches take longer than these kernels run, so they would time the host. """
     import torch
-    from deepcv_b200._lib import ACT_RELU, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, check, lib
-    tdt, dt, esize = (torch.bfloat16, DCV_BF16, 2) if dtype_name == 'bf16' else (torch.float32, DCV_F32, 4)
-    n, c, h, w, k = batch, 3, size, size, 4
-    reps = max(4, int(200e6 / (n * h * w * (c + k) * esize)) + 1)
-    xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
-    ys = [torch.empty(n, h, w, k, device=dev, dtype=tdt) for _ in range(reps)]
-    wt = torch.randn(k, 5, 5, c, device=dev).to(tdt)
-    bias = torch.zeros(k, device=dev)
-    stats = torch.empty(n, k, 2, device=dev)
-    shape = ConvShape(n, h, w, c, k, 5, 5, 1, 1, 2, 2, 1, 1, h, w)
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    P = lambda t: ctypes.c_void_p(t.data_ptr())
-
-    def launch(i):
-        check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(wt), P(bias), P(ys[i]), P(stats), ACT_RELU, 0., dt, ALGO_DIRECT, st), 'conv2d_fwd')
-    for i in range(reps):
-        launch(i)
-    torch.cuda.synchronize()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 5
-    start.record()
-    for _ in range(iters):
+    with torch.cuda.stream(stream):
         for i in range(reps):
             launch(i)
-    end.record()
     torch.cuda.synchronize()
-    per_launch_s = start.elapsed_time(end) / 1e3 / (iters * reps)
-    alg_bytes = n * h * w * (c + k) * esize + k * 25 * c * esize
-    achieved = alg_bytes / per_launch_s / 1e9
-    return dict(bound='hbm', kernel='conv_fwd_direct_kernel (3->4 ch, 5x5, bias + ReLU + statistics epilogue; includes its 4 KB statistics memset)', achieved=achieved, peak=peaks['hbm_gbs'],
-                unit='GB/s', frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=per_launch_s * 1e6)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        for i in range(reps):
+            launch(i)
+    graph.replay()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        start.record()
+        for _ in range(iters):
+            graph.replay()
+        end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / (iters * reps)
+
+
+def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
+    """ Roofline of the dominant kernel of the step, called through the C ABI with preallocated buffers, timed live with CUDA events on the stream it is
+    launched on (graph replay, buffers cycled beyond L2).
+      cifar     the 5x5 direct weight-gradient convolution (4 -> 4 channels, 32x32): the largest share of the CIFAR step in the ncu launch list
+                (profiles/). HBM-bound by the accounting of SURVEY.md section 8.d (arithmetic intensity 43-72 FLOP/B): algorithmic bytes per launch =
+                read x + read dy + write dw.
+      imagenet  the tcgen05 implicit-GEMM forward convolution of the 64 -> 64 channel 3x3 layers at 56x56 (also run as their data gradient): the largest
+                share of the ImageNet-shaped step. Tensor-bound: 2*N*P*Q*K*C*R*S FLOP per launch against the measured dense bf16 peak. """
+    import ctypes
+    import torch
+    from deepcv_b200._lib import ACT_LEAKY_RELU, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, check, lib
+    tdt, dt, esize = (torch.bfloat16, DCV_BF16, 2) if dtype_name == 'bf16' else (torch.float32, DCV_F32, 4)
+    stream = torch.cuda.Stream()
+    st = ctypes.c_void_p(stream.cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    with torch.cuda.stream(stream):
+        if workload == 'cifar':
+            n, c, h, w, k = batch, 4, size, size, 4
+            reps = max(4, int(300e6 / (n * h * w * (c + k) * esize)) + 1)
+            xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
+            dys = [torch.randn(n, h, w, k, device=dev).to(tdt) for _ in range(reps)]
+            dw = torch.empty(k, 5, 5, c, device=dev)
+            shape = ConvShape(n, h, w, c, k, 5, 5, 1, 1, 2, 2, 1, 1, h, w)
+
+            def launch(i):
+                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xs[i]), P(dys[i]), P(dw), None, dt, ALGO_DIRECT, st), 'conv2d_wgrad')
+            ms = _graph_time_ms(launch, reps, 20, stream)
+            alg_bytes = n * h * w * (c + k) * esize + k * 25 * c * 4
+            achieved = alg_bytes / (ms / 1e3) / 1e9
+            return dict(bound='hbm', kernel='conv_wgrad_direct_s1_kernel (4->4 ch, 5x5, 32x32; includes the 1.6 KB memset of dw)', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
+                        frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
+                        note='latency-bound at this size: 8.4 MB per launch is 1.3 us of HBM time; see DESIGN.md section 5')
+        n, c, h, w, k = batch, 64, 56, 56, 64
+        if dtype_name != 'bf16':
+            return None
+        reps = max(3, int(400e6 / (n * h * w * (c + k) * esize)) + 1)
+        xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
+        ys = [torch.empty(n, h, w, k, device=dev, dtype=tdt) for _ in range(reps)]
+        wt = (torch.randn(k, 3, 3, c, device=dev) * 0.05).to(tdt)
+        bias = torch.zeros(k, device=dev)
+        shape = ConvShape(n, h, w, c, k, 3, 3, 1, 1, 1, 1, 1, 1, h, w)
+
+        def launch(i):
+            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(wt), P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, dt, ALGO_AUTO, st), 'conv2d_fwd')
+        ms = _graph_time_ms(launch, reps, 10, stream)
+        flop = 2.0 * n * h * w * k * c * 9
+        achieved = flop / (ms / 1e3) / 1e12
+        return dict(bound='tensor', kernel='conv_fwd_tc_kernel<64> (64->64 ch, 3x3, 56x56, bias + LeakyReLU epilogue)', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
+                    frac=achieved / peaks['bf16_tflops'], traffic=None, peak_source=peaks['source'] + ', burst figure (kernel timed alone)', algorithmic_flop_per_launch=flop, us_per_launch=ms * 1e3)
 
 
 def load_peaks():
@@ -316,7 +351,7 @@ def run_b200(args):
     if rank != 0:
         shutdown()
         return
-    roofline = time_dominant_kernel(batch, size, dev, peaks, args.dtype) if args.workload == 'cifar' else None
+    roofline = time_dominant_kernel(args.workload, batch, size, dev, peaks, args.dtype)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_reference_run(spec, steps=30, warmup=2, seconds=args.cpu_seconds, batch=min(batch, 512 if args.workload == 'cifar' else 8))
@@ -330,6 +365,21 @@ def run_b200(args):
     shutdown()
 
 
+def run_preprocess_sweep(args):
+    """ BASELINE.json configs[4]: the uint8 normalise / flip / crop kernel alone, 32^2 .. 1024^2, achieved HBM GB/s on algorithmic bytes
+    (3*h*w*(1 + sizeof(out)) per image) against the measured copy bandwidth. Runs tools/elementwise_bench.py and folds its lines into one. """
+    if int(os.environ.get('RANK', 0)) != 0:
+        return
+    out = subprocess.run([sys.executable, str(ROOT / 'tools' / 'elementwise_bench.py'), '--what', 'preprocess'], capture_output=True, text=True, check=True).stdout
+    rows = [json.loads(l) for l in out.splitlines() if l.startswith('{')]
+    peaks = load_peaks()
+    best = max(rows, key=lambda r: r['GBps'])
+    print(json.dumps(dict(metric='preprocess achieved HBM bandwidth', value=best['GBps'], unit='GB/s', n_gpus=1, higher_is_better=True, dtype='u8', data='synthetic',
+                          config=dict(workload='uint8 HWC -> pad-crop -> flip -> normalise sweep 32^2..1024^2 (bf16 and fp32 outputs), ~1 GB of traffic per launch'),
+                          roofline=dict(bound='hbm', achieved=best['GBps'], peak=peaks['hbm_gbs'], unit='GB/s', frac=best['GBps'] / peaks['hbm_gbs'], traffic=None, kernel=best['kernel']),
+                          sweep=rows)))
+
+
 def main():
     args = parse_args()
     if os.environ.get('DCV_BENCH_WATCHDOG'):   # debugging aid: dump all Python stacks and exit if the run is still going after N seconds
@@ -337,6 +387,8 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ['DCV_BENCH_WATCHDOG']), exit=True)
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'preprocess':
+        run_preprocess_sweep(args)
     else:
         run_b200(args)
 

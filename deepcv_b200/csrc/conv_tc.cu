@@ -600,6 +600,7 @@ struct WgradParams {
   int n, h, w, c, k, r, s, pad_h, pad_w, p, q;
   int tw, th, tn, tiles_w, tiles_h, tiles_n, pixel_tiles;
   int k_tiles, c_tiles, splits;
+  int chan_taps;   // 1: the S_TAPS atoms of the B operand are consecutive 64-channel blocks of x (1x1 filters: c >= 128), not column taps
   float* dw;
 };
 
@@ -668,7 +669,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
         mbar_wait(bempty(bs), bph ^ 1u);
         mbar_expect_tx(bfull(bs), B_BYTES);
 #pragma unroll
-        for (int ss = 0; ss < S_TAPS; ++ss) tma_load_4d(smem_b + bs * B_BYTES + ss * WG_SLAB, &map_x, bfull(bs), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
+        for (int ss = 0; ss < S_TAPS; ++ss) {
+          if (prm.chan_taps) tma_load_4d(smem_b + bs * B_BYTES + ss * WG_SLAB, &map_x, bfull(bs), (ct * S_TAPS + ss) * 64, q0 - prm.pad_w, p0 + rr - prm.pad_h, n0);
+          else tma_load_4d(smem_b + bs * B_BYTES + ss * WG_SLAB, &map_x, bfull(bs), ct * 64, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
+        }
         if (++bs == WG_NB) { bs = 0; bph ^= 1u; }
       }
     }
@@ -710,7 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
         uint32_t v[32];
         tmem_ld32(taddr + ss * 64 + c0, v);
         if (krow < prm.k) {
-          float* dst = prm.dw + (((size_t)krow * prm.r + rr) * prm.s + ss) * prm.c + ct * 64 + c0;
+          float* dst = prm.chan_taps ? prm.dw + (((size_t)krow * prm.r + rr) * prm.s) * prm.c + (ct * S_TAPS + ss) * 64 + c0
+                                     : prm.dw + (((size_t)krow * prm.r + rr) * prm.s + ss) * prm.c + ct * 64 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic operations
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
@@ -759,6 +764,12 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
   DCV_REQUIRE(ptiles < (1ll << 30), "conv2d_wgrad (tcgen05): too many pixel tiles");
   prm.pixel_tiles = (int)ptiles;
   prm.k_tiles = (s->k + 127) / 128; prm.c_tiles = s->c / 64;
+  // 1x1-wide filters (the im2col GEMM of the stem: c = kpad = 192): group 3 or 2 channel blocks into one MMA instead of column taps
+  int taps = s->s;
+  if (s->s == 1 && prm.c_tiles >= 2) {
+    taps = prm.c_tiles % 3 == 0 ? 3 : (prm.c_tiles % 2 == 0 ? 2 : 1);
+    if (taps > 1) { prm.chan_taps = 1; prm.c_tiles /= taps; }
+  }
   const int units = prm.k_tiles * s->r * prm.c_tiles;
   // One CTA per SM fits (192 KB of shared memory): pick the pixel split that minimises (waves of CTAs) x (pixel tiles per CTA + fixed cost) — e.g.
   // 3 units x 49 splits = 147 CTAs in one wave, never 297 CTAs in two waves plus a one-CTA tail.
@@ -789,8 +800,8 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
     if (make_map(&mx, x, 4, dims, strides, box)) return 1;
   }
   const int grid = units * splits;
-  if (s->s == 1) return launch_wgrad<1>(mdy, mx, prm, grid, st);
-  if (s->s == 2) return launch_wgrad<2>(mdy, mx, prm, grid, st);
+  if (taps == 1) return launch_wgrad<1>(mdy, mx, prm, grid, st);
+  if (taps == 2) return launch_wgrad<2>(mdy, mx, prm, grid, st);
   return launch_wgrad<3>(mdy, mx, prm, grid, st);
 }
 

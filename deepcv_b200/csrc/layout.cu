@@ -79,6 +79,65 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, cons
   }
 }
 
+// Row-staged variant (the 7x7 / stride-2 stem): a CTA owns ONE output row (image, p). The R input rows that row reads are copied once into shared
+// memory with coalesced 16-byte loads — zero-filled left / right margins and zero rows stand in for the convolution padding, so the gather has no
+// bounds checks — and every 16-byte output vector is then assembled from 2-byte shared-memory reads. The first version gathered straight from global
+// memory (8 scalar loads with 4 bounds checks each per vector): 1.05 ms for the 1.2 GB stem buffer = 19 % of HBM bandwidth, LSU-bound.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const T* __restrict__ x, T* __restrict__ col, const dcv_conv_shape s, const int kpad, const int rowlen, const int lpad,
+                                                          const int vec_stage, const int tab_offset_bytes, const FastDiv div_vpp, const FastDiv div_sc, const FastDiv div_c, const FastDiv div_p) {
+  constexpr int VE = 16 / sizeof(T);
+  extern __shared__ __align__(16) unsigned char im2col_smem[];
+  T* rows = reinterpret_cast<T*>(im2col_smem);   // [R][rowlen]
+  const int img = (int)div_p.div(blockIdx.x), op = (int)blockIdx.x - img * s.p;
+  const int wc = s.w * s.c, iy0 = op * s.stride_h - s.pad_h;
+  const T* ximg = x + (size_t)img * s.h * wc;
+  if (vec_stage) {
+    const int gpr = rowlen / VE;   // 16-byte groups per staged row; groups are entirely inside or outside [lpad, lpad + wc)
+    for (int i = threadIdx.x; i < s.r * gpr; i += 256) {
+      const int r = i / gpr, o = (i - r * gpr) * VE, e = o - lpad;
+      const int iy = iy0 + r * s.dil_h;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (iy >= 0 && iy < s.h && e >= 0 && e < wc) v = __ldg(reinterpret_cast<const uint4*>(ximg + (size_t)iy * wc + e));
+      *reinterpret_cast<uint4*>(rows + r * rowlen + o) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < s.r * rowlen; i += 256) {
+      const int r = i / rowlen, e = (i - r * rowlen) - lpad;
+      const int iy = iy0 + r * s.dil_h;
+      T v = from_f<T>(0.f);
+      if (iy >= 0 && iy < s.h && e >= 0 && e < wc) v = ximg[(size_t)iy * wc + e];
+      rows[i] = v;
+    }
+  }
+  // offset table: tab[kk] = position of column kk = (r, s, c) relative to the first staged element of an output pixel's window, -1 for the zero padding
+  int* tab = reinterpret_cast<int*>(im2col_smem + tab_offset_bytes);
+  {
+    const int rsc = s.r * s.s * s.c, sc = s.s * s.c;
+    for (int kk = threadIdx.x; kk < kpad; kk += 256) {
+      int o = -1;
+      if (kk < rsc) { const int rr = (int)div_sc.div((uint32_t)kk), rem = kk - rr * sc, ss = (int)div_c.div((uint32_t)rem), cc = rem - ss * s.c; o = rr * rowlen + ss * s.dil_w * s.c + cc; }
+      tab[kk] = o;
+    }
+    if (threadIdx.x < VE) rows[s.r * rowlen + threadIdx.x] = from_f<T>(0.f);   // the zero every padding column reads
+  }
+  __syncthreads();
+  const int vpp = kpad / VE;
+  const int total = s.q * vpp, zero_at = s.r * rowlen;
+  T* out = col + (size_t)blockIdx.x * s.q * kpad;
+  for (int idx = threadIdx.x; idx < total; idx += 256) {
+    const int q = (int)div_vpp.div((uint32_t)idx), v = idx - q * vpp;
+    const int base = lpad + (q * s.stride_w - s.pad_w) * s.c;
+    int o[VE];
+#pragma unroll
+    for (int e = 0; e < VE; e += 4) { const int4 t = *reinterpret_cast<const int4*>(tab + v * VE + e); o[e] = t.x; o[e + 1] = t.y; o[e + 2] = t.z; o[e + 3] = t.w; }
+    __align__(16) T vals[VE];
+#pragma unroll
+    for (int e = 0; e < VE; ++e) vals[e] = rows[o[e] >= 0 ? base + o[e] : zero_at];
+    __stcs(reinterpret_cast<uint4*>(out + (size_t)idx * VE), *reinterpret_cast<const uint4*>(vals));
+  }
+}
+
 template <typename TS, typename TD>
 static int launch_transpose(const void* src, void* dst, int batch, int rows, int cols, cudaStream_t st) {
   const int tiles_r = (rows + 31) / 32, tiles_c = (cols + 31) / 32;
@@ -135,6 +194,30 @@ int dcv_im2col(const dcv_conv_shape* shape, const void* x, void* col, int kpad, 
   const size_t total = (size_t)shape->n * shape->p * shape->q * (kpad / ve);
   DCV_REQUIRE(total < (1ull << 31), "im2col: %zu output vectors exceed the 32-bit index range", total);
   const FastDiv d_vpp(kpad / ve), d_q(shape->q), d_p(shape->p), d_sc(shape->s * shape->c), d_c(shape->c);
+  {
+    // row-staged kernel when the R input rows (plus zero margins) fit in shared memory
+    const int wc = shape->w * shape->c;
+    int lpad = shape->pad_w * shape->c;
+    lpad = (lpad + ve - 1) / ve * ve;
+    // largest staged index read: lpad + ((q-1)*stride - pad)*c + (s-1)*dil*c + c - 1
+    int need = lpad + ((shape->q - 1) * shape->stride_w - shape->pad_w + (shape->s - 1) * shape->dil_w + 1) * shape->c;
+    if (need < lpad + wc) need = lpad + wc;
+    const int rowlen = (need + ve - 1) / ve * ve;
+    const size_t esize = dtype == DCV_BF16 ? 2 : 4;
+    const size_t tab_off = ((size_t)(shape->r * rowlen + ve) * esize + 15) / 16 * 16;   // staged rows + one vector of zeros, then the offset table
+    const size_t smem = tab_off + (size_t)kpad * sizeof(int);
+    const long long ctas = (long long)shape->n * shape->p;
+    if (smem <= 96 * 1024 && ctas < (1ll << 31)) {
+      const int vec_stage = (wc % ve == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) ? 1 : 0;
+      DCV_DISPATCH_DTYPE(dtype, T, {
+        auto kern = im2col_rows_kernel<T>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)ctas, 256, smem, as_stream(stream)>>>((const T*)x, (T*)col, *shape, kpad, rowlen, lpad, vec_stage, (int)tab_off, d_vpp, d_sc, d_c, d_p);
+      });
+      DCV_LAUNCH_CHECK("im2col_rows_kernel");
+      return 0;
+    }
+  }
   DCV_DISPATCH_DTYPE(dtype, T, (im2col_kernel<T><<<grid_for(total, 256, kNumSMs * 32), 256, 0, as_stream(stream)>>>((const T*)x, (T*)col, *shape, kpad, d_vpp, d_q, d_p, d_sc, d_c)));
   DCV_LAUNCH_CHECK("im2col_kernel");
   return 0;

@@ -97,10 +97,10 @@ __device__ __forceinline__ int chan_of(const NcGeom& g, int colg, int ve, int e)
 // addresses for the 4-channel layers, 105 us of L2 atomic serialisation.)
 template <int VE, int NV>
 __device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, float* dst, int dst_stride) {
-  __shared__ float red[256 * 16];  // [row][col][NV*VE] flattened; VE*NV <= 16
-  __shared__ float red2[256];
   constexpr int PER = VE * NV;
-  static_assert(PER <= 16, "column_reduce_atomic: too many values per thread");
+  static_assert(PER <= 40, "column_reduce_atomic: too many values per thread");
+  __shared__ float red[256 * PER];  // [row][col][NV*VE] flattened
+  __shared__ float red2[256];
   const int t = row * g.cols_per_block + col;
   __syncthreads();   // previous use of red / red2
 #pragma unroll
@@ -153,6 +153,7 @@ template <typename T, int VE> __device__ __forceinline__ void unpack_raw(const R
 constexpr int UNR = DCV_UNR;   // rows in flight per thread: the bf16 kernels were latency-bound at ~45 % of HBM with one load per iteration
 
 // ---- statistics: stats[n][c][2] += {sum y, sum y^2}
+constexpr int SUNR = 2 * UNR;   // one tensor only: twice the rows in flight to cover the HBM latency-bandwidth product
 template <typename T, int VE>
 __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, float* __restrict__ stats, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
@@ -164,12 +165,12 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, flo
     if (colg < g.cv) {
       const T* base = y + ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
       int p = p0 + row;
-      for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
-        Raw<T, VE> r[UNR];
+      for (; p + (SUNR - 1) * g.rows < p1; p += SUNR * g.rows) {
+        Raw<T, VE> r[SUNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.span);
+        for (int u = 0; u < SUNR; ++u) r[u] = load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.span);
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < SUNR; ++u) {
           float v[VE];
           unpack_raw<T, VE>(r[u], v);
 #pragma unroll
@@ -225,15 +226,29 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
   });
 }
 
-// ---- backward reduce: s[n][c][2] += {sum dz, sum dz*y}
-template <typename T, int VE>
+// ---- backward reduce: s[n][c][5] += {sum dz, sum dz*y, sum_{y>0} dz, sum_{y>0} y, #{y>0}}
+// The last three (MASK = 1: ReLU / LeakyReLU blocks with a convolution bias) let the finalize kernel produce the bias gradient in closed form:
+// dy = act'(y) * (P*dz + Q*y + R) with act'(y) in {1, slope} piecewise constant, so sum dy is bilinear in these per-(n,c) sums and the apply pass
+// stays a pure streaming map (no CTA reduction, no same-address atomics).
+constexpr int kBwdSums = 5;
+template <typename T, int VE, int MASK>
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y, float* __restrict__ s, const NcGeom g) {
+  constexpr int NV = MASK ? 5 : 2;
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
   for_each_segment(g, [&](int img, int p0, int p1) {
-    float acc[2][VE];
+    float acc[NV][VE];
 #pragma unroll
-    for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < VE; ++e) acc[v][e] = 0.f;
+    auto add = [&](const float* a, const float* b) {
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]);
+        if (MASK) { const bool pos = b[e] > 0.f; acc[2][e] += pos ? a[e] : 0.f; acc[3][e] += pos ? b[e] : 0.f; acc[4][e] += pos ? 1.f : 0.f; }
+      }
+    };
     if (colg < g.cv) {
       const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
       int p = p0 + row;
@@ -245,19 +260,17 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
         for (int u = 0; u < UNR; ++u) {
           float a[VE], b[VE];
           unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
-#pragma unroll
-          for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
+          add(a, b);
         }
       }
       for (; p < p1; p += g.rows) {
         float a[VE], b[VE];
         load_vec<T, VE>(dz + base + (size_t)p * g.span, a);
         load_vec<T, VE>(y + base + (size_t)p * g.span, b);
-#pragma unroll
-        for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
+        add(a, b);
       }
     }
-    column_reduce_atomic<VE, 2>(acc, g, col, row, s + (size_t)img * g.c * 2, 2);
+    column_reduce_atomic<VE, NV>(acc, g, col, row, s + (size_t)img * g.c * kBwdSums, kBwdSums);
   });
 }
 
@@ -343,41 +356,55 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
   const int tid = threadIdx.x, nt = blockDim.x;
   // this CTA owns channels [ch_lo, ch_hi): whole GroupNorm groups (cpb is a multiple of the group size), so every phase below is CTA-local
   const int ch_lo = blockIdx.x * cpb, ch_hi = min(c, ch_lo + cpb), cl = ch_hi - ch_lo;
-  // 1. BatchNorm per channel: one warp per channel, lanes stride over the images, fp64 warp reduction
+  // 1. BatchNorm per channel: `wpc` warps per channel (all warps busy even with 4 channels), lanes stride over the images, fp64 warp reduction,
+  //    partials combined through shared memory by one thread per channel
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  for (int ch = ch_lo + warp; ch < ch_hi; ch += nwarps) {
-    double alpha = 1.0, beta = 0.0, mean = 0.0, rstd = 1.0;
-    if (prm.use_bn) {
-      double var;
-      if (prm.bn_training) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int i = lane; i < n; i += 32) { s1 += (double)stats[((size_t)i * c + ch) * 2]; s2 += (double)stats[((size_t)i * c + ch) * 2 + 1]; }
-        s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
-        const double m = (double)n * hw;
-        mean = s1 / m;
-        var = s2 / m - mean * mean;
-        if (var < 0.0) var = 0.0;
-        if (lane == 0 && prm.bn_running_mean && prm.bn_running_var) {
-          double mom = (double)prm.bn_momentum;
-          if (mom < 0.0) mom = 1.0 / (double)((prm.bn_num_batches_tracked ? *prm.bn_num_batches_tracked : 0) + 1);
-          const double unbiased = m > 1.0 ? var * m / (m - 1.0) : var;
-          prm.bn_running_mean[ch] = (float)((1.0 - mom) * (double)prm.bn_running_mean[ch] + mom * mean);
-          prm.bn_running_var[ch] = (float)((1.0 - mom) * (double)prm.bn_running_var[ch] + mom * unbiased);
-        }
-      } else {
-        mean = (double)prm.bn_running_mean[ch];
-        var = (double)prm.bn_running_var[ch];
-      }
-      rstd = rsqrt(var + (double)prm.bn_eps);
-      const double gamma = prm.bn_weight ? (double)prm.bn_weight[ch] : 1.0;
-      const double bias = prm.bn_bias ? (double)prm.bn_bias[ch] : 0.0;
-      alpha = gamma * rstd;
-      beta = bias - mean * alpha;
+  __shared__ double part[32][2];
+  const int wpc = max(1, nwarps / max(cl, 1)), cpp = nwarps / wpc;   // warps per channel, channels per pass
+  for (int c0 = 0; c0 < cl; c0 += cpp) {
+    const int chl = c0 + warp / wpc, sub = warp % wpc;
+    const bool on = warp / wpc < cpp && chl < cl && prm.use_bn && prm.bn_training;
+    if (on) {
+      const int ch = ch_lo + chl;
+      double s1 = 0.0, s2 = 0.0;
+      for (int i = sub * 32 + lane; i < n; i += wpc * 32) { s1 += (double)stats[((size_t)i * c + ch) * 2]; s2 += (double)stats[((size_t)i * c + ch) * 2 + 1]; }
+      s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+      if (lane == 0) { part[warp][0] = s1; part[warp][1] = s2; }
     }
-    if (lane == 0) {
+    __syncthreads();
+    if (tid < cpp && c0 + tid < cl) {
+      const int ch = ch_lo + c0 + tid;
+      double alpha = 1.0, beta = 0.0, mean = 0.0, rstd = 1.0;
+      if (prm.use_bn) {
+        double var;
+        if (prm.bn_training) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int j = 0; j < wpc; ++j) { s1 += part[tid * wpc + j][0]; s2 += part[tid * wpc + j][1]; }
+          const double m = (double)n * hw;
+          mean = s1 / m;
+          var = s2 / m - mean * mean;
+          if (var < 0.0) var = 0.0;
+          if (prm.bn_running_mean && prm.bn_running_var) {
+            double mom = (double)prm.bn_momentum;
+            if (mom < 0.0) mom = 1.0 / (double)((prm.bn_num_batches_tracked ? *prm.bn_num_batches_tracked : 0) + 1);
+            const double unbiased = m > 1.0 ? var * m / (m - 1.0) : var;
+            prm.bn_running_mean[ch] = (float)((1.0 - mom) * (double)prm.bn_running_mean[ch] + mom * mean);
+            prm.bn_running_var[ch] = (float)((1.0 - mom) * (double)prm.bn_running_var[ch] + mom * unbiased);
+          }
+        } else {
+          mean = (double)prm.bn_running_mean[ch];
+          var = (double)prm.bn_running_var[ch];
+        }
+        rstd = rsqrt(var + (double)prm.bn_eps);
+        const double gamma = prm.bn_weight ? (double)prm.bn_weight[ch] : 1.0;
+        const double bias = prm.bn_bias ? (double)prm.bn_bias[ch] : 0.0;
+        alpha = gamma * rstd;
+        beta = bias - mean * alpha;
+      }
       saved[2 * ch] = (float)mean; saved[2 * ch + 1] = (float)rstd;
       saved[off_alpha(c) + 2 * ch] = (float)alpha; saved[off_alpha(c) + 2 * ch + 1] = (float)beta;
     }
+    __syncthreads();
   }
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0 && prm.use_bn && prm.bn_training && prm.bn_num_batches_tracked) *prm.bn_num_batches_tracked += 1;
@@ -439,7 +466,8 @@ __device__ __forceinline__ void gn_adjoint_coeffs(const dcv_norm_params& prm, co
 
 __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, const float* __restrict__ s,
                                                             float* __restrict__ saved, float* __restrict__ pqr, float* __restrict__ d_bn_w, float* __restrict__ d_bn_b,
-                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b, const int cpb) {
+                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b, const int act, const float slope, float* __restrict__ d_bias,
+                                                            const int cpb) {
   const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1, cg = c / G;
   const double hw = (double)prm.hw;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -457,7 +485,7 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
         const int ch = grp * cg + k;
         const double gam = prm.gn_weight ? (double)prm.gn_weight[ch] : 1.0;
         const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
-        const double s1 = (double)s[((size_t)img * c + ch) * 2], s2 = (double)s[((size_t)img * c + ch) * 2 + 1];
+        const double s1 = (double)s[((size_t)img * c + ch) * kBwdSums], s2 = (double)s[((size_t)img * c + ch) * kBwdSums + 1];
         a += gam * s1;
         b += gam * r * (al * s2 + (be - mean_u) * s1);
       }
@@ -467,37 +495,48 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
     __syncthreads();
   }
   // 2. per-channel sums over images: BatchNorm adjoint sums U1 = sum du, U2 = sum du*y_hat; parameter gradients.
-  //    One warp per channel, lanes stride over the images, fp64 warp reductions.
+  //    `wpc` warps per channel, lanes stride over the images, fp64 warp reductions, partials combined through shared memory.
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  for (int ch = ch_lo + warp; ch < ch_hi; ch += nwarps) {
-    const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
-    const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
-    double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
-    for (int img = lane; img < n; img += 32) {
-      const size_t i = (size_t)img * c + ch;
-      const double sy = (double)stats[2 * i], syy = (double)stats[2 * i + 1], s1 = (double)s[2 * i], s2 = (double)s[2 * i + 1];
-      double D1, D2, D3;
-      gn_adjoint_coeffs(prm, saved, img, ch, G, D1, D2, D3);
-      u1 += D1 * s1 + D2 * sy + D3 * hw;
-      u2raw += D1 * s2 + D2 * syy + D3 * sy;
-      if (prm.use_gn) {
-        const size_t gi = (size_t)img * G + ch / cg;
-        const double mean_u = (double)saved[off_gn(c) + 2 * gi], r = (double)saved[off_gn(c) + 2 * gi + 1];
-        dgw += r * (al * s2 + (be - mean_u) * s1);
-        dgb += s1;
+  __shared__ double part[32][4];
+  const int wpc = max(1, nwarps / max(cl, 1)), cpp = nwarps / wpc;
+  for (int c0 = 0; c0 < cl; c0 += cpp) {
+    const int chl = c0 + warp / wpc, sub = warp % wpc;
+    if (warp / wpc < cpp && chl < cl) {
+      const int ch = ch_lo + chl;
+      const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
+      double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
+      for (int img = sub * 32 + lane; img < n; img += wpc * 32) {
+        const size_t i = (size_t)img * c + ch;
+        const double sy = (double)stats[2 * i], syy = (double)stats[2 * i + 1], s1 = (double)s[kBwdSums * i], s2 = (double)s[kBwdSums * i + 1];
+        double D1, D2, D3;
+        gn_adjoint_coeffs(prm, saved, img, ch, G, D1, D2, D3);
+        u1 += D1 * s1 + D2 * sy + D3 * hw;
+        u2raw += D1 * s2 + D2 * syy + D3 * sy;
+        if (prm.use_gn) {
+          const size_t gi = (size_t)img * G + ch / cg;
+          const double mean_u = (double)saved[off_gn(c) + 2 * gi], r = (double)saved[off_gn(c) + 2 * gi + 1];
+          dgw += r * (al * s2 + (be - mean_u) * s1);
+          dgb += s1;
+        }
       }
+      u1 = warp_sum_d(u1); u2raw = warp_sum_d(u2raw);
+      if (prm.use_gn) { dgw = warp_sum_d(dgw); dgb = warp_sum_d(dgb); }
+      if (lane == 0) { part[warp][0] = u1; part[warp][1] = u2raw; part[warp][2] = dgw; part[warp][3] = dgb; }
     }
-    u1 = warp_sum_d(u1); u2raw = warp_sum_d(u2raw);
-    if (prm.use_gn) { dgw = warp_sum_d(dgw); dgb = warp_sum_d(dgb); }
-    if (lane == 0) {
+    __syncthreads();
+    if (tid < cpp && c0 + tid < cl) {
+      const int ch = ch_lo + c0 + tid;
+      const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
+      double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
+      for (int j = 0; j < wpc; ++j) { u1 += part[tid * wpc + j][0]; u2raw += part[tid * wpc + j][1]; dgw += part[tid * wpc + j][2]; dgb += part[tid * wpc + j][3]; }
       const double u2 = rc * (u2raw - mu * u1);
       saved[off_u(c, n, G) + 2 * ch] = (float)u1;
       saved[off_u(c, n, G) + 2 * ch + 1] = (float)u2;
       if (prm.use_bn) { if (d_bn_w) d_bn_w[ch] = (float)u2; if (d_bn_b) d_bn_b[ch] = (float)u1; }
       if (prm.use_gn) { if (d_gn_w) d_gn_w[ch] = (float)dgw; if (d_gn_b) d_gn_b[ch] = (float)dgb; }
     }
+    __syncthreads();
   }
-  __syncthreads();
   // 3. P, Q, R per (n, c)
   const double m = (double)n * hw;
   for (int j = tid; j < n * cl; j += nt) {
@@ -519,6 +558,36 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
       }
     }
     pqr[3 * (size_t)i] = (float)P; pqr[3 * (size_t)i + 1] = (float)Q; pqr[3 * (size_t)i + 2] = (float)R;
+  }
+  // 4. convolution-bias gradient in closed form (piecewise-linear activations): d_bias[c] = sum over (n, hw) of act'(y) * (P*dz + Q*y + R)
+  //    = sum_n P*(sl*Sdz + (1-sl)*S1) + Q*(sl*Sy + (1-sl)*S2) + R*(sl*hw + (1-sl)*S3), sl = slope (0 for ReLU, 1 for no activation).
+  if (d_bias) {
+    __syncthreads();   // pqr of this CTA's channels (written above, read back below by other threads)
+    const double sl = act == DCV_ACT_NONE ? 1.0 : (act == DCV_ACT_RELU ? 0.0 : (double)slope);
+    for (int c0 = 0; c0 < cl; c0 += cpp) {
+      const int chl = c0 + warp / wpc, sub = warp % wpc;
+      if (warp / wpc < cpp && chl < cl) {
+        const int ch = ch_lo + chl;
+        double acc = 0.0;
+        for (int img = sub * 32 + lane; img < n; img += wpc * 32) {
+          const size_t i = (size_t)img * c + ch;
+          const double P = (double)pqr[3 * i], Q = (double)pqr[3 * i + 1], R = (double)pqr[3 * i + 2];
+          const double sdz = (double)s[kBwdSums * i], sy = (double)stats[2 * i];
+          double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+          if (act != DCV_ACT_NONE) { m1 = (double)s[kBwdSums * i + 2]; m2 = (double)s[kBwdSums * i + 3]; m3 = (double)s[kBwdSums * i + 4]; }
+          acc += P * (sl * sdz + (1.0 - sl) * m1) + Q * (sl * sy + (1.0 - sl) * m2) + R * (sl * hw + (1.0 - sl) * m3);
+        }
+        acc = warp_sum_d(acc);
+        if (lane == 0) part[warp][0] = acc;
+      }
+      __syncthreads();
+      if (tid < cpp && c0 + tid < cl) {
+        double acc = 0.0;
+        for (int j = 0; j < wpc; ++j) acc += part[tid * wpc + j][0];
+        d_bias[ch_lo + c0 + tid] = (float)acc;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -561,10 +630,11 @@ int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dty
   return 0;
 }
 
-// Channels per finalize CTA: whole GroupNorm groups, about 4096 (image, channel) items per CTA, at most one CTA per SM.
+// Channels per finalize CTA: whole GroupNorm groups, about 512 (image, channel) items per CTA (a 1024-thread CTA then makes one pass over them; ncu on
+// the former single-CTA launch for the CIFAR layers: 13 us of serial latency), at most one CTA per SM.
 static void finalize_grid(const dcv_norm_params* prm, int* cpb, int* blocks) {
   const int cg = prm->use_gn ? prm->c / prm->gn_groups : 1;
-  int per = 4096 / (prm->n > 0 ? prm->n : 1);
+  int per = 512 / (prm->n > 0 ? prm->n : 1);
   if (per < 1) per = 1;
   per = (per + cg - 1) / cg * cg;
   while ((prm->c + per - 1) / per > dcv::kNumSMs) per += cg;
@@ -607,30 +677,34 @@ int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw
   return 0;
 }
 
-int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream) {
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int act, int dtype, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(dz && y && s_nc, "norm_bwd_reduce: null pointer");
   if (check_nc("norm_bwd_reduce", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(s_nc, 0, (size_t)n * c * 2 * sizeof(float), st);
+  cudaMemsetAsync(s_nc, 0, (size_t)n * c * kBwdSums * sizeof(float), st);
   dim3 grid; int block;
-  DCV_DISPATCH_DTYPE(dtype, T, {
-    constexpr int VE = 16 / sizeof(T);
-    if (vec_ok(dz, y, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, VE>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
-    else { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, 1>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
-  });
+#define DCV_BWD_REDUCE(MASK_)                                                                                                                                   \
+  DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                                \
+    constexpr int VE = 16 / sizeof(T);                                                                                                                          \
+    if (vec_ok(dz, y, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, VE, MASK_>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, VE, MASK_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); } \
+    else { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, 1, MASK_>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, 1, MASK_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); } \
+  })
+  if (act == DCV_ACT_RELU || act == DCV_ACT_LEAKY_RELU) { DCV_BWD_REDUCE(1); } else { DCV_BWD_REDUCE(0); }
+#undef DCV_BWD_REDUCE
   DCV_LAUNCH_CHECK("bwd_reduce_kernel");
   return 0;
 }
 
 int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
-                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream) {
+                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, int act, float slope, float* d_bias_c, void* stream) {
   using namespace dcv;
   if (check_norm_params(prm, "norm_bwd_finalize")) return 1;
   DCV_REQUIRE(stats_nc && s_nc && saved && pqr_nc, "norm_bwd_finalize: null pointer");
+  DCV_REQUIRE(!d_bias_c || act == DCV_ACT_NONE || act == DCV_ACT_RELU || act == DCV_ACT_LEAKY_RELU, "norm_bwd_finalize: the closed-form bias gradient needs a piecewise-linear activation (got %d); use act_norm_bwd_apply's dbias", act);
   int cpb, blocks;
   finalize_grid(prm, &cpb, &blocks);
-  bwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias, cpb);
+  bwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias, act, slope, d_bias_c, cpb);
   DCV_LAUNCH_CHECK("bwd_finalize_kernel");
   return 0;
 }
