@@ -458,13 +458,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const WgradArgs 
 // column taps of that row (S*16 accumulators); it walks output rows y (strided over the threads that share the unit) and slides along x keeping the
 // S input columns of row y+r in registers: per pixel 2 shared 128-bit loads (dy, newest input column) feed 16*S FMAs.
 template <typename T, int S, int TW, int TH, int KC, int CC>
-__global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradArgs a) {
-  constexpr int NT = 256, NPIX = TW * TH, TWP = TW + 1;   // TWP: odd row pitch (in pixels) of the staged dy tile => conflict-free 128-bit loads across rows   // KC / CC: channel slab widths (4, 8 or 16) = shared-memory pixel strides
+__global__ void __launch_bounds__(256, 2) conv_wgrad_direct_s1_kernel(const WgradArgs a) {   // <= 128 registers: 2 CTAs of 256 threads or 3 of 160 per SM
+  constexpr int NPIX = TW * TH, TWP = TW + 1;   // TWP: odd row pitch (in pixels) of the staged dy tile => conflict-free 128-bit loads across rows   // KC / CC: channel slab widths (4, 8 or 16) = shared-memory pixel strides
   extern __shared__ __align__(16) float smem[];
   const dcv_conv_shape& s = a.s;
   float* s_dy = smem;                 // [NPIX][KC]
   float* s_x = smem + TH * TWP * KC;  // [in_th][in_tw (odd)][CC]
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, NT = blockDim.x;   // NT = units * L rounded up to whole warps (<= 256): no idle warps holding registers
   const int tile = blockIdx.x, tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
   int z = blockIdx.z;
   const int k0 = (z % a.kslabs) * KC; z /= a.kslabs;
@@ -563,24 +563,50 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_s1_kernel(const WgradAr
       }
     }
   }
-  // combine the L lanes of each unit with shuffles, then one atomic per dw element
+  // Combine the L lanes of each unit. Halving butterfly over the 16 (k, c) register-block entries: at lane bit b a lane keeps one half of its live
+  // entries and receives the partner's sums of that half, so after log2(min(L, 16)) steps every lane owns 16 / min(L, 16) entries, fully summed over
+  // those lanes (15 shuffles per tap instead of 16 per step), then (L == 32) one plain exchange. The atomics are spread over the lanes as well.
+  // (First version: every lane reduced all 16 * S values with log2(L) shuffle steps each and lane 0 issued all the atomics: ~35 % of the kernel's
+  // instructions on the 4-channel 5x5 layers.)
+  int cur_shift = 0;   // entries still live per tap = 16 >> cur_shift
+  if (warp_has_work) {
 #pragma unroll
-  for (int ss = 0; ss < S; ++ss) {
+    for (int st = 0; st < 4; ++st) {
+      const int b = 1 << st;
+      if (b < L) {
+        const bool upper = (part & b) != 0;
+        const int half = 8 >> st;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float v = acc[ss][i];
-      if (warp_has_work) for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[ss][i] = v;
+        for (int ss = 0; ss < S; ++ss)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < half) {
+              const float send = upper ? acc[ss][j] : acc[ss][j + half];
+              const float keep = upper ? acc[ss][j + half] : acc[ss][j];
+              acc[ss][j] = keep + __shfl_xor_sync(0xffffffffu, send, b);
+            }
+        cur_shift = st + 1;
+      }
     }
-    if (active && part == 0) {
+    if (L == 32) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int ss = 0; ss < S; ++ss) acc[ss][0] += __shfl_xor_sync(0xffffffffu, acc[ss][0], 16);
+    }
+  }
+  if (active && part < 16) {
+    const int live = 16 >> cur_shift;
+    // entry index of acc[.][j]: the halving steps consumed the index bits from the top (bit 3 at lane bit 0, bit 2 at lane bit 1, ...)
+    int ibase = 0;
+    for (int st = 0; st < cur_shift; ++st) ibase += ((part >> st) & 1) * (8 >> st);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kk = k0 + kq * 4 + i, cc = c0 + cq * 4 + j;
-          if (kk < s.k && cc < s.c) atomicAdd(a.dw + (((size_t)kk * s.r + rr) * S + ss) * s.c + cc, acc[ss][i * 4 + j]);
+    for (int ss = 0; ss < S; ++ss)
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < live) {
+          const int e = ibase + j, i = e >> 2, jj = e & 3;
+          const int kk = k0 + kq * 4 + i, cc = c0 + cq * 4 + jj;
+          if (kk < s.k && cc < s.c) atomicAdd(a.dw + (((size_t)kk * s.r + rr) * S + ss) * s.c + cc, acc[ss][j]);
         }
-    }
   }
 }
 
@@ -756,8 +782,15 @@ static int launch_wgrad_s1_cfg(WgradArgs a, cudaStream_t st) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   // Exactly one resident wave of CTAs when the batch allows it (ncu on the 4->4 5x5 layer: 128 registers => 2 CTAs per SM = 296 slots, and the former
   // "4 per SM" guess launched 594 CTAs = 2.01 waves, the last two CTAs costing a third of the kernel); at most 8 images per CTA otherwise.
+  // threads = (filter rows x 4k x 4c register blocks) x L lanes each, whole warps; same rule as in the kernel
+  const int units_full = s.r * ((KC < s.k ? KC : s.k) + 3) / 4 * (((CC < s.c ? CC : s.c) + 3) / 4);
+  int lanes = 32;
+  while (lanes > 1 && units_full * lanes > 256) lanes >>= 1;
+  int nthreads = (units_full * lanes + 31) / 32 * 32;
+  if (nthreads > 256) nthreads = 256;
+  if (nthreads < 64) nthreads = 64;
   int occ = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem) != cudaSuccess || occ < 1) occ = 1;
   long long gy = (long long)kNumSMs * occ / ((long long)tiles * slabs);
   if (gy < 1) gy = 1;
   const long long elems = (long long)s.k * s.r * s.s * s.c;
@@ -769,7 +802,7 @@ static int launch_wgrad_s1_cfg(WgradArgs a, cudaStream_t st) {
   a.vec_dy = (s.k % 4 == 0 && reinterpret_cast<uintptr_t>(a.dy) % (4 * sizeof(T)) == 0) ? 1 : 0;
   a.vec_x = (s.c % 4 == 0 && reinterpret_cast<uintptr_t>(a.x) % (4 * sizeof(T)) == 0) ? 1 : 0;
   dim3 grid(tiles, (unsigned)gy, (unsigned)slabs);
-  kern<<<grid, 256, smem, st>>>(a);
+  kern<<<grid, nthreads, smem, st>>>(a);
   DCV_LAUNCH_CHECK("conv_wgrad_direct_s1_kernel");
   return 0;
 }

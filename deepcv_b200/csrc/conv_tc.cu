@@ -125,35 +125,44 @@ struct FwdParams {
 
 // A pipeline stage holds G consecutive k-blocks (G A slabs + G B slabs) behind ONE full/empty barrier pair: with 64 output channels a k-block is only
 // 4 x 32 MMA cycles, and the single-thread producer / issuer loops (mbarrier try_wait ~90 cycles each) would otherwise dominate.
-template <int N_TILE>
+// RES = 1 (64 -> 64 channel 3x3 layers: all R*S*C/64 <= 9 weight slabs = 72 KB): the weights are loaded ONCE per CTA into a resident region and the
+// ring only carries the A slabs. These layers are bound by L2 -> SM traffic (24 KB per 1 MFLOP k-block = 44 FLOP/B against a ~12 TB/s TMA ceiling);
+// dropping the 8 KB weight slab per k-block raises that to 66 FLOP/B.
+constexpr int kMaxResidentKb = 9;
+template <int N_TILE, int RES = 0>
 struct FwdSmem {
   static constexpr int G = N_TILE == 64 ? 3 : (N_TILE == 128 ? 2 : 1);
   static constexpr int kStages = N_TILE == 256 ? 4 : 3;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = N_TILE * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = G * (A_BYTES + B_BYTES);
-  static constexpr size_t kBytes = 1024 /* alignment slack */ + (size_t)kStages * STAGE_BYTES + 256;
+  static constexpr int STAGE_BYTES = RES ? G * A_BYTES : G * (A_BYTES + B_BYTES);
+  static constexpr int RES_BYTES = RES ? kMaxResidentKb * B_BYTES : 0;
+  static constexpr size_t kBytes = 1024 /* alignment slack */ + (size_t)RES_BYTES + (size_t)kStages * STAGE_BYTES + 256;
 };
 
-template <int N_TILE>
+template <int N_TILE, int RES>
 __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FwdParams prm) {
-  using S = FwdSmem<N_TILE>;
+  using S = FwdSmem<N_TILE, RES>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // resident weight slabs (RES), then the ring
+  const uint32_t base = res_base + S::RES_BYTES;
   constexpr int G = S::G;
   const uint32_t bars = base + kStages * S::STAGE_BYTES;        // 8-byte mbarriers
   auto slab_a = [&](int stage, int j) { return base + stage * S::STAGE_BYTES + j * S::A_BYTES; };
   auto slab_b = [&](int stage, int j) { return base + stage * S::STAGE_BYTES + G * S::A_BYTES + j * S::B_BYTES; };
+  auto slab_res = [&](int kb) { return res_base + kb * S::B_BYTES; };
   auto full = [&](int i) { return bars + 8u * i; };
   auto empty = [&](int i) { return bars + 8u * (kStages + i); };
   auto tfull = [&](int i) { return bars + 8u * (2 * kStages + i); };
   auto tempty = [&](int i) { return bars + 8u * (2 * kStages + 2 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  const uint32_t bres = bars + 8u * (2 * kStages + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    mbar_init(bres, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
@@ -175,6 +184,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (RES) {   // all weight slabs, once (RES implies a single output-channel tile)
+        mbar_expect_tx(bres, (uint32_t)num_kb * S::B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab_res(kb), &map_w, bres, kb * BLOCK_K, 0);
+      }
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
         const int nt = tile % prm.n_tiles_k;
         int pt = tile / prm.n_tiles_k;
@@ -188,10 +201,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
         for (int kb0 = 0; kb0 < num_kb; kb0 += G) {
           const int cnt = min(G, num_kb - kb0);
           mbar_wait(empty(stage), phase ^ 1u);
-          mbar_expect_tx(full(stage), (uint32_t)cnt * (S::A_BYTES + S::B_BYTES));
+          mbar_expect_tx(full(stage), (uint32_t)cnt * (RES ? S::A_BYTES : S::A_BYTES + S::B_BYTES));
           for (int j = 0; j < cnt; ++j) {
             tma_load_4d(slab_a(stage, j), &map_x, full(stage), cb * BLOCK_K, q0 + ss - prm.pad_w, p0 + rr - prm.pad_h, n0);
-            tma_load_2d(slab_b(stage, j), &map_w, full(stage), (rr * prm.s + ss) * prm.c + cb * BLOCK_K, nt * N_TILE);
+            if (!RES) tma_load_2d(slab_b(stage, j), &map_w, full(stage), (rr * prm.s + ss) * prm.c + cb * BLOCK_K, nt * N_TILE);
             if (++cb == cblocks) { cb = 0; if (++ss == prm.s) { ss = 0; if (++rr == prm.r) rr = 0; } }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -204,17 +217,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
       constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
+      // the producer starts every tile at k-block kstart (see there); with resident weights the slab index must follow it
+      const int kstart = (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)num_kb);
+      if (RES) mbar_wait(bres, 0);
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * N_TILE);
+        int kb = kstart;
         for (int kb0 = 0; kb0 < num_kb; kb0 += G) {
           const int cnt = min(G, num_kb - kb0);
           mbar_wait(full(stage), phase);
           tc_fence_after();
           for (int j = 0; j < cnt; ++j) {
             const uint64_t adesc = make_desc(slab_a(stage, j), 0, 1024);
-            const uint64_t bdesc = make_desc(slab_b(stage, j), 0, 1024);
+            const uint64_t bdesc = make_desc(RES ? slab_res(kb) : slab_b(stage, j), 0, 1024);
+            if (++kb == num_kb) kb = 0;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kb0 | j | k) != 0);
@@ -309,10 +327,10 @@ static int num_sms() {
   return sms;
 }
 
-template <int N_TILE>
+template <int N_TILE, int RES = 0>
 static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const FwdParams& prm, cudaStream_t st) {
-  auto kern = conv_fwd_tc_kernel<N_TILE>;
-  const size_t smem = FwdSmem<N_TILE>::kBytes;
+  auto kern = conv_fwd_tc_kernel<N_TILE, RES>;
+  const size_t smem = FwdSmem<N_TILE, RES>::kBytes;
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
@@ -581,6 +599,7 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   int rc;
   if (n_tile == 256) rc = launch_fwd<256>(mx, mw, prm, st);
   else if (n_tile == 128) rc = launch_fwd<128>(mx, mw, prm, st);
+  else if (prm.n_tiles_k == 1 && s->r * s->s * (s->c / BLOCK_K) <= kMaxResidentKb && getenv("DCV_TC_NO_RESIDENT") == nullptr) rc = launch_fwd<64, 1>(mx, mw, prm, st);
   else rc = launch_fwd<64>(mx, mw, prm, st);
   if (rc) return rc;
   if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);

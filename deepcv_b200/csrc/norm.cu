@@ -98,15 +98,16 @@ __device__ __forceinline__ int chan_of(const NcGeom& g, int colg, int ve, int e)
 template <int VE, int NV>
 __device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcGeom& g, int col, int row, float* dst, int dst_stride) {
   constexpr int PER = VE * NV;
-  static_assert(PER <= 40, "column_reduce_atomic: too many values per thread");
-  __shared__ float red[256 * PER];  // [row][col][NV*VE] flattened
+  static_assert(PER <= 16, "column_reduce_atomic: too many values per thread");
+  constexpr int PST = PER + 1;           // odd per-thread stride: the 16 stores of a warp's 32 threads would otherwise hit 2 banks (16-way conflict)
+  __shared__ float red[256 * PST];  // [row][col][NV*VE] flattened
   __shared__ float red2[256];
   const int t = row * g.cols_per_block + col;
   __syncthreads();   // previous use of red / red2
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int e = 0; e < VE; ++e) red[t * PER + v * VE + e] = acc[v][e];
+    for (int e = 0; e < VE; ++e) red[t * PST + v * VE + e] = acc[v][e];
   __syncthreads();
   const int epc = g.pack > 1 ? g.c : VE;                  // distinct channels per column
   const int outs = g.cols_per_block * NV * epc, nthr = blockDim.x;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void column_reduce_atomic(float (*acc)[VE], const NcG
     const int cl = oo / (NV * epc), k = oo - cl * (NV * epc), v = k / epc, e0 = k - v * epc;
     float s = 0.f;
     for (int r = part; r < g.rows; r += parts)
-      for (int e = e0; e < VE; e += epc) s += red[(r * g.cols_per_block + cl) * PER + v * VE + e];
+      for (int e = e0; e < VE; e += epc) s += red[(r * g.cols_per_block + cl) * PST + v * VE + e];
     if (parts > 1) red2[o] = s;
     else {
       const int colg = blockIdx.z * g.cols_per_block + cl;
@@ -144,6 +145,11 @@ template <typename T, int VE> __device__ __forceinline__ Raw<T, VE> load_raw(con
   if constexpr (VE == 1) r.v = *p; else r.v = *reinterpret_cast<const uint4*>(p);
   return r;
 }
+template <typename T, int VE> __device__ __forceinline__ Raw<T, VE> zero_raw() {
+  Raw<T, VE> r;
+  if constexpr (VE == 1) r.v = from_f<T>(0.f); else r.v = make_uint4(0u, 0u, 0u, 0u);
+  return r;
+}
 template <typename T, int VE> __device__ __forceinline__ void unpack_raw(const Raw<T, VE>& r, float* out) {
   if constexpr (VE == 1) out[0] = to_f<T>(r.v); else vec_unpack<T>(r.v, out);
 }
@@ -153,7 +159,7 @@ template <typename T, int VE> __device__ __forceinline__ void unpack_raw(const R
 constexpr int UNR = DCV_UNR;   // rows in flight per thread: the bf16 kernels were latency-bound at ~45 % of HBM with one load per iteration
 
 // ---- statistics: stats[n][c][2] += {sum y, sum y^2}
-constexpr int SUNR = 2 * UNR;   // one tensor only: twice the rows in flight to cover the HBM latency-bandwidth product
+constexpr int SUNR = UNR;   // (8 rows in flight measured no better than 4, and slower once the tail loads were predicated)
 template <typename T, int VE>
 __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, float* __restrict__ stats, const NcGeom g) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
@@ -164,11 +170,12 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, flo
     for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
     if (colg < g.cv) {
       const T* base = y + ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
-      int p = p0 + row;
-      for (; p + (SUNR - 1) * g.rows < p1; p += SUNR * g.rows) {
+      // SUNR rows in flight per thread; the loads of a short range / the tail are predicated, not serialised (a thread with 6 rows used to issue 6
+      // dependent loads: 15 us for the 12.8 MB 7x7 tensors)
+      for (int p = p0 + row; p < p1; p += SUNR * g.rows) {
         Raw<T, VE> r[SUNR];
 #pragma unroll
-        for (int u = 0; u < SUNR; ++u) r[u] = load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.span);
+        for (int u = 0; u < SUNR; ++u) r[u] = (p + u * g.rows < p1) ? load_raw<T, VE>(base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
 #pragma unroll
         for (int u = 0; u < SUNR; ++u) {
           float v[VE];
@@ -176,12 +183,6 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, flo
 #pragma unroll
           for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
         }
-      }
-      for (; p < p1; p += g.rows) {
-        float v[VE];
-        load_vec<T, VE>(base + (size_t)p * g.span, v);
-#pragma unroll
-        for (int e = 0; e < VE; ++e) { acc[0][e] += v[e]; acc[1][e] = fmaf(v[e], v[e], acc[1][e]); }
       }
     }
     column_reduce_atomic<VE, 2>(acc, g, col, row, stats + (size_t)img * g.c * 2, 2);
@@ -202,75 +203,55 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
       A[e] = t.x; B[e] = t.y;
     }
     const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
-    int p = p0 + row;
-    for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+    for (int p = p0 + row; p < p1; p += UNR * g.rows) {
       Raw<T, VE> r[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) r[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span);
+      for (int u = 0; u < UNR; ++u) r[u] = (p + u * g.rows < p1) ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         float v[VE];
         unpack_raw<T, VE>(r[u], v);
 #pragma unroll
         for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
-        store_vec<T, VE>(z + base + (size_t)(p + u * g.rows) * g.span, v);
+        if (p + u * g.rows < p1) store_vec<T, VE>(z + base + (size_t)(p + u * g.rows) * g.span, v);
       }
-    }
-    for (; p < p1; p += g.rows) {
-      float v[VE];
-      load_vec<T, VE>(y + base + (size_t)p * g.span, v);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
-      store_vec<T, VE>(z + base + (size_t)p * g.span, v);
     }
   });
 }
 
-// ---- backward reduce: s[n][c][5] += {sum dz, sum dz*y, sum_{y>0} dz, sum_{y>0} y, #{y>0}}
-// The last three (MASK = 1: ReLU / LeakyReLU blocks with a convolution bias) let the finalize kernel produce the bias gradient in closed form:
-// dy = act'(y) * (P*dz + Q*y + R) with act'(y) in {1, slope} piecewise constant, so sum dy is bilinear in these per-(n,c) sums and the apply pass
-// stays a pure streaming map (no CTA reduction, no same-address atomics).
-constexpr int kBwdSums = 5;
-template <typename T, int VE, int MASK>
+// ---- backward reduce: s[n][c][2] += {sum dz, sum dz*y}
+// (Tried and dropped: three more activation-mask sums here so that the finalize kernel could give the convolution-bias gradient in closed form and the
+// apply pass would need no reduction. Measured on B200: the reduce went from 42.7 to 60.5 us on the 64-channel 56x56 tensor — 40 accumulators per thread,
+// ALU-bound — while the apply only gained 65.2 -> 62.6 us.)
+constexpr int kBwdSums = 2;
+template <typename T, int VE>
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y, float* __restrict__ s, const NcGeom g) {
-  constexpr int NV = MASK ? 5 : 2;
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
   for_each_segment(g, [&](int img, int p0, int p1) {
-    float acc[NV][VE];
+    float acc[2][VE];
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int e = 0; e < VE; ++e) acc[v][e] = 0.f;
-    auto add = [&](const float* a, const float* b) {
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]);
-        if (MASK) { const bool pos = b[e] > 0.f; acc[2][e] += pos ? a[e] : 0.f; acc[3][e] += pos ? b[e] : 0.f; acc[4][e] += pos ? 1.f : 0.f; }
-      }
-    };
+    for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
     if (colg < g.cv) {
       const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
-      int p = p0 + row;
-      for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+      for (int p = p0 + row; p < p1; p += UNR * g.rows) {
         Raw<T, VE> ra[UNR], rb[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span); }
+        for (int u = 0; u < UNR; ++u) {
+          const bool on = p + u * g.rows < p1;
+          ra[u] = on ? load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+          rb[u] = on ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+        }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           float a[VE], b[VE];
           unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
-          add(a, b);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
         }
       }
-      for (; p < p1; p += g.rows) {
-        float a[VE], b[VE];
-        load_vec<T, VE>(dz + base + (size_t)p * g.span, a);
-        load_vec<T, VE>(y + base + (size_t)p * g.span, b);
-        add(a, b);
-      }
     }
-    column_reduce_atomic<VE, NV>(acc, g, col, row, s + (size_t)img * g.c * kBwdSums, kBwdSums);
+    column_reduce_atomic<VE, 2>(acc, g, col, row, s + (size_t)img * g.c * kBwdSums, kBwdSums);
   });
 }
 
@@ -313,23 +294,22 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz
         }
         store_vec<T, VE>(dy + off, a);
       };
-      int p = p0 + row;
-      for (; p + (UNR - 1) * g.rows < p1; p += UNR * g.rows) {
+      for (int p = p0 + row; p < p1; p += UNR * g.rows) {
         Raw<T, VE> ra[UNR], rb[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { ra[u] = load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span); rb[u] = load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span); }
+        for (int u = 0; u < UNR; ++u) {
+          const bool on = p + u * g.rows < p1;
+          ra[u] = on ? load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+          rb[u] = on ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+        }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          float a[VE], b[VE];
-          unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
-          one(a, b, base + (size_t)(p + u * g.rows) * g.span);
+          if (p + u * g.rows < p1) {
+            float a[VE], b[VE];
+            unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+            one(a, b, base + (size_t)(p + u * g.rows) * g.span);
+          }
         }
-      }
-      for (; p < p1; p += g.rows) {
-        float a[VE], b[VE];
-        load_vec<T, VE>(dz + base + (size_t)p * g.span, a);
-        load_vec<T, VE>(y + base + (size_t)p * g.span, b);
-        one(a, b, base + (size_t)p * g.span);
       }
     });
   }
@@ -466,8 +446,7 @@ __device__ __forceinline__ void gn_adjoint_coeffs(const dcv_norm_params& prm, co
 
 __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_params prm, const float* __restrict__ stats, const float* __restrict__ s,
                                                             float* __restrict__ saved, float* __restrict__ pqr, float* __restrict__ d_bn_w, float* __restrict__ d_bn_b,
-                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b, const int act, const float slope, float* __restrict__ d_bias,
-                                                            const int cpb) {
+                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b, const int cpb) {
   const int n = prm.n, c = prm.c, G = prm.use_gn ? prm.gn_groups : 1, cg = c / G;
   const double hw = (double)prm.hw;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -559,36 +538,6 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
     }
     pqr[3 * (size_t)i] = (float)P; pqr[3 * (size_t)i + 1] = (float)Q; pqr[3 * (size_t)i + 2] = (float)R;
   }
-  // 4. convolution-bias gradient in closed form (piecewise-linear activations): d_bias[c] = sum over (n, hw) of act'(y) * (P*dz + Q*y + R)
-  //    = sum_n P*(sl*Sdz + (1-sl)*S1) + Q*(sl*Sy + (1-sl)*S2) + R*(sl*hw + (1-sl)*S3), sl = slope (0 for ReLU, 1 for no activation).
-  if (d_bias) {
-    __syncthreads();   // pqr of this CTA's channels (written above, read back below by other threads)
-    const double sl = act == DCV_ACT_NONE ? 1.0 : (act == DCV_ACT_RELU ? 0.0 : (double)slope);
-    for (int c0 = 0; c0 < cl; c0 += cpp) {
-      const int chl = c0 + warp / wpc, sub = warp % wpc;
-      if (warp / wpc < cpp && chl < cl) {
-        const int ch = ch_lo + chl;
-        double acc = 0.0;
-        for (int img = sub * 32 + lane; img < n; img += wpc * 32) {
-          const size_t i = (size_t)img * c + ch;
-          const double P = (double)pqr[3 * i], Q = (double)pqr[3 * i + 1], R = (double)pqr[3 * i + 2];
-          const double sdz = (double)s[kBwdSums * i], sy = (double)stats[2 * i];
-          double m1 = 0.0, m2 = 0.0, m3 = 0.0;
-          if (act != DCV_ACT_NONE) { m1 = (double)s[kBwdSums * i + 2]; m2 = (double)s[kBwdSums * i + 3]; m3 = (double)s[kBwdSums * i + 4]; }
-          acc += P * (sl * sdz + (1.0 - sl) * m1) + Q * (sl * sy + (1.0 - sl) * m2) + R * (sl * hw + (1.0 - sl) * m3);
-        }
-        acc = warp_sum_d(acc);
-        if (lane == 0) part[warp][0] = acc;
-      }
-      __syncthreads();
-      if (tid < cpp && c0 + tid < cl) {
-        double acc = 0.0;
-        for (int j = 0; j < wpc; ++j) acc += part[tid * wpc + j][0];
-        d_bias[ch_lo + c0 + tid] = (float)acc;
-      }
-      __syncthreads();
-    }
-  }
 }
 
 // 16-byte vectors are usable when a pixel is a whole number of vectors, or a vector a whole number of pixels (and of an image's pixels)
@@ -677,34 +626,30 @@ int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw
   return 0;
 }
 
-int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int act, int dtype, void* stream) {
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(dz && y && s_nc, "norm_bwd_reduce: null pointer");
   if (check_nc("norm_bwd_reduce", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(s_nc, 0, (size_t)n * c * kBwdSums * sizeof(float), st);
   dim3 grid; int block;
-#define DCV_BWD_REDUCE(MASK_)                                                                                                                                   \
-  DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                                \
-    constexpr int VE = 16 / sizeof(T);                                                                                                                          \
-    if (vec_ok(dz, y, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, VE, MASK_>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, VE, MASK_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); } \
-    else { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, 1, MASK_>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, 1, MASK_><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); } \
-  })
-  if (act == DCV_ACT_RELU || act == DCV_ACT_LEAKY_RELU) { DCV_BWD_REDUCE(1); } else { DCV_BWD_REDUCE(0); }
-#undef DCV_BWD_REDUCE
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (vec_ok(dz, y, nullptr, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, VE>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, VE><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
+    else { static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, 1>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); bwd_reduce_kernel<T, 1><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, s_nc, g); }
+  });
   DCV_LAUNCH_CHECK("bwd_reduce_kernel");
   return 0;
 }
 
 int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
-                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, int act, float slope, float* d_bias_c, void* stream) {
+                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream) {
   using namespace dcv;
   if (check_norm_params(prm, "norm_bwd_finalize")) return 1;
   DCV_REQUIRE(stats_nc && s_nc && saved && pqr_nc, "norm_bwd_finalize: null pointer");
-  DCV_REQUIRE(!d_bias_c || act == DCV_ACT_NONE || act == DCV_ACT_RELU || act == DCV_ACT_LEAKY_RELU, "norm_bwd_finalize: the closed-form bias gradient needs a piecewise-linear activation (got %d); use act_norm_bwd_apply's dbias", act);
   int cpb, blocks;
   finalize_grid(prm, &cpb, &blocks);
-  bwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias, act, slope, d_bias_c, cpb);
+  bwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, s_nc, saved, pqr_nc, d_bn_weight, d_bn_bias, d_gn_weight, d_gn_bias, cpb);
   DCV_LAUNCH_CHECK("bwd_finalize_kernel");
   return 0;
 }

@@ -17,8 +17,6 @@ import torch
 
 from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, NormParams, check, lib)
 
-NORM_BWD_SUMS = 5   # DCV_NORM_BWD_SUMS (include/deepcv_b200.h)
-
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count']
 
@@ -241,15 +239,9 @@ class _ConvBlock(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         targets = grad_out or {}
         pqr = d_bn_w = d_bn_b = d_gn_w = d_gn_b = None
-        dbias = None
-        if has_bias:
-            dbias = targets.get('bias', None)
-            dbias = torch.empty((k,), **f32) if dbias is None else dbias
-        # with a piecewise-linear activation the finalize kernel produces the bias gradient in closed form and the apply pass is a pure map
-        dbias_closed_form = cfg.any and has_bias and act in (ACT_NONE, ACT_RELU, ACT_LEAKY_RELU)
         if cfg.any:
-            s_nc = torch.empty((n, k, NORM_BWD_SUMS), **f32)
-            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, act if dbias_closed_form else ACT_NONE, dt, st), 'norm_bwd_reduce')
+            s_nc = torch.empty((n, k, 2), **f32)
+            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, st), 'norm_bwd_reduce')
             pqr = torch.empty((n, k, 3), **f32)
             if cfg.use_bn and bn_w is not None:
                 d_bn_w, d_bn_b = targets.get('bn_w', None), targets.get('bn_b', None)
@@ -261,12 +253,16 @@ class _ConvBlock(torch.autograd.Function):
                 d_gn_b = torch.empty((k,), **f32) if d_gn_b is None else d_gn_b
             prm = _norm_params(cfg, n, k, p * q, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
             check(lib.dcv_norm_bwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(s_nc), _ptr(saved), _ptr(pqr),
-                                            _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), act, slope, _ptr(dbias) if dbias_closed_form else None, st), 'norm_bwd_finalize')
+                                            _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'norm_bwd_finalize')
         need_dy_pass = cfg.any or act != ACT_NONE or has_bias
         dy = dz
+        dbias = None
         if need_dy_pass:
             dy = empty_nhwc(n, k, p, q, y.dtype, dev)
-            check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), None if dbias_closed_form else _ptr(dbias), act, slope, n, p * q, k, dt, st), 'act_norm_bwd_apply')
+            if has_bias:
+                dbias = targets.get('bias', None)
+                dbias = torch.empty((k,), **f32) if dbias is None else dbias
+            check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, st), 'act_norm_bwd_apply')
         dw = None
         if ctx.needs_input_grad[1]:
             dw = targets.get('weight', None)

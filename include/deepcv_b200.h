@@ -112,17 +112,12 @@ size_t dcv_norm_saved_floats(int n, int c, int groups);
 int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, float* ab_nc, float* saved, void* stream);
 /* z = A*y + B. */
 int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw, int c, int dtype, void* stream);
-/* s_nc[n][c][DCV_NORM_BWD_SUMS] = { sum(dz), sum(dz*y), sum_{y>0}(dz), sum_{y>0}(y), #{y>0} } (overwritten). The last three are only computed
- * for `act` = ReLU / LeakyReLU (the activation between the convolution and the norm): they give dcv_norm_bwd_finalize the convolution-bias
- * gradient in closed form. */
-#define DCV_NORM_BWD_SUMS 5
-int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int act, int dtype, void* stream);
+/* s_nc[n][c][2] = { sum(dz), sum(dz*y) } (overwritten). */
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream);
 /* -> pqr_nc[n][c][3] with dy_pre_activation = P*dz + Q*y + R, plus parameter gradients (any may be NULL; overwritten).
- * `saved` is the forward's buffer; its trailing scratch region is written. d_bias_c (may be NULL) receives the gradient of the convolution bias,
- * sum over (n,hw) of act'(y)*(P*dz + Q*y + R); only for act = none / ReLU / LeakyReLU (same `act` as given to dcv_norm_bwd_reduce) — for other
- * activations pass NULL here and let dcv_act_norm_bwd_apply accumulate it. */
+ * `saved` is the forward's buffer; its trailing scratch region is written. */
 int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
-                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, int act, float slope, float* d_bias_c, void* stream);
+                          float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream);
 /* dy = act'(y) * (P*dz + Q*y + R) (pqr_nc == NULL: P=1,Q=R=0); if dbias_c != NULL accumulates sum over (n,hw) of dy into
  * dbias_c[c] (fp32, overwritten). `y` is the activation OUTPUT (ReLU / LeakyReLU / Sigmoid / none are recoverable
  * from it). */

@@ -1,0 +1,125 @@
+""" Kernel-level parity through the C ABI (run on the B200: `pytest -m gpu`): the streaming BatchNorm / GroupNorm kernels, the row-staged im2col and
+the tcgen05 weight gradient on the shapes their work decomposition treats specially — ranges that cross image boundaries, channel counts smaller
+than a 16-byte vector (packed pixels), scalar fallbacks, predicated tails, 1x1 filters whose channel blocks share one MMA. Each is checked against
+the same arithmetic written with stock torch ops in fp64 on the CPU (integer / index work bit-exact, floating point within the stated tolerance). """
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from deepcv_b200._lib import check, lib
+    check(lib.dcv_device_check(), 'device_check')
+    return torch.device('cuda', 0)
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+# (n, hw, c): many images with few pixels (several images per CTA), few images with many pixels (several CTAs per image), packed 1/2/4-channel
+# vectors, channel counts that force the scalar path, more vector columns than threads
+NORM_SHAPES = [(512, 1024, 4), (512, 256, 16), (7, 49, 512), (3, 3136, 64), (33, 5, 3), (2, 10, 2), (4, 6, 1), (5, 77, 24), (2, 9, 4104), (300, 1, 8), (1, 40000, 8)]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('n,hw,c', NORM_SHAPES)
+def test_norm_streaming_kernels(dev, n, hw, c, dtype):
+    """ dcv_norm_stats / _apply_fwd / _bwd_reduce / dcv_act_norm_bwd_apply against fp64 torch on the values as stored (fp32 accumulation on the
+    device: 1e-5 relative on the sums; the maps are exact up to one rounding of the output type). """
+    from deepcv_b200._lib import ACT_LEAKY_RELU, DCV_BF16, DCV_F32, check, lib
+    dt = DCV_F32 if dtype == torch.float32 else DCV_BF16
+    g = torch.Generator().manual_seed(n * 131 + hw * 7 + c)
+    y = torch.randn(n, hw, c, generator=g).to(dtype)
+    dz = torch.randn(n, hw, c, generator=g).to(dtype)
+    ab = torch.randn(n, c, 2, generator=g)
+    pqr = torch.randn(n, c, 3, generator=g)
+    yd, dzd, abd, pqrd = y.to(dev), dz.to(dev), ab.to(dev), pqr.to(dev)
+    y64, dz64 = y.double(), dz.double()
+    st = stream()
+    # statistics
+    stats = torch.full((n, c, 2), 7., device=dev)
+    check(lib.dcv_norm_stats(P(yd), P(stats), n, hw, c, dt, st), 'norm_stats')
+    ref = torch.stack([y64.sum(1), (y64 * y64).sum(1)], -1)
+    assert rel(stats, ref) <= 1e-5
+    # forward apply
+    z = torch.empty_like(yd)
+    check(lib.dcv_norm_apply_fwd(P(yd), P(abd), P(z), n, hw, c, dt, st), 'norm_apply_fwd')
+    zref = (ab[:, None, :, 0].double() * y64 + ab[:, None, :, 1].double())
+    tol = 1e-6 if dtype == torch.float32 else 2.0 ** -8
+    assert float(((z.double().cpu() - zref).abs() / (zref.abs() + 1.)).max()) <= tol
+    # backward reduce
+    s_nc = torch.full((n, c, 2), -3., device=dev)
+    check(lib.dcv_norm_bwd_reduce(P(dzd), P(yd), P(s_nc), n, hw, c, dt, st), 'norm_bwd_reduce')
+    ref = torch.stack([dz64.sum(1), (dz64 * y64).sum(1)], -1)
+    assert rel(s_nc, ref) <= 1e-5
+    # backward apply + bias gradient
+    dy = torch.empty_like(yd)
+    dbias = torch.full((c,), 11., device=dev)
+    check(lib.dcv_act_norm_bwd_apply(P(dzd), P(yd), P(pqrd), P(dy), P(dbias), ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st), 'act_norm_bwd_apply')
+    pre = pqr[:, None, :, 0].double() * dz64 + pqr[:, None, :, 1].double() * y64 + pqr[:, None, :, 2].double()
+    dyref = pre * torch.where(y64 > 0, 1.0, 0.01)
+    assert float(((dy.double().cpu() - dyref).abs() / (dyref.abs() + 1.)).max()) <= tol
+    assert rel(dbias, dyref.sum((0, 1))) <= 1e-4   # summed in fp32 from the unrounded values, whatever the output type
+    # without parameters (P = 1, Q = R = 0) and without a bias gradient
+    check(lib.dcv_act_norm_bwd_apply(P(dzd), P(yd), None, P(dy), None, ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st), 'act_norm_bwd_apply')
+    assert float(((dy.double().cpu() - dz64 * torch.where(y64 > 0, 1.0, 0.01)).abs()).max()) <= (1e-6 if dtype == torch.float32 else 2.0 ** -7 * float(dz64.abs().max()))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('n,c,h,w,r,s,stride,pad,dil', [(2, 3, 224, 224, 7, 7, 2, 3, 1), (3, 3, 33, 29, 7, 7, 2, 3, 1), (2, 5, 17, 19, 3, 3, 1, 1, 1), (2, 16, 24, 24, 3, 3, 2, 1, 1),
+                                                        (2, 8, 20, 20, 3, 3, 1, 2, 2), (1, 1, 9, 40, 5, 3, 3, 0, 1), (2, 4, 12, 12, 1, 1, 1, 0, 1)])
+def test_im2col_bit_exact(dev, n, c, h, w, r, s, stride, pad, dil, dtype):
+    """ dcv_im2col (row-staged kernel) against torch unfold: pure data movement, bit-exact, zero in the padding and in the columns beyond R*S*C. """
+    from deepcv_b200._lib import DCV_BF16, DCV_F32, ConvShape, check, lib
+    dt = DCV_F32 if dtype == torch.float32 else DCV_BF16
+    p = (h + 2 * pad - dil * (r - 1) - 1) // stride + 1
+    q = (w + 2 * pad - dil * (s - 1) - 1) // stride + 1
+    g = torch.Generator().manual_seed(h * w + c)
+    x = torch.randn(n, c, h, w, generator=g).to(dtype)
+    rsc = r * s * c
+    kpad = (rsc + 63) // 64 * 64
+    col = torch.full((n, p, q, kpad), 5., dtype=dtype, device=dev)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    shape = ConvShape(n, h, w, c, 64, r, s, stride, stride, pad, pad, dil, dil, p, q)
+    check(lib.dcv_im2col(ctypes.byref(shape), P(x_nhwc), P(col), kpad, dt, stream()), 'im2col')
+    unf = F.unfold(x.float(), (r, s), dilation=dil, padding=pad, stride=stride)           # [n][c*r*s][p*q], rows ordered (c, r, s)
+    ref = unf.view(n, c, r, s, p, q).permute(0, 4, 5, 2, 3, 1).reshape(n, p, q, rsc)       # -> (r, s, c) fastest c
+    got = col.float().cpu()
+    assert torch.equal(got[..., :rsc], ref)
+    assert float(got[..., rsc:].abs().max()) == 0. if kpad > rsc else True
+
+
+@pytest.mark.parametrize('n,c,hw,k', [(4, 192, 14, 64), (3, 128, 9, 128), (2, 256, 12, 64), (2, 64, 16, 128), (5, 320, 7, 64)])
+def test_tcgen05_wgrad_pointwise_channel_blocks(dev, n, c, hw, k):
+    """ 1x1 filters: the weight gradient groups 3 or 2 consecutive 64-channel blocks of x into one N = 192 / 128 MMA (the im2col GEMM of the stem has
+    c = kpad = 192). bf16 operands, fp32 accumulation: 2e-2 of max|dw| against fp64 on the same bf16 values (measured ~1e-3). """
+    from deepcv_b200._lib import ALGO_TCGEN05, DCV_BF16, ConvShape, check, lib
+    g = torch.Generator().manual_seed(c + k)
+    x = torch.randn(n, hw, hw, c, generator=g).bfloat16()
+    dy = torch.randn(n, hw, hw, k, generator=g).bfloat16()
+    shape = ConvShape(n, hw, hw, c, k, 1, 1, 1, 1, 0, 0, 1, 1, hw, hw)
+    if not lib.dcv_conv2d_tc_supported(ctypes.byref(shape), DCV_BF16, 2):
+        pytest.skip('shape not on the tcgen05 weight-gradient path')
+    dw = torch.full((k, 1, 1, c), 9., device=dev)
+    xd, dyd = x.to(dev), dy.to(dev)   # keep the device copies alive across the asynchronous launch
+    check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xd), P(dyd), P(dw), None, DCV_BF16, ALGO_TCGEN05, stream()), 'conv2d_wgrad')
+    torch.cuda.synchronize()
+    ref = dy.double().reshape(-1, k).t() @ x.double().reshape(-1, c)
+    assert rel(dw.reshape(k, c), ref) <= 2e-2
+    assert rel(dw.reshape(k, c), ref) <= 5e-3, 'fp32 accumulation of bf16 products should be far inside the bf16 tolerance'

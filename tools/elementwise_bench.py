@@ -76,7 +76,6 @@ def main():
             zs = [torch.empty_like(y) for y in ys]
             dz = [torch.randn(n, hw, c, device=dev).to(tdt) for _ in range(min(reps, 4))]
             stats = torch.empty(n, c, 2, device=dev)
-            stats5 = torch.empty(n, c, 5, device=dev)
             ab = torch.rand(n, c, 2, device=dev)
             pqr = torch.rand(n, c, 3, device=dev)
             dbias = torch.empty(c, device=dev)
@@ -84,8 +83,8 @@ def main():
             if 'norm' in what:
                 report(f'stats_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_stats(P(ys[i]), P(stats), n, hw, c, dt, st)), reps), E * es)
                 report(f'apply_fwd_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_apply_fwd(P(ys[i]), P(ab), P(zs[i]), n, hw, c, dt, st)), reps), 2 * E * es)
-                report(f'bwd_reduce_kernel (+ activation-mask sums) {tag}', timeit(lambda i: check(lib.dcv_norm_bwd_reduce(P(dz[i % len(dz)]), P(ys[i]), P(stats5), n, hw, c, ACT_LEAKY_RELU, dt, st)), reps), 2 * E * es)
-                report(f'bwd_apply_kernel (bias gradient from finalize) {tag}', timeit(lambda i: check(lib.dcv_act_norm_bwd_apply(P(dz[i % len(dz)]), P(ys[i]), P(pqr), P(zs[i]), None, ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st)), reps), 3 * E * es)
+                report(f'bwd_reduce_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_bwd_reduce(P(dz[i % len(dz)]), P(ys[i]), P(stats), n, hw, c, dt, st)), reps), 2 * E * es)
+                report(f'bwd_apply_kernel {tag}', timeit(lambda i: check(lib.dcv_act_norm_bwd_apply(P(dz[i % len(dz)]), P(ys[i]), P(pqr), P(zs[i]), P(dbias), ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st)), reps), 3 * E * es)
             if 'pool' in what and hw in (3136, 784, 1024, 256):
                 h = int(hw ** 0.5)
                 outs = [torch.empty(n, h // 2, h // 2, c, device=dev, dtype=tdt) for _ in range(reps)]
