@@ -35,7 +35,7 @@ IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=None, help='timed steps (default: 1000 cifar, 50 imagenet: about half a second of device time)')
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cifar', choices=['cifar', 'imagenet', 'preprocess'])
@@ -44,7 +44,10 @@ def parse_args():
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the bounded CPU baseline sample')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 50 if args.workload == 'imagenet' else 1000
+    return args
 
 
 def workload_spec(name: str, batch):
@@ -63,15 +66,17 @@ def workload_spec(name: str, batch):
 
 
 class ClockSampler:
-    """ nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). """
+    """ nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The sampler is started early and
+    `wait_ready()` blocks until it has delivered its first row, so that even a 100 ms timed region is covered; rows carry the host time at
+    which they were read and `summary(t0, t1)` keeps the ones inside the region (or the nearest one when the region is shorter than a period). """
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index: int, period_ms: int = 20):
+        self.rows, self.proc, self.index, self.period_ms = [], None, index, period_ms
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -81,19 +86,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def wait_ready(self, timeout: float = 10.0):
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(2.5 * self.period_ms / 1e3)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
-    def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+    def summary(self, t0=None, t1=None):
+        rows = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        if t0 is not None and rows:
+            inside = [(t, r) for t, r in rows if t0 <= t <= t1 + 1.5 * self.period_ms / 1e3]
+            rows = inside or [min(rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))]
+        sm = [float(r[0]) for _, r in rows]
+        mx = [float(r[1]) for _, r in rows if r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for _, r in rows for i in range(4) if r[3 + i].lower().startswith('active')})
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
@@ -300,16 +314,20 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    window = {}
+
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        window['t0'] = time.time()
         start.record()
         for i in range(steps):
             fn(warmup + i)
         end.record()
         barrier()
+        window['t1'] = time.time()
         ms = start.elapsed_time(end)
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -321,7 +339,9 @@ def run_b200(args):
     def step_resident(i):
         runner.step(pool_dev[i % pool_n], labels_dev[i % pool_n])
     with ClockSampler(local_rank) as clocks:
+        clocks.wait_ready()
         ms = timed(step_resident, args.steps, max(args.warmup, 3))
+        clock_window = (window['t0'], window['t1'])
     value = world * batch * args.steps / (ms / 1e3)
 
     # ---- end to end: host (pinned) uint8 batches in, loss out, every step
@@ -360,7 +380,7 @@ def run_b200(args):
                 config=dict(workload=spec['label'], per_gpu_batch=batch, global_batch=batch * world, parallelism=f'dp{world}', step='fused u8 preprocess(normalise+flip+crop) + fwd + CE + bwd + '
                             + ('bucketed NCCL all-reduce + ' if world > 1 else '') + 'AdamW' + ('' if args.no_graph else ', one CUDA graph replay per step'),
                             l2='inputs cycle through a pool of %d distinct uint8 batches (%.0f MB > 126 MB L2)' % (pool_n, pool_n * batch_bytes / 1e6), final_loss=losses[-1] if losses else None),
-                e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=clocks.summary(), roofline=roofline, cpu_baseline=cpu)
+                e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=clocks.summary(*clock_window), roofline=roofline, cpu_baseline=cpu)
     print(json.dumps(line))
     shutdown()
 

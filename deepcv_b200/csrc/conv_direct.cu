@@ -700,6 +700,11 @@ template <typename T>
 static int launch_fwd(const DirectConvArgs& a, cudaStream_t st) {
   if (a.s.k <= 4) return launch_fwd_kc<T, 4>(a, st);
   if (a.s.k <= 8) return launch_fwd_kc<T, 8>(a, st);
+  // Small maps (the 16x16 CIFAR layers: one 64-thread tile per image) leave most of the machine idle with 16-channel slabs: 512 CTAs x 2 warps = 7 warps
+  // per SM. 8-channel slabs double the CTAs for the price of staging the input tile twice.
+  static const bool kc16_only = getenv("DCV_FWD_KC16") != nullptr;
+  const long long tiles16 = (long long)((a.s.q + 15) / 16) * ((a.s.p + 15) / 16) * a.s.n * ((a.s.k + 15) / 16);
+  if (!kc16_only && a.s.q < 24 && tiles16 * 64 < (long long)kNumSMs * 1024) return launch_fwd_kc<T, 8>(a, st);
   return launch_fwd_kc<T, 16>(a, st);
 }
 
