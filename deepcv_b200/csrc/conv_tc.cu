@@ -28,6 +28,13 @@ constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// One lane of a converged warp. With `if (lane == 0)` ptxas cannot prove that a single thread executes the warp-level tcgen05 / TMA instructions and wraps
+// each of them in an ELECT + BRA.U.ANY loop (4 extra instructions per MMA: the issue loop, not the tensor pipe, paced the 64-channel layers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       if (RES) {   // all weight slabs, once (RES implies a single output-channel tile)
         mbar_expect_tx(bres, (uint32_t)num_kb * S::B_BYTES);
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one lane) =====
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
@@ -266,6 +273,149 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + nt * N_TILE + c0 : nullptr, prm.slope, dst + c0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N_TILE) : "memory");
+  }
+}
+
+// ---- forward / data gradient, halo variant: 64-channel-class 3x3 layers on large maps (the 64 -> 64 layers at 56x56) ------------------------------
+// Measured ceiling of the per-tap kernel above at N_TILE = 64: 35-38 % of the tensor peak, and it is the SHARED-MEMORY PORT (128 B/clk/SM), not L2: a
+// k-block writes 16 KB (A) + 8 KB (B) through TMA and the four MMAs read the same 24 KB back, 48 KB of port traffic per 128 MMA cycles = 33 %
+// (N_TILE 128: 50 %, 256: 67 % — the three measured plateaus). Keeping the weights resident moved it to 40 %. Here the A operand is written ONCE per tile:
+//   * pixel tile = 8 wide x th <= 16 tall of one image; ONE TMA box {64 ch, 8 + S - 1, th + R - 1} brings the tile with its halo (TMA zero fill =
+//     padding), 180 rows x 128 B for a 3x3 filter instead of nine 16 KB slabs;
+//   * the operand of tap (r, s) is the same buffer read through a K-major SWIZZLE_128B descriptor that starts (r * (8 + S - 1) + s) rows = 128-byte
+//     steps into it, 8-row groups (8 + S - 1) * 128 B apart. Experiment scratch/e1_shift_test.cu (B200): the tcgen05 swizzle is a function of the
+//     absolute shared-memory address, so any 128-byte row offset reads TMA-written data correctly with base_offset = 0 (max error 0 for shifts 0..15);
+//   * all R*S*C/64 weight slabs stay resident (<= 144 KB).
+// Port traffic per tile: 9 x 24 KB of MMA reads + 23 KB of writes instead of + 144 KB.
+struct FwdHaloParams {
+  int n, c, k, r, s, pad_h, pad_w, p, q;
+  int th, tiles_w, tiles_h, total_tiles, stages;
+  int act; float slope;
+  const float* bias;
+  __nv_bfloat16* y;
+};
+
+constexpr int HALO_TW = 8, HALO_STAGE_BYTES = 23 * 1024;   // (16 + 2) x (8 + 2) rows x 128 B = 23040, rounded up to the 1024-byte swizzle period
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FwdHaloParams prm) {
+  constexpr int B_BYTES = N_TILE * BLOCK_K * 2, kMaxStages = 8;
+  extern __shared__ uint8_t smem_raw[];
+  const int cblocks = prm.c / BLOCK_K, num_kb = prm.r * prm.s * cblocks, stages = prm.stages;
+  const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring = res_base + (uint32_t)num_kb * B_BYTES;
+  const uint32_t bars = ring + (uint32_t)stages * HALO_STAGE_BYTES;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (kMaxStages + i); };
+  auto tfull = [&](int i) { return bars + 8u * (2 * kMaxStages + i); };
+  auto tempty = [&](int i) { return bars + 8u * (2 * kMaxStages + 2 + i); };
+  const uint32_t bres = bars + 8u * (2 * kMaxStages + 4), tmem_slot = bars + 8u * (2 * kMaxStages + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int box_w = HALO_TW + prm.s - 1, box_h = prm.th + prm.r - 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    mbar_init(bres, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * N_TILE) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto decode = [&](int tile, int& q0, int& p0, int& img) {
+    q0 = (tile % prm.tiles_w) * HALO_TW; int t = tile / prm.tiles_w;
+    p0 = (t % prm.tiles_h) * prm.th; img = t / prm.tiles_h;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {   // ===== producer: the weights once, then one halo box per (tile, channel block)
+      mbar_expect_tx(bres, (uint32_t)num_kb * B_BYTES);
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(res_base + kb * B_BYTES, &map_w, bres, kb * BLOCK_K, 0);
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t box_bytes = (uint32_t)box_w * box_h * 128u;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        int q0, p0, img; decode(tile, q0, p0, img);
+        for (int cb = 0; cb < cblocks; ++cb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_expect_tx(full(stage), box_bytes);
+          tma_load_4d(ring + stage * HALO_STAGE_BYTES, &map_x, full(stage), cb * BLOCK_K, q0 - prm.pad_w, p0 - prm.pad_h, img);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {   // ===== MMA issuer
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      const uint32_t sbo = (uint32_t)box_w * 128u;
+      mbar_wait(bres, 0);
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * N_TILE);
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t abuf = ring + stage * HALO_STAGE_BYTES;
+          for (int rr = 0; rr < prm.r; ++rr)
+            for (int ss = 0; ss < prm.s; ++ss) {
+              const uint64_t adesc = make_desc(abuf + (uint32_t)(rr * box_w + ss) * 128u, 0, sbo);
+              const uint64_t bdesc = make_desc(res_base + (uint32_t)((rr * prm.s + ss) * cblocks + cb) * B_BYTES, 0, 1024);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          umma_commit(empty(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps: accumulator row = tile pixel (y = row / 8, x = row % 8)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      int q0, p0, img; decode(tile, q0, p0, img);
+      const int q = q0 + xl, p = p0 + yl;
+      const bool valid = yl < prm.th && q < prm.q && p < prm.p;
+      __nv_bfloat16* dst = prm.y + (((size_t)img * prm.p + p) * prm.q + q) * prm.k;
+      mbar_wait(tfull(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0);
       }
       tc_fence_before();
       __syncwarp();
@@ -402,7 +552,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_fwd_tc_v2_kernel(const __g
   };
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== A producer: S column-shifted boxes per channel block
+    if (elect_one()) {   // ===== A producer: S column-shifted boxes per channel block
       int slot = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
         int nt, q0, p0, img; decode(tile, nt, q0, p0, img);
@@ -416,7 +566,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_fwd_tc_v2_kernel(const __g
       }
     }
   } else if (warp == 2) {
-    if (lane == 0) {   // ===== B producer: one weight slab per (channel block, s, r)
+    if (elect_one()) {   // ===== B producer: one weight slab per (channel block, s, r)
       int slot = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
         int nt, q0, p0, img; decode(tile, nt, q0, p0, img);
@@ -431,7 +581,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_fwd_tc_v2_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer
+    if (elect_one()) {   // ===== MMA issuer
       constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
       int aslot = 0, bslot = 0; uint32_t aph = 0, bph = 0;
       int as = 0; uint32_t aphase = 0;
@@ -553,6 +703,62 @@ static int conv_fwd_tc_v2(const dcv_conv_shape* s, const void* x, const void* w,
   return n_tile == 128 ? launch_fwd_v2<128>(mx, mw, prm, st) : launch_fwd_v2<64>(mx, mw, prm, st);
 }
 
+// Halo variant: filters wider than one tap, a single output-channel tile of 64 or 128 whose weight slabs all stay resident (<= 144 KB), and a map that
+// 8 x th tiles cover with <= 15 % overhang (56 x 56: 7 x 4 tiles of 8 x 14, 12.5 %; the 28 / 14 / 7 pixel maps lose more than they gain).
+static bool fwd_halo_applicable(const dcv_conv_shape* s) {
+  static const bool disabled = getenv("DCV_TC_NO_HALO") != nullptr;
+  if (disabled || (s->k != 64 && s->k != 128) || s->r * s->s < 2 || s->r > 3 || s->s > 3) return false;
+  const int num_kb = s->r * s->s * (s->c / BLOCK_K);
+  if ((size_t)num_kb * s->k * BLOCK_K * 2 > 144 * 1024) return false;
+  const int tiles_h = (s->p + 15) / 16, th = (s->p + tiles_h - 1) / tiles_h, tiles_w = (s->q + HALO_TW - 1) / HALO_TW;
+  const double cover = (double)s->p * s->q / ((double)tiles_h * 16 * tiles_w * HALO_TW);
+  (void)th;
+  return cover >= 0.85;
+}
+
+template <int N_TILE>
+static int launch_fwd_halo(const CUtensorMap& mx, const CUtensorMap& mw, const FwdHaloParams& prm, size_t smem, cudaStream_t st) {
+  auto kern = conv_fwd_tc_halo_kernel<N_TILE>;
+  static size_t configured = 0;
+  if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
+  kern<<<grid, kThreads, smem, st>>>(mx, mw, prm);
+  DCV_LAUNCH_CHECK("conv_fwd_tc_halo_kernel");
+  return 0;
+}
+
+static int conv_fwd_tc_halo(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, int act, float slope, cudaStream_t st) {
+  FwdHaloParams prm{};
+  prm.n = s->n; prm.c = s->c; prm.k = s->k; prm.r = s->r; prm.s = s->s; prm.pad_h = s->pad_h; prm.pad_w = s->pad_w; prm.p = s->p; prm.q = s->q;
+  prm.tiles_h = (s->p + 15) / 16;
+  prm.th = (s->p + prm.tiles_h - 1) / prm.tiles_h;
+  prm.tiles_w = (s->q + HALO_TW - 1) / HALO_TW;
+  const long long tiles = (long long)s->n * prm.tiles_h * prm.tiles_w;
+  DCV_REQUIRE(tiles < (1ll << 31), "conv2d_fwd (tcgen05): too many tiles");
+  prm.total_tiles = (int)tiles;
+  prm.act = act; prm.slope = slope; prm.bias = bias; prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+  const size_t res_bytes = (size_t)s->r * s->s * (s->c / BLOCK_K) * s->k * BLOCK_K * 2;
+  int stages = (int)((227 * 1024 - 1024 - 256 - res_bytes) / HALO_STAGE_BYTES);
+  if (stages > 8) stages = 8;
+  DCV_REQUIRE(stages >= 2, "conv2d_fwd (tcgen05 halo): %zu bytes of weights leave no room for the activation ring", res_bytes);
+  prm.stages = stages;
+  const size_t smem = 1024 + res_bytes + (size_t)stages * HALO_STAGE_BYTES + 256;
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)s->c, (cuuint64_t)s->w, (cuuint64_t)s->h, (cuuint64_t)s->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s->c * 2, (cuuint64_t)s->w * s->c * 2, (cuuint64_t)s->h * s->w * s->c * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(HALO_TW + s->s - 1), (cuuint32_t)(prm.th + s->r - 1), 1u};
+    if (make_map(&mx, x, 4, dims, strides, box)) return 1;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)s->r * s->s * s->c, (cuuint64_t)s->k};
+    const cuuint64_t strides[1] = {(cuuint64_t)s->r * s->s * s->c * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)s->k};
+    if (make_map(&mw, w, 2, dims, strides, box)) return 1;
+  }
+  return s->k == 128 ? launch_fwd_halo<128>(mx, mw, prm, smem, st) : launch_fwd_halo<64>(mx, mw, prm, smem, st);
+}
+
 }  // namespace tc
 
 bool conv_tc_fwd_supported(const dcv_conv_shape* s, int dtype) {
@@ -569,6 +775,11 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0), "conv2d_fwd (tcgen05): pointers must be 16-byte aligned");
   if (fwd_v2_applicable(s)) {
     if (conv_fwd_tc_v2(s, x, w, bias, y, act, slope, st)) return 1;
+    if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
+    return 0;
+  }
+  if (fwd_halo_applicable(s)) {
+    if (conv_fwd_tc_halo(s, x, w, bias, y, act, slope, st)) return 1;
     if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
     return 0;
   }
@@ -669,7 +880,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== producer: per pixel tile one dy tile (A ring) then its S column-shifted x tiles (B ring)
+    if (elect_one()) {   // ===== producer: per pixel tile one dy tile (A ring) then its S column-shifted x tiles (B ring)
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       // CTAs of different units walk the same pixel tiles: start each unit at a different tile so that concurrently running CTAs do not all pull the
       // same lines out of one L2 slice at the same moment (measured 3x slower on the 7x7 maps when they did)
@@ -696,7 +907,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer
+    if (elect_one()) {   // ===== MMA issuer
       // ONE MMA covers all S_TAPS taps: N = S_TAPS x 64, the taps' x slabs being the 64-element MN atoms of B, one slab (LBO) apart. Issuing the taps
       // separately re-read the dy operand from shared memory once per tap (6 KB per 32 MMA cycles: shared-memory-read bound at 2/3 of the tensor rate).
       constexpr uint32_t idesc = make_idesc(128, S_TAPS * 64, 1, 1);

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python tools/conv_layer_bench.py --batch 256 --ops fwd,dgrad --only s1 > gpurun_out/conv_layers_halo.log 2>&1; echo "conv layers rc=$?"; cat gpurun_out/conv_layers_halo.log | tail -2 | cut -c1-230
+timeout 300 python bench.py --workload imagenet --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_imagenet.log 2>&1; echo "imagenet rc=$?"; tail -1 gpurun_out/bench_imagenet.log | cut -c1-200

@@ -192,6 +192,11 @@ TC_CASES = [  # n, c, h, w, k, ksize, pad, act, bn
     (2, 256, 9, 11, 512, (3, 3), (1, 1), 'leaky', True),
     (1, 64, 56, 56, 64, (3, 3), (1, 1), 'leaky', True),
     (2, 64, 10, 10, 64, (5, 5), (1, 1), 'relu', False),
+    # halo variant (one TMA box per tile, taps as row-shifted descriptors, resident weights): ragged edges, two channel blocks, N = 128, 2x3 filter
+    (3, 64, 30, 21, 64, (3, 3), (1, 1), 'leaky', True),
+    (2, 128, 40, 24, 64, (3, 3), (1, 1), 'relu', False),
+    (2, 64, 31, 16, 128, (3, 3), (1, 1), 'leaky', True),
+    (2, 64, 16, 24, 64, (2, 3), (0, 1), 'none', False),
 ]
 
 
