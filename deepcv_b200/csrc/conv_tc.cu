@@ -873,6 +873,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Output channels 64..127 of this k tile: when the layer has only 64 of them the second MN atom of the dy operand is all zeros. It is zeroed here once
+  // instead of being zero-filled by a second TMA box per pixel tile (16 KB of shared-memory writes per tile for nothing).
+  const bool second_atom = prm.k > kt * 128 + 64;
+  if (!second_atom) {
+    for (int i = threadIdx.x; i < WG_NA * (WG_SLAB / 16); i += kThreads) {
+      const int slot = i / (WG_SLAB / 16), off = i - slot * (WG_SLAB / 16);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_a + slot * A_BYTES + WG_SLAB + off * 16), "r"(0) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor-core (async proxy) reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -892,9 +902,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
         const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
         const int q0 = pw * prm.tw, p0 = ph * prm.th, n0 = pn * prm.tn;
         mbar_wait(aempty(as), aph ^ 1u);
-        mbar_expect_tx(afull(as), A_BYTES);
+        mbar_expect_tx(afull(as), second_atom ? A_BYTES : WG_SLAB);
         tma_load_4d(smem_a + as * A_BYTES, &map_dy, afull(as), kt * 128, q0, p0, n0);
-        tma_load_4d(smem_a + as * A_BYTES + WG_SLAB, &map_dy, afull(as), kt * 128 + 64, q0, p0, n0);    // zero-filled when k has only 64 channels
+        if (second_atom) tma_load_4d(smem_a + as * A_BYTES + WG_SLAB, &map_dy, afull(as), kt * 128 + 64, q0, p0, n0);
         if (++as == WG_NA) { as = 0; aph ^= 1u; }
         mbar_wait(bempty(bs), bph ^ 1u);
         mbar_expect_tx(bfull(bs), B_BYTES);

@@ -226,6 +226,8 @@ class _ConvBlock(torch.autograd.Function):
             out = empty_nhwc(n, k, p, q, x.dtype, dev)
             check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, p * q, k, dt, st), 'norm_apply_fwd')
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
+        # the fp32 master weight, when it already is [K][R][S][C] in memory: the data-gradient operand is packed straight from it in backward
+        ctx.w_master = weight.detach() if (weight.dtype == torch.float32 and weight.permute(0, 2, 3, 1).is_contiguous()) else None
         ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape)
         return out
 
@@ -285,7 +287,8 @@ class _ConvBlock(torch.autograd.Function):
             if algo != ALGO_DIRECT and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 1):
                 # operand of the data-gradient convolution: [C][R-1-r][S-1-s][K] in the activation dtype
                 wt = torch.empty((shape.c, shape.r, shape.s, shape.k), dtype=y.dtype, device=dev)
-                w32 = _cast_raw(w_op, torch.float32) if w_op.dtype != torch.float32 else w_op
+                # NB: packing from the fp32 master rounds to bf16 once, exactly like the forward operand (a bf16 -> fp32 -> bf16 round trip is the identity)
+                w32 = ctx.w_master if ctx.w_master is not None else (_cast_raw(w_op, torch.float32) if w_op.dtype != torch.float32 else w_op)
                 check(lib.dcv_pack_conv_weight(_ptr(w32), _ptr(wt), dt, shape.k, shape.r, shape.s, shape.c, 1, st), 'pack_conv_weight')
             check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), _ptr(dy), _ptr(w_op), _ptr(wt), _ptr(dx), dt, algo, st), 'conv2d_dgrad')
 
