@@ -52,6 +52,11 @@ SYMBOLS = {
     'dcv_norm_saved_floats': (c_size_t, [c_int, c_int, c_int]),
     'dcv_norm_fwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P]),
     'dcv_norm_apply_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_conv2d_gather_supported': (c_int, [POINTER(ConvShape), P, c_int, c_int]),
+    'dcv_gather_pack_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_gather_unpack_wgrad': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_conv2d_fwd_gather': (c_int, [POINTER(ConvShape), P, P, c_int, P, P, P, c_int, c_float, P]),
+    'dcv_conv2d_wgrad_gather': (c_int, [POINTER(ConvShape), P, P, P, c_int, P]),
     'dcv_norm_bwd_reduce': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_bwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P, P, P, P, P, P]),
     'dcv_act_norm_bwd_apply': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, P]),

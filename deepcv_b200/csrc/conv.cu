@@ -10,6 +10,9 @@ bool conv_tc_fwd_supported(const dcv_conv_shape*, int dtype);
 bool conv_tc_wgrad_supported(const dcv_conv_shape*, int dtype);
 int conv_fwd_tc(const dcv_conv_shape*, const void*, const void*, const float*, void*, float*, int, float, cudaStream_t);
 int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, cudaStream_t);
+bool conv_fwd_tc_gather_supported(const dcv_conv_shape*, const void* x, int kpad, int dtype);
+int conv_fwd_tc_gather(const dcv_conv_shape*, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, cudaStream_t);
+int conv_wgrad_tc_gather(const dcv_conv_shape*, const void* x, const void* dy, float* dw_col, int kpad, cudaStream_t);
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*);
 
 static dcv_conv_shape dgrad_as_fwd(const dcv_conv_shape& s) {
@@ -45,6 +48,25 @@ int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, co
   DCV_REQUIRE(algo != DCV_ALGO_TCGEN05 || tc_ok, "conv2d_fwd: tcgen05 algorithm does not support this shape/dtype (needs bf16, c %% 64 == 0, k %% 16 == 0, stride 1, dilation 1)");
   if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(shape, x, w, bias, y, stats_nc, act, slope, st);
   return conv_fwd_direct(shape, x, w, bias, y, stats_nc, act, slope, dtype, st);
+}
+
+int dcv_conv2d_gather_supported(const dcv_conv_shape* shape, const void* x, int kpad, int dtype) {
+  return dcv::conv_fwd_tc_gather_supported(shape, x, kpad, dtype) ? 1 : 0;
+}
+
+int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc,
+                          int act, float slope, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(shape, "conv2d_fwd_gather: null shape");
+  cudaStream_t st = as_stream(stream);
+  if (stats_nc) cudaMemsetAsync(stats_nc, 0, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
+  return conv_fwd_tc_gather(shape, x, w_col, kpad, bias, y, stats_nc, act, slope, st);
+}
+
+int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(shape, "conv2d_wgrad_gather: null shape");
+  return conv_wgrad_tc_gather(shape, x, dy, dw_col, kpad, as_stream(stream));
 }
 
 int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w, const void* wt, void* dx, int dtype, int algo, void* stream) {

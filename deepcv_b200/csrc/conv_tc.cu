@@ -45,6 +45,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// Same, for the many-thread waiters (epilogue / producer warps): back off between polls so that spinning warps do not eat the issue slots of the
+// warps that have work (ncu on the gather kernel: 20 % of all warp instructions were try_wait polls).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -53,6 +63,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier like the tensor variants
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+constexpr int kZeroRowBytes = 8192;
+__device__ __align__(16) unsigned char g_zero_row[kZeroRowBytes];   // source of the rows above / below the image (vertical padding)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
@@ -431,6 +451,384 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_halo_kernel(const __g
   }
 }
 
+// ---- forward, gather variant: convolutions TMA cannot address (few input channels, strides: the 3 -> 64, 7x7 / stride-2 stem) ---------------------
+// The explicit im2col route materialises col[n][p][q][kpad] (1.2 GB for the stem at batch 256: 338 us to write it + a GEMM that is HBM-bound reading it
+// back = the most expensive layer of the ImageNet-shaped step). Here eight PRODUCER warps build the 128 x kpad im2col tile of one output-row segment
+// directly in shared memory, in the K-major SWIZZLE_128B layout TMA would have produced (16-byte chunk j of row m lives at chunk j ^ (m & 7) of its
+// 128-byte line): the R input rows the segment reads are staged by TMA (one 384-byte box per row piece, rows outside the image zero-filled) into a
+// double-buffered area with zeroed margins. (cp.async staging by the producers themselves was 5x slower: the fence.proxy.async they need after
+// writing the tile compiles to MEMBAR.ALL.CTA, which waits for their in-flight prefetch of the NEXT tile — a full L2 / DRAM round trip per tile.)
+// K order ("row padded"): column kk = r * RP + x, x < RP = S*C rounded up to 8; for x >= S*C the WEIGHT is zero, so the tile may hold whatever follows in
+// the staged row there. A 16-byte chunk is then always 8 CONTIGUOUS staged elements at a 2-byte-aligned address: five aligned 32-bit shared loads and a
+// funnel shift, no per-element gather, no masks. Lanes of a warp take 32 consecutive pixels of one chunk column (12 bytes apart: conflict-free).
+// Weights ([K][kpad] in the same K order) are resident. MMA / TMEM / epilogue as above.
+struct GatherParams {
+  dcv_conv_shape s;
+  int kpad, kblocks, rowlen, lpad, rows_bytes, rp;   // rp: elements per filter row in the K order (S*C rounded up to 8)
+  int nboxes;                                         // TMA boxes (GA_BOX_W elements each) per staged row
+  int tiles_q, total_tiles;
+  int act; float slope;
+  const float* bias;
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+};
+constexpr int GA_BOX_W = 192;   // elements per staging box: 384 B, a multiple of the 128-byte alignment TMA wants for its shared-memory destination
+constexpr int GA_THREADS = 448, GA_STAGES = 2, GA_PRODUCERS = 256, GA_ROW_BUFS = 3;   // warps: 0 weights (TMA), 1 MMA, 2..5 epilogue, 6..13 producers
+
+// Producer warp `pw` of GA_PRODUCERS / 32 builds its share of the (chunk column, 32-row band) units of the tile; lane = row within the band. The
+// unit list of a warp is the same for every tile: it is decoded ONCE into registers (ncu on the version that decoded it per unit: three runtime integer
+// divisions = ~75 instructions per unit, 63 % of the kernel's 355 M warp instructions, the kernel issue-bound at 5300 cycles per 128-pixel tile).
+// (Earlier versions: one thread per row walking an offset table with data-dependent branches; one thread per chunk column with the 8 offsets in
+// registers — 8 two-byte loads per chunk with 4-way bank conflicts.)
+constexpr int GA_MAX_UNITS = (256 / 8) * (BLOCK_M / 32) / (GA_PRODUCERS / 32);   // 16
+struct GatherUnits {
+  int n;
+  uint32_t dst[GA_MAX_UNITS];   // byte offset of the unit's 16-byte chunk of row `lane` inside the stage, before the swizzle XOR
+  int src[GA_MAX_UNITS];        // element offset of the chunk's first element relative to the pixel's window start; -1: zero chunk (K padding)
+  int band[GA_MAX_UNITS];
+};
+
+__device__ __forceinline__ void gather_units_setup(const GatherParams& prm, int pw, GatherUnits& g) {
+  const int ncols = prm.kpad / 8, cpr = prm.rp / 8, real_cols = prm.s.r * cpr, units = ncols * (BLOCK_M / 32);
+  g.n = 0;
+#pragma unroll
+  for (int i = 0; i < GA_MAX_UNITS; ++i) {
+    const int u = pw + i * (GA_PRODUCERS / 32);
+    g.dst[i] = 0u; g.src[i] = -1; g.band[i] = 0;
+    if (u < units) {
+      const int cc = u % ncols, band = u / ncols;   // consecutive warps take consecutive chunk columns of one band
+      g.n = i + 1;
+      g.band[i] = band;
+      g.dst[i] = (uint32_t)(cc >> 3) * (BLOCK_M * 128) + (uint32_t)(band * 32) * 128u + (uint32_t)(cc & 7) * 16u;
+      if (cc < real_cols) { const int rr = cc / cpr; g.src[i] = rr * prm.rowlen + (cc - rr * cpr) * 8; }
+    }
+  }
+}
+
+__device__ __forceinline__ void gather_build_tile(const GatherParams& prm, const GatherUnits& g, const __nv_bfloat16* rows, uint32_t a_stage, int q0, int lane) {
+  const dcv_conv_shape& s = prm.s;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(rows);
+  const uint32_t lane_dst = a_stage + (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7) * 16u;   // band * 32 is a multiple of 8: (m & 7) == (lane & 7)
+  const int step = s.stride_w * s.c, base0 = prm.lpad - s.pad_w * s.c;
+#pragma unroll
+  for (int i = 0; i < GA_MAX_UNITS; ++i) {
+    if (i < g.n) {
+      uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+      if (g.src[i] >= 0) {
+        // overhang pixels (q >= Q) read the first pixel's window: finite data, and their accumulator rows are never stored
+        const int q = q0 + g.band[i] * 32 + lane;
+        const int idx = base0 + (q < s.q ? q : 0) * step + g.src[i];   // first element of the chunk (2-byte units)
+        const uint32_t* wp = words + (idx >> 1);
+        const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
+        const uint32_t sh = (uint32_t)(idx & 1) * 16u;
+        w0 = __funnelshift_r(a0, a1, sh); w1 = __funnelshift_r(a1, a2, sh); w2 = __funnelshift_r(a2, a3, sh); w3 = __funnelshift_r(a3, a4, sh);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((lane_dst + g.dst[i]) ^ sw), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+    }
+  }
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GatherParams prm) {
+  constexpr int B_BYTES = N_TILE * BLOCK_K * 2, A_SLAB = BLOCK_M * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = res_base + (uint32_t)prm.kblocks * B_BYTES;
+  const uint32_t a_stage_bytes = (uint32_t)prm.kblocks * A_SLAB;
+  const uint32_t rows_base = a_base + GA_STAGES * a_stage_bytes;
+  const uint32_t bars = rows_base + (uint32_t)GA_ROW_BUFS * (uint32_t)prm.rows_bytes;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (GA_STAGES + i); };
+  auto tfull = [&](int i) { return bars + 8u * (2 * GA_STAGES + i); };
+  auto tempty = [&](int i) { return bars + 8u * (2 * GA_STAGES + 2 + i); };
+  const uint32_t bres = bars + 8u * (2 * GA_STAGES + 4), tmem_slot = bars + 8u * (2 * GA_STAGES + 5);
+  auto rfull = [&](int i) { return bars + 8u * (2 * GA_STAGES + 6 + i); };    // staged rows of buffer i landed (TMA)
+  auto rempty = [&](int i) { return bars + 8u * (2 * GA_STAGES + 6 + GA_ROW_BUFS + i); };   // all producer warps are done reading buffer i
+  uint8_t* gen_base = smem_raw + (res_base - smem_u32(smem_raw));   // generic-address view of the same buffer
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const dcv_conv_shape& s = prm.s;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GA_STAGES; ++i) { mbar_init(full(i), GA_PRODUCERS / 32); mbar_init(empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    mbar_init(bres, 1);
+    for (int i = 0; i < GA_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), GA_PRODUCERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * N_TILE) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // both staging buffers start as zeros: TMA only ever writes [lpad, lpad + nboxes * GA_BOX_W) of each row, the margins are the convolution padding
+  for (uint32_t i = threadIdx.x; i < (uint32_t)GA_ROW_BUFS * (uint32_t)prm.rows_bytes / 16u; i += GA_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rows_base + i * 16u), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto decode = [&](int tile, int& q0, int& op, int& img) {
+    q0 = (tile % prm.tiles_q) * BLOCK_M; const int t = tile / prm.tiles_q;
+    op = t % s.p; img = t / s.p;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {   // ===== weights once, then the input rows of every tile
+      mbar_expect_tx(bres, (uint32_t)prm.kblocks * B_BYTES);
+      for (int kb = 0; kb < prm.kblocks; ++kb) tma_load_2d(res_base + kb * B_BYTES, &map_w, bres, kb * BLOCK_K, 0);
+      int buf = 0; uint32_t rphase = 0;
+      const uint32_t row_bytes = (uint32_t)(s.w * s.c) * 2u;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        int q0, op, img; decode(tile, q0, op, img);
+        mbar_wait(rempty(buf), rphase ^ 1u);
+        mbar_expect_tx(rfull(buf), (uint32_t)s.r * row_bytes);
+        const int iy0 = op * s.stride_h - s.pad_h;
+        for (int r = 0; r < s.r; ++r) {   // ONE bulk copy per input row (28 small tensor boxes per tile made the single issuing thread the bottleneck)
+          const int iy = iy0 + r * s.dil_h;
+          const void* src = (iy >= 0 && iy < s.h) ? (const void*)(prm.x + ((size_t)img * s.h + iy) * (size_t)(s.w * s.c)) : (const void*)g_zero_row;
+          bulk_load_1d(rows_base + (uint32_t)buf * (uint32_t)prm.rows_bytes + (uint32_t)(r * prm.rowlen + prm.lpad) * 2u, src, row_bytes, rfull(buf));
+        }
+        if (++buf == GA_ROW_BUFS) { buf = 0; rphase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {   // ===== MMA issuer
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      mbar_wait(bres, 0);
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty(as), aphase ^ 1u);
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * N_TILE);
+        for (int kb = 0; kb < prm.kblocks; ++kb) {
+          const uint64_t adesc = make_desc(a_base + stage * a_stage_bytes + kb * A_SLAB, 0, 1024);
+          const uint64_t bdesc = make_desc(res_base + kb * B_BYTES, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(empty(stage));
+        umma_commit(tfull(as));
+        if (++stage == GA_STAGES) { stage = 0; phase ^= 1u; }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue warps 2..5 (TMEM lane quarter = warp % 4): accumulator row = pixel q0 + row of output row (img, op)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      int q0, op, img; decode(tile, q0, op, img);
+      const int q = q0 + row;
+      const bool valid = q < s.q;
+      __nv_bfloat16* dst = prm.y + (((size_t)img * s.p + op) * s.q + q) * s.k;
+      mbar_wait_relaxed(tfull(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else {
+    // ===== producer warps 6..13
+    const int pw = warp - (GA_THREADS - GA_PRODUCERS) / 32;
+    GatherUnits units;
+    gather_units_setup(prm, pw, units);
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t rphase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      int q0, op, img; decode(tile, q0, op, img);
+      mbar_wait_relaxed(rfull(buf), rphase);
+      mbar_wait_relaxed(empty(stage), phase ^ 1u);
+      const __nv_bfloat16* rows = reinterpret_cast<const __nv_bfloat16*>(gen_base + (rows_base - res_base) + (size_t)buf * prm.rows_bytes);
+      gather_build_tile(prm, units, rows, a_base + stage * a_stage_bytes, q0, lane);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(full(stage)); mbar_arrive(rempty(buf)); }
+      if (++stage == GA_STAGES) { stage = 0; phase ^= 1u; }
+      if (++buf == GA_ROW_BUFS) { buf = 0; rphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N_TILE) : "memory");
+  }
+}
+
+// ---- weight gradient, gather variant ---------------------------------------------------------------------------------------------------------
+// dw_col[k][kk] = sum over output pixels of dy[pix][k] * col[pix][kk] with col built on the fly: the tile the producers write for the forward kernel
+// ([128 pixels][kpad], 128-byte rows, one 16 KB slab per 64 columns) is, read MN-major, exactly the B operand of the weight gradient (pixels = K rows,
+// the kpad / 64 slabs = MN atoms one LBO apart). A = the dy tile of the same 128 pixels through TMA (a box along q; pixels beyond the row are zero filled
+// and so switch off whatever the producers left in those rows). One N = kpad MMA per 16 pixels; each CTA accumulates its share of the tiles in TMEM and
+// adds it into dw_col with vector reductions at the end.
+struct GatherWgradParams {
+  GatherParams g;
+  float* dw_col;
+};
+constexpr int GW_NA = 2;   // dy tile slots (2 x 16 KB atoms each)
+
+__global__ void __launch_bounds__(GA_THREADS, 1) conv_wgrad_tc_gather_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const GatherWgradParams wp) {
+  const GatherParams& prm = wp.g;
+  constexpr int A_SLAB = BLOCK_M * 128, DY_BYTES = 2 * A_SLAB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t dy_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = dy_base + GW_NA * DY_BYTES;
+  const uint32_t b_stage_bytes = (uint32_t)prm.kblocks * A_SLAB;
+  const uint32_t rows_base = b_base + GA_STAGES * b_stage_bytes;
+  const uint32_t bars = rows_base + (uint32_t)GA_ROW_BUFS * (uint32_t)prm.rows_bytes;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (GA_STAGES + i); };
+  auto afull = [&](int i) { return bars + 8u * (2 * GA_STAGES + i); };
+  auto aempty = [&](int i) { return bars + 8u * (2 * GA_STAGES + GW_NA + i); };
+  auto rfull = [&](int i) { return bars + 8u * (2 * GA_STAGES + 2 * GW_NA + i); };
+  auto rempty = [&](int i) { return bars + 8u * (2 * GA_STAGES + 2 * GW_NA + GA_ROW_BUFS + i); };
+  const uint32_t done = bars + 8u * (2 * GA_STAGES + 2 * GW_NA + 2 * GA_ROW_BUFS), tmem_slot = done + 8u;
+  uint8_t* gen_base = smem_raw + (dy_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const dcv_conv_shape& s = prm.s;
+  const bool second_atom = s.k > 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GA_STAGES; ++i) { mbar_init(full(i), GA_PRODUCERS / 32); mbar_init(empty(i), 1); }
+    for (int i = 0; i < GW_NA; ++i) { mbar_init(afull(i), 1); mbar_init(aempty(i), 1); }
+    for (int i = 0; i < GA_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), GA_PRODUCERS / 32); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dy)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the staging rows (margins = padding) and, for 64 output channels, the unused second atom of every dy slot
+  for (uint32_t i = threadIdx.x; i < (uint32_t)GA_ROW_BUFS * (uint32_t)prm.rows_bytes / 16u; i += GA_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rows_base + i * 16u), "r"(0) : "memory");
+  if (!second_atom)
+    for (uint32_t i = threadIdx.x; i < (uint32_t)GW_NA * (A_SLAB / 16); i += GA_THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dy_base + (i / (A_SLAB / 16)) * DY_BYTES + A_SLAB + (i % (A_SLAB / 16)) * 16u), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto decode = [&](int tile, int& q0, int& op, int& img) {
+    q0 = (tile % prm.tiles_q) * BLOCK_M; const int t = tile / prm.tiles_q;
+    op = t % s.p; img = t / s.p;
+  };
+  const int my_tiles = (int)blockIdx.x < prm.total_tiles ? (prm.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    if (elect_one()) {   // ===== TMA: per tile the dy slab(s) and the R input rows
+      int buf = 0; uint32_t rphase = 0;
+      int as = 0; uint32_t aph = 0;
+      const uint32_t row_bytes = (uint32_t)(s.w * s.c) * 2u;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        int q0, op, img; decode(tile, q0, op, img);
+        mbar_wait(aempty(as), aph ^ 1u);
+        mbar_expect_tx(afull(as), second_atom ? DY_BYTES : A_SLAB);
+        tma_load_4d(dy_base + as * DY_BYTES, &map_dy, afull(as), 0, q0, op, img);
+        if (second_atom) tma_load_4d(dy_base + as * DY_BYTES + A_SLAB, &map_dy, afull(as), 64, q0, op, img);
+        if (++as == GW_NA) { as = 0; aph ^= 1u; }
+        mbar_wait(rempty(buf), rphase ^ 1u);
+        mbar_expect_tx(rfull(buf), (uint32_t)s.r * row_bytes);
+        const int iy0 = op * s.stride_h - s.pad_h;
+        for (int r = 0; r < s.r; ++r) {
+          const int iy = iy0 + r * s.dil_h;
+          const void* src = (iy >= 0 && iy < s.h) ? (const void*)(prm.x + ((size_t)img * s.h + iy) * (size_t)(s.w * s.c)) : (const void*)g_zero_row;
+          bulk_load_1d(rows_base + (uint32_t)buf * (uint32_t)prm.rows_bytes + (uint32_t)(r * prm.rowlen + prm.lpad) * 2u, src, row_bytes, rfull(buf));
+        }
+        if (++buf == GA_ROW_BUFS) { buf = 0; rphase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {   // ===== MMA issuer: D[128 k][kpad] += dy^T * col over this CTA's tiles
+      const uint32_t idesc = make_idesc(128, prm.kpad, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(afull(as), aph);
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = dy_base + as * DY_BYTES, sb = b_base + stage * b_stage_bytes;
+#pragma unroll
+        for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {
+          const uint64_t adesc = make_desc(sa + ks * UMMA_K * 128, A_SLAB, 1024);
+          const uint64_t bdesc = make_desc(sb + ks * UMMA_K * 128, A_SLAB, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | ks) != 0);
+        }
+        umma_commit(empty(stage));
+        umma_commit(aempty(as));
+        if (++stage == GA_STAGES) { stage = 0; phase ^= 1u; }
+        if (++as == GW_NA) { as = 0; aph ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else if (warp < 6) {
+    if (my_tiles > 0) {   // ===== epilogue, once: TMEM lane = output channel, column = im2col column
+      const int quarter = warp & 3;
+      const int krow = quarter * 32 + lane;
+      mbar_wait_relaxed(done, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < prm.kpad; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        if (krow < s.k) {
+          float* dst = wp.dw_col + (size_t)krow * prm.kpad + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                         "f"(__uint_as_float(v[j + 3])) : "memory");
+        }
+      }
+    }
+  } else {
+    // ===== producer warps: the im2col tile of every tile, as in the forward kernel
+    const int pw = warp - (GA_THREADS - GA_PRODUCERS) / 32;
+    GatherUnits units;
+    gather_units_setup(prm, pw, units);
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t rphase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      int q0, op, img; decode(tile, q0, op, img);
+      mbar_wait_relaxed(rfull(buf), rphase);
+      mbar_wait_relaxed(empty(stage), phase ^ 1u);
+      const __nv_bfloat16* rows = reinterpret_cast<const __nv_bfloat16*>(gen_base + (rows_base - dy_base) + (size_t)buf * prm.rows_bytes);
+      gather_build_tile(prm, units, rows, b_base + stage * b_stage_bytes, q0, lane);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(full(stage)); mbar_arrive(rempty(buf)); }
+      if (++stage == GA_STAGES) { stage = 0; phase ^= 1u; }
+      if (++buf == GA_ROW_BUFS) { buf = 0; rphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -759,7 +1157,114 @@ static int conv_fwd_tc_halo(const dcv_conv_shape* s, const void* x, const void* 
   return s->k == 128 ? launch_fwd_halo<128>(mx, mw, prm, smem, st) : launch_fwd_halo<64>(mx, mw, prm, smem, st);
 }
 
+// x viewed as [N][H][W*C] bf16 rows for the gather kernels' staging: box = GA_BOX_W elements of one row, no swizzle, zero fill outside the tensor
+// (rows above / below the image = vertical padding; the tail of the last box beyond W*C lands in the zero margin).
+static int make_rows_map(CUtensorMap* map, const void* x, const dcv_conv_shape* s) {
+  EncodeTiledFn fn = encode_tiled();
+  DCV_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)s->w * s->c, (cuuint64_t)s->h, (cuuint64_t)s->n};
+  const cuuint64_t strides[2] = {(cuuint64_t)s->w * s->c * 2, (cuuint64_t)s->h * s->w * s->c * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)GA_BOX_W, 1u, 1u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (staging rows) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// Geometry of the gather kernels' staging area; false when the layer does not fit (falls back to the explicit im2col route).
+static bool gather_geometry(const dcv_conv_shape* s, const void* x, int kpad, GatherParams* prm, size_t* smem, int b_bytes) {
+  const int wc = s->w * s->c, rp = (s->s * s->c + 7) / 8 * 8;
+  if (wc * 2 > kZeroRowBytes || s->dil_w != 1 || kpad % BLOCK_K != 0 || kpad < s->r * rp || kpad > 256 || wc % 8 != 0 || reinterpret_cast<uintptr_t>(x) % 16 != 0) return false;
+  prm->rp = rp;
+  int lpad = s->pad_w * s->c;
+  lpad = (lpad + 63) / 64 * 64;   // every staged row (and every box inside it) starts on a 128-byte boundary
+  // the last tile's overhang pixels are not gathered, so the farthest element read belongs to pixel q - 1
+  int need = lpad + ((s->q - 1) * s->stride_w - s->pad_w) * s->c + rp + 2;   // a chunk reads 5 aligned words = up to 10 elements from its first one
+  prm->nboxes = 0;
+  if (need < lpad + wc) need = lpad + wc;
+  const int rowlen = (need + 63) / 64 * 64;
+  prm->s = *s; prm->kpad = kpad; prm->kblocks = kpad / BLOCK_K; prm->rowlen = rowlen; prm->lpad = lpad;
+  prm->rows_bytes = s->r * rowlen * 2;   // a multiple of 128
+  prm->tiles_q = (s->q + BLOCK_M - 1) / BLOCK_M;
+  const long long tiles = (long long)s->n * s->p * prm->tiles_q;
+  if (tiles >= (1ll << 31)) return false;
+  prm->total_tiles = (int)tiles;
+  if (GA_PRODUCERS % (kpad / 8) != 0 && GA_PRODUCERS / (kpad / 8) < 1) return false;
+  *smem = 1024 + (size_t)prm->kblocks * b_bytes + (size_t)GA_STAGES * prm->kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * prm->rows_bytes + 256;
+  return *smem <= 227 * 1024;
+}
+
 }  // namespace tc
+
+bool conv_fwd_tc_gather_supported(const dcv_conv_shape* s, const void* x, int kpad, int dtype) {
+  if (!s || dtype != DCV_BF16 || (s->k != 64 && s->k != 128) || tc::encode_tiled() == nullptr) return false;
+  if ((long long)s->n * s->p * s->q < 128) return false;
+  tc::GatherParams prm{}; size_t smem = 0;
+  return tc::gather_geometry(s, x, kpad, &prm, &smem, s->k * tc::BLOCK_K * 2);
+}
+
+// w_col: [K][kpad] bf16, columns (r, s, c) of the [K][R][S][C] weights followed by zeros.
+int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, cudaStream_t st) {
+  using namespace tc;
+  DCV_REQUIRE(x && w_col && y, "conv2d_fwd_gather: null pointer");
+  GatherParams prm{}; size_t smem = 0;
+  DCV_REQUIRE(gather_geometry(s, x, kpad, &prm, &smem, s->k * BLOCK_K * 2), "conv2d_fwd_gather: shape not supported (see dcv_conv2d_gather_supported)");
+  prm.act = act; prm.slope = slope; prm.bias = bias; prm.x = reinterpret_cast<const __nv_bfloat16*>(x); prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+  CUtensorMap mw;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)s->k};
+    const cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)s->k};
+    if (make_map(&mw, w_col, 2, dims, strides, box)) return 1;
+  }
+  CUtensorMap mx;
+  if (make_rows_map(&mx, x, s)) return 1;
+  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
+  if (s->k == 128) {
+    auto kern = conv_fwd_tc_gather_kernel<128>;
+    static size_t configured = 0;
+    if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    kern<<<grid, GA_THREADS, smem, st>>>(mw, mx, prm);
+  } else {
+    auto kern = conv_fwd_tc_gather_kernel<64>;
+    static size_t configured = 0;
+    if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    kern<<<grid, GA_THREADS, smem, st>>>(mw, mx, prm);
+  }
+  DCV_LAUNCH_CHECK("conv_fwd_tc_gather_kernel");
+  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
+  return 0;
+}
+
+// dw_col: [K][kpad] fp32 in the gather K order (overwritten).
+int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy, float* dw_col, int kpad, cudaStream_t st) {
+  using namespace tc;
+  DCV_REQUIRE(x && dy && dw_col, "conv2d_wgrad_gather: null pointer");
+  DCV_REQUIRE(reinterpret_cast<uintptr_t>(dy) % 16 == 0 && reinterpret_cast<uintptr_t>(dw_col) % 16 == 0, "conv2d_wgrad_gather: pointers must be 16-byte aligned");
+  GatherWgradParams wp{}; size_t smem_fwd = 0;
+  DCV_REQUIRE(gather_geometry(s, x, kpad, &wp.g, &smem_fwd, s->k * BLOCK_K * 2), "conv2d_wgrad_gather: shape not supported (see dcv_conv2d_gather_supported)");
+  wp.g.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  wp.dw_col = dw_col;
+  const size_t smem = 1024 + (size_t)GW_NA * 2 * BLOCK_M * 128 + (size_t)GA_STAGES * wp.g.kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * wp.g.rows_bytes + 256;
+  DCV_REQUIRE(smem <= 227 * 1024, "conv2d_wgrad_gather: %zu bytes of shared memory needed", smem);
+  cudaMemsetAsync(dw_col, 0, (size_t)s->k * kpad * sizeof(float), st);
+  CUtensorMap mdy, mx;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)s->k, (cuuint64_t)s->q, (cuuint64_t)s->p, (cuuint64_t)s->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s->k * 2, (cuuint64_t)s->q * s->k * 2, (cuuint64_t)s->p * s->q * s->k * 2};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)BLOCK_M, 1u, 1u};
+    if (make_map(&mdy, dy, 4, dims, strides, box)) return 1;
+  }
+  if (make_rows_map(&mx, x, s)) return 1;
+  auto kern = conv_wgrad_tc_gather_kernel;
+  static size_t configured = 0;
+  if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+  const int grid = wp.g.total_tiles < num_sms() ? wp.g.total_tiles : num_sms();
+  kern<<<grid, GA_THREADS, smem, st>>>(mdy, mx, wp);
+  DCV_LAUNCH_CHECK("conv_wgrad_tc_gather_kernel");
+  return 0;
+}
 
 bool conv_tc_fwd_supported(const dcv_conv_shape* s, int dtype) {
   if (!s || dtype != DCV_BF16) return false;

@@ -158,6 +158,24 @@ static int transpose_dispatch(const void* src, int sd, void* dst, int dd, int ba
   return 1;
 }
 
+// Weight operand of the gather convolution kernels (conv_tc.cu): [K][kpad] with column r * rp + x = w[k][r][x] for x < sc = S*C, zero elsewhere
+// ("row padded" K order: every 16-byte chunk of an im2col row is 8 contiguous input elements); and the way back for the weight gradient.
+template <typename T>
+__global__ void gather_pack_weight_kernel(const T* __restrict__ w, T* __restrict__ w_col, int k, int r, int sc, int rp, int kpad) {
+  const size_t total = (size_t)k * kpad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % kpad), kk = (int)(i / kpad), rr = j / rp, x = j - rr * rp;
+    w_col[i] = (rr < r && x < sc) ? w[((size_t)kk * r + rr) * sc + x] : from_f<T>(0.f);
+  }
+}
+__global__ void gather_unpack_wgrad_kernel(const float* __restrict__ dw_col, float* __restrict__ dw, int k, int r, int sc, int rp, int kpad) {
+  const size_t total = (size_t)k * r * sc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % sc); const size_t t = i / sc; const int rr = (int)(t % r), kk = (int)(t / r);
+    dw[i] = dw_col[(size_t)kk * kpad + rr * rp + x];
+  }
+}
+
 }  // namespace dcv
 
 extern "C" {
@@ -220,6 +238,24 @@ int dcv_im2col(const dcv_conv_shape* shape, const void* x, void* col, int kpad, 
   }
   DCV_DISPATCH_DTYPE(dtype, T, (im2col_kernel<T><<<grid_for(total, 256, kNumSMs * 32), 256, 0, as_stream(stream)>>>((const T*)x, (T*)col, *shape, kpad, d_vpp, d_q, d_p, d_sc, d_c)));
   DCV_LAUNCH_CHECK("im2col_kernel");
+  return 0;
+}
+
+int dcv_gather_pack_weight(const void* w_krsc, void* w_col, int k, int r, int sc, int kpad, int dtype, void* stream) {
+  using namespace dcv;
+  const int rp = (sc + 7) / 8 * 8;
+  DCV_REQUIRE(w_krsc && w_col && k > 0 && r > 0 && sc > 0 && kpad >= r * rp, "gather_pack_weight: bad arguments (kpad=%d must cover %d filter rows of %d)", kpad, r, rp);
+  DCV_DISPATCH_DTYPE(dtype, T, (gather_pack_weight_kernel<T><<<grid_for((size_t)k * kpad, 256), 256, 0, as_stream(stream)>>>((const T*)w_krsc, (T*)w_col, k, r, sc, rp, kpad)));
+  DCV_LAUNCH_CHECK("gather_pack_weight_kernel");
+  return 0;
+}
+
+int dcv_gather_unpack_wgrad(const float* dw_col, float* dw_krsc, int k, int r, int sc, int kpad, void* stream) {
+  using namespace dcv;
+  const int rp = (sc + 7) / 8 * 8;
+  DCV_REQUIRE(dw_col && dw_krsc && k > 0 && r > 0 && sc > 0 && kpad >= r * rp, "gather_unpack_wgrad: bad arguments");
+  gather_unpack_wgrad_kernel<<<grid_for((size_t)k * r * sc, 256), 256, 0, as_stream(stream)>>>(dw_col, dw_krsc, k, r, sc, rp, kpad);
+  DCV_LAUNCH_CHECK("gather_unpack_wgrad_kernel");
   return 0;
 }
 

@@ -11,6 +11,7 @@ Conventions
     modules in `deepcv_b200.meta.nn`, for shape inference only).
 """
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -150,6 +151,9 @@ class NormConfig:
         return self.use_bn or self.use_gn
 
 
+_USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
+
+
 def _conv_shape(x: torch.Tensor, weight: torch.Tensor, stride, padding, dilation) -> ConvShape:
     n, c, h, w = x.shape
     k, cw, r, s = weight.shape
@@ -205,14 +209,25 @@ class _ConvBlock(torch.autograd.Function):
             gemm_shape = ConvShape(n, p, q, kpad, k, 1, 1, 1, 1, 0, 0, 1, 1, p, q)
             if not lib.dcv_conv2d_tc_supported(ctypes.byref(gemm_shape), dt, 0):
                 gemm_shape = None
+        gathered = False
         if gemm_shape is not None:
-            col = torch.empty((n, p, q, kpad), dtype=x.dtype, device=dev)
-            check(lib.dcv_im2col(ctypes.byref(shape), _ptr(x), _ptr(col), kpad, dt, st), 'im2col')
-            w_col = torch.empty((k, kpad), dtype=x.dtype, device=dev)
-            check(lib.dcv_fill_zero(_ptr(w_col), w_col.numel() * w_col.element_size(), st), 'fill_zero')
-            check(lib.dcv_copy_channels_in(_ptr(w_op), _ptr(w_col), k, rsc, kpad, 0, dt, st), 'copy_channels_in(weight)')
-            check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd(im2col)')
-            x = col   # what the weight gradient needs; the data gradient only needs dy and the weights
+            # gather kernels: producer warps build the im2col tile in shared memory, col[n][p][q][kpad] (1.2 GB for the stem at batch 256) is never
+            # materialised. Their K order pads every filter row to a multiple of 8 elements (see dcv_gather_pack_weight).
+            sc = shape.s * shape.c
+            kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
+            gathered = bool(_USE_GATHER and lib.dcv_conv2d_gather_supported(ctypes.byref(shape), _ptr(x), kpad_g, dt))
+            if gathered:
+                w_col = torch.empty((k, kpad_g), dtype=x.dtype, device=dev)
+                check(lib.dcv_gather_pack_weight(_ptr(w_op), _ptr(w_col), k, shape.r, sc, kpad_g, dt, st), 'gather_pack_weight')
+                check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), _ptr(x), _ptr(w_col), kpad_g, _ptr(bias), _ptr(y), _ptr(stats), act, slope, st), 'conv2d_fwd_gather')
+            else:
+                w_col = torch.empty((k, kpad), dtype=x.dtype, device=dev)
+                check(lib.dcv_fill_zero(_ptr(w_col), w_col.numel() * w_col.element_size(), st), 'fill_zero')
+                check(lib.dcv_copy_channels_in(_ptr(w_op), _ptr(w_col), k, rsc, kpad, 0, dt, st), 'copy_channels_in(weight)')
+                col = torch.empty((n, p, q, kpad), dtype=x.dtype, device=dev)
+                check(lib.dcv_im2col(ctypes.byref(shape), _ptr(x), _ptr(col), kpad, dt, st), 'im2col')
+                check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd(im2col)')
+                x = col   # what the weight gradient needs; the data gradient only needs dy and the weights
         else:
             check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd')
         saved = None
@@ -228,13 +243,13 @@ class _ConvBlock(torch.autograd.Function):
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
         # the fp32 master weight, when it already is [K][R][S][C] in memory: the data-gradient operand is packed straight from it in backward
         ctx.w_master = weight.detach() if (weight.dtype == torch.float32 and weight.permute(0, 2, 3, 1).is_contiguous()) else None
-        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape)
+        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape, gathered)
         return out
 
     @staticmethod
     def backward(ctx, dz):
         x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv = ctx.saved_tensors
-        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape, gemm_shape = ctx.cfg
+        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape, gemm_shape, gathered = ctx.cfg
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st, dt = y.device, _stream(), _dt(y)
         dz = as_nhwc(dz.detach(), y.dtype)
@@ -270,7 +285,13 @@ class _ConvBlock(torch.autograd.Function):
             dw = targets.get('weight', None)
             if dw is None:
                 dw = torch.empty((k, shape.r, shape.s, shape.c), **f32).permute(0, 3, 1, 2)
-            if gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
+            if gathered:                 # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
+                sc = shape.s * shape.c
+                kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
+                dw_col = torch.empty((k, kpad_g), **f32)
+                check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), kpad_g, st), 'conv2d_wgrad_gather')
+                check(lib.dcv_gather_unpack_wgrad(_ptr(dw_col), _ptr(dw), k, shape.r, sc, kpad_g, st), 'gather_unpack_wgrad')
+            elif gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
                 dw_col = torch.empty((k, gemm_shape.c), **f32)
                 check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, st), 'conv2d_wgrad(im2col)')
                 check(lib.dcv_copy_channels_out(_ptr(dw_col), _ptr(dw), k, gemm_shape.c, 0, shape.r * shape.s * shape.c, DCV_F32, st), 'copy_channels_out(dw)')

@@ -77,6 +77,19 @@ int dcv_fill_zero(void* dst, size_t bytes, void* stream);
 /* 1 iff DCV_ALGO_AUTO would run `op` (0 = forward, 1 = data gradient, 2 = weight gradient) of this shape / dtype on the tcgen05 kernels
  * (bf16, stride 1, dilation 1, c and k multiples of 64); lets the caller skip preparing the `wt` operand otherwise. */
 int dcv_conv2d_tc_supported(const dcv_conv_shape* shape, int dtype, int op);
+/* Convolutions the TMA-fed kernels cannot address (few input channels, strides: the 3 -> 64, 7x7 / stride-2 stem of the ImageNet-shaped nets) without
+ * materialising col[n][p][q][kpad]: producer warps build the im2col tile in shared memory (software gather into the tcgen05 operand layout).
+ * `w_col` = [K][kpad] bf16 from dcv_gather_pack_weight; kpad a multiple of 64, <= 256; K = 64 or 128; dilation_w = 1.
+ * dcv_conv2d_gather_supported: 1 iff this shape / pointer alignment is served (else use dcv_im2col + the 1x1 GEMM). */
+int dcv_conv2d_gather_supported(const dcv_conv_shape* shape, const void* x, int kpad, int dtype);
+/* K order of the gather kernels ("row padded"): column r*RP + x of w_col / dw_col = w[k][r][x] for x < S*C, RP = S*C rounded up to 8; kpad >= R*RP.
+ * dcv_gather_pack_weight: [K][R][S*C] (dtype) -> w_col [K][kpad] (same dtype, zeros elsewhere); dcv_gather_unpack_wgrad: dw_col [K][kpad] -> [K][R][S*C], fp32. */
+int dcv_gather_pack_weight(const void* w_krsc, void* w_col, int k, int r, int sc, int kpad, int dtype, void* stream);
+int dcv_gather_unpack_wgrad(const float* dw_col, float* dw_krsc, int k, int r, int sc, int kpad, void* stream);
+int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc,
+                          int act, float slope, void* stream);
+/* dw_col[K][kpad] (fp32, gather K order, overwritten) = sum over pixels of dy * im2col(x); unpack with dcv_gather_unpack_wgrad. */
+int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, void* stream);
 /* y = act(conv(x, w) + bias); if stats_nc != NULL also accumulates per-(image, channel) sum(y) and sum(y*y) of the
  * values written to y into stats_nc[n][k][2] (fp32, overwritten). bias may be NULL. */
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,

@@ -236,7 +236,9 @@ def test_tcgen05_convolution_matches_direct_and_oracle(dev, case):
     assert_close(outs['tc'][1], xr.grad, 2 * BF16_TOL, 'dx vs oracle')
 
 
-@pytest.mark.parametrize('n,c,h,w,k,ks,stride,pad', [(3, 3, 40, 36, 64, 7, 2, 3), (2, 5, 17, 19, 128, 3, 1, 1), (2, 16, 24, 24, 64, 3, 2, 1)])
+@pytest.mark.parametrize('n,c,h,w,k,ks,stride,pad', [(3, 3, 40, 36, 64, 7, 2, 3), (2, 5, 17, 19, 128, 3, 1, 1), (2, 16, 24, 24, 64, 3, 2, 1),
+                                                     # rows that are whole 16-byte groups: served by the gather kernel (im2col tile built in shared memory)
+                                                     (2, 3, 48, 40, 64, 7, 2, 3), (1, 3, 224, 224, 64, 7, 2, 3), (2, 8, 20, 24, 128, 5, 1, 2), (3, 3, 8, 264, 64, 3, 1, 1)])
 def test_im2col_tensor_core_path_matches_direct(dev, n, c, h, w, k, ks, stride, pad):
     """ Convolutions with few input channels / strides (the 7x7 stride-2 stem) run as explicit im2col + tcgen05 GEMM in bf16 mode: same numbers as
     the direct kernels on the same operands (forward, weight gradient; the data gradient stays on the direct kernel). """
