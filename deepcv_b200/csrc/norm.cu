@@ -340,6 +340,8 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
   //    partials combined through shared memory by one thread per channel
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   __shared__ double part[32][2];
+  constexpr int kShCh = 64;
+  __shared__ float sh_ab[kShCh][2];   // alpha, beta of this CTA's channels (when it has at most kShCh): phases 2 / 3 read them here, not from global
   const int wpc = max(1, nwarps / max(cl, 1)), cpp = nwarps / wpc;   // warps per channel, channels per pass
   for (int c0 = 0; c0 < cl; c0 += cpp) {
     const int chl = c0 + warp / wpc, sub = warp % wpc;
@@ -352,45 +354,55 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
       if (lane == 0) { part[warp][0] = s1; part[warp][1] = s2; }
     }
     __syncthreads();
-    if (tid < cpp && c0 + tid < cl) {
-      const int ch = ch_lo + c0 + tid;
+    if (warp < cpp && c0 + warp < cl) {   // warp w finishes channel c0 + w: its lanes fold the wpc partials
+      const int ch = ch_lo + c0 + warp;
       double alpha = 1.0, beta = 0.0, mean = 0.0, rstd = 1.0;
+      // parameters are fetched before the reduction so that their latency overlaps it
+      const double gamma = (prm.use_bn && prm.bn_weight) ? (double)prm.bn_weight[ch] : 1.0;
+      const double bias = (prm.use_bn && prm.bn_bias) ? (double)prm.bn_bias[ch] : 0.0;
+      const bool run = prm.use_bn && prm.bn_running_mean && prm.bn_running_var;
+      const double rm = run ? (double)prm.bn_running_mean[ch] : 0.0, rv = run ? (double)prm.bn_running_var[ch] : 1.0;
       if (prm.use_bn) {
         double var;
         if (prm.bn_training) {
-          double s1 = 0.0, s2 = 0.0;
-          for (int j = 0; j < wpc; ++j) { s1 += part[tid * wpc + j][0]; s2 += part[tid * wpc + j][1]; }
+          double s1 = lane < wpc ? part[warp * wpc + lane][0] : 0.0, s2 = lane < wpc ? part[warp * wpc + lane][1] : 0.0;
+          s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
           const double m = (double)n * hw;
           mean = s1 / m;
           var = s2 / m - mean * mean;
           if (var < 0.0) var = 0.0;
-          if (prm.bn_running_mean && prm.bn_running_var) {
+          if (run && lane == 0) {
             double mom = (double)prm.bn_momentum;
             if (mom < 0.0) mom = 1.0 / (double)((prm.bn_num_batches_tracked ? *prm.bn_num_batches_tracked : 0) + 1);
             const double unbiased = m > 1.0 ? var * m / (m - 1.0) : var;
-            prm.bn_running_mean[ch] = (float)((1.0 - mom) * (double)prm.bn_running_mean[ch] + mom * mean);
-            prm.bn_running_var[ch] = (float)((1.0 - mom) * (double)prm.bn_running_var[ch] + mom * unbiased);
+            prm.bn_running_mean[ch] = (float)((1.0 - mom) * rm + mom * mean);
+            prm.bn_running_var[ch] = (float)((1.0 - mom) * rv + mom * unbiased);
           }
         } else {
-          mean = (double)prm.bn_running_mean[ch];
-          var = (double)prm.bn_running_var[ch];
+          mean = rm;
+          var = rv;
         }
         rstd = rsqrt(var + (double)prm.bn_eps);
-        const double gamma = prm.bn_weight ? (double)prm.bn_weight[ch] : 1.0;
-        const double bias = prm.bn_bias ? (double)prm.bn_bias[ch] : 0.0;
         alpha = gamma * rstd;
         beta = bias - mean * alpha;
       }
-      saved[2 * ch] = (float)mean; saved[2 * ch + 1] = (float)rstd;
-      saved[off_alpha(c) + 2 * ch] = (float)alpha; saved[off_alpha(c) + 2 * ch + 1] = (float)beta;
+      if (lane == 0) {
+        saved[2 * ch] = (float)mean; saved[2 * ch + 1] = (float)rstd;
+        saved[off_alpha(c) + 2 * ch] = (float)alpha; saved[off_alpha(c) + 2 * ch + 1] = (float)beta;
+        if (cl <= kShCh) { sh_ab[c0 + warp][0] = (float)alpha; sh_ab[c0 + warp][1] = (float)beta; }   // same float rounding as the copy the backward reads
+      }
     }
     __syncthreads();
   }
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0 && prm.use_bn && prm.bn_training && prm.bn_num_batches_tracked) *prm.bn_num_batches_tracked += 1;
-  // 2. GroupNorm per (n, group) on u = alpha*y + beta
-  if (prm.use_gn) {
-    const int cg = c / G;
+  const bool ab_in_smem = cl <= kShCh;
+  auto alpha_of = [&](int ch) { return ab_in_smem ? (double)sh_ab[ch - ch_lo][0] : (double)saved[off_alpha(c) + 2 * ch]; };
+  auto beta_of = [&](int ch) { return ab_in_smem ? (double)sh_ab[ch - ch_lo][1] : (double)saved[off_alpha(c) + 2 * ch + 1]; };
+  const int cg = c / G;
+  if (prm.use_gn && cg <= 16) {
+    // 2 + 3 merged (small groups: the CIFAR layers have 1 or 4 channels per group): one thread per (image, group) computes the group statistics
+    // and writes the combined affine of its channels — no second pass over global memory, no barrier in between
     const double mg = (double)cg * hw;
     const int g_lo = ch_lo / cg, gl = cl / cg;
     for (int j = tid; j < n * gl; j += nt) {
@@ -399,7 +411,38 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
       double su = 0.0, suu = 0.0;
       for (int k = 0; k < cg; ++k) {
         const int ch = grp * cg + k;
-        const double al = (double)saved[off_alpha(c) + 2 * ch], be = (double)saved[off_alpha(c) + 2 * ch + 1];
+        const double al = alpha_of(ch), be = beta_of(ch);
+        const double sy = (double)stats[((size_t)img * c + ch) * 2], syy = (double)stats[((size_t)img * c + ch) * 2 + 1];
+        su += al * sy + hw * be;
+        suu += al * al * syy + 2.0 * al * be * sy + hw * be * be;
+      }
+      const double meand = su / mg;
+      double var = suu / mg - meand * meand;
+      if (var < 0.0) var = 0.0;
+      const float mean_f = (float)meand, rstd_f = (float)rsqrt(var + (double)prm.gn_eps);
+      saved[off_gn(c) + 2 * (size_t)i] = mean_f;
+      saved[off_gn(c) + 2 * (size_t)i + 1] = rstd_f;
+      for (int k = 0; k < cg; ++k) {
+        const int ch = grp * cg + k;
+        const double a2 = (prm.gn_weight ? (double)prm.gn_weight[ch] : 1.0) * (double)rstd_f;
+        const double b2 = (prm.gn_bias ? (double)prm.gn_bias[ch] : 0.0) - (double)mean_f * a2;
+        const size_t o = (size_t)img * c + ch;
+        ab[2 * o] = (float)(a2 * alpha_of(ch)); ab[2 * o + 1] = (float)(a2 * beta_of(ch) + b2);
+      }
+    }
+    return;
+  }
+  // 2. GroupNorm per (n, group) on u = alpha*y + beta
+  if (prm.use_gn) {
+    const double mg = (double)cg * hw;
+    const int g_lo = ch_lo / cg, gl = cl / cg;
+    for (int j = tid; j < n * gl; j += nt) {
+      const int img = j / gl, grp = g_lo + (j - img * gl);
+      const size_t i = (size_t)img * G + grp;
+      double su = 0.0, suu = 0.0;
+      for (int k = 0; k < cg; ++k) {
+        const int ch = grp * cg + k;
+        const double al = alpha_of(ch), be = beta_of(ch);
         const double sy = (double)stats[((size_t)img * c + ch) * 2], syy = (double)stats[((size_t)img * c + ch) * 2 + 1];
         su += al * sy + hw * be;
         suu += al * al * syy + 2.0 * al * be * sy + hw * be * be;
@@ -413,11 +456,10 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(const dcv_norm_param
     __syncthreads();
   }
   // 3. combined affine per (n, c)
-  const int cg = c / G;
   for (int j = tid; j < n * cl; j += nt) {
     const int img = j / cl, ch = ch_lo + (j - img * cl);
     const size_t i = (size_t)img * c + ch;
-    double A = (double)saved[off_alpha(c) + 2 * ch], B = (double)saved[off_alpha(c) + 2 * ch + 1];
+    double A = alpha_of(ch), B = beta_of(ch);
     if (prm.use_gn) {
       const size_t gi = (size_t)img * G + ch / cg;
       const double mean = (double)saved[off_gn(c) + 2 * gi], rstd = (double)saved[off_gn(c) + 2 * gi + 1];
