@@ -473,7 +473,7 @@ struct GatherParams {
   __nv_bfloat16* y;
 };
 constexpr int GA_BOX_W = 192;   // elements per staging box: 384 B, a multiple of the 128-byte alignment TMA wants for its shared-memory destination
-constexpr int GA_THREADS = 448, GA_STAGES = 2, GA_PRODUCERS = 256, GA_ROW_BUFS = 3;   // warps: 0 weights (TMA), 1 MMA, 2..5 epilogue, 6..13 producers
+constexpr int GA_THREADS = 448, GA_STAGES = 2, GA_FWD_STAGES = 3, GA_PRODUCERS = 256, GA_ROW_BUFS = 3;   // warps: 0 weights (TMA), 1 MMA, 2..5 epilogue, 6..13 producers
 
 // Producer warp `pw` of GA_PRODUCERS / 32 builds its share of the (chunk column, 32-row band) units of the tile; lane = row within the band. The
 // unit list of a warp is the same for every tile: it is decoded ONCE into registers (ncu on the version that decoded it per unit: three runtime integer
@@ -535,21 +535,21 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const
   const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = res_base + (uint32_t)prm.kblocks * B_BYTES;
   const uint32_t a_stage_bytes = (uint32_t)prm.kblocks * A_SLAB;
-  const uint32_t rows_base = a_base + GA_STAGES * a_stage_bytes;
+  const uint32_t rows_base = a_base + GA_FWD_STAGES * a_stage_bytes;
   const uint32_t bars = rows_base + (uint32_t)GA_ROW_BUFS * (uint32_t)prm.rows_bytes;
   auto full = [&](int i) { return bars + 8u * i; };
-  auto empty = [&](int i) { return bars + 8u * (GA_STAGES + i); };
-  auto tfull = [&](int i) { return bars + 8u * (2 * GA_STAGES + i); };
-  auto tempty = [&](int i) { return bars + 8u * (2 * GA_STAGES + 2 + i); };
-  const uint32_t bres = bars + 8u * (2 * GA_STAGES + 4), tmem_slot = bars + 8u * (2 * GA_STAGES + 5);
-  auto rfull = [&](int i) { return bars + 8u * (2 * GA_STAGES + 6 + i); };    // staged rows of buffer i landed (TMA)
-  auto rempty = [&](int i) { return bars + 8u * (2 * GA_STAGES + 6 + GA_ROW_BUFS + i); };   // all producer warps are done reading buffer i
+  auto empty = [&](int i) { return bars + 8u * (GA_FWD_STAGES + i); };
+  auto tfull = [&](int i) { return bars + 8u * (2 * GA_FWD_STAGES + i); };
+  auto tempty = [&](int i) { return bars + 8u * (2 * GA_FWD_STAGES + 2 + i); };
+  const uint32_t bres = bars + 8u * (2 * GA_FWD_STAGES + 4), tmem_slot = bars + 8u * (2 * GA_FWD_STAGES + 5);
+  auto rfull = [&](int i) { return bars + 8u * (2 * GA_FWD_STAGES + 6 + i); };    // staged rows of buffer i landed (TMA)
+  auto rempty = [&](int i) { return bars + 8u * (2 * GA_FWD_STAGES + 6 + GA_ROW_BUFS + i); };   // all producer warps are done reading buffer i
   uint8_t* gen_base = smem_raw + (res_base - smem_u32(smem_raw));   // generic-address view of the same buffer
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const dcv_conv_shape& s = prm.s;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GA_STAGES; ++i) { mbar_init(full(i), GA_PRODUCERS / 32); mbar_init(empty(i), 1); }
+    for (int i = 0; i < GA_FWD_STAGES; ++i) { mbar_init(full(i), GA_PRODUCERS / 32); mbar_init(empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
     mbar_init(bres, 1);
     for (int i = 0; i < GA_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), GA_PRODUCERS / 32); }
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const
         }
         umma_commit(empty(stage));
         umma_commit(tfull(as));
-        if (++stage == GA_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == GA_FWD_STAGES) { stage = 0; phase ^= 1u; }
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) { mbar_arrive(full(stage)); mbar_arrive(rempty(buf)); }
-      if (++stage == GA_STAGES) { stage = 0; phase ^= 1u; }
+      if (++stage == GA_FWD_STAGES) { stage = 0; phase ^= 1u; }
       if (++buf == GA_ROW_BUFS) { buf = 0; rphase ^= 1u; }
     }
   }
@@ -1191,7 +1191,7 @@ static bool gather_geometry(const dcv_conv_shape* s, const void* x, int kpad, Ga
   if (tiles >= (1ll << 31)) return false;
   prm->total_tiles = (int)tiles;
   if (GA_PRODUCERS % (kpad / 8) != 0 && GA_PRODUCERS / (kpad / 8) < 1) return false;
-  *smem = 1024 + (size_t)prm->kblocks * b_bytes + (size_t)GA_STAGES * prm->kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * prm->rows_bytes + 256;
+  *smem = 1024 + (size_t)prm->kblocks * b_bytes + (size_t)GA_FWD_STAGES * prm->kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * prm->rows_bytes + 256;
   return *smem <= 227 * 1024;
 }
 

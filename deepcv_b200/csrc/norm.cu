@@ -545,16 +545,21 @@ __global__ void __launch_bounds__(1024) bwd_finalize_kernel(const dcv_norm_param
       if (lane == 0) { part[warp][0] = u1; part[warp][1] = u2raw; part[warp][2] = dgw; part[warp][3] = dgb; }
     }
     __syncthreads();
-    if (tid < cpp && c0 + tid < cl) {
-      const int ch = ch_lo + c0 + tid;
+    if (warp < cpp && c0 + warp < cl) {   // warp w finishes channel c0 + w: its lanes fold the wpc partials
+      const int ch = ch_lo + c0 + warp;
       const double mu = (double)saved[2 * ch], rc = (double)saved[2 * ch + 1];
-      double u1 = 0.0, u2raw = 0.0, dgw = 0.0, dgb = 0.0;
-      for (int j = 0; j < wpc; ++j) { u1 += part[tid * wpc + j][0]; u2raw += part[tid * wpc + j][1]; dgw += part[tid * wpc + j][2]; dgb += part[tid * wpc + j][3]; }
-      const double u2 = rc * (u2raw - mu * u1);
-      saved[off_u(c, n, G) + 2 * ch] = (float)u1;
-      saved[off_u(c, n, G) + 2 * ch + 1] = (float)u2;
-      if (prm.use_bn) { if (d_bn_w) d_bn_w[ch] = (float)u2; if (d_bn_b) d_bn_b[ch] = (float)u1; }
-      if (prm.use_gn) { if (d_gn_w) d_gn_w[ch] = (float)dgw; if (d_gn_b) d_gn_b[ch] = (float)dgb; }
+      const bool has = lane < wpc;
+      double u1 = has ? part[warp * wpc + lane][0] : 0.0, u2raw = has ? part[warp * wpc + lane][1] : 0.0;
+      double dgw = has ? part[warp * wpc + lane][2] : 0.0, dgb = has ? part[warp * wpc + lane][3] : 0.0;
+      u1 = warp_sum_d(u1); u2raw = warp_sum_d(u2raw);
+      if (prm.use_gn) { dgw = warp_sum_d(dgw); dgb = warp_sum_d(dgb); }
+      if (lane == 0) {
+        const double u2 = rc * (u2raw - mu * u1);
+        saved[off_u(c, n, G) + 2 * ch] = (float)u1;
+        saved[off_u(c, n, G) + 2 * ch + 1] = (float)u2;
+        if (prm.use_bn) { if (d_bn_w) d_bn_w[ch] = (float)u2; if (d_bn_b) d_bn_b[ch] = (float)u1; }
+        if (prm.use_gn) { if (d_gn_w) d_gn_w[ch] = (float)dgw; if (d_gn_b) d_gn_b[ch] = (float)dgb; }
+      }
     }
     __syncthreads();
   }
