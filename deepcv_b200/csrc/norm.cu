@@ -636,6 +636,8 @@ static void finalize_grid(const dcv_norm_params* prm, int* cpb, int* blocks) {
   while ((prm->c + per - 1) / per > dcv::kNumSMs) per += cg;
   *cpb = per;
   *blocks = (prm->c + per - 1) / per;
+  // momentum = None (cumulative moving average): every channel's update reads num_batches_tracked and block 0 increments it — one CTA, no race
+  if (prm->use_bn && prm->bn_training && prm->bn_momentum < 0.f && prm->bn_num_batches_tracked) { *cpb = prm->c; *blocks = 1; }
 }
 
 static int check_norm_params(const dcv_norm_params* prm, const char* name) {

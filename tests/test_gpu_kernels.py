@@ -123,3 +123,47 @@ def test_tcgen05_wgrad_pointwise_channel_blocks(dev, n, c, hw, k):
     ref = dy.double().reshape(-1, k).t() @ x.double().reshape(-1, c)
     assert rel(dw.reshape(k, c), ref) <= 2e-2
     assert rel(dw.reshape(k, c), ref) <= 5e-3, 'fp32 accumulation of bf16 products should be far inside the bf16 tolerance'
+
+
+@pytest.mark.parametrize('momentum', [0.07359778246238029, None])
+@pytest.mark.parametrize('n,hw,c,groups', [(6, 49, 96, 0), (512, 16, 4, 4), (3, 100, 256, 32), (2, 9, 2048, 0)])
+def test_norm_finalize_running_statistics_and_affine(dev, n, hw, c, groups, momentum):
+    """ dcv_norm_fwd_finalize over several steps against torch.nn.BatchNorm2d (+ GroupNorm): running_mean / running_var / num_batches_tracked (also with
+    momentum=None, the cumulative average, where every channel's update reads the counter: served by a single CTA) and the folded per-(n,c) affine
+    applied to y reproduces BatchNorm -> GroupNorm of the reference modules. """
+    from deepcv_b200._lib import DCV_F32, NormParams, check, lib
+    torch.manual_seed(c + n)
+    bn = torch.nn.BatchNorm2d(c, eps=1e-5, momentum=momentum)
+    gn = torch.nn.GroupNorm(groups, c) if groups else None
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+        if gn is not None:
+            gn.weight.uniform_(0.5, 1.5); gn.bias.normal_()
+    rm, rv = bn.running_mean.clone().to(dev), bn.running_var.clone().to(dev)
+    nbt = torch.zeros((), dtype=torch.int64, device=dev)
+    bw, bb = bn.weight.detach().to(dev), bn.bias.detach().to(dev)
+    gw = gn.weight.detach().to(dev) if gn is not None else None
+    gb = gn.bias.detach().to(dev) if gn is not None else None
+    side = int(round(hw ** 0.5))
+    assert side * side == hw
+    st = stream()
+    for step in range(3):
+        y = torch.randn(n, c, side, side) * (1.0 + step) + 0.3 * step
+        ref = bn(y)
+        if gn is not None:
+            ref = gn(ref)
+        yd = y.permute(0, 2, 3, 1).contiguous().to(dev)                     # NHWC
+        stats = torch.empty(n, c, 2, device=dev)
+        check(lib.dcv_norm_stats(P(yd), P(stats), n, hw, c, DCV_F32, st), 'norm_stats')
+        G = groups if groups else 1
+        saved = torch.empty(int(lib.dcv_norm_saved_floats(n, c, G)), device=dev)
+        ab = torch.empty(n, c, 2, device=dev)
+        prm = NormParams(n, c, hw, 1, 1, 1e-5, -1.0 if momentum is None else momentum, P(bw), P(bb), P(rm), P(rv), P(nbt),
+                         1 if groups else 0, G, 1e-5, P(gw), P(gb))
+        check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), P(stats), P(ab), P(saved), st), 'norm_fwd_finalize')
+        z = torch.empty_like(yd)
+        check(lib.dcv_norm_apply_fwd(P(yd), P(ab), P(z), n, hw, c, DCV_F32, st), 'norm_apply_fwd')
+        torch.cuda.synchronize()
+        assert int(nbt) == step + 1 == int(bn.num_batches_tracked)
+        assert rel(rm, bn.running_mean) <= 1e-5 and rel(rv, bn.running_var) <= 1e-5
+        assert rel(z.permute(0, 3, 1, 2), ref.detach()) <= 1e-4
