@@ -63,10 +63,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 // 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier like the tensor variants
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -467,8 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_halo_kernel(const __g
 // The explicit im2col route materialises col[n][p][q][kpad] (1.2 GB for the stem at batch 256: 338 us to write it + a GEMM that is HBM-bound reading it
 // back = the most expensive layer of the ImageNet-shaped step). Here eight PRODUCER warps build the 128 x kpad im2col tile of one output-row segment
 // directly in shared memory, in the K-major SWIZZLE_128B layout TMA would have produced (16-byte chunk j of row m lives at chunk j ^ (m & 7) of its
-// 128-byte line): the R input rows the segment reads are staged by TMA (one 384-byte box per row piece, rows outside the image zero-filled) into a
-// double-buffered area with zeroed margins. (cp.async staging by the producers themselves was 5x slower: the fence.proxy.async they need after
+// 128-byte line): the R input rows the segment reads are staged by ONE bulk copy each (cp.async.bulk, rows outside the image come from a zero row) into
+// a triple-buffered area with zeroed margins. (cp.async staging by the producers themselves was 5x slower: the fence.proxy.async they need after
 // writing the tile compiles to MEMBAR.ALL.CTA, which waits for their in-flight prefetch of the NEXT tile — a full L2 / DRAM round trip per tile.)
 // K order ("row padded"): column kk = r * RP + x, x < RP = S*C rounded up to 8; for x >= S*C the WEIGHT is zero, so the tile may hold whatever follows in
 // the staged row there. A 16-byte chunk is then always 8 CONTIGUOUS staged elements at a 2-byte-aligned address: five aligned 32-bit shared loads and a
@@ -477,14 +473,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_halo_kernel(const __g
 struct GatherParams {
   dcv_conv_shape s;
   int kpad, kblocks, rowlen, lpad, rows_bytes, rp;   // rp: elements per filter row in the K order (S*C rounded up to 8)
-  int nboxes;                                         // TMA boxes (GA_BOX_W elements each) per staged row
   int tiles_q, total_tiles;
   int act; float slope;
   const float* bias;
   const __nv_bfloat16* x;
   __nv_bfloat16* y;
 };
-constexpr int GA_BOX_W = 192;   // elements per staging box: 384 B, a multiple of the 128-byte alignment TMA wants for its shared-memory destination
 constexpr int GA_THREADS = 448, GA_STAGES = 2, GA_FWD_STAGES = 3, GA_PRODUCERS = 256, GA_ROW_BUFS = 3;   // warps: 0 weights (TMA), 1 MMA, 2..5 epilogue, 6..13 producers
 
 // Producer warp `pw` of GA_PRODUCERS / 32 builds its share of the (chunk column, 32-row band) units of the tile; lane = row within the band. The
@@ -541,7 +535,7 @@ __device__ __forceinline__ void gather_build_tile(const GatherParams& prm, const
 }
 
 template <int N_TILE>
-__global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GatherParams prm) {
+__global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const __grid_constant__ CUtensorMap map_w, const GatherParams prm) {
   constexpr int B_BYTES = N_TILE * BLOCK_K * 2, A_SLAB = BLOCK_M * 128;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -567,13 +561,12 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const
     for (int i = 0; i < GA_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), GA_PRODUCERS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * N_TILE) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // both staging buffers start as zeros: TMA only ever writes [lpad, lpad + nboxes * GA_BOX_W) of each row, the margins are the convolution padding
+  // the staging buffers start as zeros: the bulk copies only ever write [lpad, lpad + W*C) of each row, the margins are the convolution padding
   for (uint32_t i = threadIdx.x; i < (uint32_t)GA_ROW_BUFS * (uint32_t)prm.rows_bytes / 16u; i += GA_THREADS)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rows_base + i * 16u), "r"(0) : "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -694,7 +687,7 @@ struct GatherWgradParams {
 };
 constexpr int GW_NA = 2;   // dy tile slots (2 x 16 KB atoms each)
 
-__global__ void __launch_bounds__(GA_THREADS, 1) conv_wgrad_tc_gather_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const GatherWgradParams wp) {
+__global__ void __launch_bounds__(GA_THREADS, 1) conv_wgrad_tc_gather_kernel(const __grid_constant__ CUtensorMap map_dy, const GatherWgradParams wp) {
   const GatherParams& prm = wp.g;
   constexpr int A_SLAB = BLOCK_M * 128, DY_BYTES = 2 * A_SLAB;
   extern __shared__ uint8_t smem_raw[];
@@ -722,7 +715,6 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_wgrad_tc_gather_kernel(con
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dy)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
@@ -900,219 +892,6 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const FwdPar
 }
 
 
-// ---- forward / data gradient, "row-halo" variant for 3x3-class filters on maps with >= 14 rows ---------------------------------------------------
-// The per-tap kernel above re-reads every input element R*S times and every weight once per 128 pixels from L2, which caps the 64..256-channel layers
-// far below the tensor peak. Here a CTA works on a PAIR of horizontally adjacent 8-wide, th-tall pixel tiles:
-//   * A: for a 64-channel block only S column-shifted boxes {64 ch, 16 px, th+R-1 rows} are loaded (3 instead of 9 for a 3x3 filter). One box row
-//     = 16 pixels = two 1024-byte swizzle groups: tile 0 is the even groups, tile 1 the odd ones (stride 2048 B between a tile's 8-row groups), and
-//     the filter row r is just a start offset of r*2048 B — plain K-major SWIZZLE_128B descriptors, no re-swizzling.
-//   * B: each streamed weight slab feeds 2 x 4 MMAs (both tiles), halving weight traffic per pixel.
-//   * D: 2 tiles x N_TILE columns, double buffered (4 x N_TILE <= 512 TMEM columns => N_TILE <= 128).
-// Warps: 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3..6 = epilogue.
-struct FwdV2Params {
-  int n, c, k, r, s, pad_h, pad_w, p, q;
-  int th, tiles_h, pairs_w, n_tiles_k, total_tiles;
-  int act; float slope;
-  const float* bias;
-  __nv_bfloat16* y;
-};
-
-constexpr int V2_THREADS = 224, V2_A_SLOTS = 4, V2_B_SLOTS = 4, V2_A_BYTES = 18 * 2048;
-
-template <int N_TILE>
-__global__ void __launch_bounds__(V2_THREADS, 1) conv_fwd_tc_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FwdV2Params prm) {
-  constexpr int B_BYTES = N_TILE * 128;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_a = base, smem_b = base + V2_A_SLOTS * V2_A_BYTES;
-  const uint32_t bars = smem_b + V2_B_SLOTS * B_BYTES;
-  auto afull = [&](int i) { return bars + 8u * i; };
-  auto aempty = [&](int i) { return bars + 8u * (V2_A_SLOTS + i); };
-  auto bfull = [&](int i) { return bars + 8u * (2 * V2_A_SLOTS + i); };
-  auto bempty = [&](int i) { return bars + 8u * (2 * V2_A_SLOTS + V2_B_SLOTS + i); };
-  auto tfull = [&](int i) { return bars + 8u * (2 * V2_A_SLOTS + 2 * V2_B_SLOTS + i); };
-  auto tempty = [&](int i) { return bars + 8u * (2 * V2_A_SLOTS + 2 * V2_B_SLOTS + 2 + i); };
-  const uint32_t tmem_slot = bars + 8u * (2 * V2_A_SLOTS + 2 * V2_B_SLOTS + 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < V2_A_SLOTS; ++i) { mbar_init(afull(i), 1); mbar_init(aempty(i), 1); }
-    for (int i = 0; i < V2_B_SLOTS; ++i) { mbar_init(bfull(i), 1); mbar_init(bempty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(4 * N_TILE) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int cblocks = prm.c / BLOCK_K;
-  const uint32_t a_bytes = (uint32_t)(prm.th + prm.r - 1) * 2048u;
-
-  // tile -> (n_tile, pair column, tile row, image)
-  auto decode = [&](int tile, int& nt, int& q0, int& p0, int& img) {
-    nt = tile % prm.n_tiles_k; int t = tile / prm.n_tiles_k;
-    q0 = (t % prm.pairs_w) * 16; t /= prm.pairs_w;
-    p0 = (t % prm.tiles_h) * prm.th; img = t / prm.tiles_h;
-  };
-
-  if (warp == 0) {
-    if (elect_one()) {   // ===== A producer: S column-shifted boxes per channel block
-      int slot = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        int nt, q0, p0, img; decode(tile, nt, q0, p0, img);
-        for (int cb = 0; cb < cblocks; ++cb)
-          for (int ss = 0; ss < prm.s; ++ss) {
-            mbar_wait(aempty(slot), phase ^ 1u);
-            mbar_expect_tx(afull(slot), a_bytes);
-            tma_load_4d(smem_a + slot * V2_A_BYTES, &map_x, afull(slot), cb * BLOCK_K, q0 + ss - prm.pad_w, p0 - prm.pad_h, img);
-            if (++slot == V2_A_SLOTS) { slot = 0; phase ^= 1u; }
-          }
-      }
-    }
-  } else if (warp == 2) {
-    if (elect_one()) {   // ===== B producer: one weight slab per (channel block, s, r)
-      int slot = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        int nt, q0, p0, img; decode(tile, nt, q0, p0, img);
-        for (int cb = 0; cb < cblocks; ++cb)
-          for (int ss = 0; ss < prm.s; ++ss)
-            for (int rr = 0; rr < prm.r; ++rr) {
-              mbar_wait(bempty(slot), phase ^ 1u);
-              mbar_expect_tx(bfull(slot), B_BYTES);
-              tma_load_2d(smem_b + slot * B_BYTES, &map_w, bfull(slot), (rr * prm.s + ss) * prm.c + cb * BLOCK_K, nt * N_TILE);
-              if (++slot == V2_B_SLOTS) { slot = 0; phase ^= 1u; }
-            }
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {   // ===== MMA issuer
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
-      int aslot = 0, bslot = 0; uint32_t aph = 0, bph = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty(as), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * N_TILE);
-        uint32_t first = 1;
-        for (int cb = 0; cb < cblocks; ++cb)
-          for (int ss = 0; ss < prm.s; ++ss) {
-            mbar_wait(afull(aslot), aph);
-            tc_fence_after();
-            const uint32_t abuf = smem_a + aslot * V2_A_BYTES;
-            for (int rr = 0; rr < prm.r; ++rr) {
-              mbar_wait(bfull(bslot), bph);
-              tc_fence_after();
-              const uint64_t bdesc = make_desc(smem_b + bslot * B_BYTES, 0, 1024);
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                const uint64_t adesc = make_desc(abuf + rr * 2048 + t * 1024, 0, 2048);
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                  umma_bf16(d0 + (uint32_t)(t * N_TILE), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
-              }
-              first = 0;
-              umma_commit(bempty(bslot));
-              if (++bslot == V2_B_SLOTS) { bslot = 0; bph ^= 1u; }
-            }
-            umma_commit(aempty(aslot));
-            if (++aslot == V2_A_SLOTS) { aslot = 0; aph ^= 1u; }
-          }
-        umma_commit(tfull(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
-      }
-    }
-  } else {
-    // ===== epilogue warps 3..6: lane quarter = warp % 4
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int hl = row >> 3, wl = row & 7;
-    int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-      int nt, q0, p0, img; decode(tile, nt, q0, p0, img);
-      const int p = p0 + hl;
-      const bool row_ok = hl < prm.th && p < prm.p;
-      mbar_wait(tfull(as), aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const int q = q0 + t * 8 + wl;
-        const bool valid = row_ok && q < prm.q;
-        __nv_bfloat16* dst = prm.y + (((size_t)img * prm.p + p) * prm.q + q) * prm.k + (size_t)nt * N_TILE;
-        const uint32_t taddr = tmem_base + (uint32_t)(as * 2 * N_TILE + t * N_TILE) + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + nt * N_TILE + c0 : nullptr, prm.slope, dst + c0);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * N_TILE) : "memory");
-  }
-}
-
-template <int N_TILE>
-static int launch_fwd_v2(const CUtensorMap& mx, const CUtensorMap& mw, const FwdV2Params& prm, cudaStream_t st) {
-  auto kern = conv_fwd_tc_v2_kernel<N_TILE>;
-  const size_t smem = 1024 + (size_t)V2_A_SLOTS * V2_A_BYTES + (size_t)V2_B_SLOTS * N_TILE * 128 + 256;
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
-  kern<<<grid, V2_THREADS, smem, st>>>(mx, mw, prm);
-  DCV_LAUNCH_CHECK("conv_fwd_tc_v2_kernel");
-  return 0;
-}
-
-static bool fwd_v2_applicable(const dcv_conv_shape* s) {
-  // Measured on B200 (profiles/r01_tc_conv_layers.txt): after the epilogue was slimmed down the per-tap kernel is as fast or faster on every
-  // ResNet-style layer (this variant spends 24 % of its MMA rows on tile overhang), so it is opt-in.
-  static const bool enabled = getenv("DCV_TC_V2") != nullptr;
-  return enabled && s->r >= 2 && s->r <= 3 && s->s >= 2 && s->s <= 3 && s->p >= 14 && s->q >= 12;
-}
-
-static int conv_fwd_tc_v2(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, int act, float slope, cudaStream_t st) {
-  FwdV2Params prm{};
-  prm.n = s->n; prm.c = s->c; prm.k = s->k; prm.r = s->r; prm.s = s->s; prm.pad_h = s->pad_h; prm.pad_w = s->pad_w; prm.p = s->p; prm.q = s->q;
-  prm.tiles_h = (s->p + 15) / 16;
-  prm.th = (s->p + prm.tiles_h - 1) / prm.tiles_h;
-  prm.pairs_w = (s->q + 15) / 16;
-  const int n_tile = s->k % 128 == 0 ? 128 : 64;
-  prm.n_tiles_k = s->k / n_tile;
-  const long long tiles = (long long)s->n * prm.tiles_h * prm.pairs_w * prm.n_tiles_k;
-  DCV_REQUIRE(tiles < (1ll << 31), "conv2d_fwd (tcgen05): too many tiles");
-  prm.total_tiles = (int)tiles;
-  prm.act = act; prm.slope = slope; prm.bias = bias; prm.y = reinterpret_cast<__nv_bfloat16*>(y);
-  CUtensorMap mx, mw;
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)s->c, (cuuint64_t)s->w, (cuuint64_t)s->h, (cuuint64_t)s->n};
-    const cuuint64_t strides[3] = {(cuuint64_t)s->c * 2, (cuuint64_t)s->w * s->c * 2, (cuuint64_t)s->h * s->w * s->c * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, 16u, (cuuint32_t)(prm.th + s->r - 1), 1u};
-    if (make_map(&mx, x, 4, dims, strides, box)) return 1;
-  }
-  {
-    const cuuint64_t dims[2] = {(cuuint64_t)s->r * s->s * s->c, (cuuint64_t)s->k};
-    const cuuint64_t strides[1] = {(cuuint64_t)s->r * s->s * s->c * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)n_tile};
-    if (make_map(&mw, w, 2, dims, strides, box)) return 1;
-  }
-  return n_tile == 128 ? launch_fwd_v2<128>(mx, mw, prm, st) : launch_fwd_v2<64>(mx, mw, prm, st);
-}
-
 // Halo variant: filters wider than one tap, a single output-channel tile of 64 or 128 whose weight slabs all stay resident (<= 144 KB), and a map that
 // 8 x th tiles cover with <= 15 % overhang (56 x 56: 7 x 4 tiles of 8 x 14, 12.5 %; the 28 / 14 / 7 pixel maps lose more than they gain).
 static bool fwd_halo_applicable(const dcv_conv_shape* s) {
@@ -1169,21 +948,6 @@ static int conv_fwd_tc_halo(const dcv_conv_shape* s, const void* x, const void* 
   return s->k == 128 ? launch_fwd_halo<128>(mx, mw, prm, smem, st) : launch_fwd_halo<64>(mx, mw, prm, smem, st);
 }
 
-// x viewed as [N][H][W*C] bf16 rows for the gather kernels' staging: box = GA_BOX_W elements of one row, no swizzle, zero fill outside the tensor
-// (rows above / below the image = vertical padding; the tail of the last box beyond W*C lands in the zero margin).
-static int make_rows_map(CUtensorMap* map, const void* x, const dcv_conv_shape* s) {
-  EncodeTiledFn fn = encode_tiled();
-  DCV_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[3] = {(cuuint64_t)s->w * s->c, (cuuint64_t)s->h, (cuuint64_t)s->n};
-  const cuuint64_t strides[2] = {(cuuint64_t)s->w * s->c * 2, (cuuint64_t)s->h * s->w * s->c * 2};
-  const cuuint32_t box[3] = {(cuuint32_t)GA_BOX_W, 1u, 1u};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (staging rows) failed with CUresult %d", (int)r);
-  return 0;
-}
-
 // Geometry of the gather kernels' staging area; false when the layer does not fit (falls back to the explicit im2col route).
 static bool gather_geometry(const dcv_conv_shape* s, const void* x, int kpad, GatherParams* prm, size_t* smem, int b_bytes) {
   const int wc = s->w * s->c, rp = (s->s * s->c + 7) / 8 * 8;
@@ -1193,7 +957,6 @@ static bool gather_geometry(const dcv_conv_shape* s, const void* x, int kpad, Ga
   lpad = (lpad + 63) / 64 * 64;   // every staged row (and every box inside it) starts on a 128-byte boundary
   // the last tile's overhang pixels are not gathered, so the farthest element read belongs to pixel q - 1
   int need = lpad + ((s->q - 1) * s->stride_w - s->pad_w) * s->c + rp + 2;   // a chunk reads 5 aligned words = up to 10 elements from its first one
-  prm->nboxes = 0;
   if (need < lpad + wc) need = lpad + wc;
   const int rowlen = (need + 63) / 64 * 64;
   prm->s = *s; prm->kpad = kpad; prm->kblocks = kpad / BLOCK_K; prm->rowlen = rowlen; prm->lpad = lpad;
@@ -1230,19 +993,17 @@ int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col
     const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)s->k};
     if (make_map(&mw, w_col, 2, dims, strides, box)) return 1;
   }
-  CUtensorMap mx;
-  if (make_rows_map(&mx, x, s)) return 1;
   const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
   if (s->k == 128) {
     auto kern = conv_fwd_tc_gather_kernel<128>;
     static size_t configured = 0;
     if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
-    kern<<<grid, GA_THREADS, smem, st>>>(mw, mx, prm);
+    kern<<<grid, GA_THREADS, smem, st>>>(mw, prm);
   } else {
     auto kern = conv_fwd_tc_gather_kernel<64>;
     static size_t configured = 0;
     if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
-    kern<<<grid, GA_THREADS, smem, st>>>(mw, mx, prm);
+    kern<<<grid, GA_THREADS, smem, st>>>(mw, prm);
   }
   DCV_LAUNCH_CHECK("conv_fwd_tc_gather_kernel");
   if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
@@ -1261,19 +1022,18 @@ int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy,
   const size_t smem = 1024 + (size_t)GW_NA * 2 * BLOCK_M * 128 + (size_t)GA_STAGES * wp.g.kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * wp.g.rows_bytes + 256;
   DCV_REQUIRE(smem <= 227 * 1024, "conv2d_wgrad_gather: %zu bytes of shared memory needed", smem);
   cudaMemsetAsync(dw_col, 0, (size_t)s->k * kpad * sizeof(float), st);
-  CUtensorMap mdy, mx;
+  CUtensorMap mdy;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)s->k, (cuuint64_t)s->q, (cuuint64_t)s->p, (cuuint64_t)s->n};
     const cuuint64_t strides[3] = {(cuuint64_t)s->k * 2, (cuuint64_t)s->q * s->k * 2, (cuuint64_t)s->p * s->q * s->k * 2};
     const cuuint32_t box[4] = {64u, (cuuint32_t)BLOCK_M, 1u, 1u};
     if (make_map(&mdy, dy, 4, dims, strides, box)) return 1;
   }
-  if (make_rows_map(&mx, x, s)) return 1;
   auto kern = conv_wgrad_tc_gather_kernel;
   static size_t configured = 0;
   if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
   const int grid = wp.g.total_tiles < num_sms() ? wp.g.total_tiles : num_sms();
-  kern<<<grid, GA_THREADS, smem, st>>>(mdy, mx, wp);
+  kern<<<grid, GA_THREADS, smem, st>>>(mdy, wp);
   DCV_LAUNCH_CHECK("conv_wgrad_tc_gather_kernel");
   return 0;
 }
@@ -1290,11 +1050,6 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   using namespace tc;
   DCV_REQUIRE(x && w && y, "conv2d_fwd (tcgen05): null pointer");
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0), "conv2d_fwd (tcgen05): pointers must be 16-byte aligned");
-  if (fwd_v2_applicable(s)) {
-    if (conv_fwd_tc_v2(s, x, w, bias, y, act, slope, st)) return 1;
-    if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
-    return 0;
-  }
   if (fwd_halo_applicable(s)) {
     if (conv_fwd_tc_halo(s, x, w, bias, y, act, slope, st)) return 1;
     if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
