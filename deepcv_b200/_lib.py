@@ -36,6 +36,7 @@ SYMBOLS = {
     'dcv_last_error': (c_char_p, []),
     'dcv_device_check': (c_int, []),
     'dcv_launch_count': (c_uint64, []),
+    'dcv_set_accumulators_prezeroed': (c_int, [c_int]),
     'dcv_preprocess_u8': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P]),
     'dcv_nchw_to_nhwc': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_nhwc_to_nchw': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -44,7 +44,7 @@ int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, co
   DCV_REQUIRE(shape, "conv2d_fwd: null shape");
   cudaStream_t st = as_stream(stream);
   const bool tc_ok = conv_tc_fwd_supported(shape, dtype);
-  if (stats_nc) cudaMemsetAsync(stats_nc, 0, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
+  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
   DCV_REQUIRE(algo != DCV_ALGO_TCGEN05 || tc_ok, "conv2d_fwd: tcgen05 algorithm does not support this shape/dtype (needs bf16, c %% 64 == 0, k %% 16 == 0, stride 1, dilation 1)");
   if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(shape, x, w, bias, y, stats_nc, act, slope, st);
   return conv_fwd_direct(shape, x, w, bias, y, stats_nc, act, slope, dtype, st);
@@ -59,7 +59,7 @@ int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void
   using namespace dcv;
   DCV_REQUIRE(shape, "conv2d_fwd_gather: null shape");
   cudaStream_t st = as_stream(stream);
-  if (stats_nc) cudaMemsetAsync(stats_nc, 0, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
+  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
   return conv_fwd_tc_gather(shape, x, w_col, kpad, bias, y, stats_nc, act, slope, st);
 }
 

@@ -1021,7 +1021,7 @@ int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy,
   wp.dw_col = dw_col;
   const size_t smem = 1024 + (size_t)GW_NA * 2 * BLOCK_M * 128 + (size_t)GA_STAGES * wp.g.kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * wp.g.rows_bytes + 256;
   DCV_REQUIRE(smem <= 227 * 1024, "conv2d_wgrad_gather: %zu bytes of shared memory needed", smem);
-  cudaMemsetAsync(dw_col, 0, (size_t)s->k * kpad * sizeof(float), st);
+  zero_accumulator(dw_col, (size_t)s->k * kpad * sizeof(float), st);
   CUtensorMap mdy;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)s->k, (cuuint64_t)s->q, (cuuint64_t)s->p, (cuuint64_t)s->n};
@@ -1296,7 +1296,7 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
   if (const char* e = getenv("DCV_WGRAD_SPLITS")) { const int v = atoi(e); if (v >= 1 && v <= prm.pixel_tiles) splits = v; }   // tuning aid
   prm.splits = splits;
   prm.dw = dw;
-  cudaMemsetAsync(dw, 0, (size_t)s->k * s->r * s->s * s->c * sizeof(float), st);
+  zero_accumulator(dw, (size_t)s->k * s->r * s->s * s->c * sizeof(float), st);
 
   CUtensorMap mdy, mx;
   {

@@ -243,7 +243,7 @@ static int skinny_bwd(const void* x, const float* w, const float* y, const float
   linear_skinny_dx_kernel<NB, TX><<<(m + 3) / 4, 128, 0, st>>>(w, y, dy, (TX*)dx, dpre, m, n, k, act, slope);
   DCV_LAUNCH_CHECK("linear_skinny_dx_kernel");
   if (dw) {
-    cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), st);
+    zero_accumulator(dw, (size_t)n * k * sizeof(float), st);
     const int rows = 32;
     linear_skinny_dw_kernel<NB, TX><<<dim3((k + 255) / 256, (m + rows - 1) / rows), 256, 0, st>>>((const TX*)x, dpre, dw, db, m, n, k, rows);
     DCV_LAUNCH_CHECK("linear_skinny_dw_kernel");
@@ -276,7 +276,7 @@ int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy,
   using namespace dcv;
   DCV_REQUIRE(x && w && y && dy && dpre_ws && m > 0 && n > 0 && k > 0, "linear_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
-  if (db) cudaMemsetAsync(db, 0, (size_t)n * sizeof(float), st);
+  zero_accumulator(db, (size_t)n * sizeof(float), st);
   if (n <= 32 && y_dtype == DCV_F32) {
     DCV_DISPATCH_DTYPE(x_dtype, TX, {
       if (n <= 8) return skinny_bwd<8, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);

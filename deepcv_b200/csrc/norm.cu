@@ -615,7 +615,7 @@ int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dty
   DCV_REQUIRE(y && stats_nc, "norm_stats: null pointer");
   if (check_nc("norm_stats", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(stats_nc, 0, (size_t)n * c * 2 * sizeof(float), st);
+  zero_accumulator(stats_nc, (size_t)n * c * 2 * sizeof(float), st);
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
@@ -680,7 +680,7 @@ int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int h
   DCV_REQUIRE(dz && y && s_nc, "norm_bwd_reduce: null pointer");
   if (check_nc("norm_bwd_reduce", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(s_nc, 0, (size_t)n * c * kBwdSums * sizeof(float), st);
+  zero_accumulator(s_nc, (size_t)n * c * kBwdSums * sizeof(float), st);
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
@@ -709,7 +709,7 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
   DCV_REQUIRE(dz && y && dy, "act_norm_bwd_apply: null pointer");
   if (check_nc("act_norm_bwd_apply", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  if (dbias_c) cudaMemsetAsync(dbias_c, 0, (size_t)c * sizeof(float), st);
+  zero_accumulator(dbias_c, (size_t)c * sizeof(float), st);
   dim3 grid; int block;
 #define DCV_BWD_APPLY(ACT_)                                                                                                                                   \
   DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                              \

@@ -15,6 +15,7 @@ CIFAR-10 network is launch-latency-bound, not bandwidth-bound (SURVEY.md section
 import enum
 import logging
 import multiprocessing
+import os
 from collections import OrderedDict, defaultdict
 from pathlib import Path
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Type, Union
@@ -273,7 +274,7 @@ class GraphedTrainStep:
     loss tensor (device scalar, no sync). Requires an optimizer whose `step` is capture-safe (`FlatAdamW`). """
 
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, optimizer: FlatAdamW, example_x: torch.Tensor, example_y: torch.Tensor, warmup_iters: int = 3,
-                 preprocess: Optional[torch.nn.Module] = None):
+                 preprocess: Optional[torch.nn.Module] = None, use_accumulator_arena: bool = True):
         if not example_x.is_cuda:
             raise RuntimeError('deepcv_b200: GraphedTrainStep needs CUDA tensors')
         self.model, self.loss_fn, self.optimizer, self.preprocess = model, loss_fn, optimizer, preprocess
@@ -292,13 +293,27 @@ class GraphedTrainStep:
         optimizer.set_lr_device()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        # One zeroed arena per step for all atomically-filled accumulators + ONE memset of the flat gradient buffer, instead of a memset node in front of
+        # every kernel that accumulates (ops.AccumulatorArena). The last warm-up step runs in counting mode to size the arena.
+        self.use_arena = use_accumulator_arena and os.environ.get('DCV_NO_ARENA') is None
         with torch.cuda.stream(side):
-            for _ in range(warmup_iters):
+            for i in range(warmup_iters):
+                if self.use_arena and i == warmup_iters - 1:
+                    ops.ARENA.measure()
                 self._eager_step()
+            if self.use_arena:
+                ops.ARENA.end_measure(example_x.device)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager_step()
+            if self.use_arena:
+                flat = getattr(optimizer, '_flat', None)
+                ops.ARENA.begin_step(extra_zero=[flat.flat_grads] if flat is not None else [])
+            try:
+                self.static_loss = self._eager_step()
+            finally:
+                if self.use_arena:
+                    ops.ARENA.end_step()
 
     def _eager_step(self) -> torch.Tensor:
         x = self.static_x

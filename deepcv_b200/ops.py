@@ -151,6 +151,63 @@ class NormConfig:
         return self.use_bn or self.use_gn
 
 
+class AccumulatorArena:
+    """ One zeroed buffer per training step for every accumulator the kernels fill with atomics (per-(n,c) statistics, backward sums, bias / weight
+    gradients that are not written straight into the flat gradient buffer): `begin_step` zeroes it (and any extra tensors, e.g. the flat gradient
+    buffer) with ONE memset each and tells the library not to zero accumulators itself (`dcv_set_accumulators_prezeroed`) — a CIFAR step otherwise
+    carries ~22 memset nodes of 2-3 us. Used by `GraphedTrainStep` around the captured step; outside `begin_step` .. `end_step` nothing changes.
+    `measure()` .. `end_measure()` runs a step in counting mode to size the buffer. An allocation that does not fit raises (never a silent fallback). """
+
+    def __init__(self):
+        self.buf, self.off, self.active, self.counting, self.need = None, 0, False, False, 0
+
+    def measure(self):
+        self.counting, self.need = True, 0
+
+    def end_measure(self, device) -> int:
+        self.counting = False
+        if self.buf is None or self.buf.numel() < self.need or self.buf.device != device:
+            self.buf = torch.empty((max(self.need, 256),), dtype=torch.uint8, device=device)
+        return self.need
+
+    def begin_step(self, extra_zero=()):
+        if self.buf is None:
+            raise RuntimeError('deepcv_b200: AccumulatorArena.begin_step before measure() / end_measure()')
+        st = _stream()
+        check(lib.dcv_fill_zero(_ptr(self.buf), self.buf.numel(), st), 'fill_zero(arena)')
+        for t in extra_zero:
+            check(lib.dcv_fill_zero(_ptr(t), t.numel() * t.element_size(), st), 'fill_zero(gradients)')
+        self.off, self.active = 0, True
+        lib.dcv_set_accumulators_prezeroed(1)
+
+    def end_step(self):
+        self.active = False
+        lib.dcv_set_accumulators_prezeroed(0)
+
+    def alloc(self, shape, device) -> torch.Tensor:
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        nbytes = (numel * 4 + 255) // 256 * 256
+        if self.active:
+            if self.off + nbytes > self.buf.numel():
+                raise RuntimeError(f'deepcv_b200: accumulator arena exhausted ({self.off} + {nbytes} > {self.buf.numel()} bytes): the step changed shape since it was measured')
+            out = self.buf[self.off:self.off + numel * 4].view(torch.float32).view(*shape)
+            self.off += nbytes
+            return out
+        if self.counting:
+            self.need += nbytes
+        return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+
+
+ARENA = AccumulatorArena()
+
+
+def _acc_empty(shape, device) -> torch.Tensor:
+    """ fp32 accumulator buffer: from the step's zeroed arena when one is active, else plain (the filling entry point zeroes it). """
+    return ARENA.alloc(shape, device)
+
+
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
 
 
@@ -198,7 +255,7 @@ class _ConvBlock(torch.autograd.Function):
         dt = _dt(x)
         w_op = _weight_operand(weight, x.dtype)
         y = empty_nhwc(n, k, p, q, x.dtype, dev)
-        stats = torch.empty((n, k, 2), dtype=torch.float32, device=dev) if cfg.any else None
+        stats = _acc_empty((n, k, 2), dev) if cfg.any else None
         # Convolutions the implicit-GEMM tensor-core kernel cannot address directly (few input channels / strides: the 7x7 stride-2 stem) go
         # through an explicit im2col: conv(x, w) == 1x1 conv of col[n][p][q][kpad] with the weights zero-padded to [K][kpad].
         rsc = shape.r * shape.s * shape.c
@@ -257,7 +314,7 @@ class _ConvBlock(torch.autograd.Function):
         targets = grad_out or {}
         pqr = d_bn_w = d_bn_b = d_gn_w = d_gn_b = None
         if cfg.any:
-            s_nc = torch.empty((n, k, 2), **f32)
+            s_nc = _acc_empty((n, k, 2), dev)
             check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, st), 'norm_bwd_reduce')
             pqr = torch.empty((n, k, 3), **f32)
             if cfg.use_bn and bn_w is not None:
@@ -278,21 +335,21 @@ class _ConvBlock(torch.autograd.Function):
             dy = empty_nhwc(n, k, p, q, y.dtype, dev)
             if has_bias:
                 dbias = targets.get('bias', None)
-                dbias = torch.empty((k,), **f32) if dbias is None else dbias
+                dbias = _acc_empty((k,), dev) if dbias is None else dbias
             check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, st), 'act_norm_bwd_apply')
         dw = None
         if ctx.needs_input_grad[1]:
             dw = targets.get('weight', None)
             if dw is None:
-                dw = torch.empty((k, shape.r, shape.s, shape.c), **f32).permute(0, 3, 1, 2)
+                dw = _acc_empty((k, shape.r, shape.s, shape.c), dev).permute(0, 3, 1, 2)
             if gathered:                 # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
                 sc = shape.s * shape.c
                 kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
-                dw_col = torch.empty((k, kpad_g), **f32)
+                dw_col = _acc_empty((k, kpad_g), dev)
                 check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), kpad_g, st), 'conv2d_wgrad_gather')
                 check(lib.dcv_gather_unpack_wgrad(_ptr(dw_col), _ptr(dw), k, shape.r, sc, kpad_g, st), 'gather_unpack_wgrad')
             elif gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
-                dw_col = torch.empty((k, gemm_shape.c), **f32)
+                dw_col = _acc_empty((k, gemm_shape.c), dev)
                 check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, st), 'conv2d_wgrad(im2col)')
                 check(lib.dcv_copy_channels_out(_ptr(dw_col), _ptr(dw), k, gemm_shape.c, 0, shape.r * shape.s * shape.c, DCV_F32, st), 'copy_channels_out(dw)')
             else:
@@ -571,11 +628,11 @@ class _Linear(torch.autograd.Function):
         dx = torch.empty((m, k), dtype=x.dtype, device=x.device) if ctx.needs_input_grad[0] else None
         dw = targets.get('weight', None) if ctx.needs_input_grad[1] else None
         if dw is None and ctx.needs_input_grad[1]:
-            dw = torch.empty((n, k), **f32)
+            dw = _acc_empty((n, k), x.device)
         db = None
         if has_bias:
             db = targets.get('bias', None)
-            db = torch.empty((n,), **f32) if db is None else db
+            db = _acc_empty((n,), x.device) if db is None else db
         dpre = torch.empty((m, n), **f32)
         check(lib.dcv_linear_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dpre), m, n, k, act, slope, _dt(x), DCV_F32, _stream()), 'linear_bwd')
         return dx, (None if 'weight' in targets else dw), (None if ('bias' in targets or not has_bias) else db), None, None, None

@@ -43,6 +43,11 @@ int dcv_abi_version(void);
 const char* dcv_last_error(void);
 /* 0 iff the current CUDA device exists and is compute capability 10.x (B200). */
 int dcv_device_check(void);
+/* Accumulator outputs (statistics, sums and gradients that the kernels fill with atomics: stats_nc, s_nc, dbias_c, dw, dw_col, db) are zeroed by the
+ * entry point that fills them unless the caller has declared, with on != 0, that it zeroes all of them itself (one memset per step instead of one per
+ * kernel; see deepcv_b200/ops.py AccumulatorArena). Process-wide (the training loop launches from two threads: forward and autograd's). Returns the
+ * previous setting. */
+int dcv_set_accumulators_prezeroed(int on);
 /* Number of kernel launches issued through this library since load (for bench.py's `gpu_launches`). */
 uint64_t dcv_launch_count(void);
 
