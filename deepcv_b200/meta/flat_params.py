@@ -46,7 +46,7 @@ class FlatParameters:
         total = 0
         for p in params:
             self.offsets.append(total)
-            total += (p.numel() + 3) // 4 * 4  # 16-byte aligned slices
+            total += (p.numel() + 7) // 8 * 8  # 32-byte aligned fp32 slices = 16-byte aligned slices of a bf16 shadow of the buffer (TMA needs 16)
         self.numel = total
         self.flat_params = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_grads = torch.zeros(total, dtype=torch.float32, device=device)

@@ -296,6 +296,19 @@ class GraphedTrainStep:
         # One zeroed arena per step for all atomically-filled accumulators + ONE memset of the flat gradient buffer, instead of a memset node in front of
         # every kernel that accumulates (ops.AccumulatorArena). The last warm-up step runs in counting mode to size the arena.
         self.use_arena = use_accumulator_arena and os.environ.get('DCV_NO_ARENA') is None
+        # one bf16 cast of the flat parameter buffer per step instead of one per convolution (ops.set_param_shadows); bf16 steps only
+        flat_p = getattr(optimizer, '_flat', None)
+        op_dtype = getattr(preprocess, 'dtype', None) if preprocess is not None else (example_x.dtype if example_x.is_floating_point() else None)
+        self._shadow = None
+        if flat_p is not None and op_dtype == torch.bfloat16 and os.environ.get('DCV_NO_SHADOW') is None:
+            self._shadow = torch.empty(flat_p.flat_params.numel(), dtype=torch.bfloat16, device=example_x.device)
+            ops.set_param_shadows([(flat_p.flat_params, self._shadow)])
+        try:
+            self._capture(side, warmup_iters, example_x, optimizer)
+        finally:
+            ops.set_param_shadows([])   # eager forwards outside the captured step cast per layer: they must never see one-step-old shadows
+
+    def _capture(self, side, warmup_iters, example_x, optimizer):
         with torch.cuda.stream(side):
             for i in range(warmup_iters):
                 if self.use_arena and i == warmup_iters - 1:
@@ -316,6 +329,8 @@ class GraphedTrainStep:
                     ops.ARENA.end_step()
 
     def _eager_step(self) -> torch.Tensor:
+        if self._shadow is not None:
+            ops.refresh_param_shadows()
         x = self.static_x
         if self.preprocess is not None:
             x = self.preprocess(x, flip=self.static_flip, crop_yx=self.static_crop)

@@ -223,12 +223,42 @@ def _conv_shape(x: torch.Tensor, weight: torch.Tensor, stride, padding, dilation
     return ConvShape(n, h, w, c, k, r, s, stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], p, q)
 
 
+# Low-precision shadows of flat fp32 parameter buffers (meta/flat_params.py): ONE cast kernel per step instead of one per convolution. Only the captured
+# training step registers one (GraphedTrainStep refreshes it at the top of the step and unregisters after capture), so a forward that runs outside that
+# step can never see weights that are one optimizer update old.
+_PARAM_SHADOWS: List[Tuple[torch.Tensor, torch.Tensor]] = []
+
+
+def set_param_shadows(pairs) -> None:
+    """ pairs: [(flat fp32 parameter buffer, same-length buffer of the operand dtype)]; [] unregisters. """
+    _PARAM_SHADOWS[:] = list(pairs)
+
+
+def refresh_param_shadows() -> None:
+    for src, dst in _PARAM_SHADOWS:
+        check(lib.dcv_cast(_ptr(src), _dt(src), _ptr(dst), _dt(dst), src.numel(), _stream()), 'cast(flat parameters)')
+
+
+def _shadow_view(weight: torch.Tensor, dtype: torch.dtype) -> Optional[torch.Tensor]:
+    for src, dst in _PARAM_SHADOWS:
+        if dst.dtype != dtype or weight.dtype != src.dtype or weight.device != src.device:
+            continue
+        off = weight.data_ptr() - src.data_ptr()
+        if 0 <= off and off + weight.numel() * 4 <= src.numel() * 4 and off % 4 == 0:
+            k, c, r, s_ = weight.shape
+            return dst[off // 4: off // 4 + weight.numel()].view(k, r, s_, c).permute(0, 3, 1, 2)
+    return None
+
+
 def _weight_operand(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """ fp32 OIHW parameter -> [K][R][S][C] tensor of the activation dtype (zero-copy when it already is one). """
     k, c, r, s = weight.shape
     if weight.permute(0, 2, 3, 1).is_contiguous():
         if weight.dtype == dtype:
             return weight
+        shadow = _shadow_view(weight, dtype) if _PARAM_SHADOWS else None
+        if shadow is not None:
+            return shadow
         out = torch.empty((k, r, s, c), dtype=dtype, device=weight.device).permute(0, 3, 1, 2)
         check(lib.dcv_cast(_ptr(weight), _dt(weight), _ptr(out), _dt(out), weight.numel(), _stream()), 'cast(weight)')
         return out
