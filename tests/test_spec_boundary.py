@@ -198,3 +198,33 @@ def test_piecewise_linear_and_engine():
     state = eng.run(list(range(5)), max_epochs=2)
     assert state.iteration == 10 and state.epoch == 2
     assert [round(v, 4) for _, v in seen[:6]] == [0.0, 0.25, 0.5, 0.75, 1.0, round(1 - 1 / 6, 4)]
+
+
+def test_accumulator_arena_counts_and_parameter_shadow_views():
+    """ Host logic of the two per-step consolidations of the captured training step (no kernel involved): the accumulator arena sizes itself in
+    counting mode and hands out plain tensors outside a step; a convolution weight that lives in a flat parameter buffer maps to the same element
+    range of the buffer's low-precision shadow, in the same [K][R][S][C] order. """
+    import torch
+    from deepcv_b200 import ops
+    arena = ops.AccumulatorArena()
+    t = arena.alloc((3, 5, 2), torch.device('cpu'))
+    assert t.shape == (3, 5, 2) and t.dtype == torch.float32 and arena.need == 0
+    arena.measure()
+    arena.alloc((3, 5, 2), torch.device('cpu'))
+    arena.alloc((7,), torch.device('cpu'))
+    assert arena.need == 256 + 256                       # 120 and 28 bytes, each rounded up to 256
+    assert arena.end_measure(torch.device('cpu')) == 512 and arena.buf.numel() >= 512 and not arena.counting
+    flat = torch.arange(64, dtype=torch.float32)
+    shadow = flat.to(torch.bfloat16)
+    k, c, r, s = 2, 3, 2, 2
+    w = flat[8:8 + k * c * r * s].view(k, r, s, c).permute(0, 3, 1, 2)    # logically OIHW, physically KRSC, inside the flat buffer
+    ops.set_param_shadows([(flat, shadow)])
+    try:
+        v = ops._shadow_view(w, torch.bfloat16)
+        assert v is not None and v.shape == w.shape and v.data_ptr() == shadow.data_ptr() + 8 * 2
+        assert torch.equal(v.float(), w)
+        assert ops._shadow_view(torch.zeros(k, c, r, s).permute(0, 1, 2, 3), torch.bfloat16) is None      # not in the buffer
+        assert ops._shadow_view(w, torch.float16) is None                                                  # no shadow of that dtype
+    finally:
+        ops.set_param_shadows([])
+    assert ops._shadow_view(w, torch.bfloat16) is None
