@@ -214,8 +214,12 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
             ms = _graph_time_ms(launch, reps, 20, stream)
             alg_bytes = n * h * w * (c + k) * esize + k * 25 * c * 4
             achieved = alg_bytes / (ms / 1e3) / 1e9
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at batch 512 (profiles/r01_ncu_full_summary.txt:
+            # 8.46 MB read, 0 written — dw stays in L2), only quoted for the shape it was captured on
+            traffic = 8.46e6 if (n, size, dtype_name) == (512, 32, 'bf16') else None
             return dict(bound='hbm', kernel='conv_wgrad_direct_s1_kernel (4->4 ch, 5x5, 32x32; includes the 1.6 KB memset of dw)', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
-                        frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
+                        frac=achieved / peaks['hbm_gbs'], traffic=traffic, traffic_source='ncu --set full, profiles/r01_ncu_full_summary.txt', peak_source=peaks['source'],
+                        algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
                         note='latency-bound at this size: 8.4 MB per launch is 1.3 us of HBM time; see DESIGN.md section 5')
         n, c, h, w, k = batch, 64, 56, 56, 64
         if dtype_name != 'bf16':
@@ -232,8 +236,12 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
         ms = _graph_time_ms(launch, reps, 10, stream)
         flop = 2.0 * n * h * w * k * c * 9
         achieved = flop / (ms / 1e3) / 1e12
-        return dict(bound='tensor', kernel='conv_fwd_tc_kernel<64> (64->64 ch, 3x3, 56x56, bias + LeakyReLU epilogue)', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
-                    frac=achieved / peaks['bf16_tflops'], traffic=None, peak_source=peaks['source'] + ', burst figure (kernel timed alone)', algorithmic_flop_per_launch=flop, us_per_launch=ms * 1e3)
+        # traffic: DRAM bytes of one `ncu --set full` capture of this kernel at batch 256 (profiles/r01_ncu_full_summary.txt: 102.9 MB read = the input tensor once,
+        # 50.7 MB written before the kernel ends — the rest of the 102.8 MB output is still in L2)
+        traffic = 153.6e6 if n == 256 else None
+        return dict(bound='tensor', kernel='conv_fwd_tc_halo_kernel<64> (64->64 ch, 3x3, 56x56, bias + LeakyReLU epilogue)', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
+                    frac=achieved / peaks['bf16_tflops'], traffic=traffic, traffic_unit='bytes of DRAM per launch', traffic_source='ncu --set full, profiles/r01_ncu_full_summary.txt',
+                    peak_source=peaks['source'] + ', burst figure (kernel timed alone)', algorithmic_flop_per_launch=flop, us_per_launch=ms * 1e3)
 
 
 def load_peaks():
