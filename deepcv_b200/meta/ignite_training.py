@@ -296,6 +296,7 @@ class GraphedTrainStep:
         # One zeroed arena per step for all atomically-filled accumulators + ONE memset of the flat gradient buffer, instead of a memset node in front of
         # every kernel that accumulates (ops.AccumulatorArena). The last warm-up step runs in counting mode to size the arena.
         self.use_arena = use_accumulator_arena and os.environ.get('DCV_NO_ARENA') is None
+        self.arena = ops.AccumulatorArena() if self.use_arena else None   # owned by this object: the graph replays write into its buffer
         # one bf16 cast of the flat parameter buffer per step instead of one per convolution (ops.set_param_shadows); bf16 steps only
         flat_p = getattr(optimizer, '_flat', None)
         op_dtype = getattr(preprocess, 'dtype', None) if preprocess is not None else (example_x.dtype if example_x.is_floating_point() else None)
@@ -312,21 +313,21 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for i in range(warmup_iters):
                 if self.use_arena and i == warmup_iters - 1:
-                    ops.ARENA.measure()
+                    self.arena.measure()
                 self._eager_step()
             if self.use_arena:
-                ops.ARENA.end_measure(example_x.device)
+                self.arena.end_measure(example_x.device)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         with torch.cuda.graph(self.graph):
             if self.use_arena:
                 flat = getattr(optimizer, '_flat', None)
-                ops.ARENA.begin_step(extra_zero=[flat.flat_grads] if flat is not None else [])
+                self.arena.begin_step(extra_zero=[flat.flat_grads] if flat is not None else [])
             try:
                 self.static_loss = self._eager_step()
             finally:
                 if self.use_arena:
-                    ops.ARENA.end_step()
+                    self.arena.end_step()
 
     def _eager_step(self) -> torch.Tensor:
         if self._shadow is not None:

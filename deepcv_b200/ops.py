@@ -156,16 +156,21 @@ class AccumulatorArena:
     gradients that are not written straight into the flat gradient buffer): `begin_step` zeroes it (and any extra tensors, e.g. the flat gradient
     buffer) with ONE memset each and tells the library not to zero accumulators itself (`dcv_set_accumulators_prezeroed`) — a CIFAR step otherwise
     carries ~22 memset nodes of 2-3 us. Used by `GraphedTrainStep` around the captured step; outside `begin_step` .. `end_step` nothing changes.
-    `measure()` .. `end_measure()` runs a step in counting mode to size the buffer. An allocation that does not fit raises (never a silent fallback). """
+    `measure()` .. `end_measure()` runs a step in counting mode to size the buffer. An allocation that does not fit raises (never a silent fallback).
+    One instance per captured step: the graph replays keep writing into `buf`. """
 
     def __init__(self):
         self.buf, self.off, self.active, self.counting, self.need = None, 0, False, False, 0
 
     def measure(self):
+        global _CURRENT_ARENA
         self.counting, self.need = True, 0
+        _CURRENT_ARENA = self
 
     def end_measure(self, device) -> int:
+        global _CURRENT_ARENA
         self.counting = False
+        _CURRENT_ARENA = None
         if self.buf is None or self.buf.numel() < self.need or self.buf.device != device:
             self.buf = torch.empty((max(self.need, 256),), dtype=torch.uint8, device=device)
         return self.need
@@ -177,11 +182,15 @@ class AccumulatorArena:
         check(lib.dcv_fill_zero(_ptr(self.buf), self.buf.numel(), st), 'fill_zero(arena)')
         for t in extra_zero:
             check(lib.dcv_fill_zero(_ptr(t), t.numel() * t.element_size(), st), 'fill_zero(gradients)')
+        global _CURRENT_ARENA
         self.off, self.active = 0, True
+        _CURRENT_ARENA = self
         lib.dcv_set_accumulators_prezeroed(1)
 
     def end_step(self):
+        global _CURRENT_ARENA
         self.active = False
+        _CURRENT_ARENA = None
         lib.dcv_set_accumulators_prezeroed(0)
 
     def alloc(self, shape, device) -> torch.Tensor:
@@ -200,12 +209,16 @@ class AccumulatorArena:
         return torch.empty(tuple(shape), dtype=torch.float32, device=device)
 
 
-ARENA = AccumulatorArena()
+# The arena of the step being measured / captured, if any. Each GraphedTrainStep owns its arena (the captured graph holds pointers into its buffer, so the
+# buffer must live exactly as long as the graph), hence no module-level instance.
+_CURRENT_ARENA: Optional[AccumulatorArena] = None
 
 
 def _acc_empty(shape, device) -> torch.Tensor:
     """ fp32 accumulator buffer: from the step's zeroed arena when one is active, else plain (the filling entry point zeroes it). """
-    return ARENA.alloc(shape, device)
+    if _CURRENT_ARENA is not None:
+        return _CURRENT_ARENA.alloc(shape, device)
+    return torch.empty(tuple(int(d) for d in shape), dtype=torch.float32, device=device)
 
 
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
