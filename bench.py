@@ -65,6 +65,16 @@ def workload_spec(name: str, batch):
     return dict(hp=hp, classes=classes, size=size, mean=mean, std=std, pad=pad, batch=batch or b, label=label)
 
 
+def needs_remeasure(clocks: dict) -> bool:
+    """ Timing rule: a run that saw hw_slowdown / hw_thermal_slowdown / sw_thermal_slowdown, or SM clocks stuck well below max with no reason at all, is
+    rejected and re-measured once; sw_power_cap is kept and noted. """
+    bad = {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    if bad & set(clocks.get('reasons') or []):
+        return True
+    sm, mx = clocks.get('sm_mhz'), clocks.get('sm_max_mhz')
+    return bool(sm and mx and not clocks.get('reasons') and sm < 0.7 * mx)
+
+
 class ClockSampler:
     """ nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The sampler is started early and
     `wait_ready()` blocks until it has delivered its first row, so that even a 100 ms timed region is covered; rows carry the host time at
@@ -346,10 +356,22 @@ def run_b200(args):
     # ---- device-resident throughput
     def step_resident(i):
         runner.step(pool_dev[i % pool_n], labels_dev[i % pool_n])
+    remeasured = False
     with ClockSampler(local_rank) as clocks:
         clocks.wait_ready()
         ms = timed(step_resident, args.steps, max(args.warmup, 3))
         clock_window = (window['t0'], window['t1'])
+        again = needs_remeasure(clocks.summary(*clock_window))
+        if world > 1:   # collective decision: `timed` contains barriers
+            flag = torch.tensor([int(again)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            again = bool(int(flag.item()))
+        if again:
+            # hardware / thermal slowdown, or clocks far below max with no reason given (a leftover lock): the number is rejected and taken ONCE more
+            time.sleep(2.0)
+            remeasured = True
+            ms = timed(step_resident, args.steps, max(args.warmup, 3))
+            clock_window = (window['t0'], window['t1'])
     value = world * batch * args.steps / (ms / 1e3)
 
     # ---- end to end: host (pinned) uint8 batches in, loss out, every step
@@ -388,7 +410,7 @@ def run_b200(args):
                 config=dict(workload=spec['label'], per_gpu_batch=batch, global_batch=batch * world, parallelism=f'dp{world}', step='fused u8 preprocess(normalise+flip+crop) + fwd + CE + bwd + '
                             + ('bucketed NCCL all-reduce + ' if world > 1 else '') + 'AdamW' + ('' if args.no_graph else ', one CUDA graph replay per step'),
                             l2='inputs cycle through a pool of %d distinct uint8 batches (%.0f MB > 126 MB L2)' % (pool_n, pool_n * batch_bytes / 1e6), final_loss=losses[-1] if losses else None),
-                e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=clocks.summary(*clock_window), roofline=roofline, cpu_baseline=cpu)
+                e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=dict(clocks.summary(*clock_window), remeasured=remeasured), roofline=roofline, cpu_baseline=cpu)
     print(json.dumps(line))
     shutdown()
 

@@ -228,3 +228,29 @@ def test_accumulator_arena_counts_and_parameter_shadow_views():
     finally:
         ops.set_param_shadows([])
     assert ops._shadow_view(w, torch.bfloat16) is None
+
+
+def test_bench_clock_rules():
+    """ bench.py timing rules (host logic only): which clock samples reject a measurement, and that only samples read inside the timed window count. """
+    import importlib.util
+    import sys
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location('dcv_bench', Path(__file__).resolve().parent.parent / 'bench.py')
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    assert not bench.needs_remeasure(dict(sm_mhz=1965., sm_max_mhz=1965., reasons=[]))
+    assert not bench.needs_remeasure(dict(sm_mhz=1500., sm_max_mhz=1965., reasons=['sw_power_cap']))      # kept and noted
+    assert bench.needs_remeasure(dict(sm_mhz=1965., sm_max_mhz=1965., reasons=['hw_thermal_slowdown']))
+    assert bench.needs_remeasure(dict(sm_mhz=900., sm_max_mhz=1965., reasons=[]))                          # a leftover clock lock
+    assert not bench.needs_remeasure(dict(sm_mhz=None, sm_max_mhz=None, reasons=[]))                       # no nvidia-smi
+    cs = bench.ClockSampler(0)
+    idle = ['1965', '1965', '400', 'Not Active', 'Not Active', 'Not Active', 'Not Active']
+    busy = ['1200', '1965', '900', 'Not Active', 'Not Active', 'Not Active', 'Active']
+    cs.rows = [(10.0, idle), (10.5, busy), (11.0, idle)]
+    inside = cs.summary(10.4, 10.6)
+    assert inside['samples'] == 1 and inside['sm_mhz'] == 1200. and inside['reasons'] == ['sw_power_cap']
+    assert cs.summary(20., 21.)['samples'] == 1                                                             # nothing inside: the nearest sample
