@@ -4,8 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cifar|imagenet|preprocess] [--impl reference]
 
 A step = fused uint8 preprocess (normalise / flip / crop) -> forward -> cross-entropy -> backward -> (bucketed NCCL gradient all-reduce when
-N > 1) -> AdamW, on one synthetic batch per GPU (weak scaling). Default workload = BASELINE.json configs[1]: the default CIFAR-10
-`image_classifier` DeepcvModule, bf16 activations, batch 512 per GPU. Prints ONE JSON line (rank 0):
+N > 1) -> AdamW, on one synthetic batch per GPU (weak scaling). BASELINE.json's metric names two shapes and ONE invocation measures both
+(`--workload all`, the default): the headline keys of the line are configs[1] — the default CIFAR-10 `image_classifier` DeepcvModule, bf16, batch
+512 per GPU — and `workloads.imagenet` carries configs[3] — the ResNet-style DeepcvModule at 3x224x224, bf16, batch 256 per GPU — with its own
+value / e2e / ms_per_step / clocks / tensor roofline (per-layer forward / data-gradient / weight-gradient fractions of the measured bf16 peak).
+Both are stepped through the public API: `ignite_training.make_process_function` (what `train()` wires into the `Engine`), which captures the step
+into a CUDA graph on its first call. Prints ONE JSON line (rank 0):
   value       images/s with the uint8 batches already resident in HBM (a pool of distinct batches larger than L2 is cycled)
   e2e         same metric through the public API with HOST (pinned) uint8 batches: H2D copy of images / labels / augmentation parameters and
               D2H read of the loss inside the timed region, every step
@@ -35,32 +39,33 @@ IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=None, help='timed steps (default: 1000 cifar, 50 imagenet: about half a second of device time)')
+    ap.add_argument('--steps', type=int, default=None, help='timed steps of each workload (default: 1000 cifar, 50 imagenet: about half a second of device time)')
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='cifar', choices=['cifar', 'imagenet', 'preprocess'])
+    ap.add_argument('--workload', default='all', choices=['all', 'cifar', 'imagenet', 'preprocess'])
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: 512 cifar, 256 imagenet)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the bounded CPU baseline sample')
-    args = ap.parse_args()
-    if args.steps is None:
-        args.steps = 50 if args.workload == 'imagenet' else 1000
-    return args
+    ap.add_argument('--no-layer-table', action='store_true', help='skip the per-layer convolution table of the imagenet workload')
+    return ap.parse_args()
+
+
+def steps_for(args, workload: str) -> int:
+    return args.steps if args.steps is not None else (50 if workload == 'imagenet' else 1000)
 
 
 def workload_spec(name: str, batch):
-    from deepcv_b200.yaml_config import find_model_spec, load_parameters
+    from deepcv_b200.yaml_config import benchmark_model_spec
     if name == 'cifar':
-        hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'parameters.yml'), 'image_classifier'))
+        hp = benchmark_model_spec(ROOT / 'conf' / 'base' / 'parameters.yml', 'image_classifier')
         classes, size, mean, std, pad, b = 10, 32, CIFAR_MEAN, CIFAR_STD, 4, 512
         label = 'deepcv.classification.image default image_classifier DeepcvModule (conf/base/parameters.yml), synthetic CIFAR-10-shaped uint8 3x32x32'
     else:
-        hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'resnet_style.yml'), 'resnet_style_classifier'))
+        hp = benchmark_model_spec(ROOT / 'conf' / 'base' / 'resnet_style.yml', 'resnet_style_classifier')
         classes, size, mean, std, pad, b = 1000, 224, IMAGENET_MEAN, IMAGENET_STD, 16, 256
         label = 'ResNet-style DeepcvModule with residual/dense links (conf/base/resnet_style.yml), synthetic ImageNet-shaped uint8 3x224x224'
-    hp['architecture'] = copy.deepcopy(hp['architecture'])
     hp['architecture'][-1]['fully_connected']['out_features'] = classes
     return dict(hp=hp, classes=classes, size=size, mean=mean, std=std, pad=pad, batch=batch or b, label=label)
 
@@ -152,22 +157,32 @@ def cpu_reference_run(spec, steps: int, warmup: int, seconds: float, batch: int)
         med = statistics.median(times)
         if best is None or med < best['ms'] / 1e3:
             best = dict(ms=med * 1e3, threads=k, steps=len(times))
+    del model, opt
     return dict(value=batch / (best['ms'] / 1e3), unit=UNIT, cores=best['threads'], kind='port', ms_per_step=best['ms'],
                 sample=f"{best['steps']} timed steps of batch {batch} (fp32, preprocess + forward + backward + AdamW), best of thread counts {candidates} on {cores} host cores; median step")
 
 
 def run_reference(args):
+    """ The reference arm: the reference's CPU implementation of the path (oracle port: the reference package cannot be imported here, SURVEY.md section
+    8.c) on this box's host cores, same metric / config, each step a bounded sample. Rank 0 alone works. """
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    spec = workload_spec('cifar' if args.workload == 'preprocess' else args.workload, args.batch)
-    batch = min(spec['batch'], 512 if args.workload != 'imagenet' else 16)
-    base = cpu_reference_run(spec, max(args.steps, 3), max(args.warmup, 1), seconds=60.0, batch=batch)
-    line = dict(metric=METRIC, value=base['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=base['ms_per_step'], higher_is_better=True,
+    names = ['cifar', 'imagenet'] if args.workload in ('all', 'preprocess') else [args.workload]
+    results = {}
+    for name in names:
+        spec = workload_spec(name, args.batch)
+        batch = min(spec['batch'], 512 if name == 'cifar' else 16)
+        steps = max(3, min(steps_for(args, name), 30 if name == 'cifar' else 4))
+        base = cpu_reference_run(spec, steps, max(min(args.warmup, 3 if name == 'cifar' else 1), 1), seconds=60.0 if name == 'cifar' else 45.0, batch=batch)
+        results[name] = dict(value=base['value'], unit=UNIT, ms_per_step=base['ms_per_step'], per_step_batch=batch, config=dict(workload=spec['label']),
+                             cpu_baseline=dict(value=base['value'], unit=UNIT, cores=base['cores'], kind=base['kind'], sample=base['sample']))
+    head = results[names[0]]
+    line = dict(metric=METRIC, value=head['value'], unit=UNIT, n_gpus=args.gpus, steps=steps_for(args, names[0]), warmup=args.warmup, ms_per_step=head['ms_per_step'], higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=spec['label'], per_step_batch=batch, note='reference CPU path = oracle restatement (the reference package cannot be imported here: SURVEY.md section 8.c)'),
-                cpu_baseline=dict(value=base['value'], unit=UNIT, cores=base['cores'], kind=base['kind'], sample=base['sample']),
-                e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                config=dict(workload=head['config']['workload'], per_step_batch=head['per_step_batch'],
+                            note='reference CPU path = oracle restatement (the reference package cannot be imported here: SURVEY.md section 8.c)'),
+                cpu_baseline=head['cpu_baseline'], e2e=dict(value=head['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0, workloads=results)
     print(json.dumps(line))
 
 
@@ -195,6 +210,50 @@ def _graph_time_ms(launch, reps, iters, stream):
     return start.elapsed_time(end) / (iters * reps)
 
 
+C4_LAYERS = [  # name, c, h, k, ksize, launches per step (forward, data gradient, weight gradient) in conf/base/resnet_style.yml
+    ('s1 64->64 @56', 64, 56, 64, 3, (4, 4, 4)), ('s2in 64->128 @28', 64, 28, 128, 3, (1, 1, 1)), ('s2 128->128 @28', 128, 28, 128, 3, (4, 4, 4)),
+    ('s3in 128->256 @14', 128, 14, 256, 3, (1, 1, 1)), ('s3 256->256 @14', 256, 14, 256, 3, (4, 4, 4)), ('s4in 256->512 @7', 256, 7, 512, 3, (1, 1, 1)),
+    ('s4 512->512 @7', 512, 7, 512, 3, (2, 2, 2)),
+]
+
+
+def conv_layer_table(batch, dev, peaks):
+    """ Forward / data-gradient / weight-gradient convolution of every ResNet-style layer shape through the C ABI, timed live (graph replay, buffers cycled
+    beyond L2): TFLOP/s on 2*N*P*Q*K*C*R*S FLOP and the fraction of the measured dense bf16 peak = the "conv tensor-pipe %" of BASELINE.json's metric. """
+    import ctypes
+    import torch
+    from deepcv_b200._lib import ACT_LEAKY_RELU, ALGO_AUTO, DCV_BF16, ConvShape, check, lib
+    stream = torch.cuda.Stream()
+    st = ctypes.c_void_p(stream.cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    rows, tot_flop, tot_ms = [], 0., 0.
+    with torch.cuda.stream(stream):
+        for name, c, h, k, ks, counts in C4_LAYERS:
+            n, pad = batch, ks // 2
+            shape = ConvShape(n, h, h, c, k, ks, ks, 1, 1, pad, pad, 1, 1, h, h)
+            reps = max(2, int(300e6 // (n * h * h * (c + k) * 2)) + 1)
+            xs = [torch.randn(n, h, h, c, device=dev).bfloat16() for _ in range(reps)]
+            ys = [torch.randn(n, h, h, k, device=dev).bfloat16() for _ in range(reps)]
+            w = (torch.randn(k, ks, ks, c, device=dev) * 0.05).bfloat16()
+            wt = torch.empty(c, ks, ks, k, device=dev, dtype=torch.bfloat16)
+            w32 = w.float()
+            check(lib.dcv_pack_conv_weight(P(w32), P(wt), DCV_BF16, k, ks, ks, c, 1, st), 'pack')
+            bias, dw = torch.zeros(k, device=dev), torch.empty(k, ks, ks, c, device=dev)
+            flop = 2.0 * n * h * h * k * c * ks * ks
+            row = dict(layer=name)
+            ops_ = dict(fwd=lambda i: check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(w), P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, DCV_BF16, ALGO_AUTO, 0, st), 'fwd'),
+                        dgrad=lambda i: check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), P(ys[i]), P(w), P(wt), P(xs[i]), DCV_BF16, ALGO_AUTO, st), 'dgrad'),
+                        wgrad=lambda i: check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xs[i]), P(ys[i]), P(dw), None, DCV_BF16, ALGO_AUTO, 0, st), 'wgrad'))
+            for j, (op, fn) in enumerate(ops_.items()):
+                ms = _graph_time_ms(fn, reps, 3, stream)
+                row[op] = dict(us=round(ms * 1e3, 1), tflops=round(flop / ms / 1e9, 1), frac=round(flop / ms / 1e9 / peaks['bf16_tflops'], 3))
+                tot_flop += flop * counts[j]; tot_ms += ms * counts[j]
+            rows.append(row)
+            del xs, ys
+    return dict(per_layer=rows, weighted_conv_tflops=tot_flop / tot_ms / 1e9, weighted_conv_frac=tot_flop / tot_ms / 1e9 / peaks['bf16_tflops'],
+                note='3x3 layers of the step weighted by their launch counts; the 7x7/2 stem (gather kernels) is not in this table')
+
+
 def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
     """ Roofline of the dominant kernel of the step, called through the C ABI with preallocated buffers, timed live with CUDA events on the stream it is
     launched on (graph replay, buffers cycled beyond L2).
@@ -220,16 +279,13 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
             shape = ConvShape(n, h, w, c, k, 5, 5, 1, 1, 2, 2, 1, 1, h, w)
 
             def launch(i):
-                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xs[i]), P(dys[i]), P(dw), None, dt, ALGO_DIRECT, st), 'conv2d_wgrad')
+                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xs[i]), P(dys[i]), P(dw), None, dt, ALGO_DIRECT, 0, st), 'conv2d_wgrad')
             ms = _graph_time_ms(launch, reps, 20, stream)
             alg_bytes = n * h * w * (c + k) * esize + k * 25 * c * 4
             achieved = alg_bytes / (ms / 1e3) / 1e9
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at batch 512 (profiles/r01_ncu_full_summary.txt:
-            # 8.46 MB read, 0 written — dw stays in L2), only quoted for the shape it was captured on
-            traffic = 8.46e6 if (n, size, dtype_name) == (512, 32, 'bf16') else None
-            return dict(bound='hbm', kernel='conv_wgrad_direct_s1_kernel (4->4 ch, 5x5, 32x32; includes the 1.6 KB memset of dw)', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
-                        frac=achieved / peaks['hbm_gbs'], traffic=traffic, traffic_source='ncu --set full, profiles/r01_ncu_full_summary.txt', peak_source=peaks['source'],
-                        algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
+            return dict(bound='hbm', kernel='conv_wgrad_direct_s1_kernel<5,32,16,4,4> (4->4 ch, 5x5, 32x32; includes the 1.6 KB memset of dw)', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
+                        frac=achieved / peaks['hbm_gbs'], traffic=None, traffic_note='no ncu --set full capture of this instantiation is committed (the round-1 figure was of <3,16,16,16,16>)',
+                        peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
                         note='latency-bound at this size: 8.4 MB per launch is 1.3 us of HBM time; see DESIGN.md section 5')
         n, c, h, w, k = batch, 64, 56, 56, 64
         if dtype_name != 'bf16':
@@ -242,7 +298,7 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
         shape = ConvShape(n, h, w, c, k, 3, 3, 1, 1, 1, 1, 1, 1, h, w)
 
         def launch(i):
-            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(wt), P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, dt, ALGO_AUTO, st), 'conv2d_fwd')
+            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(wt), P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, dt, ALGO_AUTO, 0, st), 'conv2d_fwd')
         ms = _graph_time_ms(launch, reps, 10, stream)
         flop = 2.0 * n * h * w * k * c * 9
         achieved = flop / (ms / 1e3) / 1e12
@@ -262,27 +318,26 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
-def run_b200(args):
+TRAIN_FLOP_PER_IMAGE = dict(cifar=10.64e6, imagenet=11.23e9)   # convolution FLOP of one training step per image
+HBM_FLOOR_BYTES_PER_IMAGE = dict(cifar=0.38e6)                # ideal-fusion HBM traffic of the default net per image
+
+
+def measure_workload(name, args, dev, world, rank, local_rank, peaks):
+    """ One workload end to end: builds the model behind the public API, captures the step, times `value` (device-resident pool), `e2e` (pinned host
+    batches through Engine.run) and the roofline of its dominant kernel. Collective (barriers): every rank calls it. """
+    import gc
+    from collections import OrderedDict
     import torch
     import torch.distributed as dist
     from deepcv_b200 import ops
-    from deepcv_b200._lib import check, lib
     from deepcv_b200.meta.base_module import DeepcvModule
     from deepcv_b200.meta.data.preprocess import FusedPreprocess
     from deepcv_b200.meta.flat_params import FlatAdamW, flatten_parameters
-    from deepcv_b200.meta.ignite_training import CrossEntropyLoss, DataParallelModel, GraphedTrainStep
+    from deepcv_b200.meta.ignite_training import CrossEntropyLoss, DataParallelModel, Engine, make_process_function
 
-    rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    check(lib.dcv_device_check(), 'device_check')
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    peaks = load_peaks()
-    spec = workload_spec(args.workload, args.batch)
+    spec = workload_spec(name, args.batch)
     batch, size, classes = spec['batch'], spec['size'], spec['classes']
+    steps, warmup = steps_for(args, name), max(args.warmup, 3)
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
 
     torch.manual_seed(563454)   # same initial weights on every rank (DDP broadcasts rank 0's; same seed + broadcast in DataParallelModel)
@@ -291,7 +346,9 @@ def run_b200(args):
     net = DataParallelModel(model) if world > 1 else model
     flat = flatten_parameters(model)
     opt = FlatAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1. / world).attach(flat)
-    loss_fn = CrossEntropyLoss()
+    if world > 1:
+        net.reducer.average_in_finish = False   # 1 / world is applied inside the AdamW kernel
+    losses = OrderedDict(main_loss=CrossEntropyLoss())
 
     # synthetic data: a pool of distinct uint8 batches larger than L2 (126 MB), cycled
     g = torch.Generator().manual_seed(563454 + rank)
@@ -301,30 +358,21 @@ def run_b200(args):
     labels = [torch.randint(0, classes, (batch,), generator=g) for _ in range(pool_n)]
     pool_dev = [p.to(dev) for p in pool]
     labels_dev = [l.to(dev) for l in labels]
-    pool_host = [p.pin_memory() for p in pool[:8]]
-    labels_host = [l.pin_memory() for l in labels[:8]]
+    n_host = min(8, pool_n)
+    pool_host = [p.pin_memory() for p in pool[:n_host]]
+    labels_host = [l.pin_memory() for l in labels[:n_host]]
+    del pool, labels
 
+    # the public training step: what train() hands to the Engine. Its first call captures the CUDA graph (and rewinds the model / optimizer state).
     launches0 = ops.launch_count()
+    step_fn = make_process_function({}, dev, net, losses, opt, preprocess=pre, cuda_graph=False if args.no_graph else None)
+    trainer = Engine(step_fn)
+    trainer.run([(pool_host[0], labels_host[0])], max_epochs=1)
     if args.no_graph:
-        class Eager:
-            static_loss = None
-
-            def step(self, x, y):
-                net.train()
-                flip, crop = pre.draw(x.shape[0])
-                xx = pre(x.to(dev, non_blocking=True), flip=flip.to(dev, non_blocking=True), crop_yx=crop.to(dev, non_blocking=True))
-                loss = loss_fn(net(xx), y.to(dev, non_blocking=True))
-                opt.zero_grad()
-                loss.backward()
-                if world > 1:
-                    net.finish_gradient_reduction()
-                opt.step()
-                return loss
-        runner = Eager()
-        runner.step(pool_dev[0], labels_dev[0])
         launches_per_step = ops.launch_count() - launches0
+        runner = None
     else:
-        runner = GraphedTrainStep(net, loss_fn, opt, pool_dev[0], labels_dev[0], warmup_iters=3, preprocess=pre)
+        runner = next(iter(step_fn.runners.values()))
         launches_per_step = (ops.launch_count() - launches0) // 4   # 3 warm-up steps + 1 captured step
 
     def barrier():
@@ -334,15 +382,13 @@ def run_b200(args):
 
     window = {}
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
+    def timed(fn, n_warm):
+        fn(n_warm, warm=True)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         window['t0'] = time.time()
         start.record()
-        for i in range(steps):
-            fn(warmup + i)
+        fn(None, warm=False)
         end.record()
         barrier()
         window['t1'] = time.time()
@@ -353,13 +399,17 @@ def run_b200(args):
             ms = float(t)
         return ms
 
-    # ---- device-resident throughput
-    def step_resident(i):
-        runner.step(pool_dev[i % pool_n], labels_dev[i % pool_n])
+    # ---- device-resident throughput: the captured step replayed over batches already in HBM
+    def resident(n_warm, warm):
+        for i in range(n_warm if warm else steps):
+            if runner is not None:
+                runner.step(pool_dev[i % pool_n], labels_dev[i % pool_n])
+            else:
+                step_fn(trainer, (pool_dev[i % pool_n], labels_dev[i % pool_n]))
     remeasured = False
     with ClockSampler(local_rank) as clocks:
         clocks.wait_ready()
-        ms = timed(step_resident, args.steps, max(args.warmup, 3))
+        ms = timed(resident, warmup)
         clock_window = (window['t0'], window['t1'])
         again = needs_remeasure(clocks.summary(*clock_window))
         if world > 1:   # collective decision: `timed` contains barriers
@@ -370,29 +420,81 @@ def run_b200(args):
             # hardware / thermal slowdown, or clocks far below max with no reason given (a leftover lock): the number is rejected and taken ONCE more
             time.sleep(2.0)
             remeasured = True
-            ms = timed(step_resident, args.steps, max(args.warmup, 3))
+            ms = timed(resident, warmup)
             clock_window = (window['t0'], window['t1'])
-    value = world * batch * args.steps / (ms / 1e3)
+    value = world * batch * steps / (ms / 1e3)
 
-    # ---- end to end: host (pinned) uint8 batches in, loss out, every step
-    losses = []
+    # ---- end to end through the public API: Engine.run over a loader of pinned host uint8 batches; per step H2D of images / labels / augmentation
+    # parameters (+ learning rate when it changes), the graph replay, and the D2H read of the loss (`process_function` returns floats)
+    e2e_steps = max(10, steps // 2)
+    losses_seen = []
+    trainer.add_event_handler(__import__('deepcv_b200.meta.ignite_training', fromlist=['Events']).Events.ITERATION_COMPLETED, lambda e: losses_seen.append(e.state.output['main_loss']))
 
-    def step_e2e(i):
-        loss = runner.step(pool_host[i % len(pool_host)], labels_host[i % len(labels_host)])
-        losses.append(loss.item())                         # D2H read of the step's result (and the only host sync)
-    e2e_steps = max(10, args.steps // 2)
-    ms_e2e = timed(step_e2e, e2e_steps, 3)
+    def e2e_run(n_warm, warm):
+        n = n_warm if warm else e2e_steps
+        trainer.run([(pool_host[i % n_host], labels_host[i % n_host]) for i in range(n)], max_epochs=trainer.state.epoch + 1)
+    ms_e2e = timed(e2e_run, 3)
     e2e_value = world * batch * e2e_steps / (ms_e2e / 1e3)
     h2d = batch_bytes + batch * 8 + batch * (1 + 8) + 4    # images + int64 labels + flip (u8) / crop (2 x i32) + learning rate
-    e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / e2e_steps)
+    e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * len(losses), ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps,
+               api='ignite_training.Engine(make_process_function(...)).run(loader of pinned uint8 batches)')
+
+    result = dict(value=value, unit=UNIT, steps=steps, warmup=warmup, ms_per_step=ms / steps, e2e=e2e, gpu_launches=int(launches_per_step * steps), launches_per_step=int(launches_per_step),
+                  clocks=dict(clocks.summary(*clock_window), remeasured=remeasured),
+                  config=dict(workload=spec['label'], per_gpu_batch=batch, global_batch=batch * world, parallelism=f'dp{world}',
+                              step='fused u8 preprocess(normalise+flip+crop) + fwd + CE + bwd + ' + ('bucketed NCCL all-reduce + ' if world > 1 else '') + 'AdamW'
+                                   + ('' if args.no_graph else ', one CUDA graph replay per step'),
+                              l2='inputs cycle through a pool of %d distinct uint8 batches (%.0f MB > 126 MB L2)' % (pool_n, pool_n * batch_bytes / 1e6),
+                              final_loss=losses_seen[-1] if losses_seen else None))
+    flop = TRAIN_FLOP_PER_IMAGE[name] * batch
+    result['step_conv_tflops'] = flop / (ms / steps) / 1e9
+    if name == 'imagenet':
+        result['step_frac_of_sustained_bf16_peak'] = result['step_conv_tflops'] / peaks['bf16_tflops_sustained']
+    else:
+        result['step_frac_of_hbm_floor'] = (HBM_FLOOR_BYTES_PER_IMAGE[name] * batch / (ms / steps) / 1e6) / peaks['hbm_gbs']
+
+    # release the captured graph and the model before the next workload
+    if world > 1 and runner is not None:
+        runner.graph.reset()
+    del step_fn, trainer, runner, net, model, opt, flat, pool_dev, labels_dev, pool_host, labels_host
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    if rank == 0:
+        roofline = time_dominant_kernel(name, batch, size, dev, peaks, args.dtype)
+        if name == 'imagenet' and roofline is not None and not args.no_layer_table:
+            roofline['conv_layers'] = conv_layer_table(batch, dev, peaks)
+        result['roofline'] = roofline
+        result['cpu_baseline'] = None
+        if not args.no_cpu_baseline and world == 1:
+            result['cpu_baseline'] = cpu_reference_run(spec, steps=30 if name == 'cifar' else 3, warmup=2 if name == 'cifar' else 1, seconds=args.cpu_seconds if name == 'cifar' else args.cpu_seconds / 2,
+                                                       batch=min(batch, 512 if name == 'cifar' else 8))
+        torch.cuda.empty_cache()
+    barrier()
+    return result
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from deepcv_b200._lib import check, lib
+
+    rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    check(lib.dcv_device_check(), 'device_check')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks = load_peaks()
+    names = ['cifar', 'imagenet'] if args.workload == 'all' else [args.workload]
+    results = {name: measure_workload(name, args, dev, world, rank, local_rank, peaks) for name in names}
 
     def shutdown():
         # A captured CUDA graph that contains NCCL kernels keeps the communicator busy: destroy_process_group() was seen to hang on it.
-        # Release the graph first and leave the process without the collective teardown.
+        # The graphs were released per workload; leave the process without the collective teardown.
         if world > 1:
-            graph = getattr(runner, 'graph', None)
-            if graph is not None:
-                graph.reset()
             torch.cuda.synchronize()
             sys.stdout.flush()
             sys.stderr.flush()
@@ -401,16 +503,10 @@ def run_b200(args):
     if rank != 0:
         shutdown()
         return
-    roofline = time_dominant_kernel(args.workload, batch, size, dev, peaks, args.dtype)
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_reference_run(spec, steps=30, warmup=2, seconds=args.cpu_seconds, batch=min(batch, 512 if args.workload == 'cifar' else 8))
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype=args.dtype, data='synthetic',
-                config=dict(workload=spec['label'], per_gpu_batch=batch, global_batch=batch * world, parallelism=f'dp{world}', step='fused u8 preprocess(normalise+flip+crop) + fwd + CE + bwd + '
-                            + ('bucketed NCCL all-reduce + ' if world > 1 else '') + 'AdamW' + ('' if args.no_graph else ', one CUDA graph replay per step'),
-                            l2='inputs cycle through a pool of %d distinct uint8 batches (%.0f MB > 126 MB L2)' % (pool_n, pool_n * batch_bytes / 1e6), final_loss=losses[-1] if losses else None),
-                e2e=e2e, gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=dict(clocks.summary(*clock_window), remeasured=remeasured), roofline=roofline, cpu_baseline=cpu)
+    head = results[names[0]]
+    line = dict(metric=METRIC, value=head['value'], unit=UNIT, n_gpus=world, steps=head['steps'], warmup=head['warmup'], ms_per_step=head['ms_per_step'], higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype=args.dtype, data='synthetic', config=head['config'], e2e=head['e2e'], gpu_launches=sum(r['gpu_launches'] for r in results.values()),
+                launches_per_step=head['launches_per_step'], clocks=head['clocks'], roofline=head.get('roofline'), cpu_baseline=head.get('cpu_baseline'), workloads=results)
     print(json.dumps(line))
     shutdown()
 

@@ -11,6 +11,7 @@ from pathlib import Path
 __all__ = ['lib', 'ConvShape', 'NormParams', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
            'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
 
+ABI_VERSION = 2
 DCV_F32, DCV_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_SIGMOID = 0, 1, 2, 3
 ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05 = 0, 1, 2
@@ -36,7 +37,6 @@ SYMBOLS = {
     'dcv_last_error': (c_char_p, []),
     'dcv_device_check': (c_int, []),
     'dcv_launch_count': (c_uint64, []),
-    'dcv_set_accumulators_prezeroed': (c_int, [c_int]),
     'dcv_preprocess_u8': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P]),
     'dcv_nchw_to_nhwc': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_nhwc_to_nchw': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
@@ -44,23 +44,24 @@ SYMBOLS = {
     'dcv_pack_conv_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_im2col': (c_int, [POINTER(ConvShape), P, P, c_int, c_int, P]),
     'dcv_fill_zero': (c_int, [P, c_size_t, P]),
+    'dcv_gather_rows': (c_int, [P, P, P, c_int, c_int64, c_size_t, P, P]),
     'dcv_conv2d_tc_supported': (c_int, [POINTER(ConvShape), c_int, c_int]),
-    'dcv_conv2d_fwd': (c_int, [POINTER(ConvShape), P, P, P, P, P, c_int, c_float, c_int, c_int, P]),
+    'dcv_conv2d_fwd': (c_int, [POINTER(ConvShape), P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, P]),
     'dcv_conv2d_dgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, P]),
     'dcv_conv2d_wgrad_workspace': (c_size_t, [POINTER(ConvShape), c_int, c_int]),
-    'dcv_conv2d_wgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, P]),
-    'dcv_norm_stats': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_conv2d_wgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, c_int, P]),
+    'dcv_norm_stats': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_saved_floats': (c_size_t, [c_int, c_int, c_int]),
     'dcv_norm_fwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P]),
     'dcv_norm_apply_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dcv_conv2d_gather_supported': (c_int, [POINTER(ConvShape), P, c_int, c_int]),
     'dcv_gather_pack_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_gather_unpack_wgrad': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
-    'dcv_conv2d_fwd_gather': (c_int, [POINTER(ConvShape), P, P, c_int, P, P, P, c_int, c_float, P]),
-    'dcv_conv2d_wgrad_gather': (c_int, [POINTER(ConvShape), P, P, P, c_int, P]),
-    'dcv_norm_bwd_reduce': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_conv2d_fwd_gather': (c_int, [POINTER(ConvShape), P, P, c_int, P, P, P, c_int, c_float, c_int, P]),
+    'dcv_conv2d_wgrad_gather': (c_int, [POINTER(ConvShape), P, P, P, c_int, c_int, P]),
+    'dcv_norm_bwd_reduce': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_bwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P, P, P, P, P, P]),
-    'dcv_act_norm_bwd_apply': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, P]),
+    'dcv_act_norm_bwd_apply': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_avgpool2d_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_avgpool2d_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_axpby': (c_int, [P, P, P, c_float, c_float, c_size_t, c_int, P]),
@@ -69,8 +70,9 @@ SYMBOLS = {
     'dcv_bilinear_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_bilinear_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_linear_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
-    'dcv_linear_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
+    'dcv_linear_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),
     'dcv_softmax_ce': (c_int, [P, P, P, P, c_int, c_int, P]),
+    'dcv_classification_metrics': (c_int, [P, P, P, c_int, c_int, P]),
     'dcv_scale_by_device_scalar': (c_int, [P, P, P, c_size_t, P]),
     'dcv_counter_add': (c_int, [P, c_int32, P]),
     'dcv_adamw_flat': (c_int, [P, P, P, P, c_size_t, P, c_float, c_float, c_float, c_float, c_float, P, P]),
@@ -98,8 +100,8 @@ class _Library:
             for name, (restype, argtypes) in SYMBOLS.items():
                 fn = getattr(cdll, name)
                 fn.restype, fn.argtypes = restype, argtypes
-            if cdll.dcv_abi_version() != 1:
-                raise RuntimeError(f'deepcv_b200: ABI version mismatch ({cdll.dcv_abi_version()} != 1); rebuild the extension')
+            if cdll.dcv_abi_version() != ABI_VERSION:
+                raise RuntimeError(f'deepcv_b200: ABI version mismatch ({cdll.dcv_abi_version()} != {ABI_VERSION}); rebuild the extension')
             self._cdll = cdll
         return self._cdll
 

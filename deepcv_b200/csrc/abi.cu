@@ -6,10 +6,6 @@
 namespace dcv {
 static thread_local char g_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
-// process-wide, not thread-local: autograd runs the backward launches on its own worker thread
-static std::atomic<bool> g_prezeroed{false};
-bool accumulators_prezeroed() { return g_prezeroed.load(std::memory_order_relaxed); }
-void set_accumulators_prezeroed(bool on) { g_prezeroed.store(on, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -26,8 +22,6 @@ int dcv_abi_version(void) { return DCV_ABI_VERSION; }
 const char* dcv_last_error(void) { return dcv::g_error; }
 
 uint64_t dcv_launch_count(void) { return dcv::g_launches.load(std::memory_order_relaxed); }
-
-int dcv_set_accumulators_prezeroed(int on) { const int was = dcv::accumulators_prezeroed() ? 1 : 0; dcv::set_accumulators_prezeroed(on != 0); return was; }
 
 int dcv_device_check(void) {
   int dev = -1;

@@ -109,11 +109,10 @@ struct FastDiv {  // n / d for 0 <= n < 2^31, d >= 1
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // Accumulator buffers (per-(n,c) statistics, gradient sums filled by atomics) are normally zeroed by the launcher that fills them: one memset node
-// per kernel. A caller that zeroes ALL of them itself, once per step (dcv_set_accumulators_prezeroed(1), deepcv_b200/ops.py: AccumulatorArena), turns
-// those ~22 memsets of a CIFAR step into one.
-bool accumulators_prezeroed();
-void set_accumulators_prezeroed(bool on);
-inline void zero_accumulator(void* p, size_t bytes, cudaStream_t st) { if (p && bytes && !accumulators_prezeroed()) cudaMemsetAsync(p, 0, bytes, st); }
+// per kernel. A caller that zeroes ALL of them itself, once per step (deepcv_b200/ops.py: AccumulatorArena), says so per call (`acc_prezeroed` argument of
+// the accumulating entry points) and turns those ~22 memsets of a CIFAR step into one. Per call, not per process: two models / streams / threads never
+// see each other's setting.
+inline void zero_accumulator(void* p, size_t bytes, cudaStream_t st, bool prezeroed) { if (p && bytes && !prezeroed) cudaMemsetAsync(p, 0, bytes, st); }
 inline int grid_for(size_t work_items, int block, int max_blocks = kNumSMs * 16) {
   size_t g = (work_items + block - 1) / block;
   if (g < 1) g = 1;

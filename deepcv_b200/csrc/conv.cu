@@ -4,15 +4,15 @@
 namespace dcv {
 int conv_fwd_direct(const dcv_conv_shape*, const void*, const void*, const float*, void*, float*, int, float, int, cudaStream_t);
 int conv_dgrad_direct(const dcv_conv_shape*, const void*, const void*, void*, int, cudaStream_t);
-int conv_wgrad_direct(const dcv_conv_shape*, const void*, const void*, float*, int, cudaStream_t);
+int conv_wgrad_direct(const dcv_conv_shape*, const void*, const void*, float*, int, bool prezeroed, cudaStream_t);
 // conv_tc.cu
 bool conv_tc_fwd_supported(const dcv_conv_shape*, int dtype);
 bool conv_tc_wgrad_supported(const dcv_conv_shape*, int dtype);
 int conv_fwd_tc(const dcv_conv_shape*, const void*, const void*, const float*, void*, float*, int, float, cudaStream_t);
-int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, cudaStream_t);
+int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, bool prezeroed, cudaStream_t);
 bool conv_fwd_tc_gather_supported(const dcv_conv_shape*, const void* x, int kpad, int dtype);
 int conv_fwd_tc_gather(const dcv_conv_shape*, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, cudaStream_t);
-int conv_wgrad_tc_gather(const dcv_conv_shape*, const void* x, const void* dy, float* dw_col, int kpad, cudaStream_t);
+int conv_wgrad_tc_gather(const dcv_conv_shape*, const void* x, const void* dy, float* dw_col, int kpad, bool prezeroed, cudaStream_t);
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*);
 
 static dcv_conv_shape dgrad_as_fwd(const dcv_conv_shape& s) {
@@ -39,12 +39,12 @@ int dcv_conv2d_tc_supported(const dcv_conv_shape* shape, int dtype, int op) {
 }
 
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,
-                   int act, float slope, int dtype, int algo, void* stream) {
+                   int act, float slope, int dtype, int algo, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(shape, "conv2d_fwd: null shape");
   cudaStream_t st = as_stream(stream);
   const bool tc_ok = conv_tc_fwd_supported(shape, dtype);
-  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
+  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st, acc_prezeroed != 0);
   DCV_REQUIRE(algo != DCV_ALGO_TCGEN05 || tc_ok, "conv2d_fwd: tcgen05 algorithm does not support this shape/dtype (needs bf16, c %% 64 == 0, k %% 16 == 0, stride 1, dilation 1)");
   if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(shape, x, w, bias, y, stats_nc, act, slope, st);
   return conv_fwd_direct(shape, x, w, bias, y, stats_nc, act, slope, dtype, st);
@@ -55,18 +55,18 @@ int dcv_conv2d_gather_supported(const dcv_conv_shape* shape, const void* x, int 
 }
 
 int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc,
-                          int act, float slope, void* stream) {
+                          int act, float slope, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(shape, "conv2d_fwd_gather: null shape");
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st);
+  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st, acc_prezeroed != 0);
   return conv_fwd_tc_gather(shape, x, w_col, kpad, bias, y, stats_nc, act, slope, st);
 }
 
-int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, void* stream) {
+int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(shape, "conv2d_wgrad_gather: null shape");
-  return conv_wgrad_tc_gather(shape, x, dy, dw_col, kpad, as_stream(stream));
+  return conv_wgrad_tc_gather(shape, x, dy, dw_col, kpad, acc_prezeroed != 0, as_stream(stream));
 }
 
 int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w, const void* wt, void* dx, int dtype, int algo, void* stream) {
@@ -92,14 +92,14 @@ size_t dcv_conv2d_wgrad_workspace(const dcv_conv_shape* shape, int dtype, int al
   return 0;
 }
 
-int dcv_conv2d_wgrad(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, void* workspace, int dtype, int algo, void* stream) {
+int dcv_conv2d_wgrad(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, void* workspace, int dtype, int algo, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(shape, "conv2d_wgrad: null shape");
   cudaStream_t st = as_stream(stream);
   const bool tc_ok = conv_tc_wgrad_supported(shape, dtype);
   DCV_REQUIRE(algo != DCV_ALGO_TCGEN05 || tc_ok, "conv2d_wgrad: tcgen05 algorithm does not support this shape/dtype");
-  if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_wgrad_tc(shape, x, dy, dw, workspace, st);
-  return conv_wgrad_direct(shape, x, dy, dw, dtype, st);
+  if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_wgrad_tc(shape, x, dy, dw, workspace, acc_prezeroed != 0, st);
+  return conv_wgrad_direct(shape, x, dy, dw, dtype, acc_prezeroed != 0, st);
 }
 
 }  // extern "C"

@@ -836,11 +836,11 @@ static int launch_wgrad_s1(const WgradArgs& a, cudaStream_t st) {   // -1: not a
   return -1;
 }
 
-int conv_wgrad_direct(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, int dtype, cudaStream_t st) {
+int conv_wgrad_direct(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, int dtype, bool prezeroed, cudaStream_t st) {
   if (check_shape(shape, "conv2d_wgrad")) return 1;
   DCV_REQUIRE(x && dy && dw, "conv2d_wgrad: null pointer");
   const dcv_conv_shape& s = *shape;
-  zero_accumulator(dw, (size_t)s.k * s.r * s.s * s.c * sizeof(float), st);
+  zero_accumulator(dw, (size_t)s.k * s.r * s.s * s.c * sizeof(float), st, prezeroed);
   WgradArgs a{};
   a.s = s; a.x = x; a.dy = dy; a.dw = dw;
   // the 7x7/stride-2 class of layers needs the small tile to fit the input halo in shared memory

@@ -1006,12 +1006,12 @@ int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col
     kern<<<grid, GA_THREADS, smem, st>>>(mw, prm);
   }
   DCV_LAUNCH_CHECK("conv_fwd_tc_gather_kernel");
-  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
+  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
   return 0;
 }
 
 // dw_col: [K][kpad] fp32 in the gather K order (overwritten).
-int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy, float* dw_col, int kpad, cudaStream_t st) {
+int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy, float* dw_col, int kpad, bool prezeroed, cudaStream_t st) {
   using namespace tc;
   DCV_REQUIRE(x && dy && dw_col, "conv2d_wgrad_gather: null pointer");
   DCV_REQUIRE(reinterpret_cast<uintptr_t>(dy) % 16 == 0 && reinterpret_cast<uintptr_t>(dw_col) % 16 == 0, "conv2d_wgrad_gather: pointers must be 16-byte aligned");
@@ -1021,7 +1021,7 @@ int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy,
   wp.dw_col = dw_col;
   const size_t smem = 1024 + (size_t)GW_NA * 2 * BLOCK_M * 128 + (size_t)GA_STAGES * wp.g.kblocks * BLOCK_M * 128 + (size_t)GA_ROW_BUFS * wp.g.rows_bytes + 256;
   DCV_REQUIRE(smem <= 227 * 1024, "conv2d_wgrad_gather: %zu bytes of shared memory needed", smem);
-  zero_accumulator(dw_col, (size_t)s->k * kpad * sizeof(float), st);
+  zero_accumulator(dw_col, (size_t)s->k * kpad * sizeof(float), st, prezeroed);
   CUtensorMap mdy;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)s->k, (cuuint64_t)s->q, (cuuint64_t)s->p, (cuuint64_t)s->n};
@@ -1052,7 +1052,7 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0), "conv2d_fwd (tcgen05): pointers must be 16-byte aligned");
   if (fwd_halo_applicable(s)) {
     if (conv_fwd_tc_halo(s, x, w, bias, y, act, slope, st)) return 1;
-    if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
+    if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
     return 0;
   }
   FwdParams prm{};
@@ -1085,7 +1085,7 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   else if (prm.n_tiles_k == 1 && s->r * s->s * (s->c / BLOCK_K) <= kMaxResidentKb && getenv("DCV_TC_NO_RESIDENT") == nullptr) rc = launch_fwd<64, 1>(mx, mw, prm, st);
   else rc = launch_fwd<64>(mx, mw, prm, st);
   if (rc) return rc;
-  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, st);
+  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
   return 0;
 }
 
@@ -1264,7 +1264,7 @@ bool conv_tc_wgrad_supported(const dcv_conv_shape* s, int dtype) {
 
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*) { return 0; }
 
-int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float* dw, void* /*workspace*/, cudaStream_t st) {
+int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float* dw, void* /*workspace*/, bool prezeroed, cudaStream_t st) {
   using namespace tc;
   DCV_REQUIRE(x && dy && dw, "conv2d_wgrad (tcgen05): null pointer");
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0), "conv2d_wgrad (tcgen05): pointers must be 16-byte aligned");
@@ -1296,7 +1296,7 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
   if (const char* e = getenv("DCV_WGRAD_SPLITS")) { const int v = atoi(e); if (v >= 1 && v <= prm.pixel_tiles) splits = v; }   // tuning aid
   prm.splits = splits;
   prm.dw = dw;
-  zero_accumulator(dw, (size_t)s->k * s->r * s->s * s->c * sizeof(float), st);
+  zero_accumulator(dw, (size_t)s->k * s->r * s->s * s->c * sizeof(float), st, prezeroed);
 
   CUtensorMap mdy, mx;
   {

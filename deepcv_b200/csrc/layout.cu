@@ -176,6 +176,36 @@ __global__ void gather_unpack_wgrad_kernel(const float* __restrict__ dw_col, flo
   }
 }
 
+// Batch assembly for the device-resident input pipeline: dst row j = src row idx[j]; rows are `row_bytes` long (a multiple of 16, both bases 16-byte
+// aligned). One warp streams a row with 16-byte accesses; an index outside [0, n_src) traps nothing and copies nothing but flags the batch (err != 0).
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ idx, uint4* __restrict__ dst, int n, long long n_src, uint32_t vec_per_row, int* __restrict__ err) {
+  const int warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = blockIdx.x * warps_per_block + warp; j < n; j += gridDim.x * warps_per_block) {
+    const long long i = idx[j];
+    if (i < 0 || i >= n_src) { if (lane == 0 && err) *err = 1; continue; }
+    const uint4* s = src + (size_t)i * vec_per_row;
+    uint4* d = dst + (size_t)j * vec_per_row;
+    for (uint32_t v = lane; v < vec_per_row; v += 128) {   // 4 independent 16-byte loads in flight per lane
+      uint4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (v + u * 32 < vec_per_row) r[u] = __ldg(s + v + u * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (v + u * 32 < vec_per_row) d[v + u * 32] = r[u];
+    }
+  }
+}
+
+// rows that are not 16-byte multiples (labels: one int64 per row): one thread per 4-byte word
+__global__ void gather_rows_words_kernel(const uint32_t* __restrict__ src, const int64_t* __restrict__ idx, uint32_t* __restrict__ dst, int n, long long n_src, uint32_t words_per_row, int* __restrict__ err) {
+  const size_t total = (size_t)n * words_per_row;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t / words_per_row); const uint32_t w = (uint32_t)(t - (size_t)j * words_per_row);
+    const long long i = idx[j];
+    if (i < 0 || i >= n_src) { if (err) *err = 1; continue; }
+    dst[t] = src[(size_t)i * words_per_row + w];
+  }
+}
+
 }  // namespace dcv
 
 extern "C" {
@@ -256,6 +286,22 @@ int dcv_gather_unpack_wgrad(const float* dw_col, float* dw_krsc, int k, int r, i
   DCV_REQUIRE(dw_col && dw_krsc && k > 0 && r > 0 && sc > 0 && kpad >= r * rp, "gather_unpack_wgrad: bad arguments");
   gather_unpack_wgrad_kernel<<<grid_for((size_t)k * r * sc, 256), 256, 0, as_stream(stream)>>>(dw_col, dw_krsc, k, r, sc, rp, kpad);
   DCV_LAUNCH_CHECK("gather_unpack_wgrad_kernel");
+  return 0;
+}
+
+int dcv_gather_rows(const void* src, const int64_t* idx, void* dst, int n, long long n_src, size_t row_bytes, int* err_flag, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(src && idx && dst && n > 0 && n_src > 0, "gather_rows: bad arguments");
+  if (row_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(src) % 16 != 0 || reinterpret_cast<uintptr_t>(dst) % 16 != 0) {
+    DCV_REQUIRE(row_bytes % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0, "gather_rows: rows must be multiples of 4 bytes at 4-byte aligned bases");
+    gather_rows_words_kernel<<<grid_for((size_t)n * (row_bytes / 4), 256), 256, 0, as_stream(stream)>>>((const uint32_t*)src, idx, (uint32_t*)dst, n, n_src, (uint32_t)(row_bytes / 4), err_flag);
+    DCV_LAUNCH_CHECK("gather_rows_words_kernel");
+    return 0;
+  }
+  const int wpb = 8;
+  int grid = (n + wpb - 1) / wpb; if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  gather_rows_kernel<<<grid, wpb * 32, 0, as_stream(stream)>>>((const uint4*)src, idx, (uint4*)dst, n, n_src, (uint32_t)(row_bytes / 16), err_flag);
+  DCV_LAUNCH_CHECK("gather_rows_kernel");
   return 0;
 }
 

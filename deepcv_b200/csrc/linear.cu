@@ -239,11 +239,11 @@ static int skinny_fwd(const void* x, const float* w, const float* bias, float* y
 }
 
 template <int NB, typename TX>
-static int skinny_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, float* db, float* dpre, int m, int n, int k, int act, float slope, cudaStream_t st) {
+static int skinny_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, float* db, float* dpre, int m, int n, int k, int act, float slope, bool prezeroed, cudaStream_t st) {
   linear_skinny_dx_kernel<NB, TX><<<(m + 3) / 4, 128, 0, st>>>(w, y, dy, (TX*)dx, dpre, m, n, k, act, slope);
   DCV_LAUNCH_CHECK("linear_skinny_dx_kernel");
   if (dw) {
-    zero_accumulator(dw, (size_t)n * k * sizeof(float), st);
+    zero_accumulator(dw, (size_t)n * k * sizeof(float), st, prezeroed);
     const int rows = 32;
     linear_skinny_dw_kernel<NB, TX><<<dim3((k + 255) / 256, (m + rows - 1) / rows), 256, 0, st>>>((const TX*)x, dpre, dw, db, m, n, k, rows);
     DCV_LAUNCH_CHECK("linear_skinny_dw_kernel");
@@ -272,16 +272,16 @@ int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, in
 }
 
 int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy, void* dx, float* dw, float* db, float* dpre_ws,
-                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, void* stream) {
+                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(x && w && y && dy && dpre_ws && m > 0 && n > 0 && k > 0, "linear_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(db, (size_t)n * sizeof(float), st);
+  zero_accumulator(db, (size_t)n * sizeof(float), st, acc_prezeroed != 0);
   if (n <= 32 && y_dtype == DCV_F32) {
     DCV_DISPATCH_DTYPE(x_dtype, TX, {
-      if (n <= 8) return skinny_bwd<8, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);
-      if (n <= 16) return skinny_bwd<16, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);
-      return skinny_bwd<32, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, st);
+      if (n <= 8) return skinny_bwd<8, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, st);
+      if (n <= 16) return skinny_bwd<16, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, st);
+      return skinny_bwd<32, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, st);
     });
   }
   int gy = (m + 31) / 32; if (gy > 64) gy = 64;

@@ -4,11 +4,18 @@
 
 namespace dcv {
 
-// one warp per row
+constexpr int64_t kIgnoreIndex = -100;   // torch.nn.CrossEntropyLoss default `ignore_index`
+
+// one warp per row. Rows whose target is `ignore_index` contribute nothing and the mean runs over the other rows (torch semantics); any other target
+// outside [0, n) poisons the loss with NaN instead of reading out of bounds (torch device-asserts there).
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, float* __restrict__ loss,
                                   float* __restrict__ dlogits, int m, int n) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= m) return;
+  int valid = 0;
+  for (int i = lane; i < m; i += 32) valid += target[i] != kIgnoreIndex;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
   const float* row = logits + (size_t)warp * n;
   float mx = -INFINITY;
   for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
@@ -19,10 +26,39 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_
   se = warp_sum(se);
   const float lse = mx + logf(se);
   const int64_t t = target[warp];
-  const float inv_m = 1.f / (float)m;
+  const bool ignored = t == kIgnoreIndex, bad = !ignored && (t < 0 || t >= n);
+  const float inv_m = valid > 0 ? 1.f / (float)valid : 0.f;
   if (dlogits)
-    for (int j = lane; j < n; j += 32) dlogits[(size_t)warp * n + j] = (expf(row[j] - lse) - (j == t ? 1.f : 0.f)) * inv_m;
-  if (lane == 0) atomicAdd(loss, (lse - row[t]) * inv_m);
+    for (int j = lane; j < n; j += 32) dlogits[(size_t)warp * n + j] = (ignored || bad) ? 0.f : (expf(row[j] - lse) - (j == t ? 1.f : 0.f)) * inv_m;
+  if (lane == 0) {
+    if (bad) atomicAdd(loss, __int_as_float(0x7fc00000));
+    else if (!ignored) atomicAdd(loss, (lse - row[t]) * inv_m);
+  }
+}
+
+// Evaluation metrics, accumulated over batches: acc[0] += sum of per-row cross entropies, acc[1] += rows whose argmax is the target, acc[2] += rows counted.
+__global__ void classification_metrics_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, float* __restrict__ acc, int m, int n) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  const int64_t t = target[warp];
+  if (t == kIgnoreIndex) return;
+  const float* row = logits + (size_t)warp * n;
+  float mx = -INFINITY; int arg = 0x7fffffff;
+  for (int j = lane; j < n; j += 32) { const float v = row[j]; if (v > mx) { mx = v; arg = j; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {   // max with the lowest index on ties (torch.argmax)
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o); const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  float se = 0.f;
+  for (int j = lane; j < n; j += 32) se += expf(row[j] - mx);
+  se = warp_sum(se);
+  if (lane == 0) {
+    const bool bad = t < 0 || t >= n;
+    atomicAdd(acc, bad ? __int_as_float(0x7fc00000) : (mx + logf(se) - row[t]));
+    if (!bad && arg == (int)t) atomicAdd(acc + 1, 1.f);
+    atomicAdd(acc + 2, 1.f);
+  }
 }
 
 __global__ void scale_dev_kernel(const float* __restrict__ src, const float* __restrict__ scale_dev, float* __restrict__ dst, size_t count) {
@@ -61,6 +97,14 @@ int dcv_softmax_ce(const float* logits, const int64_t* target, float* loss, floa
   cudaMemsetAsync(loss, 0, sizeof(float), st);
   softmax_ce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(logits, target, loss, dlogits, m, n);
   DCV_LAUNCH_CHECK("softmax_ce_kernel");
+  return 0;
+}
+
+int dcv_classification_metrics(const float* logits, const int64_t* target, float* acc3, int m, int n, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(logits && target && acc3 && m > 0 && n > 0, "classification_metrics: bad arguments");
+  classification_metrics_kernel<<<(m * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, target, acc3, m, n);
+  DCV_LAUNCH_CHECK("classification_metrics_kernel");
   return 0;
 }
 

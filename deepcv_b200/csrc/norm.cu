@@ -610,12 +610,12 @@ size_t dcv_norm_saved_floats(int n, int c, int groups) {
   return 4 * (size_t)c + 4 * (size_t)n * G + 2 * (size_t)c;
 }
 
-int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dtype, void* stream) {
+int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dtype, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(y && stats_nc, "norm_stats: null pointer");
   if (check_nc("norm_stats", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(stats_nc, (size_t)n * c * 2 * sizeof(float), st);
+  zero_accumulator(stats_nc, (size_t)n * c * 2 * sizeof(float), st, acc_prezeroed != 0);
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
@@ -675,12 +675,12 @@ int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw
   return 0;
 }
 
-int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream) {
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(dz && y && s_nc, "norm_bwd_reduce: null pointer");
   if (check_nc("norm_bwd_reduce", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(s_nc, (size_t)n * c * kBwdSums * sizeof(float), st);
+  zero_accumulator(s_nc, (size_t)n * c * kBwdSums * sizeof(float), st, acc_prezeroed != 0);
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
@@ -704,12 +704,12 @@ int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, con
 }
 
 int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
-                           int n, int hw, int c, int dtype, void* stream) {
+                           int n, int hw, int c, int dtype, int acc_prezeroed, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(dz && y && dy, "act_norm_bwd_apply: null pointer");
   if (check_nc("act_norm_bwd_apply", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(dbias_c, (size_t)c * sizeof(float), st);
+  zero_accumulator(dbias_c, (size_t)c * sizeof(float), st, acc_prezeroed != 0);
   dim3 grid; int block;
 #define DCV_BWD_APPLY(ACT_)                                                                                                                                   \
   DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                              \

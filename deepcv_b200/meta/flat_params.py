@@ -50,6 +50,7 @@ class FlatParameters:
         self.numel = total
         self.flat_params = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_grads = torch.zeros(total, dtype=torch.float32, device=device)
+        self.zeroed_by_step = False   # True while a captured step zeroes `flat_grads` itself (GraphedTrainStep)
         self._grad_views: Dict[int, torch.Tensor] = {}
         with torch.no_grad():
             for p, off in zip(params, self.offsets):
@@ -84,6 +85,14 @@ class FlatParameters:
             mk = lambda buf: buf[off:off + n].view(p.shape)
         return mk(self.flat_params), mk(self.flat_grads)
 
+    def views_of(self, buf: torch.Tensor, p: torch.Tensor, off: int) -> torch.Tensor:
+        """ View of another flat buffer of the same layout (optimizer moments) with `p`'s shape and physical element order. """
+        n = p.numel()
+        if p.dim() == 4 and p.permute(0, 2, 3, 1).is_contiguous() and not p.is_contiguous():
+            k, c, r, s = p.shape
+            return buf[off:off + n].view(k, r, s, c).permute(0, 3, 1, 2)
+        return buf[off:off + n].view(p.shape)
+
     def grad_view(self, p: torch.Tensor) -> torch.Tensor:
         return self._grad_views[id(p)]
 
@@ -108,6 +117,21 @@ class FlatParameters:
         for p in self.params:
             if p.grad is not self._grad_views[id(p)]:
                 p.grad = self._grad_views[id(p)]
+
+    def reset_gradients(self, memset: bool = True):
+        """ What `zero_grad()` means for the flat buffer: `.grad`s point into it again, the whole buffer is zero (ONE memset: parameters of layers that
+        this step does not run, or of modules the library does not own, must not keep last step's values) and every fused layer writes — not
+        accumulates — its gradients on its next backward. `memset=False` when the caller has zeroed the buffer itself (captured step: the arena's
+        `begin_step(extra_zero=[flat_grads])`). """
+        self.restore_grad_views()
+        if memset:
+            if self.flat_grads.is_cuda:
+                check(lib.dcv_fill_zero(_ptr(self.flat_grads), self.flat_grads.numel() * 4, _stream()), 'fill_zero(flat gradients)')
+            else:
+                self.flat_grads.zero_()
+        for layer in self.layers:
+            if layer._grad_out is not None:
+                layer._grad_out['_written'] = False
 
 
 def flatten_parameters(model: torch.nn.Module, bucket_bytes: int = 8 << 20) -> FlatParameters:
@@ -140,13 +164,40 @@ class FlatAdamW(torch.optim.Optimizer):
         return self
 
     def zero_grad(self, set_to_none: bool = True):
-        """ Gradients are overwritten (not accumulated) by the backward kernels: nothing to clear in flat mode. """
+        """ Flat mode: one memset of the flat gradient buffer (none inside a captured step whose arena zeroes it up front); the fused layers then
+        write their gradients straight into their slices on the next backward. """
         if self._flat is None:
             super().zero_grad(set_to_none=set_to_none)
         else:
-            self._flat.restore_grad_views()
-            for p in self._flat.foreign_params:
-                p.grad.zero_()
+            self._flat.reset_gradients(memset=not self._flat.zeroed_by_step)
+
+    def state_dict(self):
+        """ torch layout plus the device-side step counter (read back once here), so that bias correction resumes where it stopped. """
+        sd = super().state_dict()
+        sd['flat_step'] = int(self._dev_state['step'].item()) if self._dev_state is not None else 0
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        step = int(state_dict.pop('flat_step', 0))
+        super().load_state_dict(state_dict)
+        st = self._device_state(self.param_groups[0]['params'][0].device)
+        st['step'].fill_(step)
+        st['lr_value'] = None
+
+    def per_parameter_state(self) -> Dict[str, Dict[str, Any]]:
+        """ `torch.optim.AdamW`-style state per parameter ({'step', 'exp_avg', 'exp_avg_sq'} views of the flat moments, in `model.named_parameters()` order):
+        what a checkpoint needs to interchange with the stock optimizer (the reference saves 'optimizer' in `to_save`, `ignite_training.py:319`). """
+        if self._flat is None or 'flat' not in self.state:
+            return {}
+        flat, st = self._flat, self.state['flat']
+        step = torch.tensor(float(self._dev_state['step'].item()) if self._dev_state is not None else 0.)
+        names = {id(p): n for n, p in flat.model.named_parameters()}
+        out = {}
+        for p, off in zip(flat.params, flat.offsets):
+            v1, v2 = flat.views_of(st['exp_avg'], p, off), flat.views_of(st['exp_avg_sq'], p, off)
+            out[names[id(p)]] = dict(step=step.clone(), exp_avg=v1, exp_avg_sq=v2)
+        return out
 
     def _device_state(self, device):
         if self._dev_state is None:
@@ -203,37 +254,45 @@ class FlatAdamW(torch.optim.Optimizer):
 
 class GradientBucketReducer:
     """ Data-parallel gradient averaging over the flat gradient buffer: one `all_reduce(SUM)` per bucket on a communication stream,
-    launched as soon as backward has enqueued the bucket's last producer; the 1/world_size factor is folded into the optimizer
-    (`FlatAdamW.grad_scale`). BatchNorm statistics are never exchanged (per-replica BN, reference `use_sync_batch_norm: False`). """
+    launched as soon as backward has enqueued the bucket's last producer. "Enqueued" is reported by the fused layers themselves, at the END of
+    their backward (`ops._backward_done` -> the `_done` entry of `FusedLayer._grad_out`): a module full-backward hook fires when the gradient
+    w.r.t. the layer's INPUT is ready, which for a first layer whose input needs no gradient is before its weight-gradient kernels are enqueued.
+    Buckets that hold parameters of modules the library does not own, or of layers that did not run this step, are reduced by `finish()`.
+    The 1/world_size factor is applied by `finish()` unless an optimizer has taken it over (`FlatAdamW.grad_scale`, then `average_in_finish`
+    is False). BatchNorm statistics are never exchanged (per-replica BN, reference `use_sync_batch_norm: False`). """
 
     def __init__(self, flat: FlatParameters, process_group=None, overlap: bool = True):
         self.flat, self.group, self.overlap = flat, process_group, overlap
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.is_cuda = flat.flat_grads.is_cuda
         self.comm_stream = torch.cuda.Stream(device=flat.flat_grads.device) if self.is_cuda else None
-        # how many fused layers produce gradients into each bucket
-        self._producers = [0] * len(flat.buckets)
+        self.average_in_finish = True
+        foreign = {flat.bucket_of[id(p)] for p in flat.foreign_params}
+        self._early_ok = [b not in foreign for b in range(len(flat.buckets))]
         self._layer_buckets: Dict[int, List[int]] = {}
+        # fused layers that write into each bucket: a bucket is complete when each of them has finished its backward
+        self._producers = [0] * len(flat.buckets)
         for layer in flat.layers:
             touched = sorted({flat.bucket_of[id(p)] for p in layer.parameters(recurse=True) if id(p) in flat.bucket_of})
             self._layer_buckets[id(layer)] = touched
             for b in touched:
                 self._producers[b] += 1
-            if layer._grad_out is not None:
-                layer._grad_out = dict(layer._grad_out)
-        self._pending = list(self._producers)
-        self._hooks = []
-        if overlap and self.world_size > 1:
-            for layer in flat.layers:
-                self._hooks.append(layer.register_full_backward_hook(self._make_hook(layer)))
+            if layer._grad_out is not None and overlap and self.world_size > 1:
+                layer._grad_out['_done'] = self._make_done(layer)
+        self.begin_step()
 
-    def _make_hook(self, layer):
-        def _hook(module, grad_input, grad_output):
+    def _make_done(self, layer):
+        def _done():
+            if id(layer) in self._finished:     # a second backward through the same layer (shared weights): its bucket waits for `finish()`
+                for b in self._layer_buckets[id(layer)]:
+                    self._early_ok_step[b] = False
+                return
+            self._finished.add(id(layer))
             for b in self._layer_buckets[id(layer)]:
                 self._pending[b] -= 1
-                if self._pending[b] == 0:
+                if self._pending[b] == 0 and self._early_ok_step[b] and not self._launched[b]:
                     self._launch(b)
-        return _hook
+        return _done
 
     def _launch(self, b: int):
         start, end = self.flat.buckets[b]
@@ -249,16 +308,26 @@ class GradientBucketReducer:
     def begin_step(self):
         self._pending = list(self._producers)
         self._launched = [False] * len(self.flat.buckets)
+        self._early_ok_step = list(self._early_ok)
+        self._finished = set()
 
     def finish(self):
-        """ After `backward()`: reduce whatever was not launched by the hooks, then make the compute stream wait for the results. """
+        """ After `backward()`: reduce whatever was not launched early, make the compute stream wait for the results, average. """
         if self.world_size <= 1:
             return
-        if not hasattr(self, '_launched'):
-            self.begin_step()
+        relaunch = [b for b in range(len(self.flat.buckets)) if self._launched[b] and not self._early_ok_step[b]]
+        if relaunch:
+            raise RuntimeError('deepcv_b200: a gradient bucket was all-reduced before a second backward pass wrote into it (weights shared between layers '
+                               'that complete at different times); construct the data-parallel wrap with `overlap=False`')
         for b in range(len(self.flat.buckets)):
             if not self._launched[b]:
                 self._launch(b)
         if self.is_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self.average_in_finish:
+            g = self.flat.flat_grads
+            if self.is_cuda:
+                check(lib.dcv_axpby(_ptr(g), None, _ptr(g), 1. / self.world_size, 0., g.numel(), 0, _stream()), 'axpby(average gradients)')
+            else:
+                g.mul_(1. / self.world_size)
         self.begin_step()

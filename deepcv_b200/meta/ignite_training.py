@@ -12,6 +12,7 @@ overlapped with the rest of backward (`flat_params.GradientBucketReducer`), inst
 (forward, backward, all-reduce, AdamW) can be captured once into a CUDA graph and replayed (`GraphedTrainStep`), because the default
 CIFAR-10 network is launch-latency-bound, not bandwidth-bound.
 """
+import ctypes
 import enum
 import logging
 import multiprocessing
@@ -25,11 +26,12 @@ import torch.distributed as dist
 from torch.utils.data import DataLoader, Dataset
 
 from .. import ops
+from .._lib import check, lib
 from .flat_params import FlatAdamW, FlatParameters, GradientBucketReducer, flatten_parameters
 from .hyperparams import HYPERPARAMS_T, to_hyperparameters
 
 __all__ = ['MAIN_TRAINING_LOSS_NAME', 'Events', 'State', 'Engine', 'PiecewiseLinear', 'BackendConfig', 'CrossEntropyLoss', 'train', 'make_process_function',
-           'GraphedTrainStep', 'DataParallelModel']
+           'make_eager_process_function', 'GraphedTrainStep', 'GraphedEvalStep', 'DeviceDataLoader', 'evaluate', 'DataParallelModel']
 
 MAIN_TRAINING_LOSS_NAME = 'main_loss'
 
@@ -248,16 +250,33 @@ def _setup_distributed_training(device, backend_conf: BackendConfig, model: torc
     return model
 
 
-def make_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDict[str, Callable]', optimizer: torch.optim.Optimizer) -> Callable[[Engine, Any], Dict[str, float]]:
-    """ The training step of the reference, line for line (:233-255). """
+def _fused_layers(model: torch.nn.Module):
+    from .nn import FusedLayer
+    return [m for m in model.modules() if isinstance(m, FusedLayer)]
+
+
+def _move_batch(batch, device):
+    x, *y = tuple(b.to(device, non_blocking=True) if isinstance(b, torch.Tensor) and b.device != device else b for b in batch)
+    return x, (y[0] if len(y) == 1 else y)
+
+
+def make_eager_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDict[str, Callable]', optimizer: torch.optim.Optimizer,
+                                preprocess: Optional[torch.nn.Module] = None) -> Callable[[Engine, Any], Dict[str, float]]:
+    """ The training step of the reference, line for line (:233-255), one kernel launch after the other. """
+    inner = model.module if isinstance(model, DataParallelModel) else model
+    flat = getattr(inner, '_flat_parameters', None)
+
     def process_function(engine: Engine, batch) -> Dict[str, float]:
-        x, *y = tuple(b.to(device, non_blocking=True) if isinstance(b, torch.Tensor) and b.device != device else b for b in batch)
-        if len(y) == 1:
-            y = y[0]
+        x, y = _move_batch(batch, device)
         model.train()
+        if preprocess is not None:
+            preprocess.train()
+            x = preprocess(x)
         y_pred = model(x)
         batch_losses = {n: loss(y_pred, y) for n, loss in losses.items()}
         optimizer.zero_grad()
+        if flat is not None and not isinstance(optimizer, FlatAdamW):
+            flat.reset_gradients()   # a stock optimizer's zero_grad(set_to_none=True) dropped the `.grad` views into the flat buffer
         batch_losses[MAIN_TRAINING_LOSS_NAME].backward()
         if isinstance(model, DataParallelModel):
             model.finish_gradient_reduction()
@@ -266,19 +285,65 @@ def make_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDi
     return process_function
 
 
+def make_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDict[str, Callable]', optimizer: torch.optim.Optimizer,
+                          preprocess: Optional[torch.nn.Module] = None, cuda_graph: Optional[bool] = None) -> Callable[[Engine, Any], Dict[str, float]]:
+    """ `process_function(engine, batch) -> {loss name: float}` of the reference (:233-255). With a `FlatAdamW` over flat buffers on a CUDA device the
+    step is captured into a CUDA graph the first time a batch shape is seen (`GraphedTrainStep`, model / optimizer / BatchNorm state rewound after the
+    warm-up steps) and replayed afterwards — the default network's step is launch-bound: 2.8 ms eager, 0.6 ms replayed. `cuda_graph=False` (or any
+    other optimizer) keeps the eager step. At most 4 distinct batch shapes are captured (`drop_last=True` loaders have one). """
+    capturable = isinstance(optimizer, FlatAdamW) and optimizer._flat is not None and torch.device(device).type == 'cuda' and os.environ.get('DCV_NO_GRAPH') is None
+    if cuda_graph is None:
+        cuda_graph = capturable
+    if cuda_graph and not capturable:
+        raise RuntimeError('deepcv_b200: a CUDA-graph training step needs a CUDA device and a `FlatAdamW` attached to the flattened parameters of the model')
+    eager = make_eager_process_function(hp, device, model, losses, optimizer, preprocess)
+    if not cuda_graph:
+        return eager
+    runners: Dict[Any, GraphedTrainStep] = {}
+
+    dev = torch.device(device)
+
+    def _on_device(t: torch.Tensor) -> bool:
+        return t.is_cuda and (dev.index is None or t.device.index == dev.index)
+
+    def process_function(engine: Engine, batch) -> Dict[str, float]:
+        x, *y = batch
+        y = y[0] if len(y) == 1 else y
+        if not (isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor)):
+            return eager(engine, batch)
+        key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+        runner = runners.get(key)
+        if runner is None:
+            if len(runners) >= 4:
+                raise RuntimeError(f'deepcv_b200: more than 4 distinct batch shapes in one training run (got {key}); use a `drop_last=True` loader or `cuda_graph=False`')
+            # batches that already live on the device (DeviceDataLoader yields the same buffers every time) become the graph's static inputs: no copy
+            # per step; host batches (pinned, from a DataLoader) are copied straight into the static buffers by `step`
+            adopt = _on_device(x) and _on_device(y)
+            runner = runners[key] = GraphedTrainStep(model, losses, optimizer, x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), preprocess=preprocess,
+                                                     restore_state=True, adopt_inputs=adopt)
+        runner.step(x, y)
+        return {n: float(v) for n, v in zip(runner.static_losses.keys(), torch.stack(list(runner.static_losses.values())).tolist())}
+    process_function.runners = runners
+    return process_function
+
+
 class GraphedTrainStep:
     """ The same step captured ONCE into a CUDA graph (forward, backward, bucket all-reduces, AdamW) and replayed per batch.
 
-    `step(x, y)` copies the batch into static buffers (x may be the raw uint8 batch when `model` starts with `FusedPreprocess`; the per-sample
+    `step(x, y)` copies the batch into static buffers (x may be the raw uint8 batch when `preprocess` is a `FusedPreprocess`; the per-sample
     flip / crop parameters are drawn on the host and copied in too), refreshes the device learning rate, replays the graph and returns the
-    loss tensor (device scalar, no sync). Requires an optimizer whose `step` is capture-safe (`FlatAdamW`). """
+    main loss tensor (device scalar, no sync); `static_losses` holds every loss term. Requires an optimizer whose `step` is capture-safe (`FlatAdamW`).
+    `restore_state`: parameters, BatchNorm statistics and optimizer state are put back (in place) to what they were before the warm-up / capture
+    steps. `adopt_inputs`: `example_x` / `example_y` themselves become the static buffers (a loader that always yields the same tensors then needs
+    no copy). All per-step resources (accumulator arena, bf16 parameter shadow) live in a `StepContext` owned by this object. """
 
-    def __init__(self, model: torch.nn.Module, loss_fn: Callable, optimizer: FlatAdamW, example_x: torch.Tensor, example_y: torch.Tensor, warmup_iters: int = 3,
-                 preprocess: Optional[torch.nn.Module] = None, use_accumulator_arena: bool = True):
+    def __init__(self, model: torch.nn.Module, loss_fn: Union[Callable, 'OrderedDict[str, Callable]'], optimizer: FlatAdamW, example_x: torch.Tensor, example_y: torch.Tensor,
+                 warmup_iters: int = 3, preprocess: Optional[torch.nn.Module] = None, use_accumulator_arena: bool = True, restore_state: bool = False, adopt_inputs: bool = False):
         if not example_x.is_cuda:
             raise RuntimeError('deepcv_b200: GraphedTrainStep needs CUDA tensors')
-        self.model, self.loss_fn, self.optimizer, self.preprocess = model, loss_fn, optimizer, preprocess
-        self.static_x, self.static_y = example_x.clone(), example_y.clone()
+        self.model, self.optimizer, self.preprocess = model, optimizer, preprocess
+        self.losses = loss_fn if isinstance(loss_fn, dict) else OrderedDict([(MAIN_TRAINING_LOSS_NAME, loss_fn)])
+        self.static_x, self.static_y = (example_x, example_y) if adopt_inputs else (example_x.clone(), example_y.clone())
         n = example_x.shape[0]
         self.static_flip = self.static_crop = None
         self._host_flip = self._host_crop = None
@@ -288,28 +353,75 @@ class GraphedTrainStep:
             self._host_flip = torch.zeros(n, dtype=torch.uint8).pin_memory()
             self._host_crop = torch.full((n, 2), int(preprocess.pad), dtype=torch.int32).pin_memory()
         self.graph = torch.cuda.CUDAGraph()
+        self.static_losses: 'OrderedDict[str, torch.Tensor]' = OrderedDict()
         self.static_loss = None
+        inner = model.module if isinstance(model, DataParallelModel) else model
+        self.flat: Optional[FlatParameters] = getattr(optimizer, '_flat', None) or getattr(inner, '_flat_parameters', None)
+        if isinstance(optimizer, FlatAdamW) and optimizer._flat is None and self.flat is not None:
+            optimizer.attach(self.flat)   # a flattened model's fused layers write into the flat buffer: the optimizer must step that buffer
+        if self.flat is not None and not isinstance(optimizer, FlatAdamW):
+            raise RuntimeError('deepcv_b200: the model\'s parameters live in flat buffers (flatten_parameters / DataParallelModel); a captured step needs `FlatAdamW`')
+        snapshot = self._snapshot(inner) if restore_state else None
         model.train()
+        if preprocess is not None:
+            preprocess.train()
         optimizer.set_lr_device()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         # One zeroed arena per step for all atomically-filled accumulators + ONE memset of the flat gradient buffer, instead of a memset node in front of
         # every kernel that accumulates (ops.AccumulatorArena). The last warm-up step runs in counting mode to size the arena.
         self.use_arena = use_accumulator_arena and os.environ.get('DCV_NO_ARENA') is None
-        self.arena = ops.AccumulatorArena() if self.use_arena else None   # owned by this object: the graph replays write into its buffer
-        # one bf16 cast of the flat parameter buffer per step instead of one per convolution (ops.set_param_shadows); bf16 steps only
-        flat_p = getattr(optimizer, '_flat', None)
+        self.ctx = ops.StepContext(ops.AccumulatorArena() if self.use_arena else None)   # owned by this object: the graph replays write into its buffers
+        self.arena = self.ctx.arena
+        # one bf16 cast of the flat parameter buffer per step instead of one per convolution; bf16 steps only
         op_dtype = getattr(preprocess, 'dtype', None) if preprocess is not None else (example_x.dtype if example_x.is_floating_point() else None)
         self._shadow = None
-        if flat_p is not None and op_dtype == torch.bfloat16 and os.environ.get('DCV_NO_SHADOW') is None:
-            self._shadow = torch.empty(flat_p.flat_params.numel(), dtype=torch.bfloat16, device=example_x.device)
-            ops.set_param_shadows([(flat_p.flat_params, self._shadow)])
+        if self.flat is not None and op_dtype == torch.bfloat16 and os.environ.get('DCV_NO_SHADOW') is None:
+            self._shadow = torch.empty(self.flat.flat_params.numel(), dtype=torch.bfloat16, device=example_x.device)
+            self.ctx.shadows = [(self.flat.flat_params, self._shadow)]
+        layers = _fused_layers(inner)
+        previous = [l._step_ctx for l in layers]
+        for l in layers:
+            l._step_ctx = self.ctx
         try:
-            self._capture(side, warmup_iters, example_x, optimizer)
+            self._capture(side, max(1, warmup_iters), example_x)
         finally:
-            ops.set_param_shadows([])   # eager forwards outside the captured step cast per layer: they must never see one-step-old shadows
+            # eager forwards outside the captured step allocate / cast per layer: they must never see this step's arena or one-step-old shadows
+            for l, prev in zip(layers, previous):
+                l._step_ctx = prev
+            if self.flat is not None:
+                self.flat.zeroed_by_step = False
+        if snapshot is not None:
+            self._restore(inner, snapshot)
 
-    def _capture(self, side, warmup_iters, example_x, optimizer):
+    # ---- state rewind (in place: the captured graph holds the addresses)
+    def _snapshot(self, inner):
+        opt = self.optimizer
+        st = opt.state.get('flat') if isinstance(opt, FlatAdamW) else None
+        return dict(params=[p.detach().clone() for p in inner.parameters()], buffers=[b.detach().clone() for b in inner.buffers()],
+                    moments=None if not st else (st['exp_avg'].clone(), st['exp_avg_sq'].clone()),
+                    step=int(opt._dev_state['step'].item()) if getattr(opt, '_dev_state', None) is not None else 0,
+                    rng=None if self.preprocess is None else self.preprocess.generator.get_state())
+
+    def _restore(self, inner, snap):
+        with torch.no_grad():
+            for p, v in zip(inner.parameters(), snap['params']):
+                p.copy_(v)
+            for b, v in zip(inner.buffers(), snap['buffers']):
+                b.copy_(v)
+            opt = self.optimizer
+            st = opt.state.get('flat') if isinstance(opt, FlatAdamW) else None
+            if st:
+                if snap['moments'] is None:
+                    st['exp_avg'].zero_(), st['exp_avg_sq'].zero_()
+                else:
+                    st['exp_avg'].copy_(snap['moments'][0]), st['exp_avg_sq'].copy_(snap['moments'][1])
+            if getattr(opt, '_dev_state', None) is not None:
+                opt._dev_state['step'].fill_(snap['step'])
+        if snap['rng'] is not None:
+            self.preprocess.generator.set_state(snap['rng'])
+
+    def _capture(self, side, warmup_iters, example_x):
         with torch.cuda.stream(side):
             for i in range(warmup_iters):
                 if self.use_arena and i == warmup_iters - 1:
@@ -321,22 +433,26 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         with torch.cuda.graph(self.graph):
             if self.use_arena:
-                flat = getattr(optimizer, '_flat', None)
-                self.arena.begin_step(extra_zero=[flat.flat_grads] if flat is not None else [])
+                self.arena.begin_step(extra_zero=[self.flat.flat_grads] if self.flat is not None else [])
+                if self.flat is not None:
+                    self.flat.zeroed_by_step = True
             try:
-                self.static_loss = self._eager_step()
+                self._eager_step()
             finally:
                 if self.use_arena:
                     self.arena.end_step()
+                if self.flat is not None:
+                    self.flat.zeroed_by_step = False
 
     def _eager_step(self) -> torch.Tensor:
-        if self._shadow is not None:
-            ops.refresh_param_shadows()
+        self.ctx.refresh_shadows()
         x = self.static_x
         if self.preprocess is not None:
             x = self.preprocess(x, flip=self.static_flip, crop_yx=self.static_crop)
         y_pred = self.model(x)
-        loss = self.loss_fn(y_pred, self.static_y)
+        for name, fn in self.losses.items():
+            self.static_losses[name] = fn(y_pred, self.static_y)
+        loss = self.static_loss = self.static_losses[MAIN_TRAINING_LOSS_NAME]
         self.optimizer.zero_grad()
         loss.backward()
         if isinstance(self.model, DataParallelModel):
@@ -345,8 +461,10 @@ class GraphedTrainStep:
         return loss
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        self.static_x.copy_(x, non_blocking=True)
-        self.static_y.copy_(y, non_blocking=True)
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        if y.data_ptr() != self.static_y.data_ptr():
+            self.static_y.copy_(y, non_blocking=True)
         if self.preprocess is not None:
             flip, crop = self.preprocess.draw(x.shape[0])
             if flip is not None:
@@ -359,49 +477,236 @@ class GraphedTrainStep:
         return self.static_loss
 
 
+# ------------------------------------------------------------------------------------------------------------------------------
+# Input pipeline (reference: DataLoader + `dataloader_prefetch_batches`, ignite_training.py:211-218, meta/data/datasets.py:76-115)
+
+class DeviceDataLoader:
+    """ The whole dataset resident in HBM (uint8 H x W x C images when the recipe is `FusedPreprocess`, else whatever the per-sample transforms
+    produce) and batches assembled on the device: per epoch ONE host -> device copy of the sampler's index list, per batch ONE launch of the
+    row-gather kernel (`dcv_gather_rows`) per tensor, writing into buffers that never move — a captured training step adopts them as its static
+    inputs, so no per-sample copy, no collate, no pinned staging, no per-batch copy. Sampling follows `torch.utils.data`: a host-side
+    `randperm` (seeded generator) when `shuffle`, `DistributedSampler` sharding (pad to a multiple of the world size, rank-strided) when
+    `world_size > 1`, `drop_last` semantics as in `DataLoader`. """
+
+    def __init__(self, dataset: Dataset, batch_size: int, device, shuffle: bool = False, drop_last: bool = False, seed: int = 0, rank: int = 0, world_size: int = 1,
+                 max_resident_bytes: int = 32 << 30):
+        self.device, self.batch_size, self.shuffle, self.drop_last = torch.device(device), int(batch_size), bool(shuffle), bool(drop_last)
+        self.rank, self.world_size, self.seed, self.epoch = int(rank), int(world_size), int(seed), 0
+        first = dataset[0]
+        if not isinstance(first, tuple):
+            raise TypeError('DeviceDataLoader expects a dataset of (input, target, ...) tuples')
+        n = len(dataset)
+        columns = [[] for _ in first]
+        nbytes = sum(torch.as_tensor(v).numel() * torch.as_tensor(v).element_size() for v in first) * n
+        if nbytes > max_resident_bytes:
+            raise MemoryError(f'deepcv_b200: dataset of {nbytes / 2**30:.1f} GiB exceeds `max_resident_bytes` ({max_resident_bytes / 2**30:.1f} GiB)')
+        for i in range(n):
+            for col, v in zip(columns, dataset[i]):
+                col.append(torch.as_tensor(v))
+        self.columns = [torch.stack(col).contiguous().to(self.device) for col in columns]      # one H2D copy per column, once
+        self.n = n
+        self._batch_bufs = [torch.empty((self.batch_size, *c.shape[1:]), dtype=c.dtype, device=self.device) for c in self.columns]
+        self._err = torch.zeros((), dtype=torch.int32, device=self.device)
+        self._idx_dev = None
+
+    def set_epoch(self, epoch: int):
+        self.epoch = int(epoch)
+
+    def _indices(self) -> torch.Tensor:
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            idx = torch.randperm(self.n, generator=g)
+        else:
+            idx = torch.arange(self.n)
+        if self.world_size > 1:   # DistributedSampler: pad by wrapping around, then rank-strided shards
+            total = (self.n + self.world_size - 1) // self.world_size * self.world_size
+            if total > self.n:
+                idx = torch.cat([idx, idx[: total - self.n]])
+            idx = idx[self.rank:total:self.world_size]
+        return idx.contiguous()
+
+    def __len__(self) -> int:
+        per_rank = (self.n + self.world_size - 1) // self.world_size
+        return per_rank // self.batch_size if self.drop_last else (per_rank + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        idx = self._indices()
+        self._idx_dev = idx.pin_memory().to(self.device, non_blocking=True)
+        st = ops._stream()
+        for b in range(len(self)):
+            lo = b * self.batch_size
+            cnt = min(self.batch_size, idx.numel() - lo)
+            out = []
+            for col, buf in zip(self.columns, self._batch_bufs):
+                row_bytes = col[0].numel() * col.element_size()
+                dst = buf if cnt == self.batch_size else buf[:cnt]
+                check(lib.dcv_gather_rows(ops._ptr(col), ctypes.c_void_p(self._idx_dev.data_ptr() + lo * 8), ops._ptr(dst), cnt, self.n, row_bytes, ops._ptr(self._err), st), 'gather_rows')
+                out.append(dst)
+            yield tuple(out)
+        if int(self._err.item()) != 0:
+            raise IndexError('DeviceDataLoader: a sampler index was outside the dataset')
+
+
+def _find_fused_preprocess(dataset) -> Optional[torch.nn.Module]:
+    """ The `FusedPreprocess` of a `PreprocessedDataset` built from a fused recipe (its per-sample call keeps images uint8; the arithmetic runs per
+    batch on the device, at the top of the step). """
+    from .data.preprocess import FusedPreprocess
+    tf = getattr(dataset, '_img_transform', None)
+    for t in ([tf] if isinstance(tf, FusedPreprocess) else list(getattr(tf, 'transforms', []) or [])):
+        if isinstance(t, FusedPreprocess):
+            return t
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Evaluation (reference: `create_supervised_evaluator` runs every `validate_every_epochs` epochs and at the end, :288-307)
+
+class GraphedEvalStep:
+    """ Forward in eval mode (BatchNorm on running statistics, no autograd tape) + classification metrics, captured once per batch shape and replayed:
+    the accumulators `acc3` = (sum of cross entropies, correct predictions, rows) stay on the device until `result()`. """
+
+    def __init__(self, model: torch.nn.Module, example_x: torch.Tensor, example_y: torch.Tensor, preprocess: Optional[torch.nn.Module] = None, adopt_inputs: bool = False):
+        self.model, self.preprocess = model, preprocess
+        self.static_x, self.static_y = (example_x, example_y) if adopt_inputs else (example_x.clone(), example_y.clone())
+        self.acc3 = torch.zeros(3, dtype=torch.float32, device=example_x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+        self.acc3.zero_()
+
+    def _eager(self):
+        was_training = self.model.training
+        self.model.eval()
+        if self.preprocess is not None:
+            self.preprocess.eval()
+        try:
+            with torch.no_grad():
+                x = self.static_x if self.preprocess is None else self.preprocess(self.static_x)
+                logits = self.model(x)
+                logits = ops._cast_raw(logits.contiguous(), torch.float32)
+                check(lib.dcv_classification_metrics(ops._ptr(logits), ops._ptr(self.static_y), ops._ptr(self.acc3), logits.shape[0], logits.shape[1], ops._stream()), 'classification_metrics')
+        finally:
+            self.model.train(was_training)
+
+    def step(self, x, y):
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        if y.data_ptr() != self.static_y.data_ptr():
+            self.static_y.copy_(y, non_blocking=True)
+        self.graph.replay()
+
+    def result(self, reset: bool = True) -> Dict[str, float]:
+        loss_sum, correct, rows = self.acc3.tolist()
+        if reset:
+            self.acc3.zero_()
+        return {'loss': loss_sum / max(rows, 1.), 'accuracy': correct / max(rows, 1.), 'samples': int(rows)}
+
+
+def evaluate(model: torch.nn.Module, data: Iterable, device, preprocess: Optional[torch.nn.Module] = None, runners: Optional[dict] = None) -> Dict[str, float]:
+    """ Loss (cross entropy) and accuracy of a classifier over `data` (batches of (x, y)), the metrics the reference's evaluators compute. """
+    runners = {} if runners is None else runners
+    inner = model.module if isinstance(model, DataParallelModel) else model
+    total = {'loss': 0., 'accuracy': 0., 'samples': 0}
+    for batch in data:
+        x, y = _move_batch(batch, device)
+        key = (tuple(x.shape), x.dtype)
+        runner = runners.get(key)
+        if runner is None:
+            runner = runners[key] = GraphedEvalStep(inner, x, y, preprocess=preprocess)
+        runner.step(x, y)
+    for runner in runners.values():
+        r = runner.result()
+        total['loss'] += r['loss'] * r['samples']; total['accuracy'] += r['accuracy'] * r['samples']; total['samples'] += r['samples']
+    n = max(total['samples'], 1)
+    return {'loss': total['loss'] / n, 'accuracy': total['accuracy'] / n, 'samples': total['samples']}
+
+
 def train(hp: HYPERPARAMS_T, model: torch.nn.Module, losses, datasets: Dict[str, Dataset], opt: Type[torch.optim.Optimizer] = FlatAdamW, backend_conf: BackendConfig = None,
           loss_weights=None, metrics: Dict[str, Callable] = None, callbacks_handler=None, nni_compression_pruner=None) -> Tuple[Dict[str, float], State]:
     """ Training procedure (reference :178-370, without the bookkeeping handlers). `datasets` maps 'trainset' (and optionally 'validset' /
-    'testset') to datasets yielding `(x, y)`; returns (last batch losses, engine state). """
+    'testset') to datasets yielding `(x, y)`; returns (validation metrics — the last batch losses when there is no validation set —, engine state).
+    On a CUDA device the datasets are made resident in HBM and batched by `DeviceDataLoader` (hp `device_resident_dataset`, default True; falls back
+    to `torch.utils.data.DataLoader` when a dataset exceeds hp `max_resident_bytes`), the step is CUDA-graph replayed when `opt` is `FlatAdamW`, and
+    the validation set is evaluated every `validate_every_epochs` epochs and at the end with batches 32 times the training batch (:214). """
     TRAINING_HP_DEFAULTS = {'optimizer_opts': ..., 'epochs': ..., 'batch_size': ..., 'scheduler': None, 'output_path': Path.cwd() / 'data/04_training/',
                             'log_output_dir_to_mlflow': True, 'validate_every_epochs': 1, 'save_every_iters': 1000, 'log_grads_every_iters': -1, 'log_progress_every_iters': 100,
                             'seed': None, 'prefetch_batches': True, 'resume_from': '', 'crash_iteration': -1, 'deterministic_cudnn': False, 'use_sync_batch_norm': False,
-                            'num_workers': 0}
+                            'num_workers': 0, 'device_resident_dataset': True, 'max_resident_bytes': 32 << 30, 'cuda_graph': None}
     backend_conf = backend_conf if backend_conf is not None else BackendConfig()
     hp, _ = to_hyperparameters(hp, TRAINING_HP_DEFAULTS, raise_if_missing=True)
     device = backend_conf.device
+    seed = 0 if hp['seed'] is None else int(hp['seed'])
     if hp['seed'] is not None:
         torch.manual_seed(backend_conf.rank + hp['seed'])  # a different seed per worker (reference :208)
 
-    trainset = datasets['trainset'] if isinstance(datasets, dict) else datasets[0]
-    sampler = torch.utils.data.distributed.DistributedSampler(trainset) if (backend_conf.distributed and dist.is_initialized()) else None
-    train_loader = DataLoader(trainset, batch_size=hp['batch_size'], shuffle=sampler is None, sampler=sampler, num_workers=hp['num_workers'], pin_memory=backend_conf.is_cuda, drop_last=True)
-
+    named = dict(datasets) if isinstance(datasets, dict) else dict(zip(('trainset', 'validset', 'testset'), datasets))
+    trainset = named['trainset']
+    preprocess = _find_fused_preprocess(trainset)
+    if preprocess is not None:
+        preprocess = preprocess.to(device)
+    distributed = backend_conf.distributed and dist.is_available()
     model = model.to(device)
     model = _setup_distributed_training(device, backend_conf, model, use_sync_batch_norm=hp['use_sync_batch_norm'])
+    world, rank = (dist.get_world_size(), dist.get_rank()) if (distributed and dist.is_initialized()) else (1, 0)
+
+    def _loader(ds, batch_size, is_train):
+        if backend_conf.is_cuda and hp['device_resident_dataset']:
+            try:
+                return DeviceDataLoader(ds, batch_size, device, shuffle=is_train, drop_last=is_train, seed=seed, rank=rank if is_train else 0, world_size=world if is_train else 1,
+                                        max_resident_bytes=hp['max_resident_bytes'])
+            except MemoryError as e:
+                logging.warning(f'{e}; falling back to torch.utils.data.DataLoader')
+        sampler = torch.utils.data.distributed.DistributedSampler(ds) if (is_train and world > 1) else None
+        return DataLoader(ds, batch_size=batch_size, shuffle=is_train and sampler is None, sampler=sampler, num_workers=hp['num_workers'], pin_memory=backend_conf.is_cuda, drop_last=is_train)
+    train_loader = _loader(trainset, hp['batch_size'], True)
+    eval_sets = {n: ds for n, ds in named.items() if n != 'trainset' and ds is not None}
+
     losses = _setup_ignite_losses(losses, loss_weights=loss_weights, device=device)
     optimizer = opt(model.parameters(), **hp['optimizer_opts'])
+    inner = model.module if isinstance(model, DataParallelModel) else model
     if isinstance(optimizer, FlatAdamW):
-        flat = flatten_parameters(model.module if isinstance(model, DataParallelModel) else model)
-        optimizer.attach(flat)
-        if isinstance(model, DataParallelModel):
+        optimizer.attach(flatten_parameters(inner))
+        if isinstance(model, DataParallelModel):   # the optimizer kernel applies 1/world_size: no separate averaging pass
             optimizer.grad_scale = 1. / model.world_size
+            model.reducer.average_in_finish = False
     scheduler = None
     if hp['scheduler'] is not None:
         args_to_eval = hp['scheduler']['eval_args'] if 'eval_args' in hp['scheduler'] else {}
         scheduler_kwargs = {n: eval(v, {'hp': hp, 'iterations': len(train_loader)}) if n in args_to_eval else v for n, v in hp['scheduler']['kwargs'].items()}
         scheduler = hp['scheduler']['type'](optimizer=optimizer, **scheduler_kwargs)
 
-    trainer = Engine(make_process_function(hp, device, model, losses, optimizer))
+    trainer = Engine(make_process_function(hp, device, model, losses, optimizer, preprocess=preprocess, cuda_graph=hp['cuda_graph']))
     if scheduler is not None:
         trainer.add_event_handler(Events.ITERATION_STARTED, scheduler)
-    if sampler is not None:
-        trainer.add_event_handler(Events.EPOCH_STARTED, lambda engine: sampler.set_epoch(engine.state.epoch))
+    if hasattr(train_loader, 'set_epoch'):
+        trainer.add_event_handler(Events.EPOCH_STARTED, lambda engine: train_loader.set_epoch(engine.state.epoch))
+    elif getattr(train_loader, 'sampler', None) is not None and hasattr(train_loader.sampler, 'set_epoch'):
+        trainer.add_event_handler(Events.EPOCH_STARTED, lambda engine: train_loader.sampler.set_epoch(engine.state.epoch))
     if hp['crash_iteration'] is not None and hp['crash_iteration'] >= 0:
         @trainer.on(Events.ITERATION_STARTED)
         def _(engine):
             if engine.state.iteration == hp['crash_iteration']:
                 raise Exception(f'STOP at iteration: {engine.state.iteration}')
 
+    eval_metrics: Dict[str, float] = {}
+    if eval_sets and backend_conf.is_cuda:
+        name0 = 'validset' if 'validset' in eval_sets else next(iter(eval_sets))
+        eval_loader = _loader(eval_sets[name0], hp['batch_size'] * 32, False)
+        eval_runners: dict = {}
+
+        def _run_validation(engine: Engine):
+            every = hp['validate_every_epochs']
+            if engine.state.epoch == engine.state.max_epochs or (every and engine.state.epoch % every == 0):
+                m = evaluate(model, eval_loader, device, preprocess=preprocess, runners=eval_runners)
+                eval_metrics.update({f'valid_{k}': v for k, v in m.items()})
+                engine.state.metrics.update(eval_metrics)
+        trainer.add_event_handler(Events.EPOCH_COMPLETED, _run_validation)
+
     state = trainer.run(train_loader, max_epochs=hp['epochs'])
-    return state.output, state
+    return (dict(eval_metrics) if eval_metrics else state.output), state

@@ -181,7 +181,8 @@ class FusedLayer(torch.nn.Sequential):
         super().__init__(*modules)
         self.preactivation = bool(preactivation)
         self.algo = ALGO_AUTO
-        self._grad_out: Optional[dict] = None  # filled by deepcv_b200.parallel when gradients live in flat buckets
+        self._grad_out: Optional[dict] = None  # filled by flat_params.FlatParameters when gradients live in flat buckets
+        self._step_ctx: Optional[ops.StepContext] = None  # set by the driver of a captured step (accumulator arena, parameter shadow)
         self._plan()
 
     def _plan(self):
@@ -240,14 +241,14 @@ class FusedLayer(torch.nn.Sequential):
             return self._meta_forward(x)
         op, bn, gn = self._op, self._bn, self._gn
         if isinstance(op, torch.nn.Linear):
-            return ops.linear_act(x, op.weight, op.bias, self._act, self._slope, grad_out=self._grad_out)
+            return ops.linear_act(x, op.weight, op.bias, self._act, self._slope, grad_out=self._grad_out, step_ctx=self._step_ctx)
         training = bn.training if bn is not None else self.training
         return ops.conv_block(x, op.weight, op.bias, op.stride, op.padding, op.dilation, self._act, self._slope, norm=self._norm_config(), training=training,
                               bn_weight=bn.weight if bn is not None else None, bn_bias=bn.bias if bn is not None else None,
                               running_mean=bn.running_mean if bn is not None else None, running_var=bn.running_var if bn is not None else None,
                               num_batches_tracked=bn.num_batches_tracked if bn is not None else None,
                               gn_weight=gn.weight if gn is not None else None, gn_bias=gn.bias if gn is not None else None,
-                              algo=self.algo, grad_out=self._grad_out)
+                              algo=self.algo, grad_out=self._grad_out, step_ctx=self._step_ctx)
 
 
 def layer(layer_op: torch.nn.Module, act_fn: Optional[Type[torch.nn.Module]], dropout_prob: float = None, preactivation: bool = False,

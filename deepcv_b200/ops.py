@@ -19,7 +19,7 @@ import torch
 from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, NormParams, check, lib)
 
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
-           'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count']
+           'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
 _DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
@@ -154,23 +154,19 @@ class NormConfig:
 class AccumulatorArena:
     """ One zeroed buffer per training step for every accumulator the kernels fill with atomics (per-(n,c) statistics, backward sums, bias / weight
     gradients that are not written straight into the flat gradient buffer): `begin_step` zeroes it (and any extra tensors, e.g. the flat gradient
-    buffer) with ONE memset each and tells the library not to zero accumulators itself (`dcv_set_accumulators_prezeroed`) — a CIFAR step otherwise
+    buffer) with ONE memset each; while it is active the accumulating entry points are called with `acc_prezeroed = 1` — a CIFAR step otherwise
     carries ~22 memset nodes of 2-3 us. Used by `GraphedTrainStep` around the captured step; outside `begin_step` .. `end_step` nothing changes.
     `measure()` .. `end_measure()` runs a step in counting mode to size the buffer. An allocation that does not fit raises (never a silent fallback).
-    One instance per captured step: the graph replays keep writing into `buf`. """
+    One instance per captured step: the graph replays keep writing into `buf`. Reached through the `StepContext` of the layers, never a global. """
 
     def __init__(self):
         self.buf, self.off, self.active, self.counting, self.need = None, 0, False, False, 0
 
     def measure(self):
-        global _CURRENT_ARENA
         self.counting, self.need = True, 0
-        _CURRENT_ARENA = self
 
     def end_measure(self, device) -> int:
-        global _CURRENT_ARENA
         self.counting = False
-        _CURRENT_ARENA = None
         if self.buf is None or self.buf.numel() < self.need or self.buf.device != device:
             self.buf = torch.empty((max(self.need, 256),), dtype=torch.uint8, device=device)
         return self.need
@@ -182,16 +178,10 @@ class AccumulatorArena:
         check(lib.dcv_fill_zero(_ptr(self.buf), self.buf.numel(), st), 'fill_zero(arena)')
         for t in extra_zero:
             check(lib.dcv_fill_zero(_ptr(t), t.numel() * t.element_size(), st), 'fill_zero(gradients)')
-        global _CURRENT_ARENA
         self.off, self.active = 0, True
-        _CURRENT_ARENA = self
-        lib.dcv_set_accumulators_prezeroed(1)
 
     def end_step(self):
-        global _CURRENT_ARENA
         self.active = False
-        _CURRENT_ARENA = None
-        lib.dcv_set_accumulators_prezeroed(0)
 
     def alloc(self, shape, device) -> torch.Tensor:
         numel = 1
@@ -209,16 +199,52 @@ class AccumulatorArena:
         return torch.empty(tuple(shape), dtype=torch.float32, device=device)
 
 
-# The arena of the step being measured / captured, if any. Each GraphedTrainStep owns its arena (the captured graph holds pointers into its buffer, so the
-# buffer must live exactly as long as the graph), hence no module-level instance.
-_CURRENT_ARENA: Optional[AccumulatorArena] = None
+class StepContext:
+    """ Per-step resources of ONE model's training step, handed to the fused layers by whoever drives the step (`GraphedTrainStep` sets
+    `FusedLayer._step_ctx` on the layers of its model for the duration of warm-up + capture): the accumulator arena and the low-precision
+    shadow of the flat parameter buffer. It travels as an argument through the autograd functions (forward thread and autograd's worker thread
+    see the same object), so two models, streams or capturing threads never share state — there is no module-level "current" anything. """
+
+    def __init__(self, arena: Optional[AccumulatorArena] = None):
+        self.arena = arena
+        self.shadows: List[Tuple[torch.Tensor, torch.Tensor]] = []   # (flat fp32 parameter buffer, same-length buffer of the operand dtype)
+
+    @property
+    def prezeroed(self) -> int:
+        """ 1 iff accumulators come from the arena that the step zeroes up front (and so does the flat gradient buffer). """
+        return int(self.arena is not None and self.arena.active)
+
+    def acc_empty(self, shape, device) -> torch.Tensor:
+        if self.arena is not None:
+            return self.arena.alloc(shape, device)
+        return torch.empty(tuple(int(d) for d in shape), dtype=torch.float32, device=device)
+
+    def refresh_shadows(self) -> None:
+        """ ONE cast kernel per step instead of one per convolution. """
+        for src, dst in self.shadows:
+            check(lib.dcv_cast(_ptr(src), _dt(src), _ptr(dst), _dt(dst), src.numel(), _stream()), 'cast(flat parameters)')
+
+    def shadow_view(self, weight: torch.Tensor, dtype: torch.dtype) -> Optional[torch.Tensor]:
+        for src, dst in self.shadows:
+            if dst.dtype != dtype or weight.dtype != src.dtype or weight.device != src.device:
+                continue
+            off = weight.data_ptr() - src.data_ptr()
+            if 0 <= off and off + weight.numel() * 4 <= src.numel() * 4 and off % 4 == 0:
+                k, c, r, s_ = weight.shape
+                return dst[off // 4: off // 4 + weight.numel()].view(k, r, s_, c).permute(0, 3, 1, 2)
+        return None
 
 
-def _acc_empty(shape, device) -> torch.Tensor:
+_NO_CTX = StepContext()   # eager calls outside a driven step: plain allocations, entry points zero their accumulators, per-layer weight casts
+
+
+def _pz(sctx: Optional['StepContext']) -> int:
+    return 0 if sctx is None else sctx.prezeroed
+
+
+def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Tensor:
     """ fp32 accumulator buffer: from the step's zeroed arena when one is active, else plain (the filling entry point zeroes it). """
-    if _CURRENT_ARENA is not None:
-        return _CURRENT_ARENA.alloc(shape, device)
-    return torch.empty(tuple(int(d) for d in shape), dtype=torch.float32, device=device)
+    return (sctx or _NO_CTX).acc_empty(shape, device)
 
 
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
@@ -236,40 +262,14 @@ def _conv_shape(x: torch.Tensor, weight: torch.Tensor, stride, padding, dilation
     return ConvShape(n, h, w, c, k, r, s, stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], p, q)
 
 
-# Low-precision shadows of flat fp32 parameter buffers (meta/flat_params.py): ONE cast kernel per step instead of one per convolution. Only the captured
-# training step registers one (GraphedTrainStep refreshes it at the top of the step and unregisters after capture), so a forward that runs outside that
-# step can never see weights that are one optimizer update old.
-_PARAM_SHADOWS: List[Tuple[torch.Tensor, torch.Tensor]] = []
-
-
-def set_param_shadows(pairs) -> None:
-    """ pairs: [(flat fp32 parameter buffer, same-length buffer of the operand dtype)]; [] unregisters. """
-    _PARAM_SHADOWS[:] = list(pairs)
-
-
-def refresh_param_shadows() -> None:
-    for src, dst in _PARAM_SHADOWS:
-        check(lib.dcv_cast(_ptr(src), _dt(src), _ptr(dst), _dt(dst), src.numel(), _stream()), 'cast(flat parameters)')
-
-
-def _shadow_view(weight: torch.Tensor, dtype: torch.dtype) -> Optional[torch.Tensor]:
-    for src, dst in _PARAM_SHADOWS:
-        if dst.dtype != dtype or weight.dtype != src.dtype or weight.device != src.device:
-            continue
-        off = weight.data_ptr() - src.data_ptr()
-        if 0 <= off and off + weight.numel() * 4 <= src.numel() * 4 and off % 4 == 0:
-            k, c, r, s_ = weight.shape
-            return dst[off // 4: off // 4 + weight.numel()].view(k, r, s_, c).permute(0, 3, 1, 2)
-    return None
-
-
-def _weight_operand(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """ fp32 OIHW parameter -> [K][R][S][C] tensor of the activation dtype (zero-copy when it already is one). """
+def _weight_operand(weight: torch.Tensor, dtype: torch.dtype, sctx: Optional[StepContext] = None) -> torch.Tensor:
+    """ fp32 OIHW parameter -> [K][R][S][C] tensor of the activation dtype (zero-copy when it already is one, or a view of the step's
+    low-precision shadow of the flat parameter buffer). """
     k, c, r, s = weight.shape
     if weight.permute(0, 2, 3, 1).is_contiguous():
         if weight.dtype == dtype:
             return weight
-        shadow = _shadow_view(weight, dtype) if _PARAM_SHADOWS else None
+        shadow = sctx.shadow_view(weight, dtype) if (sctx is not None and sctx.shadows) else None
         if shadow is not None:
             return shadow
         out = torch.empty((k, r, s, c), dtype=dtype, device=weight.device).permute(0, 3, 1, 2)
@@ -290,15 +290,16 @@ def _norm_params(cfg: NormConfig, n: int, c: int, hw: int, training: bool, bn_w,
 
 class _ConvBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out):
+    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx):
         _require_cuda(x, weight)
         shape = _conv_shape(x, weight, stride, padding, dilation)
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st = x.device, _stream()
         dt = _dt(x)
-        w_op = _weight_operand(weight, x.dtype)
+        pz = _pz(sctx)
+        w_op = _weight_operand(weight, x.dtype, sctx)
         y = empty_nhwc(n, k, p, q, x.dtype, dev)
-        stats = _acc_empty((n, k, 2), dev) if cfg.any else None
+        stats = _acc_empty((n, k, 2), dev, sctx) if cfg.any else None
         # Convolutions the implicit-GEMM tensor-core kernel cannot address directly (few input channels / strides: the 7x7 stride-2 stem) go
         # through an explicit im2col: conv(x, w) == 1x1 conv of col[n][p][q][kpad] with the weights zero-padded to [K][kpad].
         rsc = shape.r * shape.s * shape.c
@@ -319,17 +320,17 @@ class _ConvBlock(torch.autograd.Function):
             if gathered:
                 w_col = torch.empty((k, kpad_g), dtype=x.dtype, device=dev)
                 check(lib.dcv_gather_pack_weight(_ptr(w_op), _ptr(w_col), k, shape.r, sc, kpad_g, dt, st), 'gather_pack_weight')
-                check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), _ptr(x), _ptr(w_col), kpad_g, _ptr(bias), _ptr(y), _ptr(stats), act, slope, st), 'conv2d_fwd_gather')
+                check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), _ptr(x), _ptr(w_col), kpad_g, _ptr(bias), _ptr(y), _ptr(stats), act, slope, pz, st), 'conv2d_fwd_gather')
             else:
                 w_col = torch.empty((k, kpad), dtype=x.dtype, device=dev)
                 check(lib.dcv_fill_zero(_ptr(w_col), w_col.numel() * w_col.element_size(), st), 'fill_zero')
                 check(lib.dcv_copy_channels_in(_ptr(w_op), _ptr(w_col), k, rsc, kpad, 0, dt, st), 'copy_channels_in(weight)')
                 col = torch.empty((n, p, q, kpad), dtype=x.dtype, device=dev)
                 check(lib.dcv_im2col(ctypes.byref(shape), _ptr(x), _ptr(col), kpad, dt, st), 'im2col')
-                check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd(im2col)')
+                check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz, st), 'conv2d_fwd(im2col)')
                 x = col   # what the weight gradient needs; the data gradient only needs dy and the weights
         else:
-            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, st), 'conv2d_fwd')
+            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz, st), 'conv2d_fwd')
         saved = None
         out = y
         if cfg.any:
@@ -343,22 +344,25 @@ class _ConvBlock(torch.autograd.Function):
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
         # the fp32 master weight, when it already is [K][R][S][C] in memory: the data-gradient operand is packed straight from it in backward
         ctx.w_master = weight.detach() if (weight.dtype == torch.float32 and weight.permute(0, 2, 3, 1).is_contiguous()) else None
-        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape, gathered)
+        ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape, gathered, sctx)
         return out
 
     @staticmethod
     def backward(ctx, dz):
         x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv = ctx.saved_tensors
-        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape, gemm_shape, gathered = ctx.cfg
+        shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape, gemm_shape, gathered, sctx = ctx.cfg
+        pz = _pz(sctx)
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st, dt = y.device, _stream(), _dt(y)
         dz = as_nhwc(dz.detach(), y.dtype)
         f32 = dict(dtype=torch.float32, device=dev)
-        targets = grad_out or {}
+        # gradients go straight into the caller's bucket slices on the FIRST backward after `zero_grad`; a second backward through the same layer before the
+        # next `zero_grad` (weights shared between two calls, gradient accumulation) returns tensors instead, which autograd accumulates into `.grad`
+        targets = grad_out if (grad_out and not grad_out.get('_written', False)) else {}
         pqr = d_bn_w = d_bn_b = d_gn_w = d_gn_b = None
         if cfg.any:
-            s_nc = _acc_empty((n, k, 2), dev)
-            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, st), 'norm_bwd_reduce')
+            s_nc = _acc_empty((n, k, 2), dev, sctx)
+            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, pz, st), 'norm_bwd_reduce')
             pqr = torch.empty((n, k, 3), **f32)
             if cfg.use_bn and bn_w is not None:
                 d_bn_w, d_bn_b = targets.get('bn_w', None), targets.get('bn_b', None)
@@ -378,27 +382,27 @@ class _ConvBlock(torch.autograd.Function):
             dy = empty_nhwc(n, k, p, q, y.dtype, dev)
             if has_bias:
                 dbias = targets.get('bias', None)
-                dbias = _acc_empty((k,), dev) if dbias is None else dbias
-            check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, st), 'act_norm_bwd_apply')
+                dbias = _acc_empty((k,), dev, sctx) if dbias is None else dbias
+            check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, pz, st), 'act_norm_bwd_apply')
         dw = None
         if ctx.needs_input_grad[1]:
             dw = targets.get('weight', None)
             if dw is None:
-                dw = _acc_empty((k, shape.r, shape.s, shape.c), dev).permute(0, 3, 1, 2)
+                dw = _acc_empty((k, shape.r, shape.s, shape.c), dev, sctx).permute(0, 3, 1, 2)
             if gathered:                 # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
                 sc = shape.s * shape.c
                 kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
-                dw_col = _acc_empty((k, kpad_g), dev)
-                check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), kpad_g, st), 'conv2d_wgrad_gather')
+                dw_col = _acc_empty((k, kpad_g), dev, sctx)
+                check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), kpad_g, pz, st), 'conv2d_wgrad_gather')
                 check(lib.dcv_gather_unpack_wgrad(_ptr(dw_col), _ptr(dw), k, shape.r, sc, kpad_g, st), 'gather_unpack_wgrad')
             elif gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
-                dw_col = _acc_empty((k, gemm_shape.c), dev)
-                check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, st), 'conv2d_wgrad(im2col)')
+                dw_col = _acc_empty((k, gemm_shape.c), dev, sctx)
+                check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, pz, st), 'conv2d_wgrad(im2col)')
                 check(lib.dcv_copy_channels_out(_ptr(dw_col), _ptr(dw), k, gemm_shape.c, 0, shape.r * shape.s * shape.c, DCV_F32, st), 'copy_channels_out(dw)')
             else:
                 ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
                 ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
-                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, st), 'conv2d_wgrad')
+                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, pz, st), 'conv2d_wgrad')
         if _DEBUG_CAPTURE is not None:
             _DEBUG_CAPTURE.append(dict(wshape=wshape, dz=dz.clone(), y=y.clone(), dy=dy.clone(), pqr=None if pqr is None else pqr.clone(), saved=None if saved is None else saved.clone(), dz_ptr=dz.data_ptr(), y_ptr=y.data_ptr(), dy_ptr=dy.data_ptr(), x=x.clone(), dw=None if dw is None else dw.clone()))
         dx = None
@@ -415,21 +419,35 @@ class _ConvBlock(torch.autograd.Function):
 
         def ret(name, g):  # gradients written straight into a caller-provided bucket slice are not handed to autograd again
             return None if (g is None or name in targets) else g
+        _backward_done(grad_out, targets)
         return (dx, ret('weight', dw), ret('bias', dbias) if has_bias else None, ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b),
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def _backward_done(grad_out: Optional[dict], targets: dict) -> None:
+    """ End of a fused layer's backward: every kernel that writes this layer's parameter gradients has been enqueued on the current stream. Marks the
+    bucket slices as written and tells the data-parallel reducer (`flat_params.GradientBucketReducer`), which may now all-reduce a bucket whose last
+    producer this was. (Module full-backward hooks fire BEFORE the weight-gradient kernels of a layer whose input needs no gradient are enqueued.) """
+    if not grad_out:
+        return
+    if targets is grad_out:
+        grad_out['_written'] = True
+    done = grad_out.get('_done')
+    if done is not None:
+        done()
 
 
 def conv_block(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: Sequence[int], padding: Sequence[int], dilation: Sequence[int],
                act: int = ACT_NONE, slope: float = 0., norm: Optional[NormConfig] = None, training: bool = True,
                bn_weight=None, bn_bias=None, running_mean=None, running_var=None, num_batches_tracked=None, gn_weight=None, gn_bias=None,
-               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None) -> torch.Tensor:
+               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None) -> torch.Tensor:
     """ act(conv2d(x, weight) + bias) followed by the configured BatchNorm / GroupNorm, as one autograd node.
     `grad_out` optionally maps 'weight' / 'bias' / 'bn_w' / 'bn_b' / 'gn_w' / 'gn_b' to preallocated fp32 tensors (slices of a
     flat gradient bucket) that backward fills in place instead of returning new tensors. """
     x = as_nhwc(x)
     norm = norm if norm is not None else NormConfig()
     return _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
-                            tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out)
+                            tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -646,7 +664,7 @@ def flatten_nchw(x: torch.Tensor) -> torch.Tensor:
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, slope, grad_out):
+    def forward(ctx, x, weight, bias, act, slope, grad_out, sctx):
         _require_cuda(x, weight)
         m, k = x.shape
         n = weight.shape[0]
@@ -656,14 +674,14 @@ class _Linear(torch.autograd.Function):
         y = torch.empty((m, n), dtype=torch.float32, device=x.device)
         check(lib.dcv_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), m, n, k, act, slope, _dt(x), DCV_F32, _stream()), 'linear_fwd')
         ctx.save_for_backward(x, w, y)
-        ctx.cfg = (act, slope, bias is not None, grad_out)
+        ctx.cfg = (act, slope, bias is not None, grad_out, sctx)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
-        act, slope, has_bias, grad_out = ctx.cfg
-        targets = grad_out or {}
+        act, slope, has_bias, grad_out, sctx = ctx.cfg
+        targets = grad_out if (grad_out and not grad_out.get('_written', False)) else {}
         m, k = x.shape
         n = w.shape[0]
         dy = _cast_raw(dy.detach().contiguous(), torch.float32)
@@ -671,23 +689,25 @@ class _Linear(torch.autograd.Function):
         dx = torch.empty((m, k), dtype=x.dtype, device=x.device) if ctx.needs_input_grad[0] else None
         dw = targets.get('weight', None) if ctx.needs_input_grad[1] else None
         if dw is None and ctx.needs_input_grad[1]:
-            dw = _acc_empty((n, k), x.device)
+            dw = _acc_empty((n, k), x.device, sctx)
         db = None
         if has_bias:
             db = targets.get('bias', None)
-            db = _acc_empty((n,), x.device) if db is None else db
+            db = _acc_empty((n,), x.device, sctx) if db is None else db
         dpre = torch.empty((m, n), **f32)
-        check(lib.dcv_linear_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dpre), m, n, k, act, slope, _dt(x), DCV_F32, _stream()), 'linear_bwd')
-        return dx, (None if 'weight' in targets else dw), (None if ('bias' in targets or not has_bias) else db), None, None, None
+        check(lib.dcv_linear_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dpre), m, n, k, act, slope, _dt(x), DCV_F32, _pz(sctx), _stream()), 'linear_bwd')
+        _backward_done(grad_out, targets)
+        return dx, (None if 'weight' in targets else dw), (None if ('bias' in targets or not has_bias) else db), None, None, None, None
 
 
-def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE, slope: float = 0., grad_out: Optional[dict] = None) -> torch.Tensor:
+def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE, slope: float = 0., grad_out: Optional[dict] = None,
+               step_ctx: Optional[StepContext] = None) -> torch.Tensor:
     """ act(x @ weight.T + bias) with fp32 output (logits / losses stay fp32 whatever the activation dtype). """
     if x.dim() != 2:
         x = flatten_nchw(x) if x.dim() == 4 else x.reshape(x.shape[0], -1)
     if not x.is_contiguous():
         x = x.contiguous()
-    return _Linear.apply(x, weight, bias, int(act), float(slope), grad_out)
+    return _Linear.apply(x, weight, bias, int(act), float(slope), grad_out, step_ctx)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------

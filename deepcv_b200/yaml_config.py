@@ -13,7 +13,7 @@ from typing import Any, Dict, Union
 
 import yaml
 
-__all__ = ['load_parameters', 'loads_parameters', 'UnresolvedPythonName', 'PYTHON_NAME_SHIMS', 'find_model_spec']
+__all__ = ['load_parameters', 'loads_parameters', 'UnresolvedPythonName', 'PYTHON_NAME_SHIMS', 'find_model_spec', 'benchmark_model_spec']
 
 _PY_NAME_PREFIX = 'tag:yaml.org,2002:python/name:'
 _PY_OBJECT_PREFIX = 'tag:yaml.org,2002:python/object:'
@@ -112,3 +112,17 @@ def find_model_spec(parameters: Dict[str, Any], model_name: str) -> Dict[str, An
         if model_name in entry:
             return entry[model_name]
     raise KeyError(f'Error: no model named "{model_name}" under `models:` (found: {[next(iter(e)) for e in parameters["models"]]})')
+
+
+def benchmark_model_spec(path: Union[str, Path], model_name: str, out_features: int = None) -> Dict[str, Any]:
+    """ The hp dict of `model_name` from a `parameters.yml`-style file, as the benchmark configs use it (note iii):
+    a private copy with `spectral_norm: null` — `conf/base/parameters.yml:83` sets it and `base_module.py:109-111` then applies
+    `torch.nn.utils.spectral_norm` to a container without a `weight`, which raises — and, optionally, the head's `out_features`
+    (the reference deduces it from the dataset's classes, `classification/image.py:44-50`). """
+    import copy
+    hp = dict(find_model_spec(load_parameters(path), model_name))
+    hp['architecture'] = copy.deepcopy(hp['architecture'])
+    hp['spectral_norm'] = None
+    if out_features is not None:
+        hp['architecture'][-1]['fully_connected']['out_features'] = int(out_features)
+    return hp

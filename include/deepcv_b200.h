@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DCV_ABI_VERSION 1
+#define DCV_ABI_VERSION 2
 
 enum dcv_dtype { DCV_F32 = 0, DCV_BF16 = 1 };
 enum dcv_act { DCV_ACT_NONE = 0, DCV_ACT_RELU = 1, DCV_ACT_LEAKY_RELU = 2, DCV_ACT_SIGMOID = 3 };
@@ -44,10 +44,9 @@ const char* dcv_last_error(void);
 /* 0 iff the current CUDA device exists and is compute capability 10.x (B200). */
 int dcv_device_check(void);
 /* Accumulator outputs (statistics, sums and gradients that the kernels fill with atomics: stats_nc, s_nc, dbias_c, dw, dw_col, db) are zeroed by the
- * entry point that fills them unless the caller has declared, with on != 0, that it zeroes all of them itself (one memset per step instead of one per
- * kernel; see deepcv_b200/ops.py AccumulatorArena). Process-wide (the training loop launches from two threads: forward and autograd's). Returns the
- * previous setting. */
-int dcv_set_accumulators_prezeroed(int on);
+ * entry point that fills them unless the caller passes `acc_prezeroed` != 0: it then guarantees that it has zeroed them itself on the same stream (one
+ * memset per step instead of one per kernel; see deepcv_b200/ops.py AccumulatorArena). The flag travels with each call: there is no library-wide state
+ * besides the launch counter and the thread-local error string. */
 /* Number of kernel launches issued through this library since load (for bench.py's `gpu_launches`). */
 uint64_t dcv_launch_count(void);
 
@@ -77,6 +76,10 @@ int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, i
  * then the 1x1 convolution of `col` with the weights padded to [K][kpad]. */
 int dcv_im2col(const dcv_conv_shape* shape, const void* x, void* col, int kpad, int dtype, void* stream);
 int dcv_fill_zero(void* dst, size_t bytes, void* stream);
+/* Batch assembly of the device-resident input pipeline (replaces the DataLoader + collate of meta/ignite_training.py:211-218 and the prefetcher of
+ * meta/data/datasets.py:76-115): dst row j = src row idx[j] for j < n; rows of `row_bytes` (a multiple of 4; 16-byte multiples take the vector path) bytes. An index outside [0, n_src) copies
+ * nothing and sets *err_flag (device int, may be NULL) to 1. */
+int dcv_gather_rows(const void* src, const int64_t* idx, void* dst, int n, long long n_src, size_t row_bytes, int* err_flag, void* stream);
 
 /* ---- convolution (torch.nn.Conv2d built at meta/submodule_creators.py:251, run at meta/nn.py:553) ---------------- */
 /* 1 iff DCV_ALGO_AUTO would run `op` (0 = forward, 1 = data gradient, 2 = weight gradient) of this shape / dtype on the tcgen05 kernels
@@ -92,20 +95,20 @@ int dcv_conv2d_gather_supported(const dcv_conv_shape* shape, const void* x, int 
 int dcv_gather_pack_weight(const void* w_krsc, void* w_col, int k, int r, int sc, int kpad, int dtype, void* stream);
 int dcv_gather_unpack_wgrad(const float* dw_col, float* dw_krsc, int k, int r, int sc, int kpad, void* stream);
 int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc,
-                          int act, float slope, void* stream);
+                          int act, float slope, int acc_prezeroed, void* stream);
 /* dw_col[K][kpad] (fp32, gather K order, overwritten) = sum over pixels of dy * im2col(x); unpack with dcv_gather_unpack_wgrad. */
-int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, void* stream);
+int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, int acc_prezeroed, void* stream);
 /* y = act(conv(x, w) + bias); if stats_nc != NULL also accumulates per-(image, channel) sum(y) and sum(y*y) of the
  * values written to y into stats_nc[n][k][2] (fp32, overwritten). bias may be NULL. */
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,
-                   int act, float slope, int dtype, int algo, void* stream);
+                   int act, float slope, int dtype, int algo, int acc_prezeroed, void* stream);
 /* dx[n][h][w][c] = sum_{k,r,s} dy[n][p][q][k] * w[k][r][s][c]; `w` as in fwd, `wt` the transpose_flip packing (may be
  * NULL for the direct algorithm). */
 int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w, const void* wt, void* dx, int dtype, int algo, void* stream);
 /* dw[k][r][s][c] (fp32) = sum_{n,p,q} dy[n][p][q][k] * x[n][..][..][c]. dw is overwritten. `workspace` (fp32, at least
  * dcv_conv2d_wgrad_workspace(shape) bytes, may be NULL when that is 0) is scratch for split accumulation. */
 size_t dcv_conv2d_wgrad_workspace(const dcv_conv_shape* shape, int dtype, int algo);
-int dcv_conv2d_wgrad(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, void* workspace, int dtype, int algo, void* stream);
+int dcv_conv2d_wgrad(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, void* workspace, int dtype, int algo, int acc_prezeroed, void* stream);
 
 /* ---- normalisation (BatchNorm2d / GroupNorm after the activation: meta/nn.py:448-516,553; parameters.yml:10,82) ---
  * Any {BatchNorm, GroupNorm} stack applied to y collapses to one affine per (image, channel): z = A[n][c]*y + B[n][c],
@@ -123,7 +126,7 @@ typedef struct dcv_norm_params {
 } dcv_norm_params;
 
 /* sum(y), sum(y*y) per (image, channel) -> stats_nc[n][c][2] (overwritten). For tensors whose producer did not fuse it. */
-int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dtype, void* stream);
+int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dtype, int acc_prezeroed, void* stream);
 /* stats_nc -> ab_nc[n][c][2] (A, B) and `saved` (fp32, dcv_norm_saved_floats(n,c,groups) floats: BN mean/rstd [c][2],
  * BN alpha/beta [c][2], GN mean/rstd [n][groups][2]); updates the running statistics when bn_training. */
 size_t dcv_norm_saved_floats(int n, int c, int groups);
@@ -131,7 +134,7 @@ int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, flo
 /* z = A*y + B. */
 int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw, int c, int dtype, void* stream);
 /* s_nc[n][c][2] = { sum(dz), sum(dz*y) } (overwritten). */
-int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, void* stream);
+int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, int acc_prezeroed, void* stream);
 /* -> pqr_nc[n][c][3] with dy_pre_activation = P*dz + Q*y + R, plus parameter gradients (any may be NULL; overwritten).
  * `saved` is the forward's buffer; its trailing scratch region is written. */
 int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
@@ -140,7 +143,7 @@ int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, con
  * dbias_c[c] (fp32, overwritten). `y` is the activation OUTPUT (ReLU / LeakyReLU / Sigmoid / none are recoverable
  * from it). */
 int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
-                           int n, int hw, int c, int dtype, void* stream);
+                           int n, int hw, int c, int dtype, int acc_prezeroed, void* stream);
 
 /* ---- pooling / links (meta/submodule_creators.py:163-176, 272-332; meta/nn.py:416, 665-676) --------------------- */
 /* AvgPool2d(kernel, stride), no padding, floor output size. */
@@ -162,11 +165,16 @@ int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, in
 /* dpre = act'(y)*dy; dx = dpre @ w (x_dtype, may be NULL); dw = dpre^T @ x, db = sum_m dpre (fp32, overwritten).
  * dpre_ws: fp32 [m][n] scratch. */
 int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy, void* dx, float* dw, float* db, float* dpre_ws,
-                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, void* stream);
+                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, void* stream);
 
 /* ---- loss / optimiser (classification/image.py:70-71) ------------------------------------------------------------ */
-/* CrossEntropyLoss(reduction='mean') over logits[m][n] (fp32) and int64 targets: loss[0] and dlogits = (softmax - onehot)/m. */
+/* CrossEntropyLoss(reduction='mean') over logits[m][n] (fp32) and int64 targets: loss[0] and dlogits = (softmax - onehot)/m_valid. Rows whose target is
+ * -100 (torch's default ignore_index) are skipped and the mean runs over the others; any other target outside [0, n) makes the loss NaN. */
 int dcv_softmax_ce(const float* logits, const int64_t* target, float* loss, float* dlogits, int m, int n, void* stream);
+/* Evaluation metrics of a classifier (the `create_supervised_evaluator` metrics of meta/ignite_training.py:288-307: loss + accuracy), ACCUMULATED into
+ * acc3 (device float[3], zeroed by the caller before the first batch): acc3[0] += sum of per-row cross entropies, acc3[1] += rows whose argmax (lowest
+ * index on ties) equals the target, acc3[2] += rows counted (targets equal to -100 are skipped). */
+int dcv_classification_metrics(const float* logits, const int64_t* target, float* acc3, int m, int n, void* stream);
 /* dst[i] = src[i] * (*scale_dev): chain rule through the loss with the upstream gradient left on the device (no host sync). */
 int dcv_scale_by_device_scalar(const float* src, const float* scale_dev, float* dst, size_t count, void* stream);
 /* AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, amsgrad=False). `step_dev` is a device int32 holding the

@@ -116,11 +116,9 @@ def torchvision_preprocess() -> Dict[str, torch.Tensor]:
 
 
 def oracle_net(model_yaml: str, model_name: str, input_shape, batch: int, classes: int, seed: int = 563454) -> Dict[str, Any]:
-    from deepcv_b200.yaml_config import find_model_spec, load_parameters
+    from deepcv_b200.yaml_config import benchmark_model_spec
     from oracle.deepcv_oracle import OracleDeepcvModule, train_step
-    hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / model_yaml), model_name))
-    hp['architecture'] = copy.deepcopy(hp['architecture'])
-    hp['architecture'][-1]['fully_connected']['out_features'] = classes
+    hp = benchmark_model_spec(ROOT / 'conf' / 'base' / model_yaml, model_name, out_features=classes)
     torch.manual_seed(seed)
     model = OracleDeepcvModule(input_shape, hp)
     # non-trivial affine parameters everywhere (GroupNorm / biases start at 1 / 0): parity must not hide behind zeros

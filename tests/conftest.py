@@ -20,9 +20,5 @@ def golden_dir():
 
 @pytest.fixture(scope='session')
 def default_hp():
-    import copy
-    from deepcv_b200.yaml_config import find_model_spec, load_parameters
-    hp = dict(find_model_spec(load_parameters(ROOT / 'conf' / 'base' / 'parameters.yml'), 'image_classifier'))
-    hp['architecture'] = copy.deepcopy(hp['architecture'])
-    hp['architecture'][-1]['fully_connected']['out_features'] = 10
-    return hp
+    from deepcv_b200.yaml_config import benchmark_model_spec
+    return benchmark_model_spec(ROOT / 'conf' / 'base' / 'parameters.yml', 'image_classifier', out_features=10)

@@ -1,6 +1,7 @@
 """ World-size-2 data-parallel host logic on CPU (gloo): flat gradient buckets, bucket partition in reverse parameter order, SUM all-reduce of every
-bucket exactly once per step (hook-driven and `finish()` paths), per-rank seeds / DistributedSampler sharding. The CUDA kernels are not involved:
-gradients are written into the flat buffer by hand, as the backward kernels would. """
+bucket exactly once per step (early launches driven by the layers' end-of-backward notifications, and the `finish()` path), gradient averaging,
+per-rank seeds / DistributedSampler sharding. The CUDA kernels are not involved: gradients are written into the flat buffer by hand, as the backward
+kernels would, and `ops._backward_done` is called as the end of each layer's backward does. """
 import os
 import socket
 import sys
@@ -45,22 +46,47 @@ def _worker(rank, world, port, hp):
         tgt = layer._grad_out['weight']
         assert tgt.shape == layer._op.weight.shape and tgt.permute(0, 2, 3, 1).is_contiguous()
 
-        # ---- reduction: hooks path (fire every layer's hook in backward order) and finish() path
-        for use_hooks in (True, False):
+        # ---- reduction: early launches (every layer reports the end of its backward, in backward order) and the finish() path
+        from deepcv_b200 import ops
+        assert all(not l._backward_hooks for l in flat.layers), 'module full-backward hooks fire before a first layer has enqueued its weight gradient'
+        dp.reducer.average_in_finish = False
+        for early in (True, False):
             dp.reducer.begin_step()
             flat.flat_grads.fill_(float(rank + 1))
-            if use_hooks:
-                for layer in reversed(flat.layers):
-                    for hook in layer._backward_hooks.values():
-                        hook(layer, None, None)
+            if early:
+                launched_before_last = None
+                for i, layer in enumerate(reversed(flat.layers)):
+                    if i == len(flat.layers) - 1:
+                        launched_before_last = list(dp.reducer._launched)
+                    ops._backward_done(layer._grad_out, layer._grad_out)
+                    assert layer._grad_out['_written']
+                # the bucket holding the first layer's gradients is only reduced once that layer itself has reported
+                first_buckets = dp.reducer._layer_buckets[id(flat.layers[0])]
+                assert not any(launched_before_last[b] for b in first_buckets) and any(launched_before_last)
             dp.finish_gradient_reduction()
             assert torch.all(flat.flat_grads == 3.0), 'every bucket must be SUM-reduced exactly once'
-        # the 1/world scaling is folded into the optimizer
+        # averaging: by finish() (any optimizer) ...
+        dp.reducer.average_in_finish = True
+        flat.flat_grads.fill_(float(rank + 1))
+        dp.finish_gradient_reduction()
+        assert torch.all(flat.flat_grads == 1.5)
+        # ... a second backward through one layer before its bucket has gone (shared weights): that bucket waits for finish()
+        dp.reducer.average_in_finish = False
+        flat.flat_grads.fill_(1.0)
+        last = flat.layers[-1]
+        ops._backward_done(last._grad_out, last._grad_out)
+        dp.finish_gradient_reduction()
+        assert torch.all(flat.flat_grads == 2.0)
+        # ... or folded into the optimizer kernel
         opt = FlatAdamW(model.parameters(), lr=1e-3).attach(flat)
         opt.grad_scale = 1. / dp.world_size
         assert opt.grad_scale == 0.5
-        opt.zero_grad()                                     # must keep (not drop) the gradient views
+        flat.flat_grads.fill_(7.0)
+        opt.zero_grad()                                     # keeps (does not drop) the gradient views, zeroes the buffer, re-arms direct writes
         assert all(p.grad is flat.grad_view(p) for p in model.parameters())
+        assert torch.all(flat.flat_grads == 0) and not any(l._grad_out['_written'] for l in flat.layers)
+        sd = opt.state_dict()
+        assert sd['flat_step'] == 0
 
         # sampler sharding + per-rank seed as in train()
         ds = torch.utils.data.TensorDataset(torch.arange(64))

@@ -54,7 +54,7 @@ def test_norm_streaming_kernels(dev, n, hw, c, dtype):
     st = stream()
     # statistics
     stats = torch.full((n, c, 2), 7., device=dev)
-    check(lib.dcv_norm_stats(P(yd), P(stats), n, hw, c, dt, st), 'norm_stats')
+    check(lib.dcv_norm_stats(P(yd), P(stats), n, hw, c, dt, 0, st), 'norm_stats')
     ref = torch.stack([y64.sum(1), (y64 * y64).sum(1)], -1)
     assert rel(stats, ref) <= 1e-5
     # forward apply
@@ -65,19 +65,19 @@ def test_norm_streaming_kernels(dev, n, hw, c, dtype):
     assert float(((z.double().cpu() - zref).abs() / (zref.abs() + 1.)).max()) <= tol
     # backward reduce
     s_nc = torch.full((n, c, 2), -3., device=dev)
-    check(lib.dcv_norm_bwd_reduce(P(dzd), P(yd), P(s_nc), n, hw, c, dt, st), 'norm_bwd_reduce')
+    check(lib.dcv_norm_bwd_reduce(P(dzd), P(yd), P(s_nc), n, hw, c, dt, 0, st), 'norm_bwd_reduce')
     ref = torch.stack([dz64.sum(1), (dz64 * y64).sum(1)], -1)
     assert rel(s_nc, ref) <= 1e-5
     # backward apply + bias gradient
     dy = torch.empty_like(yd)
     dbias = torch.full((c,), 11., device=dev)
-    check(lib.dcv_act_norm_bwd_apply(P(dzd), P(yd), P(pqrd), P(dy), P(dbias), ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st), 'act_norm_bwd_apply')
+    check(lib.dcv_act_norm_bwd_apply(P(dzd), P(yd), P(pqrd), P(dy), P(dbias), ACT_LEAKY_RELU, 0.01, n, hw, c, dt, 0, st), 'act_norm_bwd_apply')
     pre = pqr[:, None, :, 0].double() * dz64 + pqr[:, None, :, 1].double() * y64 + pqr[:, None, :, 2].double()
     dyref = pre * torch.where(y64 > 0, 1.0, 0.01)
     assert float(((dy.double().cpu() - dyref).abs() / (dyref.abs() + 1.)).max()) <= tol
     assert rel(dbias, dyref.sum((0, 1))) <= 1e-4   # summed in fp32 from the unrounded values, whatever the output type
     # without parameters (P = 1, Q = R = 0) and without a bias gradient
-    check(lib.dcv_act_norm_bwd_apply(P(dzd), P(yd), None, P(dy), None, ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st), 'act_norm_bwd_apply')
+    check(lib.dcv_act_norm_bwd_apply(P(dzd), P(yd), None, P(dy), None, ACT_LEAKY_RELU, 0.01, n, hw, c, dt, 0, st), 'act_norm_bwd_apply')
     assert float(((dy.double().cpu() - dz64 * torch.where(y64 > 0, 1.0, 0.01)).abs()).max()) <= (1e-6 if dtype == torch.float32 else 2.0 ** -7 * float(dz64.abs().max()))
 
 
@@ -118,7 +118,7 @@ def test_tcgen05_wgrad_pointwise_channel_blocks(dev, n, c, hw, k):
         pytest.skip('shape not on the tcgen05 weight-gradient path')
     dw = torch.full((k, 1, 1, c), 9., device=dev)
     xd, dyd = x.to(dev), dy.to(dev)   # keep the device copies alive across the asynchronous launch
-    check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xd), P(dyd), P(dw), None, DCV_BF16, ALGO_TCGEN05, stream()), 'conv2d_wgrad')
+    check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xd), P(dyd), P(dw), None, DCV_BF16, ALGO_TCGEN05, 0, stream()), 'conv2d_wgrad')
     torch.cuda.synchronize()
     ref = dy.double().reshape(-1, k).t() @ x.double().reshape(-1, c)
     assert rel(dw.reshape(k, c), ref) <= 2e-2
@@ -154,7 +154,7 @@ def test_norm_finalize_running_statistics_and_affine(dev, n, hw, c, groups, mome
             ref = gn(ref)
         yd = y.permute(0, 2, 3, 1).contiguous().to(dev)                     # NHWC
         stats = torch.empty(n, c, 2, device=dev)
-        check(lib.dcv_norm_stats(P(yd), P(stats), n, hw, c, DCV_F32, st), 'norm_stats')
+        check(lib.dcv_norm_stats(P(yd), P(stats), n, hw, c, DCV_F32, 0, st), 'norm_stats')
         G = groups if groups else 1
         saved = torch.empty(int(lib.dcv_norm_saved_floats(n, c, G)), device=dev)
         ab = torch.empty(n, c, 2, device=dev)

@@ -81,10 +81,10 @@ def main():
             dbias = torch.empty(c, device=dev)
             tag = f'c{c} hw{hw} n{n} {"bf16" if es == 2 else "fp32"}'
             if 'norm' in what:
-                report(f'stats_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_stats(P(ys[i]), P(stats), n, hw, c, dt, st)), reps), E * es)
+                report(f'stats_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_stats(P(ys[i]), P(stats), n, hw, c, dt, 0, st)), reps), E * es)
                 report(f'apply_fwd_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_apply_fwd(P(ys[i]), P(ab), P(zs[i]), n, hw, c, dt, st)), reps), 2 * E * es)
-                report(f'bwd_reduce_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_bwd_reduce(P(dz[i % len(dz)]), P(ys[i]), P(stats), n, hw, c, dt, st)), reps), 2 * E * es)
-                report(f'bwd_apply_kernel {tag}', timeit(lambda i: check(lib.dcv_act_norm_bwd_apply(P(dz[i % len(dz)]), P(ys[i]), P(pqr), P(zs[i]), P(dbias), ACT_LEAKY_RELU, 0.01, n, hw, c, dt, st)), reps), 3 * E * es)
+                report(f'bwd_reduce_kernel {tag}', timeit(lambda i: check(lib.dcv_norm_bwd_reduce(P(dz[i % len(dz)]), P(ys[i]), P(stats), n, hw, c, dt, 0, st)), reps), 2 * E * es)
+                report(f'bwd_apply_kernel {tag}', timeit(lambda i: check(lib.dcv_act_norm_bwd_apply(P(dz[i % len(dz)]), P(ys[i]), P(pqr), P(zs[i]), P(dbias), ACT_LEAKY_RELU, 0.01, n, hw, c, dt, 0, st)), reps), 3 * E * es)
             if 'pool' in what and hw in (3136, 784, 1024, 256):
                 h = int(hw ** 0.5)
                 outs = [torch.empty(n, h // 2, h // 2, c, device=dev, dtype=tdt) for _ in range(reps)]
