@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
-__all__ = ['lib', 'ConvShape', 'NormParams', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
+__all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
            'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
 
 ABI_VERSION = 2
@@ -28,6 +28,16 @@ class NormParams(Structure):
                 ('bn_num_batches_tracked', c_void_p),
                 ('use_gn', c_int32), ('gn_groups', c_int32), ('gn_eps', c_float),
                 ('gn_weight', c_void_p), ('gn_bias', c_void_p)]
+
+
+class ScNorm(Structure):
+    """ `dcv_sc_norm`: a raw block output's pending BatchNorm o GroupNorm, its raw sums and backward sum buffers (few-channel path). """
+    _fields_ = [('enabled', c_int32), ('n', c_int32), ('c', c_int32), ('hw', c_int32), ('use_bn', c_int32), ('bn_training', c_int32),
+                ('bn_eps', c_float), ('bn_momentum', c_float),
+                ('bn_weight', c_void_p), ('bn_bias', c_void_p), ('bn_running_mean', c_void_p), ('bn_running_var', c_void_p), ('bn_num_batches_tracked', c_void_p),
+                ('use_gn', c_int32), ('gn_groups', c_int32), ('gn_eps', c_float),
+                ('gn_weight', c_void_p), ('gn_bias', c_void_p),
+                ('stats_nc', c_void_p), ('bn_sums', c_void_p), ('s_nc', c_void_p), ('u_sums', c_void_p)]
 
 
 P = c_void_p
@@ -50,6 +60,13 @@ SYMBOLS = {
     'dcv_conv2d_dgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, P]),
     'dcv_conv2d_wgrad_workspace': (c_size_t, [POINTER(ConvShape), c_int, c_int]),
     'dcv_conv2d_wgrad': (c_int, [POINTER(ConvShape), P, P, P, P, c_int, c_int, c_int, P]),
+    'dcv_sc_conv_supported': (c_int, [POINTER(ConvShape), c_int]),
+    'dcv_sc_norm_floats': (c_size_t, [c_int, c_int, c_int]),
+    'dcv_sc_conv_fwd': (c_int, [POINTER(ConvShape), P, POINTER(ScNorm), c_int, P, P, c_int, c_float, P, POINTER(ScNorm), P]),
+    'dcv_sc_conv_wgrad': (c_int, [POINTER(ConvShape), P, POINTER(ScNorm), P, P, POINTER(ScNorm), c_int, c_float, P, P, P, P, P, P, P]),
+    'dcv_sc_conv_dgrad': (c_int, [POINTER(ConvShape), P, P, POINTER(ScNorm), c_int, c_float, P, P, P, POINTER(ScNorm), P]),
+    'dcv_sc_affine_pool_fwd': (c_int, [P, POINTER(ScNorm), c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_sc_affine_pool_bwd': (c_int, [P, P, POINTER(ScNorm), P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_stats': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_saved_floats': (c_size_t, [c_int, c_int, c_int]),
     'dcv_norm_fwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P]),

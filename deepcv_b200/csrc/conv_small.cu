@@ -1,0 +1,856 @@
+// Few-channel convolution blocks (the default CIFAR-10 `image_classifier`: 3/4/16 channels, 5x5 and 3x3 filters, 32x32 and 16x16 maps) as three
+// fused kernels per block — forward, weight gradient, data gradient — with the BatchNorm / GroupNorm that FOLLOWS the block's activation never run
+// as passes of its own (reference block order: meta/nn.py:553 `Conv2d -> act -> BatchNorm2d -> GroupNorm`, spec conf/base/parameters.yml:8-19).
+//
+// Why not the tcgen05 kernels: K = R*S*C is 36..144 and N = 4..16 output channels; an M = 128 UMMA tile needs a software im2col tile in the swizzled
+// operand layout (2.3 us per 128-pixel tile measured for the gather kernel) for 0.1 us of MMA. Here the implicit-GEMM A fragments of warp-level
+// `mma.sync.m16n8k16` (bf16 -> fp32) are read STRAIGHT from the NHWC image tile in shared memory: with K ordered (tap, channel) a fragment register is
+// two adjacent channels of one tap = one aligned 32-bit shared load, no im2col at all. The step is bound by HBM traffic and launch latency, not math
+// (arithmetic intensity 43-72 FLOP/B), so what matters is the number of passes over the activations and of launches:
+//
+//   forward   reads the producer's RAW output y_prev and applies its pending normalisation z = A[n][c]*y + B[n][c] while staging the tile
+//             ("normalise on load": z is never written), convolves, adds bias, activates, stores y (bf16) and accumulates the statistics of y:
+//             per-(image, channel) sums (plain stores: a CTA owns whole images) and sharded per-channel batch sums (atomics).
+//   A, B      are NOT produced by a finalize kernel: every consumer CTA derives them for ITS image from the raw sums in a ~100-flop prologue
+//             (BatchNorm from the batch sums, GroupNorm from the image's sums, fp64). The CTA that handles image 0 also updates the running statistics.
+//   backward  the consumer's data-gradient kernel writes dz (gradient w.r.t. the producer's normalised output) and, in its epilogue, the sums
+//             s[n][c] = {sum dz, sum dz*y} plus the image's contribution to the BatchNorm adjoint sums (sharded atomics). The producer's weight- and
+//             data-gradient kernels then derive P, Q, R of dy = act'(y)*(P*dz + Q*y + R) per image in their prologue and apply it WHILE LOADING their
+//             operand: no reduce / finalize / apply passes, dy is never written.
+// Per block: 3 launches instead of 9 (conv, finalize, apply, reduce, finalize, apply, wgrad, dgrad + weight packing), and three activation-sized
+// tensors (z, dy, the transposed weights) never touch HBM.
+#include "common.cuh"
+
+namespace dcv {
+namespace sc {
+
+constexpr int kThreads = 256;   // 8 warps
+constexpr int kWarps = kThreads / 32;
+constexpr int kShards = 16;     // per-channel batch sums are spread over this many accumulators (index image % kShards): 32 atomics per address at batch 512
+constexpr int kMaxC = 32;       // channels of a normalised tensor on this path
+
+typedef __nv_bfloat16 bf16;
+
+// Normalisation algebra of ONE image held in shared memory (lane = channel). z = A*y + B; BatchNorm u = al*y + be (mean mu, rstd rc);
+// GroupNorm of u: mean gmean, rstd gr of the channel's group; backward: du = D1*dz + D2*y + D3, dy_pre = P*dz + Q*y + R.
+struct Coef {
+  float A[kMaxC], B[kMaxC], al[kMaxC], be[kMaxC], mu[kMaxC], rc[kMaxC], gmean[kMaxC], gr[kMaxC];
+  float D1[kMaxC], D2[kMaxC], D3[kMaxC], P[kMaxC], Q[kMaxC], R[kMaxC];
+};
+
+// ---- forward coefficients of image `img` from the raw sums. Called by ONE whole warp (lane = channel, c <= 32).
+__device__ void norm_forward_coeffs(const dcv_sc_norm& nd, int img, Coef& cf, bool update_running) {
+  const int lane = threadIdx.x & 31, c = nd.c;
+  double al = 1.0, be = 0.0, mean = 0.0, rstd = 1.0;
+  if (lane < c && nd.use_bn) {
+    double var;
+    const bool run = nd.bn_running_mean && nd.bn_running_var;
+    if (nd.bn_training) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int sh = 0; sh < kShards; ++sh) { s1 += (double)nd.bn_sums[(sh * c + lane) * 2]; s2 += (double)nd.bn_sums[(sh * c + lane) * 2 + 1]; }
+      const double m = (double)nd.n * (double)nd.hw;
+      mean = s1 / m;
+      var = s2 / m - mean * mean;
+      if (var < 0.0) var = 0.0;
+      if (update_running && run) {
+        double mom = (double)nd.bn_momentum;
+        if (mom < 0.0) mom = 1.0 / (double)((nd.bn_num_batches_tracked ? *nd.bn_num_batches_tracked : 0) + 1);
+        const double unbiased = m > 1.0 ? var * m / (m - 1.0) : var;
+        nd.bn_running_mean[lane] = (float)((1.0 - mom) * (double)nd.bn_running_mean[lane] + mom * mean);
+        nd.bn_running_var[lane] = (float)((1.0 - mom) * (double)nd.bn_running_var[lane] + mom * unbiased);
+      }
+    } else {
+      mean = (double)nd.bn_running_mean[lane];
+      var = (double)nd.bn_running_var[lane];
+    }
+    rstd = rsqrt(var + (double)nd.bn_eps);
+    al = (nd.bn_weight ? (double)nd.bn_weight[lane] : 1.0) * rstd;
+    be = (nd.bn_bias ? (double)nd.bn_bias[lane] : 0.0) - mean * al;
+  }
+  if (lane < c) { cf.al[lane] = (float)al; cf.be[lane] = (float)be; cf.mu[lane] = (float)mean; cf.rc[lane] = (float)rstd; }
+  __syncwarp();
+  if (update_running && lane == 0 && nd.use_bn && nd.bn_training && nd.bn_num_batches_tracked) *nd.bn_num_batches_tracked += 1;   // every lane has read it above
+  if (lane < c) {
+    double A = (double)cf.al[lane], B = (double)cf.be[lane];   // the float-rounded values: the backward kernels recompute exactly these
+    float gmean = 0.f, gr = 1.f;
+    if (nd.use_gn) {
+      const int cg = c / nd.gn_groups, g0 = lane / cg * cg;
+      const double hw = (double)nd.hw;
+      double su = 0.0, suu = 0.0;
+      for (int k = 0; k < cg; ++k) {
+        const int ch = g0 + k;
+        const double a_ = (double)cf.al[ch], b_ = (double)cf.be[ch];
+        const double sy = (double)nd.stats_nc[((size_t)img * c + ch) * 2], syy = (double)nd.stats_nc[((size_t)img * c + ch) * 2 + 1];
+        su += a_ * sy + hw * b_;
+        suu += a_ * a_ * syy + 2.0 * a_ * b_ * sy + hw * b_ * b_;
+      }
+      const double mg = (double)cg * hw, mean_u = su / mg;
+      double var = suu / mg - mean_u * mean_u;
+      if (var < 0.0) var = 0.0;
+      gmean = (float)mean_u; gr = (float)rsqrt(var + (double)nd.gn_eps);
+      const double a2 = (nd.gn_weight ? (double)nd.gn_weight[lane] : 1.0) * (double)gr;
+      const double b2 = (nd.gn_bias ? (double)nd.gn_bias[lane] : 0.0) - (double)gmean * a2;
+      B = a2 * B + b2;
+      A = a2 * A;
+    }
+    cf.gmean[lane] = gmean; cf.gr[lane] = gr; cf.A[lane] = (float)A; cf.B[lane] = (float)B;
+  }
+  __syncwarp();
+}
+
+// ---- GroupNorm adjoint of image `img`: D1, D2, D3 from the image's sums s[c][2] = {sum dz, sum dz*y} (any memory). One warp, after norm_forward_coeffs.
+__device__ void norm_backward_D(const dcv_sc_norm& nd, Coef& cf, const float* s) {
+  const int lane = threadIdx.x & 31, c = nd.c;
+  if (lane < c) {
+    double D1 = 1.0, D2 = 0.0, D3 = 0.0;
+    if (nd.use_gn) {
+      const int cg = c / nd.gn_groups, g0 = lane / cg * cg;
+      const double r = (double)cf.gr[lane], mean_u = (double)cf.gmean[lane], mg = (double)cg * (double)nd.hw;
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < cg; ++k) {
+        const int ch = g0 + k;
+        const double gam = nd.gn_weight ? (double)nd.gn_weight[ch] : 1.0;
+        const double s1 = (double)s[2 * ch], s2 = (double)s[2 * ch + 1];
+        a += gam * s1;
+        b += gam * r * ((double)cf.al[ch] * s2 + ((double)cf.be[ch] - mean_u) * s1);
+      }
+      const double Ag = a / mg, Bg = b / mg, gam = nd.gn_weight ? (double)nd.gn_weight[lane] : 1.0;
+      D1 = r * gam;
+      D2 = -r * Bg * r * (double)cf.al[lane];
+      D3 = -r * Ag - r * Bg * r * ((double)cf.be[lane] - mean_u);
+    }
+    cf.D1[lane] = (float)D1; cf.D2[lane] = (float)D2; cf.D3[lane] = (float)D3;
+  }
+  __syncwarp();
+}
+
+// ---- what the kernel that COMPLETES the sums s of image `img` does with them (one warp; s in shared memory): stores them for the producer's backward
+// kernels and adds the image's terms of the BatchNorm adjoint sums / GroupNorm parameter gradients to the sharded accumulators u_sums[shard][c][4] =
+// {U1 = sum du, U2raw = sum du*y, d gn_weight, d gn_bias}.
+__device__ void norm_backward_image_sums(const dcv_sc_norm& nd, int img, Coef& cf, const float* s) {
+  norm_forward_coeffs(nd, img, cf, false);
+  norm_backward_D(nd, cf, s);
+  const int lane = threadIdx.x & 31, c = nd.c;
+  if (lane < c) {
+    const double s1 = (double)s[2 * lane], s2 = (double)s[2 * lane + 1], hw = (double)nd.hw;
+    const double sy = (double)nd.stats_nc[((size_t)img * c + lane) * 2], syy = (double)nd.stats_nc[((size_t)img * c + lane) * 2 + 1];
+    const double D1 = (double)cf.D1[lane], D2 = (double)cf.D2[lane], D3 = (double)cf.D3[lane];
+    nd.s_nc[((size_t)img * c + lane) * 2] = (float)s1;
+    nd.s_nc[((size_t)img * c + lane) * 2 + 1] = (float)s2;
+    float* u = nd.u_sums + ((size_t)(img % kShards) * c + lane) * 4;
+    atomicAdd(u, (float)(D1 * s1 + D2 * sy + D3 * hw));
+    atomicAdd(u + 1, (float)(D1 * s2 + D2 * syy + D3 * sy));
+    if (nd.use_gn) {
+      atomicAdd(u + 2, (float)((double)cf.gr[lane] * ((double)cf.al[lane] * s2 + ((double)cf.be[lane] - (double)cf.gmean[lane]) * s1)));
+      atomicAdd(u + 3, (float)s1);
+    }
+  }
+  __syncwarp();
+}
+
+// ---- P, Q, R of image `img` (one warp): forward coefficients, D from the stored sums, BatchNorm adjoint from the complete batch sums.
+// `param_grads`: this warp also writes the normalisation parameter gradients (one CTA of one kernel per block does).
+__device__ void norm_backward_pqr(const dcv_sc_norm& nd, int img, Coef& cf, bool param_grads, float* d_bn_w, float* d_bn_b, float* d_gn_w, float* d_gn_b) {
+  norm_forward_coeffs(nd, img, cf, false);
+  norm_backward_D(nd, cf, nd.s_nc + (size_t)img * nd.c * 2);
+  const int lane = threadIdx.x & 31, c = nd.c;
+  if (lane < c) {
+    double U1 = 0.0, U2raw = 0.0, dgw = 0.0, dgb = 0.0;
+    for (int sh = 0; sh < kShards; ++sh) {
+      const float* u = nd.u_sums + ((size_t)sh * c + lane) * 4;
+      U1 += (double)u[0]; U2raw += (double)u[1]; dgw += (double)u[2]; dgb += (double)u[3];
+    }
+    const double D1 = (double)cf.D1[lane], D2 = (double)cf.D2[lane], D3 = (double)cf.D3[lane];
+    double P = D1, Q = D2, R = D3, u2 = 0.0;
+    if (nd.use_bn) {
+      const double al = (double)cf.al[lane];
+      if (nd.bn_training) {
+        const double mu = (double)cf.mu[lane], rc = (double)cf.rc[lane], m = (double)nd.n * (double)nd.hw;
+        u2 = rc * (U2raw - mu * U1);
+        P = al * D1;
+        Q = al * (D2 - rc * u2 / m);
+        R = al * (D3 - U1 / m + mu * rc * u2 / m);
+      } else {
+        u2 = (double)cf.rc[lane] * (U2raw - (double)cf.mu[lane] * U1);
+        P = al * D1; Q = al * D2; R = al * D3;
+      }
+    }
+    cf.P[lane] = (float)P; cf.Q[lane] = (float)Q; cf.R[lane] = (float)R;
+    if (param_grads) {
+      if (nd.use_bn) { if (d_bn_w) d_bn_w[lane] = (float)u2; if (d_bn_b) d_bn_b[lane] = (float)U1; }
+      if (nd.use_gn) { if (d_gn_w) d_gn_w[lane] = (float)dgw; if (d_gn_b) d_gn_b[lane] = (float)dgb; }
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == DCV_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == DCV_ACT_LEAKY_RELU) return v > 0.f ? v : v * slope;
+  if (act == DCV_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+__device__ __forceinline__ float act_bwd(float y, int act, float slope) {
+  if (act == DCV_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == DCV_ACT_LEAKY_RELU) return y > 0.f ? 1.f : slope;
+  if (act == DCV_ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+
+__device__ __forceinline__ void mma16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float round_bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---- operand staging -------------------------------------------------------------------------------------------------------------------------
+// Source element of image-local index (pixel, channel): either the plain tensor, the producer's raw output with its pending affine (A, B), or the
+// pre-activation gradient dy = act'(y) * (P*dz + Q*y + R) assembled from dz and y. One functor type per kernel keeps the loaders generic.
+struct SrcPlain {
+  const bf16* x; const Coef* cf;   // cf == nullptr: plain
+  __device__ __forceinline__ void load8(size_t e0, int c0, int cmask, float* v) const {   // 8 consecutive elements starting at e0 (16-byte aligned), channel of element i = (c0 + i) & cmask
+    vec_unpack<bf16>(*reinterpret_cast<const uint4*>(x + e0), v);
+    if (cf) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int ch = (c0 + i) & cmask; v[i] = fmaf(cf->A[ch], v[i], cf->B[ch]); }
+    }
+  }
+  __device__ __forceinline__ float load1(size_t e, int ch) const {
+    const float v = __bfloat162float(x[e]);
+    return cf ? fmaf(cf->A[ch], v, cf->B[ch]) : v;
+  }
+};
+struct SrcDy {
+  const bf16* dz; const bf16* y; const Coef* cf;   // cf == nullptr: P = 1, Q = R = 0
+  int act; float slope;
+  __device__ __forceinline__ void load8(size_t e0, int c0, int cmask, float* v) const {
+    float b[8];
+    vec_unpack<bf16>(*reinterpret_cast<const uint4*>(dz + e0), v);
+    vec_unpack<bf16>(*reinterpret_cast<const uint4*>(y + e0), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = (c0 + i) & cmask;
+      const float pre = cf ? fmaf(cf->P[ch], v[i], fmaf(cf->Q[ch], b[i], cf->R[ch])) : v[i];
+      v[i] = pre * act_bwd(b[i], act, slope);
+    }
+  }
+  __device__ __forceinline__ float load1(size_t e, int ch) const {
+    const float a = __bfloat162float(dz[e]), b = __bfloat162float(y[e]);
+    const float pre = cf ? fmaf(cf->P[ch], a, fmaf(cf->Q[ch], b, cf->R[ch])) : a;
+    return pre * act_bwd(b, act, slope);
+  }
+};
+
+// NHWC tile with halo: tile[(y + PAD) * Wp + x + PAD][CI] = src(y, x, 0..c_src) (channels >= c_src zero). The halo was zeroed once and is never written.
+// `sum8`: when non-null, per-thread sums of the 8 vector slots (the bias gradient of the weight-gradient kernel; only the vector path fills it).
+template <int CI, typename Src>
+__device__ __forceinline__ void stage_nhwc(bf16* tile, const Src& src, size_t img_elem0, int H, int W, int Wp, int PAD, int c_src, int tid) {
+  if (c_src == CI && (img_elem0 % 8) == 0) {
+    const int nvec = H * W * CI / 8;
+    for (int v = tid; v < nvec; v += kThreads) {
+      const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix / W, x = pix - y * W;
+      float f[8];
+      src.load8(img_elem0 + e0, c0, CI - 1, f);
+      bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI + c0;
+      if (CI == 4) {   // two pixels of 8 bytes each (x is even, so both are in the same row)
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
+        *reinterpret_cast<uint2*>(dst + 4) = make_uint2(pack2(f[4], f[5]), pack2(f[6], f[7]));
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+      }
+    }
+  } else {
+    for (int pix = tid; pix < H * W; pix += kThreads) {
+      const int y = pix / W, x = pix - y * W;
+      bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI;
+#pragma unroll
+      for (int c = 0; c < CI; ++c) dst[c] = __float2bfloat16_rn(c < c_src ? src.load1(img_elem0 + (size_t)pix * c_src + c, c) : 0.f);
+    }
+  }
+}
+
+// ---- implicit-GEMM core shared by forward and data gradient ------------------------------------------------------------------------------------
+// One image: M = H*W pixels (16 consecutive pixels of a row per m-tile; W % 16 == 0), N = NT*8 output columns, K = (tap, channel) of a KS x KS window
+// over a CI-channel NHWC tile. `breg`: the B fragments (weights), resident in registers for the whole kernel. `epi(y, x, col, v0, v1)` receives the two
+// adjacent output columns col, col+1 of pixel (y, x).
+template <int CI, int NT, int KS> struct Core {
+  static constexpr int KK = KS * KS * CI, KSTEPS = (KK + 15) / 16, CW = CI / 2;
+  uint32_t breg[KSTEPS][NT][2];
+  int aoff[KSTEPS][2];
+
+  // wsel(tap_r, tap_s, cin, col) -> weight value as bf16 bits (0 when out of range)
+  template <typename WSel>
+  __device__ __forceinline__ void setup(int Wp, WSel wsel) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < KSTEPS; ++j)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int kk = 16 * j + 8 * h2 + 2 * t, tap = kk / CI, c = kk % CI;
+        const bool on = tap < KS * KS;
+        aoff[j][h2] = on ? ((tap / KS) * Wp + tap % KS) * CW + c / 2 : 0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int col = nt * 8 + g;
+          const uint32_t lo = on ? wsel(tap / KS, tap % KS, c, col) : 0u, hi = on ? wsel(tap / KS, tap % KS, c + 1, col) : 0u;
+          breg[j][nt][h2] = lo | (hi << 16);
+        }
+      }
+  }
+
+  template <typename Epi>
+  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Epi epi) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+    const int mtiles = H * W / 16;
+    for (int mt = warp; mt < mtiles; mt += kWarps) {
+      const int p0 = mt * 16, y = p0 / W, x0 = p0 - y * W;
+      const int pb = (y * Wp + x0 + g) * CW;
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < KSTEPS; ++j) {
+        const uint32_t a0 = tw[pb + aoff[j][0]], a1 = tw[pb + 8 * CW + aoff[j][0]], a2 = tw[pb + aoff[j][1]], a3 = tw[pb + 8 * CW + aoff[j][1]];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma16816(acc[nt], a0, a1, a2, a3, breg[j][nt][0], breg[j][nt][1]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        epi(y, x0 + g, nt * 8 + 2 * t, acc[nt][0], acc[nt][1]);
+        epi(y, x0 + g + 8, nt * 8 + 2 * t, acc[nt][2], acc[nt][3]);
+      }
+    }
+  }
+};
+
+// Sum over the 8 lanes that share `t` (same output columns), then ONE shared-memory atomic per (column, value) and warp.
+__device__ __forceinline__ void reduce_cols_to_smem(float v, float* dst) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  if ((threadIdx.x & 31) < 4) atomicAdd(dst, v);
+}
+
+// ---- forward ----------------------------------------------------------------------------------------------------------------------------------
+struct FwdArgs {
+  int n, h, w, c_src, k_out, act, update_running; float slope;
+  const bf16* x; const bf16* wgt; const float* bias; bf16* y;
+  dcv_sc_norm xn, yn;
+};
+
+template <int CI, int NT, int KS>
+__global__ void __launch_bounds__(kThreads) sc_fwd_kernel(const FwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* tile = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ Coef cfx;
+  __shared__ float sh_stat[NT * 8][2];
+  constexpr int PAD = KS / 2;
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, t = lane & 3;
+  for (int i = tid; i < Hp * Wp * CI / 8; i += kThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  Core<CI, NT, KS> core;
+  const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
+  core.setup(Wp, [&](int r, int s, int c, int col) -> uint32_t {
+    return (c < a.c_src && col < a.k_out) ? (uint32_t)wb[((size_t)(col * KS + r) * KS + s) * a.c_src + c] : 0u;
+  });
+  float bias_r[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { const int col = nt * 8 + 2 * t + e; bias_r[nt][e] = (a.bias && col < a.k_out) ? a.bias[col] : 0.f; }
+
+  for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+    __syncthreads();   // the previous image's tile has been consumed (first pass: the halo is zeroed)
+    if (tid < 32 && a.xn.enabled) norm_forward_coeffs(a.xn, img, cfx, a.update_running != 0 && img == 0);
+    if (tid < NT * 8 * 2) (&sh_stat[0][0])[tid] = 0.f;
+    __syncthreads();
+    SrcPlain src{a.x, a.xn.enabled ? &cfx : nullptr};
+    stage_nhwc<CI>(tile, src, (size_t)img * H * W * a.c_src, H, W, Wp, PAD, a.c_src, tid);
+    __syncthreads();
+    float s1[NT][2], s2[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
+    bf16* yimg = a.y + (size_t)img * H * W * a.k_out;
+    core.run(tile, H, W, Wp, [&](int y, int x, int col, float v0, float v1) {
+      const int nt = col >> 3;
+      v0 = round_bf(act_fwd(v0 + bias_r[nt][0], a.act, a.slope));
+      v1 = round_bf(act_fwd(v1 + bias_r[nt][1], a.act, a.slope));
+      if (col < a.k_out) *reinterpret_cast<uint32_t*>(yimg + ((size_t)y * W + x) * a.k_out + col) = pack2(v0, v1);
+      s1[nt][0] += v0; s1[nt][1] += v1; s2[nt][0] = fmaf(v0, v0, s2[nt][0]); s2[nt][1] = fmaf(v1, v1, s2[nt][1]);   // statistics of the STORED values
+    });
+    if (a.yn.enabled) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          reduce_cols_to_smem(s1[nt][e], &sh_stat[nt * 8 + 2 * t + e][0]);
+          reduce_cols_to_smem(s2[nt][e], &sh_stat[nt * 8 + 2 * t + e][1]);
+        }
+      __syncthreads();
+      if (tid < a.k_out) {   // this CTA owns the whole image: plain stores per (image, channel); the batch sums are sharded atomics
+        const float v1 = sh_stat[tid][0], v2 = sh_stat[tid][1];
+        a.yn.stats_nc[((size_t)img * a.k_out + tid) * 2] = v1;
+        a.yn.stats_nc[((size_t)img * a.k_out + tid) * 2 + 1] = v2;
+        if (a.yn.use_bn && a.yn.bn_training) {
+          atomicAdd(a.yn.bn_sums + ((size_t)(img % kShards) * a.k_out + tid) * 2, v1);
+          atomicAdd(a.yn.bn_sums + ((size_t)(img % kShards) * a.k_out + tid) * 2 + 1, v2);
+        }
+      }
+    }
+  }
+}
+
+// ---- data gradient ------------------------------------------------------------------------------------------------------------------------------
+// dx[n][y][x][c] = sum_{k,r,s} dy[n][y + PAD - r][x + PAD - s][k] * w[k][r][s][c]: the forward core over the dy tile (KI = channels of dy) with the weights
+// read transposed and flipped. dy is assembled while staging (SrcDy). When the layer's input is a producer's raw output with a pending normalisation
+// (xn.enabled), dx is the gradient w.r.t. the NORMALISED input and the epilogue accumulates the producer's backward sums against its raw output x_raw.
+struct DgradArgs {
+  int n, h, w, c_in, k_out, act; float slope;
+  const bf16* dz; const bf16* y; const bf16* wgt; bf16* dx; const bf16* x_raw;
+  dcv_sc_norm yn, xn;
+};
+
+template <int KI, int NT, int KS>
+__global__ void __launch_bounds__(kThreads) sc_dgrad_kernel(const DgradArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* tile = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ Coef cfy, cfx;
+  __shared__ float sh_s[NT * 8][2];
+  constexpr int PAD = KS / 2;
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, t = lane & 3;
+  for (int i = tid; i < Hp * Wp * KI / 8; i += kThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  Core<KI, NT, KS> core;
+  const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
+  core.setup(Wp, [&](int r, int s, int k, int col) -> uint32_t {   // tile channel k = output channel of the layer, column = input channel of the layer
+    return (k < a.k_out && col < a.c_in) ? (uint32_t)wb[((size_t)(k * KS + (KS - 1 - r)) * KS + (KS - 1 - s)) * a.c_in + col] : 0u;
+  });
+  for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+    __syncthreads();
+    if (tid < 32 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy, false, nullptr, nullptr, nullptr, nullptr);
+    if (tid < NT * 8 * 2) (&sh_s[0][0])[tid] = 0.f;
+    __syncthreads();
+    SrcDy src{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
+    stage_nhwc<KI>(tile, src, (size_t)img * H * W * a.k_out, H, W, Wp, PAD, a.k_out, tid);
+    __syncthreads();
+    float s1[NT][2], s2[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
+    const size_t img0 = (size_t)img * H * W * a.c_in;
+    core.run(tile, H, W, Wp, [&](int y, int x, int col, float v0, float v1) {
+      if (col < a.c_in) {
+        const size_t e = img0 + ((size_t)y * W + x) * a.c_in + col;
+        v0 = round_bf(v0); v1 = round_bf(v1);
+        *reinterpret_cast<uint32_t*>(a.dx + e) = pack2(v0, v1);
+        if (a.xn.enabled) {
+          const uint32_t yr = *reinterpret_cast<const uint32_t*>(a.x_raw + e);
+          const int nt = col >> 3;
+          s1[nt][0] += v0; s1[nt][1] += v1; s2[nt][0] = fmaf(v0, bf_lo(yr), s2[nt][0]); s2[nt][1] = fmaf(v1, bf_hi(yr), s2[nt][1]);
+        }
+      }
+    });
+    if (a.xn.enabled) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          reduce_cols_to_smem(s1[nt][e], &sh_s[nt * 8 + 2 * t + e][0]);
+          reduce_cols_to_smem(s2[nt][e], &sh_s[nt * 8 + 2 * t + e][1]);
+        }
+      __syncthreads();
+      if (tid < 32) norm_backward_image_sums(a.xn, img, cfx, &sh_s[0][0]);
+    }
+  }
+}
+
+// ---- weight gradient ----------------------------------------------------------------------------------------------------------------------------
+// dw[k][r][s][c] = sum over (image, pixel) of dy[pix][k] * z[pix + (r, s) - PAD][c] as the GEMM D[(tap, c)][k] += Zt[(tap, c)][pix] * dy[pix][k]: M = KS*KS*CI
+// rows, N = NT*8 output channels, K = pixels (16 consecutive pixels of a row per k-step). Both operands need PIXEL pairs in a register, so they are staged
+// channel-planar: dyT[k][pix] and Z[c][(y + PAD) * Wp + x + PAD]; a tap shifts the pixel index by r*Wp + s, which is odd for odd s, so a second copy of Z
+// shifted by one pixel (Z1[i] = Z0[i + 1]) keeps every fragment register one ALIGNED 32-bit shared load (Wp is even: the parity of the shift is s & 1).
+// z (the layer's input) is normalised while staging, dy is assembled from dz and y while staging (and summed into the bias gradient); each warp keeps
+// its share of D in registers across all the CTA's images, the CTA reduces once in shared memory and adds into dw with one atomic per element.
+struct WgradArgs {
+  int n, h, w, c_src, k_out, act; float slope;
+  const bf16* x; const bf16* dz; const bf16* y;
+  float* dw; float* dbias; float* d_bn_w; float* d_bn_b; float* d_gn_w; float* d_gn_b;
+  dcv_sc_norm xn, yn;
+};
+
+__device__ __forceinline__ void store_pair_planar(bf16* plane, int pos, float lo, float hi) {
+  if ((pos & 1) == 0) *reinterpret_cast<uint32_t*>(plane + pos) = pack2(lo, hi);
+  else { plane[pos] = __float2bfloat16_rn(lo); plane[pos + 1] = __float2bfloat16_rn(hi); }
+}
+
+template <int CI, int NT, int KS>
+__global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PAD = KS / 2, MROWS = KS * KS * CI, MT = (MROWS + 15) / 16, KO = NT * 8;
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, PS = Hp * Wp;   // PS: plane stride (elements), even
+  bf16* z0 = reinterpret_cast<bf16*>(smem_raw);          // [CI][PS]
+  bf16* z1 = z0 + (size_t)CI * PS;                       // [CI][PS], z1[i] = z0[i + 1]
+  bf16* dyT = z1 + (size_t)CI * PS;                      // [KO][HW]
+  float* sh_dw = reinterpret_cast<float*>(dyT + (size_t)KO * HW);   // [MT*16][KO]
+  __shared__ Coef cfx, cfy;
+  __shared__ float sh_db[KO];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 2 * CI * PS / 8; i += kThreads) reinterpret_cast<uint4*>(z0)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < KO * HW / 8; i += kThreads) reinterpret_cast<uint4*>(dyT)[i] = make_uint4(0u, 0u, 0u, 0u);   // rows >= k_out stay zero
+  for (int i = tid; i < MT * 16 * KO; i += kThreads) sh_dw[i] = 0.f;
+  if (tid < KO) sh_db[tid] = 0.f;
+  // per-thread A row offsets (32-bit words into z0 / z1): rows g and g + 8 of every m-tile
+  int zoff[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int row = mt * 16 + g + 8 * h2, tap = row / CI, c = row % CI, r = tap / KS, s = tap % KS;
+      zoff[mt][h2] = row < MROWS ? ((s & 1) * CI * PS + c * PS + r * Wp + s - (s & 1)) / 2 : 0;
+    }
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  float db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) db[i] = 0.f;
+  const uint32_t* zw = reinterpret_cast<const uint32_t*>(z0);
+  const uint32_t* dw_ = reinterpret_cast<const uint32_t*>(dyT);
+
+  for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+    __syncthreads();   // previous image consumed / initial zeroing done
+    if (warp == 0 && a.xn.enabled) norm_forward_coeffs(a.xn, img, cfx, false);
+    if (warp == 1 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy, img == 0, a.d_bn_w, a.d_bn_b, a.d_gn_w, a.d_gn_b);
+    __syncthreads();
+    // ---- stage z (planar, two copies) and dy (planar)
+    {
+      SrcPlain sx{a.x, a.xn.enabled ? &cfx : nullptr};
+      const size_t e_img = (size_t)img * HW * a.c_src;
+      if (a.c_src == CI && (e_img % 8) == 0) {
+        for (int v = tid; v < HW * CI / 8; v += kThreads) {
+          const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix / W, x = pix - y * W, pos = (y + PAD) * Wp + x + PAD;
+          float f[8];
+          sx.load8(e_img + e0, c0, CI - 1, f);
+          if (CI == 4) {   // pixels (x, x + 1), channels 0..3: a pixel PAIR per plane
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { store_pair_planar(z0 + c * PS, pos, f[c], f[4 + c]); store_pair_planar(z1 + c * PS, pos - 1, f[c], f[4 + c]); }
+          } else {         // 8 channels of one pixel
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const bf16 b = __float2bfloat16_rn(f[i]); z0[(c0 + i) * PS + pos] = b; z1[(c0 + i) * PS + pos - 1] = b; }
+          }
+        }
+      } else {
+        for (int pix = tid; pix < HW; pix += kThreads) {
+          const int y = pix / W, x = pix - y * W, pos = (y + PAD) * Wp + x + PAD;
+          for (int c = 0; c < a.c_src; ++c) { const bf16 b = __float2bfloat16_rn(sx.load1(e_img + (size_t)pix * a.c_src + c, c)); z0[c * PS + pos] = b; z1[c * PS + pos - 1] = b; }
+        }
+      }
+      SrcDy sd{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
+      const size_t k_img = (size_t)img * HW * a.k_out;
+      const int kv = a.k_out;   // channels of dy
+      if ((kv == 4 || kv % 8 == 0) && (k_img % 8) == 0) {
+        for (int v = tid; v < HW * kv / 8; v += kThreads) {
+          const int e0 = v * 8, pix = e0 / kv, c0 = e0 % kv;
+          float f[8];
+          sd.load8(k_img + e0, c0, kv - 1, f);   // kv is a power of two here (4, 8, 16)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) db[i] += round_bf(f[i]);
+          if (kv == 4) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t*>(dyT + (size_t)c * HW + pix) = pack2(f[c], f[4 + c]);   // pix is even
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dyT[(size_t)(c0 + i) * HW + pix] = __float2bfloat16_rn(f[i]);
+          }
+        }
+      } else {
+        for (int pix = tid; pix < HW; pix += kThreads)
+          for (int c = 0; c < kv; ++c) {
+            const float v = round_bf(sd.load1(k_img + (size_t)pix * kv + c, c));
+            dyT[(size_t)c * HW + pix] = __float2bfloat16_rn(v);
+            atomicAdd(&sh_db[c], v);
+          }
+      }
+    }
+    __syncthreads();
+    // ---- MMA over the image's pixel chunks
+    for (int ch = warp; ch < HW / 16; ch += kWarps) {
+      const int p0 = ch * 16, y = p0 / W, x0 = p0 - y * W;
+      const int pw = (y * Wp + x0) / 2 + t;   // pixel-pair word of this thread's k columns (2t, 2t + 1); + 4 words = pixels + 8
+      uint32_t b0[NT], b1[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int ko = nt * 8 + g;
+        b0[nt] = dw_[((size_t)ko * HW + p0) / 2 + t];
+        b1[nt] = dw_[((size_t)ko * HW + p0) / 2 + t + 4];
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t a0 = zw[zoff[mt][0] + pw], a1 = zw[zoff[mt][1] + pw], a2 = zw[zoff[mt][0] + pw + 4], a3 = zw[zoff[mt][1] + pw + 4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma16816(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+      }
+    }
+  }
+  // ---- CTA reduction, then one atomic per weight-gradient element
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int r0 = mt * 16 + g, col = nt * 8 + 2 * t;
+      atomicAdd(&sh_dw[r0 * KO + col], acc[mt][nt][0]); atomicAdd(&sh_dw[r0 * KO + col + 1], acc[mt][nt][1]);
+      atomicAdd(&sh_dw[(r0 + 8) * KO + col], acc[mt][nt][2]); atomicAdd(&sh_dw[(r0 + 8) * KO + col + 1], acc[mt][nt][3]);
+    }
+  {
+    // bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 fixed per thread (kThreads * 8 is a multiple of kv)
+    const int kv = a.k_out;
+    if ((kv == 4 || kv % 8 == 0)) {
+      const int c0 = (tid * 8) % kv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (db[i] != 0.f) atomicAdd(&sh_db[(c0 + i) & (kv - 1)], db[i]);
+    }
+  }
+  __syncthreads();
+  const int total = a.k_out * KS * KS * a.c_src;
+  for (int i = tid; i < total; i += kThreads) {
+    const int c = i % a.c_src, tap = (i / a.c_src) % (KS * KS), k = i / (a.c_src * KS * KS);
+    const float v = sh_dw[(tap * CI + c) * KO + k];
+    if (v != 0.f) atomicAdd(a.dw + i, v);
+  }
+  if (a.dbias && tid < a.k_out) atomicAdd(a.dbias + tid, sh_db[tid]);
+}
+
+// ---- normalise (+ average-pool) a raw output into a plain tensor: the consumer of a pending normalisation that is not one of the kernels above ----------
+// zp[n][oy][ox][c] = A[n][c] * mean_{pool x pool}(y) + B[n][c]   (pooling is linear and the affine is per (image, channel): pool(z) = A*pool(y) + B).
+struct PoolArgs { int n, h, w, c, pool, update_running; const bf16* y; bf16* z; const bf16* dzp; bf16* dz; dcv_sc_norm nd; };
+
+__global__ void __launch_bounds__(kThreads) sc_affine_pool_fwd_kernel(const PoolArgs a) {
+  __shared__ Coef cf;
+  const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
+  const float inv = 1.f / (float)(a.pool * a.pool);
+  for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+    __syncthreads();
+    if (tid < 32) norm_forward_coeffs(a.nd, img, cf, a.update_running != 0 && img == 0);
+    __syncthreads();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.y + (size_t)img * a.h * a.w * a.c);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(a.z + (size_t)img * oh * ow * a.c);
+    for (int i = tid; i < oh * ow * c2; i += kThreads) {
+      const int cp = i % c2, opix = i / c2, oy = opix / ow, ox = opix - oy * ow;
+      float v0 = 0.f, v1 = 0.f;
+      for (int r = 0; r < a.pool; ++r)
+        for (int s = 0; s < a.pool; ++s) {
+          const uint32_t u = src[((size_t)(oy * a.pool + r) * a.w + ox * a.pool + s) * c2 + cp];
+          v0 += bf_lo(u); v1 += bf_hi(u);
+        }
+      dst[i] = pack2(fmaf(cf.A[2 * cp], v0 * inv, cf.B[2 * cp]), fmaf(cf.A[2 * cp + 1], v1 * inv, cf.B[2 * cp + 1]));
+    }
+  }
+}
+
+// backward: dz = dzp / pool^2 spread over the window (written, bf16), s[n][c] = {sum dz, sum dz*y}, then the image's adjoint sums.
+__global__ void __launch_bounds__(kThreads) sc_affine_pool_bwd_kernel(const PoolArgs a) {
+  __shared__ Coef cf;
+  __shared__ float sh_s[kMaxC][2];
+  const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
+  const float inv = 1.f / (float)(a.pool * a.pool);
+  const bool fixed_cp = (kThreads % c2) == 0;   // a thread then always works on the same channel pair: sums stay in registers
+  for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+    __syncthreads();
+    if (tid < kMaxC * 2) (&sh_s[0][0])[tid] = 0.f;
+    __syncthreads();
+    const uint32_t* ysrc = reinterpret_cast<const uint32_t*>(a.y + (size_t)img * a.h * a.w * a.c);
+    const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(a.dzp + (size_t)img * oh * ow * a.c);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(a.dz + (size_t)img * a.h * a.w * a.c);
+    float t1a = 0.f, t1b = 0.f, t2a = 0.f, t2b = 0.f;
+    for (int i = tid; i < oh * ow * c2; i += kThreads) {
+      const int cp = i % c2, opix = i / c2, oy = opix / ow, ox = opix - oy * ow;
+      const uint32_t gu = gsrc[i];
+      const float g0 = round_bf(bf_lo(gu) * inv), g1 = round_bf(bf_hi(gu) * inv);
+      const uint32_t gp = pack2(g0, g1);
+      float l1a = 0.f, l1b = 0.f, l2a = 0.f, l2b = 0.f;
+      for (int r = 0; r < a.pool; ++r)
+        for (int s = 0; s < a.pool; ++s) {
+          const size_t e = ((size_t)(oy * a.pool + r) * a.w + ox * a.pool + s) * c2 + cp;
+          const uint32_t yu = ysrc[e];
+          dst[e] = gp;
+          l1a += g0; l1b += g1; l2a = fmaf(g0, bf_lo(yu), l2a); l2b = fmaf(g1, bf_hi(yu), l2b);
+        }
+      if (fixed_cp) { t1a += l1a; t1b += l1b; t2a += l2a; t2b += l2b; }
+      else { atomicAdd(&sh_s[2 * cp][0], l1a); atomicAdd(&sh_s[2 * cp + 1][0], l1b); atomicAdd(&sh_s[2 * cp][1], l2a); atomicAdd(&sh_s[2 * cp + 1][1], l2b); }
+    }
+    if (fixed_cp) {
+      const int cp = tid % c2;
+      atomicAdd(&sh_s[2 * cp][0], t1a); atomicAdd(&sh_s[2 * cp + 1][0], t1b); atomicAdd(&sh_s[2 * cp][1], t2a); atomicAdd(&sh_s[2 * cp + 1][1], t2b);
+    }
+    __syncthreads();
+    if (tid < 32) norm_backward_image_sums(a.nd, img, cf, &sh_s[0][0]);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------------------------------
+static int pick_ci(int c) { return c <= 4 ? 4 : (c == 16 ? 16 : 0); }
+
+static bool shape_ok(const dcv_conv_shape* s, int dtype) {
+  if (!s || dtype != DCV_BF16) return false;
+  if (s->stride_h != 1 || s->stride_w != 1 || s->dil_h != 1 || s->dil_w != 1 || s->r != s->s || (s->r != 3 && s->r != 5)) return false;
+  if (s->pad_h != s->r / 2 || s->pad_w != s->r / 2 || s->p != s->h || s->q != s->w) return false;
+  if (s->w % 16 != 0 || s->w > 64 || s->h > 64 || (s->h * s->w) % 16 != 0) return false;
+  const int ci = pick_ci(s->c), ki = pick_ci(s->k);
+  if (!ci || !ki || s->k % 2 != 0 || s->c < 1) return false;
+  if (s->r == 5 && (ci != 4 || ki != 4)) return false;   // 5x5 over 16 channels: 25 k-steps of resident weight fragments do not fit the register file
+  return true;
+}
+
+static int num_ctas(int n) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = kNumSMs; }
+  return n < 4 * sms ? n : 4 * sms;
+}
+
+template <typename K> static int set_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    DCV_REQUIRE(bytes <= 200 * 1024, "sc: %zu bytes of shared memory needed", bytes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  }
+  return 0;
+}
+
+static dcv_sc_norm norm_or_off(const dcv_sc_norm* nd) { dcv_sc_norm z{}; return nd ? *nd : z; }
+
+static int check_norm(const dcv_sc_norm* nd, int n, int c, int hw, const char* what, bool backward) {
+  if (!nd || !nd->enabled) return 0;
+  DCV_REQUIRE(nd->n == n && nd->c == c && nd->hw == hw, "%s: normalisation descriptor is for [%d][%d][%d], tensor is [%d][%d][%d]", what, nd->n, nd->hw, nd->c, n, hw, c);
+  DCV_REQUIRE(c <= kMaxC && c % 2 == 0, "%s: %d channels (this path serves even channel counts up to %d)", what, c, kMaxC);
+  DCV_REQUIRE(nd->stats_nc && (!nd->use_bn || !nd->bn_training || nd->bn_sums), "%s: missing statistics buffers", what);
+  DCV_REQUIRE(!nd->use_gn || (nd->gn_groups > 0 && c % nd->gn_groups == 0), "%s: num_channels=%d not divisible by num_groups=%d", what, c, nd->gn_groups);
+  DCV_REQUIRE(!nd->use_bn || nd->bn_training || (nd->bn_running_mean && nd->bn_running_var), "%s: eval-mode BatchNorm needs running statistics", what);
+  DCV_REQUIRE(!backward || (nd->s_nc && nd->u_sums), "%s: missing backward sum buffers", what);
+  return 0;
+}
+
+}  // namespace sc
+}  // namespace dcv
+
+extern "C" {
+
+int dcv_sc_conv_supported(const dcv_conv_shape* shape, int dtype) { return dcv::sc::shape_ok(shape, dtype) ? 1 : 0; }
+
+size_t dcv_sc_norm_floats(int n, int c, int which) {
+  /* which: 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums */
+  switch (which) {
+    case 0: case 2: return (size_t)n * c * 2;
+    case 1: return (size_t)dcv::sc::kShards * c * 2;
+    default: return (size_t)dcv::sc::kShards * c * 4;
+  }
+}
+
+#define SC_DISPATCH(CI_, NT_, KS_, KERN, ARGS, SMEM)                                                                \
+  do {                                                                                                              \
+    auto kern = KERN<CI_, NT_, KS_>;                                                                                \
+    if (set_smem(kern, SMEM)) return 1;                                                                             \
+    kern<<<num_ctas((ARGS).n), kThreads, SMEM, st>>>(ARGS);                                                         \
+  } while (0)
+
+int dcv_sc_conv_fwd(const dcv_conv_shape* s, const void* x, const dcv_sc_norm* x_norm, int update_running, const void* w, const float* bias, int act, float slope,
+                    void* y, const dcv_sc_norm* y_norm, void* stream) {
+  using namespace dcv; using namespace dcv::sc;
+  DCV_REQUIRE(shape_ok(s, DCV_BF16), "sc_conv_fwd: shape not served by the few-channel kernels (see dcv_sc_conv_supported)");
+  DCV_REQUIRE(x && w && y, "sc_conv_fwd: null pointer");
+  if (check_norm(x_norm, s->n, s->c, s->h * s->w, "sc_conv_fwd (input)", false) || check_norm(y_norm, s->n, s->k, s->h * s->w, "sc_conv_fwd (output)", false)) return 1;
+  cudaStream_t st = as_stream(stream);
+  FwdArgs a{};
+  a.n = s->n; a.h = s->h; a.w = s->w; a.c_src = s->c; a.k_out = s->k; a.act = act; a.slope = slope; a.update_running = update_running;
+  a.x = (const bf16*)x; a.wgt = (const bf16*)w; a.bias = bias; a.y = (bf16*)y; a.xn = norm_or_off(x_norm); a.yn = norm_or_off(y_norm);
+  const int ci = pick_ci(s->c), nt = s->k <= 8 ? 1 : 2;
+  const size_t smem = (size_t)(s->h + s->r - 1) * (s->w + s->r - 1) * ci * 2;
+  if (s->r == 5) SC_DISPATCH(4, 1, 5, sc_fwd_kernel, a, smem);
+  else if (ci == 4 && nt == 1) SC_DISPATCH(4, 1, 3, sc_fwd_kernel, a, smem);
+  else if (ci == 4) SC_DISPATCH(4, 2, 3, sc_fwd_kernel, a, smem);
+  else if (nt == 1) SC_DISPATCH(16, 1, 3, sc_fwd_kernel, a, smem);
+  else SC_DISPATCH(16, 2, 3, sc_fwd_kernel, a, smem);
+  DCV_LAUNCH_CHECK("sc_fwd_kernel");
+  return 0;
+}
+
+int dcv_sc_conv_dgrad(const dcv_conv_shape* s, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope, const void* w, void* dx,
+                      const void* x_raw, const dcv_sc_norm* x_norm, void* stream) {
+  using namespace dcv; using namespace dcv::sc;
+  DCV_REQUIRE(shape_ok(s, DCV_BF16) && s->c % 2 == 0, "sc_conv_dgrad: shape not served by the few-channel kernels");
+  DCV_REQUIRE(dz && y && w && dx, "sc_conv_dgrad: null pointer");
+  if (check_norm(y_norm, s->n, s->k, s->h * s->w, "sc_conv_dgrad (output)", true) || check_norm(x_norm, s->n, s->c, s->h * s->w, "sc_conv_dgrad (input)", true)) return 1;
+  DCV_REQUIRE(!(x_norm && x_norm->enabled) || x_raw, "sc_conv_dgrad: the producer's raw output is needed for its backward sums");
+  cudaStream_t st = as_stream(stream);
+  DgradArgs a{};
+  a.n = s->n; a.h = s->h; a.w = s->w; a.c_in = s->c; a.k_out = s->k; a.act = act; a.slope = slope;
+  a.dz = (const bf16*)dz; a.y = (const bf16*)y; a.wgt = (const bf16*)w; a.dx = (bf16*)dx; a.x_raw = (const bf16*)x_raw; a.yn = norm_or_off(y_norm); a.xn = norm_or_off(x_norm);
+  const int ki = pick_ci(s->k), nt = s->c <= 8 ? 1 : 2;
+  const size_t smem = (size_t)(s->h + s->r - 1) * (s->w + s->r - 1) * ki * 2;
+  if (s->r == 5) SC_DISPATCH(4, 1, 5, sc_dgrad_kernel, a, smem);
+  else if (ki == 4 && nt == 1) SC_DISPATCH(4, 1, 3, sc_dgrad_kernel, a, smem);
+  else if (ki == 4) SC_DISPATCH(4, 2, 3, sc_dgrad_kernel, a, smem);
+  else if (nt == 1) SC_DISPATCH(16, 1, 3, sc_dgrad_kernel, a, smem);
+  else SC_DISPATCH(16, 2, 3, sc_dgrad_kernel, a, smem);
+  DCV_LAUNCH_CHECK("sc_dgrad_kernel");
+  return 0;
+}
+
+int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm* x_norm, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope,
+                      float* dw, float* dbias, float* d_bn_w, float* d_bn_b, float* d_gn_w, float* d_gn_b, void* stream) {
+  using namespace dcv; using namespace dcv::sc;
+  DCV_REQUIRE(shape_ok(s, DCV_BF16), "sc_conv_wgrad: shape not served by the few-channel kernels");
+  DCV_REQUIRE(x && dz && y && dw, "sc_conv_wgrad: null pointer");
+  if (check_norm(x_norm, s->n, s->c, s->h * s->w, "sc_conv_wgrad (input)", false) || check_norm(y_norm, s->n, s->k, s->h * s->w, "sc_conv_wgrad (output)", true)) return 1;
+  cudaStream_t st = as_stream(stream);
+  WgradArgs a{};
+  a.n = s->n; a.h = s->h; a.w = s->w; a.c_src = s->c; a.k_out = s->k; a.act = act; a.slope = slope;
+  a.x = (const bf16*)x; a.dz = (const bf16*)dz; a.y = (const bf16*)y; a.dw = dw; a.dbias = dbias; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b; a.d_gn_w = d_gn_w; a.d_gn_b = d_gn_b;
+  a.xn = norm_or_off(x_norm); a.yn = norm_or_off(y_norm);
+  const int ci = pick_ci(s->c), nt = s->k <= 8 ? 1 : 2, ko = nt * 8, mt = (s->r * s->s * ci + 15) / 16;
+  const size_t ps = (size_t)(s->h + s->r - 1) * (s->w + s->r - 1), hw = (size_t)s->h * s->w;
+  const size_t smem = 2 * ci * ps * 2 + ko * hw * 2 + (size_t)mt * 16 * ko * 4;
+  // persistent over images: fewer CTAs = fewer atomics on dw
+  auto grid_of = [&](int n) { const int g = num_ctas(n); return g < 2 * kNumSMs ? g : 2 * kNumSMs; };
+#define SC_WGRAD(CI_, NT_, KS_)                                                         \
+  do {                                                                                  \
+    auto kern = sc_wgrad_kernel<CI_, NT_, KS_>;                                         \
+    if (set_smem(kern, smem)) return 1;                                                 \
+    kern<<<grid_of(a.n), kThreads, smem, st>>>(a);                                      \
+  } while (0)
+  if (s->r == 5) SC_WGRAD(4, 1, 5);
+  else if (ci == 4 && nt == 1) SC_WGRAD(4, 1, 3);
+  else if (ci == 4) SC_WGRAD(4, 2, 3);
+  else if (nt == 1) SC_WGRAD(16, 1, 3);
+  else SC_WGRAD(16, 2, 3);
+#undef SC_WGRAD
+  DCV_LAUNCH_CHECK("sc_wgrad_kernel");
+  return 0;
+}
+
+int dcv_sc_affine_pool_fwd(const void* y, const dcv_sc_norm* norm, int update_running, void* z, int n, int h, int w, int c, int pool, void* stream) {
+  using namespace dcv; using namespace dcv::sc;
+  DCV_REQUIRE(y && z && norm && norm->enabled && n > 0 && pool >= 1 && h % pool == 0 && w % pool == 0, "sc_affine_pool_fwd: bad arguments");
+  if (check_norm(norm, n, c, h * w, "sc_affine_pool_fwd", false)) return 1;
+  PoolArgs a{}; a.n = n; a.h = h; a.w = w; a.c = c; a.pool = pool; a.update_running = update_running; a.y = (const bf16*)y; a.z = (bf16*)z; a.nd = *norm;
+  sc_affine_pool_fwd_kernel<<<num_ctas(n), kThreads, 0, as_stream(stream)>>>(a);
+  DCV_LAUNCH_CHECK("sc_affine_pool_fwd_kernel");
+  return 0;
+}
+
+int dcv_sc_affine_pool_bwd(const void* dzp, const void* y, const dcv_sc_norm* norm, void* dz, int n, int h, int w, int c, int pool, void* stream) {
+  using namespace dcv; using namespace dcv::sc;
+  DCV_REQUIRE(dzp && y && dz && norm && norm->enabled && n > 0 && pool >= 1 && h % pool == 0 && w % pool == 0, "sc_affine_pool_bwd: bad arguments");
+  if (check_norm(norm, n, c, h * w, "sc_affine_pool_bwd", true)) return 1;
+  PoolArgs a{}; a.n = n; a.h = h; a.w = w; a.c = c; a.pool = pool; a.y = (const bf16*)y; a.dzp = (const bf16*)dzp; a.dz = (bf16*)dz; a.nd = *norm;
+  sc_affine_pool_bwd_kernel<<<num_ctas(n), kThreads, 0, as_stream(stream)>>>(a);
+  DCV_LAUNCH_CHECK("sc_affine_pool_bwd_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -65,13 +65,22 @@ class DeepcvModule(torch.nn.Module):
         if x.device.type == 'cuda' and x.dim() == 4:
             x = ops.as_nhwc(x)
 
-        if self.is_sequential_nn():
-            return self._child_modules(x)
-
+        # A few-channel convolution block may hand its RAW output on with the normalisation still pending (`ops.PendingAffine`) when the next
+        # submodule applies it while loading (another such block, an average pooling) and nobody else refers to that output.
+        names = list(self._child_modules._modules.keys()) if isinstance(self._child_modules, torch.nn.Sequential) else list(self._child_modules.keys())
+        children = [self._child_modules._modules[n] for n in names] if isinstance(self._child_modules, torch.nn.Sequential) else [self._child_modules[n] for n in names]
+        sequential = self.is_sequential_nn()
         referenced_output_features: Dict[str, torch.Tensor] = {}
-        remaining_submodule_references = copy.copy(self._submodule_references)
-        for name, subm in self._child_modules.items():
-            refs = getattr(subm, 'referenced_submodules', None)
+        remaining_submodule_references = {} if sequential else copy.copy(self._submodule_references)
+        for i, (name, subm) in enumerate(zip(names, children)):
+            if isinstance(x, ops.PendingAffine) and not getattr(subm, 'accepts_pending_affine', False):
+                x = ops.materialize(x)
+            n_referrers = sum(name in r for r in remaining_submodule_references.values())
+            kwargs = {}
+            if getattr(subm, 'can_defer_affine', False):
+                kwargs['defer_affine'] = i + 1 < len(children) and n_referrers == 0 and getattr(children[i + 1], 'accepts_pending_affine', False) \
+                    and not getattr(children[i + 1], 'referenced_submodules', None)
+            refs = None if sequential else getattr(subm, 'referenced_submodules', None)
             if refs is not None and len(refs) > 0:
                 current_subm_references = OrderedDict([(ref, referenced_output_features[ref]) for ref in refs])
                 # Release stored features once their last referrer has consumed them
@@ -79,15 +88,16 @@ class DeepcvModule(torch.nn.Module):
                 for referenced_submodule in refs:
                     if not any(referenced_submodule in r for r in remaining_submodule_references.values()):
                         referenced_output_features.pop(referenced_submodule, None)
-                x = subm(x, referenced_submodules_out=current_subm_references)
+                x = subm(x, referenced_submodules_out=current_subm_references, **kwargs)
             else:
-                x = subm(x)
+                x = subm(x, **kwargs)
             # Keep this output if a later submodule names it in `_from`. The kept tensor and the one flowing on are two autograd
             # aliases whose gradients are summed by a library kernel (ops.fork).
             n_referrers = sum(name in r for r in remaining_submodule_references.values())
             if n_referrers > 0:
+                x = ops.materialize(x)
                 x, referenced_output_features[name] = ops.fork(x) if x.device.type == 'cuda' else (x, x)
-        return x
+        return ops.materialize(x)
 
     def __str__(self) -> str:
         return str(self.describe())

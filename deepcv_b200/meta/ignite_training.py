@@ -445,6 +445,11 @@ class GraphedTrainStep:
                     self.flat.zeroed_by_step = False
 
     def _eager_step(self) -> torch.Tensor:
+        # Drop the previous iteration's losses first: they keep its autograd graph alive, and with it the parameters' AccumulateGrad nodes, which remember
+        # the stream they were created on (the warm-up side stream) — reused inside the capture, the engine would make the capturing stream wait for
+        # that uncaptured stream at the end of backward ("dependency created on uncaptured work in another stream").
+        self.static_losses.clear()
+        self.static_loss = None
         self.ctx.refresh_shadows()
         x = self.static_x
         if self.preprocess is not None:

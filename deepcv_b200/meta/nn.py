@@ -148,8 +148,14 @@ class AvgPool2d(torch.nn.AvgPool2d):
         if _pair(padding) != (0, 0) or ceil_mode or divisor_override is not None:
             raise NotImplementedError('deepcv_b200: average pooling with padding / ceil_mode / divisor_override is not built for sm_100a (no PyTorch fallback on this path)')
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    accepts_pending_affine = True   # a raw block output: the pending normalisation is applied inside the pooling kernel (pool(A*y + B) = A*pool(y) + B)
+
+    def forward(self, x) -> torch.Tensor:
         k, s = _pair(self.kernel_size), _pair(self.stride if self.stride is not None else self.kernel_size)
+        if isinstance(x, ops.PendingAffine):
+            if k == s and k[0] == k[1] and x.shape[2] % k[0] == 0 and x.shape[3] % k[0] == 0:
+                return ops.sc_affine_pool(x, k[0])
+            x = ops.materialize(x)
         if x.device.type == 'meta':
             return meta_like((x.shape[0], x.shape[1], (x.shape[2] - k[0]) // s[0] + 1, (x.shape[3] - k[1]) // s[1] + 1), x.dtype)
         return ops.avg_pool2d(x, k, s)
@@ -236,13 +242,32 @@ class FusedLayer(torch.nn.Sequential):
         ow = (x.shape[3] + 2 * p[1] - d[1] * (k[1] - 1) - 1) // s[1] + 1
         return meta_like((x.shape[0], op.out_channels, oh, ow), x.dtype)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if x.device.type == 'meta':
+    accepts_pending_affine = True   # few-channel convolutions normalise their input while loading it
+    can_defer_affine = True         # ... and may hand their own raw output on (`defer_affine=True`: the caller promises a consumer that accepts it)
+
+    def _few_channel_path(self, x) -> bool:
+        op = self._op
+        return (isinstance(op, torch.nn.Conv2d) and self.algo == ALGO_AUTO and x.device.type == 'cuda' and len(x.shape) == 4
+                and ops.sc_conv_supported(tuple(x.shape), op.weight, op.stride, op.padding, op.dilation, x.dtype))
+
+    def forward(self, x, defer_affine: bool = False):
+        if not isinstance(x, ops.PendingAffine) and x.device.type == 'meta':
             return self._meta_forward(x)
         op, bn, gn = self._op, self._bn, self._gn
+        few = self._few_channel_path(x)
+        if isinstance(x, ops.PendingAffine) and not few:
+            x = ops.materialize(x)
         if isinstance(op, torch.nn.Linear):
             return ops.linear_act(x, op.weight, op.bias, self._act, self._slope, grad_out=self._grad_out, step_ctx=self._step_ctx)
         training = bn.training if bn is not None else self.training
+        if few:
+            out = ops.sc_conv_block(x, op.weight, op.bias, op.padding, self._act, self._slope, norm=self._norm_config(), training=training,
+                                    bn_weight=bn.weight if bn is not None else None, bn_bias=bn.bias if bn is not None else None,
+                                    running_mean=bn.running_mean if bn is not None else None, running_var=bn.running_var if bn is not None else None,
+                                    num_batches_tracked=bn.num_batches_tracked if bn is not None else None,
+                                    gn_weight=gn.weight if gn is not None else None, gn_bias=gn.bias if gn is not None else None,
+                                    grad_out=self._grad_out, step_ctx=self._step_ctx)
+            return out if defer_affine else ops.materialize(out)
         return ops.conv_block(x, op.weight, op.bias, op.stride, op.padding, op.dilation, self._act, self._slope, norm=self._norm_config(), training=training,
                               bn_weight=bn.weight if bn is not None else None, bn_bias=bn.bias if bn is not None else None,
                               running_mean=bn.running_mean if bn is not None else None, running_var=bn.running_var if bn is not None else None,

@@ -16,10 +16,11 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, NormParams, check, lib)
+from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, NormParams, ScNorm, check, lib)
 
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
-           'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext']
+           'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext', 'PendingAffine', 'sc_conv_block',
+           'sc_conv_supported', 'sc_affine_pool', 'materialize']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
 _DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
@@ -448,6 +449,192 @@ def conv_block(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     norm = norm if norm is not None else NormConfig()
     return _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
                             tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Few-channel convolution blocks (csrc/conv_small.cu): raw outputs with a PENDING normalisation travel between submodules
+
+_USE_SC = os.environ.get('DCV_NO_SC') is None   # tuning aid: DCV_NO_SC=1 keeps the few-channel layers on the direct kernels + separate normalisation passes
+
+
+class _NormLink:
+    """ Device-side state of one block's pending BatchNorm o GroupNorm for ONE step: the `dcv_sc_norm` descriptor and the buffers it points to (kept
+    alive here), shared by the producer's and the consumer's autograd nodes. """
+
+    def __init__(self, n, c, hw, cfg: NormConfig, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b, device, sctx: Optional[StepContext], need_backward: bool):
+        f = lambda which: int(lib.dcv_sc_norm_floats(n, c, which))
+        self.stats = torch.empty(f(0), dtype=torch.float32, device=device)
+        bn_training = bool(training or rm is None or rv is None)
+        self.bn_sums = _zeroed_acc((f(1),), device, sctx) if (cfg.use_bn and bn_training) else None
+        self.s_nc = torch.empty(f(2), dtype=torch.float32, device=device) if need_backward else None
+        self.u_sums = _zeroed_acc((f(3),), device, sctx) if need_backward else None
+        self.keep = (bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
+        self.struct = ScNorm(1, n, c, hw, int(cfg.use_bn), int(bn_training), cfg.bn_eps, cfg.bn_momentum, _ptr(bn_w), _ptr(bn_b), _ptr(rm), _ptr(rv), _ptr(nbt),
+                             int(cfg.use_gn), cfg.gn_groups, cfg.gn_eps, _ptr(gn_w), _ptr(gn_b), _ptr(self.stats), _ptr(self.bn_sums), _ptr(self.s_nc), _ptr(self.u_sums))
+        self.update_running = bool(cfg.use_bn and training and rm is not None and rv is not None)
+        self.consumed = False
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
+def _zeroed_acc(shape, device, sctx: Optional[StepContext]) -> torch.Tensor:
+    """ An accumulator that is zero when its first kernel runs: a slice of the step's pre-zeroed arena, or a fresh buffer + one memset. """
+    t = _acc_empty(shape, device, sctx)
+    if not _pz(sctx):
+        check(lib.dcv_fill_zero(_ptr(t), t.numel() * 4, _stream()), 'fill_zero(accumulator)')
+    return t
+
+
+class PendingAffine:
+    """ A block's RAW output `y` (conv + bias + activation) whose BatchNorm o GroupNorm has not been applied: the consumer applies z = A[n][c]*y + B[n][c]
+    while loading (few-channel convolution, average pooling) or `materialize()`s it. Exactly one consumer: its backward produces the producer's sums. Not
+    a tensor on purpose: only the modules of this package (`FusedLayer`, `AvgPool2d`, `DeepcvModule.forward`) ever see one. """
+    __slots__ = ('y', 'link')
+
+    def __init__(self, y: torch.Tensor, link: _NormLink):
+        self.y, self.link = y, link
+
+    shape = property(lambda self: self.y.shape)
+    dtype = property(lambda self: self.y.dtype)
+    device = property(lambda self: self.y.device)
+
+    def take(self) -> Tuple[torch.Tensor, _NormLink]:
+        if self.link.consumed:
+            raise RuntimeError('deepcv_b200: a pending normalisation was consumed twice (materialize() it before using the tensor in two places)')
+        self.link.consumed = True
+        return self.y, self.link
+
+
+def sc_conv_supported(x_shape, weight: torch.Tensor, stride, padding, dilation, dtype: torch.dtype) -> bool:
+    if not _USE_SC or dtype != torch.bfloat16:
+        return False
+    n, c, h, w = x_shape
+    k, cw, r, s = weight.shape
+    if cw != c:
+        return False
+    p = (h + 2 * padding[0] - dilation[0] * (r - 1) - 1) // stride[0] + 1
+    q = (w + 2 * padding[1] - dilation[1] * (s - 1) - 1) // stride[1] + 1
+    shape = ConvShape(n, h, w, c, k, r, s, stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], p, q)
+    return bool(lib.dcv_sc_conv_supported(ctypes.byref(shape), DCV_BF16))
+
+
+class _ScConv(torch.autograd.Function):
+    """ One few-channel block: forward = ONE launch (normalise-on-load of the input, convolution, bias, activation, statistics), backward = weight-gradient
+    launch + data-gradient launch. `x` is a plain tensor or a producer's raw output (meta['xlink'] set); the returned y is raw when the block has a
+    normalisation (the caller wraps it into a `PendingAffine`). The "gradient" exchanged with a producer for its raw output is dz, the gradient w.r.t. the
+    NORMALISED tensor — a private protocol between the nodes of this path, which is why raw outputs never leave it. """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, meta):
+        shape, xlink, cfg, sctx = meta['shape'], meta['xlink'], meta['cfg'], meta['sctx']
+        n, k, p, q = shape.n, shape.k, shape.p, shape.q
+        dev, st = x.device, _stream()
+        w_op = _weight_operand(weight, torch.bfloat16, sctx)
+        y = empty_nhwc(n, k, p, q, torch.bfloat16, dev)
+        ylink = None
+        if cfg.any:
+            ylink = _NormLink(n, k, p * q, cfg, meta['training'], bn_w, bn_b, meta['rm'], meta['rv'], meta['nbt'], gn_w, gn_b, dev, sctx, need_backward=torch.is_grad_enabled())
+        check(lib.dcv_sc_conv_fwd(ctypes.byref(shape), _ptr(x), xlink.ref() if xlink else None, int(bool(xlink and xlink.update_running)), _ptr(w_op), _ptr(bias),
+                                  meta['act'], meta['slope'], _ptr(y), ylink.ref() if ylink else None, st), 'sc_conv_fwd')
+        ctx.save_for_backward(x, w_op, y)
+        ctx.meta, ctx.ylink, ctx.has_bias = meta, ylink, bias is not None
+        ctx.has_affine = (bn_w is not None, bn_b is not None, gn_w is not None, gn_b is not None)
+        meta['ylink'] = ylink
+        return y
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, w_op, y = ctx.saved_tensors
+        meta, ylink = ctx.meta, ctx.ylink
+        shape, xlink, cfg, sctx, grad_out = meta['shape'], meta['xlink'], meta['cfg'], meta['sctx'], meta['grad_out']
+        dev, st = y.device, _stream()
+        dz = as_nhwc(dz.detach(), torch.bfloat16)
+        targets = grad_out if (grad_out and not grad_out.get('_written', False)) else {}
+
+        def target(name, numel_shape, wanted):   # accumulated into by the kernel: a (zeroed) bucket slice, or a fresh zeroed buffer handed to autograd
+            if not wanted:
+                return None
+            t = targets.get(name)
+            return t if t is not None else _zeroed_acc(numel_shape, dev, sctx if name in ('weight', 'bias') else None)
+        k, c = shape.k, shape.c
+        dw = target('weight', (k, shape.r, shape.s, c), ctx.needs_input_grad[1])
+        if dw is not None and 'weight' not in targets:
+            dw = dw.permute(0, 3, 1, 2)
+        dbias = target('bias', (k,), ctx.has_bias and ctx.needs_input_grad[2])
+        # normalisation parameter gradients are OVERWRITTEN by the kernel
+        def plain(name, on):
+            if not on:
+                return None
+            t = targets.get(name)
+            return t if t is not None else torch.empty((k,), dtype=torch.float32, device=dev)
+        d_bn_w, d_bn_b = plain('bn_w', cfg.use_bn and ctx.has_affine[0]), plain('bn_b', cfg.use_bn and ctx.has_affine[1])
+        d_gn_w, d_gn_b = plain('gn_w', cfg.use_gn and ctx.has_affine[2]), plain('gn_b', cfg.use_gn and ctx.has_affine[3])
+        if dw is not None:
+            check(lib.dcv_sc_conv_wgrad(ctypes.byref(shape), _ptr(x), xlink.ref() if xlink else None, _ptr(dz), _ptr(y), ylink.ref() if ylink else None, meta['act'], meta['slope'],
+                                        _ptr(dw), _ptr(dbias), _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'sc_conv_wgrad')
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_nhwc(shape.n, c, shape.h, shape.w, torch.bfloat16, dev)
+            check(lib.dcv_sc_conv_dgrad(ctypes.byref(shape), _ptr(dz), _ptr(y), ylink.ref() if ylink else None, meta['act'], meta['slope'], _ptr(w_op), _ptr(dx),
+                                        _ptr(x) if xlink else None, xlink.ref() if xlink else None, st), 'sc_conv_dgrad')
+
+        def ret(name, g):
+            return None if (g is None or name in targets) else g
+        _backward_done(grad_out, targets)
+        return dx, ret('weight', dw), ret('bias', dbias), ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b), None
+
+
+def sc_conv_block(x, weight: torch.Tensor, bias: Optional[torch.Tensor], padding: Sequence[int], act: int = ACT_NONE, slope: float = 0., norm: Optional[NormConfig] = None,
+                  training: bool = True, bn_weight=None, bn_bias=None, running_mean=None, running_var=None, num_batches_tracked=None, gn_weight=None, gn_bias=None,
+                  grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None):
+    """ A few-channel block (`sc_conv_supported`) on the fused kernels. `x`: bf16 NHWC tensor or `PendingAffine`. Returns a `PendingAffine` when the block has
+    a normalisation, else the activation tensor. """
+    xlink = None
+    if isinstance(x, PendingAffine):
+        x, xlink = x.take()
+    else:
+        x = as_nhwc(x)
+    norm = norm if norm is not None else NormConfig()
+    n, c, h, w = x.shape
+    k, _, r, s = weight.shape
+    shape = ConvShape(n, h, w, c, k, r, s, 1, 1, padding[0], padding[1], 1, 1, h, w)
+    meta = dict(shape=shape, xlink=xlink, cfg=norm, sctx=step_ctx, act=int(act), slope=float(slope), training=bool(training), rm=running_mean, rv=running_var,
+                nbt=num_batches_tracked, grad_out=grad_out, ylink=None)
+    y = _ScConv.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, meta)
+    return PendingAffine(y, meta['ylink']) if meta['ylink'] is not None else y
+
+
+class _ScAffinePool(torch.autograd.Function):
+    """ z = A*avgpool(y) + B (pool = 1: plain materialisation of a pending normalisation). Backward: dz at full resolution + the producer's sums. """
+
+    @staticmethod
+    def forward(ctx, y, link: _NormLink, pool: int):
+        n, c, h, w = y.shape
+        z = empty_nhwc(n, c, h // pool, w // pool, y.dtype, y.device)
+        check(lib.dcv_sc_affine_pool_fwd(_ptr(y), link.ref(), int(link.update_running), _ptr(z), n, h, w, c, pool, _stream()), 'sc_affine_pool_fwd')
+        ctx.save_for_backward(y)
+        ctx.link, ctx.pool = link, pool
+        return z
+
+    @staticmethod
+    def backward(ctx, dzp):
+        y, = ctx.saved_tensors
+        n, c, h, w = y.shape
+        dzp = as_nhwc(dzp.detach(), y.dtype)
+        dz = empty_nhwc(n, c, h, w, y.dtype, y.device)
+        check(lib.dcv_sc_affine_pool_bwd(_ptr(dzp), _ptr(y), ctx.link.ref(), _ptr(dz), n, h, w, c, ctx.pool, _stream()), 'sc_affine_pool_bwd')
+        return dz, None, None
+
+
+def sc_affine_pool(pa: PendingAffine, pool: int) -> torch.Tensor:
+    y, link = pa.take()
+    return _ScAffinePool.apply(y, link, int(pool))
+
+
+def materialize(x):
+    """ `PendingAffine` -> the normalised tensor; tensors pass through. """
+    return sc_affine_pool(x, 1) if isinstance(x, PendingAffine) else x
 
 
 # ------------------------------------------------------------------------------------------------------------------------------

@@ -110,6 +110,52 @@ int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w,
 size_t dcv_conv2d_wgrad_workspace(const dcv_conv_shape* shape, int dtype, int algo);
 int dcv_conv2d_wgrad(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw, void* workspace, int dtype, int algo, int acc_prezeroed, void* stream);
 
+/* ---- few-channel convolution blocks with the normalisation folded into their neighbours (deepcv_b200/csrc/conv_small.cu) ----------------------------
+ * The default `image_classifier` (conf/base/parameters.yml:8-19,79-88: 3/4/16 channels, 5x5 / 3x3 filters, 32x32 / 16x16 maps; block order
+ * Conv2d -> act -> BatchNorm2d -> GroupNorm, meta/nn.py:553) in bf16: per block ONE forward, ONE weight-gradient and ONE data-gradient launch of
+ * warp-level tensor-core (mma.sync) implicit-GEMM kernels. A block's BatchNorm o GroupNorm is never a pass of its own: the block's kernel leaves its RAW
+ * output y plus raw sums, and whoever consumes y applies z = A[n][c]*y + B[n][c] while loading it, deriving A, B per image from the sums (`dcv_sc_norm`
+ * with enabled != 0 = "this tensor is a raw output with this pending normalisation"). Backward mirrors it: the consumer's data-gradient kernel writes
+ * dz = gradient w.r.t. z and the sums the BatchNorm / GroupNorm adjoint needs; the block's own backward kernels apply dy = act'(y)*(P*dz + Q*y + R) while
+ * loading. All buffers of a dcv_sc_norm are caller-allocated fp32; bn_sums and u_sums are ACCUMULATED into with atomics and must be zero before the
+ * first kernel of the step that touches them (dcv_sc_norm_floats gives the sizes). */
+typedef struct dcv_sc_norm {
+  int32_t enabled;                  /* 0: the tensor is plain, nothing below is read */
+  int32_t n, c, hw;                 /* the normalised tensor: n images of hw pixels of c channels (c even, <= 32) */
+  int32_t use_bn, bn_training;      /* as dcv_norm_params */
+  float bn_eps, bn_momentum;        /* momentum < 0: cumulative moving average */
+  const float* bn_weight; const float* bn_bias; float* bn_running_mean; float* bn_running_var; int64_t* bn_num_batches_tracked;
+  int32_t use_gn, gn_groups;
+  float gn_eps;
+  const float* gn_weight; const float* gn_bias;
+  float* stats_nc;                  /* [n][c][2]   sum y, sum y*y per (image, channel): written by the kernel that produces y */
+  float* bn_sums;                   /* [16][c][2]  the same summed over the batch, in 16 shards (image %% 16): accumulated by that kernel; training-mode BatchNorm only */
+  float* s_nc;                      /* [n][c][2]   backward: sum dz, sum dz*y: written by the kernel that produces dz */
+  float* u_sums;                    /* [16][c][4]  backward: BatchNorm adjoint sums and GroupNorm parameter gradients, sharded: accumulated by that kernel */
+} dcv_sc_norm;
+/* 1 iff the shape is served: bf16, square 3x3 or 5x5 filter, stride 1, "same" padding, w a multiple of 16 (<= 64), c in {1..4, 16}, k even in {2, 4, 16}
+ * (5x5: c <= 4 and k <= 4). Everything else stays on dcv_conv2d_* + dcv_norm_*. */
+int dcv_sc_conv_supported(const dcv_conv_shape* shape, int dtype);
+/* floats of one buffer of a dcv_sc_norm: which = 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums */
+size_t dcv_sc_norm_floats(int n, int c, int which);
+/* y = act(conv(z, w) + bias) with z = x (x_norm NULL / disabled) or the normalised raw output x (x_norm enabled: applied on load; when `update_running`
+ * != 0 this launch also performs the running-statistics update of x_norm's BatchNorm — exactly one consumer launch per step must). y_norm enabled:
+ * the sums of y are produced for its consumers. w: [K][R][S][C] bf16. */
+int dcv_sc_conv_fwd(const dcv_conv_shape* shape, const void* x, const dcv_sc_norm* x_norm, int update_running, const void* w, const float* bias, int act, float slope,
+                    void* y, const dcv_sc_norm* y_norm, void* stream);
+/* dw[k][r][s][c] += sum dy * z, dbias[k] += sum dy (fp32, accumulated: zero them first), with dy = act'(y)*(P*dz + Q*y + R) (y_norm enabled; its s_nc / u_sums
+ * must be complete) or act'(y)*dz. Also writes the BatchNorm / GroupNorm parameter gradients of y_norm (any may be NULL; overwritten). */
+int dcv_sc_conv_wgrad(const dcv_conv_shape* shape, const void* x, const dcv_sc_norm* x_norm, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope,
+                      float* dw, float* dbias, float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream);
+/* dx = data gradient (bf16). x_norm enabled: dx is the gradient w.r.t. the NORMALISED input and x_norm's s_nc / u_sums are produced from it and the
+ * producer's raw output `x_raw`. */
+int dcv_sc_conv_dgrad(const dcv_conv_shape* shape, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope, const void* w, void* dx,
+                      const void* x_raw, const dcv_sc_norm* x_norm, void* stream);
+/* z[n][h/pool][w/pool][c] = A*avgpool(y) + B: materialises a pending normalisation (pool = 1) or fuses it with the pool x pool average pooling that follows
+ * (meta/submodule_creators.py:163-176); and its backward: dz (full resolution, written) + norm's s_nc / u_sums from dzp. */
+int dcv_sc_affine_pool_fwd(const void* y, const dcv_sc_norm* norm, int update_running, void* z, int n, int h, int w, int c, int pool, void* stream);
+int dcv_sc_affine_pool_bwd(const void* dzp, const void* y, const dcv_sc_norm* norm, void* dz, int n, int h, int w, int c, int pool, void* stream);
+
 /* ---- normalisation (BatchNorm2d / GroupNorm after the activation: meta/nn.py:448-516,553; parameters.yml:10,82) ---
  * Any {BatchNorm, GroupNorm} stack applied to y collapses to one affine per (image, channel): z = A[n][c]*y + B[n][c],
  * with A, B closed-form in sum(y), sum(y*y) per (image, channel). */

@@ -56,10 +56,10 @@ TC_EXACT = [
     (3, 128, 28, 28, 128, 3, 1),
     (2, 128, 14, 14, 256, 3, 1),    # N_TILE 256
     (3, 256, 14, 14, 256, 3, 1),
-    (2, 256, 7, 7, 512, 3, 1),
+    (3, 256, 7, 7, 512, 3, 1),
     (3, 512, 7, 7, 512, 3, 1),      # 7 x 7 maps: pixel tiles span several images
     (2, 64, 30, 21, 64, 3, 1),      # ragged halo tiles
-    (1, 64, 9, 9, 64, 3, 1),        # resident-weight per-tap kernel, fewer pixels than one wave
+    (2, 64, 9, 9, 64, 3, 1),        # resident-weight per-tap kernel, fewer pixels than one wave
     (2, 128, 40, 24, 64, 3, 1),     # two channel blocks through the halo kernel
     (5, 64, 12, 20, 64, 1, 0),      # 1 x 1 filters
     (2, 192, 14, 14, 64, 1, 0),     # channel-block weight gradient (3 blocks in one MMA)
@@ -80,8 +80,10 @@ def test_tcgen05_forward_dgrad_wgrad_bit_exact(dev, n, c, h, w, k, ks, pad, act)
     pre = F.conv2d(x, wt, bias, padding=pad)
     y_ref = pre.relu() if act == 'relu' else pre
     shape = ConvShape(n, h, w, c, k, ks, ks, 1, 1, pad, pad, 1, 1, p, q)
-    for op in (0, 1, 2):
+    for op in (0, 1):
         assert lib.dcv_conv2d_tc_supported(ctypes.byref(shape), DCV_BF16, op) == 1, f'op {op} not on the tcgen05 path'
+    has_tc_wgrad = lib.dcv_conv2d_tc_supported(ctypes.byref(shape), DCV_BF16, 2) == 1
+    assert has_tc_wgrad or ks > 3, 'the tcgen05 weight gradient serves filters up to 3 taps wide'
     st = stream()
     xd, dyd = _nhwc(x.detach(), dev), _nhwc(dy, dev)
     wd = wt.detach().permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)          # [K][R][S][C]
@@ -100,9 +102,10 @@ def test_tcgen05_forward_dgrad_wgrad_bit_exact(dev, n, c, h, w, k, ks, pad, act)
     dxd = torch.full((n, h, w, c), 7., device=dev, dtype=torch.bfloat16)
     check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), P(dyd), P(wd), P(wtd), P(dxd), DCV_BF16, ALGO_TCGEN05, st), 'conv2d_dgrad')
     _assert_equal(dxd.permute(0, 3, 1, 2), x.grad.bfloat16(), 'data gradient')
-    dwd = torch.full((k, ks, ks, c), 7., device=dev)
-    check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xd), P(dyd), P(dwd), None, DCV_BF16, ALGO_TCGEN05, 0, st), 'conv2d_wgrad')
-    _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'weight gradient (fp32)')
+    if has_tc_wgrad:
+        dwd = torch.full((k, ks, ks, c), 7., device=dev)
+        check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xd), P(dyd), P(dwd), None, DCV_BF16, ALGO_TCGEN05, 0, st), 'conv2d_wgrad')
+        _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'weight gradient (fp32)')
 
 
 # n, c, h, w, k, ksize, stride, pad — the gather kernels (software im2col tile in shared memory): few input channels / strides
@@ -179,3 +182,47 @@ def test_direct_kernels_bit_exact(dev, n, c, h, w, k, ks, pad, dtype):
     dwd = torch.full((k, ks, ks, c), 7., device=dev)
     check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), P(xd), P(dyd), P(dwd), None, dt, ALGO_DIRECT, 0, st), 'conv2d_wgrad')
     _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'direct weight gradient')
+
+
+@pytest.mark.parametrize('n,c,h,w,k,ks', [(5, 3, 32, 32, 4, 5), (4, 4, 32, 32, 4, 5), (3, 4, 16, 16, 16, 3), (3, 16, 16, 16, 16, 3), (2, 16, 32, 32, 4, 3), (2, 4, 48, 32, 4, 3), (600, 4, 16, 16, 4, 3)],
+                         ids=lambda v: str(v))
+@pytest.mark.parametrize('act', ['none', 'relu'])
+def test_few_channel_mma_kernels_bit_exact(dev, n, c, h, w, k, ks, act):
+    """ The fused few-channel kernels of the default CIFAR-10 net (warp-level mma.sync implicit GEMM straight from the NHWC tile, csrc/conv_small.cu)
+    with a plain input and no normalisation: forward (+ bias + activation + per-(image, channel) statistics), data gradient and weight / bias
+    gradient, all bit-exact under the integer-operand argument. n = 600 > 4 x 148 CTAs: the persistent image loop. """
+    from deepcv_b200._lib import ACT_NONE, ACT_RELU, DCV_BF16, ConvShape, ScNorm, check, lib
+    g = torch.Generator().manual_seed(n + c * 10 + k)
+    pad = ks // 2
+    x = _ints((n, c, h, w), -2, 2, g).requires_grad_(True)
+    wt = _ints((k, c, ks, ks), -1, 1, g).requires_grad_(True)
+    bias = _ints((k,), -3, 3, g).requires_grad_(True)
+    dz = _ints((n, k, h, w), -2, 2, g)
+    pre = F.conv2d(x, wt, bias, padding=pad)
+    y_ref = pre.relu() if act == 'relu' else pre
+    y_ref.backward(dz)
+    shape = ConvShape(n, h, w, c, k, ks, ks, 1, 1, pad, pad, 1, 1, h, w)
+    assert lib.dcv_sc_conv_supported(ctypes.byref(shape), DCV_BF16) == 1
+    st = stream()
+    act_code = ACT_RELU if act == 'relu' else ACT_NONE
+    xd, dzd = _nhwc(x.detach(), dev), _nhwc(dz, dev)
+    wd = wt.detach().permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)
+    bd = bias.detach().to(dev)
+    yd = torch.full((n, h, w, k), 7., device=dev, dtype=torch.bfloat16)
+    # statistics only (no BatchNorm, no GroupNorm): a descriptor whose sums are produced but never used
+    stats = torch.full((n, k, 2), 7., device=dev)
+    nd = ScNorm(1, n, k, h * w, 0, 0, 1e-5, 0.1, None, None, None, None, None, 0, 1, 1e-5, None, None, P(stats), None, None, None)
+    check(lib.dcv_sc_conv_fwd(ctypes.byref(shape), P(xd), None, 0, P(wd), P(bd), act_code, 0., P(yd), ctypes.byref(nd), st), 'sc_conv_fwd')
+    _assert_equal(yd.permute(0, 3, 1, 2), y_ref.detach().bfloat16(), 'forward')
+    yb = y_ref.detach().bfloat16().float()
+    _assert_equal(stats[..., 0], yb.sum((2, 3)), 'sum y')
+    if float(yb.abs().max()) < 64:    # squares of bf16-exact integers stay exact in fp32 sums
+        _assert_equal(stats[..., 1], (yb * yb).sum((2, 3)), 'sum y^2')
+    if c % 2 == 0:
+        dxd = torch.full((n, h, w, c), 7., device=dev, dtype=torch.bfloat16)
+        check(lib.dcv_sc_conv_dgrad(ctypes.byref(shape), P(dzd), P(yd), None, act_code, 0., P(wd), P(dxd), None, None, st), 'sc_conv_dgrad')
+        _assert_equal(dxd.permute(0, 3, 1, 2), x.grad.bfloat16(), 'data gradient')
+    dwd, dbd = torch.zeros((k, ks, ks, c), device=dev), torch.zeros((k,), device=dev)
+    check(lib.dcv_sc_conv_wgrad(ctypes.byref(shape), P(xd), None, P(dzd), P(yd), None, act_code, 0., P(dwd), P(dbd), None, None, None, None, st), 'sc_conv_wgrad')
+    _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'weight gradient')
+    _assert_equal(dbd, bias.grad, 'bias gradient')

@@ -370,7 +370,10 @@ def _oracle_runs(hp, input_shape, state, x, y, dtype):
     float32 CPU torch. The plain fp32 oracle is returned too: logits / loss are also held to the north-star tolerance against it. """
     from oracle.deepcv_oracle import OracleDeepcvModule, emulate_bf16_storage, train_step
     out = {}
-    for name, dt, emulate in (('plain', torch.float32, False), ('ref32', torch.float32, dtype == torch.bfloat16), ('ref64', torch.float64, dtype == torch.bfloat16)):
+    runs = [('plain', torch.float32, False), ('ref32', torch.float32, dtype == torch.bfloat16), ('ref64', torch.float64, dtype == torch.bfloat16)]
+    if dtype == torch.bfloat16:
+        runs.append(('plain64', torch.float64, False))
+    for name, dt, emulate in runs:
         m = OracleDeepcvModule(input_shape, hp)
         m.load_state_dict(state)
         m = m.to(dt)
@@ -410,7 +413,7 @@ def test_default_net_against_golden(dev, golden_dir, default_hp, dtype):
         if 'running' in n:
             assert_close(v, ref32['state'][n], 1e-4 if dtype == torch.float32 else 1e-3, n)
     if dtype == torch.bfloat16:
-        _record_distance_to_fp32_oracle('default net (batch 8, 32x32)', model, plain, ceiling=DEFAULT_NET_BF16_GRAD_CEILING)
+        _record_distance_to_fp32_oracle('default net (batch 8, 32x32)', model, plain, runs['plain64'], ceiling=DEFAULT_NET_BF16_GRAD_CEILING)
 
 
 # north_star: "logits and gradients within ... 2e-2 in bf16" of the reference CPU path. Logits / loss meet that bar against the PLAIN fp32 oracle
@@ -418,15 +421,18 @@ def test_default_net_against_golden(dev, golden_dir, default_hp, dtype):
 # (profiles/r01_bf16_sensitivity.txt: rounding one forward tensor to bf16 already moves them by 4-8 %), so the gradient gate above compares with the
 # oracle that rounds where the device stores bf16. The distance to the plain fp32 oracle is not hidden: it is measured, printed and held under a
 # recorded ceiling here (max over parameter tensors of max|g - g32| / max|g32|; ceilings = about 1.5x the value measured on B200, see the test log).
-DEFAULT_NET_BF16_GRAD_CEILING = 1.0
-RESNET_BF16_GRAD_CEILING = 1.5
+DEFAULT_NET_BF16_GRAD_CEILING = 0.6    # measured on B200: 0.35 worst, 0.08 median (26 well-conditioned tensors)
+RESNET_BF16_GRAD_CEILING = 0.8         # measured on B200: 0.51 (96x96, batch 6) / 0.41 (224x224, batch 3) worst, 0.32 / 0.20 median
 
 
-def _record_distance_to_fp32_oracle(what, model, plain, ceiling):
-    dist = {n: rel_err(p.grad, plain['grads'][n]) for n, p in model.named_parameters() if float(plain['grads'][n].abs().max()) > 0}
+def _record_distance_to_fp32_oracle(what, model, plain, plain64, ceiling):
+    """ Tensors whose reference gradient is itself rounding noise (analytically zero: a convolution bias in front of a training-mode BatchNorm, BatchNorm
+    affine under a one-channel-per-group GroupNorm — the fp32 oracle is then > 1e-3 away from the fp64 oracle) carry no information and are left out. """
+    dist = {n: rel_err(p.grad, plain['grads'][n]) for n, p in model.named_parameters()
+            if float(plain['grads'][n].abs().max()) > 0 and rel_err(plain['grads'][n], plain64['grads'][n]) <= 1e-3}
     worst = max(dist, key=dist.get)
     med = sorted(dist.values())[len(dist) // 2]
-    print(f'\n[bf16 vs plain fp32 oracle] {what}: worst parameter-gradient distance {dist[worst]:.3f} ({worst}), median {med:.3f}, over {len(dist)} tensors; ceiling {ceiling}')
+    print(f'\n[bf16 vs plain fp32 oracle] {what}: worst parameter-gradient distance {dist[worst]:.3f} ({worst}), median {med:.3f}, over {len(dist)} well-conditioned tensors; ceiling {ceiling}')
     assert dist[worst] <= ceiling, f'{what}: bf16 gradient distance to the plain fp32 oracle {dist[worst]:.3f} ({worst}) exceeds the recorded ceiling {ceiling}'
 
 
@@ -470,7 +476,7 @@ def test_resnet_style_net_against_oracle(dev, dtype, size, batch):
     bad = {n: e for n, e in bad.items() if e > 1.}
     assert not bad, f'gradient parity failures (x allowed bound): {bad}'
     if dtype == torch.bfloat16:
-        _record_distance_to_fp32_oracle(f'ResNet-style net ({size}x{size}, batch {batch})', model, runs['plain'], ceiling=RESNET_BF16_GRAD_CEILING)
+        _record_distance_to_fp32_oracle(f'ResNet-style net ({size}x{size}, batch {batch})', model, runs['plain'], runs['plain64'], ceiling=RESNET_BF16_GRAD_CEILING)
 
 
 def test_resnet_style_net_full_resolution_bf16(dev):
@@ -504,7 +510,7 @@ def test_resnet_style_net_full_resolution_bf16(dev):
           f'worst gradient excess {max(excess.values()):.2f}x of the bound ({max(excess, key=excess.get)})')
     bad = {n: e for n, e in excess.items() if e > 1.}
     assert not bad, f'gradient parity failures (x allowed bound): {bad}'
-    _record_distance_to_fp32_oracle('ResNet-style net (224x224, batch 3)', model, runs['plain'], ceiling=RESNET_BF16_GRAD_CEILING)
+    _record_distance_to_fp32_oracle('ResNet-style net (224x224, batch 3)', model, runs['plain'], runs['plain64'], ceiling=RESNET_BF16_GRAD_CEILING)
 
 
 def test_training_steps_flat_adamw_and_graph_replay(dev, golden_dir, default_hp):
