@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(kThreads) sc_dgrad_kernel(const DgradArgs a) {
       if (col < a.c_in) {
         const size_t e = img0 + ((size_t)y * W + x) * a.c_in + col;
         v0 = round_bf(v0); v1 = round_bf(v1);
-        *reinterpret_cast<uint32_t*>(a.dx + e) = pack2(v0, v1);
+        if ((a.c_in & 1) == 0) *reinterpret_cast<uint32_t*>(a.dx + e) = pack2(v0, v1);
+        else { a.dx[e] = __float2bfloat16_rn(v0); if (col + 1 < a.c_in) a.dx[e + 1] = __float2bfloat16_rn(v1); }   // odd channel counts (a 3-channel input image)
         if (a.xn.enabled) {
           const uint32_t yr = *reinterpret_cast<const uint32_t*>(a.x_raw + e);
           const int nt = col >> 3;
@@ -782,7 +783,7 @@ int dcv_sc_conv_fwd(const dcv_conv_shape* s, const void* x, const dcv_sc_norm* x
 int dcv_sc_conv_dgrad(const dcv_conv_shape* s, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope, const void* w, void* dx,
                       const void* x_raw, const dcv_sc_norm* x_norm, void* stream) {
   using namespace dcv; using namespace dcv::sc;
-  DCV_REQUIRE(shape_ok(s, DCV_BF16) && s->c % 2 == 0, "sc_conv_dgrad: shape not served by the few-channel kernels");
+  DCV_REQUIRE(shape_ok(s, DCV_BF16), "sc_conv_dgrad: shape not served by the few-channel kernels");
   DCV_REQUIRE(dz && y && w && dx, "sc_conv_dgrad: null pointer");
   if (check_norm(y_norm, s->n, s->k, s->h * s->w, "sc_conv_dgrad (output)", true) || check_norm(x_norm, s->n, s->c, s->h * s->w, "sc_conv_dgrad (input)", true)) return 1;
   DCV_REQUIRE(!(x_norm && x_norm->enabled) || x_raw, "sc_conv_dgrad: the producer's raw output is needed for its backward sums");

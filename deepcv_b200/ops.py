@@ -534,7 +534,7 @@ class _ScConv(torch.autograd.Function):
         y = empty_nhwc(n, k, p, q, torch.bfloat16, dev)
         ylink = None
         if cfg.any:
-            ylink = _NormLink(n, k, p * q, cfg, meta['training'], bn_w, bn_b, meta['rm'], meta['rv'], meta['nbt'], gn_w, gn_b, dev, sctx, need_backward=torch.is_grad_enabled())
+            ylink = _NormLink(n, k, p * q, cfg, meta['training'], bn_w, bn_b, meta['rm'], meta['rv'], meta['nbt'], gn_w, gn_b, dev, sctx, need_backward=meta['need_backward'])
         check(lib.dcv_sc_conv_fwd(ctypes.byref(shape), _ptr(x), xlink.ref() if xlink else None, int(bool(xlink and xlink.update_running)), _ptr(w_op), _ptr(bias),
                                   meta['act'], meta['slope'], _ptr(y), ylink.ref() if ylink else None, st), 'sc_conv_fwd')
         ctx.save_for_backward(x, w_op, y)
@@ -600,7 +600,7 @@ def sc_conv_block(x, weight: torch.Tensor, bias: Optional[torch.Tensor], padding
     k, _, r, s = weight.shape
     shape = ConvShape(n, h, w, c, k, r, s, 1, 1, padding[0], padding[1], 1, 1, h, w)
     meta = dict(shape=shape, xlink=xlink, cfg=norm, sctx=step_ctx, act=int(act), slope=float(slope), training=bool(training), rm=running_mean, rv=running_var,
-                nbt=num_batches_tracked, grad_out=grad_out, ylink=None)
+                nbt=num_batches_tracked, grad_out=grad_out, ylink=None, need_backward=torch.is_grad_enabled())
     y = _ScConv.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, meta)
     return PendingAffine(y, meta['ylink']) if meta['ylink'] is not None else y
 

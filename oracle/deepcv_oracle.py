@@ -345,8 +345,30 @@ def _q(x, fwd=True, bwd=False):
     return _Round.apply(x, fwd, bwd)
 
 
+def _few_channel_block(op, x_shape) -> bool:
+    """ Mirror of `dcv_sc_conv_supported` (include/deepcv_b200.h): the blocks the device runs on its fused few-channel kernels. """
+    if not isinstance(op, torch.nn.Conv2d) or len(x_shape) != 4:
+        return False
+    k, (r, s), (h, w) = op.out_channels, op.kernel_size, x_shape[2:]
+    ok = r == s and r in (3, 5) and op.stride == (1, 1) and op.dilation == (1, 1) and op.padding == (r // 2, r // 2) and op.groups == 1
+    ok = ok and w % 16 == 0 and w <= 64 and h <= 64 and (h * w) % 16 == 0 and (op.in_channels <= 4 or op.in_channels == 16) and k % 2 == 0 and (k <= 4 or k == 16)
+    return ok and (r == 3 or (op.in_channels <= 4 and k <= 4))
+
+
 def emulate_bf16_storage(model: torch.nn.Module) -> torch.nn.Module:
-    """ Patches (in place) the forward of every block of an `OracleDeepcvModule` so that it rounds tensors where the device path stores bf16. """
+    """ Patches (in place) the forward of every block of an `OracleDeepcvModule` so that it rounds tensors where the device path stores bf16.
+    A few-channel block directly followed by a non-overlapping average pooling (and not referenced by a later link) never stores its normalised output:
+    the device pools the raw output in fp32 and applies the normalisation to the pooled value (pool(A*y + B) = A*pool(y) + B), one rounding later. """
+    for container in model.modules():
+        subs = getattr(container, '_submodules', None)
+        if isinstance(subs, dict):
+            names, mods = list(subs.keys()), list(subs.values())
+            referenced = {r for m in mods for r in (getattr(m, 'referenced_submodules', None) or [])}
+            for name, m, nxt in zip(names, mods, mods[1:]):
+                if isinstance(nxt, torch.nn.AvgPool2d) and name not in referenced:
+                    ks, st = nxt.kernel_size, nxt.stride
+                    ks, st = (ks, ks) if isinstance(ks, int) else tuple(ks), (st, st) if isinstance(st, int) else tuple(st)
+                    m._emul_next_pool = ks[0] if (ks == st and ks[0] == ks[1]) else 0
     for m in model.modules():
         if isinstance(m, torch.nn.Sequential) and len(m) > 0 and any(isinstance(c, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)) for c in m):
             def fwd(x, m=m):
@@ -369,7 +391,10 @@ def emulate_bf16_storage(model: torch.nn.Module) -> torch.nn.Module:
                 if norms:
                     for nrm in norms:
                         y = nrm(y)
-                    y = _q(y)                                          # z stored bf16
+                    pool = getattr(m, '_emul_next_pool', 0)
+                    fused_pool = pool and _few_channel_block(op, x.shape) and y.shape[2] % pool == 0 and y.shape[3] % pool == 0
+                    if not fused_pool:
+                        y = _q(y)                                      # z stored bf16 (or rounded to bf16 when the next few-channel block stages it)
                 return y
             m.forward = fwd
         elif isinstance(m, (torch.nn.AvgPool2d,)):

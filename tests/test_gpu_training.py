@@ -77,10 +77,12 @@ def test_train_entry_point_graph_replay_matches_eager(dev, default_hp):
     assert state_a.iteration == state_b.iteration == 2 * (167 // 32) and state_a.epoch == 2
     assert set(metrics_a) == {'valid_loss', 'valid_accuracy', 'valid_samples'} and metrics_a['valid_samples'] == 70
     # Convolution / fully connected weights (BatchNorm affine under a one-channel-per-group GroupNorm and the convolution biases in front of BatchNorm
-    # have analytically zero gradients: Adam turns their rounding noise — which depends on the atomics' order — into +-lr steps on both sides)
+    # have analytically zero gradients: Adam turns their rounding noise — which depends on the atomics' order — into +-lr steps on both sides). Early
+    # Adam steps are ~lr * sign(g): a component whose gradient is near zero may differ by a few lr (1e-3 at the peak of the schedule) after 10 steps.
     for (n, a), (_, b) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
         if a.dtype.is_floating_point and a.dim() >= 2:
-            assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()), n
+            assert float((a - b).abs().max()) <= 5e-3, n
+            assert float((a - b).abs().mean()) <= 5e-4, n
     assert abs(metrics_a['valid_loss'] - metrics_b['valid_loss']) <= 1e-3 * abs(metrics_b['valid_loss'])
     assert metrics_a['valid_accuracy'] == pytest.approx(metrics_b['valid_accuracy'], abs=2 / 70)
     assert state_a.output['main_loss'] == pytest.approx(state_b.output['main_loss'], rel=1e-3)
