@@ -471,6 +471,7 @@ class GraphedTrainStep:
         if y.data_ptr() != self.static_y.data_ptr():
             self.static_y.copy_(y, non_blocking=True)
         if self.preprocess is not None:
+            self.preprocess.train()   # the captured step is a TRAINING step (reference :246 `model.train()`): an evaluation pass in between must not freeze the draws
             flip, crop = self.preprocess.draw(x.shape[0])
             if flip is not None:
                 self._host_flip.copy_(flip)
@@ -587,6 +588,7 @@ class GraphedEvalStep:
 
     def _eager(self):
         was_training = self.model.training
+        pre_was_training = self.preprocess.training if self.preprocess is not None else False
         self.model.eval()
         if self.preprocess is not None:
             self.preprocess.eval()
@@ -598,6 +600,8 @@ class GraphedEvalStep:
                 check(lib.dcv_classification_metrics(ops._ptr(logits), ops._ptr(self.static_y), ops._ptr(self.acc3), logits.shape[0], logits.shape[1], ops._stream()), 'classification_metrics')
         finally:
             self.model.train(was_training)
+            if self.preprocess is not None:
+                self.preprocess.train(pre_was_training)   # a preprocess left in eval mode would stop drawing flips / crop offsets for the training steps
 
     def step(self, x, y):
         if x.data_ptr() != self.static_x.data_ptr():

@@ -81,11 +81,11 @@ def test_train_entry_point_graph_replay_matches_eager(dev, default_hp):
     # Adam steps are ~lr * sign(g): a component whose gradient is near zero may differ by a few lr (1e-3 at the peak of the schedule) after 10 steps.
     for (n, a), (_, b) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
         if a.dtype.is_floating_point and a.dim() >= 2:
-            assert float((a - b).abs().max()) <= 5e-3, n
-            assert float((a - b).abs().mean()) <= 5e-4, n
+            assert float((a - b).abs().max()) <= 5e-4, n       # measured 1e-5 .. 1.5e-4 (eager vs eager: 1e-8 .. 8e-5)
+            assert float((a - b).abs().mean()) <= 5e-5, n
     assert abs(metrics_a['valid_loss'] - metrics_b['valid_loss']) <= 1e-3 * abs(metrics_b['valid_loss'])
     assert metrics_a['valid_accuracy'] == pytest.approx(metrics_b['valid_accuracy'], abs=2 / 70)
-    assert state_a.output['main_loss'] == pytest.approx(state_b.output['main_loss'], rel=1e-3)
+    assert state_a.output['main_loss'] == pytest.approx(state_b.output['main_loss'], rel=1e-5)   # second epoch, after a validation pass: same draws
     # the evaluation metrics are those of stock torch on the model's own eval-mode logits
     from deepcv_b200.meta.data.preprocess import FusedPreprocess
     test = datasets['testset']
