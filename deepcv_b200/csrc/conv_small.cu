@@ -24,8 +24,11 @@
 namespace dcv {
 namespace sc {
 
-constexpr int kThreads = 256;   // 8 warps
+constexpr int kThreads = 128;   // forward / data gradient / pooling: 4 warps per image, >= 4 CTAs resident per SM => a batch of 512 images is ONE wave
 constexpr int kWarps = kThreads / 32;
+constexpr int kMinCtas = 4;
+constexpr int kWgThreads = 256; // weight gradient: 8 warps, 2 CTAs per SM, persistent over images (fewer global atomics on dw)
+constexpr int kWgWarps = kWgThreads / 32;
 constexpr int kShards = 16;     // per-channel batch sums are spread over this many accumulators (index image % kShards): 32 atomics per address at batch 512
 constexpr int kMaxC = 32;       // channels of a normalised tensor on this path
 
@@ -39,7 +42,7 @@ struct Coef {
 };
 
 // ---- forward coefficients of image `img` from the raw sums. Called by ONE whole warp (lane = channel, c <= 32).
-__device__ void norm_forward_coeffs(const dcv_sc_norm& nd, int img, Coef& cf, bool update_running) {
+__device__ __noinline__ void norm_forward_coeffs(const dcv_sc_norm& nd, int img, Coef& cf, bool update_running) {
   const int lane = threadIdx.x & 31, c = nd.c;
   double al = 1.0, be = 0.0, mean = 0.0, rstd = 1.0;
   if (lane < c && nd.use_bn) {
@@ -99,7 +102,7 @@ __device__ void norm_forward_coeffs(const dcv_sc_norm& nd, int img, Coef& cf, bo
 }
 
 // ---- GroupNorm adjoint of image `img`: D1, D2, D3 from the image's sums s[c][2] = {sum dz, sum dz*y} (any memory). One warp, after norm_forward_coeffs.
-__device__ void norm_backward_D(const dcv_sc_norm& nd, Coef& cf, const float* s) {
+__device__ __noinline__ void norm_backward_D(const dcv_sc_norm& nd, Coef& cf, const float* s) {
   const int lane = threadIdx.x & 31, c = nd.c;
   if (lane < c) {
     double D1 = 1.0, D2 = 0.0, D3 = 0.0;
@@ -127,7 +130,7 @@ __device__ void norm_backward_D(const dcv_sc_norm& nd, Coef& cf, const float* s)
 // ---- what the kernel that COMPLETES the sums s of image `img` does with them (one warp; s in shared memory): stores them for the producer's backward
 // kernels and adds the image's terms of the BatchNorm adjoint sums / GroupNorm parameter gradients to the sharded accumulators u_sums[shard][c][4] =
 // {U1 = sum du, U2raw = sum du*y, d gn_weight, d gn_bias}.
-__device__ void norm_backward_image_sums(const dcv_sc_norm& nd, int img, Coef& cf, const float* s) {
+__device__ __noinline__ void norm_backward_image_sums(const dcv_sc_norm& nd, int img, Coef& cf, const float* s) {
   norm_forward_coeffs(nd, img, cf, false);
   norm_backward_D(nd, cf, s);
   const int lane = threadIdx.x & 31, c = nd.c;
@@ -150,7 +153,7 @@ __device__ void norm_backward_image_sums(const dcv_sc_norm& nd, int img, Coef& c
 
 // ---- P, Q, R of image `img` (one warp): forward coefficients, D from the stored sums, BatchNorm adjoint from the complete batch sums.
 // `param_grads`: this warp also writes the normalisation parameter gradients (one CTA of one kernel per block does).
-__device__ void norm_backward_pqr(const dcv_sc_norm& nd, int img, Coef& cf, bool param_grads, float* d_bn_w, float* d_bn_b, float* d_gn_w, float* d_gn_b) {
+__device__ __noinline__ void norm_backward_pqr(const dcv_sc_norm& nd, int img, Coef& cf, bool param_grads, float* d_bn_w, float* d_bn_b, float* d_gn_w, float* d_gn_b) {
   norm_forward_coeffs(nd, img, cf, false);
   norm_backward_D(nd, cf, nd.s_nc + (size_t)img * nd.c * 2);
   const int lane = threadIdx.x & 31, c = nd.c;
@@ -253,8 +256,9 @@ template <int CI, typename Src>
 __device__ __forceinline__ void stage_nhwc(bf16* tile, const Src& src, size_t img_elem0, int H, int W, int Wp, int PAD, int c_src, int tid) {
   if (c_src == CI && (img_elem0 % 8) == 0) {
     const int nvec = H * W * CI / 8;
+    const int wlog = 31 - __clz(W);   // W is a power of two (shape_ok)
     for (int v = tid; v < nvec; v += kThreads) {
-      const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix / W, x = pix - y * W;
+      const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix >> wlog, x = pix & (W - 1);
       float f[8];
       src.load8(img_elem0 + e0, c0, CI - 1, f);
       bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI + c0;
@@ -266,8 +270,9 @@ __device__ __forceinline__ void stage_nhwc(bf16* tile, const Src& src, size_t im
       }
     }
   } else {
+    const int wlog = 31 - __clz(W);
     for (int pix = tid; pix < H * W; pix += kThreads) {
-      const int y = pix / W, x = pix - y * W;
+      const int y = pix >> wlog, x = pix & (W - 1);
       bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI;
 #pragma unroll
       for (int c = 0; c < CI; ++c) dst[c] = __float2bfloat16_rn(c < c_src ? src.load1(img_elem0 + (size_t)pix * c_src + c, c) : 0.f);
@@ -304,14 +309,18 @@ template <int CI, int NT, int KS> struct Core {
       }
   }
 
-  template <typename Epi>
-  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Epi epi) const {
+  // `pre(y, x, col, slot)` may start global loads whose results the epilogue needs (issued before the MMAs of the tile, consumed after them);
+  // `epi(y, x, col, v0, v1, slot)` receives the two adjacent output columns col, col + 1 of pixel (y, x); slot = 2 * nt + (0: pixel x0 + g, 1: pixel x0 + g + 8).
+  template <typename Pre, typename Epi>
+  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Pre pre, Epi epi) const {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-    const int mtiles = H * W / 16;
+    const int mtiles = H * W / 16, wlog = 31 - __clz(W);
     for (int mt = warp; mt < mtiles; mt += kWarps) {
-      const int p0 = mt * 16, y = p0 / W, x0 = p0 - y * W;
+      const int p0 = mt * 16, y = p0 >> wlog, x0 = p0 & (W - 1);
       const int pb = (y * Wp + x0 + g) * CW;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { pre(y, x0 + g, nt * 8 + 2 * t, 2 * nt); pre(y, x0 + g + 8, nt * 8 + 2 * t, 2 * nt + 1); }
       float acc[NT][4];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
@@ -323,8 +332,8 @@ template <int CI, int NT, int KS> struct Core {
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        epi(y, x0 + g, nt * 8 + 2 * t, acc[nt][0], acc[nt][1]);
-        epi(y, x0 + g + 8, nt * 8 + 2 * t, acc[nt][2], acc[nt][3]);
+        epi(y, x0 + g, nt * 8 + 2 * t, acc[nt][0], acc[nt][1], 2 * nt);
+        epi(y, x0 + g + 8, nt * 8 + 2 * t, acc[nt][2], acc[nt][3], 2 * nt + 1);
       }
     }
   }
@@ -346,7 +355,7 @@ struct FwdArgs {
 };
 
 template <int CI, int NT, int KS>
-__global__ void __launch_bounds__(kThreads) sc_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_raw);
   __shared__ Coef cfx;
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(kThreads) sc_fwd_kernel(const FwdArgs a) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
     bf16* yimg = a.y + (size_t)img * H * W * a.k_out;
-    core.run(tile, H, W, Wp, [&](int y, int x, int col, float v0, float v1) {
+    core.run(tile, H, W, Wp, [](int, int, int, int) {}, [&](int y, int x, int col, float v0, float v1, int) {
       const int nt = col >> 3;
       v0 = round_bf(act_fwd(v0 + bias_r[nt][0], a.act, a.slope));
       v1 = round_bf(act_fwd(v1 + bias_r[nt][1], a.act, a.slope));
@@ -417,7 +426,7 @@ struct DgradArgs {
 };
 
 template <int KI, int NT, int KS>
-__global__ void __launch_bounds__(kThreads) sc_dgrad_kernel(const DgradArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const DgradArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_raw);
   __shared__ Coef cfy, cfx;
@@ -442,14 +451,17 @@ __global__ void __launch_bounds__(kThreads) sc_dgrad_kernel(const DgradArgs a) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
     const size_t img0 = (size_t)img * H * W * a.c_in;
-    core.run(tile, H, W, Wp, [&](int y, int x, int col, float v0, float v1) {
+    uint32_t yraw[2 * NT];   // the producer's raw output at this thread's output elements: loaded BEFORE the tile's MMAs (an L2 round trip), used after them
+    core.run(tile, H, W, Wp, [&](int y, int x, int col, int slot) {
+      if (a.xn.enabled && col < a.c_in) yraw[slot] = *reinterpret_cast<const uint32_t*>(a.x_raw + img0 + ((size_t)y * W + x) * a.c_in + col);   // c_in is even here (check_norm)
+    }, [&](int y, int x, int col, float v0, float v1, int slot) {
       if (col < a.c_in) {
         const size_t e = img0 + ((size_t)y * W + x) * a.c_in + col;
         v0 = round_bf(v0); v1 = round_bf(v1);
         if ((a.c_in & 1) == 0) *reinterpret_cast<uint32_t*>(a.dx + e) = pack2(v0, v1);
         else { a.dx[e] = __float2bfloat16_rn(v0); if (col + 1 < a.c_in) a.dx[e + 1] = __float2bfloat16_rn(v1); }   // odd channel counts (a 3-channel input image)
         if (a.xn.enabled) {
-          const uint32_t yr = *reinterpret_cast<const uint32_t*>(a.x_raw + e);
+          const uint32_t yr = yraw[slot];
           const int nt = col >> 3;
           s1[nt][0] += v0; s1[nt][1] += v1; s2[nt][0] = fmaf(v0, bf_lo(yr), s2[nt][0]); s2[nt][1] = fmaf(v1, bf_hi(yr), s2[nt][1]);
         }
@@ -489,10 +501,10 @@ __device__ __forceinline__ void store_pair_planar(bf16* plane, int pos, float lo
 }
 
 template <int CI, int NT, int KS>
-__global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
+__global__ void __launch_bounds__(kWgThreads) sc_wgrad_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int PAD = KS / 2, MROWS = KS * KS * CI, MT = (MROWS + 15) / 16, KO = NT * 8;
-  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, PS = Hp * Wp;   // PS: plane stride (elements), even
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, PS = Hp * Wp, wlog = 31 - __clz(W);   // PS: plane stride (elements), even; W: power of two
   bf16* z0 = reinterpret_cast<bf16*>(smem_raw);          // [CI][PS]
   bf16* z1 = z0 + (size_t)CI * PS;                       // [CI][PS], z1[i] = z0[i + 1]
   bf16* dyT = z1 + (size_t)CI * PS;                      // [KO][HW]
@@ -500,9 +512,9 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
   __shared__ Coef cfx, cfy;
   __shared__ float sh_db[KO];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < 2 * CI * PS / 8; i += kThreads) reinterpret_cast<uint4*>(z0)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < KO * HW / 8; i += kThreads) reinterpret_cast<uint4*>(dyT)[i] = make_uint4(0u, 0u, 0u, 0u);   // rows >= k_out stay zero
-  for (int i = tid; i < MT * 16 * KO; i += kThreads) sh_dw[i] = 0.f;
+  for (int i = tid; i < 2 * CI * PS / 8; i += kWgThreads) reinterpret_cast<uint4*>(z0)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < KO * HW / 8; i += kWgThreads) reinterpret_cast<uint4*>(dyT)[i] = make_uint4(0u, 0u, 0u, 0u);   // rows >= k_out stay zero
+  for (int i = tid; i < MT * 16 * KO; i += kWgThreads) sh_dw[i] = 0.f;
   if (tid < KO) sh_db[tid] = 0.f;
   // per-thread A row offsets (32-bit words into z0 / z1): rows g and g + 8 of every m-tile
   int zoff[MT][2];
@@ -534,8 +546,8 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
       SrcPlain sx{a.x, a.xn.enabled ? &cfx : nullptr};
       const size_t e_img = (size_t)img * HW * a.c_src;
       if (a.c_src == CI && (e_img % 8) == 0) {
-        for (int v = tid; v < HW * CI / 8; v += kThreads) {
-          const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix / W, x = pix - y * W, pos = (y + PAD) * Wp + x + PAD;
+        for (int v = tid; v < HW * CI / 8; v += kWgThreads) {
+          const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix >> wlog, x = pix & (W - 1), pos = (y + PAD) * Wp + x + PAD;
           float f[8];
           sx.load8(e_img + e0, c0, CI - 1, f);
           if (CI == 4) {   // pixels (x, x + 1), channels 0..3: a pixel PAIR per plane
@@ -547,8 +559,8 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
           }
         }
       } else {
-        for (int pix = tid; pix < HW; pix += kThreads) {
-          const int y = pix / W, x = pix - y * W, pos = (y + PAD) * Wp + x + PAD;
+        for (int pix = tid; pix < HW; pix += kWgThreads) {
+          const int y = pix >> wlog, x = pix & (W - 1), pos = (y + PAD) * Wp + x + PAD;
           for (int c = 0; c < a.c_src; ++c) { const bf16 b = __float2bfloat16_rn(sx.load1(e_img + (size_t)pix * a.c_src + c, c)); z0[c * PS + pos] = b; z1[c * PS + pos - 1] = b; }
         }
       }
@@ -556,7 +568,7 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
       const size_t k_img = (size_t)img * HW * a.k_out;
       const int kv = a.k_out;   // channels of dy
       if ((kv == 4 || kv % 8 == 0) && (k_img % 8) == 0) {
-        for (int v = tid; v < HW * kv / 8; v += kThreads) {
+        for (int v = tid; v < HW * kv / 8; v += kWgThreads) {
           const int e0 = v * 8, pix = e0 / kv, c0 = e0 % kv;
           float f[8];
           sd.load8(k_img + e0, c0, kv - 1, f);   // kv is a power of two here (4, 8, 16)
@@ -571,7 +583,7 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
           }
         }
       } else {
-        for (int pix = tid; pix < HW; pix += kThreads)
+        for (int pix = tid; pix < HW; pix += kWgThreads)
           for (int c = 0; c < kv; ++c) {
             const float v = round_bf(sd.load1(k_img + (size_t)pix * kv + c, c));
             dyT[(size_t)c * HW + pix] = __float2bfloat16_rn(v);
@@ -581,8 +593,8 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
     }
     __syncthreads();
     // ---- MMA over the image's pixel chunks
-    for (int ch = warp; ch < HW / 16; ch += kWarps) {
-      const int p0 = ch * 16, y = p0 / W, x0 = p0 - y * W;
+    for (int ch = warp; ch < HW / 16; ch += kWgWarps) {
+      const int p0 = ch * 16, y = p0 >> wlog, x0 = p0 & (W - 1);
       const int pw = (y * Wp + x0) / 2 + t;   // pixel-pair word of this thread's k columns (2t, 2t + 1); + 4 words = pixels + 8
       uint32_t b0[NT], b1[NT];
 #pragma unroll
@@ -610,17 +622,29 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
       atomicAdd(&sh_dw[(r0 + 8) * KO + col], acc[mt][nt][2]); atomicAdd(&sh_dw[(r0 + 8) * KO + col + 1], acc[mt][nt][3]);
     }
   {
-    // bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 fixed per thread (kThreads * 8 is a multiple of kv)
+    // bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 fixed per thread (kWgThreads * 8 is a multiple of kv)
+    // Lanes whose (lane * 8) % kv agree hold the same channels: butterfly over them, then one shared-memory atomic per (warp, channel) — 256 threads
+    // adding 8 values each straight onto 4..16 addresses was 60 % of this kernel's instructions (ncu, round 2: retried shared-memory atomics).
     const int kv = a.k_out;
     if ((kv == 4 || kv % 8 == 0)) {
-      const int c0 = (tid * 8) % kv;
+      if (kv == 4) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) if (db[i] != 0.f) atomicAdd(&sh_db[(c0 + i) & (kv - 1)], db[i]);
+        for (int i = 0; i < 4; ++i) { db[i] += db[i + 4]; db[i + 4] = 0.f; }
+      }
+      const int stride = kv >= 8 ? kv / 8 : 1, nval = kv == 4 ? 4 : 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nval) {
+          float v = db[i];
+          for (int o = 16; o >= stride; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane < stride) atomicAdd(&sh_db[(lane * 8 + i) & (kv - 1)], v);
+        }
+      }
     }
   }
   __syncthreads();
   const int total = a.k_out * KS * KS * a.c_src;
-  for (int i = tid; i < total; i += kThreads) {
+  for (int i = tid; i < total; i += kWgThreads) {
     const int c = i % a.c_src, tap = (i / a.c_src) % (KS * KS), k = i / (a.c_src * KS * KS);
     const float v = sh_dw[(tap * CI + c) * KO + k];
     if (v != 0.f) atomicAdd(a.dw + i, v);
@@ -632,7 +656,7 @@ __global__ void __launch_bounds__(kThreads) sc_wgrad_kernel(const WgradArgs a) {
 // zp[n][oy][ox][c] = A[n][c] * mean_{pool x pool}(y) + B[n][c]   (pooling is linear and the affine is per (image, channel): pool(z) = A*pool(y) + B).
 struct PoolArgs { int n, h, w, c, pool, update_running; const bf16* y; bf16* z; const bf16* dzp; bf16* dz; dcv_sc_norm nd; };
 
-__global__ void __launch_bounds__(kThreads) sc_affine_pool_fwd_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_fwd_kernel(const PoolArgs a) {
   __shared__ Coef cf;
   const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
   const float inv = 1.f / (float)(a.pool * a.pool);
@@ -656,7 +680,7 @@ __global__ void __launch_bounds__(kThreads) sc_affine_pool_fwd_kernel(const Pool
 }
 
 // backward: dz = dzp / pool^2 spread over the window (written, bf16), s[n][c] = {sum dz, sum dz*y}, then the image's adjoint sums.
-__global__ void __launch_bounds__(kThreads) sc_affine_pool_bwd_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_bwd_kernel(const PoolArgs a) {
   __shared__ Coef cf;
   __shared__ float sh_s[kMaxC][2];
   const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
@@ -688,7 +712,15 @@ __global__ void __launch_bounds__(kThreads) sc_affine_pool_bwd_kernel(const Pool
     }
     if (fixed_cp) {
       const int cp = tid % c2;
-      atomicAdd(&sh_s[2 * cp][0], t1a); atomicAdd(&sh_s[2 * cp + 1][0], t1b); atomicAdd(&sh_s[2 * cp][1], t2a); atomicAdd(&sh_s[2 * cp + 1][1], t2b);
+      if ((c2 & (c2 - 1)) == 0 && c2 <= 32) {   // lanes with equal lane % c2 hold the same channel pair: butterfly, then one atomic per (warp, value)
+        for (int o = 16; o >= c2; o >>= 1) {
+          t1a += __shfl_xor_sync(0xffffffffu, t1a, o); t1b += __shfl_xor_sync(0xffffffffu, t1b, o);
+          t2a += __shfl_xor_sync(0xffffffffu, t2a, o); t2b += __shfl_xor_sync(0xffffffffu, t2b, o);
+        }
+        if ((tid & 31) < c2) { atomicAdd(&sh_s[2 * cp][0], t1a); atomicAdd(&sh_s[2 * cp + 1][0], t1b); atomicAdd(&sh_s[2 * cp][1], t2a); atomicAdd(&sh_s[2 * cp + 1][1], t2b); }
+      } else {
+        atomicAdd(&sh_s[2 * cp][0], t1a); atomicAdd(&sh_s[2 * cp + 1][0], t1b); atomicAdd(&sh_s[2 * cp][1], t2a); atomicAdd(&sh_s[2 * cp + 1][1], t2b);
+      }
     }
     __syncthreads();
     if (tid < 32) norm_backward_image_sums(a.nd, img, cf, &sh_s[0][0]);
@@ -702,7 +734,7 @@ static bool shape_ok(const dcv_conv_shape* s, int dtype) {
   if (!s || dtype != DCV_BF16) return false;
   if (s->stride_h != 1 || s->stride_w != 1 || s->dil_h != 1 || s->dil_w != 1 || s->r != s->s || (s->r != 3 && s->r != 5)) return false;
   if (s->pad_h != s->r / 2 || s->pad_w != s->r / 2 || s->p != s->h || s->q != s->w) return false;
-  if (s->w % 16 != 0 || s->w > 64 || s->h > 64 || (s->h * s->w) % 16 != 0) return false;
+  if ((s->w != 16 && s->w != 32 && s->w != 64) || s->h > 64 || (s->h * s->w) % 16 != 0) return false;   // the kernels split pixel indices with shifts
   const int ci = pick_ci(s->c), ki = pick_ci(s->k);
   if (!ci || !ki || s->k % 2 != 0 || s->c < 1) return false;
   if (s->r == 5 && (ci != 4 || ki != 4)) return false;   // 5x5 over 16 channels: 25 k-steps of resident weight fragments do not fit the register file
@@ -822,7 +854,7 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm*
   do {                                                                                  \
     auto kern = sc_wgrad_kernel<CI_, NT_, KS_>;                                         \
     if (set_smem(kern, smem)) return 1;                                                 \
-    kern<<<grid_of(a.n), kThreads, smem, st>>>(a);                                      \
+    kern<<<grid_of(a.n), kWgThreads, smem, st>>>(a);                                      \
   } while (0)
   if (s->r == 5) SC_WGRAD(4, 1, 5);
   else if (ci == 4 && nt == 1) SC_WGRAD(4, 1, 3);

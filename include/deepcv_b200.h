@@ -133,7 +133,7 @@ typedef struct dcv_sc_norm {
   float* s_nc;                      /* [n][c][2]   backward: sum dz, sum dz*y: written by the kernel that produces dz */
   float* u_sums;                    /* [16][c][4]  backward: BatchNorm adjoint sums and GroupNorm parameter gradients, sharded: accumulated by that kernel */
 } dcv_sc_norm;
-/* 1 iff the shape is served: bf16, square 3x3 or 5x5 filter, stride 1, "same" padding, w a multiple of 16 (<= 64), c in {1..4, 16}, k even in {2, 4, 16}
+/* 1 iff the shape is served: bf16, square 3x3 or 5x5 filter, stride 1, "same" padding, w in {16, 32, 64}, c in {1..4, 16}, k even in {2, 4, 16}
  * (5x5: c <= 4 and k <= 4). Everything else stays on dcv_conv2d_* + dcv_norm_*. */
 int dcv_sc_conv_supported(const dcv_conv_shape* shape, int dtype);
 /* floats of one buffer of a dcv_sc_norm: which = 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums */
