@@ -11,7 +11,7 @@ from pathlib import Path
 __all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
            'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DCV_F32, DCV_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_SIGMOID = 0, 1, 2, 3
 ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05 = 0, 1, 2
@@ -37,7 +37,7 @@ class ScNorm(Structure):
                 ('bn_weight', c_void_p), ('bn_bias', c_void_p), ('bn_running_mean', c_void_p), ('bn_running_var', c_void_p), ('bn_num_batches_tracked', c_void_p),
                 ('use_gn', c_int32), ('gn_groups', c_int32), ('gn_eps', c_float),
                 ('gn_weight', c_void_p), ('gn_bias', c_void_p),
-                ('stats_nc', c_void_p), ('bn_sums', c_void_p), ('s_nc', c_void_p), ('u_sums', c_void_p)]
+                ('stats_nc', c_void_p), ('bn_sums', c_void_p), ('s_nc', c_void_p), ('u_sums', c_void_p), ('coef_nc', c_void_p), ('d_nc', c_void_p)]
 
 
 P = c_void_p

@@ -3,20 +3,30 @@
 // as passes of its own (reference block order: meta/nn.py:553 `Conv2d -> act -> BatchNorm2d -> GroupNorm`, spec conf/base/parameters.yml:8-19).
 //
 // Why not the tcgen05 kernels: K = R*S*C is 36..144 and N = 4..16 output channels; an M = 128 UMMA tile needs a software im2col tile in the swizzled
-// operand layout (2.3 us per 128-pixel tile measured for the gather kernel) for 0.1 us of MMA. Here the implicit-GEMM A fragments of warp-level
-// `mma.sync.m16n8k16` (bf16 -> fp32) are read STRAIGHT from the NHWC image tile in shared memory: with K ordered (tap, channel) a fragment register is
-// two adjacent channels of one tap = one aligned 32-bit shared load, no im2col at all. The step is bound by HBM traffic and launch latency, not math
-// (arithmetic intensity 43-72 FLOP/B), so what matters is the number of passes over the activations and of launches:
+// operand layout (2.3 us per 128-pixel tile measured for the gather kernel) for 0.1 us of MMA. Here warp-level `mma.sync.m16n8k16` (bf16 -> fp32)
+// takes its operands with `ldmatrix` STRAIGHT from the NHWC image tile in shared memory (one tile layout for all three kernels, no im2col, no
+// transposed copies):
+//   * 16-channel tensors: an 8x8 ldmatrix block is 8 pixels x 8 channels (16 bytes of a pixel); forward / data gradient read it as the A operand
+//     (M = pixels, K = (tap, channel)), the weight gradient reads the same block TRANSPOSED (`ldmatrix.trans`: M = (tap, channel), K = pixels).
+//   * 4-channel tensors (8 bytes per pixel): a 16-byte ldmatrix row is a PIXEL PAIR (2j, 2j+1), so the GEMM runs over pixel pairs and the pair's
+//     parity moves into N: out[2j + par][k] = sum_{s', c} z[2j + s'][c] * w[s' - par][c][k] with s' = 0..KS (a (KS+1)-wide window, zero weights where
+//     s' - par falls outside the filter), N = (par, k). Every MMA column is useful (N = 8 for 4 output channels instead of 4 + 4 padding), M halves:
+//     256 MMAs per 32x32 image of a 5x5 4->4 layer instead of 448, each fed by ONE ldmatrix.x4 instead of four 32-bit loads.
+//     The weight gradient uses the same identity transposed: D[(s', c)][(par, k)] = sum_j z[2j + s'][c] * dy[2j + par][k], dw[s] = D[s][par 0] + D[s + 1][par 1].
+// The step is bound by latency and instruction issue, not math or HBM (arithmetic intensity 43-72 FLOP/B; 8 MB per launch is
+// 1.3 us of HBM time), so what matters is the number of launches, passes, instructions and dependent round trips:
 //
 //   forward   reads the producer's RAW output y_prev and applies its pending normalisation z = A[n][c]*y + B[n][c] while staging the tile
 //             ("normalise on load": z is never written), convolves, adds bias, activates, stores y (bf16) and accumulates the statistics of y:
-//             per-(image, channel) sums (plain stores: a CTA owns whole images) and sharded per-channel batch sums (atomics).
-//   A, B      are NOT produced by a finalize kernel: every consumer CTA derives them for ITS image from the raw sums in a ~100-flop prologue
-//             (BatchNorm from the batch sums, GroupNorm from the image's sums, fp64). The CTA that handles image 0 also updates the running statistics.
+//             per-(image, channel) sums (plain stores: a CTA owns whole images) and sharded per-channel batch sums (atomics). The raw image is
+//             fetched into registers BEFORE the coefficient prologue, so its L2 round trip overlaps the prologue's.
+//   A, B      are NOT produced by a finalize kernel: the FIRST consumer CTA of an image derives them from the raw sums in a ~100-flop fp64 prologue
+//             (BatchNorm from the batch sums, GroupNorm from the image's sums) and caches the image's eight coefficients in `coef_nc`; the backward
+//             kernels load them (one round trip) instead of repeating the division / rsqrt chains. The CTA of image 0 updates the running statistics.
 //   backward  the consumer's data-gradient kernel writes dz (gradient w.r.t. the producer's normalised output) and, in its epilogue, the sums
-//             s[n][c] = {sum dz, sum dz*y} plus the image's contribution to the BatchNorm adjoint sums (sharded atomics). The producer's weight- and
-//             data-gradient kernels then derive P, Q, R of dy = act'(y)*(P*dz + Q*y + R) per image in their prologue and apply it WHILE LOADING their
-//             operand: no reduce / finalize / apply passes, dy is never written.
+//             s[n][c] = {sum dz, sum dz*y}, the image's GroupNorm adjoint coefficients (`d_nc`) and its contribution to the BatchNorm adjoint sums
+//             (sharded atomics). The producer's weight- and data-gradient kernels then derive P, Q, R of dy = act'(y)*(P*dz + Q*y + R) per image in
+//             their prologue and apply it WHILE LOADING their operand: no reduce / finalize / apply passes, dy is never written.
 // Per block: 3 launches instead of 9 (conv, finalize, apply, reduce, finalize, apply, wgrad, dgrad + weight packing), and three activation-sized
 // tensors (z, dy, the transposed weights) never touch HBM.
 #include "common.cuh"
@@ -97,6 +107,22 @@ __device__ __noinline__ void norm_forward_coeffs(const dcv_sc_norm& nd, int img,
       A = a2 * A;
     }
     cf.gmean[lane] = gmean; cf.gr[lane] = gr; cf.A[lane] = (float)A; cf.B[lane] = (float)B;
+    if (nd.coef_nc) {   // the backward kernels load exactly these floats
+      float4* o = reinterpret_cast<float4*>(nd.coef_nc + ((size_t)img * c + lane) * 8);
+      o[0] = make_float4(cf.A[lane], cf.B[lane], cf.al[lane], cf.be[lane]);
+      o[1] = make_float4(cf.mu[lane], cf.rc[lane], gmean, gr);
+    }
+  }
+  __syncwarp();
+}
+
+// ---- the cached forward coefficients of image `img` (backward kernels). One warp.
+__device__ __forceinline__ void load_coeffs(const dcv_sc_norm& nd, int img, Coef& cf) {
+  const int lane = threadIdx.x & 31;
+  if (lane < nd.c) {
+    const float4* o = reinterpret_cast<const float4*>(nd.coef_nc + ((size_t)img * nd.c + lane) * 8);
+    const float4 a = o[0], b = o[1];
+    cf.A[lane] = a.x; cf.B[lane] = a.y; cf.al[lane] = a.z; cf.be[lane] = a.w; cf.mu[lane] = b.x; cf.rc[lane] = b.y; cf.gmean[lane] = b.z; cf.gr[lane] = b.w;
   }
   __syncwarp();
 }
@@ -131,15 +157,15 @@ __device__ __noinline__ void norm_backward_D(const dcv_sc_norm& nd, Coef& cf, co
 // kernels and adds the image's terms of the BatchNorm adjoint sums / GroupNorm parameter gradients to the sharded accumulators u_sums[shard][c][4] =
 // {U1 = sum du, U2raw = sum du*y, d gn_weight, d gn_bias}.
 __device__ __noinline__ void norm_backward_image_sums(const dcv_sc_norm& nd, int img, Coef& cf, const float* s) {
-  norm_forward_coeffs(nd, img, cf, false);
+  load_coeffs(nd, img, cf);
   norm_backward_D(nd, cf, s);
   const int lane = threadIdx.x & 31, c = nd.c;
   if (lane < c) {
+    *reinterpret_cast<float4*>(nd.d_nc + ((size_t)img * c + lane) * 4) = make_float4(cf.D1[lane], cf.D2[lane], cf.D3[lane], 0.f);   // for the producer's backward kernels
     const double s1 = (double)s[2 * lane], s2 = (double)s[2 * lane + 1], hw = (double)nd.hw;
     const double sy = (double)nd.stats_nc[((size_t)img * c + lane) * 2], syy = (double)nd.stats_nc[((size_t)img * c + lane) * 2 + 1];
     const double D1 = (double)cf.D1[lane], D2 = (double)cf.D2[lane], D3 = (double)cf.D3[lane];
-    nd.s_nc[((size_t)img * c + lane) * 2] = (float)s1;
-    nd.s_nc[((size_t)img * c + lane) * 2 + 1] = (float)s2;
+    if (nd.s_nc) { nd.s_nc[((size_t)img * c + lane) * 2] = (float)s1; nd.s_nc[((size_t)img * c + lane) * 2 + 1] = (float)s2; }   // diagnostic only: nothing reads it
     float* u = nd.u_sums + ((size_t)(img % kShards) * c + lane) * 4;
     atomicAdd(u, (float)(D1 * s1 + D2 * sy + D3 * hw));
     atomicAdd(u + 1, (float)(D1 * s2 + D2 * syy + D3 * sy));
@@ -151,13 +177,14 @@ __device__ __noinline__ void norm_backward_image_sums(const dcv_sc_norm& nd, int
   __syncwarp();
 }
 
-// ---- P, Q, R of image `img` (one warp): forward coefficients, D from the stored sums, BatchNorm adjoint from the complete batch sums.
+// ---- P, Q, R of image `img` (one warp): cached forward coefficients and D, BatchNorm adjoint from the complete batch sums.
 // `param_grads`: this warp also writes the normalisation parameter gradients (one CTA of one kernel per block does).
 __device__ __noinline__ void norm_backward_pqr(const dcv_sc_norm& nd, int img, Coef& cf, bool param_grads, float* d_bn_w, float* d_bn_b, float* d_gn_w, float* d_gn_b) {
-  norm_forward_coeffs(nd, img, cf, false);
-  norm_backward_D(nd, cf, nd.s_nc + (size_t)img * nd.c * 2);
+  load_coeffs(nd, img, cf);
   const int lane = threadIdx.x & 31, c = nd.c;
   if (lane < c) {
+    const float4 d = *reinterpret_cast<const float4*>(nd.d_nc + ((size_t)img * c + lane) * 4);
+    cf.D1[lane] = d.x; cf.D2[lane] = d.y; cf.D3[lane] = d.z;
     double U1 = 0.0, U2raw = 0.0, dgw = 0.0, dgb = 0.0;
     for (int sh = 0; sh < kShards; ++sh) {
       const float* u = nd.u_sums + ((size_t)sh * c + lane) * 4;
@@ -200,10 +227,22 @@ __device__ __forceinline__ float act_bwd(float y, int act, float slope) {
   return 1.f;
 }
 
-__device__ __forceinline__ void mma16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// ldmatrix: lane l supplies the 16-byte row (l & 7) of 8x8 matrix (l >> 3); register i of thread (g = lane / 4, t = lane % 4) is elements (2t, 2t + 1) of
+// row g of matrix i — or, with .trans, rows (2t, 2t + 1) of column g.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -214,11 +253,14 @@ __device__ __forceinline__ float round_bf(float v) { return __bfloat162float(__f
 
 // ---- operand staging -------------------------------------------------------------------------------------------------------------------------
 // Source element of image-local index (pixel, channel): either the plain tensor, the producer's raw output with its pending affine (A, B), or the
-// pre-activation gradient dy = act'(y) * (P*dz + Q*y + R) assembled from dz and y. One functor type per kernel keeps the loaders generic.
+// pre-activation gradient dy = act'(y) * (P*dz + Q*y + R) assembled from dz and y. `fetch` only issues the global loads (their results are first
+// touched by `decode`), so a kernel can put a prologue and a barrier between the two.
 struct SrcPlain {
   const bf16* x; const Coef* cf;   // cf == nullptr: plain
-  __device__ __forceinline__ void load8(size_t e0, int c0, int cmask, float* v) const {   // 8 consecutive elements starting at e0 (16-byte aligned), channel of element i = (c0 + i) & cmask
-    vec_unpack<bf16>(*reinterpret_cast<const uint4*>(x + e0), v);
+  struct Raw { uint4 a; };
+  __device__ __forceinline__ Raw fetch(size_t e0) const { Raw r; r.a = *reinterpret_cast<const uint4*>(x + e0); return r; }
+  __device__ __forceinline__ void decode(const Raw& r, int c0, int cmask, float* v) const {   // channel of element i = (c0 + i) & cmask
+    vec_unpack<bf16>(r.a, v);
     if (cf) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { const int ch = (c0 + i) & cmask; v[i] = fmaf(cf->A[ch], v[i], cf->B[ch]); }
@@ -232,10 +274,14 @@ struct SrcPlain {
 struct SrcDy {
   const bf16* dz; const bf16* y; const Coef* cf;   // cf == nullptr: P = 1, Q = R = 0
   int act; float slope;
-  __device__ __forceinline__ void load8(size_t e0, int c0, int cmask, float* v) const {
+  struct Raw { uint4 a, b; };
+  __device__ __forceinline__ Raw fetch(size_t e0) const {
+    Raw r; r.a = *reinterpret_cast<const uint4*>(dz + e0); r.b = *reinterpret_cast<const uint4*>(y + e0); return r;
+  }
+  __device__ __forceinline__ void decode(const Raw& r, int c0, int cmask, float* v) const {
     float b[8];
-    vec_unpack<bf16>(*reinterpret_cast<const uint4*>(dz + e0), v);
-    vec_unpack<bf16>(*reinterpret_cast<const uint4*>(y + e0), b);
+    vec_unpack<bf16>(r.a, v);
+    vec_unpack<bf16>(r.b, b);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ch = (c0 + i) & cmask;
@@ -250,96 +296,173 @@ struct SrcDy {
   }
 };
 
-// NHWC tile with halo: tile[(y + PAD) * Wp + x + PAD][CI] = src(y, x, 0..c_src) (channels >= c_src zero). The halo was zeroed once and is never written.
-// `sum8`: when non-null, per-thread sums of the 8 vector slots (the bias gradient of the weight-gradient kernel; only the vector path fills it).
-template <int CI, typename Src>
-__device__ __forceinline__ void stage_nhwc(bf16* tile, const Src& src, size_t img_elem0, int H, int W, int Wp, int PAD, int c_src, int tid) {
-  if (c_src == CI && (img_elem0 % 8) == 0) {
-    const int nvec = H * W * CI / 8;
-    const int wlog = 31 - __clz(W);   // W is a power of two (shape_ok)
-    for (int v = tid; v < nvec; v += kThreads) {
-      const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix >> wlog, x = pix & (W - 1);
-      float f[8];
-      src.load8(img_elem0 + e0, c0, CI - 1, f);
-      bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI + c0;
-      if (CI == 4) {   // two pixels of 8 bytes each (x is even, so both are in the same row)
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
-        *reinterpret_cast<uint2*>(dst + 4) = make_uint2(pack2(f[4], f[5]), pack2(f[6], f[7]));
-      } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-      }
-    }
-  } else {
-    const int wlog = 31 - __clz(W);
-    for (int pix = tid; pix < H * W; pix += kThreads) {
-      const int y = pix >> wlog, x = pix & (W - 1);
-      bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI;
+// NHWC tile with halo: tile[(y + PAD) * Wp + x + PAD][CI] = src(y, x, 0..c_src) (channels >= c_src zero). The halo and the padding channels were zeroed
+// once and are never written. Three routes: whole 16-byte vectors when the tensor has exactly CI channels (two-phase: `fetch` the first PF vectors of
+// every thread, [the caller's prologue + barrier], `store`); 16-byte loads + 2-byte tile stores when c_src < CI but the image is a whole number of
+// aligned vectors (the 3-channel network input); scalar otherwise.
+constexpr int kPF = 4;   // vectors of a thread in flight across the prologue
+template <int CI, int NTHR, typename Src> struct Stager {
+  typename Src::Raw raw[kPF];
+  bool vec;
+  __device__ __forceinline__ void fetch(const Src& src, size_t e_img, int HW, int c_src, int tid) {
+    vec = (c_src == CI) && (e_img % 8) == 0;
+    if (vec) {
+      const int nvec = HW * CI / 8;
 #pragma unroll
-      for (int c = 0; c < CI; ++c) dst[c] = __float2bfloat16_rn(c < c_src ? src.load1(img_elem0 + (size_t)pix * c_src + c, c) : 0.f);
+      for (int i = 0; i < kPF; ++i) { const int v = tid + i * NTHR; if (v < nvec) raw[i] = src.fetch(e_img + (size_t)v * 8); }
     }
   }
-}
-
-// ---- implicit-GEMM core shared by forward and data gradient ------------------------------------------------------------------------------------
-// One image: M = H*W pixels (16 consecutive pixels of a row per m-tile; W % 16 == 0), N = NT*8 output columns, K = (tap, channel) of a KS x KS window
-// over a CI-channel NHWC tile. `breg`: the B fragments (weights), resident in registers for the whole kernel. `epi(y, x, col, v0, v1)` receives the two
-// adjacent output columns col, col+1 of pixel (y, x).
-template <int CI, int NT, int KS> struct Core {
-  static constexpr int KK = KS * KS * CI, KSTEPS = (KK + 15) / 16, CW = CI / 2;
-  uint32_t breg[KSTEPS][NT][2];
-  int aoff[KSTEPS][2];
-
-  // wsel(tap_r, tap_s, cin, col) -> weight value as bf16 bits (0 when out of range)
-  template <typename WSel>
-  __device__ __forceinline__ void setup(int Wp, WSel wsel) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __device__ __forceinline__ void put(bf16* tile, const Src& src, const typename Src::Raw& r, int v, int W, int wlog, int Wp, int PAD) const {
+    const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix >> wlog, x = pix & (W - 1);
+    float f[8];
+    src.decode(r, c0, CI - 1, f);
+    bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI + c0;
+    if (CI == 4) {   // two pixels of 8 bytes each (x is even, so both are in the same row)
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
+      *reinterpret_cast<uint2*>(dst + 4) = make_uint2(pack2(f[4], f[5]), pack2(f[6], f[7]));
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+  }
+  __device__ __forceinline__ void store(bf16* tile, const Src& src, size_t e_img, int H, int W, int Wp, int PAD, int c_src, int tid) {
+    const int wlog = 31 - __clz(W), HW = H * W;
+    if (vec) {
+      const int nvec = HW * CI / 8;
 #pragma unroll
-    for (int j = 0; j < KSTEPS; ++j)
+      for (int i = 0; i < kPF; ++i) { const int v = tid + i * NTHR; if (v < nvec) put(tile, src, raw[i], v, W, wlog, Wp, PAD); }
+      for (int v = tid + kPF * NTHR; v < nvec; v += NTHR) put(tile, src, src.fetch(e_img + (size_t)v * 8), v, W, wlog, Wp, PAD);
+    } else if (src.cf == nullptr && c_src < CI && (HW * c_src) % 8 == 0 && ((e_img * 2) % 16) == 0 && sizeof(typename Src::Raw) == sizeof(uint4)) {
+      const int nvec = HW * c_src / 8;
+      for (int v = tid; v < nvec; v += NTHR) {
+        const typename Src::Raw r = src.fetch(e_img + (size_t)v * 8);
+        float f[8];
+        vec_unpack<bf16>(r.a, f);
+        int pix = (v * 8) / c_src, c = (v * 8) - pix * c_src;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int kk = 16 * j + 8 * h2 + 2 * t, tap = kk / CI, c = kk % CI;
-        const bool on = tap < KS * KS;
-        aoff[j][h2] = on ? ((tap / KS) * Wp + tap % KS) * CW + c / 2 : 0;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int col = nt * 8 + g;
-          const uint32_t lo = on ? wsel(tap / KS, tap % KS, c, col) : 0u, hi = on ? wsel(tap / KS, tap % KS, c + 1, col) : 0u;
-          breg[j][nt][h2] = lo | (hi << 16);
+        for (int i = 0; i < 8; ++i) {
+          const int y = pix >> wlog, x = pix & (W - 1);
+          tile[((size_t)(y + PAD) * Wp + x + PAD) * CI + c] = __float2bfloat16_rn(f[i]);
+          if (++c == c_src) { c = 0; ++pix; }
         }
       }
-  }
-
-  // `pre(y, x, col, slot)` may start global loads whose results the epilogue needs (issued before the MMAs of the tile, consumed after them);
-  // `epi(y, x, col, v0, v1, slot)` receives the two adjacent output columns col, col + 1 of pixel (y, x); slot = 2 * nt + (0: pixel x0 + g, 1: pixel x0 + g + 8).
-  template <typename Pre, typename Epi>
-  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Pre pre, Epi epi) const {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-    const int mtiles = H * W / 16, wlog = 31 - __clz(W);
-    for (int mt = warp; mt < mtiles; mt += kWarps) {
-      const int p0 = mt * 16, y = p0 >> wlog, x0 = p0 & (W - 1);
-      const int pb = (y * Wp + x0 + g) * CW;
+    } else {
+      for (int pix = tid; pix < HW; pix += NTHR) {
+        const int y = pix >> wlog, x = pix & (W - 1);
+        bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) { pre(y, x0 + g, nt * 8 + 2 * t, 2 * nt); pre(y, x0 + g + 8, nt * 8 + 2 * t, 2 * nt + 1); }
-      float acc[NT][4];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-#pragma unroll
-      for (int j = 0; j < KSTEPS; ++j) {
-        const uint32_t a0 = tw[pb + aoff[j][0]], a1 = tw[pb + 8 * CW + aoff[j][0]], a2 = tw[pb + aoff[j][1]], a3 = tw[pb + 8 * CW + aoff[j][1]];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma16816(acc[nt], a0, a1, a2, a3, breg[j][nt][0], breg[j][nt][1]);
-      }
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        epi(y, x0 + g, nt * 8 + 2 * t, acc[nt][0], acc[nt][1], 2 * nt);
-        epi(y, x0 + g + 8, nt * 8 + 2 * t, acc[nt][2], acc[nt][3], 2 * nt + 1);
+        for (int c = 0; c < CI; ++c) dst[c] = __float2bfloat16_rn(c < c_src ? src.load1(e_img + (size_t)pix * c_src + c, c) : 0.f);
       }
     }
   }
 };
 
-// Sum over the 8 lanes that share `t` (same output columns), then ONE shared-memory atomic per (column, value) and warp.
+// ---- GEMM geometry shared by the three kernels ------------------------------------------------------------------------------------------------------
+// CI: channels of the tile (4: pixel-pair mode, 16: plain mode); NO: channels on the other side (4 or 16); KS: filter size.
+// A "chunk" is one 16-byte ldmatrix row's worth of the (tap, channel) index: pair mode: two adjacent taps (s0, s0 + 1), s0 even, of filter row r, 4 channels
+// each; plain mode: half (8 channels) of one tap.
+template <int CI, int NO, int KS> struct Geo {
+  static constexpr bool PAIR = (CI == 4);
+  static constexpr int CPR = (KS + 1) / 2;                              // chunks per filter row (pair mode)
+  static constexpr int NCH = PAIR ? KS * CPR : KS * KS * 2;             // chunks
+  static constexpr int KSTEPS = (NCH + 1) / 2;                          // forward / data gradient: k-steps of 16 = 2 chunks
+  static constexpr int N = PAIR ? 2 * NO : (NO < 8 ? 8 : NO);           // GEMM columns: (parity, channel) or channel
+  static constexpr int NT = N / 8;
+  static constexpr int PIXB = CI * 2;                                   // bytes per tile pixel
+  // byte offset of chunk `ch` relative to the row address of the pixel (pair)
+  __device__ static __forceinline__ int chunk_off(int ch, int Wp) {
+    if (ch >= NCH) return 0;   // padding chunk: any valid address (its weights / results are zero / ignored)
+    if (PAIR) return ((ch / CPR) * Wp + 2 * (ch % CPR)) * PIXB;
+    const int tap = ch >> 1;
+    return ((tap / KS) * Wp + tap % KS) * PIXB + (ch & 1) * 16;
+  }
+  // (filter row, filter column, channel) of element e (0..7) of chunk ch for GEMM column n; returns false when the product term does not exist
+  __device__ static __forceinline__ bool decode(int ch, int e, int n, int& r, int& s, int& c, int& o) {
+    if (ch >= NCH) return false;
+    if (PAIR) {
+      r = ch / CPR; c = e & 3; o = n % NO;
+      s = 2 * (ch % CPR) + (e >> 2) - n / NO;
+      return s >= 0 && s < KS;
+    }
+    const int tap = ch >> 1;
+    r = tap / KS; s = tap % KS; c = (ch & 1) * 8 + e; o = n;
+    return n < NO;
+  }
+};
+
+// ---- implicit-GEMM core shared by forward and data gradient ------------------------------------------------------------------------------------
+// One image: M = pixel pairs (pair mode) or pixels, 16 consecutive per m-tile; A by ldmatrix.x4 from the tile; `breg`: the B fragments (weights),
+// resident in registers for the whole kernel. `pre(y, x, o, slot)` may start global loads whose results the epilogue needs (issued before the tile's
+// MMAs); `epi(y, x, o, v0, v1, slot)` receives output channels o, o + 1 of pixel (y, x).
+template <int CI, int NO, int KS> struct Core {
+  typedef Geo<CI, NO, KS> G;
+  static constexpr int KSTEPS = G::KSTEPS, NT = G::NT;
+  uint32_t breg[KSTEPS][NT][2];
+  int aoff[KSTEPS];
+
+  // wsel(r, s, c, o) -> weight of tile channel c for output channel o at filter position (r, s), as bf16 bits (0 when out of range)
+  template <typename WSel>
+  __device__ __forceinline__ void setup(int Wp, WSel wsel) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < KSTEPS; ++j) {
+      aoff[j] = G::chunk_off(2 * j + (lane >> 4), Wp);
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          int r, s, c, o;
+          const bool on = G::decode(2 * j + h2, 2 * t, nt * 8 + g, r, s, c, o);
+          const uint32_t lo = on ? wsel(r, s, c, o) : 0u, hi = on ? wsel(r, s, c + 1, o) : 0u;
+          breg[j][nt][h2] = lo | (hi << 16);
+        }
+    }
+  }
+
+  template <typename Pre, typename Epi>
+  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Pre pre, Epi epi) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t tile_u = smem_u32(tile);
+    const int wlog = 31 - __clz(W);
+    const int mtiles = G::PAIR ? H * W / 32 : H * W / 16;
+    const int arow = ((lane >> 3) & 1) * 8 + (lane & 7);   // this lane's ldmatrix row of the m-tile
+    for (int mt = warp; mt < mtiles; mt += kWarps) {
+      int ya, xa, y0, x0, y1, x1;   // (ya, xa): this lane's A row; (y0, x0) / (y1, x1): the pixels (pair mode: even pixel of the pair) of accumulator rows g / g + 8
+      if (G::PAIR) {
+        const int qa = mt * 16 + arow, q0 = mt * 16 + g, q1 = q0 + 8, hl = wlog - 1, hm = (W >> 1) - 1;
+        ya = qa >> hl; xa = (qa & hm) * 2; y0 = q0 >> hl; x0 = (q0 & hm) * 2; y1 = q1 >> hl; x1 = (q1 & hm) * 2;
+      } else {
+        const int pa = mt * 16 + arow, p0 = mt * 16 + g, p1 = p0 + 8;
+        ya = pa >> wlog; xa = pa & (W - 1); y0 = p0 >> wlog; x0 = p0 & (W - 1); y1 = p1 >> wlog; x1 = p1 & (W - 1);
+      }
+      const uint32_t abase = tile_u + (uint32_t)((ya * Wp + xa) * G::PIXB);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = nt * 8 + 2 * t, par = G::PAIR ? n / NO : 0, o = G::PAIR ? n % NO : n;
+        pre(y0, x0 + par, o, 2 * nt); pre(y1, x1 + par, o, 2 * nt + 1);
+      }
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < KSTEPS; ++j) {
+        uint32_t a[4];
+        ldsm_x4(abase + aoff[j], a);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma16816(acc[nt], a, breg[j][nt][0], breg[j][nt][1]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n = nt * 8 + 2 * t, par = G::PAIR ? n / NO : 0, o = G::PAIR ? n % NO : n;
+        epi(y0, x0 + par, o, acc[nt][0], acc[nt][1], 2 * nt);
+        epi(y1, x1 + par, o, acc[nt][2], acc[nt][3], 2 * nt + 1);
+      }
+    }
+  }
+  // output channel of accumulator columns (nt, 2t), for per-thread column bookkeeping
+  __device__ static __forceinline__ int out_channel(int nt, int t) { const int n = nt * 8 + 2 * t; return G::PAIR ? n % NO : n; }
+};
+
+// Per-column partial sums of a thread -> sum over the 8 lanes that share `t` (same columns), then ONE shared-memory atomic per (column, value) and warp.
 __device__ __forceinline__ void reduce_cols_to_smem(float v, float* dst) {
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -354,43 +477,47 @@ struct FwdArgs {
   dcv_sc_norm xn, yn;
 };
 
-template <int CI, int NT, int KS>
+template <int CI, int NO, int KS>
 __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_raw);
+  typedef Core<CI, NO, KS> C;
+  constexpr int NT = C::NT, PAD = KS / 2;
   __shared__ Coef cfx;
-  __shared__ float sh_stat[NT * 8][2];
-  constexpr int PAD = KS / 2;
+  __shared__ float sh_stat[kMaxC][2];
   const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, t = lane & 3;
+  SrcPlain src{a.x, a.xn.enabled ? &cfx : nullptr};
+  Stager<CI, kThreads, SrcPlain> stager;
+  stager.fetch(src, (size_t)blockIdx.x * H * W * a.c_src, H * W, a.c_src, tid);   // the first image's L2 round trip overlaps everything up to the barrier
   for (int i = tid; i < Hp * Wp * CI / 8; i += kThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-  Core<CI, NT, KS> core;
+  C core;
   const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
-  core.setup(Wp, [&](int r, int s, int c, int col) -> uint32_t {
-    return (c < a.c_src && col < a.k_out) ? (uint32_t)wb[((size_t)(col * KS + r) * KS + s) * a.c_src + c] : 0u;
+  core.setup(Wp, [&](int r, int s, int c, int o) -> uint32_t {
+    return (c < a.c_src && o < a.k_out) ? (uint32_t)wb[((size_t)(o * KS + r) * KS + s) * a.c_src + c] : 0u;
   });
   float bias_r[NT][2];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int e = 0; e < 2; ++e) { const int col = nt * 8 + 2 * t + e; bias_r[nt][e] = (a.bias && col < a.k_out) ? a.bias[col] : 0.f; }
+    for (int e = 0; e < 2; ++e) { const int o = C::out_channel(nt, t) + e; bias_r[nt][e] = (a.bias && o < a.k_out) ? a.bias[o] : 0.f; }
 
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
-    __syncthreads();   // the previous image's tile has been consumed (first pass: the halo is zeroed)
+    const size_t e_img = (size_t)img * H * W * a.c_src;
+    if (img != (int)blockIdx.x) { __syncthreads(); stager.fetch(src, e_img, H * W, a.c_src, tid); }   // the previous image's tile has been consumed
     if (tid < 32 && a.xn.enabled) norm_forward_coeffs(a.xn, img, cfx, a.update_running != 0 && img == 0);
-    if (tid < NT * 8 * 2) (&sh_stat[0][0])[tid] = 0.f;
-    __syncthreads();
-    SrcPlain src{a.x, a.xn.enabled ? &cfx : nullptr};
-    stage_nhwc<CI>(tile, src, (size_t)img * H * W * a.c_src, H, W, Wp, PAD, a.c_src, tid);
+    if (tid >= 32 && tid < 32 + kMaxC * 2) (&sh_stat[0][0])[tid - 32] = 0.f;
+    __syncthreads();   // coefficients ready, halo zeroed
+    stager.store(tile, src, e_img, H, W, Wp, PAD, a.c_src, tid);
     __syncthreads();
     float s1[NT][2], s2[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
     bf16* yimg = a.y + (size_t)img * H * W * a.k_out;
-    core.run(tile, H, W, Wp, [](int, int, int, int) {}, [&](int y, int x, int col, float v0, float v1, int) {
-      const int nt = col >> 3;
+    core.run(tile, H, W, Wp, [](int, int, int, int) {}, [&](int y, int x, int o, float v0, float v1, int slot) {
+      const int nt = slot >> 1;
       v0 = round_bf(act_fwd(v0 + bias_r[nt][0], a.act, a.slope));
       v1 = round_bf(act_fwd(v1 + bias_r[nt][1], a.act, a.slope));
-      if (col < a.k_out) *reinterpret_cast<uint32_t*>(yimg + ((size_t)y * W + x) * a.k_out + col) = pack2(v0, v1);
+      if (o < a.k_out) *reinterpret_cast<uint32_t*>(yimg + ((size_t)y * W + x) * a.k_out + o) = pack2(v0, v1);
       s1[nt][0] += v0; s1[nt][1] += v1; s2[nt][0] = fmaf(v0, v0, s2[nt][0]); s2[nt][1] = fmaf(v1, v1, s2[nt][1]);   // statistics of the STORED values
     });
     if (a.yn.enabled) {
@@ -398,8 +525,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArg
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          reduce_cols_to_smem(s1[nt][e], &sh_stat[nt * 8 + 2 * t + e][0]);
-          reduce_cols_to_smem(s2[nt][e], &sh_stat[nt * 8 + 2 * t + e][1]);
+          const int o = C::out_channel(nt, t) + e;   // < kMaxC
+          reduce_cols_to_smem(s1[nt][e], &sh_stat[o][0]);
+          reduce_cols_to_smem(s2[nt][e], &sh_stat[o][1]);
         }
       __syncthreads();
       if (tid < a.k_out) {   // this CTA owns the whole image: plain stores per (image, channel); the batch sums are sharded atomics
@@ -425,44 +553,48 @@ struct DgradArgs {
   dcv_sc_norm yn, xn;
 };
 
-template <int KI, int NT, int KS>
+template <int KI, int NO, int KS>
 __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const DgradArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_raw);
+  typedef Core<KI, NO, KS> C;
+  constexpr int NT = C::NT, PAD = KS / 2;
   __shared__ Coef cfy, cfx;
-  __shared__ float sh_s[NT * 8][2];
-  constexpr int PAD = KS / 2;
+  __shared__ float sh_s[kMaxC][2];
   const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, t = lane & 3;
+  SrcDy src{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
+  Stager<KI, kThreads, SrcDy> stager;
+  stager.fetch(src, (size_t)blockIdx.x * H * W * a.k_out, H * W, a.k_out, tid);
   for (int i = tid; i < Hp * Wp * KI / 8; i += kThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-  Core<KI, NT, KS> core;
+  C core;
   const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
-  core.setup(Wp, [&](int r, int s, int k, int col) -> uint32_t {   // tile channel k = output channel of the layer, column = input channel of the layer
-    return (k < a.k_out && col < a.c_in) ? (uint32_t)wb[((size_t)(k * KS + (KS - 1 - r)) * KS + (KS - 1 - s)) * a.c_in + col] : 0u;
+  core.setup(Wp, [&](int r, int s, int k, int o) -> uint32_t {   // tile channel k = output channel of the layer, GEMM column o = input channel of the layer
+    return (k < a.k_out && o < a.c_in) ? (uint32_t)wb[((size_t)(k * KS + (KS - 1 - r)) * KS + (KS - 1 - s)) * a.c_in + o] : 0u;
   });
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
-    __syncthreads();
+    const size_t e_img = (size_t)img * H * W * a.k_out;
+    if (img != (int)blockIdx.x) { __syncthreads(); stager.fetch(src, e_img, H * W, a.k_out, tid); }
     if (tid < 32 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy, false, nullptr, nullptr, nullptr, nullptr);
-    if (tid < NT * 8 * 2) (&sh_s[0][0])[tid] = 0.f;
+    if (tid >= 32 && tid < 32 + kMaxC * 2) (&sh_s[0][0])[tid - 32] = 0.f;
     __syncthreads();
-    SrcDy src{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
-    stage_nhwc<KI>(tile, src, (size_t)img * H * W * a.k_out, H, W, Wp, PAD, a.k_out, tid);
+    stager.store(tile, src, e_img, H, W, Wp, PAD, a.k_out, tid);
     __syncthreads();
     float s1[NT][2], s2[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
     const size_t img0 = (size_t)img * H * W * a.c_in;
     uint32_t yraw[2 * NT];   // the producer's raw output at this thread's output elements: loaded BEFORE the tile's MMAs (an L2 round trip), used after them
-    core.run(tile, H, W, Wp, [&](int y, int x, int col, int slot) {
-      if (a.xn.enabled && col < a.c_in) yraw[slot] = *reinterpret_cast<const uint32_t*>(a.x_raw + img0 + ((size_t)y * W + x) * a.c_in + col);   // c_in is even here (check_norm)
-    }, [&](int y, int x, int col, float v0, float v1, int slot) {
-      if (col < a.c_in) {
-        const size_t e = img0 + ((size_t)y * W + x) * a.c_in + col;
+    core.run(tile, H, W, Wp, [&](int y, int x, int o, int slot) {
+      if (a.xn.enabled && o < a.c_in) yraw[slot] = *reinterpret_cast<const uint32_t*>(a.x_raw + img0 + ((size_t)y * W + x) * a.c_in + o);   // c_in is even here (check_norm)
+    }, [&](int y, int x, int o, float v0, float v1, int slot) {
+      if (o < a.c_in) {
+        const size_t e = img0 + ((size_t)y * W + x) * a.c_in + o;
         v0 = round_bf(v0); v1 = round_bf(v1);
         if ((a.c_in & 1) == 0) *reinterpret_cast<uint32_t*>(a.dx + e) = pack2(v0, v1);
-        else { a.dx[e] = __float2bfloat16_rn(v0); if (col + 1 < a.c_in) a.dx[e + 1] = __float2bfloat16_rn(v1); }   // odd channel counts (a 3-channel input image)
+        else { a.dx[e] = __float2bfloat16_rn(v0); if (o + 1 < a.c_in) a.dx[e + 1] = __float2bfloat16_rn(v1); }   // odd channel counts (a 3-channel input image)
         if (a.xn.enabled) {
           const uint32_t yr = yraw[slot];
-          const int nt = col >> 3;
+          const int nt = slot >> 1;
           s1[nt][0] += v0; s1[nt][1] += v1; s2[nt][0] = fmaf(v0, bf_lo(yr), s2[nt][0]); s2[nt][1] = fmaf(v1, bf_hi(yr), s2[nt][1]);
         }
       }
@@ -472,8 +604,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          reduce_cols_to_smem(s1[nt][e], &sh_s[nt * 8 + 2 * t + e][0]);
-          reduce_cols_to_smem(s2[nt][e], &sh_s[nt * 8 + 2 * t + e][1]);
+          const int o = C::out_channel(nt, t) + e;
+          reduce_cols_to_smem(s1[nt][e], &sh_s[o][0]);
+          reduce_cols_to_smem(s2[nt][e], &sh_s[o][1]);
         }
       __syncthreads();
       if (tid < 32) norm_backward_image_sums(a.xn, img, cfx, &sh_s[0][0]);
@@ -482,12 +615,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
 }
 
 // ---- weight gradient ----------------------------------------------------------------------------------------------------------------------------
-// dw[k][r][s][c] = sum over (image, pixel) of dy[pix][k] * z[pix + (r, s) - PAD][c] as the GEMM D[(tap, c)][k] += Zt[(tap, c)][pix] * dy[pix][k]: M = KS*KS*CI
-// rows, N = NT*8 output channels, K = pixels (16 consecutive pixels of a row per k-step). Both operands need PIXEL pairs in a register, so they are staged
-// channel-planar: dyT[k][pix] and Z[c][(y + PAD) * Wp + x + PAD]; a tap shifts the pixel index by r*Wp + s, which is odd for odd s, so a second copy of Z
-// shifted by one pixel (Z1[i] = Z0[i + 1]) keeps every fragment register one ALIGNED 32-bit shared load (Wp is even: the parity of the shift is s & 1).
-// z (the layer's input) is normalised while staging, dy is assembled from dz and y while staging (and summed into the bias gradient); each warp keeps
-// its share of D in registers across all the CTA's images, the CTA reduces once in shared memory and adds into dw with one atomic per element.
+// dw[k][r][s][c] = sum over (image, pixel) of dy[pix][k] * z[pix + (r, s) - PAD][c] as the GEMM D[(tap, c)][k] += Zt[(tap, c)][pix] * dy[pix][k]: M = chunks
+// of 8 (tap, channel) rows (two per m-tile), K = pixels (pair mode: pixel pairs), N = output channels (pair mode: (parity, channel)). Both operands come
+// TRANSPOSED out of NHWC tiles with ldmatrix.trans: z is the same halo tile the forward kernel builds (normalised while staging), dy is assembled from dz
+// and y while staging (and summed into the bias gradient). Each warp keeps its share of D in registers across all the CTA's images; the CTA reduces
+// once in shared memory (in dw's own layout) and adds into dw with one atomic per element.
 struct WgradArgs {
   int n, h, w, c_src, k_out, act; float slope;
   const bf16* x; const bf16* dz; const bf16* y;
@@ -495,36 +627,29 @@ struct WgradArgs {
   dcv_sc_norm xn, yn;
 };
 
-__device__ __forceinline__ void store_pair_planar(bf16* plane, int pos, float lo, float hi) {
-  if ((pos & 1) == 0) *reinterpret_cast<uint32_t*>(plane + pos) = pack2(lo, hi);
-  else { plane[pos] = __float2bfloat16_rn(lo); plane[pos + 1] = __float2bfloat16_rn(hi); }
-}
-
-template <int CI, int NT, int KS>
-__global__ void __launch_bounds__(kWgThreads) sc_wgrad_kernel(const WgradArgs a) {
+template <int CI, int NO, int KS>
+__global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int PAD = KS / 2, MROWS = KS * KS * CI, MT = (MROWS + 15) / 16, KO = NT * 8;
-  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, PS = Hp * Wp, wlog = 31 - __clz(W);   // PS: plane stride (elements), even; W: power of two
-  bf16* z0 = reinterpret_cast<bf16*>(smem_raw);          // [CI][PS]
-  bf16* z1 = z0 + (size_t)CI * PS;                       // [CI][PS], z1[i] = z0[i + 1]
-  bf16* dyT = z1 + (size_t)CI * PS;                      // [KO][HW]
-  float* sh_dw = reinterpret_cast<float*>(dyT + (size_t)KO * HW);   // [MT*16][KO]
+  typedef Geo<CI, NO, KS> G;
+  constexpr int PAD = KS / 2, MT = (G::NCH + 1) / 2, NT = G::NT, KOP = G::PAIR ? NO : (NO < 8 ? 8 : NO);   // KOP: channel stride of the dy tile
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, wlog = 31 - __clz(W);
+  bf16* tile = reinterpret_cast<bf16*>(smem_raw);                       // [Hp][Wp][CI]
+  bf16* dyt = tile + (size_t)Hp * Wp * CI;                               // [HW][KOP]
+  float* sh_dw = reinterpret_cast<float*>(dyt + (size_t)HW * KOP);       // [k_out][KS][KS][c_src]
   __shared__ Coef cfx, cfy;
-  __shared__ float sh_db[KO];
+  __shared__ float sh_db[kMaxC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < 2 * CI * PS / 8; i += kWgThreads) reinterpret_cast<uint4*>(z0)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < KO * HW / 8; i += kWgThreads) reinterpret_cast<uint4*>(dyT)[i] = make_uint4(0u, 0u, 0u, 0u);   // rows >= k_out stay zero
-  for (int i = tid; i < MT * 16 * KO; i += kWgThreads) sh_dw[i] = 0.f;
-  if (tid < KO) sh_db[tid] = 0.f;
-  // per-thread A row offsets (32-bit words into z0 / z1): rows g and g + 8 of every m-tile
-  int zoff[MT][2];
+  const int total = a.k_out * KS * KS * a.c_src;
+  for (int i = tid; i < Hp * Wp * CI / 8; i += kWgThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < HW * KOP / 8; i += kWgThreads) reinterpret_cast<uint4*>(dyt)[i] = make_uint4(0u, 0u, 0u, 0u);   // padding channels stay zero
+  for (int i = tid; i < total; i += kWgThreads) sh_dw[i] = 0.f;
+  if (tid < kMaxC) sh_db[tid] = 0.f;
+  // per-lane ldmatrix geometry. A (x4.trans): matrix mi = lane / 8: chunk (mi & 1) of the m-tile, k half (mi >> 1); B: see below.
+  const int mi = lane >> 3, li = lane & 7;
+  int aoff[MT];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      const int row = mt * 16 + g + 8 * h2, tap = row / CI, c = row % CI, r = tap / KS, s = tap % KS;
-      zoff[mt][h2] = row < MROWS ? ((s & 1) * CI * PS + c * PS + r * Wp + s - (s & 1)) / 2 : 0;
-    }
+  for (int mt = 0; mt < MT; ++mt) aoff[mt] = G::chunk_off(2 * mt + (mi & 1), Wp);
+  const uint32_t tile_u = smem_u32(tile), dyt_u = smem_u32(dyt);
   float acc[MT][NT][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
@@ -533,99 +658,119 @@ __global__ void __launch_bounds__(kWgThreads) sc_wgrad_kernel(const WgradArgs a)
   float db[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) db[i] = 0.f;
-  const uint32_t* zw = reinterpret_cast<const uint32_t*>(z0);
-  const uint32_t* dw_ = reinterpret_cast<const uint32_t*>(dyT);
+  SrcPlain sx{a.x, a.xn.enabled ? &cfx : nullptr};
+  SrcDy sd{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
+  Stager<CI, kWgThreads, SrcPlain> stx;
+  const int kv = a.k_out;   // channels of dy
+  const int nks = G::PAIR ? HW / 32 : HW / 16;
 
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+    const size_t e_img = (size_t)img * HW * a.c_src, k_img = (size_t)img * HW * kv;
     __syncthreads();   // previous image consumed / initial zeroing done
-    if (warp == 0 && a.xn.enabled) norm_forward_coeffs(a.xn, img, cfx, false);
+    stx.fetch(sx, e_img, HW, a.c_src, tid);
+    const bool dvec = (kv == 4 || kv % 8 == 0) && (k_img % 8) == 0;
+    const int ndv = HW * kv / 8;
+    SrcDy::Raw draw[2];
+    if (dvec) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { const int v = tid + i * kWgThreads; if (v < ndv) draw[i] = sd.fetch(k_img + (size_t)v * 8); }
+    }
+    if (warp == 0 && a.xn.enabled) load_coeffs(a.xn, img, cfx);
     if (warp == 1 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy, img == 0, a.d_bn_w, a.d_bn_b, a.d_gn_w, a.d_gn_b);
     __syncthreads();
-    // ---- stage z (planar, two copies) and dy (planar)
-    {
-      SrcPlain sx{a.x, a.xn.enabled ? &cfx : nullptr};
-      const size_t e_img = (size_t)img * HW * a.c_src;
-      if (a.c_src == CI && (e_img % 8) == 0) {
-        for (int v = tid; v < HW * CI / 8; v += kWgThreads) {
-          const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix >> wlog, x = pix & (W - 1), pos = (y + PAD) * Wp + x + PAD;
-          float f[8];
-          sx.load8(e_img + e0, c0, CI - 1, f);
-          if (CI == 4) {   // pixels (x, x + 1), channels 0..3: a pixel PAIR per plane
+    // ---- stage z (halo tile) and dy
+    stx.store(tile, sx, e_img, H, W, Wp, PAD, a.c_src, tid);
+    auto put_dy = [&](const SrcDy::Raw& r, int v) {
+      const int e0 = v * 8, pix = e0 / kv, c0 = e0 % kv;
+      float f[8];
+      sd.decode(r, c0, kv - 1, f);   // kv is a power of two here (4, 8, 16, 32)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { store_pair_planar(z0 + c * PS, pos, f[c], f[4 + c]); store_pair_planar(z1 + c * PS, pos - 1, f[c], f[4 + c]); }
-          } else {         // 8 channels of one pixel
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const bf16 b = __float2bfloat16_rn(f[i]); z0[(c0 + i) * PS + pos] = b; z1[(c0 + i) * PS + pos - 1] = b; }
-          }
-        }
+      for (int i = 0; i < 8; ++i) db[i] += round_bf(f[i]);
+      if (kv == KOP) {
+        *reinterpret_cast<uint4*>(dyt + e0) = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+      } else if (kv == 4) {   // two pixels of 4 channels into 8-channel rows
+        *reinterpret_cast<uint2*>(dyt + (size_t)pix * KOP) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
+        *reinterpret_cast<uint2*>(dyt + (size_t)(pix + 1) * KOP) = make_uint2(pack2(f[4], f[5]), pack2(f[6], f[7]));
       } else {
-        for (int pix = tid; pix < HW; pix += kWgThreads) {
-          const int y = pix >> wlog, x = pix & (W - 1), pos = (y + PAD) * Wp + x + PAD;
-          for (int c = 0; c < a.c_src; ++c) { const bf16 b = __float2bfloat16_rn(sx.load1(e_img + (size_t)pix * a.c_src + c, c)); z0[c * PS + pos] = b; z1[c * PS + pos - 1] = b; }
-        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dyt[(size_t)pix * KOP + c0 + i] = __float2bfloat16_rn(f[i]);
       }
-      SrcDy sd{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
-      const size_t k_img = (size_t)img * HW * a.k_out;
-      const int kv = a.k_out;   // channels of dy
-      if ((kv == 4 || kv % 8 == 0) && (k_img % 8) == 0) {
-        for (int v = tid; v < HW * kv / 8; v += kWgThreads) {
-          const int e0 = v * 8, pix = e0 / kv, c0 = e0 % kv;
-          float f[8];
-          sd.load8(k_img + e0, c0, kv - 1, f);   // kv is a power of two here (4, 8, 16)
+    };
+    if (dvec) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) db[i] += round_bf(f[i]);
-          if (kv == 4) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t*>(dyT + (size_t)c * HW + pix) = pack2(f[c], f[4 + c]);   // pix is even
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dyT[(size_t)(c0 + i) * HW + pix] = __float2bfloat16_rn(f[i]);
-          }
+      for (int i = 0; i < 2; ++i) { const int v = tid + i * kWgThreads; if (v < ndv) put_dy(draw[i], v); }
+      for (int v = tid + 2 * kWgThreads; v < ndv; v += kWgThreads) put_dy(sd.fetch(k_img + (size_t)v * 8), v);
+    } else {
+      for (int pix = tid; pix < HW; pix += kWgThreads)
+        for (int c = 0; c < kv; ++c) {
+          const float v = round_bf(sd.load1(k_img + (size_t)pix * kv + c, c));
+          dyt[(size_t)pix * KOP + c] = __float2bfloat16_rn(v);
+          atomicAdd(&sh_db[c], v);
         }
-      } else {
-        for (int pix = tid; pix < HW; pix += kWgThreads)
-          for (int c = 0; c < kv; ++c) {
-            const float v = round_bf(sd.load1(k_img + (size_t)pix * kv + c, c));
-            dyT[(size_t)c * HW + pix] = __float2bfloat16_rn(v);
-            atomicAdd(&sh_db[c], v);
-          }
-      }
     }
     __syncthreads();
-    // ---- MMA over the image's pixel chunks
-    for (int ch = warp; ch < HW / 16; ch += kWgWarps) {
-      const int p0 = ch * 16, y = p0 >> wlog, x0 = p0 & (W - 1);
-      const int pw = (y * Wp + x0) / 2 + t;   // pixel-pair word of this thread's k columns (2t, 2t + 1); + 4 words = pixels + 8
-      uint32_t b0[NT], b1[NT];
+    // ---- MMA over the image's k-steps (16 pixel pairs / pixels each)
+    for (int ks = warp; ks < nks; ks += kWgWarps) {
+      // A rows: the k index (pixel pair / pixel) ks * 16 + (mi >> 1) * 8 + li
+      const int ka = ks * 16 + (mi >> 1) * 8 + li;
+      int ya, xa;
+      if (G::PAIR) { ya = ka >> (wlog - 1); xa = (ka & ((W >> 1) - 1)) * 2; } else { ya = ka >> wlog; xa = ka & (W - 1); }
+      const uint32_t abase = tile_u + (uint32_t)((ya * Wp + xa) * G::PIXB);
+      // B fragments of this k-step
+      uint32_t b[NT][2];
+      if (G::PAIR) {
+        if (NT == 1) {           // NO = 4: a row = pixel pair = (parity, 4 channels); x2: matrix = k half
+          const int kb = ks * 16 + (mi & 1) * 8 + li;
+          ldsm_x2_t(dyt_u + (uint32_t)(kb * 16), b[0]);
+        } else {                 // NO = 16: n-tile nt = (parity nt >> 1, channel half nt & 1); two x4: matrices (nt, k half)
+          const int kb = ks * 16 + (mi & 1) * 8 + li;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int ko = nt * 8 + g;
-        b0[nt] = dw_[((size_t)ko * HW + p0) / 2 + t];
-        b1[nt] = dw_[((size_t)ko * HW + p0) / 2 + t + 4];
+          for (int h = 0; h < NT / 2; ++h) {
+            const int nt = 2 * h + (mi >> 1);
+            uint32_t r4[4];
+            ldsm_x4_t(dyt_u + (uint32_t)(((2 * kb + (nt >> 1)) * NO + (nt & 1) * 8) * 2), r4);
+            b[2 * h][0] = r4[0]; b[2 * h][1] = r4[1]; b[2 * h + 1][0] = r4[2]; b[2 * h + 1][1] = r4[3];
+          }
+        }
+      } else {
+        const int kb = ks * 16 + (mi & 1) * 8 + li;
+        if (NT == 1) {
+          ldsm_x2_t(dyt_u + (uint32_t)(kb * KOP * 2), b[0]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < NT / 2; ++h) {
+            const int nt = 2 * h + (mi >> 1);
+            uint32_t r4[4];
+            ldsm_x4_t(dyt_u + (uint32_t)((kb * KOP + nt * 8) * 2), r4);
+            b[2 * h][0] = r4[0]; b[2 * h][1] = r4[1]; b[2 * h + 1][0] = r4[2]; b[2 * h + 1][1] = r4[3];
+          }
+        }
       }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const uint32_t a0 = zw[zoff[mt][0] + pw], a1 = zw[zoff[mt][1] + pw], a2 = zw[zoff[mt][0] + pw + 4], a3 = zw[zoff[mt][1] + pw + 4];
+        uint32_t af[4];
+        ldsm_x4_t(abase + aoff[mt], af);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma16816(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+        for (int nt = 0; nt < NT; ++nt) mma16816(acc[mt][nt], af, b[nt][0], b[nt][1]);
       }
     }
   }
-  // ---- CTA reduction, then one atomic per weight-gradient element
+  // ---- CTA reduction in dw's layout, then one atomic per weight-gradient element
   __syncthreads();
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int r0 = mt * 16 + g, col = nt * 8 + 2 * t;
-      atomicAdd(&sh_dw[r0 * KO + col], acc[mt][nt][0]); atomicAdd(&sh_dw[r0 * KO + col + 1], acc[mt][nt][1]);
-      atomicAdd(&sh_dw[(r0 + 8) * KO + col], acc[mt][nt][2]); atomicAdd(&sh_dw[(r0 + 8) * KO + col + 1], acc[mt][nt][3]);
-    }
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int r, s, c, o;
+        if (G::decode(2 * mt + (q >> 1), g, nt * 8 + 2 * t + (q & 1), r, s, c, o) && c < a.c_src && o < a.k_out)
+          atomicAdd(&sh_dw[((o * KS + r) * KS + s) * a.c_src + c], acc[mt][nt][q]);
+      }
   {
-    // bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 fixed per thread (kWgThreads * 8 is a multiple of kv)
+    // bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 = (tid * 8) % kv (kWgThreads * 8 is a multiple of kv).
     // Lanes whose (lane * 8) % kv agree hold the same channels: butterfly over them, then one shared-memory atomic per (warp, channel) — 256 threads
     // adding 8 values each straight onto 4..16 addresses was 60 % of this kernel's instructions (ncu, round 2: retried shared-memory atomics).
-    const int kv = a.k_out;
     if ((kv == 4 || kv % 8 == 0)) {
       if (kv == 4) {
 #pragma unroll
@@ -643,10 +788,8 @@ __global__ void __launch_bounds__(kWgThreads) sc_wgrad_kernel(const WgradArgs a)
     }
   }
   __syncthreads();
-  const int total = a.k_out * KS * KS * a.c_src;
   for (int i = tid; i < total; i += kWgThreads) {
-    const int c = i % a.c_src, tap = (i / a.c_src) % (KS * KS), k = i / (a.c_src * KS * KS);
-    const float v = sh_dw[(tap * CI + c) * KO + k];
+    const float v = sh_dw[i];
     if (v != 0.f) atomicAdd(a.dw + i, v);
   }
   if (a.dbias && tid < a.k_out) atomicAdd(a.dbias + tid, sh_db[tid]);
@@ -730,14 +873,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_bwd_kernel(
 // ---- host side --------------------------------------------------------------------------------------------------------------------------------
 static int pick_ci(int c) { return c <= 4 ? 4 : (c == 16 ? 16 : 0); }
 
+static size_t wgrad_smem(const dcv_conv_shape* s) {
+  const int ci = pick_ci(s->c), no = pick_ci(s->k), kop = ci == 4 ? no : (no < 8 ? 8 : no);
+  return (size_t)(s->h + s->r - 1) * (s->w + s->s - 1) * ci * 2 + (size_t)s->h * s->w * kop * 2 + (size_t)s->k * s->r * s->s * s->c * 4;
+}
+
 static bool shape_ok(const dcv_conv_shape* s, int dtype) {
   if (!s || dtype != DCV_BF16) return false;
   if (s->stride_h != 1 || s->stride_w != 1 || s->dil_h != 1 || s->dil_w != 1 || s->r != s->s || (s->r != 3 && s->r != 5)) return false;
   if (s->pad_h != s->r / 2 || s->pad_w != s->r / 2 || s->p != s->h || s->q != s->w) return false;
-  if ((s->w != 16 && s->w != 32 && s->w != 64) || s->h > 64 || (s->h * s->w) % 16 != 0) return false;   // the kernels split pixel indices with shifts
+  if ((s->w != 16 && s->w != 32 && s->w != 64) || s->h > 64 || (s->h * s->w) % 32 != 0) return false;   // pixel indices split with shifts; 16 pixel pairs per m-tile
   const int ci = pick_ci(s->c), ki = pick_ci(s->k);
   if (!ci || !ki || s->k % 2 != 0 || s->c < 1) return false;
   if (s->r == 5 && (ci != 4 || ki != 4)) return false;   // 5x5 over 16 channels: 25 k-steps of resident weight fragments do not fit the register file
+  if (wgrad_smem(s) > 100 * 1024) return false;          // two weight-gradient CTAs per SM
   return true;
 }
 
@@ -764,7 +913,7 @@ static int check_norm(const dcv_sc_norm* nd, int n, int c, int hw, const char* w
   DCV_REQUIRE(nd->stats_nc && (!nd->use_bn || !nd->bn_training || nd->bn_sums), "%s: missing statistics buffers", what);
   DCV_REQUIRE(!nd->use_gn || (nd->gn_groups > 0 && c % nd->gn_groups == 0), "%s: num_channels=%d not divisible by num_groups=%d", what, c, nd->gn_groups);
   DCV_REQUIRE(!nd->use_bn || nd->bn_training || (nd->bn_running_mean && nd->bn_running_var), "%s: eval-mode BatchNorm needs running statistics", what);
-  DCV_REQUIRE(!backward || (nd->s_nc && nd->u_sums), "%s: missing backward sum buffers", what);
+  DCV_REQUIRE(!backward || (nd->u_sums && nd->coef_nc && nd->d_nc), "%s: missing backward buffers (u_sums, coef_nc, d_nc)", what);
   return 0;
 }
 
@@ -776,11 +925,13 @@ extern "C" {
 int dcv_sc_conv_supported(const dcv_conv_shape* shape, int dtype) { return dcv::sc::shape_ok(shape, dtype) ? 1 : 0; }
 
 size_t dcv_sc_norm_floats(int n, int c, int which) {
-  /* which: 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums */
+  /* which: 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums, 4 coef_nc, 5 d_nc */
   switch (which) {
     case 0: case 2: return (size_t)n * c * 2;
     case 1: return (size_t)dcv::sc::kShards * c * 2;
-    default: return (size_t)dcv::sc::kShards * c * 4;
+    case 3: return (size_t)dcv::sc::kShards * c * 4;
+    case 4: return (size_t)n * c * 8;
+    default: return (size_t)n * c * 4;
   }
 }
 
@@ -801,13 +952,13 @@ int dcv_sc_conv_fwd(const dcv_conv_shape* s, const void* x, const dcv_sc_norm* x
   FwdArgs a{};
   a.n = s->n; a.h = s->h; a.w = s->w; a.c_src = s->c; a.k_out = s->k; a.act = act; a.slope = slope; a.update_running = update_running;
   a.x = (const bf16*)x; a.wgt = (const bf16*)w; a.bias = bias; a.y = (bf16*)y; a.xn = norm_or_off(x_norm); a.yn = norm_or_off(y_norm);
-  const int ci = pick_ci(s->c), nt = s->k <= 8 ? 1 : 2;
+  const int ci = pick_ci(s->c), no = pick_ci(s->k);
   const size_t smem = (size_t)(s->h + s->r - 1) * (s->w + s->r - 1) * ci * 2;
-  if (s->r == 5) SC_DISPATCH(4, 1, 5, sc_fwd_kernel, a, smem);
-  else if (ci == 4 && nt == 1) SC_DISPATCH(4, 1, 3, sc_fwd_kernel, a, smem);
-  else if (ci == 4) SC_DISPATCH(4, 2, 3, sc_fwd_kernel, a, smem);
-  else if (nt == 1) SC_DISPATCH(16, 1, 3, sc_fwd_kernel, a, smem);
-  else SC_DISPATCH(16, 2, 3, sc_fwd_kernel, a, smem);
+  if (s->r == 5) SC_DISPATCH(4, 4, 5, sc_fwd_kernel, a, smem);
+  else if (ci == 4 && no == 4) SC_DISPATCH(4, 4, 3, sc_fwd_kernel, a, smem);
+  else if (ci == 4) SC_DISPATCH(4, 16, 3, sc_fwd_kernel, a, smem);
+  else if (no == 4) SC_DISPATCH(16, 4, 3, sc_fwd_kernel, a, smem);
+  else SC_DISPATCH(16, 16, 3, sc_fwd_kernel, a, smem);
   DCV_LAUNCH_CHECK("sc_fwd_kernel");
   return 0;
 }
@@ -823,13 +974,13 @@ int dcv_sc_conv_dgrad(const dcv_conv_shape* s, const void* dz, const void* y, co
   DgradArgs a{};
   a.n = s->n; a.h = s->h; a.w = s->w; a.c_in = s->c; a.k_out = s->k; a.act = act; a.slope = slope;
   a.dz = (const bf16*)dz; a.y = (const bf16*)y; a.wgt = (const bf16*)w; a.dx = (bf16*)dx; a.x_raw = (const bf16*)x_raw; a.yn = norm_or_off(y_norm); a.xn = norm_or_off(x_norm);
-  const int ki = pick_ci(s->k), nt = s->c <= 8 ? 1 : 2;
+  const int ki = pick_ci(s->k), no = pick_ci(s->c);
   const size_t smem = (size_t)(s->h + s->r - 1) * (s->w + s->r - 1) * ki * 2;
-  if (s->r == 5) SC_DISPATCH(4, 1, 5, sc_dgrad_kernel, a, smem);
-  else if (ki == 4 && nt == 1) SC_DISPATCH(4, 1, 3, sc_dgrad_kernel, a, smem);
-  else if (ki == 4) SC_DISPATCH(4, 2, 3, sc_dgrad_kernel, a, smem);
-  else if (nt == 1) SC_DISPATCH(16, 1, 3, sc_dgrad_kernel, a, smem);
-  else SC_DISPATCH(16, 2, 3, sc_dgrad_kernel, a, smem);
+  if (s->r == 5) SC_DISPATCH(4, 4, 5, sc_dgrad_kernel, a, smem);
+  else if (ki == 4 && no == 4) SC_DISPATCH(4, 4, 3, sc_dgrad_kernel, a, smem);
+  else if (ki == 4) SC_DISPATCH(4, 16, 3, sc_dgrad_kernel, a, smem);
+  else if (no == 4) SC_DISPATCH(16, 4, 3, sc_dgrad_kernel, a, smem);
+  else SC_DISPATCH(16, 16, 3, sc_dgrad_kernel, a, smem);
   DCV_LAUNCH_CHECK("sc_dgrad_kernel");
   return 0;
 }
@@ -845,9 +996,8 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm*
   a.n = s->n; a.h = s->h; a.w = s->w; a.c_src = s->c; a.k_out = s->k; a.act = act; a.slope = slope;
   a.x = (const bf16*)x; a.dz = (const bf16*)dz; a.y = (const bf16*)y; a.dw = dw; a.dbias = dbias; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b; a.d_gn_w = d_gn_w; a.d_gn_b = d_gn_b;
   a.xn = norm_or_off(x_norm); a.yn = norm_or_off(y_norm);
-  const int ci = pick_ci(s->c), nt = s->k <= 8 ? 1 : 2, ko = nt * 8, mt = (s->r * s->s * ci + 15) / 16;
-  const size_t ps = (size_t)(s->h + s->r - 1) * (s->w + s->r - 1), hw = (size_t)s->h * s->w;
-  const size_t smem = 2 * ci * ps * 2 + ko * hw * 2 + (size_t)mt * 16 * ko * 4;
+  const int ci = pick_ci(s->c), no = pick_ci(s->k);
+  const size_t smem = wgrad_smem(s);
   // persistent over images: fewer CTAs = fewer atomics on dw
   auto grid_of = [&](int n) { const int g = num_ctas(n); return g < 2 * kNumSMs ? g : 2 * kNumSMs; };
 #define SC_WGRAD(CI_, NT_, KS_)                                                         \
@@ -856,11 +1006,11 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm*
     if (set_smem(kern, smem)) return 1;                                                 \
     kern<<<grid_of(a.n), kWgThreads, smem, st>>>(a);                                      \
   } while (0)
-  if (s->r == 5) SC_WGRAD(4, 1, 5);
-  else if (ci == 4 && nt == 1) SC_WGRAD(4, 1, 3);
-  else if (ci == 4) SC_WGRAD(4, 2, 3);
-  else if (nt == 1) SC_WGRAD(16, 1, 3);
-  else SC_WGRAD(16, 2, 3);
+  if (s->r == 5) SC_WGRAD(4, 4, 5);
+  else if (ci == 4 && no == 4) SC_WGRAD(4, 4, 3);
+  else if (ci == 4) SC_WGRAD(4, 16, 3);
+  else if (no == 4) SC_WGRAD(16, 4, 3);
+  else SC_WGRAD(16, 16, 3);
 #undef SC_WGRAD
   DCV_LAUNCH_CHECK("sc_wgrad_kernel");
   return 0;

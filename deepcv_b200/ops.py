@@ -466,11 +466,13 @@ class _NormLink:
         self.stats = torch.empty(f(0), dtype=torch.float32, device=device)
         bn_training = bool(training or rm is None or rv is None)
         self.bn_sums = _zeroed_acc((f(1),), device, sctx) if (cfg.use_bn and bn_training) else None
-        self.s_nc = torch.empty(f(2), dtype=torch.float32, device=device) if need_backward else None
+        self.s_nc = None   # diagnostic output of the kernels (sum dz, sum dz*y per (image, channel)); nothing reads it
         self.u_sums = _zeroed_acc((f(3),), device, sctx) if need_backward else None
+        self.coef = torch.empty(f(4), dtype=torch.float32, device=device) if need_backward else None   # forward coefficients cached for the backward kernels
+        self.d_nc = torch.empty(f(5), dtype=torch.float32, device=device) if need_backward else None
         self.keep = (bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
         self.struct = ScNorm(1, n, c, hw, int(cfg.use_bn), int(bn_training), cfg.bn_eps, cfg.bn_momentum, _ptr(bn_w), _ptr(bn_b), _ptr(rm), _ptr(rv), _ptr(nbt),
-                             int(cfg.use_gn), cfg.gn_groups, cfg.gn_eps, _ptr(gn_w), _ptr(gn_b), _ptr(self.stats), _ptr(self.bn_sums), _ptr(self.s_nc), _ptr(self.u_sums))
+                             int(cfg.use_gn), cfg.gn_groups, cfg.gn_eps, _ptr(gn_w), _ptr(gn_b), _ptr(self.stats), _ptr(self.bn_sums), _ptr(self.s_nc), _ptr(self.u_sums), _ptr(self.coef), _ptr(self.d_nc))
         self.update_running = bool(cfg.use_bn and training and rm is not None and rv is not None)
         self.consumed = False
 

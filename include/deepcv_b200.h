@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DCV_ABI_VERSION 2
+#define DCV_ABI_VERSION 3
 
 enum dcv_dtype { DCV_F32 = 0, DCV_BF16 = 1 };
 enum dcv_act { DCV_ACT_NONE = 0, DCV_ACT_RELU = 1, DCV_ACT_LEAKY_RELU = 2, DCV_ACT_SIGMOID = 3 };
@@ -130,13 +130,16 @@ typedef struct dcv_sc_norm {
   const float* gn_weight; const float* gn_bias;
   float* stats_nc;                  /* [n][c][2]   sum y, sum y*y per (image, channel): written by the kernel that produces y */
   float* bn_sums;                   /* [16][c][2]  the same summed over the batch, in 16 shards (image %% 16): accumulated by that kernel; training-mode BatchNorm only */
-  float* s_nc;                      /* [n][c][2]   backward: sum dz, sum dz*y: written by the kernel that produces dz */
+  float* s_nc;                      /* [n][c][2]   backward: sum dz, sum dz*y: written by the kernel that produces dz (diagnostic; may be NULL) */
   float* u_sums;                    /* [16][c][4]  backward: BatchNorm adjoint sums and GroupNorm parameter gradients, sharded: accumulated by that kernel */
+  float* coef_nc;                   /* [n][c][8]   A, B, BatchNorm alpha / beta / mean / rstd, GroupNorm mean / rstd per (image, channel): written by the FIRST
+                                     *             forward consumer of y, loaded by the backward kernels; NULL when no backward will follow */
+  float* d_nc;                      /* [n][c][4]   backward: GroupNorm adjoint coefficients D1, D2, D3 per (image, channel): written by the kernel that produces dz */
 } dcv_sc_norm;
 /* 1 iff the shape is served: bf16, square 3x3 or 5x5 filter, stride 1, "same" padding, w in {16, 32, 64}, c in {1..4, 16}, k even in {2, 4, 16}
  * (5x5: c <= 4 and k <= 4). Everything else stays on dcv_conv2d_* + dcv_norm_*. */
 int dcv_sc_conv_supported(const dcv_conv_shape* shape, int dtype);
-/* floats of one buffer of a dcv_sc_norm: which = 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums */
+/* floats of one buffer of a dcv_sc_norm: which = 0 stats_nc, 1 bn_sums, 2 s_nc, 3 u_sums, 4 coef_nc, 5 d_nc */
 size_t dcv_sc_norm_floats(int n, int c, int which);
 /* y = act(conv(z, w) + bias) with z = x (x_norm NULL / disabled) or the normalised raw output x (x_norm enabled: applied on load; when `update_running`
  * != 0 this launch also performs the running-statistics update of x_norm's BatchNorm — exactly one consumer launch per step must). y_norm enabled:

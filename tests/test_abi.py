@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
     for name in _header_symbols():
         assert hasattr(cdll, name), f'{name} declared in include/deepcv_b200.h but not exported by {path.name}'
     cdll.dcv_abi_version.restype = ctypes.c_int
-    assert cdll.dcv_abi_version() == 2
+    from deepcv_b200._lib import ABI_VERSION
+    assert cdll.dcv_abi_version() == ABI_VERSION
     exported = subprocess.run(['nm', '-D', '--defined-only', str(path)], capture_output=True, text=True).stdout
     undeclared = {s for s in re.findall(r' T (dcv_[a-z0-9_]+)', exported)} - set(SYMBOLS)
     assert not undeclared, f'exported but not declared: {undeclared}'
