@@ -301,15 +301,15 @@ struct SrcDy {
 // every thread, [the caller's prologue + barrier], `store`); 16-byte loads + 2-byte tile stores when c_src < CI but the image is a whole number of
 // aligned vectors (the 3-channel network input); scalar otherwise.
 constexpr int kPF = 4;   // vectors of a thread in flight across the prologue
-template <int CI, int NTHR, typename Src> struct Stager {
-  typename Src::Raw raw[kPF];
+template <int CI, int NTHR, typename Src, int PF = kPF> struct Stager {
+  typename Src::Raw raw[PF];
   bool vec;
   __device__ __forceinline__ void fetch(const Src& src, size_t e_img, int HW, int c_src, int tid) {
     vec = (c_src == CI) && (e_img % 8) == 0;
     if (vec) {
       const int nvec = HW * CI / 8;
 #pragma unroll
-      for (int i = 0; i < kPF; ++i) { const int v = tid + i * NTHR; if (v < nvec) raw[i] = src.fetch(e_img + (size_t)v * 8); }
+      for (int i = 0; i < PF; ++i) { const int v = tid + i * NTHR; if (v < nvec) raw[i] = src.fetch(e_img + (size_t)v * 8); }
     }
   }
   __device__ __forceinline__ void put(bf16* tile, const Src& src, const typename Src::Raw& r, int v, int W, int wlog, int Wp, int PAD) const {
@@ -329,8 +329,8 @@ template <int CI, int NTHR, typename Src> struct Stager {
     if (vec) {
       const int nvec = HW * CI / 8;
 #pragma unroll
-      for (int i = 0; i < kPF; ++i) { const int v = tid + i * NTHR; if (v < nvec) put(tile, src, raw[i], v, W, wlog, Wp, PAD); }
-      for (int v = tid + kPF * NTHR; v < nvec; v += NTHR) put(tile, src, src.fetch(e_img + (size_t)v * 8), v, W, wlog, Wp, PAD);
+      for (int i = 0; i < PF; ++i) { const int v = tid + i * NTHR; if (v < nvec) put(tile, src, raw[i], v, W, wlog, Wp, PAD); }
+      for (int v = tid + PF * NTHR; v < nvec; v += NTHR) put(tile, src, src.fetch(e_img + (size_t)v * 8), v, W, wlog, Wp, PAD);
     } else if (src.cf == nullptr && c_src < CI && (HW * c_src) % 8 == 0 && ((e_img * 2) % 16) == 0 && sizeof(typename Src::Raw) == sizeof(uint4)) {
       const int nvec = HW * c_src / 8;
       for (int v = tid; v < nvec; v += NTHR) {
@@ -462,12 +462,28 @@ template <int CI, int NO, int KS> struct Core {
   __device__ static __forceinline__ int out_channel(int nt, int t) { const int n = nt * 8 + 2 * t; return G::PAIR ? n % NO : n; }
 };
 
-// Per-column partial sums of a thread -> sum over the 8 lanes that share `t` (same columns), then ONE shared-memory atomic per (column, value) and warp.
-__device__ __forceinline__ void reduce_cols_to_smem(float v, float* dst) {
+// Per-column partial sums of a thread -> sum over the 8 lanes that share `t` (same columns) -> the warp's own slot part[warp][column][which] (a plain
+// store: fp32 shared-memory atomics are compare-and-swap spin loops, ATOMS.CAST.SPIN — 30 % of the weight-gradient kernel before they were removed).
+// `fold_cols` then adds the warps' slots of the GEMM columns that belong to output channel o (pair mode: both parities).
+constexpr int kMaxN = 32;   // GEMM columns
+__device__ __forceinline__ void reduce_cols_to_slot(float v, float* slot) {
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 16);
-  if ((threadIdx.x & 31) < 4) atomicAdd(dst, v);
+  if ((threadIdx.x & 31) < 4) *slot = v;
+}
+template <typename G> __device__ __forceinline__ float fold_cols(const float (*part)[kMaxN][2], int o, int which) {
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    if (G::PAIR) {
+#pragma unroll
+      for (int n = 0; n < G::N; n += G::N / 2) v += part[w][n + o][which];
+    } else {
+      v += part[w][o][which];
+    }
+  }
+  return v;
 }
 
 // ---- forward ----------------------------------------------------------------------------------------------------------------------------------
@@ -484,8 +500,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArg
   typedef Core<CI, NO, KS> C;
   constexpr int NT = C::NT, PAD = KS / 2;
   __shared__ Coef cfx;
-  __shared__ float sh_stat[kMaxC][2];
-  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, t = lane & 3;
+  __shared__ float sh_part[kWarps][kMaxN][2];
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = lane & 3;
   SrcPlain src{a.x, a.xn.enabled ? &cfx : nullptr};
   Stager<CI, kThreads, SrcPlain> stager;
   stager.fetch(src, (size_t)blockIdx.x * H * W * a.c_src, H * W, a.c_src, tid);   // the first image's L2 round trip overlaps everything up to the barrier
@@ -505,7 +521,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArg
     const size_t e_img = (size_t)img * H * W * a.c_src;
     if (img != (int)blockIdx.x) { __syncthreads(); stager.fetch(src, e_img, H * W, a.c_src, tid); }   // the previous image's tile has been consumed
     if (tid < 32 && a.xn.enabled) norm_forward_coeffs(a.xn, img, cfx, a.update_running != 0 && img == 0);
-    if (tid >= 32 && tid < 32 + kMaxC * 2) (&sh_stat[0][0])[tid - 32] = 0.f;
     __syncthreads();   // coefficients ready, halo zeroed
     stager.store(tile, src, e_img, H, W, Wp, PAD, a.c_src, tid);
     __syncthreads();
@@ -525,13 +540,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArg
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int o = C::out_channel(nt, t) + e;   // < kMaxC
-          reduce_cols_to_smem(s1[nt][e], &sh_stat[o][0]);
-          reduce_cols_to_smem(s2[nt][e], &sh_stat[o][1]);
+          reduce_cols_to_slot(s1[nt][e], &sh_part[warp][nt * 8 + 2 * t + e][0]);
+          reduce_cols_to_slot(s2[nt][e], &sh_part[warp][nt * 8 + 2 * t + e][1]);
         }
       __syncthreads();
       if (tid < a.k_out) {   // this CTA owns the whole image: plain stores per (image, channel); the batch sums are sharded atomics
-        const float v1 = sh_stat[tid][0], v2 = sh_stat[tid][1];
+        const float v1 = fold_cols<typename C::G>(sh_part, tid, 0), v2 = fold_cols<typename C::G>(sh_part, tid, 1);
         a.yn.stats_nc[((size_t)img * a.k_out + tid) * 2] = v1;
         a.yn.stats_nc[((size_t)img * a.k_out + tid) * 2 + 1] = v2;
         if (a.yn.use_bn && a.yn.bn_training) {
@@ -560,8 +574,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
   typedef Core<KI, NO, KS> C;
   constexpr int NT = C::NT, PAD = KS / 2;
   __shared__ Coef cfy, cfx;
+  __shared__ float sh_part[kWarps][kMaxN][2];
   __shared__ float sh_s[kMaxC][2];
-  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, t = lane & 3;
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = lane & 3;
   SrcDy src{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
   Stager<KI, kThreads, SrcDy> stager;
   stager.fetch(src, (size_t)blockIdx.x * H * W * a.k_out, H * W, a.k_out, tid);
@@ -575,7 +590,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
     const size_t e_img = (size_t)img * H * W * a.k_out;
     if (img != (int)blockIdx.x) { __syncthreads(); stager.fetch(src, e_img, H * W, a.k_out, tid); }
     if (tid < 32 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy, false, nullptr, nullptr, nullptr, nullptr);
-    if (tid >= 32 && tid < 32 + kMaxC * 2) (&sh_s[0][0])[tid - 32] = 0.f;
     __syncthreads();
     stager.store(tile, src, e_img, H, W, Wp, PAD, a.k_out, tid);
     __syncthreads();
@@ -604,12 +618,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int o = C::out_channel(nt, t) + e;
-          reduce_cols_to_smem(s1[nt][e], &sh_s[o][0]);
-          reduce_cols_to_smem(s2[nt][e], &sh_s[o][1]);
+          reduce_cols_to_slot(s1[nt][e], &sh_part[warp][nt * 8 + 2 * t + e][0]);
+          reduce_cols_to_slot(s2[nt][e], &sh_part[warp][nt * 8 + 2 * t + e][1]);
         }
       __syncthreads();
-      if (tid < 32) norm_backward_image_sums(a.xn, img, cfx, &sh_s[0][0]);
+      if (tid < 32) {
+        if (lane < a.c_in) { sh_s[lane][0] = fold_cols<typename C::G>(sh_part, lane, 0); sh_s[lane][1] = fold_cols<typename C::G>(sh_part, lane, 1); }
+        __syncwarp();
+        norm_backward_image_sums(a.xn, img, cfx, &sh_s[0][0]);
+      }
     }
   }
 }
@@ -618,8 +635,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
 // dw[k][r][s][c] = sum over (image, pixel) of dy[pix][k] * z[pix + (r, s) - PAD][c] as the GEMM D[(tap, c)][k] += Zt[(tap, c)][pix] * dy[pix][k]: M = chunks
 // of 8 (tap, channel) rows (two per m-tile), K = pixels (pair mode: pixel pairs), N = output channels (pair mode: (parity, channel)). Both operands come
 // TRANSPOSED out of NHWC tiles with ldmatrix.trans: z is the same halo tile the forward kernel builds (normalised while staging), dy is assembled from dz
-// and y while staging (and summed into the bias gradient). Each warp keeps its share of D in registers across all the CTA's images; the CTA reduces
-// once in shared memory (in dw's own layout) and adds into dw with one atomic per element.
+// and y while staging (and summed into the bias gradient).
+// A CTA is TWO groups of 4 warps; each group works on its own image with its own tiles and its own named barrier (the kernel is a chain of dependent
+// round trips per image — fetch, coefficients, stage, MMA — so two images in flight per CTA halve the critical path without doubling the global atomics
+// the way twice as many CTAs would). Inside a group the warps split K; every warp keeps its share of D in registers across all its images. At the end
+// the 8 warps store their D tiles to shared memory (plain stores, the tiles' space is free by then) and each dw element adds up its <= 2 x 8 sources and
+// issues one global atomic.
 struct WgradArgs {
   int n, h, w, c_src, k_out, act; float slope;
   const bf16* x; const bf16* dz; const bf16* y;
@@ -627,22 +648,33 @@ struct WgradArgs {
   dcv_sc_norm xn, yn;
 };
 
+constexpr int kGrp = 128, kGrpWarps = kGrp / 32;   // threads / warps of one image group of the weight-gradient CTA
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(kGrp) : "memory"); }
+
+template <int CI, int NO, int KS> struct WgradLayout {
+  typedef Geo<CI, NO, KS> G;
+  static constexpr int MT = (G::NCH + 1) / 2, NT = G::NT, KOP = G::PAIR ? NO : (NO < 8 ? 8 : NO);   // KOP: channel stride of the dy tile
+  __host__ __device__ static size_t group_bytes(int h, int w) { return (size_t)(h + KS - 1) * (w + KS - 1) * CI * 2 + (size_t)h * w * KOP * 2; }
+  __host__ __device__ static size_t reduce_bytes() { return (size_t)kWgWarps * MT * 16 * (NT * 8) * 4; }
+  __host__ __device__ static size_t smem_bytes(int h, int w) { const size_t a = 2 * group_bytes(h, w), b = reduce_bytes(); return a > b ? a : b; }
+};
+
 template <int CI, int NO, int KS>
 __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef Geo<CI, NO, KS> G;
-  constexpr int PAD = KS / 2, MT = (G::NCH + 1) / 2, NT = G::NT, KOP = G::PAIR ? NO : (NO < 8 ? 8 : NO);   // KOP: channel stride of the dy tile
+  typedef WgradLayout<CI, NO, KS> L;
+  constexpr int PAD = KS / 2, MT = L::MT, NT = L::NT, KOP = L::KOP, ND = NT * 8;
+  constexpr int PF = MT * NT * 4 > 40 ? 2 : 4;   // vectors of a thread in flight across the prologue (z: PF, dy: 2 * PF registers x 4): fewer when the accumulators are many
   const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, wlog = 31 - __clz(W);
-  bf16* tile = reinterpret_cast<bf16*>(smem_raw);                       // [Hp][Wp][CI]
-  bf16* dyt = tile + (size_t)Hp * Wp * CI;                               // [HW][KOP]
-  float* sh_dw = reinterpret_cast<float*>(dyt + (size_t)HW * KOP);       // [k_out][KS][KS][c_src]
-  __shared__ Coef cfx, cfy;
-  __shared__ float sh_db[kMaxC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int total = a.k_out * KS * KS * a.c_src;
-  for (int i = tid; i < Hp * Wp * CI / 8; i += kWgThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < HW * KOP / 8; i += kWgThreads) reinterpret_cast<uint4*>(dyt)[i] = make_uint4(0u, 0u, 0u, 0u);   // padding channels stay zero
-  for (int i = tid; i < total; i += kWgThreads) sh_dw[i] = 0.f;
+  const int group = warp / kGrpWarps, gtid = tid - group * kGrp, gwarp = warp - group * kGrpWarps;
+  bf16* tile = reinterpret_cast<bf16*>(smem_raw + (size_t)group * L::group_bytes(H, W));   // [Hp][Wp][CI]
+  bf16* dyt = tile + (size_t)Hp * Wp * CI;                                                  // [HW][KOP]
+  __shared__ Coef cfx[2], cfy[2];
+  __shared__ float sh_db[kMaxC];
+  for (int i = gtid; i < Hp * Wp * CI / 8; i += kGrp) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = gtid; i < HW * KOP / 8; i += kGrp) reinterpret_cast<uint4*>(dyt)[i] = make_uint4(0u, 0u, 0u, 0u);   // padding channels stay zero
   if (tid < kMaxC) sh_db[tid] = 0.f;
   // per-lane ldmatrix geometry. A (x4.trans): matrix mi = lane / 8: chunk (mi & 1) of the m-tile, k half (mi >> 1); B: see below.
   const int mi = lane >> 3, li = lane & 7;
@@ -658,28 +690,28 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs
   float db[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) db[i] = 0.f;
-  SrcPlain sx{a.x, a.xn.enabled ? &cfx : nullptr};
-  SrcDy sd{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
-  Stager<CI, kWgThreads, SrcPlain> stx;
+  SrcPlain sx{a.x, a.xn.enabled ? &cfx[group] : nullptr};
+  SrcDy sd{a.dz, a.y, a.yn.enabled ? &cfy[group] : nullptr, a.act, a.slope};
+  Stager<CI, kGrp, SrcPlain, PF> stx;
   const int kv = a.k_out;   // channels of dy
   const int nks = G::PAIR ? HW / 32 : HW / 16;
 
-  for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
+  for (int img = blockIdx.x * 2 + group; img < a.n; img += gridDim.x * 2) {
     const size_t e_img = (size_t)img * HW * a.c_src, k_img = (size_t)img * HW * kv;
-    __syncthreads();   // previous image consumed / initial zeroing done
-    stx.fetch(sx, e_img, HW, a.c_src, tid);
+    group_sync(group);   // the group's previous image consumed / initial zeroing done
+    stx.fetch(sx, e_img, HW, a.c_src, gtid);
     const bool dvec = (kv == 4 || kv % 8 == 0) && (k_img % 8) == 0;
     const int ndv = HW * kv / 8;
-    SrcDy::Raw draw[2];
+    SrcDy::Raw draw[PF];
     if (dvec) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { const int v = tid + i * kWgThreads; if (v < ndv) draw[i] = sd.fetch(k_img + (size_t)v * 8); }
+      for (int i = 0; i < PF; ++i) { const int v = gtid + i * kGrp; if (v < ndv) draw[i] = sd.fetch(k_img + (size_t)v * 8); }
     }
-    if (warp == 0 && a.xn.enabled) load_coeffs(a.xn, img, cfx);
-    if (warp == 1 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy, img == 0, a.d_bn_w, a.d_bn_b, a.d_gn_w, a.d_gn_b);
-    __syncthreads();
+    if (gwarp == 0 && a.xn.enabled) load_coeffs(a.xn, img, cfx[group]);
+    if (gwarp == 1 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy[group], img == 0, a.d_bn_w, a.d_bn_b, a.d_gn_w, a.d_gn_b);
+    group_sync(group);
     // ---- stage z (halo tile) and dy
-    stx.store(tile, sx, e_img, H, W, Wp, PAD, a.c_src, tid);
+    stx.store(tile, sx, e_img, H, W, Wp, PAD, a.c_src, gtid);
     auto put_dy = [&](const SrcDy::Raw& r, int v) {
       const int e0 = v * 8, pix = e0 / kv, c0 = e0 % kv;
       float f[8];
@@ -698,52 +730,36 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs
     };
     if (dvec) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { const int v = tid + i * kWgThreads; if (v < ndv) put_dy(draw[i], v); }
-      for (int v = tid + 2 * kWgThreads; v < ndv; v += kWgThreads) put_dy(sd.fetch(k_img + (size_t)v * 8), v);
+      for (int i = 0; i < PF; ++i) { const int v = gtid + i * kGrp; if (v < ndv) put_dy(draw[i], v); }
+      for (int v = gtid + PF * kGrp; v < ndv; v += kGrp) put_dy(sd.fetch(k_img + (size_t)v * 8), v);
     } else {
-      for (int pix = tid; pix < HW; pix += kWgThreads)
+      for (int pix = gtid; pix < HW; pix += kGrp)
         for (int c = 0; c < kv; ++c) {
           const float v = round_bf(sd.load1(k_img + (size_t)pix * kv + c, c));
           dyt[(size_t)pix * KOP + c] = __float2bfloat16_rn(v);
           atomicAdd(&sh_db[c], v);
         }
     }
-    __syncthreads();
-    // ---- MMA over the image's k-steps (16 pixel pairs / pixels each)
-    for (int ks = warp; ks < nks; ks += kWgWarps) {
+    group_sync(group);
+    // ---- MMA over the image's k-steps (16 pixel pairs / pixels each), split over the group's warps
+    for (int ks = gwarp; ks < nks; ks += kGrpWarps) {
       // A rows: the k index (pixel pair / pixel) ks * 16 + (mi >> 1) * 8 + li
       const int ka = ks * 16 + (mi >> 1) * 8 + li;
       int ya, xa;
       if (G::PAIR) { ya = ka >> (wlog - 1); xa = (ka & ((W >> 1) - 1)) * 2; } else { ya = ka >> wlog; xa = ka & (W - 1); }
       const uint32_t abase = tile_u + (uint32_t)((ya * Wp + xa) * G::PIXB);
-      // B fragments of this k-step
+      // B fragments of this k-step: rows = k index ks * 16 + (mi & 1) * 8 + li
+      const int kb = ks * 16 + (mi & 1) * 8 + li;
       uint32_t b[NT][2];
-      if (G::PAIR) {
-        if (NT == 1) {           // NO = 4: a row = pixel pair = (parity, 4 channels); x2: matrix = k half
-          const int kb = ks * 16 + (mi & 1) * 8 + li;
-          ldsm_x2_t(dyt_u + (uint32_t)(kb * 16), b[0]);
-        } else {                 // NO = 16: n-tile nt = (parity nt >> 1, channel half nt & 1); two x4: matrices (nt, k half)
-          const int kb = ks * 16 + (mi & 1) * 8 + li;
+      if (NT == 1) {             // pair mode, NO = 4: a row = pixel pair = (parity, 4 channels); plain mode: 8 (padded) channels of a pixel; x2: matrix = k half
+        ldsm_x2_t(dyt_u + (uint32_t)(G::PAIR ? kb * 16 : kb * KOP * 2), b[0]);
+      } else {                   // x4: matrices (n-tile 2h + (mi >> 1), k half mi & 1); pair mode: n-tile nt = (parity nt >> 1, channel half nt & 1)
 #pragma unroll
-          for (int h = 0; h < NT / 2; ++h) {
-            const int nt = 2 * h + (mi >> 1);
-            uint32_t r4[4];
-            ldsm_x4_t(dyt_u + (uint32_t)(((2 * kb + (nt >> 1)) * NO + (nt & 1) * 8) * 2), r4);
-            b[2 * h][0] = r4[0]; b[2 * h][1] = r4[1]; b[2 * h + 1][0] = r4[2]; b[2 * h + 1][1] = r4[3];
-          }
-        }
-      } else {
-        const int kb = ks * 16 + (mi & 1) * 8 + li;
-        if (NT == 1) {
-          ldsm_x2_t(dyt_u + (uint32_t)(kb * KOP * 2), b[0]);
-        } else {
-#pragma unroll
-          for (int h = 0; h < NT / 2; ++h) {
-            const int nt = 2 * h + (mi >> 1);
-            uint32_t r4[4];
-            ldsm_x4_t(dyt_u + (uint32_t)((kb * KOP + nt * 8) * 2), r4);
-            b[2 * h][0] = r4[0]; b[2 * h][1] = r4[1]; b[2 * h + 1][0] = r4[2]; b[2 * h + 1][1] = r4[3];
-          }
+        for (int h = 0; h < NT / 2; ++h) {
+          const int nt = 2 * h + (mi >> 1);
+          uint32_t r4[4];
+          ldsm_x4_t(dyt_u + (uint32_t)(G::PAIR ? ((2 * kb + (nt >> 1)) * NO + (nt & 1) * 8) * 2 : (kb * KOP + nt * 8) * 2), r4);
+          b[2 * h][0] = r4[0]; b[2 * h][1] = r4[1]; b[2 * h + 1][0] = r4[2]; b[2 * h + 1][1] = r4[3];
         }
       }
 #pragma unroll
@@ -755,41 +771,49 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs
       }
     }
   }
-  // ---- CTA reduction in dw's layout, then one atomic per weight-gradient element
-  __syncthreads();
+  // ---- bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 = (gtid * 8) % kv (kGrp * 8 is a multiple of kv).
+  // Lanes whose (lane * 8) % kv agree hold the same channels: butterfly over them, then one shared-memory atomic per (warp, channel).
+  if ((kv == 4 || kv % 8 == 0)) {
+    if (kv == 4) {
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+      for (int i = 0; i < 4; ++i) { db[i] += db[i + 4]; db[i + 4] = 0.f; }
+    }
+    const int stride = kv >= 8 ? kv / 8 : 1, nval = kv == 4 ? 4 : 8;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int r, s, c, o;
-        if (G::decode(2 * mt + (q >> 1), g, nt * 8 + 2 * t + (q & 1), r, s, c, o) && c < a.c_src && o < a.k_out)
-          atomicAdd(&sh_dw[((o * KS + r) * KS + s) * a.c_src + c], acc[mt][nt][q]);
-      }
-  {
-    // bias gradient: vector slot i of a thread is always the same channel: (c0 + i) & (kv - 1) with c0 = (tid * 8) % kv (kWgThreads * 8 is a multiple of kv).
-    // Lanes whose (lane * 8) % kv agree hold the same channels: butterfly over them, then one shared-memory atomic per (warp, channel) — 256 threads
-    // adding 8 values each straight onto 4..16 addresses was 60 % of this kernel's instructions (ncu, round 2: retried shared-memory atomics).
-    if ((kv == 4 || kv % 8 == 0)) {
-      if (kv == 4) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { db[i] += db[i + 4]; db[i + 4] = 0.f; }
-      }
-      const int stride = kv >= 8 ? kv / 8 : 1, nval = kv == 4 ? 4 : 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i < nval) {
-          float v = db[i];
-          for (int o = 16; o >= stride; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane < stride) atomicAdd(&sh_db[(lane * 8 + i) & (kv - 1)], v);
-        }
+    for (int i = 0; i < 8; ++i) {
+      if (i < nval) {
+        float v = db[i];
+        for (int o = 16; o >= stride; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < stride) atomicAdd(&sh_db[(lane * 8 + i) & (kv - 1)], v);
       }
     }
   }
+  // ---- the 8 warps' D tiles -> shared memory (each element has one owner: plain stores), then one thread per dw element adds its sources up
+  __syncthreads();   // every warp is done with the image tiles: their space is reused
+  float* red = reinterpret_cast<float*>(smem_raw);   // [kWgWarps][MT * 16][ND]
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float* d0 = red + ((size_t)warp * MT * 16 + mt * 16 + g) * ND + nt * 8 + 2 * t;
+      *reinterpret_cast<float2*>(d0) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(d0 + 8 * ND) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
   __syncthreads();
+  const int total = a.k_out * KS * KS * a.c_src;
   for (int i = tid; i < total; i += kWgThreads) {
-    const float v = sh_dw[i];
+    const int c = i % a.c_src, tap = (i / a.c_src) % (KS * KS), o = i / (a.c_src * KS * KS), r = tap / KS, s_ = tap % KS;
+    float v = 0.f;
+    if (G::PAIR) {   // dw[s] = D[(r, s' = s, c)][(par 0, o)] + D[(r, s' = s + 1, c)][(par 1, o)]
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int sp = s_ + par, m = (r * G::CPR + (sp >> 1)) * 8 + (sp & 1) * 4 + c, n = par * NO + o;
+        for (int w = 0; w < kWgWarps; ++w) v += red[((size_t)w * MT * 16 + m) * ND + n];
+      }
+    } else {
+      const int m = tap * 16 + c;   // chunk 2 * tap + (c >> 3), element c & 7
+      for (int w = 0; w < kWgWarps; ++w) v += red[((size_t)w * MT * 16 + m) * ND + o];
+    }
     if (v != 0.f) atomicAdd(a.dw + i, v);
   }
   if (a.dbias && tid < a.k_out) atomicAdd(a.dbias + tid, sh_db[tid]);
@@ -826,6 +850,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_fwd_kernel(
 __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_bwd_kernel(const PoolArgs a) {
   __shared__ Coef cf;
   __shared__ float sh_s[kMaxC][2];
+  __shared__ float sh_pw[kWarps][kMaxC][2];   // per-warp slots (plain stores instead of shared-memory atomics)
+  bool slots = false;
   const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
   const float inv = 1.f / (float)(a.pool * a.pool);
   const bool fixed_cp = (kThreads % c2) == 0;   // a thread then always works on the same channel pair: sums stay in registers
@@ -860,13 +886,22 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_bwd_kernel(
           t1a += __shfl_xor_sync(0xffffffffu, t1a, o); t1b += __shfl_xor_sync(0xffffffffu, t1b, o);
           t2a += __shfl_xor_sync(0xffffffffu, t2a, o); t2b += __shfl_xor_sync(0xffffffffu, t2b, o);
         }
-        if ((tid & 31) < c2) { atomicAdd(&sh_s[2 * cp][0], t1a); atomicAdd(&sh_s[2 * cp + 1][0], t1b); atomicAdd(&sh_s[2 * cp][1], t2a); atomicAdd(&sh_s[2 * cp + 1][1], t2b); }
+        if ((tid & 31) < c2) { float (*pw)[2] = sh_pw[tid >> 5]; pw[2 * cp][0] = t1a; pw[2 * cp + 1][0] = t1b; pw[2 * cp][1] = t2a; pw[2 * cp + 1][1] = t2b; }
+        slots = true;
       } else {
         atomicAdd(&sh_s[2 * cp][0], t1a); atomicAdd(&sh_s[2 * cp + 1][0], t1b); atomicAdd(&sh_s[2 * cp][1], t2a); atomicAdd(&sh_s[2 * cp + 1][1], t2b);
       }
     }
     __syncthreads();
-    if (tid < 32) norm_backward_image_sums(a.nd, img, cf, &sh_s[0][0]);
+    if (tid < 32) {
+      if (slots && tid < a.c) {
+        float v0 = 0.f, v1 = 0.f;
+        for (int w = 0; w < kWarps; ++w) { v0 += sh_pw[w][tid][0]; v1 += sh_pw[w][tid][1]; }
+        sh_s[tid][0] = v0; sh_s[tid][1] = v1;
+      }
+      __syncwarp();
+      norm_backward_image_sums(a.nd, img, cf, &sh_s[0][0]);
+    }
   }
 }
 
@@ -874,8 +909,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_bwd_kernel(
 static int pick_ci(int c) { return c <= 4 ? 4 : (c == 16 ? 16 : 0); }
 
 static size_t wgrad_smem(const dcv_conv_shape* s) {
-  const int ci = pick_ci(s->c), no = pick_ci(s->k), kop = ci == 4 ? no : (no < 8 ? 8 : no);
-  return (size_t)(s->h + s->r - 1) * (s->w + s->s - 1) * ci * 2 + (size_t)s->h * s->w * kop * 2 + (size_t)s->k * s->r * s->s * s->c * 4;
+  const int ci = pick_ci(s->c), no = pick_ci(s->k);
+  if (s->r == 5) return WgradLayout<4, 4, 5>::smem_bytes(s->h, s->w);
+  if (ci == 4 && no == 4) return WgradLayout<4, 4, 3>::smem_bytes(s->h, s->w);
+  if (ci == 4) return WgradLayout<4, 16, 3>::smem_bytes(s->h, s->w);
+  if (no == 4) return WgradLayout<16, 4, 3>::smem_bytes(s->h, s->w);
+  return WgradLayout<16, 16, 3>::smem_bytes(s->h, s->w);
 }
 
 static bool shape_ok(const dcv_conv_shape* s, int dtype) {
@@ -886,7 +925,7 @@ static bool shape_ok(const dcv_conv_shape* s, int dtype) {
   const int ci = pick_ci(s->c), ki = pick_ci(s->k);
   if (!ci || !ki || s->k % 2 != 0 || s->c < 1) return false;
   if (s->r == 5 && (ci != 4 || ki != 4)) return false;   // 5x5 over 16 channels: 25 k-steps of resident weight fragments do not fit the register file
-  if (wgrad_smem(s) > 100 * 1024) return false;          // two weight-gradient CTAs per SM
+  if (wgrad_smem(s) > 110 * 1024) return false;          // two weight-gradient CTAs per SM up to ~105 KB, one above
   return true;
 }
 
@@ -897,7 +936,7 @@ static int num_ctas(int n) {
 }
 
 template <typename K> static int set_smem(K kern, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 32 * 1024) {   // dynamic + static (coefficient structs, slots: up to ~8 KB) must stay under the 48 KB default
     DCV_REQUIRE(bytes <= 200 * 1024, "sc: %zu bytes of shared memory needed", bytes);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   }
@@ -998,8 +1037,8 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm*
   a.xn = norm_or_off(x_norm); a.yn = norm_or_off(y_norm);
   const int ci = pick_ci(s->c), no = pick_ci(s->k);
   const size_t smem = wgrad_smem(s);
-  // persistent over images: fewer CTAs = fewer atomics on dw
-  auto grid_of = [&](int n) { const int g = num_ctas(n); return g < 2 * kNumSMs ? g : 2 * kNumSMs; };
+  // persistent over images, two at a time: fewer CTAs = fewer atomics on dw
+  auto grid_of = [&](int n) { const int g = num_ctas((n + 1) / 2); return g < 2 * kNumSMs ? g : 2 * kNumSMs; };   // two images in flight per CTA
 #define SC_WGRAD(CI_, NT_, KS_)                                                         \
   do {                                                                                  \
     auto kern = sc_wgrad_kernel<CI_, NT_, KS_>;                                         \
