@@ -180,8 +180,10 @@ class FusedLayer(torch.nn.Sequential):
         conv2d:  conv + bias + activation + per-(n,c) statistics  ->  finalize  ->  one affine per (n,c) for BatchNorm∘GroupNorm
         linear:  GEMM + bias + activation
 
-    Only the post-activation order with ReLU / LeakyReLU / Sigmoid / no activation and BatchNorm / GroupNorm / InstanceNorm is
-    built; anything else raises `NotImplementedError` at construction (never a silent PyTorch fallback). """
+    Both block orders of the reference (nn.py:553) are built — post-activation `(?Dropout) - op - act - (?norms)` (convolution epilogue fusion) and
+    pre-activation `(?Dropout) - (?norms) - act - op` (`ops.pre_norm_act` in front of a plain convolution) — with ReLU / LeakyReLU / Sigmoid / no
+    activation, BatchNorm / GroupNorm / InstanceNorm and element-wise Dropout (Philox mask, `ops.dropout`); anything else raises
+    `NotImplementedError` at construction (never a silent PyTorch fallback). """
 
     def __init__(self, *modules: torch.nn.Module, preactivation: bool = False):
         super().__init__(*modules)
@@ -206,10 +208,10 @@ class FusedLayer(torch.nn.Sequential):
             # Keep the weight parameter physically [K][R][S][C] (logically still OIHW: state_dict interchange is unaffected)
             self._op.weight.data = self._op.weight.data.contiguous(memory_format=torch.channels_last)
         drop = [m for m in mods if isinstance(m, torch.nn.modules.dropout._DropoutNd)]
-        if any(m.p != 0. for m in drop):
-            raise NotImplementedError('deepcv_b200: dropout_prob != 0 is not built for sm_100a yet (the benchmark specs use 0; parity needs a shared mask)')
-        if self.preactivation:
-            raise NotImplementedError('deepcv_b200: `preactivation: true` blocks are not built for sm_100a yet')
+        if len(drop) > 1 or any(not isinstance(m, torch.nn.Dropout) for m in drop):
+            raise NotImplementedError(f'deepcv_b200: only one element-wise `torch.nn.Dropout` per layer is built (got {drop})')
+        ref('_drop', drop[0] if drop else None)     # always the first op of the block (reference nn.py:553), on the block's input
+        self._drop_state: Optional[ops.DropoutState] = None
         norm_types = (torch.nn.modules.batchnorm._BatchNorm, torch.nn.GroupNorm, torch.nn.modules.instancenorm._InstanceNorm, torch.nn.LayerNorm, torch.nn.LocalResponseNorm)
         acts = [m for m in mods if m is not self._op and m not in drop and not isinstance(m, norm_types)]
         if len(acts) > 1:
@@ -222,6 +224,8 @@ class FusedLayer(torch.nn.Sequential):
         ref('_gn', gn[0] if gn else None)
         if isinstance(self._gn, torch.nn.modules.instancenorm._InstanceNorm) and self._gn.track_running_stats:
             raise NotImplementedError('deepcv_b200: InstanceNorm with running statistics is not built')
+        if self.preactivation and self._bn is not None and self._bn.num_features != (self._op.in_channels if isinstance(self._op, torch.nn.Conv2d) else self._op.in_features):
+            raise ValueError(f'Error: pre-activation BatchNorm normalises the block input ({getattr(self._op, "in_channels", None)} channels), got num_features={self._bn.num_features}')
         if isinstance(self._op, torch.nn.Linear) and (self._bn is not None or self._gn is not None):
             raise NotImplementedError('deepcv_b200: normalisation after a fully connected layer is not built (the reference specs set `batch_norm: null` there)')
 
@@ -247,33 +251,52 @@ class FusedLayer(torch.nn.Sequential):
 
     def _few_channel_path(self, x) -> bool:
         op = self._op
-        return (isinstance(op, torch.nn.Conv2d) and self.algo == ALGO_AUTO and x.device.type == 'cuda' and len(x.shape) == 4
+        return (isinstance(op, torch.nn.Conv2d) and not self.preactivation and self.algo == ALGO_AUTO and x.device.type == 'cuda' and len(x.shape) == 4
                 and ops.sc_conv_supported(tuple(x.shape), op.weight, op.stride, op.padding, op.dilation, x.dtype))
+
+    def _norm_kwargs(self) -> dict:
+        bn, gn = self._bn, self._gn
+        return dict(bn_weight=bn.weight if bn is not None else None, bn_bias=bn.bias if bn is not None else None,
+                    running_mean=bn.running_mean if bn is not None else None, running_var=bn.running_var if bn is not None else None,
+                    num_batches_tracked=bn.num_batches_tracked if bn is not None else None,
+                    gn_weight=gn.weight if gn is not None else None, gn_bias=gn.bias if gn is not None else None)
 
     def forward(self, x, defer_affine: bool = False):
         if not isinstance(x, ops.PendingAffine) and x.device.type == 'meta':
             return self._meta_forward(x)
-        op, bn, gn = self._op, self._bn, self._gn
+        op, bn, gn, drop = self._op, self._bn, self._gn, self._drop
+        if drop is not None and drop.training and drop.p != 0.:   # reference nn.py:553: Dropout is the first op of both block orders
+            x = ops.materialize(x)
+            if self._drop_state is None or self._drop_state.counter.device != x.device:
+                self._drop_state = ops.DropoutState(x.device)
+            x = ops.dropout(x, float(drop.p), self._drop_state)
+        training = bn.training if bn is not None else self.training
+        if self.preactivation:   # `(?Dropout) - (?norms) - Act - Layer`: the normalisation and the activation act on the block input
+            x = ops.materialize(x)
+            if isinstance(op, torch.nn.Linear):
+                if x.dim() != 2:
+                    x = ops.flatten_nchw(x) if x.dim() == 4 else x.reshape(x.shape[0], -1)
+                x = ops.activation(x.contiguous(), self._act, self._slope)
+                return ops.linear_act(x, op.weight, op.bias, ACT_NONE, 0., grad_out=self._grad_out, step_ctx=self._step_ctx)
+            has_norm = bn is not None or gn is not None
+            if has_norm:
+                x = ops.pre_norm_act(x, self._norm_config(), training=training, act=self._act, slope=self._slope, grad_out=self._grad_out, step_ctx=self._step_ctx,
+                                     **self._norm_kwargs())
+            else:
+                x = ops.activation(ops.as_nhwc(x), self._act, self._slope)
+            return ops.conv_block(x, op.weight, op.bias, op.stride, op.padding, op.dilation, ACT_NONE, 0., norm=None, training=training, algo=self.algo,
+                                  grad_out=self._grad_out, step_ctx=self._step_ctx, notify=not has_norm)
         few = self._few_channel_path(x)
         if isinstance(x, ops.PendingAffine) and not few:
             x = ops.materialize(x)
         if isinstance(op, torch.nn.Linear):
             return ops.linear_act(x, op.weight, op.bias, self._act, self._slope, grad_out=self._grad_out, step_ctx=self._step_ctx)
-        training = bn.training if bn is not None else self.training
         if few:
             out = ops.sc_conv_block(x, op.weight, op.bias, op.padding, self._act, self._slope, norm=self._norm_config(), training=training,
-                                    bn_weight=bn.weight if bn is not None else None, bn_bias=bn.bias if bn is not None else None,
-                                    running_mean=bn.running_mean if bn is not None else None, running_var=bn.running_var if bn is not None else None,
-                                    num_batches_tracked=bn.num_batches_tracked if bn is not None else None,
-                                    gn_weight=gn.weight if gn is not None else None, gn_bias=gn.bias if gn is not None else None,
-                                    grad_out=self._grad_out, step_ctx=self._step_ctx)
+                                    grad_out=self._grad_out, step_ctx=self._step_ctx, **self._norm_kwargs())
             return out if defer_affine else ops.materialize(out)
         return ops.conv_block(x, op.weight, op.bias, op.stride, op.padding, op.dilation, self._act, self._slope, norm=self._norm_config(), training=training,
-                              bn_weight=bn.weight if bn is not None else None, bn_bias=bn.bias if bn is not None else None,
-                              running_mean=bn.running_mean if bn is not None else None, running_var=bn.running_var if bn is not None else None,
-                              num_batches_tracked=bn.num_batches_tracked if bn is not None else None,
-                              gn_weight=gn.weight if gn is not None else None, gn_bias=gn.bias if gn is not None else None,
-                              algo=self.algo, grad_out=self._grad_out, step_ctx=self._step_ctx)
+                              algo=self.algo, grad_out=self._grad_out, step_ctx=self._step_ctx, **self._norm_kwargs())
 
 
 def layer(layer_op: torch.nn.Module, act_fn: Optional[Type[torch.nn.Module]], dropout_prob: float = None, preactivation: bool = False,

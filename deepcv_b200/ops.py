@@ -20,7 +20,7 @@ from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, A
 
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext', 'PendingAffine', 'sc_conv_block',
-           'sc_conv_supported', 'sc_affine_pool', 'materialize']
+           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
 _DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
@@ -291,8 +291,9 @@ def _norm_params(cfg: NormConfig, n: int, c: int, hw: int, training: bool, bn_w,
 
 class _ConvBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx):
+    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx, notify=True):
         _require_cuda(x, weight)
+        ctx.notify = notify
         shape = _conv_shape(x, weight, stride, padding, dilation)
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st = x.device, _stream()
@@ -420,9 +421,10 @@ class _ConvBlock(torch.autograd.Function):
 
         def ret(name, g):  # gradients written straight into a caller-provided bucket slice are not handed to autograd again
             return None if (g is None or name in targets) else g
-        _backward_done(grad_out, targets)
+        if ctx.notify:
+            _backward_done(grad_out, targets)
         return (dx, ret('weight', dw), ret('bias', dbias) if has_bias else None, ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b),
-                None, None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def _backward_done(grad_out: Optional[dict], targets: dict) -> None:
@@ -441,14 +443,165 @@ def _backward_done(grad_out: Optional[dict], targets: dict) -> None:
 def conv_block(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: Sequence[int], padding: Sequence[int], dilation: Sequence[int],
                act: int = ACT_NONE, slope: float = 0., norm: Optional[NormConfig] = None, training: bool = True,
                bn_weight=None, bn_bias=None, running_mean=None, running_var=None, num_batches_tracked=None, gn_weight=None, gn_bias=None,
-               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None) -> torch.Tensor:
+               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None, notify: bool = True) -> torch.Tensor:
     """ act(conv2d(x, weight) + bias) followed by the configured BatchNorm / GroupNorm, as one autograd node.
     `grad_out` optionally maps 'weight' / 'bias' / 'bn_w' / 'bn_b' / 'gn_w' / 'gn_b' to preallocated fp32 tensors (slices of a
-    flat gradient bucket) that backward fills in place instead of returning new tensors. """
+    flat gradient bucket) that backward fills in place instead of returning new tensors. `notify=False`: another node of the same layer (the
+    normalisation of a pre-activation block, whose backward runs later) closes the layer's backward (`_backward_done`). """
     x = as_nhwc(x)
     norm = norm if norm is not None else NormConfig()
     return _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
-                            tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx)
+                            tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx, bool(notify))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Dropout, stand-alone activation and the pre-activation block order `[Dropout] -> norms -> act -> op` (reference: meta/nn.py:535-541, 553)
+
+class DropoutState:
+    """ What one `torch.nn.Dropout` of a fused layer needs on the device: a 64-bit seed (drawn from torch's default generator at first use, so
+    `torch.manual_seed` controls it) and the call counter (device int32, advanced by a kernel: graph-replay safe). `record`: tests set it to a list
+    to receive every mask (uint8, same strides as the input) — the masks the CPU oracle is then given. """
+
+    def __init__(self, device, seed: Optional[int] = None):
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+        self.counter = torch.zeros((), dtype=torch.int32, device=device)
+        self.record: Optional[list] = None
+
+
+def _aligned_dense(t: torch.Tensor) -> torch.Tensor:
+    t = _dense_like(t)
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p: float, state: DropoutState):
+        _require_cuda(x)
+        x = _aligned_dense(x)
+        y = torch.empty_like(x)
+        saved_call = torch.empty((), dtype=torch.int32, device=x.device)
+        mask = torch.empty_like(x, dtype=torch.uint8) if state.record is not None else None
+        st = _stream()
+        check(lib.dcv_dropout(_ptr(x), _ptr(y), _ptr(mask), x.numel(), p, state.seed, _ptr(state.counter), _ptr(saved_call), _dt(x), st), 'dropout')
+        check(lib.dcv_counter_add(_ptr(state.counter), 1, st), 'counter_add(dropout call)')
+        if mask is not None:
+            state.record.append(mask)
+        ctx.save_for_backward(saved_call)
+        ctx.p, ctx.seed = p, state.seed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved_call, = ctx.saved_tensors
+        dy = _aligned_dense(dy.detach())
+        dx = torch.empty_like(dy)
+        check(lib.dcv_dropout(_ptr(dy), _ptr(dx), None, dy.numel(), ctx.p, ctx.seed, _ptr(saved_call), None, _dt(dy), _stream()), 'dropout(backward)')
+        return dx, None, None
+
+
+def dropout(x: torch.Tensor, p: float, state: DropoutState) -> torch.Tensor:
+    """ `torch.nn.Dropout(p)` in training mode: x * keep / (1 - p), keep ~ Bernoulli(1 - p) per element (Philox mask regenerated in backward). """
+    if not 0. <= p < 1.:
+        raise ValueError(f'dropout probability has to be in [0, 1), but got {p}')
+    return x if p == 0. else _Dropout.apply(x, float(p), state)
+
+
+class _Activation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act: int, slope: float):
+        _require_cuda(x)
+        x = _aligned_dense(x)
+        y = torch.empty_like(x)
+        check(lib.dcv_activation_fwd(_ptr(x), _ptr(y), x.numel(), act, slope, _dt(x), _stream()), 'activation_fwd')
+        ctx.save_for_backward(y)
+        ctx.cfg = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, = ctx.saved_tensors
+        dy = _aligned_dense(dy.detach())
+        if dy.stride() != y.stride():
+            dy = as_nhwc(dy) if (y.dim() == 4 and is_nhwc(y)) else dy.contiguous()
+        dx = torch.empty_like(y)
+        check(lib.dcv_activation_bwd(_ptr(dy), _ptr(y), _ptr(dx), y.numel(), ctx.cfg[0], ctx.cfg[1], _dt(y), _stream()), 'activation_bwd')
+        return dx, None, None
+
+
+def activation(x: torch.Tensor, act: int, slope: float = 0.) -> torch.Tensor:
+    """ Stand-alone ReLU / LeakyReLU / Sigmoid (the activation of a pre-activation block, applied to the block's input). """
+    return x if act == ACT_NONE else _Activation.apply(x, int(act), float(slope))
+
+
+class _PreNormAct(torch.autograd.Function):
+    """ act(GroupNorm(BatchNorm(x))) on the block INPUT (pre-activation order): statistics pass, O(N*C) finalize, one fused affine pass, activation in
+    place. Backward: du = da * act'(a), then the normalisation adjoint dx = P*du + Q*x + R (reduce -> finalize -> apply). """
+
+    @staticmethod
+    def forward(ctx, x, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, act, slope, cfg: NormConfig, training: bool, grad_out, sctx):
+        _require_cuda(x)
+        n, c, h, w = x.shape
+        dev, st, dt, pz = x.device, _stream(), _dt(x), _pz(sctx)
+        stats = _acc_empty((n, c, 2), dev, sctx)
+        check(lib.dcv_norm_stats(_ptr(x), _ptr(stats), n, h * w, c, dt, pz, st), 'norm_stats')
+        groups = cfg.gn_groups if cfg.use_gn else 1
+        saved = torch.empty((int(lib.dcv_norm_saved_floats(n, c, groups)),), dtype=torch.float32, device=dev)
+        ab = torch.empty((n, c, 2), dtype=torch.float32, device=dev)
+        prm = _norm_params(cfg, n, c, h * w, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
+        check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(ab), _ptr(saved), st), 'norm_fwd_finalize')
+        a = empty_nhwc(n, c, h, w, x.dtype, dev)
+        check(lib.dcv_norm_apply_fwd(_ptr(x), _ptr(ab), _ptr(a), n, h * w, c, dt, st), 'norm_apply_fwd')
+        if act != ACT_NONE:
+            check(lib.dcv_activation_fwd(_ptr(a), _ptr(a), a.numel(), act, slope, dt, st), 'activation_fwd')
+        ctx.save_for_backward(x, a, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
+        ctx.cfg = (act, slope, cfg, training, grad_out, sctx)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, a, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv = ctx.saved_tensors
+        act, slope, cfg, training, grad_out, sctx = ctx.cfg
+        n, c, h, w = x.shape
+        dev, st, dt, pz = x.device, _stream(), _dt(x), _pz(sctx)
+        da = as_nhwc(da.detach(), x.dtype)
+        targets = grad_out if (grad_out and not grad_out.get('_written', False)) else {}
+        du = da
+        if act != ACT_NONE:
+            du = empty_nhwc(n, c, h, w, x.dtype, dev)
+            check(lib.dcv_activation_bwd(_ptr(da), _ptr(a), _ptr(du), a.numel(), act, slope, dt, st), 'activation_bwd')
+        s_nc = _acc_empty((n, c, 2), dev, sctx)
+        check(lib.dcv_norm_bwd_reduce(_ptr(du), _ptr(x), _ptr(s_nc), n, h * w, c, dt, pz, st), 'norm_bwd_reduce')
+        f32 = dict(dtype=torch.float32, device=dev)
+        pqr = torch.empty((n, c, 3), **f32)
+
+        def grad_buf(name, param):
+            if param is None:
+                return None
+            t = targets.get(name)
+            return torch.empty((c,), **f32) if t is None else t
+        d_bn_w, d_bn_b = (grad_buf('bn_w', bn_w), grad_buf('bn_b', bn_b)) if cfg.use_bn else (None, None)
+        d_gn_w, d_gn_b = (grad_buf('gn_w', gn_w), grad_buf('gn_b', gn_b)) if cfg.use_gn else (None, None)
+        prm = _norm_params(cfg, n, c, h * w, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
+        check(lib.dcv_norm_bwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(s_nc), _ptr(saved), _ptr(pqr), _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'norm_bwd_finalize')
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_nhwc(n, c, h, w, x.dtype, dev)
+            check(lib.dcv_act_norm_bwd_apply(_ptr(du), _ptr(x), _ptr(pqr), _ptr(dx), None, ACT_NONE, 0., n, h * w, c, dt, pz, st), 'act_norm_bwd_apply')
+
+        def ret(name, g):
+            return None if (g is None or name in targets) else g
+        _backward_done(grad_out, targets)
+        return dx, ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b), None, None, None, None, None, None, None, None, None
+
+
+def pre_norm_act(x: torch.Tensor, norm: NormConfig, training: bool = True, act: int = ACT_NONE, slope: float = 0., bn_weight=None, bn_bias=None, running_mean=None,
+                 running_var=None, num_batches_tracked=None, gn_weight=None, gn_bias=None, grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None) -> torch.Tensor:
+    """ The head of a pre-activation block (reference meta/nn.py:553 `(*norm_ops, act_fn(), layer_op)`): act(norms(x)) as one autograd node. It closes the
+    layer's backward (its backward runs after the convolution's): pass `notify=False` to the `conv_block` that follows. """
+    if x.dim() != 4:
+        raise NotImplementedError('deepcv_b200: normalisation in front of a fully connected layer is not built (image tensors only)')
+    return _PreNormAct.apply(as_nhwc(x), bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked, int(act), float(slope), norm, bool(training),
+                             grad_out, step_ctx)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------

@@ -159,6 +159,17 @@ int dcv_sc_conv_dgrad(const dcv_conv_shape* shape, const void* dz, const void* y
 int dcv_sc_affine_pool_fwd(const void* y, const dcv_sc_norm* norm, int update_running, void* z, int n, int h, int w, int c, int pool, void* stream);
 int dcv_sc_affine_pool_bwd(const void* dzp, const void* y, const dcv_sc_norm* norm, void* dz, int n, int h, int w, int c, int pool, void* stream);
 
+/* ---- dropout and stand-alone activations (csrc/elementwise.cu) ---
+ * Reference block orders (meta/nn.py:553): post-activation `[Dropout] -> op -> act -> norms`, pre-activation `[Dropout] -> norms -> act -> op`.
+ * y = x * keep / (1 - p) with keep ~ Bernoulli(1 - p) per element (meta/nn.py:535-541 -> torch.nn.Dropout). keep is a counter-based function
+ * (Philox4x32-10) of (seed, *call_dev, element index): nothing is stored, the backward pass calls the same entry point on dy with call_dev = the value
+ * the forward call saved in *saved_call_dev (may be NULL). Advance *call_dev with dcv_counter_add after each forward call (graph-replay safe).
+ * mask_out (may be NULL): keep as one uint8 per element, for tests that hand the same mask to the CPU oracle. x, y 16-byte aligned; y may alias x. */
+int dcv_dropout(const void* x, void* y, uint8_t* mask_out, size_t count, float p, uint64_t seed, const int32_t* call_dev, int32_t* saved_call_dev, int dtype, void* stream);
+/* y = act(x); dx = dy * act'(.) with the derivative taken from the activation OUTPUT act_out (DCV_ACT_*). Buffers 16-byte aligned; in place allowed. */
+int dcv_activation_fwd(const void* x, void* y, size_t count, int act, float slope, int dtype, void* stream);
+int dcv_activation_bwd(const void* dy, const void* act_out, void* dx, size_t count, int act, float slope, int dtype, void* stream);
+
 /* ---- normalisation (BatchNorm2d / GroupNorm after the activation: meta/nn.py:448-516,553; parameters.yml:10,82) ---
  * Any {BatchNorm, GroupNorm} stack applied to y collapses to one affine per (image, channel): z = A[n][c]*y + B[n][c],
  * with A, B closed-form in sum(y), sum(y*y) per (image, channel). */

@@ -118,8 +118,18 @@ def test_spec_errors():
         DeepcvModule((3, 8, 8), {**base, 'architecture': [{'avg_pooling': ['p', {'kernel_size': [1, 1]}]}, {'avg_pooling': {'kernel_size': [2, 2]}}, {'dense_link': {'_from': 'p'}}]})
     with pytest.raises(NotImplementedError, match='hot path'):
         DeepcvModule((3, 8, 8), {**base, 'architecture': [{'_nas_layer_choice': {'_candidates': []}}]})
-    with pytest.raises(NotImplementedError):
-        DeepcvModule((3, 8, 8), {**base, 'dropout_prob': 0.5, 'architecture': [{'conv2d': {'kernel_size': [3, 3], 'out_channels': 4}}]})
+    # dropout and the pre-activation order are built (reference nn.py:535-541, 553): same child modules in the reference's order
+    m = DeepcvModule((4, 8, 8), {**base, 'dropout_prob': 0.5, 'preactivation': True, 'batch_norm': {'affine': True, 'eps': 1e-5, 'momentum': 0.1},
+                                 'architecture': [{'conv2d': {'kernel_size': [3, 3], 'out_channels': 6}}]})
+    block = m._submodules['_submodule_0']
+    assert [type(c).__name__ for c in block] == ['Dropout', 'BatchNorm2d', type(base['act_fn']()).__name__, 'Conv2d'] and block[1].num_features == 4
+    m = DeepcvModule((4, 8, 8), {**base, 'dropout_prob': 0.5, 'batch_norm': {'affine': True, 'eps': 1e-5, 'momentum': 0.1},
+                                 'architecture': [{'conv2d': {'kernel_size': [3, 3], 'out_channels': 6}}]})
+    block = m._submodules['_submodule_0']
+    assert [type(c).__name__ for c in block] == ['Dropout', 'Conv2d', type(base['act_fn']()).__name__, 'BatchNorm2d'] and block[3].num_features == 6
+    with pytest.raises(NotImplementedError, match='Dropout'):
+        from deepcv_b200.meta.nn import FusedLayer
+        FusedLayer(torch.nn.Dropout2d(0.5), torch.nn.Conv2d(3, 4, 3))
 
 
 def test_registry_decorator():
