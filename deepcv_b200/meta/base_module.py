@@ -78,7 +78,7 @@ class DeepcvModule(torch.nn.Module):
             n_referrers = sum(name in r for r in remaining_submodule_references.values())
             kwargs = {}
             if getattr(subm, 'can_defer_affine', False):
-                kwargs['defer_affine'] = i + 1 < len(children) and n_referrers == 0 and getattr(children[i + 1], 'accepts_pending_affine', False) \
+                kwargs['defer_affine'] = not isinstance(x, (list, tuple)) and i + 1 < len(children) and n_referrers == 0 and getattr(children[i + 1], 'accepts_pending_affine', False) \
                     and not getattr(children[i + 1], 'referenced_submodules', None)
             refs = None if sequential else getattr(subm, 'referenced_submodules', None)
             if refs is not None and len(refs) > 0:
@@ -95,9 +95,13 @@ class DeepcvModule(torch.nn.Module):
             # aliases whose gradients are summed by a library kernel (ops.fork).
             n_referrers = sum(name in r for r in remaining_submodule_references.values())
             if n_referrers > 0:
-                x = ops.materialize(x)
-                x, referenced_output_features[name] = ops.fork(x) if x.device.type == 'cuda' else (x, x)
-        return ops.materialize(x)
+                if isinstance(x, (list, tuple)):   # parallel branches: every tensor of the list is kept and flows on
+                    pairs = [ops.fork(t) if t.device.type == 'cuda' else (t, t) for t in (ops.materialize(t) for t in x)]
+                    x, referenced_output_features[name] = [a for a, _ in pairs], [b for _, b in pairs]
+                else:
+                    x = ops.materialize(x)
+                    x, referenced_output_features[name] = ops.fork(x) if x.device.type == 'cuda' else (x, x)
+        return [ops.materialize(t) for t in x] if isinstance(x, (list, tuple)) else ops.materialize(x)
 
     def __str__(self) -> str:
         return str(self.describe())

@@ -12,9 +12,10 @@ module here answers a `meta` input with an empty `meta` output of the right shap
 tensors are rejected.
 """
 import enum
+import functools
 import logging
 import math
-from typing import Any, Dict, List, Optional, Sequence, Type, Union
+from typing import Any, Callable, Dict, List, Optional, Sequence, Type, Union
 
 import numpy as np
 import torch
@@ -22,7 +23,7 @@ import torch
 from .. import ops
 from .._lib import ACT_NONE, ALGO_AUTO
 
-__all__ = ['XAVIER_INIT_SUPPORTED_ACT_FN', 'NormTechnique', 'NORM_TECHNIQUES_MODULES', 'batch_norm_nd', 'instance_norm_nd', 'avg_pooling_nd', 'conv_nd',
+__all__ = ['XAVIER_INIT_SUPPORTED_ACT_FN', 'NormTechnique', 'NORM_TECHNIQUES_MODULES', 'batch_norm_nd', 'instance_norm_nd', 'avg_pooling_nd', 'conv_nd', 'forward_call_convention_dec', 'is_torch_obj',
            'get_padding_from_kernel', 'normalization_techniques', 'normalization_techniques_impl', 'layer', 'FusedLayer', 'AvgPool2d', 'Flatten',
            'get_gain_name', 'interpolate', 'get_model_capacity', 'get_out_features_shape', 'is_conv', 'is_fully_connected', 'is_torch_obj', 'meta_like']
 
@@ -30,7 +31,70 @@ XAVIER_INIT_SUPPORTED_ACT_FN = {torch.nn.ReLU: 'relu', torch.nn.LeakyReLU: 'leak
 
 
 def is_torch_obj(v) -> bool:
-    return isinstance(v, (torch.Tensor, torch.Size))
+    """ reference nn.py:706-709 as intended (the `'_module__'` typo made it always False): a single tensor, not a sequence of
+    tensors. A raw block output with a pending normalisation (`ops.PendingAffine`) counts as one tensor. """
+    return isinstance(v, (torch.Tensor, torch.Size, ops.PendingAffine))
+
+
+def forward_call_convention_dec(apply_parallel_forward: bool = False, refs_tensor_count_similar: bool = None, in_tensors_count_similar_to_refs: bool = None,
+                                ignore_prev_subm_intput: bool = False, ignore_sub_refs: bool = False):
+    """ Call convention of submodule forward functions (reference nn.py:130-194): the decorated `forward_fn` always sees a LIST of tensors — or, with
+    `apply_parallel_forward`, ONE tensor per call: the function is then applied to each input tensor in turn, together with the i-th tensor of every
+    referenced submodule output ("parallel apply": siamese / parallel branches sharing one submodule) — whether the previous submodule produced a
+    single tensor or a sequence; references arrive through `referenced_submodules_out` as `List[List[Tensor]]` (`List[Tensor]` when applied in
+    parallel); the result is flattened and a single output tensor is returned bare. `refs_tensor_count_similar` / `in_tensors_count_similar_to_refs`
+    (default: `apply_parallel_forward`) require all references (and the input) to hold the same number of tensors; `ignore_prev_subm_intput` /
+    `ignore_sub_refs` drop the respective operand. Works on plain functions and on `torch.nn.Module.forward` methods.
+
+    One deliberate difference (defect ledger): the reference consumes its operand lists with `list.pop()` — from the END — so
+    every parallel submodule would silently reverse the order of the branches; here the i-th output belongs to the i-th input. """
+    refs_tensor_count_similar = apply_parallel_forward if refs_tensor_count_similar is None else refs_tensor_count_similar
+    refs_tensor_count_similar = not ignore_sub_refs and refs_tensor_count_similar
+    in_tensors_count_similar_to_refs = apply_parallel_forward if in_tensors_count_similar_to_refs is None else in_tensors_count_similar_to_refs
+    in_tensors_count_similar_to_refs = not ignore_sub_refs and not ignore_prev_subm_intput and in_tensors_count_similar_to_refs
+
+    def _decorator(forward_fn: Callable) -> Callable:
+        @functools.wraps(forward_fn)
+        def _forward_wraper(*call_args, referenced_submodules_out=None, **kwargs):
+            bound = ()
+            if call_args and isinstance(call_args[0], torch.nn.Module):   # decorating a method: `self` comes first
+                bound, call_args = call_args[:1], call_args[1:]
+            inputs, args = (call_args[0] if call_args else None), call_args[1:]
+            if ignore_prev_subm_intput or inputs is None:
+                inputs = []
+            else:
+                inputs = [inputs] if is_torch_obj(inputs) else list(inputs)
+            if ignore_sub_refs:
+                refs = []
+            else:
+                refs = [[t] if is_torch_obj(t) else list(t) for t in (referenced_submodules_out or [])]
+                if refs:
+                    if in_tensors_count_similar_to_refs and not all(len(r) == len(inputs) for r in refs):
+                        raise ValueError(f'Error: When `in_tensors_count_similar_to_refs` is `True`, all referenced output tensor(s) should each have as many tensor(s) as input '
+                                         f'tensor(s) from previous submodule: `len(referenced_submodules_out[i] == len(inputs) =={len(inputs)}` {chr(10)}'
+                                         f'Got {len(inputs)} input tensor(s) and references of {[len(r) for r in refs]} tensor(s)')
+                    elif (ignore_prev_subm_intput or not in_tensors_count_similar_to_refs) and refs_tensor_count_similar and not all(len(r) == len(refs[0]) for r in refs):
+                        raise ValueError(f'Error: When `refs_tensor_count_similar` is `True`, all referenced output tensor(s) should each have as many tensor(s) as the first '
+                                         f'tensor(s) ref: `len(referenced_submodules_out[0])={len(refs[0])}` (or should all have only a single tensor if `refs[0]` isnt a sequence) '
+                                         f'{chr(10)}Got references of {[len(r) for r in refs]} tensor(s)')
+            if not apply_parallel_forward:
+                refs_kwarg = {'referenced_submodules_out': refs} if refs else {}
+                outs = forward_fn(*bound, inputs, *args, **refs_kwarg, **kwargs)
+                outs = [outs] if is_torch_obj(outs) else list(outs)
+            else:
+                outs = []
+                loops_count = 1   # at least one call, even when the previous output is ignored
+                if not ignore_prev_subm_intput and inputs:
+                    loops_count = len(inputs)
+                if refs:
+                    loops_count = len(refs[0])
+                for i in range(loops_count):
+                    refs_kwarg = {'referenced_submodules_out': [r[i] for r in refs]} if refs else {}
+                    rslt = forward_fn(*bound, inputs[i] if inputs else [], *args, **refs_kwarg, **kwargs)
+                    outs.extend([rslt] if is_torch_obj(rslt) else rslt)
+            return outs if len(outs) != 1 else outs[0]
+        return _forward_wraper
+    return _decorator
 
 
 def is_conv(op_t: Union[torch.nn.Module, Type]) -> bool:
@@ -150,6 +214,7 @@ class AvgPool2d(torch.nn.AvgPool2d):
 
     accepts_pending_affine = True   # a raw block output: the pending normalisation is applied inside the pooling kernel (pool(A*y + B) = A*pool(y) + B)
 
+    @forward_call_convention_dec(apply_parallel_forward=True, ignore_sub_refs=True)   # reference submodule_creators.py:175
     def forward(self, x) -> torch.Tensor:
         k, s = _pair(self.kernel_size), _pair(self.stride if self.stride is not None else self.kernel_size)
         if isinstance(x, ops.PendingAffine):
@@ -165,6 +230,7 @@ class Flatten(torch.nn.Flatten):
     """ `torch.nn.Flatten()` of the logical N x C x H x W tensor (features in (C, H, W) order), from NHWC memory. The architecture
     parser substitutes this class wherever a spec names `torch.nn.Flatten`. """
 
+    @forward_call_convention_dec(apply_parallel_forward=True, ignore_sub_refs=True)
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.device.type == 'meta' or x.dim() != 4 or self.start_dim != 1 or self.end_dim not in (-1, 3):
             if x.device.type != 'meta' and x.dim() == 4:
@@ -261,6 +327,7 @@ class FusedLayer(torch.nn.Sequential):
                     num_batches_tracked=bn.num_batches_tracked if bn is not None else None,
                     gn_weight=gn.weight if gn is not None else None, gn_bias=gn.bias if gn is not None else None)
 
+    @forward_call_convention_dec(apply_parallel_forward=True, ignore_sub_refs=True)   # reference submodule_creators.py:254: one layer shared by parallel branches
     def forward(self, x, defer_affine: bool = False):
         if not isinstance(x, ops.PendingAffine) and x.device.type == 'meta':
             return self._meta_forward(x)

@@ -14,6 +14,7 @@ import inspect
 from collections import OrderedDict
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Type, Union
 
+import numpy as np
 import torch
 
 from .. import utils
@@ -85,21 +86,20 @@ def define_nn_architecture(deepcv_module, architecture_spec: Iterable, submodule
 def _infer_out_shape(deepcv_module, subm_name: str, subm: torch.nn.Module):
     """ The reference re-runs the *whole* module on zeros after each addition (O(L^2), :103-104); one submodule on a `meta` tensor of
     the previous shape gives the same answer. Link submodules get the recorded shapes of the tensors they reference. """
-    prev_shape = deepcv_module._features_shapes[-1]
-    x = deepcv_nn.meta_like((1, *prev_shape))
+    def _dummy(shape):   # a shape, or a list of shapes when the submodule produced several tensors (parallel branches)
+        return deepcv_nn.meta_like((1, *shape)) if isinstance(shape[0], (int, np.integer)) else [deepcv_nn.meta_like((1, *s)) for s in shape]
+    x = _dummy(deepcv_module._features_shapes[-1])
     was_training = subm.training
     with torch.no_grad():
         refs = deepcv_module._submodule_references.get(subm_name)
         if refs:
             names = list(deepcv_module._submodules.keys())
-            ref_out = OrderedDict((r, deepcv_nn.meta_like((1, *deepcv_module._features_shapes[names.index(r) + 1]))) for r in refs)
+            ref_out = OrderedDict((r, _dummy(deepcv_module._features_shapes[names.index(r) + 1])) for r in refs)
             out = subm(x, referenced_submodules_out=ref_out)
         else:
             out = subm(x)
     subm.train(was_training)
-    if not isinstance(out, torch.Tensor):
-        raise NotImplementedError('deepcv_b200: submodules returning several tensors (parallel branches) are outside the hot path')
-    return tuple(out.shape[1:])
+    return tuple(out.shape[1:]) if isinstance(out, torch.Tensor) else [tuple(t.shape[1:]) for t in out]
 
 
 def _parse_torch_module_from_submodule_spec(deepcv_module, submodule_spec, submodule_pos: Union[int, str], subm_creators: Dict[str, Callable],

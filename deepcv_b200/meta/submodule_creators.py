@@ -19,7 +19,7 @@ from .. import ops
 from . import nn as deepcv_nn
 
 __all__ = ['BASIC_SUBMODULE_CREATORS', 'TENSOR_REDUCTION_FNS', 'get_reduction_fn', 'ForwardCallbackSubmodule', 'submodule_creator_dec', 'avg_pooling_creator',
-           'reduction_subm_creator', 'new_branch_creator', 'add_nn_layer_creator', 'add_residual_dense_link_creator', 'FROM', 'FROM_NAS_INPUT_CHOICE', 'NEW_BRANCH_FROM_TENSOR']
+           'reduction_subm_creator', 'select_tensor_creator', 'parse_slice', 'new_branch_creator', 'add_nn_layer_creator', 'add_residual_dense_link_creator', 'FROM', 'FROM_NAS_INPUT_CHOICE', 'NEW_BRANCH_FROM_TENSOR']
 
 # Token values of `deepcv.meta.nn_spec.yaml_tokens` used by creators (kept here as strings to avoid an import cycle)
 FROM, FROM_NAS_INPUT_CHOICE, NEW_BRANCH_FROM_TENSOR = '_from', '_from_nas_input_choice', '_new_branch_from_tensor'
@@ -63,7 +63,7 @@ class ForwardCallbackSubmodule(torch.nn.Module):
 
     def forward(self, tensors, referenced_submodules_out: 'OrderedDict[str, torch.Tensor]' = None):
         if referenced_submodules_out is not None and self.referenced_submodules is not None and self.takes_tensor_references:
-            refs = [v for n, v in referenced_submodules_out.items() if n in self.referenced_submodules]
+            refs = [v for n, v in referenced_submodules_out.items() if n in self.referenced_submodules]   # each a tensor or a list of tensors (parallel branches)
             return self.forward_callback(tensors, referenced_submodules_out=refs)
         if referenced_submodules_out or self.referenced_submodules or self.takes_tensor_references:
             raise ValueError(f'Error: Uncoherent usage of output tensor references: (Did you provided `{FROM}` to a submodule which doesnt support tensor references?){NL}'
@@ -118,7 +118,37 @@ def reduction_subm_creator(submodule_params: Dict[str, Any], fn: str, keep_dim: 
     """ reference :179-186: standalone reduction of the (list of) tensor(s) coming from the previous submodule. """
     reduction_subm_creator._check_submodule_params(submodule_params)
     reduce = get_reduction_fn(fn)
-    return ForwardCallbackSubmodule(lambda tensors: reduce(tensors, keep_dim=keep_dim))
+
+    @deepcv_nn.forward_call_convention_dec(apply_parallel_forward=False, ignore_sub_refs=True)
+    def _reduce_forward(tensors: List[torch.Tensor]):
+        return reduce(tensors, keep_dim=keep_dim) if len(tensors) > 1 else tensors[0]
+    return ForwardCallbackSubmodule(_reduce_forward)
+
+
+def parse_slice(spec) -> Union[int, slice]:
+    """ 'i' / 'start:stop[:step]' / int -> index or slice over a list of tensors (reference utils `parse_slice`). """
+    if isinstance(spec, (int, np.integer)):
+        return int(spec)
+    parts = [int(v) if v.strip() else None for v in str(spec).split(':')]
+    if len(parts) == 1:
+        return parts[0]
+    if len(parts) > 3:
+        raise ValueError(f'Error: Invalid slice specification "{spec}"')
+    return slice(*parts)
+
+
+@submodule_creator_dec(name='select_tensor', required_subm_params_keys={'slice', })
+def select_tensor_creator(submodule_params: Dict[str, Any], reduction: str = 'none') -> ForwardCallbackSubmodule:
+    """ reference :188-200: keeps `tensors[slice]` of the parallel tensors coming from the previous submodule (then the optional reduction). """
+    select_tensor_creator._check_submodule_params(submodule_params)
+    parsed_slice = parse_slice(submodule_params['slice'])
+    reduce = TENSOR_REDUCTION_FNS[reduction]
+
+    @deepcv_nn.forward_call_convention_dec(apply_parallel_forward=False, ignore_sub_refs=True)
+    def _select_tensor_forward(tensors: List[torch.Tensor]):
+        picked = tensors[parsed_slice]
+        return picked if deepcv_nn.is_torch_obj(picked) else reduce(picked)
+    return ForwardCallbackSubmodule(_select_tensor_forward)
 
 
 @submodule_creator_dec(name=NEW_BRANCH_FROM_TENSOR, allowed_subm_params_keys={FROM, FROM_NAS_INPUT_CHOICE})
@@ -129,6 +159,7 @@ def new_branch_creator(submodule_params: Dict[str, Any], reduction: str = 'conca
         raise ValueError(f'Error: "{NEW_BRANCH_FROM_TENSOR}" submodules at least needs "{FROM}" or "{FROM_NAS_INPUT_CHOICE}" param in `submodule_params`')
     reduce = TENSOR_REDUCTION_FNS[reduction]
 
+    @deepcv_nn.forward_call_convention_dec(apply_parallel_forward=True, ignore_prev_subm_intput=True, refs_tensor_count_similar=True)   # reference :210
     def _new_branch_forward(_prev_subm_out, referenced_submodules_out: List[torch.Tensor]):
         return reduce(list(referenced_submodules_out)) if len(referenced_submodules_out) > 1 else referenced_submodules_out[0]
     return ForwardCallbackSubmodule(_new_branch_forward)
@@ -145,6 +176,10 @@ def add_nn_layer_creator(layer_op_t: Type[torch.nn.Module], creator_name: str, s
     def _nn_layer_creator(submodule_params: Dict[str, Any], input_shape, act_fn: Type[torch.nn.Module] = None, dropout_prob: float = None, preactivation: bool = False,
                           batch_norm=None, layer_norm=None, instance_norm=None, group_norm=None, layer_nrm_and_mean_batch_nrm=None) -> torch.nn.Module:
         submodule_params = dict(submodule_params)
+        if not isinstance(input_shape[0], (int, np.integer)):   # parallel branches: ONE layer shared by all of them (reference :254), sized for the first
+            if any(tuple(sh) != tuple(input_shape[0]) for sh in input_shape):
+                raise ValueError(f'Error: parallel tensors fed to one "{creator_name}" layer must all have the same shape, got {list(input_shape)}')
+            input_shape = input_shape[0]
         if deepcv_nn.is_fully_connected(layer_op_t):
             if 'in_features' not in submodule_params:
                 submodule_params['in_features'] = int(np.prod(input_shape))
@@ -185,6 +220,7 @@ def add_residual_dense_link_creator(is_residual: bool, creator_name: str, submod
                              f'{creator_name} link YAML specification; You should at least provide a tensor reference.')
         reduce = TENSOR_REDUCTION_FNS[reduction]
 
+        @deepcv_nn.forward_call_convention_dec(apply_parallel_forward=apply_in_parallel, in_tensors_count_similar_to_refs=apply_in_parallel)   # reference :300
         def _forward_callback(x, referenced_submodules_out: List[torch.Tensor]):
             out = [x] if isinstance(x, torch.Tensor) else list(x)
             for refs in referenced_submodules_out:
@@ -214,5 +250,5 @@ def _outside_hot_path(name: str) -> Callable:
 
 
 for _name in ('concat_coords', 'concat_hilbert_coords', 'multiresolution_fusion', 'parallel_conv', 'hrnet_input_stem', 'hrnet_repr_head_v1', 'hrnet_repr_head_vZ',
-              'hrnet_repr_head_v2p', 'select_tensor'):
+              'hrnet_repr_head_v2p'):
     BASIC_SUBMODULE_CREATORS[_name] = _outside_hot_path(_name)

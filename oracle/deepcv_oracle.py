@@ -72,15 +72,36 @@ class Link(torch.nn.Module):
     """ meta/submodule_creators.py:272-332 (+ reduction fns :43-65 as intended): out=[x]+refs, each ref
     bilinearly rescaled to x's spatial shape iff shapes differ and `allow_scaling`; then sum / mean / concat(dim=1). """
 
-    def __init__(self, reduction: str, allow_scaling: bool, align_corners: bool = False, ignore_input: bool = False):
+    def __init__(self, reduction: str, allow_scaling: bool, align_corners: bool = False, ignore_input: bool = False, apply_in_parallel: bool = True):
         super().__init__()
         self.reduction, self.allow_scaling, self.align_corners, self.ignore_input = reduction, allow_scaling, align_corners, ignore_input
+        self.apply_in_parallel = apply_in_parallel
         self.referenced_submodules: List[str] = []
 
     def forward(self, x, referenced_submodules_out: 'OrderedDict[str, torch.Tensor]'):
-        out = [] if self.ignore_input else [x]
-        for name in self.referenced_submodules:
-            y = referenced_submodules_out[name]
+        """ meta/nn.py:130-194 call convention: operands are lists of tensors (parallel branches); applied in parallel, the i-th input is reduced with
+        the i-th tensor of every reference (all must hold as many tensors); otherwise everything is reduced together. Branch order is kept (the
+        reference's `list.pop()` would reverse it at every parallel submodule: SURVEY.md section 8.c.2-style defect, not reproduced). """
+        xs = [] if self.ignore_input else (list(x) if isinstance(x, (list, tuple)) else [x])
+        refs = [referenced_submodules_out[name] for name in self.referenced_submodules]
+        refs = [list(r) if isinstance(r, (list, tuple)) else [r] for r in refs]
+        if self.apply_in_parallel:
+            if not self.ignore_input and not all(len(r) == len(xs) for r in refs):
+                raise ValueError('Error: When `in_tensors_count_similar_to_refs` is `True`, all referenced output tensor(s) should each have as many tensor(s) as input tensor(s)')
+            if not all(len(r) == len(refs[0]) for r in refs):
+                raise ValueError('Error: When `refs_tensor_count_similar` is `True`, all referenced output tensor(s) should each have as many tensor(s)')
+            outs = []
+            for i in range(len(refs[0])):
+                o = self._reduce(([] if self.ignore_input else [xs[i]]), [r[i] for r in refs])
+                outs.extend(o if isinstance(o, list) else [o])
+        else:
+            o = self._reduce(xs, [t for r in refs for t in r])
+            outs = o if isinstance(o, list) else [o]
+        return outs[0] if len(outs) == 1 else outs
+
+    def _reduce(self, out: List[torch.Tensor], ref_tensors: List[torch.Tensor]):
+        out = list(out)
+        for y in ref_tensors:
             target = (out[0] if out else y).shape[2:]
             if y.shape[2:] != target:
                 if not self.allow_scaling:
@@ -88,6 +109,8 @@ class Link(torch.nn.Module):
                 mode = {1: 'linear', 2: 'bilinear', 3: 'trilinear'}[len(target)]
                 y = F.interpolate(y, size=target, mode=mode, align_corners=self.align_corners)  # meta/nn.py:665-676
             out.append(y)
+        if self.reduction == 'none' or len(out) == 1:
+            return out if len(out) > 1 else out[0]
         if self.reduction == 'concat':
             return torch.cat(out, dim=1)
         if self.reduction == 'sum':
@@ -95,6 +118,34 @@ class Link(torch.nn.Module):
         if self.reduction == 'mean':
             return torch.stack(out, 0).mean(0) if len(out) > 1 else out[0]
         raise ValueError(f'Error: Invalid "{self.reduction}" reduction function name.')
+
+
+class Reduce(torch.nn.Module):
+    """ meta/submodule_creators.py:179-186 (`reduce`) and :188-200 (`select_tensor`): reduction / selection over the parallel tensors of the previous
+    submodule (not applied per tensor: `takes_list`). """
+    takes_list = True
+
+    def __init__(self, reduction: str, pick=None):
+        super().__init__()
+        self.reduction, self.pick = reduction, pick
+
+    def forward(self, x):
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        if self.pick is not None:
+            xs = xs[self.pick]
+            xs = xs if isinstance(xs, list) else [xs]
+        if len(xs) == 1 or self.reduction == 'none':
+            return xs[0] if len(xs) == 1 else xs
+        if self.reduction == 'concat':
+            return torch.cat(xs, dim=1)
+        return torch.stack(xs, 0).sum(0) if self.reduction == 'sum' else torch.stack(xs, 0).mean(0)
+
+
+def _parse_slice(spec):
+    if isinstance(spec, int):
+        return spec
+    parts = [int(v) if v.strip() else None for v in str(spec).split(':')]
+    return parts[0] if len(parts) == 1 else slice(*parts)
 
 
 def _conv_or_linear_creator(op_t):
@@ -118,10 +169,10 @@ def _avg_pooling(submodule_params, input_shape):
 
 
 def _link(is_residual):
-    def creator(submodule_params, allow_scaling=False, scaling_align_corners=False, reduction='sum' if is_residual else 'concat'):
+    def creator(submodule_params, allow_scaling=False, scaling_align_corners=False, reduction='sum' if is_residual else 'concat', apply_in_parallel=True):
         if FROM not in submodule_params:
             raise ValueError('Error: Missing "_from" parameter in link YAML specification')
-        return Link(reduction, allow_scaling, scaling_align_corners)
+        return Link(reduction, allow_scaling, scaling_align_corners, apply_in_parallel=apply_in_parallel)
     return creator
 
 
@@ -135,6 +186,8 @@ CREATORS: Dict[str, Callable] = {
     'linear': _conv_or_linear_creator(torch.nn.Linear), 'fully_connected': _conv_or_linear_creator(torch.nn.Linear),
     'average_pooling': _avg_pooling, 'avg_pooling': _avg_pooling,  # both spellings: SURVEY.md §8.c.2
     'residual_link': _link(True), 'dense_link': _link(False), NEW_BRANCH: _new_branch,
+    'reduce': lambda submodule_params, fn, keep_dim=False: Reduce(fn),
+    'select_tensor': lambda submodule_params, reduction='none': Reduce(reduction, pick=_parse_slice(submodule_params['slice'])),
 }
 
 
@@ -197,7 +250,9 @@ class OracleDeepcvModule(torch.nn.Module):
             mod, _, attr = subm_type.rpartition('.')
             fn = getattr(importlib.import_module(mod), attr)
         sig = inspect.signature(fn).parameters
-        with_globals.update(prev_shapes=self._features_shapes, input_shape=self._features_shapes[-1], input_shapes=self._features_shapes[-1])
+        last = self._features_shapes[-1]
+        last = last if isinstance(last[0], (int, np.integer)) else last[0]   # parallel tensors share the layer: sized for the first (all alike)
+        with_globals.update(prev_shapes=self._features_shapes, input_shape=last, input_shapes=self._features_shapes[-1])
         provided = {n: v for n, v in with_globals.items() if n in sig}
         if 'submodule_params' in sig:
             provided['submodule_params'] = {n: v for n, v in params.items() if n not in provided}
@@ -216,7 +271,7 @@ class OracleDeepcvModule(torch.nn.Module):
         with torch.no_grad():
             out = self(torch.zeros(1, *self._input_shape))
         self.train(was_training)
-        return tuple(out.shape[1:])
+        return tuple(out.shape[1:]) if isinstance(out, torch.Tensor) else [tuple(t.shape[1:]) for t in out]
 
     # base_module.py:113-155 (return after the loop; refs released after the last referrer)
     def forward(self, x):
@@ -231,6 +286,9 @@ class OracleDeepcvModule(torch.nn.Module):
                     if not any(r in v for v in remaining.values()):
                         kept.pop(r, None)
                 x = subm(x, referenced_submodules_out=current)
+            elif isinstance(x, (list, tuple)) and not getattr(subm, 'takes_list', False):   # meta/submodule_creators.py:175,254: layers / poolings are applied to each parallel tensor (shared weights)
+                x = [subm(t) for t in x]
+                x = x[0] if len(x) == 1 else x
             else:
                 x = subm(x)
             if any(name in v for v in remaining.values()):

@@ -171,3 +171,61 @@ def test_dropout_fresh_mask_per_call_and_graph_replay(dev):
     assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
     with pytest.raises(ValueError):
         ops.dropout(static_x, 1.0, state)
+
+
+def _siamese_spec():
+    """ Parallel branches (reference meta/nn.py:130-194, submodule_creators.py:175,203-224,254,300): a dense link with `reduction: none` turns two
+    feature maps into a LIST of two tensors; the convolution block and the pooling that follow are applied to each of them (one shared layer:
+    siamese branches); a parallel residual link adds the i-th tensor of a referenced list to the i-th branch; `reduce` concatenates the branches. """
+    return {'act_fn': torch.nn.ReLU, 'dropout_prob': 0., 'batch_norm': {'affine': True, 'eps': 1e-5, 'momentum': 0.1},
+            'architecture': [{'conv2d': ['a', {'kernel_size': [3, 3], 'out_channels': 8, 'padding': 1}]},
+                             {'conv2d': ['b', {'kernel_size': [3, 3], 'out_channels': 8, 'padding': 1}]},
+                             {'dense_link': ['pair', {'_from': 'a', 'reduction': 'none'}]},          # [b, a]: two parallel tensors
+                             {'conv2d': {'kernel_size': [3, 3], 'out_channels': 8, 'padding': 1}},   # shared by both branches
+                             {'residual_link': {'_from': 'pair'}},                                   # i-th branch + i-th tensor of `pair`
+                             {'avg_pooling': {'kernel_size': [2, 2], 'stride': [2, 2]}},
+                             {'reduce': {'fn': 'concat'}},
+                             'torch.nn.Flatten',
+                             {'fully_connected': {'out_features': 5, 'act_fn': torch.nn.Sigmoid, 'batch_norm': None}}]}
+
+
+def test_parallel_branches_against_oracle(dev):
+    from deepcv_b200.meta.base_module import DeepcvModule
+    from oracle import deepcv_oracle as O
+    torch.manual_seed(21)
+    oracle = O.OracleDeepcvModule((4, 16, 16), _siamese_spec())
+    model = DeepcvModule((4, 16, 16), _siamese_spec())
+    assert model._features_shapes[3] == [(8, 16, 16), (8, 16, 16)] and model._features_shapes[4] == [(8, 16, 16), (8, 16, 16)]   # lists of shapes while branches are parallel
+    assert model._features_shapes[7] == (16, 8, 8) and model._features_shapes[-1] == (5,)
+    assert [n for n, _ in model.named_parameters()] == [n for n, _ in oracle.named_parameters()]
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(dev).train()
+    oracle.train()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(5, 4, 16, 16, generator=g)
+    t = torch.randn(5, 5, generator=g)
+    xd = x.to(dev).requires_grad_(True)
+    out = model(xd)
+    (out * t.to(dev)).sum().backward()
+    o64m = copy.deepcopy(oracle).double()
+    xr64 = x.double().requires_grad_(True)
+    o64 = o64m(xr64)
+    (o64 * t.double()).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    o32 = oracle(xr)
+    (o32 * t).sum().backward()
+
+    def gate(a, r32, r64, what):
+        allowed = FP32_TOL * float(r64.abs().max()) + 8. * float((r32.double() - r64).abs().max()) + 1e-30
+        err = float((a.detach().double().cpu() - r64).abs().max())
+        assert err <= allowed, f'{what}: |err| {err:.3e} > {allowed:.3e}'
+    gate(out, o32.detach(), o64.detach(), 'output')
+    gate(xd.grad, xr.grad, xr64.grad, 'input gradient')
+    g64 = dict(o64m.named_parameters())
+    for (n, p), (_, q) in zip(model.named_parameters(), oracle.named_parameters()):
+        gate(p.grad, q.grad, g64[n].grad, f'grad {n}')   # the shared layer's gradients are the SUM over both branches
+    # tensor-count checks of the call convention
+    bad = _siamese_spec()
+    bad['architecture'][4] = {'residual_link': {'_from': 'a'}}   # one referenced tensor for two parallel inputs
+    with pytest.raises(ValueError, match='in_tensors_count_similar_to_refs'):
+        DeepcvModule((4, 16, 16), bad)
