@@ -103,10 +103,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Column sums of a warp's 32 x 32 block held one row per lane, by recursive halving: after the step with distance d a lane keeps the half of its current
+// columns selected by (lane & d) and adds its partner's copy of them — 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 5 x 32. On return lane l holds the sum
+// of column l over the 32 rows (v is destroyed).
+__device__ __forceinline__ float warp_colsum32(float* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const bool up = (lane & d) != 0;
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      const float send = up ? v[i] : v[i + d];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, d);
+      v[i] = (up ? v[i + d] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+
 // Epilogue of 32 accumulator columns of one pixel: bias (vector loads, hoisted out of the element loop) + activation resolved at compile
-// time + packed bf16 conversion + four 16-byte stores.
-template <int ACT>
-__device__ __forceinline__ void epilogue_store32(const uint32_t* v, const float* __restrict__ bias32, float slope, __nv_bfloat16* dst) {
+// time + packed bf16 conversion + two 32-byte stores. STATS: the BatchNorm batch statistics ride along (north star: "BatchNorm statistics ... fused into
+// the conv epilogue"): sum and sum of squares of the STORED (bf16-rounded) values of each of the 32 channels over the warp's 32 pixels (rows that fall
+// outside the tensor contribute zero), added to the caller's running totals (s1, s2) of channel `lane` of this 32-channel chunk — registers kept across
+// all the tiles of the CTA and flushed with one global atomic each at the end (a first version added them to shared-memory totals per tile: fp32 shared
+// atomics are compare-and-swap loops and the four epilogue warps hit the same addresses — the epilogue became the critical path, +46 us on a 77 us
+// kernel). Every lane of the warp must call it (shuffles); only `valid` rows store.
+// STATS = 1: per-tile column sums (62 shuffles per chunk) into run[0], run[1] (lane = channel). STATS = 2: the thread's own 32 + 32 partial sums
+// run[0..31], run[32..63] (its pixel row's values), summed over the warp ONCE at the end of the kernel — for N_TILE = 64, where a tile's MMAs are too
+// short to hide a per-tile butterfly (measured: the 64 -> 64 layer at 56x56 went from 77 to 123 us with it).
+template <int ACT, int STATS>
+__device__ __forceinline__ void epilogue_store32(const uint32_t* v, const float* __restrict__ bias32, float slope, __nv_bfloat16* dst, bool valid, float* run) {
+  if (!STATS && !valid) return;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -126,6 +153,26 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t* v, const float*
   uint32_t pk[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const uint4 q = vec_pack<__nv_bfloat16>(f + 8 * j); pk[4 * j] = q.x; pk[4 * j + 1] = q.y; pk[4 * j + 2] = q.z; pk[4 * j + 3] = q.w; }
+  if (STATS == 1) {
+    float sq[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      f[2 * j] = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+      f[2 * j + 1] = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+      sq[2 * j] = f[2 * j] * f[2 * j]; sq[2 * j + 1] = f[2 * j + 1] * f[2 * j + 1];
+    }
+    run[0] += warp_colsum32(f);
+    run[1] += warp_colsum32(sq);
+    if (!valid) return;
+  } else if (STATS == 2) {
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float lo = __uint_as_float(pk[j] << 16), hi = __uint_as_float(pk[j] & 0xffff0000u);
+      run[2 * j] += lo; run[2 * j + 1] += hi;
+      run[32 + 2 * j] = fmaf(lo, lo, run[32 + 2 * j]); run[32 + 2 * j + 1] = fmaf(hi, hi, run[32 + 2 * j + 1]);
+    }
+  }
   if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
     // a lane owns 64 contiguous bytes of its pixel's row, the lanes of a warp are >= 128 bytes apart: two 256-bit stores (sm_100 STG.256) instead of four
     // 128-bit ones halve the store requests (the uint8 preprocess kernel went from 62 % to 88 % of HBM bandwidth with the same change)
@@ -139,14 +186,43 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t* v, const float*
   }
 }
 
-__device__ __forceinline__ void epilogue_store32_dyn(int act, const uint32_t* v, const float* bias32, float slope, __nv_bfloat16* dst) {
+template <int STATS>
+__device__ __forceinline__ void epilogue_store32_dyn(int act, const uint32_t* v, const float* bias32, float slope, __nv_bfloat16* dst, bool valid, float* run) {
   switch (act) {   // warp-uniform
-    case DCV_ACT_RELU: epilogue_store32<DCV_ACT_RELU>(v, bias32, slope, dst); break;
-    case DCV_ACT_LEAKY_RELU: epilogue_store32<DCV_ACT_LEAKY_RELU>(v, bias32, slope, dst); break;
-    case DCV_ACT_SIGMOID: epilogue_store32<DCV_ACT_SIGMOID>(v, bias32, slope, dst); break;
-    default: epilogue_store32<DCV_ACT_NONE>(v, bias32, slope, dst); break;
+    case DCV_ACT_RELU: epilogue_store32<DCV_ACT_RELU, STATS>(v, bias32, slope, dst, valid, run); break;
+    case DCV_ACT_LEAKY_RELU: epilogue_store32<DCV_ACT_LEAKY_RELU, STATS>(v, bias32, slope, dst, valid, run); break;
+    case DCV_ACT_SIGMOID: epilogue_store32<DCV_ACT_SIGMOID, STATS>(v, bias32, slope, dst, valid, run); break;
+    default: epilogue_store32<DCV_ACT_NONE, STATS>(v, bias32, slope, dst, valid, run); break;
   }
 }
+
+// Running channel totals of one epilogue warp over every tile the CTA has finished for output-channel tile nt; `flush` adds them to stats[k][2] (one
+// global atomic per value) when nt changes and at the end. N_TILE >= 128: lane l holds {sum, sum of squares} of channel 32 * chunk + l (per-tile
+// butterfly). N_TILE = 64: every thread holds the 2 x 32 partial sums of its own pixel row per chunk (128 registers) and the butterfly runs in flush.
+constexpr int kMaxStatChannels = 512;
+template <int N_TILE, int MODE_ = 1> struct RunStats {
+  static constexpr int MODE = MODE_, PER = MODE == 2 ? 64 : 2;
+  float v[N_TILE / 32][PER];
+  int nt;
+  __device__ __forceinline__ void reset(int nt_) {
+    nt = nt_;
+#pragma unroll
+    for (int i = 0; i < N_TILE / 32; ++i)
+#pragma unroll
+      for (int j = 0; j < PER; ++j) v[i][j] = 0.f;
+  }
+  __device__ __forceinline__ void flush(float* stats) {
+    if (nt < 0) return;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < N_TILE / 32; ++i) {
+      const float s1 = MODE == 2 ? warp_colsum32(v[i]) : v[i][0];
+      const float s2 = MODE == 2 ? warp_colsum32(v[i] + 32) : v[i][1];
+      atomicAdd(stats + 2 * (nt * N_TILE + 32 * i + lane), s1);
+      atomicAdd(stats + 2 * (nt * N_TILE + 32 * i + lane) + 1, s2);
+    }
+  }
+};
 
 struct FwdParams {
   int n, h, w, c, k, r, s, pad_h, pad_w, p, q;
@@ -156,6 +232,7 @@ struct FwdParams {
   int act; float slope;
   const float* bias;
   __nv_bfloat16* y;
+  float* stats;   // non-null: per-channel {sum, sum of squares} of y are added to stats[k][2] by the epilogue (k <= kMaxStatChannels)
 };
 
 // A pipeline stage holds G consecutive k-blocks (G A slabs + G B slabs) behind ONE full/empty barrier pair: with 64 output channels a k-block is only
@@ -193,7 +270,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
   const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
   const uint32_t bres = bars + 8u * (2 * kStages + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
@@ -285,8 +361,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
     const int row = quarter * 32 + lane;
     const int wl = row % prm.tw, hl = (row / prm.tw) % prm.th, nl = row / (prm.tw * prm.th);
     int as = 0; uint32_t aphase = 0;
+    const bool stats = prm.stats != nullptr;
+    RunStats<N_TILE> run; run.reset(-1);
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
       const int nt = tile % prm.n_tiles_k;
+      if (stats && nt != run.nt) { run.flush(prm.stats); run.reset(nt); }
       int pt = tile / prm.n_tiles_k;
       const int pw = pt % prm.tiles_w; pt /= prm.tiles_w;
       const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
@@ -296,17 +375,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_kernel(const __grid_c
       mbar_wait(tfull(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+#pragma unroll
+      for (int ci = 0; ci < N_TILE / 32; ++ci) {
+        const int c0 = 32 * ci;
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
-        if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + nt * N_TILE + c0 : nullptr, prm.slope, dst + c0);
+        if (stats) epilogue_store32_dyn<RunStats<N_TILE>::MODE>(prm.act, v, prm.bias ? prm.bias + nt * N_TILE + c0 : nullptr, prm.slope, dst + c0, valid, run.v[ci]);
+        else epilogue_store32_dyn<0>(prm.act, v, prm.bias ? prm.bias + nt * N_TILE + c0 : nullptr, prm.slope, dst + c0, valid, nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (stats) run.flush(prm.stats);
   }
   tc_fence_before();
   __syncthreads();
@@ -333,6 +415,7 @@ struct FwdHaloParams {
   int act; float slope;
   const float* bias;
   __nv_bfloat16* y;
+  float* stats;   // as FwdParams::stats
 };
 
 constexpr int HALO_TW = 8, HALO_STAGE_BYTES = 23 * 1024;   // (16 + 2) x (8 + 2) rows x 128 B = 23040, rounded up to the 1024-byte swizzle period
@@ -431,6 +514,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_halo_kernel(const __g
     const int row = quarter * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
     int as = 0; uint32_t aphase = 0;
+    const bool stats = prm.stats != nullptr;
+    typedef RunStats<N_TILE, N_TILE == 64 ? 2 : 1> RS;   // 64 channels: a tile's MMAs are too short to hide a per-tile butterfly
+    RS run; run.reset(0);
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
       int q0, p0, img; decode(tile, q0, p0, img);
       const int q = q0 + xl, p = p0 + yl;
@@ -439,17 +525,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_tc_halo_kernel(const __g
       mbar_wait(tfull(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+#pragma unroll
+      for (int ci = 0; ci < N_TILE / 32; ++ci) {
+        const int c0 = 32 * ci;
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
-        if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0);
+        if (stats) epilogue_store32_dyn<RS::MODE>(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0, valid, run.v[ci]);
+        else epilogue_store32_dyn<0>(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0, valid, nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (stats) run.flush(prm.stats);
   }
   tc_fence_before();
   __syncthreads();
@@ -478,6 +567,7 @@ struct GatherParams {
   const float* bias;
   const __nv_bfloat16* x;
   __nv_bfloat16* y;
+  float* stats;   // as FwdParams::stats
 };
 constexpr int GA_THREADS = 448, GA_STAGES = 2, GA_FWD_STAGES = 3, GA_PRODUCERS = 256, GA_ROW_BUFS = 3;   // warps: 0 weights (TMA), 1 MMA, 2..5 epilogue, 6..13 producers
 
@@ -628,6 +718,8 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int as = 0; uint32_t aphase = 0;
+    const bool stats = prm.stats != nullptr;
+    RunStats<N_TILE> run; run.reset(0);
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
       int q0, op, img; decode(tile, q0, op, img);
       const int q = q0 + row;
@@ -636,17 +728,20 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_fwd_tc_gather_kernel(const
       mbar_wait_relaxed(tfull(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+#pragma unroll
+      for (int ci = 0; ci < N_TILE / 32; ++ci) {
+        const int c0 = 32 * ci;
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
-        if (valid) epilogue_store32_dyn(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0);
+        if (stats) epilogue_store32_dyn<RunStats<N_TILE>::MODE>(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0, valid, run.v[ci]);
+        else epilogue_store32_dyn<0>(prm.act, v, prm.bias ? prm.bias + c0 : nullptr, prm.slope, dst + c0, valid, nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (stats) run.flush(prm.stats);
   } else {
     // ===== producer warps 6..13
     const int pw = warp - (GA_THREADS - GA_PRODUCERS) / 32;
@@ -916,7 +1011,7 @@ static int launch_fwd_halo(const CUtensorMap& mx, const CUtensorMap& mw, const F
   return 0;
 }
 
-static int conv_fwd_tc_halo(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, int act, float slope, cudaStream_t st) {
+static int conv_fwd_tc_halo(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, int act, float slope, float* stats, cudaStream_t st) {
   FwdHaloParams prm{};
   prm.n = s->n; prm.c = s->c; prm.k = s->k; prm.r = s->r; prm.s = s->s; prm.pad_h = s->pad_h; prm.pad_w = s->pad_w; prm.p = s->p; prm.q = s->q;
   prm.tiles_h = (s->p + 15) / 16;
@@ -925,7 +1020,7 @@ static int conv_fwd_tc_halo(const dcv_conv_shape* s, const void* x, const void* 
   const long long tiles = (long long)s->n * prm.tiles_h * prm.tiles_w;
   DCV_REQUIRE(tiles < (1ll << 31), "conv2d_fwd (tcgen05): too many tiles");
   prm.total_tiles = (int)tiles;
-  prm.act = act; prm.slope = slope; prm.bias = bias; prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+  prm.act = act; prm.slope = slope; prm.bias = bias; prm.y = reinterpret_cast<__nv_bfloat16*>(y); prm.stats = stats;
   const size_t res_bytes = (size_t)s->r * s->s * (s->c / BLOCK_K) * s->k * BLOCK_K * 2;
   int stages = (int)((227 * 1024 - 1024 - 256 - res_bytes) / HALO_STAGE_BYTES);
   if (stages > 8) stages = 8;
@@ -980,12 +1075,14 @@ bool conv_fwd_tc_gather_supported(const dcv_conv_shape* s, const void* x, int kp
 }
 
 // w_col: [K][kpad] bf16, columns (r, s, c) of the [K][R][S][C] weights followed by zeros.
-int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, cudaStream_t st) {
+int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, bool channel_totals, cudaStream_t st) {
   using namespace tc;
   DCV_REQUIRE(x && w_col && y, "conv2d_fwd_gather: null pointer");
   GatherParams prm{}; size_t smem = 0;
   DCV_REQUIRE(gather_geometry(s, x, kpad, &prm, &smem, s->k * BLOCK_K * 2), "conv2d_fwd_gather: shape not supported (see dcv_conv2d_gather_supported)");
   prm.act = act; prm.slope = slope; prm.bias = bias; prm.x = reinterpret_cast<const __nv_bfloat16*>(x); prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+  const bool fused_stats = stats_nc && channel_totals;   // per-channel totals in the epilogue, credited to image 0 of stats_nc[n][k][2] (rows of the other images stay zero)
+  prm.stats = fused_stats ? stats_nc : nullptr;
   CUtensorMap mw;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)s->k};
@@ -1006,7 +1103,7 @@ int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col
     kern<<<grid, GA_THREADS, smem, st>>>(mw, prm);
   }
   DCV_LAUNCH_CHECK("conv_fwd_tc_gather_kernel");
-  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
+  if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
   return 0;
 }
 
@@ -1046,13 +1143,16 @@ bool conv_tc_fwd_supported(const dcv_conv_shape* s, int dtype) {
   return tc::encode_tiled() != nullptr;
 }
 
-int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, float* stats_nc, int act, float slope, cudaStream_t st) {
+int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, float* stats_nc, int act, float slope, bool channel_totals, cudaStream_t st) {
   using namespace tc;
   DCV_REQUIRE(x && w && y, "conv2d_fwd (tcgen05): null pointer");
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0), "conv2d_fwd (tcgen05): pointers must be 16-byte aligned");
+  // BatchNorm-only blocks need per-CHANNEL totals only: the epilogue produces them (credited to image 0 of stats_nc[n][k][2]; the rows of the other
+  // images stay zero). A GroupNorm / InstanceNorm needs per-(image, channel) sums: pixel tiles span images, so those come from the statistics kernel.
+  const bool fused_stats = stats_nc && channel_totals && s->k <= kMaxStatChannels;
   if (fwd_halo_applicable(s)) {
-    if (conv_fwd_tc_halo(s, x, w, bias, y, act, slope, st)) return 1;
-    if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
+    if (conv_fwd_tc_halo(s, x, w, bias, y, act, slope, fused_stats ? stats_nc : nullptr, st)) return 1;
+    if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
     return 0;
   }
   FwdParams prm{};
@@ -1065,6 +1165,7 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   DCV_REQUIRE(tiles < (1ll << 31), "conv2d_fwd (tcgen05): too many tiles");
   prm.total_tiles = (int)tiles;
   prm.act = act; prm.slope = slope; prm.bias = bias; prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+  prm.stats = fused_stats ? stats_nc : nullptr;
 
   CUtensorMap mx, mw;
   {
@@ -1085,7 +1186,7 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   else if (prm.n_tiles_k == 1 && s->r * s->s * (s->c / BLOCK_K) <= kMaxResidentKb && getenv("DCV_TC_NO_RESIDENT") == nullptr) rc = launch_fwd<64, 1>(mx, mw, prm, st);
   else rc = launch_fwd<64>(mx, mw, prm, st);
   if (rc) return rc;
-  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
+  if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
   return 0;
 }
 

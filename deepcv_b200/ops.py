@@ -248,6 +248,11 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
     return (sctx or _NO_CTX).acc_empty(shape, device)
 
 
+# DCV_FUSED_STATS=1: BatchNorm-only blocks take their batch statistics from the tcgen05 epilogue (DCV_STATS_CHANNEL_TOTALS) instead of a statistics pass
+# over y. Built, bit-exact (tests/test_gpu_exact.py) and OFF by default: measured on the ImageNet-shaped step (B200, round 2) it removes 18 launches /
+# 0.45 ms of statistics kernels but lengthens the convolution epilogues — which are on these kernels' critical path — by more: 7.05 -> 7.22 ms
+# (64-channel halo kernel 77 -> 90 us with per-thread partial sums, 128 / 256-channel kernels 60 -> 90 us with a per-tile butterfly, stem 402 -> 594 us).
+_FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
 
 
@@ -302,6 +307,8 @@ class _ConvBlock(torch.autograd.Function):
         w_op = _weight_operand(weight, x.dtype, sctx)
         y = empty_nhwc(n, k, p, q, x.dtype, dev)
         stats = _acc_empty((n, k, 2), dev, sctx) if cfg.any else None
+        # BatchNorm alone needs per-channel totals only: the tcgen05 kernels then produce the statistics in their epilogue (DCV_STATS_CHANNEL_TOTALS)
+        totals = 2 if (cfg.use_bn and not cfg.use_gn and _FUSE_STATS) else 0
         # Convolutions the implicit-GEMM tensor-core kernel cannot address directly (few input channels / strides: the 7x7 stride-2 stem) go
         # through an explicit im2col: conv(x, w) == 1x1 conv of col[n][p][q][kpad] with the weights zero-padded to [K][kpad].
         rsc = shape.r * shape.s * shape.c
@@ -322,7 +329,7 @@ class _ConvBlock(torch.autograd.Function):
             if gathered:
                 w_col = torch.empty((k, kpad_g), dtype=x.dtype, device=dev)
                 check(lib.dcv_gather_pack_weight(_ptr(w_op), _ptr(w_col), k, shape.r, sc, kpad_g, dt, st), 'gather_pack_weight')
-                check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), _ptr(x), _ptr(w_col), kpad_g, _ptr(bias), _ptr(y), _ptr(stats), act, slope, pz, st), 'conv2d_fwd_gather')
+                check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), _ptr(x), _ptr(w_col), kpad_g, _ptr(bias), _ptr(y), _ptr(stats), act, slope, pz | totals, st), 'conv2d_fwd_gather')
             else:
                 w_col = torch.empty((k, kpad), dtype=x.dtype, device=dev)
                 check(lib.dcv_fill_zero(_ptr(w_col), w_col.numel() * w_col.element_size(), st), 'fill_zero')
@@ -332,7 +339,7 @@ class _ConvBlock(torch.autograd.Function):
                 check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz, st), 'conv2d_fwd(im2col)')
                 x = col   # what the weight gradient needs; the data gradient only needs dy and the weights
         else:
-            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz, st), 'conv2d_fwd')
+            check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz | totals, st), 'conv2d_fwd')
         saved = None
         out = y
         if cfg.any:

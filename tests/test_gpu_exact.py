@@ -49,6 +49,27 @@ def _assert_equal(got, ref, what):
     assert not bool(bad.any()), f'{what}: {int(bad.sum())} of {bad.numel()} values differ (max |diff| {float((got - ref).abs().max())}, first at {tuple(bad.nonzero()[0].tolist())})'
 
 
+def _check_epilogue_statistics(run, yd, y_ref, n, k, dev):
+    """ BatchNorm statistics of the tcgen05 forward kernels. Flag 0: per-(image, channel) sums of the stored values (statistics kernel behind the
+    convolution). DCV_STATS_CHANNEL_TOTALS (2): the epilogue produces per-CHANNEL totals, credited to image 0 (rows of the other images stay zero) —
+    what a BatchNorm-only block needs. Sums of integers are exact in fp32 (< 2^24); the squares may exceed that: 1e-6 relative. Same output tensor. """
+    yb = y_ref.detach().bfloat16().float()
+    for flags in (0, 2):
+        stats = torch.full((n, k, 2), 7., device=dev)
+        yd2 = torch.full_like(yd, 7.)
+        run(yd2, stats, flags)
+        assert torch.equal(yd2, yd), f'forward output changed with statistics flags {flags}'
+        st_ = stats.cpu()
+        if flags == 0:
+            s1, s2, r1, r2 = st_[..., 0], st_[..., 1], yb.sum((2, 3)), (yb * yb).sum((2, 3))
+        else:
+            assert float(st_[1:].abs().max()) == 0. if n > 1 else True, 'channel totals must be credited to image 0 only'
+            s1, s2, r1, r2 = st_[0, :, 0], st_[0, :, 1], yb.sum((0, 2, 3)), (yb.double() * yb.double()).sum((0, 2, 3)).float()
+        if float(r1.abs().max()) < 2 ** 24:
+            _assert_equal(s1, r1, f'sum y (flags {flags})')
+        assert float((s2.double() - r2.double()).abs().max()) <= 1e-6 * float(r2.abs().max()) + 1e-3, f'sum y^2 (flags {flags})'
+
+
 # n, c, h, w, k, ksize, pad — stride 1: the TMA-fed kernels
 TC_EXACT = [
     (3, 64, 56, 56, 64, 3, 1),      # halo variant (resident weights, one box per tile), 4 launches per C4 step forward, 4 more as data gradient
@@ -93,6 +114,8 @@ def test_tcgen05_forward_dgrad_wgrad_bit_exact(dev, n, c, h, w, k, ks, pad, act)
     yd = torch.full((n, p, q, k), 7., device=dev, dtype=torch.bfloat16)
     check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xd), P(wd), P(bd), P(yd), None, ACT_RELU if act == 'relu' else ACT_NONE, 0., DCV_BF16, ALGO_TCGEN05, 0, st), 'conv2d_fwd')
     _assert_equal(yd.permute(0, 3, 1, 2), y_ref.detach().bfloat16(), 'forward')
+    _check_epilogue_statistics(lambda yd2, stats, flags: check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xd), P(wd), P(bd), P(yd2), P(stats), ACT_RELU if act == 'relu' else ACT_NONE, 0.,
+                                                                                 DCV_BF16, ALGO_TCGEN05, flags, st), 'conv2d_fwd'), yd, y_ref, n, k, dev)
     if act == 'relu':
         return   # the backward kernels do not depend on the activation
     # ---- data and weight gradients of the linear convolution
@@ -143,6 +166,8 @@ def test_gather_forward_wgrad_bit_exact(dev, n, c, h, w, k, ks, stride, pad):
     bd = bias.to(dev)
     check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), P(xd), P(w_col), kpad, P(bd), P(yd), None, ACT_NONE, 0., 0, st), 'conv2d_fwd_gather')
     _assert_equal(yd.permute(0, 3, 1, 2), y_ref.detach().bfloat16(), 'gather forward')
+    _check_epilogue_statistics(lambda yd2, stats, flags: check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), P(xd), P(w_col), kpad, P(bd), P(yd2), P(stats), ACT_NONE, 0., flags, st),
+                                                               'conv2d_fwd_gather'), yd, y_ref, n, k, dev)
     dw_col = torch.full((k, kpad), 7., device=dev)
     check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), P(xd), P(dyd), P(dw_col), kpad, 0, st), 'conv2d_wgrad_gather')
     dwd = torch.full((k, ks, ks, c), 7., device=dev)
