@@ -11,7 +11,7 @@ from pathlib import Path
 __all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
            'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DCV_F32, DCV_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_SIGMOID = 0, 1, 2, 3
 ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05 = 0, 1, 2
@@ -89,8 +89,9 @@ SYMBOLS = {
     'dcv_copy_channels_out': (c_int, [P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
     'dcv_bilinear_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_bilinear_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    'dcv_linear_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
-    'dcv_linear_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),
+    'dcv_linear_flatten_fused': (c_int, [c_int, c_int]),
+    'dcv_linear_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),
+    'dcv_linear_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, P]),
     'dcv_softmax_ce': (c_int, [P, P, P, P, c_int, c_int, P]),
     'dcv_classification_metrics': (c_int, [P, P, P, c_int, c_int, P]),
     'dcv_scale_by_device_scalar': (c_int, [P, P, P, c_size_t, P]),

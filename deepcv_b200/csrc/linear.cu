@@ -116,137 +116,209 @@ __global__ void linear_dpre_kernel(const void* __restrict__ y, const void* __res
 }
 
 
-// ---- "skinny" head: n <= 32 output features (the 1280 -> 10 classifier of the default net). The generic 64x64 tile above would launch a
-// handful of CTAs; here a warp owns a row of x and keeps all n accumulators in registers (forward / dx), and the weight gradient is a
-// split-M reduction with one thread per input feature.
+// ---- "skinny" head: n <= 32 output features (the 1280 -> 10 classifier of the default net) --------------------------------------------------------
+// 13 MFLOP: pure latency. One CTA per row of x for forward / dx (512 CTAs of 4 warps: every SM holds several rows, all loads of a thread are
+// independent), 4 rows per CTA for the weight gradient; the row(s) of x are staged in shared memory with 16-byte loads first.
+// `torch.nn.Flatten` fused in (x_c > 0): x is then the NHWC image tensor [m][hw][x_c] itself and feature f = c * hw + p (the (C, H, W) order Flatten
+// gives the logical N x C x H x W tensor, reference conf/base/parameters.yml:87) is element p * x_c + c of its row — the kernels walk f (contiguous in
+// the weight matrix) and read / write x through that index map in shared memory: no transposed copy of the activations in either direction.
 template <typename TX> __device__ __forceinline__ float ldx(const TX* p, size_t i) { return to_f<TX>(p[i]); }
+constexpr int kSkinnyThreads = 128;
+
+struct FlatMap {   // feature index (weight order) -> element of the row of x
+  int x_c, hw;
+  __device__ __forceinline__ int operator()(int f) const {
+    if (x_c <= 0) return f;
+    const int c = f / hw, p = f - c * hw;
+    return p * x_c + c;
+  }
+};
+
+// Row `row` of x (k elements) -> shared memory as fp32, in x's own element order. 16-byte loads when the row is aligned.
+template <typename TX> __device__ __forceinline__ void stage_row(const TX* __restrict__ xr, float* xs, int k, int tid, int nthr) {
+  constexpr int V = 16 / sizeof(TX);
+  if ((reinterpret_cast<uintptr_t>(xr) & 15) == 0 && k % V == 0) {
+    for (int v = tid; v < k / V; v += nthr) {
+      float f[V];
+      vec_unpack<TX>(*reinterpret_cast<const uint4*>(xr + (size_t)v * V), f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) xs[v * V + i] = f[i];
+    }
+  } else {
+    for (int i = tid; i < k; i += nthr) xs[i] = ldx<TX>(xr, i);
+  }
+}
 
 template <int NB, typename TX>
-__global__ void __launch_bounds__(256) linear_skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
-                                                                int m, int n, int k, int act, float slope) {
-  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= m) return;
+__global__ void __launch_bounds__(kSkinnyThreads) linear_skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                                                                           int m, int n, int k, int act, float slope, FlatMap map) {
+  extern __shared__ float sh[];   // [k] row of x, then [warps][NB] partial sums
+  float* xs = sh;
+  float* part = sh + k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row = blockIdx.x;
+  stage_row<TX>(x + (size_t)row * k, xs, k, tid, kSkinnyThreads);
+  __syncthreads();
   float acc[NB];
 #pragma unroll
   for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-  const TX* xr = x + (size_t)row * k;
-  int kk = lane;
-  for (; kk + 96 < k; kk += 128) {   // 4 independent k positions per lane and iteration: loads of all four are in flight together
+  for (int f0 = tid; f0 < k; f0 += 4 * kSkinnyThreads) {   // 4 independent feature positions per thread and iteration
     float xv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xv[u] = ldx<TX>(xr, kk + 32 * u);
+    for (int u = 0; u < 4; ++u) { const int f = f0 + u * kSkinnyThreads; xv[u] = f < k ? xs[map(f)] : 0.f; }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       if (j < n) {
         float wv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) wv[u] = __ldg(w + (size_t)j * k + kk + 32 * u);
+        for (int u = 0; u < 4; ++u) { const int f = f0 + u * kSkinnyThreads; wv[u] = f < k ? __ldg(w + (size_t)j * k + f) : 0.f; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc[j] = fmaf(xv[u], wv[u], acc[j]);
       }
     }
   }
-  for (; kk < k; kk += 32) {
-    const float xv = ldx<TX>(xr, kk);
 #pragma unroll
-    for (int j = 0; j < NB; ++j) if (j < n) acc[j] = fmaf(xv, w[(size_t)j * k + kk], acc[j]);
+  for (int j = 0; j < NB; ++j) {
+    acc[j] = warp_sum(acc[j]);
+    if (lane == 0) part[warp * NB + j] = acc[j];
   }
-#pragma unroll
-  for (int j = 0; j < NB; ++j) acc[j] = warp_sum(acc[j]);
-  if (lane < n) {
-    float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) if (j == lane) v = acc[j];
-    v += bias ? bias[lane] : 0.f;
-    y[(size_t)row * n + lane] = act_apply(v, act, slope);
+  __syncthreads();
+  if (tid < n) {
+    float v = bias ? bias[tid] : 0.f;
+    for (int wq = 0; wq < kSkinnyThreads / 32; ++wq) v += part[wq * NB + tid];
+    y[(size_t)row * n + tid] = act_apply(v, act, slope);
   }
 }
 
 // dpre[row][j] = act'(y)*dy (written to dpre_ws) and dx[row][:] = dpre[row][:] @ w
 template <int NB, typename TX>
-__global__ void __launch_bounds__(256) linear_skinny_dx_kernel(const float* __restrict__ w, const float* __restrict__ y, const float* __restrict__ dy, TX* __restrict__ dx,
-                                                               float* __restrict__ dpre_ws, int m, int n, int k, int act, float slope) {
-  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= m) return;
-  float mine = 0.f;
-  if (lane < n) {
-    const size_t i = (size_t)row * n + lane;
-    mine = dy[i] * act_grad_from_output(y[i], act, slope);
-    dpre_ws[i] = mine;
+__global__ void __launch_bounds__(kSkinnyThreads) linear_skinny_dx_kernel(const float* __restrict__ w, const float* __restrict__ y, const float* __restrict__ dy, TX* __restrict__ dx,
+                                                                          float* __restrict__ dpre_ws, int m, int n, int k, int act, float slope, FlatMap map) {
+  extern __shared__ float sh[];   // [k] row of dx in x's element order, then [NB] dpre of the row
+  float* dxs = sh;
+  float* d = sh + k;
+  const int tid = threadIdx.x, row = blockIdx.x;
+  if (tid < NB) {
+    float mine = 0.f;
+    if (tid < n) {
+      const size_t i = (size_t)row * n + tid;
+      mine = dy[i] * act_grad_from_output(y[i], act, slope);
+      dpre_ws[i] = mine;
+    }
+    d[tid] = mine;
   }
-  float d[NB];
-#pragma unroll
-  for (int j = 0; j < NB; ++j) d[j] = __shfl_sync(0xffffffffu, mine, j);
+  __syncthreads();
   if (!dx) return;
-  TX* dxr = dx + (size_t)row * k;
-  int kk = lane;
-  for (; kk + 96 < k; kk += 128) {
+  float dj[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) dj[j] = d[j];
+  for (int f0 = tid; f0 < k; f0 += 4 * kSkinnyThreads) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       if (j < n) {
         float wv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) wv[u] = __ldg(w + (size_t)j * k + kk + 32 * u);
+        for (int u = 0; u < 4; ++u) { const int f = f0 + u * kSkinnyThreads; wv[u] = f < k ? __ldg(w + (size_t)j * k + f) : 0.f; }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = fmaf(d[j], wv[u], v[u]);
+        for (int u = 0; u < 4; ++u) v[u] = fmaf(dj[j], wv[u], v[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) dxr[kk + 32 * u] = from_f<TX>(v[u]);
+    for (int u = 0; u < 4; ++u) { const int f = f0 + u * kSkinnyThreads; if (f < k) dxs[map(f)] = v[u]; }
   }
-  for (; kk < k; kk += 32) {
-    float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) if (j < n) v = fmaf(d[j], w[(size_t)j * k + kk], v);
-    dxr[kk] = from_f<TX>(v);
-  }
-}
-
-// dw[j][kk] += sum over a chunk of rows of dpre[r][j] * x[r][kk]; db[j] += sum dpre[r][j]   (dw, db zeroed by the wrapper)
-template <int NB, typename TX>
-__global__ void __launch_bounds__(256) linear_skinny_dw_kernel(const TX* __restrict__ x, const float* __restrict__ dpre, float* __restrict__ dw, float* __restrict__ db,
-                                                               int m, int n, int k, int rows_per_cta) {
-  __shared__ float s_d[64 * NB];
-  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, m);
-  for (int i = threadIdx.x; i < (r1 - r0) * n; i += blockDim.x) s_d[(i / n) * NB + i % n] = dpre[(size_t)r0 * n + i];
   __syncthreads();
-  float acc[NB];
-#pragma unroll
-  for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-  if (kk < k) {
-    for (int r = r0; r < r1; ++r) {
-      const float xv = ldx<TX>(x, (size_t)r * k + kk);
-#pragma unroll
-      for (int j = 0; j < NB; ++j) if (j < n) acc[j] = fmaf(s_d[(r - r0) * NB + j], xv, acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) if (j < n) atomicAdd(dw + (size_t)j * k + kk, acc[j]);
-  }
-  if (db && blockIdx.x == 0 && threadIdx.x < n) {
-    float sd = 0.f;
-    for (int r = r0; r < r1; ++r) sd += s_d[(r - r0) * NB + threadIdx.x];
-    atomicAdd(db + threadIdx.x, sd);
+  TX* dxr = dx + (size_t)row * k;
+  constexpr int V = 16 / sizeof(TX);
+  if ((reinterpret_cast<uintptr_t>(dxr) & 15) == 0 && k % V == 0) {
+    for (int v = tid; v < k / V; v += kSkinnyThreads) *reinterpret_cast<uint4*>(dxr + (size_t)v * V) = vec_pack<TX>(dxs + v * V);
+  } else {
+    for (int i = tid; i < k; i += kSkinnyThreads) dxr[i] = from_f<TX>(dxs[i]);
   }
 }
 
+// dw[j][f] += sum over the CTA's rows of dpre[r][j] * x[r][f]; db[j] += sum dpre[r][j]   (dw, db zeroed by the wrapper / the caller)
+constexpr int kDwRows = 4, kDwThreads = 256, kDwPer = 5;   // features per thread: covers k <= 1280 in one CTA column, more through blockIdx.x
 template <int NB, typename TX>
-static int skinny_fwd(const void* x, const float* w, const float* bias, float* y, int m, int n, int k, int act, float slope, cudaStream_t st) {
-  linear_skinny_fwd_kernel<NB, TX><<<(m + 3) / 4, 128, 0, st>>>((const TX*)x, w, bias, y, m, n, k, act, slope);
+__global__ void __launch_bounds__(kDwThreads) linear_skinny_dw_kernel(const TX* __restrict__ x, const float* __restrict__ dpre, float* __restrict__ dw, float* __restrict__ db,
+                                                                      int m, int n, int k, FlatMap map) {
+  extern __shared__ float sh[];   // [kDwRows][k] rows of x, then [kDwRows][NB] dpre
+  float* xs = sh;
+  float* s_d = sh + (size_t)kDwRows * k;
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.y * kDwRows, rows = min(kDwRows, m - r0);
+  for (int r = 0; r < rows; ++r) stage_row<TX>(x + (size_t)(r0 + r) * k, xs + (size_t)r * k, k, tid, kDwThreads);
+  for (int i = tid; i < kDwRows * NB; i += kDwThreads) { const int r = i / NB, j = i - r * NB; s_d[i] = (r < rows && j < n) ? dpre[(size_t)(r0 + r) * n + j] : 0.f; }
+  __syncthreads();
+  const int fbase = blockIdx.x * kDwThreads * kDwPer + tid;
+  float acc[kDwPer][NB];
+#pragma unroll
+  for (int i = 0; i < kDwPer; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j] = 0.f;
+  int e[kDwPer];
+#pragma unroll
+  for (int i = 0; i < kDwPer; ++i) { const int f = fbase + i * kDwThreads; e[i] = f < k ? map(f) : 0; }
+  for (int r = 0; r < rows; ++r) {
+    float xv[kDwPer];
+#pragma unroll
+    for (int i = 0; i < kDwPer; ++i) xv[i] = xs[(size_t)r * k + e[i]];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float dv = s_d[r * NB + j];
+#pragma unroll
+      for (int i = 0; i < kDwPer; ++i) acc[i][j] = fmaf(dv, xv[i], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kDwPer; ++i) {
+    const int f = fbase + i * kDwThreads;
+    if (f < k) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) if (j < n) atomicAdd(dw + (size_t)j * k + f, acc[i][j]);
+    }
+  }
+  if (db && blockIdx.x == 0 && tid < n) {
+    float sd = 0.f;
+    for (int r = 0; r < rows; ++r) sd += s_d[r * NB + tid];
+    atomicAdd(db + tid, sd);
+  }
+}
+
+static bool skinny_fits(int n, int k) { return n <= 32 && (size_t)kDwRows * k * 4 + 1024 <= 160 * 1024; }
+
+template <int NB, typename TX>
+static int skinny_fwd(const void* x, const float* w, const float* bias, float* y, int m, int n, int k, int act, float slope, FlatMap map, cudaStream_t st) {
+  const size_t smem = ((size_t)k + (kSkinnyThreads / 32) * NB) * 4;
+  auto kern = linear_skinny_fwd_kernel<NB, TX>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<m, kSkinnyThreads, smem, st>>>((const TX*)x, w, bias, y, m, n, k, act, slope, map);
   DCV_LAUNCH_CHECK("linear_skinny_fwd_kernel");
   return 0;
 }
 
 template <int NB, typename TX>
-static int skinny_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, float* db, float* dpre, int m, int n, int k, int act, float slope, bool prezeroed, cudaStream_t st) {
-  linear_skinny_dx_kernel<NB, TX><<<(m + 3) / 4, 128, 0, st>>>(w, y, dy, (TX*)dx, dpre, m, n, k, act, slope);
-  DCV_LAUNCH_CHECK("linear_skinny_dx_kernel");
-  if (dw) {
+static int skinny_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, float* db, float* dpre, int m, int n, int k, int act, float slope,
+                      bool prezeroed, FlatMap map, cudaStream_t st) {
+  {
+    const size_t smem = ((size_t)k + NB) * 4;
+    auto kern = linear_skinny_dx_kernel<NB, TX>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<m, kSkinnyThreads, smem, st>>>(w, y, dy, (TX*)dx, dpre, m, n, k, act, slope, map);
+    DCV_LAUNCH_CHECK("linear_skinny_dx_kernel");
+  }
+  if (dw || db) {
     zero_accumulator(dw, (size_t)n * k * sizeof(float), st, prezeroed);
-    const int rows = 32;
-    linear_skinny_dw_kernel<NB, TX><<<dim3((k + 255) / 256, (m + rows - 1) / rows), 256, 0, st>>>((const TX*)x, dpre, dw, db, m, n, k, rows);
-    DCV_LAUNCH_CHECK("linear_skinny_dw_kernel");
+    const size_t smem = ((size_t)kDwRows * k + kDwRows * NB) * 4;
+    auto kern = linear_skinny_dw_kernel<NB, TX>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (dw) {
+      kern<<<dim3((k + kDwThreads * kDwPer - 1) / (kDwThreads * kDwPer), (m + kDwRows - 1) / kDwRows), kDwThreads, smem, st>>>((const TX*)x, dpre, dw, db, m, n, k, map);
+      DCV_LAUNCH_CHECK("linear_skinny_dw_kernel");
+    } else {   // frozen weight, trainable bias: the bias gradient alone
+      int gy = (m + 31) / 32; if (gy > 64) gy = 64;
+      linear_dpre_kernel<<<dim3((n + 127) / 128, gy), 128, 0, st>>>(y, dy, dpre, db, m, n, act, slope, DCV_F32);
+      DCV_LAUNCH_CHECK("linear_dpre_kernel");
+    }
   }
   return 0;
 }
@@ -255,16 +327,21 @@ static int skinny_bwd(const void* x, const float* w, const float* y, const float
 
 extern "C" {
 
+int dcv_linear_flatten_fused(int n, int k) { return dcv::skinny_fits(n, k) ? 1 : 0; }
+
 int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, int m, int n, int k, int act, float slope,
-                   int x_dtype, int y_dtype, void* stream) {
+                   int x_dtype, int y_dtype, int x_nhwc_channels, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(x && w && y && m > 0 && n > 0 && k > 0, "linear_fwd: bad arguments");
-  if (n <= 32 && y_dtype == DCV_F32) {
+  DCV_REQUIRE(x_nhwc_channels == 0 || (x_nhwc_channels > 0 && k % x_nhwc_channels == 0 && skinny_fits(n, k) && y_dtype == DCV_F32),
+              "linear_fwd: fused Flatten (x_nhwc_channels = %d) needs n <= 32 output features and k a multiple of the channel count (see dcv_linear_flatten_fused)", x_nhwc_channels);
+  const FlatMap map{x_nhwc_channels, x_nhwc_channels > 0 ? k / x_nhwc_channels : 0};
+  if (skinny_fits(n, k) && y_dtype == DCV_F32) {
     cudaStream_t st = as_stream(stream);
     DCV_DISPATCH_DTYPE(x_dtype, TX, {
-      if (n <= 8) return skinny_fwd<8, TX>(x, w, bias, (float*)y, m, n, k, act, slope, st);
-      if (n <= 16) return skinny_fwd<16, TX>(x, w, bias, (float*)y, m, n, k, act, slope, st);
-      return skinny_fwd<32, TX>(x, w, bias, (float*)y, m, n, k, act, slope, st);
+      if (n <= 8) return skinny_fwd<8, TX>(x, w, bias, (float*)y, m, n, k, act, slope, map, st);
+      if (n <= 16) return skinny_fwd<16, TX>(x, w, bias, (float*)y, m, n, k, act, slope, map, st);
+      return skinny_fwd<32, TX>(x, w, bias, (float*)y, m, n, k, act, slope, map, st);
     });
   }
   GemmArgs g{x, w, y, bias, m, n, k, k, 1, 1, k, x_dtype, DCV_F32, y_dtype, act, slope};
@@ -272,16 +349,19 @@ int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, in
 }
 
 int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy, void* dx, float* dw, float* db, float* dpre_ws,
-                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, void* stream) {
+                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, int x_nhwc_channels, void* stream) {
   using namespace dcv;
   DCV_REQUIRE(x && w && y && dy && dpre_ws && m > 0 && n > 0 && k > 0, "linear_bwd: bad arguments");
+  DCV_REQUIRE(x_nhwc_channels == 0 || (x_nhwc_channels > 0 && k % x_nhwc_channels == 0 && skinny_fits(n, k) && y_dtype == DCV_F32),
+              "linear_bwd: fused Flatten (x_nhwc_channels = %d) needs n <= 32 output features and k a multiple of the channel count", x_nhwc_channels);
+  const FlatMap map{x_nhwc_channels, x_nhwc_channels > 0 ? k / x_nhwc_channels : 0};
   cudaStream_t st = as_stream(stream);
   zero_accumulator(db, (size_t)n * sizeof(float), st, acc_prezeroed != 0);
-  if (n <= 32 && y_dtype == DCV_F32) {
+  if (skinny_fits(n, k) && y_dtype == DCV_F32) {
     DCV_DISPATCH_DTYPE(x_dtype, TX, {
-      if (n <= 8) return skinny_bwd<8, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, st);
-      if (n <= 16) return skinny_bwd<16, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, st);
-      return skinny_bwd<32, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, st);
+      if (n <= 8) return skinny_bwd<8, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, map, st);
+      if (n <= 16) return skinny_bwd<16, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, map, st);
+      return skinny_bwd<32, TX>(x, w, (const float*)y, (const float*)dy, dx, dw, db, dpre_ws, m, n, k, act, slope, acc_prezeroed != 0, map, st);
     });
   }
   int gy = (m + 31) / 32; if (gy > 64) gy = 64;

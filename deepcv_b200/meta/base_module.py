@@ -75,11 +75,16 @@ class DeepcvModule(torch.nn.Module):
         for i, (name, subm) in enumerate(zip(names, children)):
             if isinstance(x, ops.PendingAffine) and not getattr(subm, 'accepts_pending_affine', False):
                 x = ops.materialize(x)
+            if isinstance(x, ops.PendingFlatten) and not getattr(subm, 'accepts_pending_flatten', False):
+                x = ops.materialize(x)
             n_referrers = sum(name in r for r in remaining_submodule_references.values())
             kwargs = {}
             if getattr(subm, 'can_defer_affine', False):
                 kwargs['defer_affine'] = not isinstance(x, (list, tuple)) and i + 1 < len(children) and n_referrers == 0 and getattr(children[i + 1], 'accepts_pending_affine', False) \
                     and not getattr(children[i + 1], 'referenced_submodules', None)
+            if getattr(subm, 'can_defer_flatten', False):   # Flatten in front of a small fully connected head: fused into the head's kernels
+                kwargs['defer_flatten'] = not isinstance(x, (list, tuple)) and i + 1 < len(children) and n_referrers == 0 \
+                    and bool(getattr(children[i + 1], 'accepts_pending_flatten', False)) and not getattr(children[i + 1], 'referenced_submodules', None)
             refs = None if sequential else getattr(subm, 'referenced_submodules', None)
             if refs is not None and len(refs) > 0:
                 current_subm_references = OrderedDict([(ref, referenced_output_features[ref]) for ref in refs])

@@ -33,7 +33,7 @@ XAVIER_INIT_SUPPORTED_ACT_FN = {torch.nn.ReLU: 'relu', torch.nn.LeakyReLU: 'leak
 def is_torch_obj(v) -> bool:
     """ reference nn.py:706-709 as intended (the `'_module__'` typo made it always False): a single tensor, not a sequence of
     tensors. A raw block output with a pending normalisation (`ops.PendingAffine`) counts as one tensor. """
-    return isinstance(v, (torch.Tensor, torch.Size, ops.PendingAffine))
+    return isinstance(v, (torch.Tensor, torch.Size, ops.PendingAffine, ops.PendingFlatten))
 
 
 def forward_call_convention_dec(apply_parallel_forward: bool = False, refs_tensor_count_similar: bool = None, in_tensors_count_similar_to_refs: bool = None,
@@ -230,8 +230,12 @@ class Flatten(torch.nn.Flatten):
     """ `torch.nn.Flatten()` of the logical N x C x H x W tensor (features in (C, H, W) order), from NHWC memory. The architecture
     parser substitutes this class wherever a spec names `torch.nn.Flatten`. """
 
+    can_defer_flatten = True   # `defer_flatten=True`: the caller promises a consumer that reads the image tensor through the Flatten index map itself
+
     @forward_call_convention_dec(apply_parallel_forward=True, ignore_sub_refs=True)
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, defer_flatten: bool = False) -> torch.Tensor:
+        if defer_flatten and x.device.type == 'cuda' and x.dim() == 4 and self.start_dim == 1 and self.end_dim in (-1, 3):
+            return ops.PendingFlatten(ops.as_nhwc(x))
         if x.device.type == 'meta' or x.dim() != 4 or self.start_dim != 1 or self.end_dim not in (-1, 3):
             if x.device.type != 'meta' and x.dim() == 4:
                 raise NotImplementedError('deepcv_b200: only `Flatten(start_dim=1, end_dim=-1)` of image tensors is built')
@@ -312,6 +316,7 @@ class FusedLayer(torch.nn.Sequential):
         ow = (x.shape[3] + 2 * p[1] - d[1] * (k[1] - 1) - 1) // s[1] + 1
         return meta_like((x.shape[0], op.out_channels, oh, ow), x.dtype)
 
+    accepts_pending_flatten = property(lambda self: isinstance(self._op, torch.nn.Linear) and not self.preactivation and (self._drop is None or self._drop.p == 0.))
     accepts_pending_affine = True   # few-channel convolutions normalise their input while loading it
     can_defer_affine = True         # ... and may hand their own raw output on (`defer_affine=True`: the caller promises a consumer that accepts it)
 
@@ -332,6 +337,8 @@ class FusedLayer(torch.nn.Sequential):
         if not isinstance(x, ops.PendingAffine) and x.device.type == 'meta':
             return self._meta_forward(x)
         op, bn, gn, drop = self._op, self._bn, self._gn, self._drop
+        if isinstance(x, ops.PendingFlatten) and not self.accepts_pending_flatten:
+            x = ops.materialize(x)
         if drop is not None and drop.training and drop.p != 0.:   # reference nn.py:553: Dropout is the first op of both block orders
             x = ops.materialize(x)
             if self._drop_state is None or self._drop_state.counter.device != x.device:

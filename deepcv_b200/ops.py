@@ -20,7 +20,7 @@ from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, A
 
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext', 'PendingAffine', 'sc_conv_block',
-           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act']
+           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act', 'PendingFlatten']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
 _DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
@@ -794,9 +794,27 @@ def sc_affine_pool(pa: PendingAffine, pool: int) -> torch.Tensor:
     return _ScAffinePool.apply(y, link, int(pool))
 
 
+class PendingFlatten:
+    """ An image tensor (NHWC memory) whose `torch.nn.Flatten` has not been materialised: the fully connected layer that follows reads the NHWC tensor
+    through the (C, H, W)-order index map inside its kernels (`dcv_linear_fwd(..., x_nhwc_channels)`), so the transposed copy — and its mirror in backward
+    — is never made. Only handed to a consumer that declared `accepts_pending_flatten` (`DeepcvModule.forward` decides); `materialize()` otherwise. """
+    __slots__ = ('x',)
+
+    def __init__(self, x: torch.Tensor):
+        self.x = x
+
+    shape = property(lambda self: torch.Size((self.x.shape[0], self.x.shape[1] * self.x.shape[2] * self.x.shape[3])))
+    dtype = property(lambda self: self.x.dtype)
+    device = property(lambda self: self.x.device)
+
+
 def materialize(x):
-    """ `PendingAffine` -> the normalised tensor; tensors pass through. """
-    return sc_affine_pool(x, 1) if isinstance(x, PendingAffine) else x
+    """ `PendingAffine` -> the normalised tensor; `PendingFlatten` -> the flattened (N, C*H*W) tensor; tensors pass through. """
+    if isinstance(x, PendingAffine):
+        return sc_affine_pool(x, 1)
+    if isinstance(x, PendingFlatten):
+        return flatten_nchw(x.x)
+    return x
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -1013,29 +1031,32 @@ def flatten_nchw(x: torch.Tensor) -> torch.Tensor:
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, slope, grad_out, sctx):
+    def forward(ctx, x, weight, bias, act, slope, grad_out, sctx, nhwc_c=0):
         _require_cuda(x, weight)
-        m, k = x.shape
+        ctx.x_shape = tuple(x.shape)
+        m, k = (x.shape[0], x.shape[1] * x.shape[2] * x.shape[3]) if nhwc_c else x.shape   # nhwc_c > 0: x is the NHWC image tensor, Flatten fused into the kernels
         n = weight.shape[0]
         if weight.shape[1] != k:
             raise RuntimeError(f'deepcv_b200: linear layer expects {weight.shape[1]} input features, got {k}')
         w = weight if weight.is_contiguous() else weight.contiguous()
         y = torch.empty((m, n), dtype=torch.float32, device=x.device)
-        check(lib.dcv_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), m, n, k, act, slope, _dt(x), DCV_F32, _stream()), 'linear_fwd')
+        check(lib.dcv_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), m, n, k, act, slope, _dt(x), DCV_F32, nhwc_c, _stream()), 'linear_fwd')
         ctx.save_for_backward(x, w, y)
-        ctx.cfg = (act, slope, bias is not None, grad_out, sctx)
+        ctx.cfg = (act, slope, bias is not None, grad_out, sctx, nhwc_c)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
-        act, slope, has_bias, grad_out, sctx = ctx.cfg
+        act, slope, has_bias, grad_out, sctx, nhwc_c = ctx.cfg
         targets = grad_out if (grad_out and not grad_out.get('_written', False)) else {}
-        m, k = x.shape
+        m, k = (x.shape[0], x.shape[1] * x.shape[2] * x.shape[3]) if nhwc_c else x.shape
         n = w.shape[0]
         dy = _cast_raw(dy.detach().contiguous(), torch.float32)
         f32 = dict(dtype=torch.float32, device=x.device)
-        dx = torch.empty((m, k), dtype=x.dtype, device=x.device) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:   # fused Flatten: the gradient comes back in the NHWC layout of the image tensor
+            dx = empty_nhwc(*x.shape, x.dtype, x.device) if nhwc_c else torch.empty((m, k), dtype=x.dtype, device=x.device)
         dw = targets.get('weight', None) if ctx.needs_input_grad[1] else None
         if dw is None and ctx.needs_input_grad[1]:
             dw = _acc_empty((n, k), x.device, sctx)
@@ -1044,14 +1065,22 @@ class _Linear(torch.autograd.Function):
             db = targets.get('bias', None)
             db = _acc_empty((n,), x.device, sctx) if db is None else db
         dpre = torch.empty((m, n), **f32)
-        check(lib.dcv_linear_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dpre), m, n, k, act, slope, _dt(x), DCV_F32, _pz(sctx), _stream()), 'linear_bwd')
+        check(lib.dcv_linear_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dpre), m, n, k, act, slope, _dt(x), DCV_F32, _pz(sctx), nhwc_c, _stream()), 'linear_bwd')
         _backward_done(grad_out, targets)
-        return dx, (None if 'weight' in targets else dw), (None if ('bias' in targets or not has_bias) else db), None, None, None, None
+        return dx, (None if 'weight' in targets else dw), (None if ('bias' in targets or not has_bias) else db), None, None, None, None, None
 
 
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE, slope: float = 0., grad_out: Optional[dict] = None,
                step_ctx: Optional[StepContext] = None) -> torch.Tensor:
-    """ act(x @ weight.T + bias) with fp32 output (logits / losses stay fp32 whatever the activation dtype). """
+    """ act(x @ weight.T + bias) with fp32 output (logits / losses stay fp32 whatever the activation dtype). `x`: (N, K) tensor, image tensor (flattened in
+    (C, H, W) order first) or `PendingFlatten` (the same, fused into the layer's kernels when the head is small enough). """
+    if isinstance(x, PendingFlatten):
+        t = x.x
+        if t.dim() == 4 and is_nhwc(t) and t.shape[2] * t.shape[3] > 1 and lib.dcv_linear_flatten_fused(int(weight.shape[0]), int(t.shape[1] * t.shape[2] * t.shape[3])):
+            if weight.shape[1] != t.shape[1] * t.shape[2] * t.shape[3]:
+                raise RuntimeError(f'deepcv_b200: linear layer expects {weight.shape[1]} input features, got {t.shape[1] * t.shape[2] * t.shape[3]}')
+            return _Linear.apply(t, weight, bias, int(act), float(slope), grad_out, step_ctx, int(t.shape[1]))
+        x = flatten_nchw(t)
     if x.dim() != 2:
         x = flatten_nchw(x) if x.dim() == 4 else x.reshape(x.shape[0], -1)
     if not x.is_contiguous():

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DCV_ABI_VERSION 3
+#define DCV_ABI_VERSION 4
 
 enum dcv_dtype { DCV_F32 = 0, DCV_BF16 = 1 };
 enum dcv_act { DCV_ACT_NONE = 0, DCV_ACT_RELU = 1, DCV_ACT_LEAKY_RELU = 2, DCV_ACT_SIGMOID = 3 };
@@ -223,13 +223,17 @@ int dcv_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh,
 int dcv_bilinear_bwd(const void* dy, float* dx_f32, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);
 
 /* ---- fully connected head (torch.nn.Linear built at meta/submodule_creators.py:268-269) -------------------------- */
-/* y[m][n] = act(sum_k x[m][k]*w[n][k] + bias[n]); w, bias fp32. */
+/* y[m][n] = act(sum_k x[m][k]*w[n][k] + bias[n]); w, bias fp32.
+ * x_nhwc_channels > 0: `torch.nn.Flatten` (conf/base/parameters.yml:87) is fused in — x is the NHWC image tensor [m][k / C pixels][C channels] itself and
+ * weight column f = c * (k / C) + p (the (C, H, W) feature order of the logical N x C x H x W tensor) multiplies element p * C + c of the row; dx comes
+ * back in the same NHWC order. Served for the skinny head only: dcv_linear_flatten_fused(n, k) != 0 (n <= 32); pass 0 otherwise. */
+int dcv_linear_flatten_fused(int n, int k);
 int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, int m, int n, int k, int act, float slope,
-                   int x_dtype, int y_dtype, void* stream);
-/* dpre = act'(y)*dy; dx = dpre @ w (x_dtype, may be NULL); dw = dpre^T @ x, db = sum_m dpre (fp32, overwritten).
+                   int x_dtype, int y_dtype, int x_nhwc_channels, void* stream);
+/* dpre = act'(y)*dy; dx = dpre @ w (x_dtype, may be NULL); dw = dpre^T @ x (may be NULL), db = sum_m dpre (fp32, overwritten).
  * dpre_ws: fp32 [m][n] scratch. */
 int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy, void* dx, float* dw, float* db, float* dpre_ws,
-                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, void* stream);
+                   int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, int x_nhwc_channels, void* stream);
 
 /* ---- loss / optimiser (classification/image.py:70-71) ------------------------------------------------------------ */
 /* CrossEntropyLoss(reduction='mean') over logits[m][n] (fp32) and int64 targets: loss[0] and dlogits = (softmax - onehot)/m_valid. Rows whose target is

@@ -327,8 +327,11 @@ def test_bilinear(dev, in_hw, out_hw, align):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
-@pytest.mark.parametrize('m,k,n,act', [(8, 1280, 10, 'sigmoid'), (5, 768, 1000, 'none'), (130, 70, 33, 'relu')])
-def test_flatten_linear_cross_entropy(dev, dtype, m, k, n, act):
+@pytest.mark.parametrize('fused', [False, True], ids=['flatten', 'flatten-fused'])
+@pytest.mark.parametrize('m,k,n,act', [(8, 1280, 10, 'sigmoid'), (5, 768, 1000, 'none'), (130, 70, 33, 'relu'), (37, 105, 7, 'relu'), (512, 1280, 10, 'sigmoid')])
+def test_flatten_linear_cross_entropy(dev, dtype, m, k, n, act, fused):
+    """ `torch.nn.Flatten` -> fully connected layer -> cross entropy. `fused`: Flatten hands the NHWC image tensor on (`ops.PendingFlatten`) and the small
+    head's kernels walk it through the (C, H, W) index map (`dcv_linear_fwd(..., x_nhwc_channels)`); heads with more than 32 outputs materialise it. """
     from deepcv_b200 import ops
     from deepcv_b200.meta import nn as dnn
     torch.manual_seed(m)
@@ -344,13 +347,20 @@ def test_flatten_linear_cross_entropy(dev, dtype, m, k, n, act):
     loss_ref = F.cross_entropy(ref(xr.flatten(1)), y_t)
     loss_ref.backward()
     xd = x.to(dev, dtype).requires_grad_(True)
-    logits = ours(dnn.Flatten()(xd))
+    flat = dnn.Flatten()(xd, defer_flatten=fused)
+    assert isinstance(flat, ops.PendingFlatten) == fused and tuple(flat.shape) == (m, k)
+    logits = ours(flat)
     assert logits.dtype == torch.float32
     loss = ops.cross_entropy(logits, y_t.to(dev))
     loss.backward()
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     assert_close(loss, loss_ref, tol, 'loss'), assert_close(xd.grad, xr.grad, tol, 'dx')
     assert_close(ours[0].weight.grad, lin.weight.grad, tol, 'dW'), assert_close(ours[0].bias.grad, lin.bias.grad, tol, 'db')
+    # frozen weight, trainable bias: the bias gradient must still be produced
+    ours[0].weight.requires_grad_(False)
+    ours[0].bias.grad = None
+    ops.cross_entropy(ours(dnn.Flatten()(xd.detach(), defer_flatten=fused)), y_t.to(dev)).backward()
+    assert_close(ours[0].bias.grad, lin.bias.grad, tol, 'db (frozen weight)')
 
 
 # ---- whole networks ---------------------------------------------------------------------------------------------------------------------
