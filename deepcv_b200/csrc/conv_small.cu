@@ -29,6 +29,7 @@
 //             their prologue and apply it WHILE LOADING their operand: no reduce / finalize / apply passes, dy is never written.
 // Per block: 3 launches instead of 9 (conv, finalize, apply, reduce, finalize, apply, wgrad, dgrad + weight packing), and three activation-sized
 // tensors (z, dy, the transposed weights) never touch HBM.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dcv {
@@ -243,6 +244,13 @@ __device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t* r) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Programmatic dependent launch: these kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may become
+// resident while its predecessor in the stream is still draining. Everything that does not depend on the predecessor (zeroing the tile, building the
+// weight fragments: the weights were written several kernels earlier) runs first; `pdl_wait` then blocks until the predecessor has completed and its
+// writes are visible, and `pdl_trigger` lets the NEXT kernel of the stream start its own prologue. The step is a chain of ~35 latency-bound kernels of
+// 10-20 us: launch ramp + drain (~5 us each) is what this overlaps.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -504,7 +512,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArg
   const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = lane & 3;
   SrcPlain src{a.x, a.xn.enabled ? &cfx : nullptr};
   Stager<CI, kThreads, SrcPlain> stager;
-  stager.fetch(src, (size_t)blockIdx.x * H * W * a.c_src, H * W, a.c_src, tid);   // the first image's L2 round trip overlaps everything up to the barrier
   for (int i = tid; i < Hp * Wp * CI / 8; i += kThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
   C core;
   const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
@@ -516,6 +523,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_fwd_kernel(const FwdArg
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int e = 0; e < 2; ++e) { const int o = C::out_channel(nt, t) + e; bias_r[nt][e] = (a.bias && o < a.k_out) ? a.bias[o] : 0.f; }
+  pdl_wait();      // the predecessor's output (x, its sums) may be read from here on
+  pdl_trigger();
+  stager.fetch(src, (size_t)blockIdx.x * H * W * a.c_src, H * W, a.c_src, tid);   // the first image's L2 round trip overlaps the coefficient prologue
 
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
     const size_t e_img = (size_t)img * H * W * a.c_src;
@@ -579,13 +589,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_dgrad_kernel(const Dgra
   const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = lane & 3;
   SrcDy src{a.dz, a.y, a.yn.enabled ? &cfy : nullptr, a.act, a.slope};
   Stager<KI, kThreads, SrcDy> stager;
-  stager.fetch(src, (size_t)blockIdx.x * H * W * a.k_out, H * W, a.k_out, tid);
   for (int i = tid; i < Hp * Wp * KI / 8; i += kThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
   C core;
   const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
   core.setup(Wp, [&](int r, int s, int k, int o) -> uint32_t {   // tile channel k = output channel of the layer, GEMM column o = input channel of the layer
     return (k < a.k_out && o < a.c_in) ? (uint32_t)wb[((size_t)(k * KS + (KS - 1 - r)) * KS + (KS - 1 - s)) * a.c_in + o] : 0u;
   });
+  pdl_wait();
+  pdl_trigger();
+  stager.fetch(src, (size_t)blockIdx.x * H * W * a.k_out, H * W, a.k_out, tid);
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
     const size_t e_img = (size_t)img * H * W * a.k_out;
     if (img != (int)blockIdx.x) { __syncthreads(); stager.fetch(src, e_img, H * W, a.k_out, tid); }
@@ -695,6 +707,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs
   Stager<CI, kGrp, SrcPlain, PF> stx;
   const int kv = a.k_out;   // channels of dy
   const int nks = G::PAIR ? HW / 32 : HW / 16;
+  pdl_wait();
+  pdl_trigger();
 
   for (int img = blockIdx.x * 2 + group; img < a.n; img += gridDim.x * 2) {
     const size_t e_img = (size_t)img * HW * a.c_src, k_img = (size_t)img * HW * kv;
@@ -827,6 +841,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_fwd_kernel(
   __shared__ Coef cf;
   const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
   const float inv = 1.f / (float)(a.pool * a.pool);
+  pdl_wait();
+  pdl_trigger();
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
     __syncthreads();
     if (tid < 32) norm_forward_coeffs(a.nd, img, cf, a.update_running != 0 && img == 0);
@@ -855,6 +871,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sc_affine_pool_bwd_kernel(
   const int tid = threadIdx.x, c2 = a.c / 2, oh = a.h / a.pool, ow = a.w / a.pool;
   const float inv = 1.f / (float)(a.pool * a.pool);
   const bool fixed_cp = (kThreads % c2) == 0;   // a thread then always works on the same channel pair: sums stay in registers
+  pdl_wait();
+  pdl_trigger();
   for (int img = blockIdx.x; img < a.n; img += gridDim.x) {
     __syncthreads();
     if (tid < kMaxC * 2) (&sh_s[0][0])[tid] = 0.f;
@@ -935,6 +953,19 @@ static int num_ctas(int n) {
   return n < 4 * sms ? n : 4 * sms;
 }
 
+// Launch with programmatic stream serialization (see pdl_wait): the kernel may start while its predecessor in the stream drains. DCV_NO_PDL=1: plain launches.
+static bool use_pdl() { static const bool on = getenv("DCV_NO_PDL") == nullptr; return on; }
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <typename K> static int set_smem(K kern, size_t bytes) {
   if (bytes > 32 * 1024) {   // dynamic + static (coefficient structs, slots: up to ~8 KB) must stay under the 48 KB default
     DCV_REQUIRE(bytes <= 200 * 1024, "sc: %zu bytes of shared memory needed", bytes);
@@ -978,7 +1009,7 @@ size_t dcv_sc_norm_floats(int n, int c, int which) {
   do {                                                                                                              \
     auto kern = KERN<CI_, NT_, KS_>;                                                                                \
     if (set_smem(kern, SMEM)) return 1;                                                                             \
-    kern<<<num_ctas((ARGS).n), kThreads, SMEM, st>>>(ARGS);                                                         \
+    launch_pdl(kern, num_ctas((ARGS).n), kThreads, SMEM, st, ARGS);                                                 \
   } while (0)
 
 int dcv_sc_conv_fwd(const dcv_conv_shape* s, const void* x, const dcv_sc_norm* x_norm, int update_running, const void* w, const float* bias, int act, float slope,
@@ -1043,7 +1074,7 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm*
   do {                                                                                  \
     auto kern = sc_wgrad_kernel<CI_, NT_, KS_>;                                         \
     if (set_smem(kern, smem)) return 1;                                                 \
-    kern<<<grid_of(a.n), kWgThreads, smem, st>>>(a);                                      \
+    launch_pdl(kern, grid_of(a.n), kWgThreads, smem, st, a);                              \
   } while (0)
   if (s->r == 5) SC_WGRAD(4, 4, 5);
   else if (ci == 4 && no == 4) SC_WGRAD(4, 4, 3);
@@ -1060,7 +1091,7 @@ int dcv_sc_affine_pool_fwd(const void* y, const dcv_sc_norm* norm, int update_ru
   DCV_REQUIRE(y && z && norm && norm->enabled && n > 0 && pool >= 1 && h % pool == 0 && w % pool == 0, "sc_affine_pool_fwd: bad arguments");
   if (check_norm(norm, n, c, h * w, "sc_affine_pool_fwd", false)) return 1;
   PoolArgs a{}; a.n = n; a.h = h; a.w = w; a.c = c; a.pool = pool; a.update_running = update_running; a.y = (const bf16*)y; a.z = (bf16*)z; a.nd = *norm;
-  sc_affine_pool_fwd_kernel<<<num_ctas(n), kThreads, 0, as_stream(stream)>>>(a);
+  launch_pdl(sc_affine_pool_fwd_kernel, num_ctas(n), kThreads, 0, as_stream(stream), a);
   DCV_LAUNCH_CHECK("sc_affine_pool_fwd_kernel");
   return 0;
 }
@@ -1070,7 +1101,7 @@ int dcv_sc_affine_pool_bwd(const void* dzp, const void* y, const dcv_sc_norm* no
   DCV_REQUIRE(dzp && y && dz && norm && norm->enabled && n > 0 && pool >= 1 && h % pool == 0 && w % pool == 0, "sc_affine_pool_bwd: bad arguments");
   if (check_norm(norm, n, c, h * w, "sc_affine_pool_bwd", true)) return 1;
   PoolArgs a{}; a.n = n; a.h = h; a.w = w; a.c = c; a.pool = pool; a.y = (const bf16*)y; a.dzp = (const bf16*)dzp; a.dz = (bf16*)dz; a.nd = *norm;
-  sc_affine_pool_bwd_kernel<<<num_ctas(n), kThreads, 0, as_stream(stream)>>>(a);
+  launch_pdl(sc_affine_pool_bwd_kernel, num_ctas(n), kThreads, 0, as_stream(stream), a);
   DCV_LAUNCH_CHECK("sc_affine_pool_bwd_kernel");
   return 0;
 }
