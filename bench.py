@@ -257,9 +257,9 @@ def conv_layer_table(batch, dev, peaks):
 def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
     """ Roofline of the dominant kernel of the step, called through the C ABI with preallocated buffers, timed live with CUDA events on the stream it is
     launched on (graph replay, buffers cycled beyond L2).
-      cifar     the 5x5 direct weight-gradient convolution (4 -> 4 channels, 32x32): the largest share of the CIFAR step in the ncu launch list
-                (profiles/). HBM-bound by the accounting of SURVEY.md section 8.d (arithmetic intensity 43-72 FLOP/B): algorithmic bytes per launch =
-                read x + read dy + write dw.
+      cifar     the few-channel weight-gradient kernel of the 5x5 4 -> 4 channel layers at 32x32: the largest share of the CIFAR step in the ncu launch
+                list (profiles/r02_launch_summary_cifar_warm.txt). HBM-bound by the accounting of SURVEY.md section 8.d (arithmetic intensity 43-72
+                FLOP/B): algorithmic bytes per launch = read x + read dz + read y + write dw.
       imagenet  the tcgen05 implicit-GEMM forward convolution of the 64 -> 64 channel 3x3 layers at 56x56 (also run as their data gradient): the largest
                 share of the ImageNet-shaped step. Tensor-bound: 2*N*P*Q*K*C*R*S FLOP per launch against the measured dense bf16 peak. """
     import ctypes
@@ -270,7 +270,30 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
     st = ctypes.c_void_p(stream.cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     with torch.cuda.stream(stream):
-        if workload == 'cifar':
+        if workload == 'cifar' and dtype_name == 'bf16':
+            # the few-channel weight-gradient kernel of the 4 -> 4 channel 5x5 layers (3 launches per step, the largest share of the launch list): reads the
+            # layer input x, the incoming gradient dz and the layer's own output y (the activation derivative is applied while loading), writes dw
+            from deepcv_b200._lib import ACT_RELU
+            n, c, h, w, k = batch, 4, size, size, 4
+            reps = max(4, int(300e6 / (n * h * w * (c + 2 * k) * esize)) + 1)
+            xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
+            dzs = [torch.randn(n, h, w, k, device=dev).to(tdt) for _ in range(reps)]
+            ys = [torch.randn(n, h, w, k, device=dev).relu().to(tdt) for _ in range(reps)]
+            dw, db = torch.zeros(k, 5, 5, c, device=dev), torch.zeros(k, device=dev)
+            shape = ConvShape(n, h, w, c, k, 5, 5, 1, 1, 2, 2, 1, 1, h, w)
+
+            def launch(i):
+                check(lib.dcv_sc_conv_wgrad(ctypes.byref(shape), P(xs[i]), None, P(dzs[i]), P(ys[i]), None, ACT_RELU, 0., P(dw), P(db), None, None, None, None, st), 'sc_conv_wgrad')
+            ms = _graph_time_ms(launch, reps, 20, stream)
+            alg_bytes = n * h * w * (c + 2 * k) * esize + k * 25 * c * 4
+            achieved = alg_bytes / (ms / 1e3) / 1e9
+            traffic = _committed_traffic('sc_wgrad_kernel<4, 4, 5>') if n == 512 else None
+            return dict(bound='hbm', kernel='sc_wgrad_kernel<4, 4, 5> (4->4 ch, 5x5, 32x32: mma.sync weight gradient with the activation derivative applied on load)', achieved=achieved,
+                        peak=peaks['hbm_gbs'], unit='GB/s', frac=achieved / peaks['hbm_gbs'], traffic=traffic, traffic_unit='bytes of DRAM per launch',
+                        traffic_source='ncu --set full (cold caches), profiles/r02_traffic.json' if traffic else None,
+                        peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
+                        note='latency-bound at this size: 12.6 MB per launch is 1.9 us of HBM time; the kernel is a chain of dependent round trips (see DESIGN.md section 5)')
+        if workload == 'cifar':   # fp32 parity mode: the CUDA-core direct weight gradient
             n, c, h, w, k = batch, 4, size, size, 4
             reps = max(4, int(300e6 / (n * h * w * (c + k) * esize)) + 1)
             xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
@@ -284,9 +307,7 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
             alg_bytes = n * h * w * (c + k) * esize + k * 25 * c * 4
             achieved = alg_bytes / (ms / 1e3) / 1e9
             return dict(bound='hbm', kernel='conv_wgrad_direct_s1_kernel<5,32,16,4,4> (4->4 ch, 5x5, 32x32; includes the 1.6 KB memset of dw)', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
-                        frac=achieved / peaks['hbm_gbs'], traffic=None, traffic_note='no ncu --set full capture of this instantiation is committed (the round-1 figure was of <3,16,16,16,16>)',
-                        peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
-                        note='latency-bound at this size: 8.4 MB per launch is 1.3 us of HBM time; see DESIGN.md section 5')
+                        frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3)
         n, c, h, w, k = batch, 64, 56, 56, 64
         if dtype_name != 'bf16':
             return None
@@ -308,6 +329,15 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
         return dict(bound='tensor', kernel='conv_fwd_tc_halo_kernel<64> (64->64 ch, 3x3, 56x56, bias + LeakyReLU epilogue)', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
                     frac=achieved / peaks['bf16_tflops'], traffic=traffic, traffic_unit='bytes of DRAM per launch', traffic_source='ncu --set full, profiles/r01_ncu_full_summary.txt',
                     peak_source=peaks['source'] + ', burst figure (kernel timed alone)', algorithmic_flop_per_launch=flop, us_per_launch=ms * 1e3)
+
+
+def _committed_traffic(kernel_name):
+    """ DRAM bytes (read + written) of one launch of `kernel_name` from the committed `ncu --set full` capture digest (profiles/r02_traffic.json,
+    written by tools/ncu_traffic.py from `ncu -i X.ncu-rep --page raw --csv`), or None. """
+    p = ROOT / 'profiles' / 'r02_traffic.json'
+    if not p.exists():
+        return None
+    return json.loads(p.read_text()).get(kernel_name, {}).get('dram_bytes')
 
 
 def load_peaks():

@@ -73,6 +73,7 @@ def _worker(rank, world, port, hp, bucket_bytes):
             err = float((p.grad.double() - m64).abs().max())
             assert err <= allowed, f'rank {rank}: gradient of {n} is not the mean of the per-rank gradients ({err / allowed:.2f}x the bound)'
         assert names[0].endswith('weight')          # the first layer's convolution weight is covered by the loop above
+        del loss   # its autograd graph keeps the parameters' AccumulateGrad nodes (bound to this stream) alive: a later capture on another stream would depend on uncaptured work
 
         # ---- several optimisation steps, eager then graph-replayed: parameters bit-identical on all ranks
         def params_identical(tag):
