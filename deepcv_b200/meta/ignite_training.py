@@ -218,9 +218,15 @@ class DataParallelModel(torch.nn.Module):
     ranks by bucketed NCCL all-reduce overlapped with backward. Parameters are broadcast from rank 0 at construction (as DDP does);
     BatchNorm statistics stay per replica. """
 
-    def __init__(self, module: torch.nn.Module, process_group=None, bucket_bytes: int = 8 << 20, overlap: bool = True):
+    def __init__(self, module: torch.nn.Module, process_group=None, bucket_bytes: Optional[int] = None, overlap: bool = True):
         super().__init__()
         self.module = module
+        if bucket_bytes is None:
+            # 8 MB buckets (DDP's scale) for large models; a small model still gets ~4 buckets, so that all but the last (the first layers' few KB)
+            # reduce while backward runs and only one small-message latency is exposed (the default 68 KB net was ONE bucket launched after the
+            # last weight gradient). DCV_BUCKET_BYTES overrides.
+            total = sum(p.numel() for p in module.parameters()) * 4
+            bucket_bytes = int(os.environ.get('DCV_BUCKET_BYTES', 0)) or min(8 << 20, max(8 << 10, total // 4))
         self.flat = flatten_parameters(module, bucket_bytes)
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         if self.world_size > 1:
