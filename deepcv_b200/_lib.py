@@ -67,6 +67,9 @@ SYMBOLS = {
     'dcv_sc_conv_dgrad': (c_int, [POINTER(ConvShape), P, P, POINTER(ScNorm), c_int, c_float, P, P, P, POINTER(ScNorm), P]),
     'dcv_sc_affine_pool_fwd': (c_int, [P, POINTER(ScNorm), c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_sc_affine_pool_bwd': (c_int, [P, P, POINTER(ScNorm), P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dcv_peer_flag_words': (c_size_t, []),
+    'dcv_peer_max_floats': (c_size_t, []),
+    'dcv_peer_allreduce_sum': (c_int, [P, P, P, c_int, c_int, c_size_t, c_size_t, c_size_t, c_int, P, P]),
     'dcv_dropout': (c_int, [P, P, P, c_size_t, c_float, c_uint64, P, P, c_int, P]),
     'dcv_activation_fwd': (c_int, [P, P, c_size_t, c_int, c_float, c_int, P]),
     'dcv_activation_bwd': (c_int, [P, P, P, c_size_t, c_int, c_float, c_int, P]),

@@ -12,6 +12,7 @@ gradient buffer is cut into buckets (default 8 MB) in reverse parameter order = 
 all-reduced (NCCL, side stream) as soon as its last producer has been enqueued, overlapping the rest of backward.
 """
 import ctypes
+import os
 from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple
 
 import torch
@@ -252,6 +253,61 @@ class FlatAdamW(torch.optim.Optimizer):
         return loss
 
 
+class PeerAllReduce:
+    """ One-shot all-reduce of small gradient buckets over NVLink peer memory (`dcv_peer_allreduce_sum`, csrc/peer_allreduce.cu): every rank pushes its
+    slice into every peer's RECEIVE area (symmetric memory allocated through `torch.distributed._symmetric_memory` — PyTorch as the peer-mapping plumbing;
+    the kernel is ours), then adds the W slices in rank order (bit-identical on all ranks). Replaces the collective library for buckets up to `max_floats`
+    of models whose flat gradient buffer is at most `max_numel` floats (the receive area is 2 x world x numel floats); everything else stays on NCCL.
+    Construction is collective (rendezvous). Disabled with DCV_NO_PEER_ALLREDUCE=1 or when symmetric memory is unavailable (`try_create` then returns
+    None and the reducer uses NCCL for every bucket — logged, not silent). """
+    max_numel = 1 << 20
+
+    @staticmethod
+    def enabled(world_size: int, device) -> bool:
+        return (1 < world_size <= 8 and torch.device(device).type == 'cuda' and os.environ.get('DCV_NO_PEER_ALLREDUCE') is None
+                and dist.is_initialized() and dist.get_backend() == 'nccl')
+
+    def __init__(self, flat_grads: torch.Tensor, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        dev = flat_grads.device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.grads = flat_grads
+        self.stride = (flat_grads.numel() + 3) // 4 * 4
+        if self.stride > self.max_numel:
+            raise ValueError(f'gradient buffer of {flat_grads.numel()} floats exceeds the peer all-reduce limit of {self.max_numel}')
+        self.recv = symm_mem.empty(2 * self.world * self.stride, dtype=torch.float32, device=dev)
+        self.recv.zero_()
+        self._h_recv = symm_mem.rendezvous(self.recv, group)
+        self.flags = symm_mem.empty(int(lib.dcv_peer_flag_words()), dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self._h_flags = symm_mem.rendezvous(self.flags, group)
+        self.state = torch.zeros(2 * 16, dtype=torch.int32, device=dev)
+        self.max_floats = int(lib.dcv_peer_max_floats())
+        self.max_slots = 16
+        # device arrays of the peers' pointers (kept alive by the handles)
+        self._recv_dev = ctypes.c_void_p(int(self._h_recv.buffer_ptrs_dev))
+        self._flags_dev = ctypes.c_void_p(int(self._h_flags.buffer_ptrs_dev))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)   # every rank's flag words are zero before the first kernel may write into them
+
+    @classmethod
+    def try_create(cls, flat_grads: torch.Tensor, group=None):
+        try:
+            return cls(flat_grads, group)
+        except Exception as e:   # no peer access / symmetric memory on this system, or too large a model: the collective library serves every bucket
+            import logging
+            logging.warning(f'deepcv_b200: peer-memory all-reduce not used ({type(e).__name__}: {e}); gradient buckets go through NCCL')
+            return None
+
+    def serves(self, start: int, end: int, slot: int) -> bool:
+        return 0 < end - start <= self.max_floats and slot < self.max_slots and start % 4 == 0
+
+    def all_reduce(self, start: int, end: int, slot: int):
+        check(lib.dcv_peer_allreduce_sum(_ptr(self.grads), self._recv_dev, self._flags_dev, self.rank, self.world, self.stride, start, end - start, slot, _ptr(self.state), _stream()),
+              'peer_allreduce_sum')
+
+
 class GradientBucketReducer:
     """ Data-parallel gradient averaging over the flat gradient buffer: one `all_reduce(SUM)` per bucket on a communication stream,
     launched as soon as backward has enqueued the bucket's last producer. "Enqueued" is reported by the fused layers themselves, at the END of
@@ -267,6 +323,7 @@ class GradientBucketReducer:
         self.is_cuda = flat.flat_grads.is_cuda
         self.comm_stream = torch.cuda.Stream(device=flat.flat_grads.device) if self.is_cuda else None
         self.average_in_finish = True
+        self.peer: Optional[PeerAllReduce] = None   # set by DataParallelModel: small buckets then go through the one-shot peer-memory kernel
         foreign = {flat.bucket_of[id(p)] for p in flat.foreign_params}
         self._early_ok = [b not in foreign for b in range(len(flat.buckets))]
         self._layer_buckets: Dict[int, List[int]] = {}
@@ -300,7 +357,10 @@ class GradientBucketReducer:
         if self.is_cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+                if self.peer is not None and self.peer.serves(start, end, b):
+                    self.peer.all_reduce(start, end, b)      # one kernel over NVLink peer memory (small buckets: latency)
+                else:
+                    dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
         self._launched[b] = True

@@ -27,7 +27,7 @@ from torch.utils.data import DataLoader, Dataset
 
 from .. import ops
 from .._lib import check, lib
-from .flat_params import FlatAdamW, FlatParameters, GradientBucketReducer, flatten_parameters
+from .flat_params import FlatAdamW, FlatParameters, GradientBucketReducer, PeerAllReduce, flatten_parameters
 from .hyperparams import HYPERPARAMS_T, to_hyperparameters
 
 __all__ = ['MAIN_TRAINING_LOSS_NAME', 'Events', 'State', 'Engine', 'PiecewiseLinear', 'BackendConfig', 'CrossEntropyLoss', 'train', 'make_process_function',
@@ -227,13 +227,15 @@ class DataParallelModel(torch.nn.Module):
             # last weight gradient). DCV_BUCKET_BYTES overrides.
             total = sum(p.numel() for p in module.parameters()) * 4
             bucket_bytes = int(os.environ.get('DCV_BUCKET_BYTES', 0)) or min(8 << 20, max(8 << 10, total // 4))
-        self.flat = flatten_parameters(module, bucket_bytes)
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.flat = flatten_parameters(module, bucket_bytes)
         if self.world_size > 1:
             dist.broadcast(self.flat.flat_params, src=0, group=process_group)
             for b in module.buffers():
                 dist.broadcast(b, src=0, group=process_group)
         self.reducer = GradientBucketReducer(self.flat, process_group, overlap=overlap)
+        if PeerAllReduce.enabled(self.world_size, self.flat.flat_grads.device) and self.flat.flat_grads.numel() <= PeerAllReduce.max_numel:
+            self.reducer.peer = PeerAllReduce.try_create(self.flat.flat_grads, process_group)
 
     def forward(self, *args, **kwargs):
         self.reducer.begin_step()

@@ -235,6 +235,22 @@ int dcv_linear_fwd(const void* x, const float* w, const float* bias, void* y, in
 int dcv_linear_bwd(const void* x, const float* w, const void* y, const void* dy, void* dx, float* dw, float* db, float* dpre_ws,
                    int m, int n, int k, int act, float slope, int x_dtype, int y_dtype, int acc_prezeroed, int x_nhwc_channels, void* stream);
 
+/* ---- data-parallel gradient exchange over peer memory (meta/ignite_training.py:373-390: DistributedDataParallel's gradient averaging) ----
+ * One-shot SUM all-reduce of the float slice [offset, offset + count) of `grads` (this rank's flat gradient buffer, ordinary device memory), in place, for
+ * small gradient buckets (latency-bound in a collective library): every rank pushes its slice into every peer's receive area, then adds the W slices in rank
+ * order (bit-identical results on all ranks). peer_recv_dev / peer_flags_dev: DEVICE arrays of `world` pointers — entry r addresses rank r's receive area
+ * (float [2][world][recv_stride], element i of the flat buffer at index i) / flag area (dcv_peer_flag_words() zero-initialised uint32), both in symmetric
+ * memory mapped into this process. Every rank calls it with the same offset / count / slot in the same order (slot < DCV_PEER_MAX_SLOTS: the flag words
+ * and epoch counter of one bucket). state_dev: 2 * DCV_PEER_MAX_SLOTS zero-initialised uint32 of this rank. count <= dcv_peer_max_floats() (the launch
+ * must be co-resident: its CTAs wait for the peers). CUDA-graph replayable. */
+#define DCV_PEER_MAX_WORLD 8
+#define DCV_PEER_MAX_CTAS 32
+#define DCV_PEER_MAX_SLOTS 16
+size_t dcv_peer_flag_words(void);
+size_t dcv_peer_max_floats(void);
+int dcv_peer_allreduce_sum(float* grads, float* const* peer_recv_dev, uint32_t* const* peer_flags_dev, int rank, int world, size_t recv_stride, size_t offset, size_t count, int slot,
+                           uint32_t* state_dev, void* stream);
+
 /* ---- loss / optimiser (classification/image.py:70-71) ------------------------------------------------------------ */
 /* CrossEntropyLoss(reduction='mean') over logits[m][n] (fp32) and int64 targets: loss[0] and dlogits = (softmax - onehot)/m_valid. Rows whose target is
  * -100 (torch's default ignore_index) are skipped and the mean runs over the others; any other target outside [0, n) makes the loss NaN. */

@@ -125,3 +125,79 @@ def test_data_parallel_gradients_and_parameters_nccl(default_hp, bucket_bytes):
     import torch.multiprocessing as mp
     port = _free_port()
     mp.spawn(_worker, args=(2, port, default_hp, bucket_bytes), nprocs=2, join=True)
+
+
+def _peer_worker(rank, world, port):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    code = 0
+    try:
+        from deepcv_b200.meta.flat_params import PeerAllReduce
+        numel = 40000 + 3                                   # ragged: the last slice is not a whole number of 16-byte vectors
+        buf = torch.zeros(numel, device=dev)
+        peer = PeerAllReduce(buf, None)
+        assert peer.world == world and peer.max_floats >= 17010
+        g = torch.Generator().manual_seed(50 + rank)
+        slices = [(0, 17016, 0), (17016, 20000, 1), (20000, numel, 2)]      # (start, end, slot): three "buckets"
+
+        def reference(mine):
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            out = torch.zeros_like(mine)
+            for p in parts:                                  # rank order 0..W-1: the kernel's summation order => bit-identical
+                out += p
+            return out
+        for it in range(3):                                  # epochs advance; nothing is reset between calls
+            mine = torch.randn(numel, generator=g).to(dev)
+            buf.copy_(mine)
+            ref = reference(mine)
+            torch.cuda.synchronize(); dist.barrier()
+            for start, end, slot in slices:
+                peer.all_reduce(start, end, slot)
+            torch.cuda.synchronize()
+            assert torch.equal(buf, ref), f'rank {rank} iteration {it}: max |diff| {float((buf - ref).abs().max())}'
+            dist.barrier()
+        # CUDA-graph replay (the training step is one graph): static buffer, new data copied in before every replay
+        static_in = torch.zeros(numel, device=dev)
+        s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            buf.copy_(static_in)
+            for start, end, slot in slices:
+                peer.all_reduce(start, end, slot)
+        torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize(); dist.barrier()
+        with torch.cuda.graph(graph):
+            buf.copy_(static_in)
+            for start, end, slot in slices:
+                peer.all_reduce(start, end, slot)
+        for it in range(3):
+            mine = torch.randn(numel, generator=g).to(dev)
+            static_in.copy_(mine)
+            ref = reference(mine)
+            torch.cuda.synchronize(); dist.barrier()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(buf, ref), f'rank {rank} graph replay {it}: max |diff| {float((buf - ref).abs().max())}'
+            dist.barrier()
+        graph.reset()
+        torch.cuda.synchronize()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        code = 1
+    finally:
+        sys.stdout.flush(), sys.stderr.flush()
+        os._exit(code)
+
+
+def test_peer_memory_all_reduce_bit_exact():
+    """ `dcv_peer_allreduce_sum` (one-shot all-reduce of small gradient buckets over NVLink peer memory) against the sum in rank order of all ranks'
+    buffers: bit-identical on every rank, across repeated calls (epoch flags) and under CUDA-graph replay. """
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
