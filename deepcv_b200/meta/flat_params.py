@@ -351,7 +351,16 @@ class GradientBucketReducer:
                     self._launch(b)
         return _done
 
+    @property
+    def inline_peer(self) -> bool:
+        """ A model whose whole gradient buffer fits ONE one-shot peer all-reduce (the default net: 68 KB, ~9 us) is reduced by a single kernel on the
+        COMPUTE stream at the end of backward: no communication stream inside the captured step (a forked graph costs more in node scheduling than the
+        overlap of a few microseconds of exchange could return). DCV_PEER_OVERLAP=1 keeps the bucketed, overlapped schedule. """
+        return self.peer is not None and self.flat.flat_grads.numel() <= self.peer.max_floats and os.environ.get('DCV_PEER_OVERLAP') is None
+
     def _launch(self, b: int):
+        if self.inline_peer:
+            return   # `finish()` reduces the whole buffer with one kernel
         start, end = self.flat.buckets[b]
         chunk = self.flat.flat_grads[start:end]
         if self.is_cuda:
@@ -379,11 +388,14 @@ class GradientBucketReducer:
         if relaunch:
             raise RuntimeError('deepcv_b200: a gradient bucket was all-reduced before a second backward pass wrote into it (weights shared between layers '
                                'that complete at different times); construct the data-parallel wrap with `overlap=False`')
-        for b in range(len(self.flat.buckets)):
-            if not self._launched[b]:
-                self._launch(b)
-        if self.is_cuda:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self.inline_peer:
+            self.peer.all_reduce(0, self.flat.flat_grads.numel(), 0)
+        else:
+            for b in range(len(self.flat.buckets)):
+                if not self._launched[b]:
+                    self._launch(b)
+            if self.is_cuda:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
         if self.average_in_finish:
             g = self.flat.flat_grads
             if self.is_cuda:
