@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
-__all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
+__all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'PackEntry', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
            'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
 
 ABI_VERSION = 4
@@ -28,6 +28,11 @@ class NormParams(Structure):
                 ('bn_num_batches_tracked', c_void_p),
                 ('use_gn', c_int32), ('gn_groups', c_int32), ('gn_eps', c_float),
                 ('gn_weight', c_void_p), ('gn_bias', c_void_p)]
+
+
+class PackEntry(Structure):
+    """ `dcv_pack_entry` (dcv_pack_conv_weights_batched) """
+    _fields_ = [('src_off', c_uint64), ('dst_off', c_uint64), ('unit0', c_int64), ('k', c_int32), ('r', c_int32), ('s', c_int32), ('c', c_int32)]
 
 
 class ScNorm(Structure):
@@ -70,6 +75,7 @@ SYMBOLS = {
     'dcv_peer_flag_words': (c_size_t, []),
     'dcv_peer_max_floats': (c_size_t, []),
     'dcv_peer_allreduce_sum': (c_int, [P, P, P, c_int, c_int, c_size_t, c_size_t, c_size_t, c_int, P, P]),
+    'dcv_pack_conv_weights_batched': (c_int, [P, P, c_int, P, c_int, c_int64, P]),
     'dcv_dropout': (c_int, [P, P, P, c_size_t, c_float, c_uint64, P, P, c_int, P]),
     'dcv_activation_fwd': (c_int, [P, P, c_size_t, c_int, c_float, c_int, P]),
     'dcv_activation_bwd': (c_int, [P, P, P, c_size_t, c_int, c_float, c_int, P]),

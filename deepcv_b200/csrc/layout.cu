@@ -45,6 +45,45 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, TD* __restrict__
   }
 }
 
+// All data-gradient weight operands of a step in ONE launch (17 pack launches of ~8.5 us each on the ImageNet-shaped step otherwise): entry e is a
+// [K][R][S][C] fp32 weight inside the flat parameter buffer and its [C][R-1-r][S-1-s][K] copy inside one destination buffer. Work unit = (filter tap,
+// 8-channel block, 32-filter block): a lane reads 8 contiguous floats of its filter (32 bytes) and writes one element of each of 8 channel rows, the
+// warp's stores forming 64-byte runs.
+template <typename TD>
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const float* __restrict__ flat, TD* __restrict__ dst, const dcv_pack_entry* __restrict__ entries, int n_entries,
+                                                                   long long total_units) {
+  __shared__ dcv_pack_entry sh[64];
+  for (int i = threadIdx.x; i < n_entries; i += blockDim.x) sh[i] = entries[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < total_units; u += warps) {
+    int e = 0;
+    while (e + 1 < n_entries && u >= sh[e + 1].unit0) ++e;   // <= 64 entries: a short scan (warp-uniform)
+    const dcv_pack_entry& en = sh[e];
+    long long t = u - en.unit0;
+    const int kb_n = (en.k + 31) / 32, cb_n = (en.c + 7) / 8;
+    const int kb = (int)(t % kb_n); t /= kb_n;
+    const int cb = (int)(t % cb_n); t /= cb_n;
+    const int si = (int)(t % en.s), ri = (int)(t / en.s);
+    const int ki = kb * 32 + lane, c0 = cb * 8;
+    if (ki >= en.k) continue;
+    const float* src = flat + en.src_off + (((size_t)ki * en.r + ri) * en.s + si) * en.c + c0;
+    float v[8];
+    if (c0 + 8 <= en.c && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = c0 + i < en.c ? __ldg(src + i) : 0.f;
+    }
+    TD* out = dst + en.dst_off + (((size_t)c0 * en.r + (en.r - 1 - ri)) * en.s + (en.s - 1 - si)) * en.k + ki;
+    const size_t cstride = (size_t)en.r * en.s * en.k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (c0 + i < en.c) out[i * cstride] = from_f<TD>(v[i]);
+  }
+}
+
 // col[n][p][q][kpad]: entries (r, s, c) of the receptive field of output pixel (p, q) in the order of the [K][R][S][C] weight layout, zero
 // padded from R*S*C to kpad. One thread per 16-byte output vector: the (cached, redundant) gathers are scalar, the 1.2 GB-class store is coalesced.
 template <typename T>
@@ -318,6 +357,15 @@ int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, i
   const size_t total = (size_t)k * r * s * c;
   DCV_DISPATCH_DTYPE(dst_dtype, T, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w_krsc, (T*)dst, k, r, s, c, transpose_flip)));
   DCV_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
+int dcv_pack_conv_weights_batched(const float* flat_params, void* dst, int dst_dtype, const dcv_pack_entry* entries_dev, int n_entries, long long total_units, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(flat_params && dst && entries_dev && n_entries > 0 && n_entries <= 64 && total_units > 0, "pack_conv_weights_batched: bad arguments (at most 64 entries)");
+  const int grid = grid_for((size_t)total_units * 32, 256, kNumSMs * 8);
+  DCV_DISPATCH_DTYPE(dst_dtype, T, (pack_weights_batched_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(flat_params, (T*)dst, entries_dev, n_entries, total_units)));
+  DCV_LAUNCH_CHECK("pack_weights_batched_kernel");
   return 0;
 }
 

@@ -387,6 +387,11 @@ class GraphedTrainStep:
         if self.flat is not None and op_dtype == torch.bfloat16 and os.environ.get('DCV_NO_SHADOW') is None:
             self._shadow = torch.empty(self.flat.flat_params.numel(), dtype=torch.bfloat16, device=example_x.device)
             self.ctx.shadows = [(self.flat.flat_params, self._shadow)]
+            # ... and one launch for all the transposed + flipped weight operands of the data-gradient convolutions (tensor-core layers: 64-channel multiples)
+            convs = [l._op.weight for l in _fused_layers(inner) if isinstance(l._op, torch.nn.Conv2d) and l._op.in_channels % 64 == 0 and l._op.out_channels % 16 == 0
+                     and l._op.stride == (1, 1)]
+            if convs and os.environ.get('DCV_NO_BATCHED_PACK') is None:
+                self.ctx.plan_transposed_weights(self.flat.flat_params, [w.detach() for w in convs], torch.bfloat16)
         layers = _fused_layers(inner)
         previous = [l._step_ctx for l in layers]
         for l in layers:

@@ -209,6 +209,7 @@ class StepContext:
     def __init__(self, arena: Optional[AccumulatorArena] = None):
         self.arena = arena
         self.shadows: List[Tuple[torch.Tensor, torch.Tensor]] = []   # (flat fp32 parameter buffer, same-length buffer of the operand dtype)
+        self.transposed = None   # see `plan_transposed_weights`
 
     @property
     def prezeroed(self) -> int:
@@ -224,6 +225,41 @@ class StepContext:
         """ ONE cast kernel per step instead of one per convolution. """
         for src, dst in self.shadows:
             check(lib.dcv_cast(_ptr(src), _dt(src), _ptr(dst), _dt(dst), src.numel(), _stream()), 'cast(flat parameters)')
+        t = self.transposed
+        if t is not None:
+            check(lib.dcv_pack_conv_weights_batched(_ptr(t['flat']), _ptr(t['buf']), _dt(t['buf']), _ptr(t['table']), t['n'], t['units'], _stream()), 'pack_conv_weights_batched')
+
+    def plan_transposed_weights(self, flat_params: torch.Tensor, weights: Sequence[torch.Tensor], dtype: torch.dtype) -> None:
+        """ The data-gradient operands ([C][R-1-r][S-1-s][K], operand dtype) of all the given convolution weights — [K][R][S][C] slices of `flat_params` —
+        are produced by ONE kernel per step (`refresh_shadows`) into one buffer, instead of one `dcv_pack_conv_weight` launch per layer in backward. """
+        from ._lib import PackEntry
+        entries, views, dst_off, unit0 = [], {}, 0, 0
+        for w in weights:
+            k, c, r, s_ = w.shape
+            off = (w.data_ptr() - flat_params.data_ptr()) // 4
+            if not (w.dtype == torch.float32 and w.permute(0, 2, 3, 1).is_contiguous() and 0 <= off and off + w.numel() <= flat_params.numel()):
+                continue
+            entries.append(PackEntry(off, dst_off, unit0, k, r, s_, c))
+            views[w.data_ptr()] = (dst_off, (c, r, s_, k))
+            dst_off += (w.numel() + 7) // 8 * 8      # 16-byte aligned slices (TMA)
+            unit0 += r * s_ * ((c + 7) // 8) * ((k + 31) // 32)
+        if not entries or len(entries) > 64:
+            return
+        table = (PackEntry * len(entries))(*entries)
+        dev_table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(flat_params.device)
+        buf = torch.empty(dst_off, dtype=dtype, device=flat_params.device)
+        self.transposed = dict(flat=flat_params, table=dev_table, n=len(entries), units=unit0, buf=buf, views=views)
+
+    def transposed_view(self, weight: torch.Tensor, dtype: torch.dtype) -> Optional[torch.Tensor]:
+        t = self.transposed
+        if t is None or t['buf'].dtype != dtype:
+            return None
+        hit = t['views'].get(weight.data_ptr())
+        if hit is None:
+            return None
+        off, shape = hit
+        n = shape[0] * shape[1] * shape[2] * shape[3]
+        return t['buf'][off:off + n].view(*shape)
 
     def shadow_view(self, weight: torch.Tensor, dtype: torch.dtype) -> Optional[torch.Tensor]:
         for src, dst in self.shadows:
@@ -419,7 +455,9 @@ class _ConvBlock(torch.autograd.Function):
             dx = empty_nhwc(n, shape.c, shape.h, shape.w, y.dtype, dev)
             wt = None
             if algo != ALGO_DIRECT and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 1):
-                # operand of the data-gradient convolution: [C][R-1-r][S-1-s][K] in the activation dtype
+                # operand of the data-gradient convolution: [C][R-1-r][S-1-s][K] in the activation dtype — from the step's batched pack when there is one
+                wt = sctx.transposed_view(ctx.w_master, y.dtype) if (sctx is not None and ctx.w_master is not None) else None
+            if wt is None and algo != ALGO_DIRECT and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 1):
                 wt = torch.empty((shape.c, shape.r, shape.s, shape.k), dtype=y.dtype, device=dev)
                 # NB: packing from the fp32 master rounds to bf16 once, exactly like the forward operand (a bf16 -> fp32 -> bf16 round trip is the identity)
                 w32 = ctx.w_master if ctx.w_master is not None else (_cast_raw(w_op, torch.float32) if w_op.dtype != torch.float32 else w_op)

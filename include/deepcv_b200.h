@@ -70,6 +70,12 @@ int dcv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t co
 /* fp32 [K][R][S][C] weights -> `dst_dtype` copy; with `transpose_flip` != 0 writes [C][R-1-r][S-1-s][K] (the operand of
  * the data-gradient convolution). */
 int dcv_pack_conv_weight(const float* w_krsc, void* dst, int dst_dtype, int k, int r, int s, int c, int transpose_flip, void* stream);
+/* The same transposed + flipped copy for MANY layers in one launch (once per training step): entry e reads the [K][R][S][C] fp32 weight at
+ * flat_params + src_off and writes its [C][R-1-r][S-1-s][K] copy at dst + dst_off (elements of dst_dtype). unit0 = number of work units of the entries
+ * before e, one unit = (tap, 8-channel block, 32-filter block): units(e) = r * s * ceil(c / 8) * ceil(k / 32); total_units = their sum. <= 64 entries
+ * (device array). */
+typedef struct dcv_pack_entry { uint64_t src_off, dst_off; long long unit0; int32_t k, r, s, c; } dcv_pack_entry;
+int dcv_pack_conv_weights_batched(const float* flat_params, void* dst, int dst_dtype, const dcv_pack_entry* entries_dev, int n_entries, long long total_units, void* stream);
 
 /* Explicit im2col for convolutions the implicit-GEMM tensor-core kernel cannot address (few input channels, strides — the 7x7/stride-2 stem):
  * col[n][p][q][kpad] holds the (r, s, c) receptive field of every output pixel in [K][R][S][C] weight order, zero padded to kpad; the convolution is

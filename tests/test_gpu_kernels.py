@@ -167,3 +167,27 @@ def test_norm_finalize_running_statistics_and_affine(dev, n, hw, c, groups, mome
         assert int(nbt) == step + 1 == int(bn.num_batches_tracked)
         assert rel(rm, bn.running_mean) <= 1e-5 and rel(rv, bn.running_var) <= 1e-5
         assert rel(z.permute(0, 3, 1, 2), ref.detach()) <= 1e-4
+
+
+def test_batched_transposed_weight_pack(dev):
+    """ `dcv_pack_conv_weights_batched`: the data-gradient operands [C][R-1-r][S-1-s][K] (bf16) of several [K][R][S][C] fp32 weights living in one flat buffer,
+    in one launch — bit-equal to the per-layer `dcv_pack_conv_weight` and to the permute / flip / round-to-bf16 of the logical OIHW tensor. """
+    from deepcv_b200 import ops
+    torch.manual_seed(0)
+    shapes = [(64, 64, 3, 3), (128, 64, 3, 3), (48, 128, 1, 1), (16, 4, 5, 5), (10, 3, 7, 7), (512, 256, 3, 3), (33, 20, 3, 2)]   # (K, C, R, S)
+    offs, total = [], 0
+    for k, c, r, s in shapes:
+        offs.append(total)
+        total += (k * c * r * s + 7) // 8 * 8
+    flat = torch.randn(total, device=dev)
+    weights = [flat[o:o + k * c * r * s].view(k, r, s, c).permute(0, 3, 1, 2) for o, (k, c, r, s) in zip(offs, shapes)]     # logical OIHW, memory KRSC
+    ctx = ops.StepContext()
+    ctx.plan_transposed_weights(flat, weights, torch.bfloat16)
+    assert ctx.transposed is not None and ctx.transposed['n'] == len(shapes)
+    ctx.refresh_shadows()
+    for w, (k, c, r, s) in zip(weights, shapes):
+        got = ctx.transposed_view(w, torch.bfloat16)
+        assert tuple(got.shape) == (c, r, s, k)
+        ref = w.permute(1, 2, 3, 0).flip(1, 2).contiguous().bfloat16()          # [C][R-1-r][S-1-s][K]
+        assert torch.equal(got, ref), (k, c, r, s)
+    assert ctx.transposed_view(torch.randn(4, 4, 3, 3, device=dev), torch.bfloat16) is None
