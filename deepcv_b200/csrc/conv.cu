@@ -8,10 +8,10 @@ int conv_wgrad_direct(const dcv_conv_shape*, const void*, const void*, float*, i
 // conv_tc.cu
 bool conv_tc_fwd_supported(const dcv_conv_shape*, int dtype);
 bool conv_tc_wgrad_supported(const dcv_conv_shape*, int dtype);
-int conv_fwd_tc(const dcv_conv_shape*, const void*, const void*, const float*, void*, float*, int, float, bool channel_totals, cudaStream_t);
+int conv_fwd_tc(const dcv_conv_shape*, const void*, const void*, const float*, void*, float*, int, float, int stats_flags, cudaStream_t);
 int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*, bool prezeroed, cudaStream_t);
 bool conv_fwd_tc_gather_supported(const dcv_conv_shape*, const void* x, int kpad, int dtype);
-int conv_fwd_tc_gather(const dcv_conv_shape*, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, bool channel_totals, cudaStream_t);
+int conv_fwd_tc_gather(const dcv_conv_shape*, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, int stats_flags, cudaStream_t);
 int conv_wgrad_tc_gather(const dcv_conv_shape*, const void* x, const void* dy, float* dw_col, int kpad, bool prezeroed, cudaStream_t);
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*);
 
@@ -46,7 +46,7 @@ int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, co
   const bool tc_ok = conv_tc_fwd_supported(shape, dtype);
   zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st, (acc_prezeroed & DCV_ACC_PREZEROED) != 0);
   DCV_REQUIRE(algo != DCV_ALGO_TCGEN05 || tc_ok, "conv2d_fwd: tcgen05 algorithm does not support this shape/dtype (needs bf16, c %% 64 == 0, k %% 16 == 0, stride 1, dilation 1)");
-  if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(shape, x, w, bias, y, stats_nc, act, slope, (acc_prezeroed & DCV_STATS_CHANNEL_TOTALS) != 0, st);
+  if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(shape, x, w, bias, y, stats_nc, act, slope, acc_prezeroed, st);
   return conv_fwd_direct(shape, x, w, bias, y, stats_nc, act, slope, dtype, st);
 }
 
@@ -60,7 +60,7 @@ int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void
   DCV_REQUIRE(shape, "conv2d_fwd_gather: null shape");
   cudaStream_t st = as_stream(stream);
   zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st, (acc_prezeroed & DCV_ACC_PREZEROED) != 0);
-  return conv_fwd_tc_gather(shape, x, w_col, kpad, bias, y, stats_nc, act, slope, (acc_prezeroed & DCV_STATS_CHANNEL_TOTALS) != 0, st);
+  return conv_fwd_tc_gather(shape, x, w_col, kpad, bias, y, stats_nc, act, slope, acc_prezeroed, st);
 }
 
 int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, int acc_prezeroed, void* stream) {
@@ -80,7 +80,7 @@ int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w,
     tc_ok = t.pad_h >= 0 && t.pad_w >= 0 && conv_tc_fwd_supported(&t, dtype);
   }
   DCV_REQUIRE(algo != DCV_ALGO_TCGEN05 || tc_ok, "conv2d_dgrad: tcgen05 algorithm does not support this shape/dtype (or `wt` is NULL)");
-  if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(&t, dy, wt, nullptr, dx, nullptr, DCV_ACT_NONE, 0.f, false, st);
+  if (algo == DCV_ALGO_TCGEN05 || (algo == DCV_ALGO_AUTO && tc_ok)) return conv_fwd_tc(&t, dy, wt, nullptr, dx, nullptr, DCV_ACT_NONE, 0.f, 0, st);
   return conv_dgrad_direct(shape, dy, w, dx, dtype, st);
 }
 

@@ -1075,13 +1075,13 @@ bool conv_fwd_tc_gather_supported(const dcv_conv_shape* s, const void* x, int kp
 }
 
 // w_col: [K][kpad] bf16, columns (r, s, c) of the [K][R][S][C] weights followed by zeros.
-int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, bool channel_totals, cudaStream_t st) {
+int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, int stats_flags, cudaStream_t st) {
   using namespace tc;
   DCV_REQUIRE(x && w_col && y, "conv2d_fwd_gather: null pointer");
   GatherParams prm{}; size_t smem = 0;
   DCV_REQUIRE(gather_geometry(s, x, kpad, &prm, &smem, s->k * BLOCK_K * 2), "conv2d_fwd_gather: shape not supported (see dcv_conv2d_gather_supported)");
   prm.act = act; prm.slope = slope; prm.bias = bias; prm.x = reinterpret_cast<const __nv_bfloat16*>(x); prm.y = reinterpret_cast<__nv_bfloat16*>(y);
-  const bool fused_stats = stats_nc && channel_totals;   // per-channel totals in the epilogue, credited to image 0 of stats_nc[n][k][2] (rows of the other images stay zero)
+  const bool fused_stats = stats_nc && (stats_flags & DCV_STATS_CHANNEL_TOTALS) && (stats_flags & DCV_STATS_IN_EPILOGUE);   // per-channel totals in the epilogue, credited to image 0 of stats_nc[n][k][2] (rows of the other images stay zero)
   prm.stats = fused_stats ? stats_nc : nullptr;
   CUtensorMap mw;
   {
@@ -1103,7 +1103,7 @@ int conv_fwd_tc_gather(const dcv_conv_shape* s, const void* x, const void* w_col
     kern<<<grid, GA_THREADS, smem, st>>>(mw, prm);
   }
   DCV_LAUNCH_CHECK("conv_fwd_tc_gather_kernel");
-  if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
+  if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, DCV_ACC_PREZEROED | (stats_flags & DCV_STATS_CHANNEL_TOTALS), st);
   return 0;
 }
 
@@ -1143,16 +1143,16 @@ bool conv_tc_fwd_supported(const dcv_conv_shape* s, int dtype) {
   return tc::encode_tiled() != nullptr;
 }
 
-int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, float* stats_nc, int act, float slope, bool channel_totals, cudaStream_t st) {
+int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const float* bias, void* y, float* stats_nc, int act, float slope, int stats_flags, cudaStream_t st) {
   using namespace tc;
   DCV_REQUIRE(x && w && y, "conv2d_fwd (tcgen05): null pointer");
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0), "conv2d_fwd (tcgen05): pointers must be 16-byte aligned");
   // BatchNorm-only blocks need per-CHANNEL totals only: the epilogue produces them (credited to image 0 of stats_nc[n][k][2]; the rows of the other
   // images stay zero). A GroupNorm / InstanceNorm needs per-(image, channel) sums: pixel tiles span images, so those come from the statistics kernel.
-  const bool fused_stats = stats_nc && channel_totals && s->k <= kMaxStatChannels;
+  const bool fused_stats = stats_nc && (stats_flags & DCV_STATS_CHANNEL_TOTALS) && (stats_flags & DCV_STATS_IN_EPILOGUE) && s->k <= kMaxStatChannels;
   if (fwd_halo_applicable(s)) {
     if (conv_fwd_tc_halo(s, x, w, bias, y, act, slope, fused_stats ? stats_nc : nullptr, st)) return 1;
-    if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
+    if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, DCV_ACC_PREZEROED | (stats_flags & DCV_STATS_CHANNEL_TOTALS), st);
     return 0;
   }
   FwdParams prm{};
@@ -1186,7 +1186,7 @@ int conv_fwd_tc(const dcv_conv_shape* s, const void* x, const void* w, const flo
   else if (prm.n_tiles_k == 1 && s->r * s->s * (s->c / BLOCK_K) <= kMaxResidentKb && getenv("DCV_TC_NO_RESIDENT") == nullptr) rc = launch_fwd<64, 1>(mx, mw, prm, st);
   else rc = launch_fwd<64>(mx, mw, prm, st);
   if (rc) return rc;
-  if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, 1, st);
+  if (stats_nc && !fused_stats) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, DCV_ACC_PREZEROED | (stats_flags & DCV_STATS_CHANNEL_TOTALS), st);
   return 0;
 }
 

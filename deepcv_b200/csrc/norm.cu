@@ -615,7 +615,10 @@ int dcv_norm_stats(const void* y, float* stats_nc, int n, int hw, int c, int dty
   DCV_REQUIRE(y && stats_nc, "norm_stats: null pointer");
   if (check_nc("norm_stats", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(stats_nc, (size_t)n * c * 2 * sizeof(float), st, acc_prezeroed != 0);
+  zero_accumulator(stats_nc, (size_t)n * c * 2 * sizeof(float), st, (acc_prezeroed & DCV_ACC_PREZEROED) != 0);
+  // DCV_STATS_CHANNEL_TOTALS (a BatchNorm-only block): the batch is walked as ONE image of n * hw pixels — one CTA reduction per CTA instead of one per
+  // (CTA, image) — and the totals are credited to image 0. (7 x 7 maps: a CTA's range used to cross dozens of images, each with its own flush.)
+  if ((acc_prezeroed & DCV_STATS_CHANNEL_TOTALS) && (long long)n * hw < (1ll << 31)) { hw *= n; n = 1; }
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);
@@ -680,7 +683,8 @@ int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int h
   DCV_REQUIRE(dz && y && s_nc, "norm_bwd_reduce: null pointer");
   if (check_nc("norm_bwd_reduce", n, hw, c)) return 1;
   cudaStream_t st = as_stream(stream);
-  zero_accumulator(s_nc, (size_t)n * c * kBwdSums * sizeof(float), st, acc_prezeroed != 0);
+  zero_accumulator(s_nc, (size_t)n * c * kBwdSums * sizeof(float), st, (acc_prezeroed & DCV_ACC_PREZEROED) != 0);
+  if ((acc_prezeroed & DCV_STATS_CHANNEL_TOTALS) && (long long)n * hw < (1ll << 31)) { hw *= n; n = 1; }   // as dcv_norm_stats: totals credited to image 0
   dim3 grid; int block;
   DCV_DISPATCH_DTYPE(dtype, T, {
     constexpr int VE = 16 / sizeof(T);

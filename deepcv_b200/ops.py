@@ -289,6 +289,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 # 0.45 ms of statistics kernels but lengthens the convolution epilogues — which are on these kernels' critical path — by more: 7.05 -> 7.22 ms
 # (64-channel halo kernel 77 -> 90 us with per-thread partial sums, 128 / 256-channel kernels 60 -> 90 us with a per-tile butterfly, stem 402 -> 594 us).
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
+_CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
 
 
@@ -343,8 +344,8 @@ class _ConvBlock(torch.autograd.Function):
         w_op = _weight_operand(weight, x.dtype, sctx)
         y = empty_nhwc(n, k, p, q, x.dtype, dev)
         stats = _acc_empty((n, k, 2), dev, sctx) if cfg.any else None
-        # BatchNorm alone needs per-channel totals only: the tcgen05 kernels then produce the statistics in their epilogue (DCV_STATS_CHANNEL_TOTALS)
-        totals = 2 if (cfg.use_bn and not cfg.use_gn and _FUSE_STATS) else 0
+        # BatchNorm alone needs per-channel totals only (DCV_STATS_CHANNEL_TOTALS): the batch is reduced as one image; opt-in: in the tcgen05 epilogue
+        totals = (2 | (4 if _FUSE_STATS else 0)) if (cfg.use_bn and not cfg.use_gn and _CHANNEL_TOTALS) else 0
         # Convolutions the implicit-GEMM tensor-core kernel cannot address directly (few input channels / strides: the 7x7 stride-2 stem) go
         # through an explicit im2col: conv(x, w) == 1x1 conv of col[n][p][q][kpad] with the weights zero-padded to [K][kpad].
         rsc = shape.r * shape.s * shape.c
@@ -407,7 +408,8 @@ class _ConvBlock(torch.autograd.Function):
         pqr = d_bn_w = d_bn_b = d_gn_w = d_gn_b = None
         if cfg.any:
             s_nc = _acc_empty((n, k, 2), dev, sctx)
-            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, pz, st), 'norm_bwd_reduce')
+            totals = 2 if (cfg.use_bn and not cfg.use_gn and _CHANNEL_TOTALS) else 0
+            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, pz | totals, st), 'norm_bwd_reduce')
             pqr = torch.empty((n, k, 3), **f32)
             if cfg.use_bn and bn_w is not None:
                 d_bn_w, d_bn_b = targets.get('bn_w', None), targets.get('bn_b', None)

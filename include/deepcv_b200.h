@@ -104,10 +104,11 @@ int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void
                           int act, float slope, int acc_prezeroed, void* stream);
 /* dw_col[K][kpad] (fp32, gather K order, overwritten) = sum over pixels of dy * im2col(x); unpack with dcv_gather_unpack_wgrad. */
 int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, int acc_prezeroed, void* stream);
-/* Flags of the `acc_prezeroed` argument of dcv_conv2d_fwd / dcv_conv2d_fwd_gather (other entry points: 0 / 1). */
+/* Flags of the `acc_prezeroed` argument of dcv_conv2d_fwd / dcv_conv2d_fwd_gather / dcv_norm_stats / dcv_norm_bwd_reduce (other entry points: 0 / 1). */
 #define DCV_ACC_PREZEROED 1          /* the caller has zeroed every accumulator this call adds into */
-#define DCV_STATS_CHANNEL_TOTALS 2   /* only the per-CHANNEL totals of stats_nc will be used (a BatchNorm-only block: no GroupNorm / InstanceNorm): the
-                                      * tcgen05 kernels then produce the statistics in their epilogue, credited to image 0 (rows of the other images zero) */
+#define DCV_STATS_CHANNEL_TOTALS 2   /* only the per-CHANNEL totals of the [n][c][..] sums will be used (a BatchNorm-only block: no GroupNorm / InstanceNorm):
+                                      * they are credited to image 0 (rows of the other images stay zero) and the batch is reduced as one image */
+#define DCV_STATS_IN_EPILOGUE 4      /* with DCV_STATS_CHANNEL_TOTALS: the tcgen05 convolution kernels produce the statistics in their epilogue (opt-in) */
 /* y = act(conv(x, w) + bias); if stats_nc != NULL also accumulates per-(image, channel) sum(y) and sum(y*y) of the
  * values written to y into stats_nc[n][k][2] (fp32, overwritten). bias may be NULL. */
 int dcv_conv2d_fwd(const dcv_conv_shape* shape, const void* x, const void* w, const float* bias, void* y, float* stats_nc,

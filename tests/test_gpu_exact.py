@@ -51,10 +51,10 @@ def _assert_equal(got, ref, what):
 
 def _check_epilogue_statistics(run, yd, y_ref, n, k, dev):
     """ BatchNorm statistics of the tcgen05 forward kernels. Flag 0: per-(image, channel) sums of the stored values (statistics kernel behind the
-    convolution). DCV_STATS_CHANNEL_TOTALS (2): the epilogue produces per-CHANNEL totals, credited to image 0 (rows of the other images stay zero) —
-    what a BatchNorm-only block needs. Sums of integers are exact in fp32 (< 2^24); the squares may exceed that: 1e-6 relative. Same output tensor. """
+    convolution). DCV_STATS_CHANNEL_TOTALS (2): per-CHANNEL totals, credited to image 0 (rows of the other images stay zero) — what a BatchNorm-only
+    block needs — from the statistics kernel walking the batch as one image; | DCV_STATS_IN_EPILOGUE (6): produced by the convolution epilogue. Sums of integers are exact in fp32 (< 2^24); the squares may exceed that: 1e-6 relative. Same output tensor. """
     yb = y_ref.detach().bfloat16().float()
-    for flags in (0, 2):
+    for flags in (0, 2, 6):
         stats = torch.full((n, k, 2), 7., device=dev)
         yd2 = torch.full_like(yd, 7.)
         run(yd2, stats, flags)
