@@ -361,6 +361,7 @@ def measure_workload(name, args, dev, world, rank, local_rank, peaks):
     import torch.distributed as dist
     from deepcv_b200 import ops
     from deepcv_b200.meta.base_module import DeepcvModule
+    from deepcv_b200.meta.data.datasets import dataloader_prefetch_batches
     from deepcv_b200.meta.data.preprocess import FusedPreprocess
     from deepcv_b200.meta.flat_params import FlatAdamW, flatten_parameters
     from deepcv_b200.meta.ignite_training import CrossEntropyLoss, DataParallelModel, Engine, make_process_function
@@ -462,12 +463,13 @@ def measure_workload(name, args, dev, world, rank, local_rank, peaks):
 
     def e2e_run(n_warm, warm):
         n = n_warm if warm else e2e_steps
-        trainer.run([(pool_host[i % n_host], labels_host[i % n_host]) for i in range(n)], max_epochs=trainer.state.epoch + 1)
+        # `dataloader_prefetch_batches` (reference meta/data/datasets.py:76-115, what train() applies to a pinned loader): batch i + 1 is copied while step i runs
+        trainer.run(dataloader_prefetch_batches([(pool_host[i % n_host], labels_host[i % n_host]) for i in range(n)], dev), max_epochs=trainer.state.epoch + 1)
     ms_e2e = timed(e2e_run, 3)
     e2e_value = world * batch * e2e_steps / (ms_e2e / 1e3)
     h2d = batch_bytes + batch * 8 + batch * (1 + 8) + 4    # images + int64 labels + flip (u8) / crop (2 x i32) + learning rate
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * len(losses), ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps,
-               api='ignite_training.Engine(make_process_function(...)).run(loader of pinned uint8 batches)')
+               api='ignite_training.Engine(make_process_function(...)).run(dataloader_prefetch_batches(loader of pinned uint8 batches))')
 
     result = dict(value=value, unit=UNIT, steps=steps, warmup=warmup, ms_per_step=ms / steps, e2e=e2e, gpu_launches=int(launches_per_step * steps), launches_per_step=int(launches_per_step),
                   clocks=dict(clocks.summary(*clock_window), remeasured=remeasured),

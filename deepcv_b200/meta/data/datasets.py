@@ -1,0 +1,116 @@
+""" Batch prefetching to device memory — host-side mirror of `dataloader_prefetch_batches`
+(/root/reference/src/deepcv/meta/data/datasets.py:76-115; used by `train()` at meta/ignite_training.py:217-218 when `hp['prefetch_batches']`).
+
+The reference monkey-patches `DataLoader.__iter__` so that the NEXT batch is moved to the device (`.to(device, non_blocking=True)`) while the model
+computes on the current one. Same contract here — iterate it and get device-resident batches, no `.to(device)` needed in the training step — built on a
+copy stream and two fixed device buffers per batch tensor:
+
+  * `__next__` #j returns batch j (its host -> device copy was issued during step j-1) after making the compute stream wait for that copy, and
+    immediately issues the copy of batch j+1 into the OTHER buffer on the copy stream, which first waits for everything the compute stream had been
+    given up to that moment (all consumers of the buffer's previous content, batch j-1, were enqueued before the caller asked for batch j);
+  * the copy of batch j+1 therefore overlaps step j: with pinned host batches the 1.6 MB (CIFAR-10, batch 512) / 38.5 MB (224 x 224, batch 256) per
+    step leave the critical path of the CUDA-graph replayed step.
+Fixed buffers (not fresh allocations) so that a captured training step can adopt one of them as its static input. """
+from typing import Any, Iterable, Iterator, List, Optional, Tuple, Union
+
+import torch
+
+__all__ = ['dataloader_prefetch_batches', 'PrefetchedBatches']
+
+
+class PrefetchedBatches:
+    """ Iterable over `loader` whose batches (tuples / lists of tensors, or single tensors) arrive on `device`, copied one batch ahead. """
+
+    def __init__(self, loader: Iterable, device: Union[str, torch.device]):
+        self.loader, self.device = loader, torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._slots: List[Optional[List[torch.Tensor]]] = [None, None]
+
+    def __len__(self) -> int:
+        return len(self.loader)
+
+    def _issue(self, batch: Any, slot: int, after: Optional[torch.cuda.Event] = None) -> Tuple[Any, torch.cuda.Event]:
+        """ Host -> device copy of `batch` into buffer `slot` on the copy stream. Returns (device batch, completion event). """
+        single = isinstance(batch, torch.Tensor)
+        items = [batch] if single else list(batch)
+        bufs = self._slots[slot]
+        if bufs is None or len(bufs) != len(items) or any(isinstance(t, torch.Tensor) and (b is None or b.shape != t.shape or b.dtype != t.dtype) for b, t in zip(bufs, items)):
+            bufs = [torch.empty(t.shape, dtype=t.dtype, device=self.device) if isinstance(t, torch.Tensor) else None for t in items]
+            self._slots[slot] = bufs
+            after = None   # fresh blocks of the caching allocator may be recycled from tensors that work ALREADY enqueued on the compute stream still uses:
+                           # this one copy waits for the stream's current tail (first use of a slot and shape changes only, e.g. a ragged last batch)
+        # The buffer's previous content (two batches ago) must have been consumed: `after` marks the compute stream at the moment the batch in between
+        # was handed out — every consumer of the older batch had been enqueued by then. (Waiting for the stream's CURRENT tail instead would put the
+        # copy behind the step that has just been launched: no overlap at all — measured.)
+        if after is not None:
+            self.copy_stream.wait_event(after)
+        else:
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.copy_stream):
+            out = []
+            for b, t in zip(bufs, items):
+                if isinstance(t, torch.Tensor):
+                    b.copy_(t, non_blocking=True)
+                    out.append(b)
+                else:
+                    out.append(t)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        return (out[0] if single else tuple(out)), done
+
+    def __iter__(self) -> Iterator:
+        return _PrefetchIterator(self)
+
+
+class _PrefetchIterator:
+    """ `__next__` hands out the batch whose copy is in flight and (unless the consumer already did, see `prefetch`) issues the next one. A training
+    step that knows this iterator (`engine._dataloader_iter`, as the reference's `process_function` does, meta/ignite_training.py:235-237) calls
+    `prefetch()` right AFTER it has launched its work: the host-side cost of issuing the copy then hides under the device time of the step instead of
+    preceding it. """
+
+    def __init__(self, owner: PrefetchedBatches):
+        self._owner, self._it = owner, iter(owner.loader)
+        self._slot, self._pending, self._exhausted, self._handed_out = 0, None, False, None
+        self._prefetched_batch = None      # the attribute the reference's process_function looks for
+        self.prefetch()
+
+    def prefetch(self) -> None:
+        """ Issues the host -> device copy of the next batch (no-op when one is already in flight or the loader is exhausted). """
+        if self._pending is not None or self._exhausted:
+            return
+        try:
+            batch = next(self._it)
+        except StopIteration:
+            self._exhausted = True
+            return
+        self._pending = self._owner._issue(batch, self._slot, self._handed_out)
+        self._prefetched_batch = self._pending[0]
+        self._slot ^= 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        self.prefetch()
+        if self._pending is None:
+            raise StopIteration
+        batch, done = self._pending
+        self._pending = None
+        current = torch.cuda.current_stream(self._owner.device)
+        self._handed_out = torch.cuda.Event()
+        self._handed_out.record(current)     # everything enqueued so far (the consumers of all earlier batches) precedes the next-but-one copy
+        current.wait_event(done)
+        return batch
+
+
+def dataloader_prefetch_batches(dataloader: Iterable, device: Union[None, str, torch.device] = None) -> Iterable:
+    """ reference :76-115. Returns an iterable that prefetches the next batch of `dataloader` to `device` during the computation on the current one;
+    `dataloader` itself when `device` is None / 'cpu' (the reference warns and returns the loader unchanged, too) or when it does not pin its batches. """
+    import logging
+    if device is None or torch.device(device).type != 'cuda':
+        logging.warning(f'Warning: DataLoader wont prefetch data batches as given `device` argument is `{device}` when prefetching is aimed at GPU(s).')
+        return dataloader
+    if getattr(dataloader, 'pin_memory', True) is False:
+        logging.warning(f'Warning: DataLoader wont prefetch data batches: set `pin_memory=True` in your DataLoader when instanciating `{type(dataloader).__name__}`')
+        return dataloader
+    return PrefetchedBatches(dataloader, device)

@@ -330,7 +330,13 @@ def make_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDi
             runner = runners[key] = GraphedTrainStep(model, losses, optimizer, x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), preprocess=preprocess,
                                                      restore_state=True, adopt_inputs=adopt)
         runner.step(x, y)
-        return {n: float(v) for n, v in zip(runner.static_losses.keys(), torch.stack(list(runner.static_losses.values())).tolist())}
+        # the step is launched; whatever the host still has to do for the NEXT step hides under its device time: the copy of the next batch (a
+        # prefetching loader: reference meta/data/datasets.py:76-115) and the draw of its augmentation parameters. Then the one sync of the step.
+        prefetch = getattr(getattr(engine, '_dataloader_iter', None), 'prefetch', None)
+        if prefetch is not None:
+            prefetch()
+        runner.prepare_next()
+        return {n: float(v) for n, v in zip(runner.static_losses.keys(), runner.read_losses())}
     process_function.runners = runners
     return process_function
 
@@ -363,6 +369,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.static_losses: 'OrderedDict[str, torch.Tensor]' = OrderedDict()
         self.static_loss = None
+        self._drawn, self._loss_pack, self._loss_host = None, None, None
         inner = model.module if isinstance(model, DataParallelModel) else model
         self.flat: Optional[FlatParameters] = getattr(optimizer, '_flat', None) or getattr(inner, '_flat_parameters', None)
         if isinstance(optimizer, FlatAdamW) and optimizer._flat is None and self.flat is not None:
@@ -484,16 +491,43 @@ class GraphedTrainStep:
         if y.data_ptr() != self.static_y.data_ptr():
             self.static_y.copy_(y, non_blocking=True)
         if self.preprocess is not None:
-            self.preprocess.train()   # the captured step is a TRAINING step (reference :246 `model.train()`): an evaluation pass in between must not freeze the draws
-            flip, crop = self.preprocess.draw(x.shape[0])
-            if flip is not None:
-                self._host_flip.copy_(flip)
-                self._host_crop.copy_(crop)
+            if not self._drawn:
+                self.prepare_next()
+            if self._drawn == 'params':
                 self.static_flip.copy_(self._host_flip, non_blocking=True)
                 self.static_crop.copy_(self._host_crop, non_blocking=True)
+            self._drawn = None
         self.optimizer.set_lr_device()
         self.graph.replay()
         return self.static_loss
+
+    def prepare_next(self) -> None:
+        """ Draws the NEXT step's per-sample augmentation parameters into the pinned staging buffers (host work that may run while the device executes
+        the current step; the draw order of the generator is unchanged). """
+        if self.preprocess is None or self._drawn:
+            return
+        self.preprocess.train()   # the captured step is a TRAINING step (reference :246 `model.train()`): an evaluation pass in between must not freeze the draws
+        flip, crop = self.preprocess.draw(self.static_x.shape[0])
+        if flip is not None:
+            self._host_flip.copy_(flip)
+            self._host_crop.copy_(crop)
+            self._drawn = 'params'
+        else:
+            self._drawn = 'none'
+
+    def read_losses(self) -> List[float]:
+        """ The loss terms of the step just replayed, as floats: ONE device -> host copy (the step's only synchronisation, the reference's `.item()`). """
+        vals = list(self.static_losses.values())
+        if self._loss_pack is None or self._loss_pack.numel() != len(vals):
+            self._loss_pack = torch.empty(len(vals), dtype=torch.float32, device=vals[0].device)
+            self._loss_host = torch.empty(len(vals), dtype=torch.float32).pin_memory()
+        if len(vals) == 1:
+            self._loss_host.copy_(vals[0].reshape(1), non_blocking=True)
+        else:
+            torch.stack(vals, out=self._loss_pack)
+            self._loss_host.copy_(self._loss_pack, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._loss_host.tolist()
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -687,6 +721,9 @@ def train(hp: HYPERPARAMS_T, model: torch.nn.Module, losses, datasets: Dict[str,
         sampler = torch.utils.data.distributed.DistributedSampler(ds) if (is_train and world > 1) else None
         return DataLoader(ds, batch_size=batch_size, shuffle=is_train and sampler is None, sampler=sampler, num_workers=hp['num_workers'], pin_memory=backend_conf.is_cuda, drop_last=is_train)
     train_loader = _loader(trainset, hp['batch_size'], True)
+    if hp['prefetch_batches'] and backend_conf.is_cuda and isinstance(train_loader, DataLoader):   # reference :217-218 (host-resident datasets only: a DeviceDataLoader has nothing to copy)
+        from .data.datasets import dataloader_prefetch_batches
+        train_loader = dataloader_prefetch_batches(train_loader, device)
     eval_sets = {n: ds for n, ds in named.items() if n != 'trainset' and ds is not None}
 
     losses = _setup_ignite_losses(losses, loss_weights=loss_weights, device=device)

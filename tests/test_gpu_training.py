@@ -172,3 +172,31 @@ def test_cross_entropy_ignored_and_invalid_targets(dev):
     bad = target.clone()
     bad[1] = 7     # out of range: NaN, not an out-of-bounds read
     assert torch.isnan(ops.cross_entropy(ld.detach(), bad.to(dev)))
+
+
+def test_prefetched_batches_order_values_and_overlap_safety(dev):
+    """ `dataloader_prefetch_batches` (reference meta/data/datasets.py:76-115): batches arrive on the device, in order, with the right values, while the
+    consumer keeps the compute stream busy (the double buffers are only rewritten after their consumers were enqueued); a ragged last batch, a
+    single-tensor loader and the CPU / unpinned cases the reference returns unchanged. """
+    from deepcv_b200.meta.data.datasets import PrefetchedBatches, dataloader_prefetch_batches
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randint(0, 256, (64, 32, 32, 3), generator=g, dtype=torch.uint8).pin_memory(), torch.randint(0, 10, (64,), generator=g).pin_memory()) for _ in range(7)]
+    batches.append((torch.randint(0, 256, (5, 32, 32, 3), generator=g, dtype=torch.uint8).pin_memory(), torch.randint(0, 10, (5,), generator=g).pin_memory()))
+    loader = dataloader_prefetch_batches(batches, dev)
+    assert isinstance(loader, PrefetchedBatches) and len(loader) == 8
+    busy = torch.randn(2048, 2048, device=dev)
+    sums, labels = [], []
+    for x, y in loader:
+        assert x.is_cuda and y.is_cuda and x.dtype == torch.uint8
+        for _ in range(3):
+            busy = (busy @ busy).clamp_(-1, 1)          # the consumer's step: queued work that reads the batch only afterwards
+        sums.append(x.sum(dtype=torch.int64) + busy[0, 0].long() * 0)
+        labels.append(y.clone())
+    torch.cuda.synchronize()
+    assert [int(s) for s in sums] == [int(b[0].sum(dtype=torch.int64)) for b in batches]
+    bad = [i for i, (l, b) in enumerate(zip(labels, batches)) if not torch.equal(l.cpu(), b[1])]
+    assert not bad, (bad, [(labels[i][:6].tolist(), batches[i][1][:6].tolist()) for i in bad])
+    singles = [torch.full((4, 3), float(i)).pin_memory() for i in range(3)]
+    assert [float(t[0, 0]) for t in dataloader_prefetch_batches(singles, dev)] == [0., 1., 2.]
+    assert dataloader_prefetch_batches(batches, 'cpu') is batches and dataloader_prefetch_batches(batches, None) is batches
+    assert list(dataloader_prefetch_batches([], dev)) == []
