@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 #include "../../include/deepcv_b200.h"
 
@@ -106,6 +107,28 @@ struct FastDiv {  // n / d for 0 <= n < 2^31, d >= 1
   __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (uint32_t)(((uint64_t)n * mul) >> 31) >> shr; }
 };
 
+
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------------------------------------
+// `launch_pdl` launches with cudaLaunchAttributeProgrammaticStreamSerialization: the kernel's CTAs may be scheduled while the previous kernel of the stream
+// is still draining. Such a kernel calls `pdl_wait()` before its first access to global data of its predecessor — it returns once the predecessor has
+// completed and flushed — and `pdl_trigger()` right after, which lets its own successor begin to launch. What overlaps is the launch ramp and a prologue
+// that touches no fresh data (zeroed tiles, weight fragments). Used by the few-channel kernels (conv_small.cu: a chain of 18 latency-bound kernels of
+// 10-20 us per CIFAR step, -13 us per step, also inside the captured graph). Measured and NOT adopted library-wide (round 2): with every kernel of the
+// ImageNet-shaped step launched this way the step got 1.3 % slower and the overlapped host -> device prefetch collapsed (7.14 -> 8.56 ms end to end).
+// DCV_NO_PDL=1: plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool use_pdl() { static const bool on = getenv("DCV_NO_PDL") == nullptr; return on; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // Accumulator buffers (per-(n,c) statistics, gradient sums filled by atomics) are normally zeroed by the launcher that fills them: one memset node

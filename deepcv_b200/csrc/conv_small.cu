@@ -244,13 +244,8 @@ __device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t* r) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// Programmatic dependent launch: these kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may become
-// resident while its predecessor in the stream is still draining. Everything that does not depend on the predecessor (zeroing the tile, building the
-// weight fragments: the weights were written several kernels earlier) runs first; `pdl_wait` then blocks until the predecessor has completed and its
-// writes are visible, and `pdl_trigger` lets the NEXT kernel of the stream start its own prologue. The step is a chain of ~35 latency-bound kernels of
-// 10-20 us: launch ramp + drain (~5 us each) is what this overlaps.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// (pdl_wait / pdl_trigger: common.cuh. Here the wait comes AFTER everything that does not depend on the predecessor: zeroing the tile, building the
+// weight fragments — the weights were written several kernels earlier.)
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -951,19 +946,6 @@ static int num_ctas(int n) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = kNumSMs; }
   return n < 4 * sms ? n : 4 * sms;
-}
-
-// Launch with programmatic stream serialization (see pdl_wait): the kernel may start while its predecessor in the stream drains. DCV_NO_PDL=1: plain launches.
-static bool use_pdl() { static const bool on = getenv("DCV_NO_PDL") == nullptr; return on; }
-template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 template <typename K> static int set_smem(K kern, size_t bytes) {
