@@ -70,6 +70,8 @@ SYMBOLS = {
     'dcv_sc_conv_fwd': (c_int, [POINTER(ConvShape), P, POINTER(ScNorm), c_int, P, P, c_int, c_float, P, POINTER(ScNorm), P]),
     'dcv_sc_conv_wgrad': (c_int, [POINTER(ConvShape), P, POINTER(ScNorm), P, P, POINTER(ScNorm), c_int, c_float, P, P, P, P, P, P, P]),
     'dcv_sc_conv_dgrad': (c_int, [POINTER(ConvShape), P, P, POINTER(ScNorm), c_int, c_float, P, P, P, POINTER(ScNorm), P]),
+    'dcv_sc_conv_bwd_supported': (c_int, [POINTER(ConvShape), c_int]),
+    'dcv_sc_conv_bwd': (c_int, [POINTER(ConvShape), P, POINTER(ScNorm), P, P, POINTER(ScNorm), c_int, c_float, P, P, P, P, P, P, P, P, P]),
     'dcv_sc_affine_pool_fwd': (c_int, [P, POINTER(ScNorm), c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_sc_affine_pool_bwd': (c_int, [P, P, POINTER(ScNorm), P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_peer_flag_words': (c_size_t, []),

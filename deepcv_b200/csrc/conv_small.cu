@@ -315,10 +315,15 @@ template <int CI, int NTHR, typename Src, int PF = kPF> struct Stager {
       for (int i = 0; i < PF; ++i) { const int v = tid + i * NTHR; if (v < nvec) raw[i] = src.fetch(e_img + (size_t)v * 8); }
     }
   }
+  float* vsum = nullptr;   // when set: 8 running sums of the (bf16-rounded) staged values per vector slot (the bias gradient; vector route only)
   __device__ __forceinline__ void put(bf16* tile, const Src& src, const typename Src::Raw& r, int v, int W, int wlog, int Wp, int PAD) const {
     const int e0 = v * 8, pix = e0 / CI, c0 = e0 % CI, y = pix >> wlog, x = pix & (W - 1);
     float f[8];
     src.decode(r, c0, CI - 1, f);
+    if (vsum) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vsum[i] += round_bf(f[i]);
+    }
     bf16* dst = tile + ((size_t)(y + PAD) * Wp + x + PAD) * CI + c0;
     if (CI == 4) {   // two pixels of 8 bytes each (x is even, so both are in the same row)
       *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
@@ -422,8 +427,11 @@ template <int CI, int NO, int KS> struct Core {
   }
 
   template <typename Pre, typename Epi>
-  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Pre pre, Epi epi) const {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  __device__ __forceinline__ void run(const bf16* tile, int H, int W, int Wp, Pre pre, Epi epi) const { run_w(tile, H, W, Wp, pre, epi, threadIdx.x >> 5); }
+  // `warp`: index of this warp among the kWarps warps that share the image (a CTA may hold several such groups)
+  template <typename Pre, typename Epi>
+  __device__ __forceinline__ void run_w(const bf16* tile, int H, int W, int Wp, Pre pre, Epi epi, const int warp) const {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint32_t tile_u = smem_u32(tile);
     const int wlog = 31 - __clz(W);
     const int mtiles = G::PAIR ? H * W / 32 : H * W / 16;
@@ -828,6 +836,197 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs
   if (a.dbias && tid < a.k_out) atomicAdd(a.dbias + tid, sh_db[tid]);
 }
 
+// ---- backward of a block in ONE launch: data gradient + weight gradient ---------------------------------------------------------------------------
+// Both gradients of a layer read the same dy = act'(y)*(P*dz + Q*y + R); as two kernels it was fetched, decoded and staged twice and the launch ramp /
+// coefficient prologue paid twice (per layer: 23-35 us + 15-20 us). Here a group of 4 warps (two groups = two images per CTA, as in the weight-gradient
+// kernel) stages the dy HALO tile once — the data gradient's A operand (ldmatrix) and, through per-lane row addresses into the same padded tile, the
+// weight gradient's B operand (ldmatrix.trans) — plus the normalised input tile z, then runs the data-gradient GEMM (dx, the producer's backward sums)
+// and the weight-gradient GEMM back to back. One image per group and launch (no persistent loop: the weight-gradient accumulators are only live after
+// the data-gradient phase, so both phases fit the 128-register budget). Served: 4->4 5x5, 4->16 3x3, 16->16 3x3 (the layers of the default net with a
+// data gradient); everything else runs the two kernels above.
+struct BwdArgs {
+  int n, h, w, c_in, k_out, act; float slope;
+  const bf16* x; const bf16* dz; const bf16* y; const bf16* wgt; bf16* dx;
+  float* dw; float* dbias; float* d_bn_w; float* d_bn_b; float* d_gn_w; float* d_gn_b;
+  dcv_sc_norm xn, yn;
+};
+
+template <int CI, int KI, int KS> struct BwdLayout {
+  typedef Geo<CI, KI, KS> WG;   // weight gradient: rows from the z tile (CI channels), columns = output channels (KI)
+  static constexpr int MT = (WG::NCH + 1) / 2, NT = WG::NT, ND = NT * 8;
+  __host__ __device__ static size_t group_bytes(int h, int w) { return (size_t)(h + KS - 1) * (w + KS - 1) * (CI + KI) * 2; }
+  __host__ __device__ static size_t reduce_bytes() { return (size_t)kWgWarps * MT * 16 * ND * 4; }
+  __host__ __device__ static size_t smem_bytes(int h, int w) { const size_t a = 2 * group_bytes(h, w), b = reduce_bytes(); return a > b ? a : b; }
+};
+
+template <int CI, int KI, int KS>
+__global__ void __launch_bounds__(kWgThreads, 2) sc_bwd_kernel(const BwdArgs a) {
+  static_assert((CI == 4 && KI == 4 && KS == 5) || (CI == 4 && KI == 16 && KS == 3) || (CI == 16 && KI == 16 && KS == 3), "combination not served");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef Core<KI, CI, KS> DC;      // data gradient: tile = dy (KI channels), GEMM columns = input channels
+  typedef BwdLayout<CI, KI, KS> L;
+  typedef typename L::WG WG;
+  constexpr int PAD = KS / 2, DNT = DC::NT, MT = L::MT, NT = L::NT, ND = L::ND;
+  const int H = a.h, W = a.w, Hp = H + KS - 1, Wp = W + KS - 1, HW = H * W, wlog = 31 - __clz(W);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int group = warp / kGrpWarps, gtid = tid - group * kGrp, gwarp = warp - group * kGrpWarps;
+  bf16* ztile = reinterpret_cast<bf16*>(smem_raw + (size_t)group * L::group_bytes(H, W));   // [Hp][Wp][CI]
+  bf16* dyt = ztile + (size_t)Hp * Wp * CI;                                                  // [Hp][Wp][KI]  (halo tile)
+  __shared__ Coef cfx[2], cfy[2], cfp[2];
+  __shared__ float sh_part[2][kWarps][kMaxN][2];
+  __shared__ float sh_s[2][kMaxC][2];
+  __shared__ float sh_db[kMaxC];
+  for (int i = gtid; i < Hp * Wp * (CI + KI) / 8; i += kGrp) reinterpret_cast<uint4*>(ztile)[i] = make_uint4(0u, 0u, 0u, 0u);   // both tiles (contiguous)
+  if (tid < kMaxC) sh_db[tid] = 0.f;
+  DC core;
+  const unsigned short* wb = reinterpret_cast<const unsigned short*>(a.wgt);
+  core.setup(Wp, [&](int r, int s, int k, int o) -> uint32_t {
+    return (k < a.k_out && o < a.c_in) ? (uint32_t)wb[((size_t)(k * KS + (KS - 1 - r)) * KS + (KS - 1 - s)) * a.c_in + o] : 0u;
+  });
+  const int mi = lane >> 3, li = lane & 7;
+  int aoff[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) aoff[mt] = WG::chunk_off(2 * mt + (mi & 1), Wp);
+  const uint32_t ztile_u = smem_u32(ztile), dyt_u = smem_u32(dyt);
+  pdl_wait();
+  pdl_trigger();
+  const int img = blockIdx.x * 2 + group;
+  const bool active = img < a.n;
+  float db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) db[i] = 0.f;
+  SrcPlain sx{a.x, a.xn.enabled ? &cfx[group] : nullptr};
+  SrcDy sd{a.dz, a.y, a.yn.enabled ? &cfy[group] : nullptr, a.act, a.slope};
+  if (active) {
+    const size_t e_img = (size_t)img * HW * a.c_in, k_img = (size_t)img * HW * a.k_out;
+    Stager<CI, kGrp, SrcPlain> stx;
+    Stager<KI, kGrp, SrcDy, 2> std_;
+    std_.vsum = db;
+    stx.fetch(sx, e_img, HW, a.c_in, gtid);
+    std_.fetch(sd, k_img, HW, a.k_out, gtid);
+    if (gwarp == 0 && a.xn.enabled) load_coeffs(a.xn, img, cfx[group]);
+    if (gwarp == 1 && a.yn.enabled) norm_backward_pqr(a.yn, img, cfy[group], img == 0, a.d_bn_w, a.d_bn_b, a.d_gn_w, a.d_gn_b);
+    group_sync(group);   // coefficients ready, tiles zeroed
+    stx.store(ztile, sx, e_img, H, W, Wp, PAD, a.c_in, gtid);
+    std_.store(dyt, sd, k_img, H, W, Wp, PAD, a.k_out, gtid);
+    group_sync(group);
+    // ---- data gradient (+ the producer's backward sums)
+    float s1[DNT][2], s2[DNT][2];
+#pragma unroll
+    for (int nt = 0; nt < DNT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
+    uint32_t yraw[2 * DNT];
+    core.run_w(dyt, H, W, Wp, [&](int y, int x, int o, int slot) {
+      if (a.xn.enabled && o < a.c_in) yraw[slot] = *reinterpret_cast<const uint32_t*>(a.x + e_img + ((size_t)y * W + x) * a.c_in + o);
+    }, [&](int y, int x, int o, float v0, float v1, int slot) {
+      if (o < a.c_in) {
+        const size_t e = e_img + ((size_t)y * W + x) * a.c_in + o;
+        v0 = round_bf(v0); v1 = round_bf(v1);
+        *reinterpret_cast<uint32_t*>(a.dx + e) = pack2(v0, v1);   // c_in is even on this path (host check)
+        if (a.xn.enabled) {
+          const uint32_t yr = yraw[slot];
+          const int nt = slot >> 1;
+          s1[nt][0] += v0; s1[nt][1] += v1; s2[nt][0] = fmaf(v0, bf_lo(yr), s2[nt][0]); s2[nt][1] = fmaf(v1, bf_hi(yr), s2[nt][1]);
+        }
+      }
+    }, gwarp);
+    if (a.xn.enabled) {
+#pragma unroll
+      for (int nt = 0; nt < DNT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          reduce_cols_to_slot(s1[nt][e], &sh_part[group][gwarp][nt * 8 + 2 * t + e][0]);
+          reduce_cols_to_slot(s2[nt][e], &sh_part[group][gwarp][nt * 8 + 2 * t + e][1]);
+        }
+      group_sync(group);
+      if (gwarp == 0) {
+        if (lane < a.c_in) { sh_s[group][lane][0] = fold_cols<typename DC::G>(sh_part[group], lane, 0); sh_s[group][lane][1] = fold_cols<typename DC::G>(sh_part[group], lane, 1); }
+        __syncwarp();
+        norm_backward_image_sums(a.xn, img, cfp[group], &sh_s[group][0][0]);
+      }
+    }
+  }
+  // ---- weight gradient: D[(tap, c)][k] += z^T dy over the image's k-steps, split over the group's warps
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  if (active) {
+    const int nks = WG::PAIR ? HW / 32 : HW / 16;
+    for (int ks = gwarp; ks < nks; ks += kGrpWarps) {
+      const int ka = ks * 16 + (mi >> 1) * 8 + li, kb = ks * 16 + (mi & 1) * 8 + li;
+      int ya, xa, yb, xb;
+      if (WG::PAIR) { ya = ka >> (wlog - 1); xa = (ka & ((W >> 1) - 1)) * 2; yb = kb >> (wlog - 1); xb = (kb & ((W >> 1) - 1)) * 2; }
+      else { ya = ka >> wlog; xa = ka & (W - 1); yb = kb >> wlog; xb = kb & (W - 1); }
+      const uint32_t abase = ztile_u + (uint32_t)((ya * Wp + xa) * WG::PIXB);
+      const uint32_t bpix = (uint32_t)((yb + PAD) * Wp + xb + PAD);   // the dy tile has a halo: pixel (y, x) sits at (y + PAD, x + PAD)
+      uint32_t b[NT][2];
+      if (NT == 1) {             // 4 -> 4 channels, 5x5: a row = pixel pair = (parity, 4 channels); PAD = 2 keeps it 16-byte aligned
+        ldsm_x2_t(dyt_u + bpix * (KI * 2), b[0]);
+      } else {
+#pragma unroll
+        for (int h = 0; h < NT / 2; ++h) {
+          const int nt = 2 * h + (mi >> 1);
+          uint32_t r4[4];
+          ldsm_x4_t(dyt_u + (WG::PAIR ? ((bpix + (nt >> 1)) * KI + (nt & 1) * 8) * 2 : (bpix * KI + nt * 8) * 2), r4);
+          b[2 * h][0] = r4[0]; b[2 * h][1] = r4[1]; b[2 * h + 1][0] = r4[2]; b[2 * h + 1][1] = r4[3];
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t af[4];
+        ldsm_x4_t(abase + aoff[mt], af);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma16816(acc[mt][nt], af, b[nt][0], b[nt][1]);
+      }
+    }
+    // bias gradient: slot i of a thread is channel (c0 + i) & (kv - 1), c0 = (gtid * 8) % kv
+    const int kv = a.k_out;
+    if (kv == 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { db[i] += db[i + 4]; db[i + 4] = 0.f; }
+    }
+    const int stride = kv >= 8 ? kv / 8 : 1, nval = kv == 4 ? 4 : 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nval) {
+        float v = db[i];
+        for (int o = 16; o >= stride; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < stride) atomicAdd(&sh_db[(lane * 8 + i) & (kv - 1)], v);
+      }
+    }
+  }
+  // ---- the 8 warps' D tiles -> shared memory (plain stores; the tiles' space is free), one thread per dw element adds its sources, one global atomic each
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_raw);   // [kWgWarps][MT * 16][ND]
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float* d0 = red + ((size_t)warp * MT * 16 + mt * 16 + g) * ND + nt * 8 + 2 * t;
+      *reinterpret_cast<float2*>(d0) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(d0 + 8 * ND) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+  __syncthreads();
+  const int total = a.k_out * KS * KS * a.c_in;
+  for (int i = tid; i < total; i += kWgThreads) {
+    const int c = i % a.c_in, tap = (i / a.c_in) % (KS * KS), o = i / (a.c_in * KS * KS), r = tap / KS, s_ = tap % KS;
+    float v = 0.f;
+    if (WG::PAIR) {
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int sp = s_ + par, m = (r * WG::CPR + (sp >> 1)) * 8 + (sp & 1) * 4 + c, n = par * KI + o;
+        for (int w = 0; w < kWgWarps; ++w) v += red[((size_t)w * MT * 16 + m) * ND + n];
+      }
+    } else {
+      const int m = tap * 16 + c;
+      for (int w = 0; w < kWgWarps; ++w) v += red[((size_t)w * MT * 16 + m) * ND + o];
+    }
+    if (v != 0.f) atomicAdd(a.dw + i, v);
+  }
+  if (a.dbias && tid < a.k_out) atomicAdd(a.dbias + tid, sh_db[tid]);
+}
+
 // ---- normalise (+ average-pool) a raw output into a plain tensor: the consumer of a pending normalisation that is not one of the kernels above ----------
 // zp[n][oy][ox][c] = A[n][c] * mean_{pool x pool}(y) + B[n][c]   (pooling is linear and the affine is per (image, channel): pool(z) = A*pool(y) + B).
 struct PoolArgs { int n, h, w, c, pool, update_running; const bf16* y; bf16* z; const bf16* dzp; bf16* dz; dcv_sc_norm nd; };
@@ -1065,6 +1264,50 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* s, const void* x, const dcv_sc_norm*
   else SC_WGRAD(16, 16, 3);
 #undef SC_WGRAD
   DCV_LAUNCH_CHECK("sc_wgrad_kernel");
+  return 0;
+}
+
+static int bwd_combo(const dcv_conv_shape* s) {   // 1: <4,4,5>  2: <4,16,3>  3: <16,16,3>  0: not served by the fused backward kernel
+  using namespace dcv::sc;
+  if (!shape_ok(s, DCV_BF16) || s->c % 2 != 0) return 0;
+  const int ci = pick_ci(s->c), ki = pick_ci(s->k);
+  if (s->k != ki) return 0;   // dy is staged with whole 16-byte vectors
+  int combo = 0;
+  size_t smem = 0;
+  if (ci == 4 && ki == 4 && s->r == 5) { combo = 1; smem = BwdLayout<4, 4, 5>::smem_bytes(s->h, s->w); }
+  else if (ci == 4 && ki == 16 && s->r == 3) { combo = 2; smem = BwdLayout<4, 16, 3>::smem_bytes(s->h, s->w); }
+  else if (ci == 16 && ki == 16 && s->r == 3) { combo = 3; smem = BwdLayout<16, 16, 3>::smem_bytes(s->h, s->w); }
+  return (combo && smem <= 100 * 1024) ? combo : 0;
+}
+
+int dcv_sc_conv_bwd_supported(const dcv_conv_shape* shape, int dtype) { return (shape && dtype == DCV_BF16) ? (bwd_combo(shape) != 0) : 0; }
+
+int dcv_sc_conv_bwd(const dcv_conv_shape* s, const void* x, const dcv_sc_norm* x_norm, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope, const void* w,
+                    void* dx, float* dw, float* dbias, float* d_bn_w, float* d_bn_b, float* d_gn_w, float* d_gn_b, void* stream) {
+  using namespace dcv; using namespace dcv::sc;
+  const int combo = s ? bwd_combo(s) : 0;
+  DCV_REQUIRE(combo != 0, "sc_conv_bwd: shape not served by the fused backward kernel (see dcv_sc_conv_bwd_supported)");
+  DCV_REQUIRE(x && dz && y && w && dx && dw, "sc_conv_bwd: null pointer");
+  if (check_norm(x_norm, s->n, s->c, s->h * s->w, "sc_conv_bwd (input)", true) || check_norm(y_norm, s->n, s->k, s->h * s->w, "sc_conv_bwd (output)", true)) return 1;
+  cudaStream_t st = as_stream(stream);
+  BwdArgs a{};
+  a.n = s->n; a.h = s->h; a.w = s->w; a.c_in = s->c; a.k_out = s->k; a.act = act; a.slope = slope;
+  a.x = (const bf16*)x; a.dz = (const bf16*)dz; a.y = (const bf16*)y; a.wgt = (const bf16*)w; a.dx = (bf16*)dx;
+  a.dw = dw; a.dbias = dbias; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b; a.d_gn_w = d_gn_w; a.d_gn_b = d_gn_b;
+  a.xn = norm_or_off(x_norm); a.yn = norm_or_off(y_norm);
+  const int grid = (s->n + 1) / 2;
+#define SC_BWD(CI_, KI_, KS_)                                                              \
+  do {                                                                                     \
+    auto kern = sc_bwd_kernel<CI_, KI_, KS_>;                                              \
+    const size_t smem = BwdLayout<CI_, KI_, KS_>::smem_bytes(s->h, s->w);                  \
+    if (set_smem(kern, smem)) return 1;                                                    \
+    launch_pdl(kern, grid, kWgThreads, smem, st, a);                                       \
+  } while (0)
+  if (combo == 1) SC_BWD(4, 4, 5);
+  else if (combo == 2) SC_BWD(4, 16, 3);
+  else SC_BWD(16, 16, 3);
+#undef SC_BWD
+  DCV_LAUNCH_CHECK("sc_bwd_kernel");
   return 0;
 }
 

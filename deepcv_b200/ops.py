@@ -654,6 +654,7 @@ def pre_norm_act(x: torch.Tensor, norm: NormConfig, training: bool = True, act: 
 # ------------------------------------------------------------------------------------------------------------------------------
 # Few-channel convolution blocks (csrc/conv_small.cu): raw outputs with a PENDING normalisation travel between submodules
 
+_FUSE_SC_BWD = os.environ.get('DCV_NO_SC_FUSED_BWD') is None   # A/B switch: separate weight-gradient and data-gradient launches for the few-channel layers
 _USE_SC = os.environ.get('DCV_NO_SC') is None   # tuning aid: DCV_NO_SC=1 keeps the few-channel layers on the direct kernels + separate normalisation passes
 
 
@@ -772,10 +773,18 @@ class _ScConv(torch.autograd.Function):
             return t if t is not None else torch.empty((k,), dtype=torch.float32, device=dev)
         d_bn_w, d_bn_b = plain('bn_w', cfg.use_bn and ctx.has_affine[0]), plain('bn_b', cfg.use_bn and ctx.has_affine[1])
         d_gn_w, d_gn_b = plain('gn_w', cfg.use_gn and ctx.has_affine[2]), plain('gn_b', cfg.use_gn and ctx.has_affine[3])
+        dx = None
+        if dw is not None and ctx.needs_input_grad[0] and _FUSE_SC_BWD and lib.dcv_sc_conv_bwd_supported(ctypes.byref(shape), DCV_BF16):
+            # one launch for both gradients: the dy tile is staged once (csrc/conv_small.cu, sc_bwd_kernel)
+            dx = empty_nhwc(shape.n, c, shape.h, shape.w, torch.bfloat16, dev)
+            check(lib.dcv_sc_conv_bwd(ctypes.byref(shape), _ptr(x), xlink.ref() if xlink else None, _ptr(dz), _ptr(y), ylink.ref() if ylink else None, meta['act'], meta['slope'],
+                                      _ptr(w_op), _ptr(dx), _ptr(dw), _ptr(dbias), _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'sc_conv_bwd')
+            _backward_done(grad_out, targets)
+            return (dx, None if 'weight' in targets else dw, None if (dbias is None or 'bias' in targets) else dbias, None if (d_bn_w is None or 'bn_w' in targets) else d_bn_w,
+                    None if (d_bn_b is None or 'bn_b' in targets) else d_bn_b, None if (d_gn_w is None or 'gn_w' in targets) else d_gn_w, None if (d_gn_b is None or 'gn_b' in targets) else d_gn_b, None)
         if dw is not None:
             check(lib.dcv_sc_conv_wgrad(ctypes.byref(shape), _ptr(x), xlink.ref() if xlink else None, _ptr(dz), _ptr(y), ylink.ref() if ylink else None, meta['act'], meta['slope'],
                                         _ptr(dw), _ptr(dbias), _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'sc_conv_wgrad')
-        dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(shape.n, c, shape.h, shape.w, torch.bfloat16, dev)
             check(lib.dcv_sc_conv_dgrad(ctypes.byref(shape), _ptr(dz), _ptr(y), ylink.ref() if ylink else None, meta['act'], meta['slope'], _ptr(w_op), _ptr(dx),

@@ -165,6 +165,12 @@ int dcv_sc_conv_wgrad(const dcv_conv_shape* shape, const void* x, const dcv_sc_n
  * producer's raw output `x_raw`. */
 int dcv_sc_conv_dgrad(const dcv_conv_shape* shape, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope, const void* w, void* dx,
                       const void* x_raw, const dcv_sc_norm* x_norm, void* stream);
+/* Both gradients of a block in ONE launch (the dy = act'(y)*(P*dz + Q*y + R) tile is staged once and feeds the data-gradient and the weight-gradient
+ * GEMMs): arguments as dcv_sc_conv_wgrad + dcv_sc_conv_dgrad (x is the layer input — raw when x_norm is enabled; dw / dbias accumulated, dx written).
+ * Served (dcv_sc_conv_bwd_supported): 4 -> 4 channels 5x5, 4 -> 16 and 16 -> 16 channels 3x3 with whole-vector channel counts. */
+int dcv_sc_conv_bwd_supported(const dcv_conv_shape* shape, int dtype);
+int dcv_sc_conv_bwd(const dcv_conv_shape* shape, const void* x, const dcv_sc_norm* x_norm, const void* dz, const void* y, const dcv_sc_norm* y_norm, int act, float slope, const void* w,
+                    void* dx, float* dw, float* dbias, float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream);
 /* z[n][h/pool][w/pool][c] = A*avgpool(y) + B: materialises a pending normalisation (pool = 1) or fuses it with the pool x pool average pooling that follows
  * (meta/submodule_creators.py:163-176); and its backward: dz (full resolution, written) + norm's s_nc / u_sums from dzp. */
 int dcv_sc_affine_pool_fwd(const void* y, const dcv_sc_norm* norm, int update_running, void* z, int n, int h, int w, int c, int pool, void* stream);

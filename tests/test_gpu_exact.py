@@ -209,7 +209,7 @@ def test_direct_kernels_bit_exact(dev, n, c, h, w, k, ks, pad, dtype):
     _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'direct weight gradient')
 
 
-@pytest.mark.parametrize('n,c,h,w,k,ks', [(5, 3, 32, 32, 4, 5), (4, 4, 32, 32, 4, 5), (3, 4, 16, 16, 16, 3), (3, 16, 16, 16, 16, 3), (2, 16, 32, 32, 4, 3), (2, 4, 48, 32, 4, 3), (600, 4, 16, 16, 4, 3)],
+@pytest.mark.parametrize('n,c,h,w,k,ks', [(5, 3, 32, 32, 4, 5), (4, 4, 32, 32, 4, 5), (3, 4, 16, 16, 16, 3), (3, 16, 16, 16, 16, 3), (2, 16, 32, 32, 4, 3), (2, 4, 48, 32, 4, 3), (600, 4, 16, 16, 4, 3), (7, 4, 16, 32, 4, 5), (5, 16, 32, 16, 16, 3)],
                          ids=lambda v: str(v))
 @pytest.mark.parametrize('act', ['none', 'relu'])
 def test_few_channel_mma_kernels_bit_exact(dev, n, c, h, w, k, ks, act):
@@ -250,3 +250,13 @@ def test_few_channel_mma_kernels_bit_exact(dev, n, c, h, w, k, ks, act):
     check(lib.dcv_sc_conv_wgrad(ctypes.byref(shape), P(xd), None, P(dzd), P(yd), None, act_code, 0., P(dwd), P(dbd), None, None, None, None, st), 'sc_conv_wgrad')
     _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'weight gradient')
     _assert_equal(dbd, bias.grad, 'bias gradient')
+    # both gradients in one launch (the dy tile staged once): the layers of the default net that need a data gradient
+    if lib.dcv_sc_conv_bwd_supported(ctypes.byref(shape), DCV_BF16):
+        dx2 = torch.full((n, h, w, c), 7., device=dev, dtype=torch.bfloat16)
+        dw2, db2 = torch.zeros((k, ks, ks, c), device=dev), torch.zeros((k,), device=dev)
+        check(lib.dcv_sc_conv_bwd(ctypes.byref(shape), P(xd), None, P(dzd), P(yd), None, act_code, 0., P(wd), P(dx2), P(dw2), P(db2), None, None, None, None, st), 'sc_conv_bwd')
+        _assert_equal(dx2.permute(0, 3, 1, 2), x.grad.bfloat16(), 'fused backward: data gradient')
+        _assert_equal(dw2.permute(0, 3, 1, 2), wt.grad, 'fused backward: weight gradient')
+        _assert_equal(db2, bias.grad, 'fused backward: bias gradient')
+    else:
+        assert (c, k, ks) not in ((4, 4, 5), (4, 16, 3), (16, 16, 3))
