@@ -257,9 +257,9 @@ def conv_layer_table(batch, dev, peaks):
 def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
     """ Roofline of the dominant kernel of the step, called through the C ABI with preallocated buffers, timed live with CUDA events on the stream it is
     launched on (graph replay, buffers cycled beyond L2).
-      cifar     the few-channel weight-gradient kernel of the 5x5 4 -> 4 channel layers at 32x32: the largest share of the CIFAR step in the ncu launch
-                list (profiles/r02_launch_summary_cifar_warm.txt). HBM-bound by the accounting of SURVEY.md section 8.d (arithmetic intensity 43-72
-                FLOP/B): algorithmic bytes per launch = read x + read dz + read y + write dw.
+      cifar     the fused few-channel backward kernel (data + weight gradient in one launch) of the 5x5 4 -> 4 channel layers at 32x32: the largest share
+                of the CIFAR step in the ncu launch list (profiles/r02_launch_summary_cifar_warm.txt). HBM-bound by the accounting of SURVEY.md section
+                8.d (arithmetic intensity 43-72 FLOP/B): algorithmic bytes per launch = read x + read dz + read y + write dx + write dw.
       imagenet  the tcgen05 implicit-GEMM forward convolution of the 64 -> 64 channel 3x3 layers at 56x56 (also run as their data gradient): the largest
                 share of the ImageNet-shaped step. Tensor-bound: 2*N*P*Q*K*C*R*S FLOP per launch against the measured dense bf16 peak. """
     import ctypes
@@ -271,28 +271,33 @@ def time_dominant_kernel(workload, batch, size, dev, peaks, dtype_name):
     P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     with torch.cuda.stream(stream):
         if workload == 'cifar' and dtype_name == 'bf16':
-            # the few-channel weight-gradient kernel of the 4 -> 4 channel 5x5 layers (3 launches per step, the largest share of the launch list): reads the
-            # layer input x, the incoming gradient dz and the layer's own output y (the activation derivative is applied while loading), writes dw
+            # the fused few-channel backward kernel of the 4 -> 4 channel 5x5 layers (2 launches per step + the same kernel at 16x16; the largest share of the
+            # launch list): reads the layer input x, the incoming gradient dz and the layer's own output y (the activation derivative is applied while
+            # loading), writes the data gradient dx and accumulates dw / dbias
             from deepcv_b200._lib import ACT_RELU
             n, c, h, w, k = batch, 4, size, size, 4
-            reps = max(4, int(300e6 / (n * h * w * (c + 2 * k) * esize)) + 1)
+            reps = max(4, int(300e6 / (n * h * w * (2 * c + 2 * k) * esize)) + 1)
             xs = [torch.randn(n, h, w, c, device=dev).to(tdt) for _ in range(reps)]
             dzs = [torch.randn(n, h, w, k, device=dev).to(tdt) for _ in range(reps)]
             ys = [torch.randn(n, h, w, k, device=dev).relu().to(tdt) for _ in range(reps)]
+            dxs = [torch.empty(n, h, w, c, device=dev, dtype=tdt) for _ in range(reps)]
+            wt = (torch.randn(k, 5, 5, c, device=dev) * 0.1).to(tdt)
             dw, db = torch.zeros(k, 5, 5, c, device=dev), torch.zeros(k, device=dev)
             shape = ConvShape(n, h, w, c, k, 5, 5, 1, 1, 2, 2, 1, 1, h, w)
+            assert lib.dcv_sc_conv_bwd_supported(ctypes.byref(shape), DCV_BF16), 'the fused few-channel backward kernel does not serve the 4 -> 4 channel 5x5 layer'
 
             def launch(i):
-                check(lib.dcv_sc_conv_wgrad(ctypes.byref(shape), P(xs[i]), None, P(dzs[i]), P(ys[i]), None, ACT_RELU, 0., P(dw), P(db), None, None, None, None, st), 'sc_conv_wgrad')
+                check(lib.dcv_sc_conv_bwd(ctypes.byref(shape), P(xs[i]), None, P(dzs[i]), P(ys[i]), None, ACT_RELU, 0., P(wt), P(dxs[i]), P(dw), P(db), None, None, None, None, st), 'sc_conv_bwd')
             ms = _graph_time_ms(launch, reps, 20, stream)
-            alg_bytes = n * h * w * (c + 2 * k) * esize + k * 25 * c * 4
+            alg_bytes = n * h * w * (2 * c + 2 * k) * esize + k * 25 * c * 4
             achieved = alg_bytes / (ms / 1e3) / 1e9
-            traffic = _committed_traffic('sc_wgrad_kernel<4, 4, 5>') if n == 512 else None
-            return dict(bound='hbm', kernel='sc_wgrad_kernel<4, 4, 5> (4->4 ch, 5x5, 32x32: mma.sync weight gradient with the activation derivative applied on load)', achieved=achieved,
+            traffic = _committed_traffic('sc_bwd_kernel<4, 4, 5>') if n == 512 else None
+            return dict(bound='hbm', kernel='sc_bwd_kernel<4, 4, 5> (4->4 ch, 5x5, 32x32: data gradient + weight gradient in one launch on mma.sync, activation derivative applied on load; '
+                        'timed without the pending-normalisation terms the step adds)', achieved=achieved,
                         peak=peaks['hbm_gbs'], unit='GB/s', frac=achieved / peaks['hbm_gbs'], traffic=traffic, traffic_unit='bytes of DRAM per launch',
                         traffic_source='ncu --set full (cold caches), profiles/r02_traffic.json' if traffic else None,
                         peak_source=peaks['source'], algorithmic_bytes_per_launch=alg_bytes, us_per_launch=ms * 1e3,
-                        note='latency-bound at this size: 12.6 MB per launch is 1.9 us of HBM time; the kernel is a chain of dependent round trips (see DESIGN.md section 5)')
+                        note='latency-bound at this size: 16.8 MB per launch is 2.5 us of HBM time; the kernel is a chain of dependent stage -> MMA -> reduce phases per image pair (see DESIGN.md section 5)')
         if workload == 'cifar':   # fp32 parity mode: the CUDA-core direct weight gradient
             n, c, h, w, k = batch, 4, size, size, 4
             reps = max(4, int(300e6 / (n * h * w * (c + k) * esize)) + 1)

@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
-__all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'PackEntry', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
+__all__ = ['lib', 'ConvShape', 'NormParams', 'ScNorm', 'PackEntry', 'LinkSource', 'LINK_MAX_SOURCES', 'check', 'library_path', 'DCV_F32', 'DCV_BF16', 'ACT_NONE', 'ACT_RELU', 'ACT_LEAKY_RELU',
            'ACT_SIGMOID', 'ALGO_AUTO', 'ALGO_DIRECT', 'ALGO_TCGEN05', 'SYMBOLS']
 
 ABI_VERSION = 4
@@ -33,6 +33,14 @@ class NormParams(Structure):
 class PackEntry(Structure):
     """ `dcv_pack_entry` (dcv_pack_conv_weights_batched) """
     _fields_ = [('src_off', c_uint64), ('dst_off', c_uint64), ('unit0', c_int64), ('k', c_int32), ('r', c_int32), ('s', c_int32), ('c', c_int32)]
+
+
+class LinkSource(Structure):
+    """ `dcv_link_source` (dcv_link_concat_fwd / _bwd) """
+    _fields_ = [('ptr', c_void_p), ('channels', c_int32), ('pool', c_int32)]
+
+
+LINK_MAX_SOURCES = 8
 
 
 class ScNorm(Structure):
@@ -96,6 +104,8 @@ SYMBOLS = {
     'dcv_avgpool2d_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_avgpool2d_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_axpby': (c_int, [P, P, P, c_float, c_float, c_size_t, c_int, P]),
+    'dcv_link_concat_fwd': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_link_concat_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_copy_channels_in': (c_int, [P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
     'dcv_copy_channels_out': (c_int, [P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
     'dcv_bilinear_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -115,6 +115,110 @@ __global__ void copy_channels_kernel(const V* __restrict__ src, V* __restrict__ 
   }
 }
 
+static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+// Dense link in ONE launch (`dense_link` = concat on the channel dim of the previous output and the `_from` tensors, a `_from`
+// tensor twice the spatial size being the 2x2 average — what the bilinear rescale with align_corners=False is at an exact 2x reduction). One thread per
+// (output pixel, channel granule of VE elements); the granule divides every source's channel count, so a thread never straddles two sources.
+struct LinkSources {
+  const void* ptr[DCV_LINK_MAX_SOURCES];
+  int units[DCV_LINK_MAX_SOURCES];   // channels / VE
+  int pool[DCV_LINK_MAX_SOURCES];    // 1 | 2
+  int count, units_total;
+};
+
+template <typename T, int VE>
+struct Granule {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[VE]) {
+    if constexpr (VE * sizeof(T) == 16) vec_unpack<T>(*reinterpret_cast<const uint4*>(p), v);
+    else {
+#pragma unroll
+      for (int e = 0; e < VE; ++e) v[e] = to_f<T>(p[e]);
+    }
+  }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[VE]) {
+    if constexpr (VE * sizeof(T) == 16) *reinterpret_cast<uint4*>(p) = vec_pack<T>(v);
+    else {
+#pragma unroll
+      for (int e = 0; e < VE; ++e) p[e] = from_f<T>(v[e]);
+    }
+  }
+};
+
+template <typename T, int VE, bool BWD>
+__global__ void link_concat_kernel(const LinkSources src, T* __restrict__ cat, int h, int w, uint32_t total, const FastDiv div_units, const FastDiv div_w) {
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t pix = div_units.div(idx);
+    int u = (int)(idx - pix * src.units_total), s = 0;
+#pragma unroll
+    for (int i = 0; i < DCV_LINK_MAX_SOURCES - 1; ++i)
+      if (i + 1 < src.count && s == i && u >= src.units[i]) { u -= src.units[i]; s = i + 1; }
+    T* t = (T*)src.ptr[s];
+    if (BWD && t == nullptr) continue;
+    const int c = src.units[s] * VE;
+    T* cat_p = cat + (size_t)idx * VE;
+    float v[VE];
+    if (src.pool[s] == 1) {
+      T* p = t + (size_t)pix * c + (size_t)u * VE;
+      if constexpr (BWD) { Granule<T, VE>::load(cat_p, v); Granule<T, VE>::store(p, v); }
+      else { Granule<T, VE>::load(p, v); Granule<T, VE>::store(cat_p, v); }
+    } else {
+      const uint32_t row = div_w.div(pix);       // row = img * h + y
+      const int x = (int)(pix - row * w);
+      T* p = t + (((size_t)row * 2) * (2 * w) + (size_t)x * 2) * c + (size_t)u * VE;   // (img*h + y)*2 == img*2h + 2y
+      if constexpr (BWD) {
+        Granule<T, VE>::load(cat_p, v);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) v[e] *= 0.25f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Granule<T, VE>::store(p + ((size_t)(q >> 1) * (2 * w) + (q & 1)) * c, v);
+      } else {
+        float v1[VE], v2[VE], v3[VE], acc[VE];   // (top pair) + (bottom pair), each pair left + right: the order torch's bilinear kernel adds them in
+        Granule<T, VE>::load(p, v);
+        Granule<T, VE>::load(p + c, v1);
+        Granule<T, VE>::load(p + (size_t)(2 * w) * c, v2);
+        Granule<T, VE>::load(p + (size_t)(2 * w + 1) * c, v3);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) acc[e] = ((v[e] + v1[e]) + (v2[e] + v3[e])) * 0.25f;
+        Granule<T, VE>::store(cat_p, acc);
+      }
+    }
+  }
+}
+
+template <typename T, int VE, bool BWD>
+static int launch_link(const dcv_link_source* sources, int count, int ctot, void* cat, int n, int h, int w, cudaStream_t st) {
+  LinkSources ls{};
+  ls.count = count; ls.units_total = ctot / VE;
+  for (int i = 0; i < count; ++i) { ls.ptr[i] = sources[i].ptr; ls.units[i] = sources[i].channels / VE; ls.pool[i] = sources[i].pool; }
+  const uint32_t total = (uint32_t)((size_t)n * h * w * ls.units_total);
+  link_concat_kernel<T, VE, BWD><<<grid_for(total, 256), 256, 0, st>>>(ls, (T*)cat, h, w, total, FastDiv(ls.units_total), FastDiv(w));
+  DCV_LAUNCH_CHECK("link_concat_kernel");
+  return 0;
+}
+
+template <bool BWD>
+static int link_concat(const char* name, const dcv_link_source* sources, int count, void* cat, int n, int h, int w, int dtype, cudaStream_t st) {
+  DCV_REQUIRE(sources && cat && count > 0 && count <= DCV_LINK_MAX_SOURCES && n > 0 && h > 0 && w > 0, "%s: bad arguments", name);
+  DCV_REQUIRE(dtype == DCV_F32 || dtype == DCV_BF16, "%s: unsupported dtype %d", name, dtype);
+  const int es = dtype == DCV_BF16 ? 2 : 4;
+  int ctot = 0, ve = 16 / es;
+  bool al16 = aligned16(cat);
+  for (int i = 0; i < count; ++i) {
+    DCV_REQUIRE(sources[i].channels > 0 && (sources[i].pool == 1 || sources[i].pool == 2) && (BWD || sources[i].ptr), "%s: bad source %d", name, i);
+    ctot += sources[i].channels;
+    while (sources[i].channels % ve) ve >>= 1;
+    al16 = al16 && (!sources[i].ptr || aligned16(sources[i].ptr));
+  }
+  DCV_REQUIRE((size_t)n * h * w * ctot < (1ull << 31), "%s: tensor too large", name);
+  if (ve * es == 16 && !al16) ve >>= 1;
+#define DCV_LINK_CASE(T, V) if (ve == V) return launch_link<T, V, BWD>(sources, count, ctot, cat, n, h, w, st)
+  if (dtype == DCV_BF16) { DCV_LINK_CASE(__nv_bfloat16, 8); DCV_LINK_CASE(__nv_bfloat16, 4); DCV_LINK_CASE(__nv_bfloat16, 2); DCV_LINK_CASE(__nv_bfloat16, 1); }
+  else { DCV_LINK_CASE(float, 4); DCV_LINK_CASE(float, 2); DCV_LINK_CASE(float, 1); }
+#undef DCV_LINK_CASE
+  return 1;
+}
+
 // torch upsample_bilinear2d source index / weights (aten/native/UpSample.h: area_pixel_compute_source_index)
 __device__ __forceinline__ void bilinear_coord(int dst, float scale, int in_size, int align_corners, int& i0, int& i1, float& l0, float& l1) {
   float src = align_corners ? scale * (float)dst : scale * ((float)dst + 0.5f) - 0.5f;
@@ -167,8 +271,6 @@ __global__ void bilinear_bwd_kernel(const T* __restrict__ dy, float* __restrict_
     atomicAdd(base + ((size_t)y1 * w + x1) * c, hl1 * wl1 * g);
   }
 }
-
-static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
 static int pool_check(const char* name, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int* p, int* q) {
   DCV_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0, "%s: bad arguments", name);
@@ -262,6 +364,14 @@ int dcv_copy_channels_in(const void* src, void* dst, size_t pixels, int c_src, i
 
 int dcv_copy_channels_out(const void* src, void* dst, size_t pixels, int c_src, int c_off, int c_dst, int dtype, void* stream) {
   return dcv::copy_channels(src, dst, pixels, c_src, c_off, c_dst, 0, c_dst, dtype, dcv::as_stream(stream));
+}
+
+int dcv_link_concat_fwd(const dcv_link_source* sources, int count, void* out, int n, int h, int w, int dtype, void* stream) {
+  return dcv::link_concat<false>("link_concat_fwd", sources, count, out, n, h, w, dtype, dcv::as_stream(stream));
+}
+
+int dcv_link_concat_bwd(const void* dout, const dcv_link_source* grads, int count, int n, int h, int w, int dtype, void* stream) {
+  return dcv::link_concat<true>("link_concat_bwd", grads, count, const_cast<void*>(dout), n, h, w, dtype, dcv::as_stream(stream));
 }
 
 int dcv_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream) {

@@ -479,7 +479,7 @@ class GraphedTrainStep:
             self.static_losses[name] = fn(y_pred, self.static_y)
         loss = self.static_loss = self.static_losses[MAIN_TRAINING_LOSS_NAME]
         self.optimizer.zero_grad()
-        loss.backward()
+        torch.autograd.backward(loss, grad_tensors=[ops.unit_grad(loss.device)])   # = loss.backward() without the ones_like fill kernel / the multiplication by one
         if isinstance(self.model, DataParallelModel):
             self.model.finish_gradient_reduction()
         self.optimizer.step(refresh_lr=False)

@@ -223,15 +223,19 @@ def add_residual_dense_link_creator(is_residual: bool, creator_name: str, submod
         @deepcv_nn.forward_call_convention_dec(apply_parallel_forward=apply_in_parallel, in_tensors_count_similar_to_refs=apply_in_parallel)   # reference :300
         def _forward_callback(x, referenced_submodules_out: List[torch.Tensor]):
             out = [x] if isinstance(x, torch.Tensor) else list(x)
-            for refs in referenced_submodules_out:
-                for y in ([refs] if isinstance(refs, torch.Tensor) else list(refs)):
-                    if out[0].shape[channel_dim + 1:] != y.shape[channel_dim + 1:]:
-                        if not allow_scaling:
-                            raise RuntimeError(f"Error: Couldn't forward throught {creator_name} link: features from link doesn't have "
-                                               f"the same shape as previous module's output shape, can't concatenate or add them. (did you forgot to allow residual/dense "
-                                               f"features to be scaled using `allow_scaling: true` parameter?). `residual_shape='{y.shape}' != prev_features_shape='{out[0].shape}'`")
-                        y = deepcv_nn.interpolate(y, out[0].shape[channel_dim + 1:], scaling_mode=scaling_mode, align_corners=scaling_align_corners)
-                    out.append(y)
+            linked = [y for refs in referenced_submodules_out for y in ([refs] if isinstance(refs, torch.Tensor) else list(refs))]
+            if reduction == 'concat' and allow_scaling and channel_dim == 1 and not scaling_align_corners and scaling_mode in (None, 'bilinear'):
+                fused = ops.link_concat_rescaled(out + linked)   # same-size and exactly-2x references: rescale + concat in one launch
+                if fused is not None:
+                    return fused
+            for y in linked:
+                if out[0].shape[channel_dim + 1:] != y.shape[channel_dim + 1:]:
+                    if not allow_scaling:
+                        raise RuntimeError(f"Error: Couldn't forward throught {creator_name} link: features from link doesn't have "
+                                           f"the same shape as previous module's output shape, can't concatenate or add them. (did you forgot to allow residual/dense "
+                                           f"features to be scaled using `allow_scaling: true` parameter?). `residual_shape='{y.shape}' != prev_features_shape='{out[0].shape}'`")
+                    y = deepcv_nn.interpolate(y, out[0].shape[channel_dim + 1:], scaling_mode=scaling_mode, align_corners=scaling_align_corners)
+                out.append(y)
             return reduce(out)
         return ForwardCallbackSubmodule(_forward_callback)
 

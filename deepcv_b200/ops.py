@@ -16,11 +16,11 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, NormParams, ScNorm, check, lib)
+from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_DIRECT, DCV_BF16, DCV_F32, ConvShape, LINK_MAX_SOURCES, LinkSource, NormParams, ScNorm, check, lib)
 
-__all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'bilinear_resize', 'flatten_nchw',
+__all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'link_concat_rescaled', 'bilinear_resize', 'flatten_nchw',
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext', 'PendingAffine', 'sc_conv_block',
-           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act', 'PendingFlatten']
+           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act', 'PendingFlatten', 'unit_grad']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
 _DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
@@ -951,33 +951,57 @@ class _Axpby(torch.autograd.Function):
 
 
 class _Concat(torch.autograd.Function):
+    """ Channel concatenation of NHWC tensors in one launch each way (`dcv_link_concat_*`); `pools[i] == 2` marks a tensor twice the output's spatial size
+    that enters as its 2x2 average (a `dense_link` reference rescaled by exactly 1/2). More than `LINK_MAX_SOURCES` same-size tensors: one slice copy each. """
+
     @staticmethod
-    def forward(ctx, *tensors):
+    def forward(ctx, pools, *tensors):
         _require_cuda(*tensors)
         n, _, h, w = tensors[0].shape
+        h, w = h // pools[0], w // pools[0]
         channels = [t.shape[1] for t in tensors]
         out = empty_nhwc(n, sum(channels), h, w, tensors[0].dtype, tensors[0].device)
+        ctx.channels, ctx.pools, ctx.fused = channels, pools, len(tensors) <= LINK_MAX_SOURCES
+        if ctx.fused:
+            srcs = (LinkSource * len(tensors))(*[LinkSource(_ptr(t), c, p) for t, c, p in zip(tensors, channels, pools)])
+            check(lib.dcv_link_concat_fwd(srcs, len(tensors), _ptr(out), n, h, w, _dt(out), _stream()), 'link_concat_fwd')
+            return out
         off = 0
         for t, c in zip(tensors, channels):
             check(lib.dcv_copy_channels_in(_ptr(t), _ptr(out), n * h * w, c, sum(channels), off, _dt(t), _stream()), 'copy_channels_in')
             off += c
-        ctx.channels = channels
         return out
 
     @staticmethod
     def backward(ctx, g):
         g = as_nhwc(g.detach())
         n, ctot, h, w = g.shape
-        grads, off = [], 0
-        for i, c in enumerate(ctx.channels):
-            if ctx.needs_input_grad[i]:
-                gi = empty_nhwc(n, c, h, w, g.dtype, g.device)
+        grads = [empty_nhwc(n, c, h * p, w * p, g.dtype, g.device) if ctx.needs_input_grad[i + 1] else None for i, (c, p) in enumerate(zip(ctx.channels, ctx.pools))]
+        if ctx.fused:
+            dsts = (LinkSource * len(grads))(*[LinkSource(_ptr(gi) if gi is not None else None, c, p) for gi, c, p in zip(grads, ctx.channels, ctx.pools)])
+            check(lib.dcv_link_concat_bwd(_ptr(g), dsts, len(grads), n, h, w, _dt(g), _stream()), 'link_concat_bwd')
+            return (None, *grads)
+        off = 0
+        for gi, c in zip(grads, ctx.channels):
+            if gi is not None:
                 check(lib.dcv_copy_channels_out(_ptr(g), _ptr(gi), n * h * w, ctot, off, c, _dt(g), _stream()), 'copy_channels_out')
-                grads.append(gi)
-            else:
-                grads.append(None)
             off += c
-        return tuple(grads)
+        return (None, *grads)
+
+
+def link_concat_rescaled(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
+    """ `dense_link` body when every `_from` tensor either has the first tensor's spatial shape or exactly twice it (bilinear, align_corners=False: the
+    2x2 average): rescale + concat in one launch. None when the list is not of that form (the caller rescales, then `link_reduce`s). """
+    if len(tensors) < 2 or len(tensors) > LINK_MAX_SOURCES or any(not (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 4) for t in tensors):
+        return None
+    n, _, h, w = tensors[0].shape
+    pools = []
+    for t in tensors:
+        if t.shape[0] != n or tuple(t.shape[2:]) not in ((h, w), (2 * h, 2 * w)):
+            return None
+        pools.append(1 if tuple(t.shape[2:]) == (h, w) else 2)
+    dtype = tensors[0].dtype
+    return _Concat.apply(tuple(pools), *[as_nhwc(t, dtype) for t in tensors])
 
 
 def link_reduce(tensors: List[torch.Tensor], reduction: str) -> torch.Tensor:
@@ -989,7 +1013,7 @@ def link_reduce(tensors: List[torch.Tensor], reduction: str) -> torch.Tensor:
     if reduction == 'concat':
         if any(t.shape[0] != tensors[0].shape[0] or t.shape[2:] != tensors[0].shape[2:] for t in tensors):
             raise RuntimeError(f'deepcv_b200: cannot concatenate tensors of shapes {[tuple(t.shape) for t in tensors]} on the channel dim')
-        return _Concat.apply(*tensors)
+        return _Concat.apply((1,) * len(tensors), *tensors)
     if reduction in ('sum', 'mean'):
         if any(t.shape != tensors[0].shape for t in tensors):
             raise RuntimeError(f'deepcv_b200: cannot {reduction} tensors of different shapes {[tuple(t.shape) for t in tensors]}')
@@ -1140,6 +1164,21 @@ def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 # ------------------------------------------------------------------------------------------------------------------------------
 # Loss (reference: classification/image.py:70 — torch.nn.CrossEntropyLoss on the head's outputs)
 
+_UNIT_GRADS = {}
+
+
+def unit_grad(device) -> torch.Tensor:
+    """ THE scalar 1.0 of `device`, handed to `torch.autograd.backward(loss, grad_tensors=[unit_grad(dev)])` by the captured training step: autograd then
+    does not launch a fill kernel for `ones_like(loss)`, and the loss's backward recognises the tensor (by address) and skips multiplying its gradient by
+    one. Never written to. """
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _UNIT_GRADS.get(key)
+    if t is None:
+        t = _UNIT_GRADS[key] = torch.ones((), dtype=torch.float32, device=device)
+    return t
+
+
 class _CrossEntropy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target):
@@ -1158,6 +1197,8 @@ class _CrossEntropy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dlogits, = ctx.saved_tensors
+        if g.data_ptr() == unit_grad(g.device).data_ptr():
+            return dlogits, None   # upstream gradient is the constant 1
         g = _cast_raw(g.detach().contiguous(), torch.float32)
         out = torch.empty_like(dlogits)
         check(lib.dcv_scale_by_device_scalar(_ptr(dlogits), _ptr(g), _ptr(out), dlogits.numel(), _stream()), 'scale_by_device_scalar')

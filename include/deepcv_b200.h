@@ -231,6 +231,18 @@ int dcv_axpby(const void* a, const void* b, void* out, float alpha, float beta, 
 /* dst[pix][c_off : c_off+c_src] = src[pix][:] (concat = write into a channel slice) and the reverse slice read. */
 int dcv_copy_channels_in(const void* src, void* dst, size_t pixels, int c_src, int c_dst, int c_off, int dtype, void* stream);
 int dcv_copy_channels_out(const void* src, void* dst, size_t pixels, int c_src, int c_off, int c_dst, int dtype, void* stream);
+/* `dense_link` in one launch (reference meta/submodule_creators.py:272-332 with reduction 'concat'): out[n][h][w][:] = the sources' channels one after the
+ * other. A source with pool == 2 is an N x 2h x 2w x channels tensor and contributes its 2x2 averages — the reference's `F.interpolate(mode='bilinear',
+ * align_corners=False)` at an exact 2x reduction (meta/nn.py:665-676). `_bwd` scatters dout back: grads[i].ptr receives source i's gradient (NULL: not
+ * needed), the pooled ones dout/4 at each of the four positions. At most DCV_LINK_MAX_SOURCES sources. */
+#define DCV_LINK_MAX_SOURCES 8
+typedef struct dcv_link_source {
+  void* ptr;
+  int32_t channels;
+  int32_t pool;
+} dcv_link_source;
+int dcv_link_concat_fwd(const dcv_link_source* sources, int count, void* out, int n, int h, int w, int dtype, void* stream);
+int dcv_link_concat_bwd(const void* dout, const dcv_link_source* grads, int count, int n, int h, int w, int dtype, void* stream);
 /* F.interpolate(mode='bilinear', align_corners) forward, and its adjoint written to fp32 dx (overwritten). */
 int dcv_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);
 int dcv_bilinear_bwd(const void* dy, float* dx_f32, int n, int h, int w, int c, int oh, int ow, int align_corners, int dtype, void* stream);

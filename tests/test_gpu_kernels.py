@@ -191,3 +191,37 @@ def test_batched_transposed_weight_pack(dev):
         ref = w.permute(1, 2, 3, 0).flip(1, 2).contiguous().bfloat16()          # [C][R-1-r][S-1-s][K]
         assert torch.equal(got, ref), (k, c, r, s)
     assert ctx.transposed_view(torch.randn(4, 4, 3, 3, device=dev), torch.bfloat16) is None
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('n,h,w,channels,pools,needs', [
+    (512, 8, 8, (16, 4), (1, 2), (True, True)),             # the default net's dense link (conf/base/parameters.yml:86)
+    (3, 5, 7, (3, 5, 2), (1, 2, 1), (True, False, True)),   # odd channel counts: scalar granules; a source that needs no gradient
+    (2, 6, 4, (8, 8, 16, 8, 24, 8, 8, 8), (1, 1, 2, 1, 1, 2, 1, 1), (True,) * 8),
+    (4, 3, 3, (6, 2), (2, 1), (True, True)),
+])
+def test_dense_link_concat_in_one_launch(dev, n, h, w, channels, pools, needs, dtype):
+    """ ops.link_concat_rescaled == F.interpolate(bilinear, align_corners=False) of the twice-larger tensors + torch.cat, bit for bit each way. """
+    from deepcv_b200 import ops
+    torch.manual_seed(sum(channels) + h)
+    srcs = [torch.randn(n, c, h * p, w * p, device=dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(r)
+            for c, p, r in zip(channels, pools, needs)]
+    if pools[0] != 1:
+        assert ops.link_concat_rescaled(srcs) is None   # the previous output defines the spatial shape: it is never rescaled
+        return
+    out = ops.link_concat_rescaled(srcs)
+    refs = [s.detach().float().requires_grad_(r) for s, r in zip(srcs, needs)]
+    parts = [F.interpolate(r, size=(h, w), mode='bilinear', align_corners=False).to(dtype).float() if p == 2 else r for r, p in zip(refs, pools)]
+    want = torch.cat(parts, dim=1)
+    assert out.shape == want.shape and torch.equal(out.float(), want)
+    g = torch.randn_like(want).to(dtype)
+    out.backward(g.contiguous(memory_format=torch.channels_last))
+    off = 0
+    for s, c, p, r in zip(srcs, channels, pools, needs):
+        gs = g[:, off:off + c].float()
+        off += c
+        if not r:
+            assert s.grad is None
+            continue
+        expect = (gs * 0.25).to(dtype).float().repeat_interleave(2, dim=2).repeat_interleave(2, dim=3) if p == 2 else gs
+        assert torch.equal(s.grad.float(), expect)
