@@ -98,6 +98,11 @@ SYMBOLS = {
     'dcv_gather_unpack_wgrad': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     'dcv_conv2d_fwd_gather': (c_int, [POINTER(ConvShape), P, P, c_int, P, P, P, c_int, c_float, c_int, P]),
     'dcv_conv2d_wgrad_gather': (c_int, [POINTER(ConvShape), P, P, P, c_int, c_int, P]),
+    'dcv_conv2d_pairs_supported': (c_int, [POINTER(ConvShape), P, c_int]),
+    'dcv_pairs_pack_weight': (c_int, [P, P, POINTER(ConvShape), c_int, P]),
+    'dcv_pairs_unpack_wgrad': (c_int, [P, P, POINTER(ConvShape), P]),
+    'dcv_conv2d_fwd_pairs': (c_int, [POINTER(ConvShape), P, P, P, P, P, c_int, c_float, c_int, P]),
+    'dcv_conv2d_wgrad_pairs': (c_int, [POINTER(ConvShape), P, P, P, c_int, P]),
     'dcv_norm_bwd_reduce': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_bwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P, P, P, P, P, P]),
     'dcv_act_norm_bwd_apply': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, c_int, P]),

@@ -13,6 +13,9 @@ int conv_wgrad_tc(const dcv_conv_shape*, const void*, const void*, float*, void*
 bool conv_fwd_tc_gather_supported(const dcv_conv_shape*, const void* x, int kpad, int dtype);
 int conv_fwd_tc_gather(const dcv_conv_shape*, const void* x, const void* w_col, int kpad, const float* bias, void* y, float* stats_nc, int act, float slope, int stats_flags, cudaStream_t);
 int conv_wgrad_tc_gather(const dcv_conv_shape*, const void* x, const void* dy, float* dw_col, int kpad, bool prezeroed, cudaStream_t);
+bool conv_tc_pairs_supported(const dcv_conv_shape*, const void* x, int dtype);
+int conv_fwd_tc_pairs(const dcv_conv_shape*, const void* x, const void* w_col, const float* bias, void* y, float* stats_nc, int act, float slope, int stats_flags, cudaStream_t);
+int conv_wgrad_tc_pairs(const dcv_conv_shape*, const void* x, const void* dy, float* dw_col, bool prezeroed, cudaStream_t);
 size_t conv_wgrad_tc_workspace(const dcv_conv_shape*);
 
 static dcv_conv_shape dgrad_as_fwd(const dcv_conv_shape& s) {
@@ -67,6 +70,24 @@ int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const vo
   using namespace dcv;
   DCV_REQUIRE(shape, "conv2d_wgrad_gather: null shape");
   return conv_wgrad_tc_gather(shape, x, dy, dw_col, kpad, acc_prezeroed != 0, as_stream(stream));
+}
+
+int dcv_conv2d_pairs_supported(const dcv_conv_shape* shape, const void* x, int dtype) {
+  return dcv::conv_tc_pairs_supported(shape, x, dtype) ? 1 : 0;
+}
+
+int dcv_conv2d_fwd_pairs(const dcv_conv_shape* shape, const void* x, const void* w_col, const float* bias, void* y, float* stats_nc, int act, float slope, int acc_prezeroed, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(shape, "conv2d_fwd_pairs: null shape");
+  cudaStream_t st = as_stream(stream);
+  zero_accumulator(stats_nc, (size_t)shape->n * shape->k * 2 * sizeof(float), st, (acc_prezeroed & DCV_ACC_PREZEROED) != 0);
+  return conv_fwd_tc_pairs(shape, x, w_col, bias, y, stats_nc, act, slope, acc_prezeroed, st);
+}
+
+int dcv_conv2d_wgrad_pairs(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int acc_prezeroed, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(shape, "conv2d_wgrad_pairs: null shape");
+  return conv_wgrad_tc_pairs(shape, x, dy, dw_col, acc_prezeroed != 0, as_stream(stream));
 }
 
 int dcv_conv2d_dgrad(const dcv_conv_shape* shape, const void* dy, const void* w, const void* wt, void* dx, int dtype, int algo, void* stream) {

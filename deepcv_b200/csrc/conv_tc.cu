@@ -928,6 +928,394 @@ __global__ void __launch_bounds__(GA_THREADS, 1) conv_wgrad_tc_gather_kernel(con
   }
 }
 
+// ---- stride-2 few-channel convolutions ("pixel pair" variant: the 3 -> 64, 7x7 / stride-2 stem) ----------------------------------------------------
+// The gather kernels above spend their time in the producers (ncu, stem at batch 256: 415 us, tensor pipe 10 %, 23 warp instructions per 16-byte chunk of the
+// im2col tile, 96 chunks per pixel band; every role waits on them). With stride 2 the im2col matrix has a structure the tensor core can address by itself:
+// stage the R input rows of an output row TRANSPOSED, one 128-byte line per PIXEL PAIR:   T[L][r][8 elements] = row r, pixels 2P and 2P + 1 (2C <= 8
+// elements; the rest of the 16-byte chunk is whatever follows in the row and meets zero weights), P = q0 - hp + L.   Output pixel q reads the pixel pairs
+// q - hp .. q - hp + 3 (8 pixels >= S + (pad & 1) taps), i.e. FOUR CONSECUTIVE LINES starting at line q - q0:
+//   * forward: the A operand of K block pp (64 elements = line m + pp of row m) is the K-major SWIZZLE_128B tile that starts at line pp — overlapping
+//     tiles, the swizzle is a function of the shared-memory address only, so every view reads the same bytes. K = 4 x 64 = 256; 16 MMAs per 128 pixels.
+//   * weight gradient: read MN-major, the same lines are the B operand with N = 256 (four 64-element atoms ONE LINE apart: LBO = 128 bytes).
+// The producers only move 16-byte chunks (4 shared loads + 1 store per chunk, R x 131 chunks per tile): 14x fewer instructions than the gather, no K-sized
+// tile in shared memory (17 KB per stage instead of 48 KB). K order of the weights: column pp * 64 + r * 8 + px * C + c = w[k][r][2 pp + px - (pad & 1)][c].
+struct PairParams {
+  dcv_conv_shape s;
+  int rowlen, lpad, rows_bytes;   // staged input rows, in elements: [lpad zeros][W * C][zeros up to rowlen]
+  int hp;                         // output pixel q reads the pixel pairs q - hp .. q - hp + 3
+  int tiles_q, total_tiles;
+  int act; float slope;
+  const float* bias;
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+};
+constexpr int PR_LINES = BLOCK_M + 3, PR_STAGE_BYTES = 18 * 1024, PR_K = 256, PR_KBLOCKS = PR_K / BLOCK_K;
+// Four producer GROUPS of two warps: group g builds the tiles i = g (mod 4) of the CTA in line stage g from row buffer g — four tiles are under construction
+// at once. (All eight warps on one tile ran at the latency of wait -> 4 units -> fence -> arrive per tile: 0.96 us per tile with the stores switched off.)
+constexpr int PR_GROUPS = 4, PR_FWD_STAGES = PR_GROUPS, PR_WG_STAGES = PR_GROUPS, PR_ROW_BUFS = PR_GROUPS, PR_PRODUCERS = PR_GROUPS * 64;
+constexpr int PR_FWD_THREADS = 64 + 256 + PR_PRODUCERS;   // warps: 0 TMA, 1 MMA, 2..9 epilogue, 10..17 producers
+constexpr int PR_WG_THREADS = 64 + 128 + PR_PRODUCERS;                                          // warps: 0 TMA, 1 MMA, 2..5 epilogue, 6..13 producers
+
+// The tiles of a CTA are a CONTIGUOUS range of (image, output row, row segment) triples walked by increments: the first versions decoded `tile` with two
+// runtime divisions per tile in every one of the 18 warps (ncu: 15 % of the kernel's instructions, and on the epilogue's critical path).
+struct PairTiles {
+  int left, tq, op, img;
+  __device__ __forceinline__ PairTiles(const PairParams& prm) {
+    const long long t = prm.total_tiles, g = gridDim.x, b = blockIdx.x;
+    const int first = (int)(b * t / g);
+    left = (int)((b + 1) * t / g) - first;
+    tq = first % prm.tiles_q; const int u = first / prm.tiles_q;
+    op = u % prm.s.p; img = u / prm.s.p;
+  }
+  __device__ __forceinline__ bool valid() const { return left > 0; }
+  __device__ __forceinline__ void next(const PairParams& prm) {
+    --left;
+    if (++tq == prm.tiles_q) { tq = 0; if (++op == prm.s.p) { op = 0; ++img; } }
+  }
+};
+
+// epilogue_store32 with the 32 bias values held in registers (loaded once per kernel: an epilogue warp of the pixel-pair kernel always serves the same columns)
+template <int ACT>
+__device__ __forceinline__ void pairs_store32(const uint32_t* v, const float* bias_regs, float slope, __nv_bfloat16* dst) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    f[j] = __uint_as_float(v[j]) + bias_regs[j];
+    if (ACT == DCV_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+    else if (ACT == DCV_ACT_LEAKY_RELU) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
+    else if (ACT == DCV_ACT_SIGMOID) f[j] = 1.f / (1.f + expf(-f[j]));
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const uint4 q = vec_pack<__nv_bfloat16>(f + 8 * j); pk[4 * j] = q.x; pk[4 * j + 1] = q.y; pk[4 * j + 2] = q.z; pk[4 * j + 3] = q.w; }
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+#pragma unroll
+    for (int w = 0; w < 16; w += 8)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(reinterpret_cast<uint32_t*>(dst) + w), "r"(pk[w]), "r"(pk[w + 1]), "r"(pk[w + 2]), "r"(pk[w + 3]),
+                   "r"(pk[w + 4]), "r"(pk[w + 5]), "r"(pk[w + 6]), "r"(pk[w + 7]) : "memory");
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  }
+}
+__device__ __forceinline__ void pairs_store32_dyn(int act, const uint32_t* v, const float* bias_regs, float slope, __nv_bfloat16* dst) {
+  switch (act) {   // warp-uniform
+    case DCV_ACT_RELU: pairs_store32<DCV_ACT_RELU>(v, bias_regs, slope, dst); break;
+    case DCV_ACT_LEAKY_RELU: pairs_store32<DCV_ACT_LEAKY_RELU>(v, bias_regs, slope, dst); break;
+    case DCV_ACT_SIGMOID: pairs_store32<DCV_ACT_SIGMOID>(v, bias_regs, slope, dst); break;
+    default: pairs_store32<DCV_ACT_NONE>(v, bias_regs, slope, dst); break;
+  }
+}
+
+// One of the two warps of a producer group builds its share of a tile: filter rows sub, sub + 2, ...; per row the 16-byte chunks of all the lines, the
+// shared loads of a whole row issued before its stores (the stores are volatile asm: the compiler does not move loads across them).
+__device__ __forceinline__ void pairs_build_tile(const PairParams& prm, const uint32_t* row_words, uint32_t t_stage, int q0, int sub, int lane) {
+  const dcv_conv_shape& s = prm.s;
+  constexpr int NLB = (PR_LINES + 31) / 32;
+  const int e_lane = prm.lpad + 2 * (q0 - prm.hp + lane) * s.c, e_step = 64 * s.c;   // first element of the pixel pair of line `lane` (even); 32 lines further
+  for (int r = sub; r < s.r; r += 2) {
+    uint32_t w[NLB][4];
+#pragma unroll
+    for (int b = 0; b < NLB; ++b) {
+      const int e0 = e_lane + b * e_step;
+      w[b][0] = w[b][1] = w[b][2] = w[b][3] = 0u;
+      if (b * 32 + lane < PR_LINES && e0 + 8 <= prm.rowlen) {   // beyond the staged row: only lines of overhang pixels (never stored / zero dy) — keep them finite
+        const uint32_t* wp = row_words + ((r * prm.rowlen + e0) >> 1);
+        w[b][0] = wp[0]; w[b][1] = wp[1]; w[b][2] = wp[2]; w[b][3] = wp[3];
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NLB; ++b)
+      if (b * 32 + lane < PR_LINES)   // 32 b + lane and lane agree modulo 8
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_stage + (uint32_t)(b * 32 + lane) * 128u + ((uint32_t)(r ^ (lane & 7)) << 4)), "r"(w[b][0]), "r"(w[b][1]), "r"(w[b][2]),
+                     "r"(w[b][3]) : "memory");
+  }
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(const __grid_constant__ CUtensorMap map_w, const PairParams prm) {
+  constexpr int B_BYTES = N_TILE * BLOCK_K * 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t t_base = res_base + PR_KBLOCKS * B_BYTES;
+  const uint32_t rows_base = t_base + PR_FWD_STAGES * PR_STAGE_BYTES;
+  const uint32_t bars = rows_base + (uint32_t)PR_ROW_BUFS * (uint32_t)prm.rows_bytes;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (PR_FWD_STAGES + i); };
+  auto tfull = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + i); };
+  auto tempty = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 2 + i); };
+  const uint32_t bres = bars + 8u * (2 * PR_FWD_STAGES + 4), tmem_slot = bars + 8u * (2 * PR_FWD_STAGES + 5);
+  auto rfull = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 6 + i); };
+  auto rempty = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 6 + PR_ROW_BUFS + i); };
+  uint8_t* gen_base = smem_raw + (res_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const dcv_conv_shape& s = prm.s;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PR_FWD_STAGES; ++i) { mbar_init(full(i), 2); mbar_init(empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 8); }
+    mbar_init(bres, 1);
+    for (int i = 0; i < PR_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * N_TILE) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // the line stages (chunks of filter rows >= R stay zero) and the row buffers (their margins are the horizontal padding) start as zeros
+  for (uint32_t i = threadIdx.x; i < (PR_FWD_STAGES * PR_STAGE_BYTES + (uint32_t)PR_ROW_BUFS * (uint32_t)prm.rows_bytes) / 16u; i += PR_FWD_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(t_base + i * 16u), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (elect_one()) {   // ===== weights once, then the R input rows of every tile (one bulk copy each; rows outside the image come from a zero row)
+      mbar_expect_tx(bres, PR_KBLOCKS * B_BYTES);
+      for (int kb = 0; kb < PR_KBLOCKS; ++kb) tma_load_2d(res_base + kb * B_BYTES, &map_w, bres, kb * BLOCK_K, 0);
+      int buf = 0; uint32_t rphase = 0;
+      const uint32_t row_bytes = (uint32_t)(s.w * s.c) * 2u;
+      for (PairTiles t(prm); t.valid(); t.next(prm)) {
+        const int op = t.op, img = t.img;
+        mbar_wait(rempty(buf), rphase ^ 1u);
+        mbar_expect_tx(rfull(buf), (uint32_t)s.r * row_bytes);
+        const int iy0 = op * s.stride_h - s.pad_h;
+        for (int r = 0; r < s.r; ++r) {
+          const int iy = iy0 + r * s.dil_h;
+          const void* src = (iy >= 0 && iy < s.h) ? (const void*)(prm.x + ((size_t)img * s.h + iy) * (size_t)(s.w * s.c)) : (const void*)g_zero_row;
+          bulk_load_1d(rows_base + (uint32_t)buf * (uint32_t)prm.rows_bytes + (uint32_t)(r * prm.rowlen + prm.lpad) * 2u, src, row_bytes, rfull(buf));
+        }
+        if (++buf == PR_ROW_BUFS) { buf = 0; rphase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {   // ===== MMA issuer: K block pp of pixel row m is line m + pp
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, N_TILE, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      mbar_wait(bres, 0);
+      for (PairTiles t(prm); t.valid(); t.next(prm)) {
+        mbar_wait(tempty(as), aphase ^ 1u);
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * N_TILE);
+#pragma unroll
+        for (int kb = 0; kb < PR_KBLOCKS; ++kb) {
+          const uint64_t adesc = make_desc(t_base + stage * PR_STAGE_BYTES + kb * 128, 0, 1024);
+          const uint64_t bdesc = make_desc(res_base + kb * B_BYTES, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(empty(stage));
+        umma_commit(tfull(as));
+        if (++stage == PR_FWD_STAGES) { stage = 0; phase ^= 1u; }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp < 10) {
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    float bias_regs[N_TILE / 64][32];
+#pragma unroll
+    for (int ci = 0; ci < N_TILE / 64; ++ci)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bias_regs[ci][j] = prm.bias ? __ldg(prm.bias + half * (N_TILE / 2) + 32 * ci + j) : 0.f;
+    for (PairTiles t(prm); t.valid(); t.next(prm)) {
+      const int q = t.tq * BLOCK_M + row;
+      const bool valid = q < s.q;
+      __nv_bfloat16* dst = prm.y + (((size_t)t.img * s.p + t.op) * s.q + q) * s.k;
+      mbar_wait_relaxed(tfull(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(as * N_TILE) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+      for (int ci = 0; ci < N_TILE / 64; ++ci) {
+        const int c0 = half * (N_TILE / 2) + 32 * ci;
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        if (valid && prm.y) pairs_store32_dyn(prm.act, v, bias_regs[ci], prm.slope, dst + c0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else {
+    // ===== producer warps 10..17: transpose the staged rows into pixel-pair lines
+    const int g = (warp - 10) >> 1, sub = warp & 1;
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(gen_base + (rows_base - res_base) + (size_t)g * prm.rows_bytes);
+    uint32_t phase = 0;
+    int i = 0;
+    for (PairTiles t(prm); t.valid(); t.next(prm), ++i) {
+      if ((i & (PR_GROUPS - 1)) != g) continue;
+      mbar_wait_relaxed(rfull(g), phase);
+      mbar_wait_relaxed(empty(g), phase ^ 1u);
+      pairs_build_tile(prm, rows, t_base + g * PR_STAGE_BYTES, t.tq * BLOCK_M, sub, lane);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(full(g)); mbar_arrive(rempty(g)); }
+      phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N_TILE) : "memory");
+  }
+}
+
+// Weight gradient on the same lines, transposed: D^T[256 weight columns][K output channels] += lines (A, MN-major: M atoms of 64 columns ONE LINE apart,
+// two M = 128 halves) x dy (B, MN-major through TMA: N = K channels, pixels beyond the row zero filled) over the CTA's tiles — N = K, not 256: a quarter of
+// the tensor time of the D[128 channels][256] form (whose M was half zero padding for K = 64), and a 16 KB dy slot per tile (K = 64), so six tiles of dy
+// are in flight: with two 32 KB slots the kernel ran at DRAM latency (ncu: 255 us, tensor pipe 44 %, every role waiting on the dy box).
+struct PairWgradParams {
+  PairParams g;
+  float* dw_col;
+  int dy_slots;
+};
+
+__global__ void __launch_bounds__(PR_WG_THREADS, 1) conv_wgrad_tc_pairs_kernel(const __grid_constant__ CUtensorMap map_dy, const PairWgradParams wp) {
+  const PairParams& prm = wp.g;
+  constexpr int A_SLAB = BLOCK_M * 128, MAX_SLOTS = 6;
+  extern __shared__ uint8_t smem_raw[];
+  const dcv_conv_shape& s = prm.s;
+  const int atoms = s.k / 64, slots = wp.dy_slots;
+  const uint32_t dy_bytes = (uint32_t)atoms * A_SLAB;
+  const uint32_t dy_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t t_base = dy_base + (uint32_t)slots * dy_bytes;
+  const uint32_t rows_base = t_base + PR_WG_STAGES * PR_STAGE_BYTES;
+  const uint32_t bars = rows_base + (uint32_t)PR_ROW_BUFS * (uint32_t)prm.rows_bytes;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (PR_WG_STAGES + i); };
+  auto afull = [&](int i) { return bars + 8u * (2 * PR_WG_STAGES + i); };
+  auto aempty = [&](int i) { return bars + 8u * (2 * PR_WG_STAGES + MAX_SLOTS + i); };
+  auto rfull = [&](int i) { return bars + 8u * (2 * PR_WG_STAGES + 2 * MAX_SLOTS + i); };
+  auto rempty = [&](int i) { return bars + 8u * (2 * PR_WG_STAGES + 2 * MAX_SLOTS + PR_ROW_BUFS + i); };
+  const uint32_t done = bars + 8u * (2 * PR_WG_STAGES + 2 * MAX_SLOTS + 2 * PR_ROW_BUFS), tmem_slot = done + 8u;
+  uint8_t* gen_base = smem_raw + (dy_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PR_WG_STAGES; ++i) { mbar_init(full(i), 2); mbar_init(empty(i), 1); }
+    for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(afull(i), 1); mbar_init(aempty(i), 1); }
+    for (int i = 0; i < PR_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), 2); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dy)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < (PR_WG_STAGES * PR_STAGE_BYTES + (uint32_t)PR_ROW_BUFS * (uint32_t)prm.rows_bytes) / 16u; i += PR_WG_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(t_base + i * 16u), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const bool any_tiles = PairTiles(prm).valid();
+
+  if (warp == 0) {
+    if (elect_one()) {   // ===== TMA: per tile the dy box(es) (pixels beyond the row are zero filled) and the R input rows
+      int buf = 0; uint32_t rphase = 0;
+      int as = 0; uint32_t aph = 0;
+      const uint32_t row_bytes = (uint32_t)(s.w * s.c) * 2u;
+      for (PairTiles t(prm); t.valid(); t.next(prm)) {
+        const int q0 = t.tq * BLOCK_M;
+        mbar_wait(aempty(as), aph ^ 1u);
+        mbar_expect_tx(afull(as), dy_bytes);
+        for (int a = 0; a < atoms; ++a) tma_load_4d(dy_base + as * dy_bytes + a * A_SLAB, &map_dy, afull(as), 64 * a, q0, t.op, t.img);
+        if (++as == slots) { as = 0; aph ^= 1u; }
+        mbar_wait(rempty(buf), rphase ^ 1u);
+        mbar_expect_tx(rfull(buf), (uint32_t)s.r * row_bytes);
+        const int iy0 = t.op * s.stride_h - s.pad_h;
+        for (int r = 0; r < s.r; ++r) {
+          const int iy = iy0 + r * s.dil_h;
+          const void* src = (iy >= 0 && iy < s.h) ? (const void*)(prm.x + ((size_t)t.img * s.h + iy) * (size_t)(s.w * s.c)) : (const void*)g_zero_row;
+          bulk_load_1d(rows_base + (uint32_t)buf * (uint32_t)prm.rows_bytes + (uint32_t)(r * prm.rowlen + prm.lpad) * 2u, src, row_bytes, rfull(buf));
+        }
+        if (++buf == PR_ROW_BUFS) { buf = 0; rphase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {   // ===== MMA issuer: per 16 pixels one M = 128 x N = K MMA for each half of the 256 weight columns
+      const uint32_t idesc = make_idesc(128, s.k, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aph = 0;
+      bool first = true;
+      for (PairTiles t(prm); t.valid(); t.next(prm)) {
+        mbar_wait(afull(as), aph);
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sdy = dy_base + as * dy_bytes, sl = t_base + stage * PR_STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {
+          const uint64_t bdesc = make_desc(sdy + ks * UMMA_K * 128, A_SLAB, 1024);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t adesc = make_desc(sl + h * 256 + ks * UMMA_K * 128, 128, 1024);
+            umma_bf16(tmem_base + (uint32_t)(h * s.k), adesc, bdesc, idesc, !(first && ks == 0));
+          }
+        }
+        first = false;
+        umma_commit(empty(stage));
+        umma_commit(aempty(as));
+        if (++stage == PR_WG_STAGES) { stage = 0; phase ^= 1u; }
+        if (++as == slots) { as = 0; aph ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else if (warp < 6) {
+    if (any_tiles) {   // ===== epilogue, once: TMEM lane = weight column within the half, TMEM column = output channel
+      const int quarter = warp & 3;
+      mbar_wait_relaxed(done, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int col = h * 128 + quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + (uint32_t)(h * s.k) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < s.k; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          float* dst = wp.dw_col + (size_t)c0 * PR_K + col;   // the 32 lanes of a warp: 32 consecutive floats
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * PR_K, __uint_as_float(v[j]));
+        }
+      }
+    }
+  } else {
+    const int g = (warp - 6) >> 1, sub = warp & 1;   // ===== producer warps 6..13, as in the forward kernel
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(gen_base + (rows_base - dy_base) + (size_t)g * prm.rows_bytes);
+    uint32_t phase = 0;
+    int i = 0;
+    for (PairTiles t(prm); t.valid(); t.next(prm), ++i) {
+      if ((i & (PR_GROUPS - 1)) != g) continue;
+      mbar_wait_relaxed(rfull(g), phase);
+      mbar_wait_relaxed(empty(g), phase ^ 1u);
+      pairs_build_tile(prm, rows, t_base + g * PR_STAGE_BYTES, t.tq * BLOCK_M, sub, lane);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(full(g)); mbar_arrive(rempty(g)); }
+      phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1132,6 +1520,95 @@ int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy,
   const int grid = wp.g.total_tiles < num_sms() ? wp.g.total_tiles : num_sms();
   kern<<<grid, GA_THREADS, smem, st>>>(mdy, wp);
   DCV_LAUNCH_CHECK("conv_wgrad_tc_gather_kernel");
+  return 0;
+}
+
+namespace tc {
+static int pairs_dy_slots(int k) { return k > 64 ? 3 : 6; }   // 96 KB of dy boxes in flight
+// Geometry of the pixel-pair kernels; false when the layer is not of that form (stride_w = 2, at most 4 input channels, window of 8 pixels, R <= 8).
+static bool pairs_geometry(const dcv_conv_shape* s, const void* x, PairParams* prm, size_t* smem_fwd, size_t* smem_wgrad) {
+  if (s->stride_w != 2 || s->dil_w != 1 || s->c < 1 || s->c > 4 || s->r < 1 || s->r > 8 || s->pad_w < 0 || s->pad_h < 0 || (s->k != 64 && s->k != 128)) return false;
+  const int e = s->pad_w & 1, wc = s->w * s->c;
+  if (s->s + e > 8 || wc % 8 != 0 || wc * 2 > kZeroRowBytes || reinterpret_cast<uintptr_t>(x) % 16 != 0) return false;
+  prm->s = *s;
+  prm->hp = (s->pad_w + e) / 2;
+  prm->lpad = (2 * prm->hp * s->c + 7) / 8 * 8;
+  int need = prm->lpad + 2 * (s->q + 2 - prm->hp) * s->c + 8;   // the last chunk a stored pixel reads (line q - 1 + 3) lies inside the row
+  if (need < prm->lpad + wc) need = prm->lpad + wc;
+  prm->rowlen = (need + 7) / 8 * 8;
+  prm->rows_bytes = s->r * prm->rowlen * 2;
+  prm->tiles_q = (s->q + BLOCK_M - 1) / BLOCK_M;
+  const long long tiles = (long long)s->n * s->p * prm->tiles_q;
+  if (tiles >= (1ll << 31) || (long long)s->n * s->p * s->q < 128) return false;
+  prm->total_tiles = (int)tiles;
+  *smem_fwd = 1024 + (size_t)PR_KBLOCKS * s->k * BLOCK_K * 2 + (size_t)PR_FWD_STAGES * PR_STAGE_BYTES + (size_t)PR_ROW_BUFS * prm->rows_bytes + 512;
+  *smem_wgrad = 1024 + (size_t)pairs_dy_slots(s->k) * (s->k / 64) * BLOCK_M * 128 + (size_t)PR_WG_STAGES * PR_STAGE_BYTES + (size_t)PR_ROW_BUFS * prm->rows_bytes + 512;
+  return *smem_fwd <= 227 * 1024 && *smem_wgrad <= 227 * 1024;
+}
+}  // namespace tc
+
+bool conv_tc_pairs_supported(const dcv_conv_shape* s, const void* x, int dtype) {
+  if (!s || dtype != DCV_BF16 || tc::encode_tiled() == nullptr) return false;
+  tc::PairParams prm{}; size_t a = 0, b = 0;
+  return tc::pairs_geometry(s, x, &prm, &a, &b);
+}
+
+// w_col: [K][256] bf16 in the pixel-pair K order (dcv_pairs_pack_weight).
+int conv_fwd_tc_pairs(const dcv_conv_shape* s, const void* x, const void* w_col, const float* bias, void* y, float* stats_nc, int act, float slope, int stats_flags, cudaStream_t st) {
+  using namespace tc;
+  DCV_REQUIRE(x && w_col && y, "conv2d_fwd_pairs: null pointer");
+  PairParams prm{}; size_t smem = 0, smem_w = 0;
+  DCV_REQUIRE(pairs_geometry(s, x, &prm, &smem, &smem_w), "conv2d_fwd_pairs: shape not supported (see dcv_conv2d_pairs_supported)");
+  prm.act = act; prm.slope = slope; prm.bias = bias; prm.x = reinterpret_cast<const __nv_bfloat16*>(x); prm.y = reinterpret_cast<__nv_bfloat16*>(y);
+  if (getenv("DCV_PAIRS_NOSTORE")) prm.y = nullptr;   // EXPERIMENT
+  CUtensorMap mw;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)PR_K, (cuuint64_t)s->k};
+    const cuuint64_t strides[1] = {(cuuint64_t)PR_K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)s->k};
+    if (make_map(&mw, w_col, 2, dims, strides, box)) return 1;
+  }
+  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
+  if (s->k == 128) {
+    auto kern = conv_fwd_tc_pairs_kernel<128>;
+    static size_t configured = 0;
+    if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    kern<<<grid, PR_FWD_THREADS, smem, st>>>(mw, prm);
+  } else {
+    auto kern = conv_fwd_tc_pairs_kernel<64>;
+    static size_t configured = 0;
+    if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    kern<<<grid, PR_FWD_THREADS, smem, st>>>(mw, prm);
+  }
+  DCV_LAUNCH_CHECK("conv_fwd_tc_pairs_kernel");
+  if (stats_nc) return dcv_norm_stats(y, stats_nc, s->n, s->p * s->q, s->k, DCV_BF16, DCV_ACC_PREZEROED | (stats_flags & DCV_STATS_CHANNEL_TOTALS), st);
+  return 0;
+}
+
+// dw_col: [K][256] fp32 in the pixel-pair K order (overwritten).
+int conv_wgrad_tc_pairs(const dcv_conv_shape* s, const void* x, const void* dy, float* dw_col, bool prezeroed, cudaStream_t st) {
+  using namespace tc;
+  DCV_REQUIRE(x && dy && dw_col, "conv2d_wgrad_pairs: null pointer");
+  DCV_REQUIRE(reinterpret_cast<uintptr_t>(dy) % 16 == 0 && reinterpret_cast<uintptr_t>(dw_col) % 16 == 0, "conv2d_wgrad_pairs: pointers must be 16-byte aligned");
+  PairWgradParams wp{}; size_t smem_f = 0, smem = 0;
+  DCV_REQUIRE(pairs_geometry(s, x, &wp.g, &smem_f, &smem), "conv2d_wgrad_pairs: shape not supported (see dcv_conv2d_pairs_supported)");
+  wp.g.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  wp.dw_col = dw_col;
+  wp.dy_slots = pairs_dy_slots(s->k);
+  zero_accumulator(dw_col, (size_t)s->k * PR_K * sizeof(float), st, prezeroed);
+  CUtensorMap mdy;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)s->k, (cuuint64_t)s->q, (cuuint64_t)s->p, (cuuint64_t)s->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s->k * 2, (cuuint64_t)s->q * s->k * 2, (cuuint64_t)s->p * s->q * s->k * 2};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)BLOCK_M, 1u, 1u};
+    if (make_map(&mdy, dy, 4, dims, strides, box)) return 1;
+  }
+  auto kern = conv_wgrad_tc_pairs_kernel;
+  static size_t configured = 0;
+  if (configured < smem) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+  const int grid = wp.g.total_tiles < num_sms() ? wp.g.total_tiles : num_sms();
+  kern<<<grid, PR_WG_THREADS, smem, st>>>(mdy, wp);
+  DCV_LAUNCH_CHECK("conv_wgrad_tc_pairs_kernel");
   return 0;
 }
 

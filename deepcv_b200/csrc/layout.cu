@@ -215,6 +215,28 @@ __global__ void gather_unpack_wgrad_kernel(const float* __restrict__ dw_col, flo
   }
 }
 
+// Weight operand of the pixel-pair convolution kernels (conv_tc.cu): [K][256], column pp * 64 + r * 8 + px * C + c = w[k][r][2 pp + px - e][c] with e = pad_w & 1
+// (output pixel q reads the pixel pairs q - hp .. q - hp + 3 of every filter row, one 128-byte line per pair), zero elsewhere; and the way back.
+constexpr int kPairsK = 256;
+template <typename T>
+__global__ void pairs_pack_weight_kernel(const T* __restrict__ w, T* __restrict__ w_col, int k, int r, int s, int c, int e) {
+  const int total = k * kPairsK;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i & (kPairsK - 1), kr = i / kPairsK, pp = kk >> 6, rr = (kk >> 3) & 7, el = kk & 7, px = el / c, ch = el - px * c, tap = 2 * pp + px - e;
+    w_col[i] = (rr < r && px < 2 && tap >= 0 && tap < s) ? w[(((size_t)kr * r + rr) * s + tap) * c + ch] : from_f<T>(0.f);
+  }
+}
+__global__ void pairs_unpack_wgrad_kernel(const float* __restrict__ dw_col, float* __restrict__ dw, int k, int r, int s, int c, int e) {
+  const int total = k * r * s * c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int ch = t % c; t /= c;
+    const int tap = t % s; t /= s;
+    const int rr = t % r, kr = t / r, wp = tap + e;
+    dw[i] = dw_col[(size_t)kr * kPairsK + (wp >> 1) * 64 + rr * 8 + (wp & 1) * c + ch];
+  }
+}
+
 // Batch assembly for the device-resident input pipeline: dst row j = src row idx[j]; rows are `row_bytes` long (a multiple of 16, both bases 16-byte
 // aligned). One warp streams a row with 16-byte accesses; an index outside [0, n_src) traps nothing and copies nothing but flags the batch (err != 0).
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ idx, uint4* __restrict__ dst, int n, long long n_src, uint32_t vec_per_row, int* __restrict__ err) {
@@ -325,6 +347,22 @@ int dcv_gather_unpack_wgrad(const float* dw_col, float* dw_krsc, int k, int r, i
   DCV_REQUIRE(dw_col && dw_krsc && k > 0 && r > 0 && sc > 0 && kpad >= r * rp, "gather_unpack_wgrad: bad arguments");
   gather_unpack_wgrad_kernel<<<grid_for((size_t)k * r * sc, 256), 256, 0, as_stream(stream)>>>(dw_col, dw_krsc, k, r, sc, rp, kpad);
   DCV_LAUNCH_CHECK("gather_unpack_wgrad_kernel");
+  return 0;
+}
+
+int dcv_pairs_pack_weight(const void* w_krsc, void* w_col, const dcv_conv_shape* shape, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(w_krsc && w_col && shape && shape->c >= 1 && shape->c <= 4 && shape->r <= 8 && shape->s + (shape->pad_w & 1) <= 8, "pairs_pack_weight: bad arguments");
+  DCV_DISPATCH_DTYPE(dtype, T, (pairs_pack_weight_kernel<T><<<grid_for((size_t)shape->k * kPairsK, 256), 256, 0, as_stream(stream)>>>((const T*)w_krsc, (T*)w_col, shape->k, shape->r, shape->s, shape->c, shape->pad_w & 1)));
+  DCV_LAUNCH_CHECK("pairs_pack_weight_kernel");
+  return 0;
+}
+
+int dcv_pairs_unpack_wgrad(const float* dw_col, float* dw_krsc, const dcv_conv_shape* shape, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dw_col && dw_krsc && shape && shape->c >= 1 && shape->c <= 4 && shape->r <= 8 && shape->s + (shape->pad_w & 1) <= 8, "pairs_unpack_wgrad: bad arguments");
+  pairs_unpack_wgrad_kernel<<<grid_for((size_t)shape->k * shape->r * shape->s * shape->c, 256), 256, 0, as_stream(stream)>>>(dw_col, dw_krsc, shape->k, shape->r, shape->s, shape->c, shape->pad_w & 1);
+  DCV_LAUNCH_CHECK("pairs_unpack_wgrad_kernel");
   return 0;
 }
 

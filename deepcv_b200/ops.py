@@ -290,6 +290,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 # (64-channel halo kernel 77 -> 90 us with per-thread partial sums, 128 / 256-channel kernels 60 -> 90 us with a per-tile butterfly, stem 402 -> 594 us).
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
+_USE_PAIRS = os.environ.get('DCV_NO_PAIRS') is None     # tuning aid: DCV_NO_PAIRS=1 sends stride-2 few-channel layers to the gather kernels instead of the pixel-pair ones
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
 
 
@@ -356,14 +357,21 @@ class _ConvBlock(torch.autograd.Function):
             gemm_shape = ConvShape(n, p, q, kpad, k, 1, 1, 1, 1, 0, 0, 1, 1, p, q)
             if not lib.dcv_conv2d_tc_supported(ctypes.byref(gemm_shape), dt, 0):
                 gemm_shape = None
-        gathered = False
+        gathered = 0
         if gemm_shape is not None:
             # gather kernels: producer warps build the im2col tile in shared memory, col[n][p][q][kpad] (1.2 GB for the stem at batch 256) is never
             # materialised. Their K order pads every filter row to a multiple of 8 elements (see dcv_gather_pack_weight).
             sc = shape.s * shape.c
             kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
-            gathered = bool(_USE_GATHER and lib.dcv_conv2d_gather_supported(ctypes.byref(shape), _ptr(x), kpad_g, dt))
-            if gathered:
+            if _USE_GATHER and _USE_PAIRS and lib.dcv_conv2d_pairs_supported(ctypes.byref(shape), _ptr(x), dt):
+                gathered = 2     # stride 2, at most four input channels (the stem): tensor-core tiles straight over pair-transposed input rows
+            elif _USE_GATHER and lib.dcv_conv2d_gather_supported(ctypes.byref(shape), _ptr(x), kpad_g, dt):
+                gathered = 1
+            if gathered == 2:
+                w_col = torch.empty((k, 256), dtype=x.dtype, device=dev)
+                check(lib.dcv_pairs_pack_weight(_ptr(w_op), _ptr(w_col), ctypes.byref(shape), dt, st), 'pairs_pack_weight')
+                check(lib.dcv_conv2d_fwd_pairs(ctypes.byref(shape), _ptr(x), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, pz | totals, st), 'conv2d_fwd_pairs')
+            elif gathered:
                 w_col = torch.empty((k, kpad_g), dtype=x.dtype, device=dev)
                 check(lib.dcv_gather_pack_weight(_ptr(w_op), _ptr(w_col), k, shape.r, sc, kpad_g, dt, st), 'gather_pack_weight')
                 check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), _ptr(x), _ptr(w_col), kpad_g, _ptr(bias), _ptr(y), _ptr(stats), act, slope, pz | totals, st), 'conv2d_fwd_gather')
@@ -436,7 +444,11 @@ class _ConvBlock(torch.autograd.Function):
             dw = targets.get('weight', None)
             if dw is None:
                 dw = _acc_empty((k, shape.r, shape.s, shape.c), dev, sctx).permute(0, 3, 1, 2)
-            if gathered:                 # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
+            if gathered == 2:            # x is the layer input; dw_col[K][256] in the pixel-pair K order, then back to [K][R][S][C]
+                dw_col = _acc_empty((k, 256), dev, sctx)
+                check(lib.dcv_conv2d_wgrad_pairs(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), pz, st), 'conv2d_wgrad_pairs')
+                check(lib.dcv_pairs_unpack_wgrad(_ptr(dw_col), _ptr(dw), ctypes.byref(shape), st), 'pairs_unpack_wgrad')
+            elif gathered:               # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
                 sc = shape.s * shape.c
                 kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
                 dw_col = _acc_empty((k, kpad_g), dev, sctx)

@@ -104,6 +104,17 @@ int dcv_conv2d_fwd_gather(const dcv_conv_shape* shape, const void* x, const void
                           int act, float slope, int acc_prezeroed, void* stream);
 /* dw_col[K][kpad] (fp32, gather K order, overwritten) = sum over pixels of dy * im2col(x); unpack with dcv_gather_unpack_wgrad. */
 int dcv_conv2d_wgrad_gather(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int kpad, int acc_prezeroed, void* stream);
+/* Stride-2 few-channel convolutions (stride_w = 2, C <= 4, S + (pad_w & 1) <= 8, R <= 8, K = 64 or 128: the 3 -> 64, 7x7 / stride-2 stem) on the "pixel pair"
+ * kernels: the input rows of an output row are staged one 128-byte line per pixel PAIR and the tensor core reads overlapping K-major (forward) / MN-major
+ * (weight gradient) tiles straight out of those lines — no im2col tile is built. w_col / dw_col: [K][256] in the K order
+ * column pp*64 + r*8 + px*C + c = w[k][r][2*pp + px - (pad_w & 1)][c] (dcv_pairs_pack_weight / dcv_pairs_unpack_wgrad; dw_col fp32, overwritten).
+ * Arguments otherwise as the gather entry points above. */
+int dcv_conv2d_pairs_supported(const dcv_conv_shape* shape, const void* x, int dtype);
+int dcv_pairs_pack_weight(const void* w_krsc, void* w_col, const dcv_conv_shape* shape, int dtype, void* stream);
+int dcv_pairs_unpack_wgrad(const float* dw_col, float* dw_krsc, const dcv_conv_shape* shape, void* stream);
+int dcv_conv2d_fwd_pairs(const dcv_conv_shape* shape, const void* x, const void* w_col, const float* bias, void* y, float* stats_nc,
+                         int act, float slope, int acc_prezeroed, void* stream);
+int dcv_conv2d_wgrad_pairs(const dcv_conv_shape* shape, const void* x, const void* dy, float* dw_col, int acc_prezeroed, void* stream);
 /* Flags of the `acc_prezeroed` argument of dcv_conv2d_fwd / dcv_conv2d_fwd_gather / dcv_norm_stats / dcv_norm_bwd_reduce (other entry points: 0 / 1). */
 #define DCV_ACC_PREZEROED 1          /* the caller has zeroed every accumulator this call adds into */
 #define DCV_STATS_CHANNEL_TOTALS 2   /* only the per-CHANNEL totals of the [n][c][..] sums will be used (a BatchNorm-only block: no GroupNorm / InstanceNorm):

@@ -175,6 +175,54 @@ def test_gather_forward_wgrad_bit_exact(dev, n, c, h, w, k, ks, stride, pad):
     _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'gather weight gradient (fp32)')
 
 
+# n, c, h, w, k, ksize, pad — stride 2, at most four input channels: the pixel-pair kernels (overlapping tensor-core tiles over pair-transposed rows)
+PAIRS_EXACT = [
+    (2, 3, 224, 224, 64, 7, 3),    # the stem of the ImageNet-shaped net, real size
+    (3, 3, 48, 40, 64, 7, 3),      # ragged rows (q = 20 < 128: one partial tile per row)
+    (2, 4, 36, 32, 128, 5, 2),     # four channels (a whole 16-byte chunk per pair), two output-channel atoms, even padding
+    (2, 2, 10, 528, 64, 3, 1),     # rows longer than two tiles
+    (3, 1, 16, 32, 64, 7, 3),      # one channel
+    (2, 3, 30, 64, 64, 8, 4),      # eight filter rows, eight taps
+]
+
+
+@pytest.mark.parametrize('n,c,h,w,k,ks,pad', PAIRS_EXACT, ids=lambda v: str(v))
+def test_pixel_pair_forward_wgrad_bit_exact(dev, n, c, h, w, k, ks, pad):
+    from deepcv_b200._lib import ACT_NONE, DCV_BF16, ConvShape, check, lib
+    g = torch.Generator().manual_seed(c * 100 + h + k)
+    stride = 2
+    p, q = (h + 2 * pad - ks) // stride + 1, (w + 2 * pad - ks) // stride + 1
+    x = _ints((n, c, h, w), -2, 2, g)
+    wt = _ints((k, c, ks, ks), -1, 1, g).requires_grad_(True)
+    bias = _ints((k,), -3, 3, g)
+    dy = _ints((n, k, p, q), -2, 2, g)
+    y_ref = F.conv2d(x, wt, bias, stride=stride, padding=pad)
+    y_ref.backward(dy)
+    shape = ConvShape(n, h, w, c, k, ks, ks, stride, stride, pad, pad, 1, 1, p, q)
+    xd, dyd = _nhwc(x, dev), _nhwc(dy, dev)
+    assert lib.dcv_conv2d_pairs_supported(ctypes.byref(shape), P(xd), DCV_BF16), 'shape not served by the pixel-pair kernels'
+    st = stream()
+    wd = wt.detach().permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)
+    w_col = torch.full((k, 256), 7., device=dev, dtype=torch.bfloat16)
+    check(lib.dcv_pairs_pack_weight(P(wd), P(w_col), ctypes.byref(shape), DCV_BF16, st), 'pairs_pack_weight')
+    assert float(w_col.float().abs().sum()) == float(wt.detach().abs().sum())   # every weight exactly once, zeros elsewhere
+    yd = torch.full((n, p, q, k), 7., device=dev, dtype=torch.bfloat16)
+    bd = bias.to(dev)
+    check(lib.dcv_conv2d_fwd_pairs(ctypes.byref(shape), P(xd), P(w_col), P(bd), P(yd), None, ACT_NONE, 0., 0, st), 'conv2d_fwd_pairs')
+    _assert_equal(yd.permute(0, 3, 1, 2), y_ref.detach().bfloat16(), 'pixel-pair forward')
+    stats = torch.full((n, k, 2), 7., device=dev)
+    check(lib.dcv_conv2d_fwd_pairs(ctypes.byref(shape), P(xd), P(w_col), P(bd), P(yd), P(stats), ACT_NONE, 0., 0, st), 'conv2d_fwd_pairs(stats)')
+    yf = y_ref.detach().bfloat16().double()
+    assert torch.equal(stats[..., 0].double().cpu(), yf.sum((2, 3))), 'sum y'
+    r2 = (yf * yf).sum((2, 3))
+    assert float((stats[..., 1].double().cpu() - r2).abs().max()) <= 1e-6 * float(r2.max()) + 1e-3, 'sum y^2'
+    dw_col = torch.full((k, 256), 7., device=dev)
+    check(lib.dcv_conv2d_wgrad_pairs(ctypes.byref(shape), P(xd), P(dyd), P(dw_col), 0, st), 'conv2d_wgrad_pairs')
+    dwd = torch.full((k, ks, ks, c), 7., device=dev)
+    check(lib.dcv_pairs_unpack_wgrad(P(dw_col), P(dwd), ctypes.byref(shape), st), 'pairs_unpack_wgrad')
+    _assert_equal(dwd.permute(0, 3, 1, 2), wt.grad, 'pixel-pair weight gradient (fp32)')
+
+
 @pytest.mark.parametrize('n,c,h,w,k,ks,pad', [(4, 3, 32, 32, 4, 5, 2), (4, 4, 32, 32, 4, 5, 2), (3, 4, 16, 16, 16, 3, 1), (3, 16, 16, 16, 16, 3, 1), (2, 5, 13, 11, 6, 3, 1)], ids=lambda v: str(v))
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
 def test_direct_kernels_bit_exact(dev, n, c, h, w, k, ks, pad, dtype):

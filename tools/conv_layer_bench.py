@@ -19,33 +19,35 @@ LAYERS = [  # name, c, h, k, ksize
 ]
 
 
+STEM_LAYERS = [('stem 3->64 7x7/2 @224', 3, 224, 64, 7, 2)]   # the gather kernels (no data gradient: the input is the image)
 CIFAR_LAYERS = [('c1 3->4 5x5 @32', 3, 32, 4, 5), ('c2 4->4 5x5 @32', 4, 32, 4, 5), ('c4 4->16 3x3 @16', 4, 16, 16, 3), ('c5 16->16 3x3 @16', 16, 16, 16, 3)]
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--net', default='resnet', choices=['resnet', 'cifar'])
+    ap.add_argument('--net', default='resnet', choices=['resnet', 'cifar', 'stem'])
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--ops', default='fwd,dgrad,wgrad')
     ap.add_argument('--algo', default='auto')
     ap.add_argument('--only', default=None, help='substring filter on the layer name')
     args = ap.parse_args()
-    algo = ALGO_AUTO if args.algo == 'auto' else ALGO_DIRECT
+    algo = ALGO_DIRECT if args.algo == 'direct' else ALGO_AUTO
     peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text()) if (ROOT / 'MEASURED_PEAKS.json').exists() else {'bf16_tflops': 1590.0}
     dev = torch.device('cuda')
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     n = args.batch
-    for name, c, h, k, ks in (LAYERS if args.net == 'resnet' else CIFAR_LAYERS):
+    for name, c, h, k, ks, *rest in {'resnet': LAYERS, 'cifar': CIFAR_LAYERS, 'stem': STEM_LAYERS}[args.net]:
         if args.only and args.only not in name:
             continue
-        pad = ks // 2
-        shape = ConvShape(n, h, h, c, k, ks, ks, 1, 1, pad, pad, 1, 1, h, h)
-        act_bytes = n * h * h * (c + k) * 2
+        pad, stride = ks // 2, (rest[0] if rest else 1)
+        ho = (h + 2 * pad - ks) // stride + 1
+        shape = ConvShape(n, h, h, c, k, ks, ks, stride, stride, pad, pad, 1, 1, ho, ho)
+        act_bytes = n * (h * h * c + ho * ho * k) * 2
         reps = max(2, int(300e6 // act_bytes) + 1)
         xs = [torch.randn(n, h, h, c, device=dev).bfloat16() for _ in range(reps)]
-        ys = [torch.randn(n, h, h, k, device=dev).bfloat16() for _ in range(reps)]
+        ys = [torch.randn(n, ho, ho, k, device=dev).bfloat16() for _ in range(reps)]
         w = (torch.randn(k, ks, ks, c, device=dev) * 0.05).bfloat16()
         w32 = w.float()
         wt = torch.empty(c, ks, ks, k, device=dev, dtype=torch.bfloat16)
@@ -54,11 +56,33 @@ def main():
         dw = torch.empty(k, ks, ks, c, device=dev)
         ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), DCV_BF16, algo))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-        flop = 2.0 * n * h * h * k * c * ks * ks
+        flop = 2.0 * n * ho * ho * k * c * ks * ks
         row = {'layer': name}
+        gather = None
+        if stride != 1:   # served by the gather kernels (software im2col in shared memory): their own weight layout
+            sc = ks * c
+            kpad = (ks * ((sc + 7) // 8 * 8) + 63) // 64 * 64
+            assert lib.dcv_conv2d_gather_supported(ctypes.byref(shape), P(xs[0]), kpad, DCV_BF16)
+            w_col = torch.empty(k, kpad, device=dev, dtype=torch.bfloat16)
+            check(lib.dcv_gather_pack_weight(P(w), P(w_col), k, ks, sc, kpad, DCV_BF16, st), 'gather_pack_weight')
+            gather = (w_col, kpad, torch.empty(k, kpad, device=dev))
+            if args.algo != 'gather' and lib.dcv_conv2d_pairs_supported(ctypes.byref(shape), P(xs[0]), DCV_BF16):   # stride 2, <= 4 channels: the pixel-pair kernels
+                w_col = torch.empty(k, 256, device=dev, dtype=torch.bfloat16)
+                check(lib.dcv_pairs_pack_weight(P(w), P(w_col), ctypes.byref(shape), DCV_BF16, st), 'pairs_pack_weight')
+                gather = (w_col, 0, torch.empty(k, 256, device=dev))
         for op in args.ops.split(','):
+            if op == 'dgrad' and stride != 1:
+                continue
             def launch(i):
-                if op == 'fwd':
+                if gather is not None and gather[1] == 0 and op == 'fwd':
+                    check(lib.dcv_conv2d_fwd_pairs(ctypes.byref(shape), P(xs[i]), P(gather[0]), P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, 0, st), op)
+                elif gather is not None and gather[1] == 0:
+                    check(lib.dcv_conv2d_wgrad_pairs(ctypes.byref(shape), P(xs[i]), P(ys[i]), P(gather[2]), 0, st), op)
+                elif gather is not None and op == 'fwd':
+                    check(lib.dcv_conv2d_fwd_gather(ctypes.byref(shape), P(xs[i]), P(gather[0]), gather[1], P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, 0, st), op)
+                elif gather is not None:
+                    check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), P(xs[i]), P(ys[i]), P(gather[2]), gather[1], 0, st), op)
+                elif op == 'fwd':
                     check(lib.dcv_conv2d_fwd(ctypes.byref(shape), P(xs[i]), P(w), P(bias), P(ys[i]), None, ACT_LEAKY_RELU, 0.01, DCV_BF16, algo, 0, st), op)
                 elif op == 'dgrad':
                     check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), P(ys[i]), P(w), P(wt), P(xs[i]), DCV_BF16, algo, st), op)
@@ -75,7 +99,7 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / (args.iters * reps)
             row[op] = dict(ms=round(ms, 4), tflops=round(flop / ms / 1e9, 1), frac_of_peak=round(flop / ms / 1e9 / peaks['bf16_tflops'], 3),
-                           tc=int(lib.dcv_conv2d_tc_supported(ctypes.byref(shape), DCV_BF16, {'fwd': 0, 'dgrad': 1, 'wgrad': 2}[op])) if algo == ALGO_AUTO else 0)
+                           tc=int(gather is not None or lib.dcv_conv2d_tc_supported(ctypes.byref(shape), DCV_BF16, {'fwd': 0, 'dgrad': 1, 'wgrad': 2}[op])) if algo == ALGO_AUTO else 0)
         print(json.dumps(row))
 
 
