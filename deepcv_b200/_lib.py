@@ -93,6 +93,8 @@ SYMBOLS = {
     'dcv_norm_saved_floats': (c_size_t, [c_int, c_int, c_int]),
     'dcv_norm_fwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P]),
     'dcv_norm_apply_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_norm_apply_add_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_norm_apply_pool_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_conv2d_gather_supported': (c_int, [POINTER(ConvShape), P, c_int, c_int]),
     'dcv_gather_pack_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_gather_unpack_wgrad': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

@@ -952,7 +952,7 @@ struct PairParams {
 constexpr int PR_LINES = BLOCK_M + 3, PR_STAGE_BYTES = 18 * 1024, PR_K = 256, PR_KBLOCKS = PR_K / BLOCK_K;
 // Four producer GROUPS of two warps: group g builds the tiles i = g (mod 4) of the CTA in line stage g from row buffer g — four tiles are under construction
 // at once. (All eight warps on one tile ran at the latency of wait -> 4 units -> fence -> arrive per tile: 0.96 us per tile with the stores switched off.)
-constexpr int PR_GROUPS = 4, PR_FWD_STAGES = PR_GROUPS, PR_WG_STAGES = PR_GROUPS, PR_ROW_BUFS = PR_GROUPS, PR_PRODUCERS = PR_GROUPS * 64;
+constexpr int PR_GROUPS = 4, PR_FWD_STAGES = PR_GROUPS, PR_WG_STAGES = PR_GROUPS, PR_ROW_BUFS = 2 * PR_GROUPS, PR_PRODUCERS = PR_GROUPS * 64;   // two row buffers per group: the rows of its next tile land while it builds the current one
 constexpr int PR_FWD_THREADS = 64 + 256 + PR_PRODUCERS;   // warps: 0 TMA, 1 MMA, 2..9 epilogue, 10..17 producers
 constexpr int PR_WG_THREADS = 64 + 128 + PR_PRODUCERS;                                          // warps: 0 TMA, 1 MMA, 2..5 epilogue, 6..13 producers
 
@@ -1138,7 +1138,7 @@ __global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(co
         const int c0 = half * (N_TILE / 2) + 32 * ci;
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
-        if (valid && prm.y) pairs_store32_dyn(prm.act, v, bias_regs[ci], prm.slope, dst + c0);
+        if (valid) pairs_store32_dyn(prm.act, v, bias_regs[ci], prm.slope, dst + c0);
       }
       tc_fence_before();
       __syncwarp();
@@ -1148,18 +1148,19 @@ __global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(co
   } else {
     // ===== producer warps 10..17: transpose the staged rows into pixel-pair lines
     const int g = (warp - 10) >> 1, sub = warp & 1;
-    const uint32_t* rows = reinterpret_cast<const uint32_t*>(gen_base + (rows_base - res_base) + (size_t)g * prm.rows_bytes);
-    uint32_t phase = 0;
-    int i = 0;
+    int i = 0, own = 0;
     for (PairTiles t(prm); t.valid(); t.next(prm), ++i) {
       if ((i & (PR_GROUPS - 1)) != g) continue;
-      mbar_wait_relaxed(rfull(g), phase);
+      const int buf = g + PR_GROUPS * (own & 1);   // = i mod PR_ROW_BUFS, the loader's order
+      const uint32_t phase = (uint32_t)(own & 1), rphase = (uint32_t)((own >> 1) & 1);
+      const uint32_t* rows = reinterpret_cast<const uint32_t*>(gen_base + (rows_base - res_base) + (size_t)buf * prm.rows_bytes);
+      mbar_wait_relaxed(rfull(buf), rphase);
       mbar_wait_relaxed(empty(g), phase ^ 1u);
       pairs_build_tile(prm, rows, t_base + g * PR_STAGE_BYTES, t.tq * BLOCK_M, sub, lane);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(full(g)); mbar_arrive(rempty(g)); }
-      phase ^= 1u;
+      if (lane == 0) { mbar_arrive(full(g)); mbar_arrive(rempty(buf)); }
+      ++own;
     }
   }
   tc_fence_before();
@@ -1294,18 +1295,19 @@ __global__ void __launch_bounds__(PR_WG_THREADS, 1) conv_wgrad_tc_pairs_kernel(c
     }
   } else {
     const int g = (warp - 6) >> 1, sub = warp & 1;   // ===== producer warps 6..13, as in the forward kernel
-    const uint32_t* rows = reinterpret_cast<const uint32_t*>(gen_base + (rows_base - dy_base) + (size_t)g * prm.rows_bytes);
-    uint32_t phase = 0;
-    int i = 0;
+    int i = 0, own = 0;
     for (PairTiles t(prm); t.valid(); t.next(prm), ++i) {
       if ((i & (PR_GROUPS - 1)) != g) continue;
-      mbar_wait_relaxed(rfull(g), phase);
+      const int buf = g + PR_GROUPS * (own & 1);   // = i mod PR_ROW_BUFS, the loader's order
+      const uint32_t phase = (uint32_t)(own & 1), rphase = (uint32_t)((own >> 1) & 1);
+      const uint32_t* rows = reinterpret_cast<const uint32_t*>(gen_base + (rows_base - dy_base) + (size_t)buf * prm.rows_bytes);
+      mbar_wait_relaxed(rfull(buf), rphase);
       mbar_wait_relaxed(empty(g), phase ^ 1u);
       pairs_build_tile(prm, rows, t_base + g * PR_STAGE_BYTES, t.tq * BLOCK_M, sub, lane);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(full(g)); mbar_arrive(rempty(g)); }
-      phase ^= 1u;
+      if (lane == 0) { mbar_arrive(full(g)); mbar_arrive(rempty(buf)); }
+      ++own;
     }
   }
   tc_fence_before();
@@ -1524,7 +1526,7 @@ int conv_wgrad_tc_gather(const dcv_conv_shape* s, const void* x, const void* dy,
 }
 
 namespace tc {
-static int pairs_dy_slots(int k) { return k > 64 ? 3 : 6; }   // 96 KB of dy boxes in flight
+static int pairs_dy_slots(int k) { return k > 64 ? 2 : 4; }   // 64 KB of dy boxes in flight
 // Geometry of the pixel-pair kernels; false when the layer is not of that form (stride_w = 2, at most 4 input channels, window of 8 pixels, R <= 8).
 static bool pairs_geometry(const dcv_conv_shape* s, const void* x, PairParams* prm, size_t* smem_fwd, size_t* smem_wgrad) {
   if (s->stride_w != 2 || s->dil_w != 1 || s->c < 1 || s->c > 4 || s->r < 1 || s->r > 8 || s->pad_w < 0 || s->pad_h < 0 || (s->k != 64 && s->k != 128)) return false;
@@ -1560,7 +1562,6 @@ int conv_fwd_tc_pairs(const dcv_conv_shape* s, const void* x, const void* w_col,
   PairParams prm{}; size_t smem = 0, smem_w = 0;
   DCV_REQUIRE(pairs_geometry(s, x, &prm, &smem, &smem_w), "conv2d_fwd_pairs: shape not supported (see dcv_conv2d_pairs_supported)");
   prm.act = act; prm.slope = slope; prm.bias = bias; prm.x = reinterpret_cast<const __nv_bfloat16*>(x); prm.y = reinterpret_cast<__nv_bfloat16*>(y);
-  if (getenv("DCV_PAIRS_NOSTORE")) prm.y = nullptr;   // EXPERIMENT
   CUtensorMap mw;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)PR_K, (cuuint64_t)s->k};

@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, flo
 }
 
 // ---- forward apply: z = A*y + B
-template <typename T, int VE>
-__global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ z, const NcGeom g) {
+template <typename T, int VE, bool ADD = false>
+__global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ z, const NcGeom g, const T* __restrict__ other = nullptr) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
   if (colg >= g.cv) return;
@@ -204,19 +204,53 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
     }
     const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
     for (int p = p0 + row; p < p1; p += UNR * g.rows) {
-      Raw<T, VE> r[UNR];
+      Raw<T, VE> r[UNR], o[ADD ? UNR : 1];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) r[u] = (p + u * g.rows < p1) ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+      for (int u = 0; u < UNR; ++u) {
+        r[u] = (p + u * g.rows < p1) ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+        if constexpr (ADD) o[u] = (p + u * g.rows < p1) ? load_raw<T, VE>(other + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+      }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         float v[VE];
         unpack_raw<T, VE>(r[u], v);
 #pragma unroll
         for (int e = 0; e < VE; ++e) v[e] = fmaf(A[e], v[e], B[e]);
+        if constexpr (ADD) {   // the residual link that follows the block (sum with a tensor of the same shape), in the same pass
+          float w[VE];
+          unpack_raw<T, VE>(o[u], w);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) v[e] += w[e];
+        }
         if (p + u * g.rows < p1) store_vec<T, VE>(z + base + (size_t)(p + u * g.rows) * g.span, v);
       }
     }
   });
+}
+
+// ---- forward apply fused with the 2x2 / stride-2 average pooling that follows the block: zp = A * avgpool(y) + B (= avgpool(A*y + B)); the normalised
+// full-resolution tensor is never written. One thread per (pooled pixel, channel vector).
+template <typename T, int VE>
+__global__ void __launch_bounds__(256) apply_pool_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ zp, int h, int w, int c, uint32_t total,
+                                                             const FastDiv div_cv, const FastDiv div_q, const FastDiv div_p) {
+  const int cv = c / VE, q = w >> 1;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t t = div_cv.div(idx);
+    const int cc = (int)(idx - t * cv);
+    const uint32_t row = div_q.div(t);             // row = img * p + oy
+    const int ox = (int)(t - row * q);
+    const uint32_t img = div_p.div(row);
+    const T* src = y + (((size_t)row * 2) * w + (size_t)ox * 2) * c + (size_t)cc * VE;   // (img*p + oy) * 2 == img*h + 2*oy
+    float v0[VE], v1[VE], v2[VE], v3[VE], out[VE];
+    load_vec<T, VE>(src, v0); load_vec<T, VE>(src + c, v1); load_vec<T, VE>(src + (size_t)w * c, v2); load_vec<T, VE>(src + (size_t)(w + 1) * c, v3);
+    const float2* abp = reinterpret_cast<const float2*>(ab) + (size_t)img * c + (size_t)cc * VE;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      const float2 k = __ldg(abp + e);
+      out[e] = fmaf(k.x, ((v0[e] + v1[e]) + (v2[e] + v3[e])) * 0.25f, k.y);
+    }
+    store_vec<T, VE>(zp + (size_t)idx * VE, out);
+  }
 }
 
 // ---- backward reduce: s[n][c][2] += {sum dz, sum dz*y}
@@ -660,6 +694,42 @@ int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, flo
   finalize_grid(prm, &cpb, &blocks);
   fwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, ab_nc, saved, cpb);
   DCV_LAUNCH_CHECK("fwd_finalize_kernel");
+  return 0;
+}
+
+int dcv_norm_apply_add_fwd(const void* y, const float* ab_nc, const void* other, void* z, int n, int hw, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(y && ab_nc && other && z, "norm_apply_add_fwd: null pointer");
+  if (check_nc("norm_apply_add_fwd", n, hw, c)) return 1;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (vec_ok(y, z, other, n, hw, c, VE)) { static const int occ = streaming_ctas_per_sm((const void*)apply_fwd_kernel<T, VE, true>); NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block); apply_fwd_kernel<T, VE, true><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g, (const T*)other); }
+    else { static const int occ = streaming_ctas_per_sm((const void*)apply_fwd_kernel<T, 1, true>); NcGeom g = make_geom<1>(n, hw, c, occ, &grid, &block); apply_fwd_kernel<T, 1, true><<<grid, block, 0, st>>>((const T*)y, ab_nc, (T*)z, g, (const T*)other); }
+  });
+  DCV_LAUNCH_CHECK("apply_fwd_kernel(add)");
+  return 0;
+}
+
+int dcv_norm_apply_pool_fwd(const void* y, const float* ab_nc, void* zp, int n, int h, int w, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(y && ab_nc && zp, "norm_apply_pool_fwd: null pointer");
+  DCV_REQUIRE(n > 0 && c > 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0, "norm_apply_pool_fwd: the 2x2 / stride-2 windows must tile the %dx%d input", h, w);
+  DCV_REQUIRE((size_t)n * (h / 2) * (w / 2) * c < (1ull << 31), "norm_apply_pool_fwd: tensor too large");
+  cudaStream_t st = as_stream(stream);
+  const int p = h / 2, q = w / 2;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    if (c % VE == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 && reinterpret_cast<uintptr_t>(zp) % 16 == 0) {
+      const uint32_t total = (uint32_t)((size_t)n * p * q * (c / VE));
+      apply_pool_fwd_kernel<T, VE><<<grid_for(total, 256), 256, 0, st>>>((const T*)y, ab_nc, (T*)zp, h, w, c, total, FastDiv(c / VE), FastDiv(q), FastDiv(p));
+    } else {
+      const uint32_t total = (uint32_t)((size_t)n * p * q * c);
+      apply_pool_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>((const T*)y, ab_nc, (T*)zp, h, w, c, total, FastDiv(c), FastDiv(q), FastDiv(p));
+    }
+  });
+  DCV_LAUNCH_CHECK("apply_pool_fwd_kernel");
   return 0;
 }
 

@@ -73,15 +73,16 @@ class DeepcvModule(torch.nn.Module):
         referenced_output_features: Dict[str, torch.Tensor] = {}
         remaining_submodule_references = {} if sequential else copy.copy(self._submodule_references)
         for i, (name, subm) in enumerate(zip(names, children)):
-            if isinstance(x, ops.PendingAffine) and not getattr(subm, 'accepts_pending_affine', False):
+            if isinstance(x, (ops.PendingAffine, ops.PendingNorm)) and not getattr(subm, 'accepts_pending_affine', False):
                 x = ops.materialize(x)
             if isinstance(x, ops.PendingFlatten) and not getattr(subm, 'accepts_pending_flatten', False):
                 x = ops.materialize(x)
             n_referrers = sum(name in r for r in remaining_submodule_references.values())
             kwargs = {}
             if getattr(subm, 'can_defer_affine', False):
+                # ... or a residual link that sums this block's output with a referenced tensor (`accepts_pending_with_references`)
                 kwargs['defer_affine'] = not isinstance(x, (list, tuple)) and i + 1 < len(children) and n_referrers == 0 and getattr(children[i + 1], 'accepts_pending_affine', False) \
-                    and not getattr(children[i + 1], 'referenced_submodules', None)
+                    and (not getattr(children[i + 1], 'referenced_submodules', None) or getattr(children[i + 1], 'accepts_pending_with_references', False))
             if getattr(subm, 'can_defer_flatten', False):   # Flatten in front of a small fully connected head: fused into the head's kernels
                 kwargs['defer_flatten'] = not isinstance(x, (list, tuple)) and i + 1 < len(children) and n_referrers == 0 \
                     and bool(getattr(children[i + 1], 'accepts_pending_flatten', False)) and not getattr(children[i + 1], 'referenced_submodules', None)

@@ -33,7 +33,7 @@ XAVIER_INIT_SUPPORTED_ACT_FN = {torch.nn.ReLU: 'relu', torch.nn.LeakyReLU: 'leak
 def is_torch_obj(v) -> bool:
     """ reference nn.py:706-709 as intended (the `'_module__'` typo made it always False): a single tensor, not a sequence of
     tensors. A raw block output with a pending normalisation (`ops.PendingAffine`) counts as one tensor. """
-    return isinstance(v, (torch.Tensor, torch.Size, ops.PendingAffine, ops.PendingFlatten))
+    return isinstance(v, (torch.Tensor, torch.Size, ops.PendingAffine, ops.PendingNorm, ops.PendingFlatten))
 
 
 def forward_call_convention_dec(apply_parallel_forward: bool = False, refs_tensor_count_similar: bool = None, in_tensors_count_similar_to_refs: bool = None,
@@ -223,7 +223,7 @@ class AvgPool2d(torch.nn.AvgPool2d):
             x = ops.materialize(x)
         if x.device.type == 'meta':
             return meta_like((x.shape[0], x.shape[1], (x.shape[2] - k[0]) // s[0] + 1, (x.shape[3] - k[1]) // s[1] + 1), x.dtype)
-        return ops.avg_pool2d(x, k, s)
+        return ops.avg_pool2d(x, k, s)   # a `PendingNorm` (tensor-core block output) with 2x2 / stride-2 windows: normalise + pool in one pass
 
 
 class Flatten(torch.nn.Flatten):
@@ -334,7 +334,7 @@ class FusedLayer(torch.nn.Sequential):
 
     @forward_call_convention_dec(apply_parallel_forward=True, ignore_sub_refs=True)   # reference submodule_creators.py:254: one layer shared by parallel branches
     def forward(self, x, defer_affine: bool = False):
-        if not isinstance(x, ops.PendingAffine) and x.device.type == 'meta':
+        if not isinstance(x, (ops.PendingAffine, ops.PendingNorm)) and x.device.type == 'meta':
             return self._meta_forward(x)
         op, bn, gn, drop = self._op, self._bn, self._gn, self._drop
         if isinstance(x, ops.PendingFlatten) and not self.accepts_pending_flatten:
@@ -360,6 +360,8 @@ class FusedLayer(torch.nn.Sequential):
                 x = ops.activation(ops.as_nhwc(x), self._act, self._slope)
             return ops.conv_block(x, op.weight, op.bias, op.stride, op.padding, op.dilation, ACT_NONE, 0., norm=None, training=training, algo=self.algo,
                                   grad_out=self._grad_out, step_ctx=self._step_ctx, notify=not has_norm)
+        if isinstance(x, ops.PendingNorm):
+            x = ops.materialize(x)
         few = self._few_channel_path(x)
         if isinstance(x, ops.PendingAffine) and not few:
             x = ops.materialize(x)
@@ -370,7 +372,7 @@ class FusedLayer(torch.nn.Sequential):
                                     grad_out=self._grad_out, step_ctx=self._step_ctx, **self._norm_kwargs())
             return out if defer_affine else ops.materialize(out)
         return ops.conv_block(x, op.weight, op.bias, op.stride, op.padding, op.dilation, self._act, self._slope, norm=self._norm_config(), training=training,
-                              algo=self.algo, grad_out=self._grad_out, step_ctx=self._step_ctx, **self._norm_kwargs())
+                              algo=self.algo, grad_out=self._grad_out, step_ctx=self._step_ctx, defer_apply=defer_affine, **self._norm_kwargs())
 
 
 def layer(layer_op: torch.nn.Module, act_fn: Optional[Type[torch.nn.Module]], dropout_prob: float = None, preactivation: bool = False,

@@ -222,7 +222,9 @@ def add_residual_dense_link_creator(is_residual: bool, creator_name: str, submod
 
         @deepcv_nn.forward_call_convention_dec(apply_parallel_forward=apply_in_parallel, in_tensors_count_similar_to_refs=apply_in_parallel)   # reference :300
         def _forward_callback(x, referenced_submodules_out: List[torch.Tensor]):
-            out = [x] if isinstance(x, torch.Tensor) else list(x)
+            if isinstance(x, ops.PendingAffine) or (isinstance(x, ops.PendingNorm) and reduction != 'sum'):
+                x = ops.materialize(x)
+            out = [x] if deepcv_nn.is_torch_obj(x) else [ops.materialize(t) for t in x]
             linked = [y for refs in referenced_submodules_out for y in ([refs] if isinstance(refs, torch.Tensor) else list(refs))]
             if reduction == 'concat' and allow_scaling and channel_dim == 1 and not scaling_align_corners and scaling_mode in (None, 'bilinear'):
                 fused = ops.link_concat_rescaled(out + linked)   # same-size and exactly-2x references: rescale + concat in one launch
@@ -237,7 +239,11 @@ def add_residual_dense_link_creator(is_residual: bool, creator_name: str, submod
                     y = deepcv_nn.interpolate(y, out[0].shape[channel_dim + 1:], scaling_mode=scaling_mode, align_corners=scaling_align_corners)
                 out.append(y)
             return reduce(out)
-        return ForwardCallbackSubmodule(_forward_callback)
+        subm = ForwardCallbackSubmodule(_forward_callback)
+        # a block's raw output with its normalisation pending (`ops.PendingNorm`) may be this link's first operand: a 'sum' adds the referenced tensor inside
+        # the block's apply pass (ops.link_reduce); anything else materialises it first
+        subm.accepts_pending_affine = subm.accepts_pending_with_references = True
+        return subm
 
     _link_creator.__doc__ = add_residual_dense_link_creator.__doc__
     return _link_creator

@@ -20,7 +20,7 @@ from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, A
 
 __all__ = ['empty_nhwc', 'is_nhwc', 'as_nhwc', 'activation_code', 'conv_block', 'NormConfig', 'avg_pool2d', 'link_reduce', 'link_concat_rescaled', 'bilinear_resize', 'flatten_nchw',
            'linear_act', 'cross_entropy', 'preprocess_u8', 'fork', 'launch_count', 'AccumulatorArena', 'StepContext', 'PendingAffine', 'sc_conv_block',
-           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act', 'PendingFlatten', 'unit_grad']
+           'sc_conv_supported', 'sc_affine_pool', 'materialize', 'DropoutState', 'dropout', 'activation', 'pre_norm_act', 'PendingFlatten', 'unit_grad', 'PendingNorm', 'apply_pending']
 
 _DTYPES = {torch.float32: DCV_F32, torch.bfloat16: DCV_BF16}
 _DEBUG_CAPTURE = None   # tests may set this to a list to capture backward intermediates of conv blocks
@@ -290,6 +290,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 # (64-channel halo kernel 77 -> 90 us with per-thread partial sums, 128 / 256-channel kernels 60 -> 90 us with a per-tile butterfly, stem 402 -> 594 us).
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
+_LAZY_APPLY = os.environ.get('DCV_NO_LAZY_APPLY') is None   # tuning aid: DCV_NO_LAZY_APPLY=1 always runs the stand-alone normalisation apply pass
 _USE_PAIRS = os.environ.get('DCV_NO_PAIRS') is None     # tuning aid: DCV_NO_PAIRS=1 sends stride-2 few-channel layers to the gather kernels instead of the pixel-pair ones
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
 
@@ -334,7 +335,7 @@ def _norm_params(cfg: NormConfig, n: int, c: int, hw: int, training: bool, bn_w,
 
 class _ConvBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx, notify=True):
+    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx, notify=True, defer_apply=False):
         _require_cuda(x, weight)
         ctx.notify = notify
         shape = _conv_shape(x, weight, stride, padding, dilation)
@@ -393,16 +394,22 @@ class _ConvBlock(torch.autograd.Function):
             ab = torch.empty((n, k, 2), dtype=torch.float32, device=dev)
             prm = _norm_params(cfg, n, k, p * q, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
             check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(ab), _ptr(saved), st), 'norm_fwd_finalize')
-            out = empty_nhwc(n, k, p, q, x.dtype, dev)
-            check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, p * q, k, dt, st), 'norm_apply_fwd')
+            if not defer_apply:
+                out = empty_nhwc(n, k, p, q, x.dtype, dev)
+                check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, p * q, k, dt, st), 'norm_apply_fwd')
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
         # the fp32 master weight, when it already is [K][R][S][C] in memory: the data-gradient operand is packed straight from it in backward
         ctx.w_master = weight.detach() if (weight.dtype == torch.float32 and weight.permute(0, 2, 3, 1).is_contiguous()) else None
         ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape, gathered, sctx)
+        if defer_apply and cfg.any:
+            # the RAW output goes on with its coefficients (`PendingNorm`): the consumer applies z = A*y + B inside its own pass (`_ApplyNorm*`) and hands
+            # back dz — the gradient w.r.t. the normalised output, exactly what this backward expects — as the "gradient" of y
+            ctx.mark_non_differentiable(ab)
+            return y, ab
         return out
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, _dab=None):
         x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv = ctx.saved_tensors
         shape, act, slope, cfg, training, algo, has_bias, grad_out, wshape, gemm_shape, gathered, sctx = ctx.cfg
         pz = _pz(sctx)
@@ -483,7 +490,7 @@ class _ConvBlock(torch.autograd.Function):
         if ctx.notify:
             _backward_done(grad_out, targets)
         return (dx, ret('weight', dw), ret('bias', dbias) if has_bias else None, ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b),
-                None, None, None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def _backward_done(grad_out: Optional[dict], targets: dict) -> None:
@@ -502,15 +509,80 @@ def _backward_done(grad_out: Optional[dict], targets: dict) -> None:
 def conv_block(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: Sequence[int], padding: Sequence[int], dilation: Sequence[int],
                act: int = ACT_NONE, slope: float = 0., norm: Optional[NormConfig] = None, training: bool = True,
                bn_weight=None, bn_bias=None, running_mean=None, running_var=None, num_batches_tracked=None, gn_weight=None, gn_bias=None,
-               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None, notify: bool = True) -> torch.Tensor:
+               algo: int = ALGO_AUTO, grad_out: Optional[dict] = None, step_ctx: Optional[StepContext] = None, notify: bool = True, defer_apply: bool = False):
     """ act(conv2d(x, weight) + bias) followed by the configured BatchNorm / GroupNorm, as one autograd node.
     `grad_out` optionally maps 'weight' / 'bias' / 'bn_w' / 'bn_b' / 'gn_w' / 'gn_b' to preallocated fp32 tensors (slices of a
     flat gradient bucket) that backward fills in place instead of returning new tensors. `notify=False`: another node of the same layer (the
-    normalisation of a pre-activation block, whose backward runs later) closes the layer's backward (`_backward_done`). """
+    normalisation of a pre-activation block, whose backward runs later) closes the layer's backward (`_backward_done`).
+    `defer_apply=True` (the caller promises ONE consumer that takes a `PendingNorm`: a 2x2 average pooling, a residual sum, or `materialize`): a block
+    with a normalisation returns its raw output and coefficients instead of running the apply pass. """
     x = as_nhwc(x)
     norm = norm if norm is not None else NormConfig()
-    return _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
-                            tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx, bool(notify))
+    defer_apply = bool(defer_apply and norm.any and _LAZY_APPLY)
+    out = _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
+                           tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx, bool(notify), defer_apply)
+    return PendingNorm(*out) if defer_apply else out
+
+
+class PendingNorm:
+    """ A tensor-core block's RAW output `y` (conv + bias + activation) and its normalisation coefficients `ab[n][c] = (A, B)`: the one consumer computes
+    z = A*y + B inside its own pass — `materialize` (the plain apply pass), a 2x2 / stride-2 average pooling (`avg_pool2d`), a residual sum
+    (`link_reduce`). The gradient a consumer returns for `y` is dz, the gradient w.r.t. z: the block's backward turns it into the gradient of y.
+    Only the modules of this package ever see one (`DeepcvModule.forward` decides who may). """
+    __slots__ = ('y', 'ab', 'consumed')
+
+    def __init__(self, y: torch.Tensor, ab: torch.Tensor):
+        self.y, self.ab, self.consumed = y, ab, False
+
+    shape = property(lambda self: self.y.shape)
+    dtype = property(lambda self: self.y.dtype)
+    device = property(lambda self: self.y.device)
+
+    def dim(self) -> int:
+        return self.y.dim()
+
+    def take(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.consumed:
+            raise RuntimeError('deepcv_b200: a pending normalisation was consumed twice (materialize() it before using the tensor in two places)')
+        self.consumed = True
+        return self.y, self.ab
+
+
+class _ApplyNorm(torch.autograd.Function):
+    """ z = A*y + B [+ other] [then 2x2 / stride-2 average pooling] of a `PendingNorm`. Backward hands dz to the producing block (see `PendingNorm`). """
+
+    @staticmethod
+    def forward(ctx, y, ab, other, pool: bool):
+        n, c, h, w = y.shape
+        ctx.geom, ctx.pool, ctx.has_other = (n, c, h, w), pool, other is not None
+        st, dt = _stream(), _dt(y)
+        if pool:
+            out = empty_nhwc(n, c, h // 2, w // 2, y.dtype, y.device)
+            check(lib.dcv_norm_apply_pool_fwd(_ptr(y), _ptr(ab), _ptr(out), n, h, w, c, dt, st), 'norm_apply_pool_fwd')
+        elif other is not None:
+            out = empty_nhwc(n, c, h, w, y.dtype, y.device)
+            check(lib.dcv_norm_apply_add_fwd(_ptr(y), _ptr(ab), _ptr(other), _ptr(out), n, h * w, c, dt, st), 'norm_apply_add_fwd')
+        else:
+            out = empty_nhwc(n, c, h, w, y.dtype, y.device)
+            check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, h * w, c, dt, st), 'norm_apply_fwd')
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w = ctx.geom
+        if ctx.pool:
+            g = as_nhwc(g.detach())
+            dz = empty_nhwc(n, c, h, w, g.dtype, g.device)
+            check(lib.dcv_avgpool2d_bwd(_ptr(g), _ptr(dz), n, h, w, c, 2, 2, 2, 2, _dt(g), _stream()), 'avgpool2d_bwd')
+            return dz, None, None, None
+        return g, None, (g if ctx.has_other else None), None
+
+
+def apply_pending(pn: PendingNorm, other: Optional[torch.Tensor] = None, pool: bool = False) -> torch.Tensor:
+    y, ab = pn.take()
+    if other is not None:
+        other = as_nhwc(other, y.dtype)
+    return _ApplyNorm.apply(y, ab, other, bool(pool))
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -870,9 +942,11 @@ class PendingFlatten:
 
 
 def materialize(x):
-    """ `PendingAffine` -> the normalised tensor; `PendingFlatten` -> the flattened (N, C*H*W) tensor; tensors pass through. """
+    """ `PendingAffine` / `PendingNorm` -> the normalised tensor; `PendingFlatten` -> the flattened (N, C*H*W) tensor; tensors pass through. """
     if isinstance(x, PendingAffine):
         return sc_affine_pool(x, 1)
+    if isinstance(x, PendingNorm):
+        return apply_pending(x)
     if isinstance(x, PendingFlatten):
         return flatten_nchw(x.x)
     return x
@@ -906,6 +980,10 @@ class _AvgPool(torch.autograd.Function):
 def avg_pool2d(x: torch.Tensor, kernel_size, stride=None) -> torch.Tensor:
     kernel = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
     stride = kernel if stride is None else ((stride, stride) if isinstance(stride, int) else tuple(stride))
+    if isinstance(x, PendingNorm):
+        if kernel == (2, 2) and stride == (2, 2) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            return apply_pending(x, pool=True)   # the normalised full-resolution tensor is never written
+        x = materialize(x)
     return _AvgPool.apply(as_nhwc(x), kernel, stride)
 
 
@@ -1019,7 +1097,11 @@ def link_concat_rescaled(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
 def link_reduce(tensors: List[torch.Tensor], reduction: str) -> torch.Tensor:
     """ 'sum' / 'mean' (elementwise over the list) or 'concat' (channel dim, first tensor first). """
     if len(tensors) == 1 and reduction in ('sum', 'mean', 'concat'):
-        return tensors[0]
+        return materialize(tensors[0])
+    if isinstance(tensors[0], PendingNorm):   # a residual link right behind a block: the sum rides in the block's apply pass
+        if reduction == 'sum' and len(tensors) == 2 and tuple(tensors[1].shape) == tuple(tensors[0].shape) and tensors[1].dtype == tensors[0].dtype:
+            return apply_pending(tensors[0], other=tensors[1])
+        tensors = [materialize(tensors[0])] + list(tensors[1:])
     dtype = tensors[0].dtype
     tensors = [as_nhwc(t, dtype) for t in tensors]
     if reduction == 'concat':

@@ -221,6 +221,13 @@ size_t dcv_norm_saved_floats(int n, int c, int groups);
 int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, float* ab_nc, float* saved, void* stream);
 /* z = A*y + B. */
 int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw, int c, int dtype, void* stream);
+/* The same pass fused with what follows the block in the architecture (meta/base_module.py decides):
+ *   _add:  z = A*y + B + other — a `residual_link` (reduction 'sum', reference meta/submodule_creators.py:272-332) whose first operand is the block output;
+ *   _pool: zp[n][h/2][w/2][c] = A*avgpool2x2(y) + B — an `avg_pooling` with kernel = stride = 2 (reference :163-176); the full-resolution normalised
+ *          tensor is never written. Backward of both needs no kernel of its own: d/dy is what the block's backward already computes from dz
+ *          (dz = the link's incoming gradient; dz = dcv_avgpool2d_bwd of the pooled gradient). */
+int dcv_norm_apply_add_fwd(const void* y, const float* ab_nc, const void* other, void* z, int n, int hw, int c, int dtype, void* stream);
+int dcv_norm_apply_pool_fwd(const void* y, const float* ab_nc, void* zp, int n, int h, int w, int c, int dtype, void* stream);
 /* s_nc[n][c][2] = { sum(dz), sum(dz*y) } (overwritten). */
 int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, int acc_prezeroed, void* stream);
 /* -> pqr_nc[n][c][3] with dy_pre_activation = P*dz + Q*y + R, plus parameter gradients (any may be NULL; overwritten).

@@ -225,3 +225,39 @@ def test_dense_link_concat_in_one_launch(dev, n, h, w, channels, pools, needs, d
             continue
         expect = (gs * 0.25).to(dtype).float().repeat_interleave(2, dim=2).repeat_interleave(2, dim=3) if p == 2 else gs
         assert torch.equal(s.grad.float(), expect)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('n,h,w,c', [(3, 8, 12, 64), (2, 6, 4, 24), (5, 2, 2, 3), (2, 56, 56, 64)])
+def test_norm_apply_fused_with_residual_sum_and_pooling(dev, n, h, w, c, dtype):
+    """ dcv_norm_apply_add_fwd = A*y + B + other and dcv_norm_apply_pool_fwd = A*avgpool2x2(y) + B against the same arithmetic in fp64 (one rounding to the
+    storage type at the end: 2^-8 relative for bf16, 1e-6 for fp32), and `ops.apply_pending` backward = the gradient w.r.t. the normalised tensor. """
+    from deepcv_b200 import ops
+    from deepcv_b200._lib import DCV_BF16, DCV_F32, check, lib
+    torch.manual_seed(n * 100 + c)
+    dt = DCV_BF16 if dtype == torch.bfloat16 else DCV_F32
+    y = torch.randn(n, h, w, c, device=dev).to(dtype)
+    other = torch.randn(n, h, w, c, device=dev).to(dtype)
+    ab = torch.randn(n, c, 2, device=dev)
+    A, B = ab[..., 0].double()[:, None, None, :], ab[..., 1].double()[:, None, None, :]
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 1e-6
+    out = torch.full_like(y, 7.)
+    check(lib.dcv_norm_apply_add_fwd(P(y), P(ab), P(other), P(out), n, h * w, c, dt, stream()), 'norm_apply_add_fwd')
+    want = A * y.double() + B + other.double()
+    assert float(((out.double() - want).abs() / (want.abs() + 1.)).max()) <= tol
+    outp = torch.full((n, h // 2, w // 2, c), 7., device=dev, dtype=dtype)
+    check(lib.dcv_norm_apply_pool_fwd(P(y), P(ab), P(outp), n, h, w, c, dt, stream()), 'norm_apply_pool_fwd')
+    wantp = F.avg_pool2d((A * y.double() + B).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert float(((outp.double() - wantp).abs() / (wantp.abs() + 1.)).max()) <= tol
+    # autograd contract of a pending normalisation: the consumer returns dz (gradient w.r.t. A*y + B) in the slot of y
+    yl = y.permute(0, 3, 1, 2).requires_grad_(True)
+    ol = other.permute(0, 3, 1, 2).requires_grad_(True)
+    z = ops.apply_pending(ops.PendingNorm(yl, ab), other=ol)
+    g = torch.randn_like(z)
+    z.backward(g)
+    assert torch.equal(yl.grad, g) and torch.equal(ol.grad, g)
+    yl.grad = None
+    zp = ops.apply_pending(ops.PendingNorm(yl, ab), pool=True)
+    gp = torch.randn_like(zp)
+    zp.backward(gp)
+    assert torch.equal(yl.grad.float(), (gp.float() * 0.25).to(dtype).float().repeat_interleave(2, dim=2).repeat_interleave(2, dim=3))
