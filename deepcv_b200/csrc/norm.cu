@@ -258,8 +258,16 @@ __global__ void __launch_bounds__(256) apply_pool_fwd_kernel(const T* __restrict
 // apply pass would need no reduction. Measured on B200: the reduce went from 42.7 to 60.5 us on the 64-channel 56x56 tensor — 40 accumulators per thread,
 // ALU-bound — while the apply only gained 65.2 -> 62.6 us.)
 constexpr int kBwdSums = 2;
-template <typename T, int VE>
-__global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y, float* __restrict__ s, const NcGeom g) {
+// POOL (both backward kernels): `dz` is the gradient of the 2x2 / stride-2 average pooling that consumed the normalised tensor, at POOLED resolution; the
+// gradient of pixel p is a quarter of the pooled pixel's (exact in bf16: the value the stand-alone pooling backward would have stored), read in place —
+// the full-resolution dz is never written. p counts pixels over whole rows of width w (h even: image boundaries fall on even rows).
+__device__ __forceinline__ uint32_t pooled_pixel(uint32_t p, const FastDiv& div_w, uint32_t w) {
+  const uint32_t r = div_w.div(p), x = p - r * w;
+  return (r >> 1) * (w >> 1) + (x >> 1);
+}
+
+template <typename T, int VE, bool POOL = false>
+__global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y, float* __restrict__ s, const NcGeom g, const FastDiv div_w = FastDiv(), uint32_t w = 0) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
   for_each_segment(g, [&](int img, int p0, int p1) {
@@ -267,19 +275,24 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
 #pragma unroll
     for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
     if (colg < g.cv) {
-      const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
+      const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE, pbase = ((size_t)img * (g.hwv >> 2)) * g.span + (size_t)colg * VE;
       for (int p = p0 + row; p < p1; p += UNR * g.rows) {
         Raw<T, VE> ra[UNR], rb[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const bool on = p + u * g.rows < p1;
-          ra[u] = on ? load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+          if constexpr (POOL) ra[u] = on ? load_raw<T, VE>(dz + pbase + (size_t)pooled_pixel((uint32_t)(p + u * g.rows), div_w, w) * g.span) : zero_raw<T, VE>();
+          else ra[u] = on ? load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
           rb[u] = on ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           float a[VE], b[VE];
           unpack_raw<T, VE>(ra[u], a); unpack_raw<T, VE>(rb[u], b);
+          if constexpr (POOL) {
+#pragma unroll
+            for (int e = 0; e < VE; ++e) a[e] *= 0.25f;
+          }
 #pragma unroll
           for (int e = 0; e < VE; ++e) { acc[0][e] += a[e]; acc[1][e] = fmaf(a[e], b[e], acc[1][e]); }
         }
@@ -297,9 +310,9 @@ template <int ACT> __device__ __forceinline__ float act_grad_t(float y, float sl
   return 1.f;
 }
 
-template <typename T, int VE, int ACT>
+template <typename T, int VE, int ACT, bool POOL = false>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ pqr,
-                                                        T* __restrict__ dy, float* __restrict__ dbias, float slope, const NcGeom g) {
+                                                        T* __restrict__ dy, float* __restrict__ dbias, float slope, const NcGeom g, const FastDiv div_w = FastDiv(), uint32_t w = 0) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
   float acc[1][VE];   // bias-gradient partial sums, kept over all the CTA's images
@@ -318,10 +331,11 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz
 #pragma unroll
         for (int e = 0; e < VE; ++e) { P[e] = 1.f; Q[e] = 0.f; R[e] = 0.f; }
       }
-      const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
+      const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE, pbase = ((size_t)img * (g.hwv >> 2)) * g.span + (size_t)colg * VE;
       auto one = [&](float* a, const float* b, size_t off) {
 #pragma unroll
         for (int e = 0; e < VE; ++e) {
+          if constexpr (POOL) a[e] *= 0.25f;
           const float pre = fmaf(P[e], a[e], fmaf(Q[e], b[e], R[e]));
           a[e] = pre * act_grad_t<ACT>(b[e], slope);
           acc[0][e] += a[e];
@@ -333,7 +347,8 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const bool on = p + u * g.rows < p1;
-          ra[u] = on ? load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
+          if constexpr (POOL) ra[u] = on ? load_raw<T, VE>(dz + pbase + (size_t)pooled_pixel((uint32_t)(p + u * g.rows), div_w, w) * g.span) : zero_raw<T, VE>();
+          else ra[u] = on ? load_raw<T, VE>(dz + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
           rb[u] = on ? load_raw<T, VE>(y + base + (size_t)(p + u * g.rows) * g.span) : zero_raw<T, VE>();
         }
 #pragma unroll
@@ -765,6 +780,31 @@ int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int h
   return 0;
 }
 
+int dcv_norm_bwd_pooled_supported(int n, int h, int w, int c, int dtype) {
+  const int ve = dtype == DCV_BF16 ? 8 : 4;
+  return (dtype == DCV_BF16 || dtype == DCV_F32) && n > 0 && c > 0 && c % ve == 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && (long long)n * h * w < (1ll << 31);
+}
+
+int dcv_norm_bwd_reduce_pooled(const void* dzp, const void* y, float* s_nc, int n, int h, int w, int c, int dtype, int acc_prezeroed, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dzp && y && s_nc, "norm_bwd_reduce_pooled: null pointer");
+  DCV_REQUIRE(dcv_norm_bwd_pooled_supported(n, h, w, c, dtype), "norm_bwd_reduce_pooled: shape not supported (see dcv_norm_bwd_pooled_supported)");
+  cudaStream_t st = as_stream(stream);
+  zero_accumulator(s_nc, (size_t)n * c * kBwdSums * sizeof(float), st, (acc_prezeroed & DCV_ACC_PREZEROED) != 0);
+  int hw = h * w;
+  if (acc_prezeroed & DCV_STATS_CHANNEL_TOTALS) { hw *= n; n = 1; }
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    DCV_REQUIRE(vec_ok(dzp, y, nullptr, n, hw, c, VE), "norm_bwd_reduce_pooled: pointers must be 16-byte aligned");
+    static const int occ = streaming_ctas_per_sm((const void*)bwd_reduce_kernel<T, VE, true>);
+    NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block);
+    bwd_reduce_kernel<T, VE, true><<<grid, block, 0, st>>>((const T*)dzp, (const T*)y, s_nc, g, FastDiv((uint32_t)w), (uint32_t)w);
+  });
+  DCV_LAUNCH_CHECK("bwd_reduce_kernel(pooled)");
+  return 0;
+}
+
 int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, const float* s_nc, float* saved, float* pqr_nc,
                           float* d_bn_weight, float* d_bn_bias, float* d_gn_weight, float* d_gn_bias, void* stream) {
   using namespace dcv;
@@ -799,6 +839,34 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
   }
 #undef DCV_BWD_APPLY
   DCV_LAUNCH_CHECK("bwd_apply_kernel");
+  return 0;
+}
+
+int dcv_act_norm_bwd_apply_pooled(const void* dzp, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
+                                  int n, int h, int w, int c, int dtype, int acc_prezeroed, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dzp && y && dy, "act_norm_bwd_apply_pooled: null pointer");
+  DCV_REQUIRE(dcv_norm_bwd_pooled_supported(n, h, w, c, dtype), "act_norm_bwd_apply_pooled: shape not supported (see dcv_norm_bwd_pooled_supported)");
+  cudaStream_t st = as_stream(stream);
+  zero_accumulator(dbias_c, (size_t)c * sizeof(float), st, acc_prezeroed != 0);
+  const int hw = h * w;
+  dim3 grid; int block;
+#define DCV_BWD_APPLY_POOLED(ACT_)                                                                                                                            \
+  DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                              \
+    constexpr int VE = 16 / sizeof(T);                                                                                                                        \
+    DCV_REQUIRE(vec_ok(dzp, y, dy, n, hw, c, VE), "act_norm_bwd_apply_pooled: pointers must be 16-byte aligned");                                             \
+    static const int occ = streaming_ctas_per_sm((const void*)bwd_apply_kernel<T, VE, ACT_, true>);                                                          \
+    NcGeom g = make_geom<VE>(n, hw, c, occ, &grid, &block, dbias_c ? 8 : 2);                                                                                  \
+    bwd_apply_kernel<T, VE, ACT_, true><<<grid, block, 0, st>>>((const T*)dzp, (const T*)y, pqr_nc, (T*)dy, dbias_c, slope, g, FastDiv((uint32_t)w), (uint32_t)w); \
+  })
+  switch (act) {
+    case DCV_ACT_RELU: DCV_BWD_APPLY_POOLED(DCV_ACT_RELU); break;
+    case DCV_ACT_LEAKY_RELU: DCV_BWD_APPLY_POOLED(DCV_ACT_LEAKY_RELU); break;
+    case DCV_ACT_SIGMOID: DCV_BWD_APPLY_POOLED(DCV_ACT_SIGMOID); break;
+    default: DCV_BWD_APPLY_POOLED(DCV_ACT_NONE); break;
+  }
+#undef DCV_BWD_APPLY_POOLED
+  DCV_LAUNCH_CHECK("bwd_apply_kernel(pooled)");
   return 0;
 }
 

@@ -322,6 +322,7 @@ class GradientBucketReducer:
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.is_cuda = flat.flat_grads.is_cuda
         self.comm_stream = torch.cuda.Stream(device=flat.flat_grads.device) if self.is_cuda else None
+        self.side_streams: List[torch.cuda.Stream] = []
         self.average_in_finish = True
         self.peer: Optional[PeerAllReduce] = None   # set by DataParallelModel: small buckets then go through the one-shot peer-memory kernel
         foreign = {flat.bucket_of[id(p)] for p in flat.foreign_params}
@@ -365,6 +366,8 @@ class GradientBucketReducer:
         chunk = self.flat.flat_grads[start:end]
         if self.is_cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            for side in self.side_streams:   # weight-gradient kernels of other layers of the bucket may still be running there (ops.StepContext.side_stream)
+                self.comm_stream.wait_stream(side)
             with torch.cuda.stream(self.comm_stream):
                 if self.peer is not None and self.peer.serves(start, end, b):
                     self.peer.all_reduce(start, end, b)      # one kernel over NVLink peer memory (small buckets: latency)

@@ -388,6 +388,13 @@ class GraphedTrainStep:
         self.use_arena = use_accumulator_arena and os.environ.get('DCV_NO_ARENA') is None
         self.ctx = ops.StepContext(ops.AccumulatorArena() if self.use_arena else None)   # owned by this object: the graph replays write into its buffers
         self.arena = self.ctx.arena
+        # the weight-gradient kernels of the tensor-core convolutions run on a second stream, concurrently with the HBM-bound normalisation backward of the
+        # layer before (ops._ConvBlock.backward); only with the flat gradient buffer (gradients written in place, nothing handed back to autograd)
+        if self.flat is not None and os.environ.get('DCV_SIDE_WGRAD') == '1':   # opt-in (see ops._SIDE_WGRAD)
+            self.ctx.side_stream = torch.cuda.Stream(device=example_x.device)
+            reducer = getattr(model, 'reducer', None)
+            if reducer is not None:
+                reducer.side_streams = [self.ctx.side_stream]
         # one bf16 cast of the flat parameter buffer per step instead of one per convolution; bf16 steps only
         op_dtype = getattr(preprocess, 'dtype', None) if preprocess is not None else (example_x.dtype if example_x.is_floating_point() else None)
         self._shadow = None
@@ -480,6 +487,7 @@ class GraphedTrainStep:
         loss = self.static_loss = self.static_losses[MAIN_TRAINING_LOSS_NAME]
         self.optimizer.zero_grad()
         torch.autograd.backward(loss, grad_tensors=[ops.unit_grad(loss.device)])   # = loss.backward() without the ones_like fill kernel / the multiplication by one
+        self.ctx.join_side()
         if isinstance(self.model, DataParallelModel):
             self.model.finish_gradient_reduction()
         self.optimizer.step(refresh_lr=False)

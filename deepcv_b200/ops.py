@@ -10,6 +10,7 @@ Conventions
   * No CPU implementation exists: a non-CUDA tensor raises `RuntimeError` (tensors on the `meta` device are handled by the
     modules in `deepcv_b200.meta.nn`, for shape inference only).
 """
+import contextlib
 import ctypes
 import os
 from typing import List, Optional, Sequence, Tuple
@@ -210,6 +211,14 @@ class StepContext:
         self.arena = arena
         self.shadows: List[Tuple[torch.Tensor, torch.Tensor]] = []   # (flat fp32 parameter buffer, same-length buffer of the operand dtype)
         self.transposed = None   # see `plan_transposed_weights`
+        self.side_stream: Optional[torch.cuda.Stream] = None   # weight-gradient kernels run here, concurrently with the rest of backward (`_ConvBlock.backward`)
+        self.keep_alive: list = []
+
+    def join_side(self) -> None:
+        """ End of backward: the compute stream waits for the weight-gradient kernels on the side stream; the tensors they used may be released. """
+        if self.side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+        self.keep_alive.clear()
 
     @property
     def prezeroed(self) -> int:
@@ -290,6 +299,8 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 # (64-channel halo kernel 77 -> 90 us with per-thread partial sums, 128 / 256-channel kernels 60 -> 90 us with a per-tile butterfly, stem 402 -> 594 us).
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
+_SIDE_WGRAD = os.environ.get('DCV_SIDE_WGRAD') == '1'   # opt-in: weight-gradient kernels on a second stream (measured: 6.377 -> 6.323 ms on the ImageNet-shaped step — they compete with the normalisation passes for HBM — not worth a second stream inside the captured step by default)
+_POOLED_BWD = os.environ.get('DCV_NO_POOLED_BWD') is None   # tuning aid: DCV_NO_POOLED_BWD=1 materialises the full-resolution gradient behind a fused normalise + pool
 _LAZY_APPLY = os.environ.get('DCV_NO_LAZY_APPLY') is None   # tuning aid: DCV_NO_LAZY_APPLY=1 always runs the stand-alone normalisation apply pass
 _USE_PAIRS = os.environ.get('DCV_NO_PAIRS') is None     # tuning aid: DCV_NO_PAIRS=1 sends stride-2 few-channel layers to the gather kernels instead of the pixel-pair ones
 _USE_GATHER = os.environ.get('DCV_NO_GATHER') is None   # tuning aid: DCV_NO_GATHER=1 forces the explicit im2col route for the stem
@@ -335,9 +346,10 @@ def _norm_params(cfg: NormConfig, n: int, c: int, hw: int, training: bool, bn_w,
 
 class _ConvBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx, notify=True, defer_apply=False):
+    def forward(ctx, x, weight, bias, bn_w, bn_b, gn_w, gn_b, rm, rv, nbt, stride, padding, dilation, act, slope, cfg: NormConfig, training: bool, algo: int, grad_out, sctx, notify=True, defer_apply=False, link=None):
         _require_cuda(x, weight)
         ctx.notify = notify
+        ctx.link = link   # side channel from the consumer of a pending normalisation (see `_ApplyNorm.backward`)
         shape = _conv_shape(x, weight, stride, padding, dilation)
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st = x.device, _stream()
@@ -415,7 +427,11 @@ class _ConvBlock(torch.autograd.Function):
         pz = _pz(sctx)
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st, dt = y.device, _stream(), _dt(y)
-        dz = as_nhwc(dz.detach(), y.dtype)
+        # a 2x2 pooling consumed the pending normalisation: its gradient arrives at POOLED resolution through the side channel (the `dz` argument is a
+        # placeholder of the right shape) and the two normalisation passes below read it in place
+        dzp = ctx.link.pop('pooled_dz', None) if ctx.link is not None else None
+        if dzp is None:
+            dz = as_nhwc(dz.detach(), y.dtype)
         f32 = dict(dtype=torch.float32, device=dev)
         # gradients go straight into the caller's bucket slices on the FIRST backward after `zero_grad`; a second backward through the same layer before the
         # next `zero_grad` (weights shared between two calls, gradient accumulation) returns tensors instead, which autograd accumulates into `.grad`
@@ -424,7 +440,10 @@ class _ConvBlock(torch.autograd.Function):
         if cfg.any:
             s_nc = _acc_empty((n, k, 2), dev, sctx)
             totals = 2 if (cfg.use_bn and not cfg.use_gn and _CHANNEL_TOTALS) else 0
-            check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, pz | totals, st), 'norm_bwd_reduce')
+            if dzp is not None:
+                check(lib.dcv_norm_bwd_reduce_pooled(_ptr(dzp), _ptr(y), _ptr(s_nc), n, p, q, k, dt, pz | totals, st), 'norm_bwd_reduce_pooled')
+            else:
+                check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, pz | totals, st), 'norm_bwd_reduce')
             pqr = torch.empty((n, k, 3), **f32)
             if cfg.use_bn and bn_w is not None:
                 d_bn_w, d_bn_b = targets.get('bn_w', None), targets.get('bn_b', None)
@@ -445,32 +464,10 @@ class _ConvBlock(torch.autograd.Function):
             if has_bias:
                 dbias = targets.get('bias', None)
                 dbias = _acc_empty((k,), dev, sctx) if dbias is None else dbias
-            check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, pz, st), 'act_norm_bwd_apply')
-        dw = None
-        if ctx.needs_input_grad[1]:
-            dw = targets.get('weight', None)
-            if dw is None:
-                dw = _acc_empty((k, shape.r, shape.s, shape.c), dev, sctx).permute(0, 3, 1, 2)
-            if gathered == 2:            # x is the layer input; dw_col[K][256] in the pixel-pair K order, then back to [K][R][S][C]
-                dw_col = _acc_empty((k, 256), dev, sctx)
-                check(lib.dcv_conv2d_wgrad_pairs(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), pz, st), 'conv2d_wgrad_pairs')
-                check(lib.dcv_pairs_unpack_wgrad(_ptr(dw_col), _ptr(dw), ctypes.byref(shape), st), 'pairs_unpack_wgrad')
-            elif gathered:               # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
-                sc = shape.s * shape.c
-                kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
-                dw_col = _acc_empty((k, kpad_g), dev, sctx)
-                check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), kpad_g, pz, st), 'conv2d_wgrad_gather')
-                check(lib.dcv_gather_unpack_wgrad(_ptr(dw_col), _ptr(dw), k, shape.r, sc, kpad_g, st), 'gather_unpack_wgrad')
-            elif gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
-                dw_col = _acc_empty((k, gemm_shape.c), dev, sctx)
-                check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, pz, st), 'conv2d_wgrad(im2col)')
-                check(lib.dcv_copy_channels_out(_ptr(dw_col), _ptr(dw), k, gemm_shape.c, 0, shape.r * shape.s * shape.c, DCV_F32, st), 'copy_channels_out(dw)')
+            if dzp is not None:
+                check(lib.dcv_act_norm_bwd_apply_pooled(_ptr(dzp), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p, q, k, dt, pz, st), 'act_norm_bwd_apply_pooled')
             else:
-                ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
-                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
-                check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, pz, st), 'conv2d_wgrad')
-        if _DEBUG_CAPTURE is not None:
-            _DEBUG_CAPTURE.append(dict(wshape=wshape, dz=dz.clone(), y=y.clone(), dy=dy.clone(), pqr=None if pqr is None else pqr.clone(), saved=None if saved is None else saved.clone(), dz_ptr=dz.data_ptr(), y_ptr=y.data_ptr(), dy_ptr=dy.data_ptr(), x=x.clone(), dw=None if dw is None else dw.clone()))
+                check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, pz, st), 'act_norm_bwd_apply')
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(n, shape.c, shape.h, shape.w, y.dtype, dev)
@@ -485,12 +482,49 @@ class _ConvBlock(torch.autograd.Function):
                 check(lib.dcv_pack_conv_weight(_ptr(w32), _ptr(wt), dt, shape.k, shape.r, shape.s, shape.c, 1, st), 'pack_conv_weight')
             check(lib.dcv_conv2d_dgrad(ctypes.byref(shape), _ptr(dy), _ptr(w_op), _ptr(wt), _ptr(dx), dt, algo, st), 'conv2d_dgrad')
 
+        # The weight gradient goes LAST and, inside a step that provides a side stream (`StepContext.side_stream`), on that stream: it only feeds the optimizer,
+        # while the data gradient is on the critical path to the previous layer — whose normalisation backward (HBM-bound reduce / finalize / apply passes)
+        # then runs concurrently with this tensor-bound kernel. The step joins the side stream before it touches the gradients (`StepContext.join_side`).
+        dw = side = None
+        if ctx.needs_input_grad[1]:
+            dw = targets.get('weight', None)
+            # only a gradient written in place into the step's flat buffer (nothing handed to autograd), by the node that closes the layer's backward
+            side = sctx.side_stream if (sctx is not None and dw is not None and ctx.notify and _SIDE_WGRAD and algo != ALGO_DIRECT) else None
+            if dw is None:
+                dw = _acc_empty((k, shape.r, shape.s, shape.c), dev, sctx).permute(0, 3, 1, 2)
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+                sctx.keep_alive.append((x, dy, dw))   # read / written on the side stream: their memory must not be handed out again before the join
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                st = _stream()
+                if gathered == 2:            # x is the layer input; dw_col[K][256] in the pixel-pair K order, then back to [K][R][S][C]
+                    dw_col = _acc_empty((k, 256), dev, sctx)
+                    check(lib.dcv_conv2d_wgrad_pairs(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), pz, st), 'conv2d_wgrad_pairs')
+                    check(lib.dcv_pairs_unpack_wgrad(_ptr(dw_col), _ptr(dw), ctypes.byref(shape), st), 'pairs_unpack_wgrad')
+                elif gathered:               # x is the layer input; dw_col[K][kpad_g] in the gather kernels' K order, then back to [K][R][S][C]
+                    sc = shape.s * shape.c
+                    kpad_g = (shape.r * ((sc + 7) // 8 * 8) + 63) // 64 * 64
+                    dw_col = _acc_empty((k, kpad_g), dev, sctx)
+                    check(lib.dcv_conv2d_wgrad_gather(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw_col), kpad_g, pz, st), 'conv2d_wgrad_gather')
+                    check(lib.dcv_gather_unpack_wgrad(_ptr(dw_col), _ptr(dw), k, shape.r, sc, kpad_g, st), 'gather_unpack_wgrad')
+                elif gemm_shape is not None:   # x is the saved im2col matrix: dw_col[K][kpad] = dy^T @ col, then drop the zero padding
+                    dw_col = _acc_empty((k, gemm_shape.c), dev, sctx)
+                    check(lib.dcv_conv2d_wgrad(ctypes.byref(gemm_shape), _ptr(x), _ptr(dy), _ptr(dw_col), None, dt, algo, pz, st), 'conv2d_wgrad(im2col)')
+                    check(lib.dcv_copy_channels_out(_ptr(dw_col), _ptr(dw), k, gemm_shape.c, 0, shape.r * shape.s * shape.c, DCV_F32, st), 'copy_channels_out(dw)')
+                else:
+                    ws_bytes = int(lib.dcv_conv2d_wgrad_workspace(ctypes.byref(shape), dt, algo))
+                    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+                    check(lib.dcv_conv2d_wgrad(ctypes.byref(shape), _ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), dt, algo, pz, st), 'conv2d_wgrad')
+        st = _stream()
+        if _DEBUG_CAPTURE is not None:
+            _DEBUG_CAPTURE.append(dict(wshape=wshape, dz=dz.clone(), y=y.clone(), dy=dy.clone(), pqr=None if pqr is None else pqr.clone(), saved=None if saved is None else saved.clone(), dz_ptr=dz.data_ptr(), y_ptr=y.data_ptr(), dy_ptr=dy.data_ptr(), x=x.clone(), dw=None if dw is None else dw.clone()))
         def ret(name, g):  # gradients written straight into a caller-provided bucket slice are not handed to autograd again
             return None if (g is None or name in targets) else g
         if ctx.notify:
-            _backward_done(grad_out, targets)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):   # "enqueued on the current stream": the reducer orders its all-reduce behind it
+                _backward_done(grad_out, targets)
         return (dx, ret('weight', dw), ret('bias', dbias) if has_bias else None, ret('bn_w', d_bn_w), ret('bn_b', d_bn_b), ret('gn_w', d_gn_w), ret('gn_b', d_gn_b),
-                None, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def _backward_done(grad_out: Optional[dict], targets: dict) -> None:
@@ -519,9 +553,10 @@ def conv_block(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     x = as_nhwc(x)
     norm = norm if norm is not None else NormConfig()
     defer_apply = bool(defer_apply and norm.any and _LAZY_APPLY)
+    link = {} if defer_apply else None
     out = _ConvBlock.apply(x, weight, bias, bn_weight, bn_bias, gn_weight, gn_bias, running_mean, running_var, num_batches_tracked,
-                           tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx, bool(notify), defer_apply)
-    return PendingNorm(*out) if defer_apply else out
+                           tuple(stride), tuple(padding), tuple(dilation), int(act), float(slope), norm, bool(training), int(algo), grad_out, step_ctx, bool(notify), defer_apply, link)
+    return PendingNorm(out[0], out[1], link) if defer_apply else out
 
 
 class PendingNorm:
@@ -529,10 +564,10 @@ class PendingNorm:
     z = A*y + B inside its own pass — `materialize` (the plain apply pass), a 2x2 / stride-2 average pooling (`avg_pool2d`), a residual sum
     (`link_reduce`). The gradient a consumer returns for `y` is dz, the gradient w.r.t. z: the block's backward turns it into the gradient of y.
     Only the modules of this package ever see one (`DeepcvModule.forward` decides who may). """
-    __slots__ = ('y', 'ab', 'consumed')
+    __slots__ = ('y', 'ab', 'link', 'consumed')
 
-    def __init__(self, y: torch.Tensor, ab: torch.Tensor):
-        self.y, self.ab, self.consumed = y, ab, False
+    def __init__(self, y: torch.Tensor, ab: torch.Tensor, link: Optional[dict] = None):
+        self.y, self.ab, self.link, self.consumed = y, ab, link, False
 
     shape = property(lambda self: self.y.shape)
     dtype = property(lambda self: self.y.dtype)
@@ -548,13 +583,26 @@ class PendingNorm:
         return self.y, self.ab
 
 
+_PLACEHOLDERS = {}
+
+
+def _placeholder_grad(shape, dtype, device) -> torch.Tensor:
+    """ A tensor of the given shape that occupies one element (stride 0): what `_ApplyNorm.backward` hands to autograd in the slot of y when the real
+    gradient travels through the side channel. Never read. """
+    key = (dtype, device.type, device.index)
+    t = _PLACEHOLDERS.get(key)
+    if t is None:
+        t = _PLACEHOLDERS[key] = torch.zeros((), dtype=dtype, device=device)
+    return t.expand(tuple(shape))
+
+
 class _ApplyNorm(torch.autograd.Function):
     """ z = A*y + B [+ other] [then 2x2 / stride-2 average pooling] of a `PendingNorm`. Backward hands dz to the producing block (see `PendingNorm`). """
 
     @staticmethod
-    def forward(ctx, y, ab, other, pool: bool):
+    def forward(ctx, y, ab, other, pool: bool, link=None):
         n, c, h, w = y.shape
-        ctx.geom, ctx.pool, ctx.has_other = (n, c, h, w), pool, other is not None
+        ctx.geom, ctx.pool, ctx.has_other, ctx.link = (n, c, h, w), pool, other is not None, link
         st, dt = _stream(), _dt(y)
         if pool:
             out = empty_nhwc(n, c, h // 2, w // 2, y.dtype, y.device)
@@ -572,17 +620,20 @@ class _ApplyNorm(torch.autograd.Function):
         n, c, h, w = ctx.geom
         if ctx.pool:
             g = as_nhwc(g.detach())
+            if ctx.link is not None and _POOLED_BWD and lib.dcv_norm_bwd_pooled_supported(n, h, w, c, _dt(g)) and g.data_ptr() % 16 == 0:
+                ctx.link['pooled_dz'] = g   # the block's normalisation backward reads the pooled gradient in place (no full-resolution dz)
+                return _placeholder_grad((n, c, h, w), g.dtype, g.device), None, None, None, None
             dz = empty_nhwc(n, c, h, w, g.dtype, g.device)
             check(lib.dcv_avgpool2d_bwd(_ptr(g), _ptr(dz), n, h, w, c, 2, 2, 2, 2, _dt(g), _stream()), 'avgpool2d_bwd')
-            return dz, None, None, None
-        return g, None, (g if ctx.has_other else None), None
+            return dz, None, None, None, None
+        return g, None, (g if ctx.has_other else None), None, None
 
 
 def apply_pending(pn: PendingNorm, other: Optional[torch.Tensor] = None, pool: bool = False) -> torch.Tensor:
     y, ab = pn.take()
     if other is not None:
         other = as_nhwc(other, y.dtype)
-    return _ApplyNorm.apply(y, ab, other, bool(pool))
+    return _ApplyNorm.apply(y, ab, other, bool(pool), pn.link)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------

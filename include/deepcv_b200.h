@@ -239,6 +239,14 @@ int dcv_norm_bwd_finalize(const dcv_norm_params* prm, const float* stats_nc, con
  * from it). */
 int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
                            int n, int hw, int c, int dtype, int acc_prezeroed, void* stream);
+/* The two backward passes of a block whose normalised output went straight into a 2x2 / stride-2 average pooling (dcv_norm_apply_pool_fwd): `dzp` is the
+ * POOLED gradient [n][h/2][w/2][c]; the gradient of a pixel is a quarter of its pooled pixel's, read in place — the full-resolution dz is never
+ * written. c a whole number of 16-byte vectors, h and w even (dcv_norm_bwd_pooled_supported). Bit-identical to dcv_avgpool2d_bwd followed by the
+ * plain passes. */
+int dcv_norm_bwd_pooled_supported(int n, int h, int w, int c, int dtype);
+int dcv_norm_bwd_reduce_pooled(const void* dzp, const void* y, float* s_nc, int n, int h, int w, int c, int dtype, int acc_prezeroed, void* stream);
+int dcv_act_norm_bwd_apply_pooled(const void* dzp, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
+                                  int n, int h, int w, int c, int dtype, int acc_prezeroed, void* stream);
 
 /* ---- pooling / links (meta/submodule_creators.py:163-176, 272-332; meta/nn.py:416, 665-676) --------------------- */
 /* AvgPool2d(kernel, stride), no padding, floor output size. */

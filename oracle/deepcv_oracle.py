@@ -416,7 +416,9 @@ def _few_channel_block(op, x_shape) -> bool:
 def emulate_bf16_storage(model: torch.nn.Module) -> torch.nn.Module:
     """ Patches (in place) the forward of every block of an `OracleDeepcvModule` so that it rounds tensors where the device path stores bf16.
     A few-channel block directly followed by a non-overlapping average pooling (and not referenced by a later link) never stores its normalised output:
-    the device pools the raw output in fp32 and applies the normalisation to the pooled value (pool(A*y + B) = A*pool(y) + B), one rounding later. """
+    the device pools the raw output in fp32 and applies the normalisation to the pooled value (pool(A*y + B) = A*pool(y) + B), one rounding later. The
+    other convolution blocks do the same in front of a 2x2 / stride-2 pooling, and add the referenced tensor of a residual sum that directly follows
+    inside their normalisation pass (no rounding of the normalised tensor in between). """
     for container in model.modules():
         subs = getattr(container, '_submodules', None)
         if isinstance(subs, dict):
@@ -427,6 +429,10 @@ def emulate_bf16_storage(model: torch.nn.Module) -> torch.nn.Module:
                     ks, st = nxt.kernel_size, nxt.stride
                     ks, st = (ks, ks) if isinstance(ks, int) else tuple(ks), (st, st) if isinstance(st, int) else tuple(st)
                     m._emul_next_pool = ks[0] if (ks == st and ks[0] == ks[1]) else 0
+                # any other block directly followed by a residual sum with ONE referenced tensor: the sum rides in the block's normalisation pass
+                # (z = A*y + B + other, one rounding)
+                if isinstance(nxt, Link) and nxt.reduction == 'sum' and len(nxt.referenced_submodules) == 1 and not nxt.ignore_input and name not in referenced:
+                    m._emul_next_sum = True
     for m in model.modules():
         if isinstance(m, torch.nn.Sequential) and len(m) > 0 and any(isinstance(c, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)) for c in m):
             def fwd(x, m=m):
@@ -450,8 +456,11 @@ def emulate_bf16_storage(model: torch.nn.Module) -> torch.nn.Module:
                     for nrm in norms:
                         y = nrm(y)
                     pool = getattr(m, '_emul_next_pool', 0)
-                    fused_pool = pool and _few_channel_block(op, x.shape) and y.shape[2] % pool == 0 and y.shape[3] % pool == 0
-                    if not fused_pool:
+                    few = _few_channel_block(op, x.shape)
+                    # few-channel blocks fuse any non-overlapping pooling; the other blocks the 2x2 / stride-2 one (and a residual sum)
+                    fused_pool = pool and (few or pool == 2) and y.shape[2] % pool == 0 and y.shape[3] % pool == 0
+                    fused_sum = getattr(m, '_emul_next_sum', False) and not few and isinstance(op, torch.nn.Conv2d)
+                    if not (fused_pool or fused_sum):
                         y = _q(y)                                      # z stored bf16 (or rounded to bf16 when the next few-channel block stages it)
                 return y
             m.forward = fwd

@@ -261,3 +261,29 @@ def test_norm_apply_fused_with_residual_sum_and_pooling(dev, n, h, w, c, dtype):
     gp = torch.randn_like(zp)
     zp.backward(gp)
     assert torch.equal(yl.grad.float(), (gp.float() * 0.25).to(dtype).float().repeat_interleave(2, dim=2).repeat_interleave(2, dim=3))
+
+
+@pytest.mark.parametrize('totals', [0, 2], ids=['per-image', 'channel-totals'])
+@pytest.mark.parametrize('n,h,w,c', [(3, 8, 12, 64), (2, 6, 4, 24), (4, 112, 112, 64)])
+def test_norm_backward_reads_pooled_gradient_in_place(dev, n, h, w, c, totals):
+    """ dcv_norm_bwd_reduce_pooled / dcv_act_norm_bwd_apply_pooled == dcv_avgpool2d_bwd followed by the plain passes: dy bit for bit, the sums to fp32
+    summation-order noise (atomics). """
+    from deepcv_b200._lib import ACT_LEAKY_RELU, DCV_BF16, check, lib
+    torch.manual_seed(h * 10 + c)
+    st = stream()
+    gp = torch.randn(n, h // 2, w // 2, c, device=dev).bfloat16()
+    y = torch.randn(n, h, w, c, device=dev).bfloat16()
+    pqr = torch.randn(n, c, 3, device=dev)
+    assert lib.dcv_norm_bwd_pooled_supported(n, h, w, c, DCV_BF16)
+    dz = torch.empty(n, h, w, c, device=dev, dtype=torch.bfloat16)
+    check(lib.dcv_avgpool2d_bwd(P(gp), P(dz), n, h, w, c, 2, 2, 2, 2, DCV_BF16, st), 'avgpool2d_bwd')
+    s_ref, s_new = torch.full((n, c, 2), 7., device=dev), torch.full((n, c, 2), 7., device=dev)
+    check(lib.dcv_norm_bwd_reduce(P(dz), P(y), P(s_ref), n, h * w, c, DCV_BF16, totals, st), 'norm_bwd_reduce')
+    check(lib.dcv_norm_bwd_reduce_pooled(P(gp), P(y), P(s_new), n, h, w, c, DCV_BF16, totals, st), 'norm_bwd_reduce_pooled')
+    assert float((s_ref - s_new).abs().max()) <= 2e-5 * float(s_ref.abs().max()) + 1e-6
+    dy_ref, dy_new = torch.full_like(y, 7.), torch.full_like(y, 7.)
+    db_ref, db_new = torch.full((c,), 7., device=dev), torch.full((c,), 7., device=dev)
+    check(lib.dcv_act_norm_bwd_apply(P(dz), P(y), P(pqr), P(dy_ref), P(db_ref), ACT_LEAKY_RELU, 0.01, n, h * w, c, DCV_BF16, 0, st), 'act_norm_bwd_apply')
+    check(lib.dcv_act_norm_bwd_apply_pooled(P(gp), P(y), P(pqr), P(dy_new), P(db_new), ACT_LEAKY_RELU, 0.01, n, h, w, c, DCV_BF16, 0, st), 'act_norm_bwd_apply_pooled')
+    assert torch.equal(dy_ref, dy_new)
+    assert float((db_ref - db_new).abs().max()) <= 2e-5 * float(db_ref.abs().max()) + 1e-6
