@@ -472,6 +472,14 @@ def measure_workload(name, args, dev, world, rank, local_rank, peaks):
         trainer.run(dataloader_prefetch_batches([(pool_host[i % n_host], labels_host[i % n_host]) for i in range(n)], dev), max_epochs=trainer.state.epoch + 1)
     ms_e2e = timed(e2e_run, 3)
     e2e_value = world * batch * e2e_steps / (ms_e2e / 1e3)
+    if os.environ.get('DCV_BENCH_PROFILE_E2E'):   # tuning aid: where the HOST time of the end-to-end loop goes (cProfile, printed to stderr, not timed)
+        import cProfile, pstats
+        prof = cProfile.Profile()
+        prof.enable()
+        e2e_run(None, warm=False)
+        torch.cuda.synchronize()
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(22)
     h2d = batch_bytes + batch * 8 + batch * (1 + 8) + 4    # images + int64 labels + flip (u8) / crop (2 x i32) + learning rate
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * len(losses), ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps,
                api='ignite_training.Engine(make_process_function(...)).run(dataloader_prefetch_batches(loader of pinned uint8 batches))')

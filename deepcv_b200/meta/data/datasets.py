@@ -87,6 +87,11 @@ class _PrefetchIterator:
         self._prefetched_batch = self._pending[0]
         self._slot ^= 1
 
+    def pending(self):
+        """ (device batch, arrival event) of the batch in flight — what the next `__next__` will hand out — or None. A captured training step copies it
+        into its static inputs ahead of time (`GraphedTrainStep.stage_next`). """
+        return self._pending
+
     def __iter__(self):
         return self
 

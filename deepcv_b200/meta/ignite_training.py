@@ -314,12 +314,15 @@ def make_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDi
     def _on_device(t: torch.Tensor) -> bool:
         return t.is_cuda and (dev.index is None or t.device.index == dev.index)
 
+    def _key(x, y):
+        return (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype) if (isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor)) else None
+
     def process_function(engine: Engine, batch) -> Dict[str, float]:
         x, *y = batch
         y = y[0] if len(y) == 1 else y
         if not (isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor)):
             return eager(engine, batch)
-        key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+        key = _key(x, y)
         runner = runners.get(key)
         if runner is None:
             if len(runners) >= 4:
@@ -332,10 +335,16 @@ def make_process_function(hp, device, model: torch.nn.Module, losses: 'OrderedDi
         runner.step(x, y)
         # the step is launched; whatever the host still has to do for the NEXT step hides under its device time: the copy of the next batch (a
         # prefetching loader: reference meta/data/datasets.py:76-115) and the draw of its augmentation parameters. Then the one sync of the step.
-        prefetch = getattr(getattr(engine, '_dataloader_iter', None), 'prefetch', None)
+        it = getattr(engine, '_dataloader_iter', None)
+        prefetch = getattr(it, 'prefetch', None)
         if prefetch is not None:
             prefetch()
         runner.prepare_next()
+        pending = getattr(it, 'pending', None)
+        if pending is not None:   # the next batch is on its way to the device: its copy into the graph's static inputs is enqueued now, behind this step
+            nxt = pending()
+            if nxt is not None and isinstance(nxt[0], (tuple, list)) and len(nxt[0]) == 2 and runners.get(_key(*nxt[0])) is runner:
+                runner.stage_next(nxt[0][0], nxt[0][1], nxt[1])
         return {n: float(v) for n, v in zip(runner.static_losses.keys(), runner.read_losses())}
     process_function.runners = runners
     return process_function
@@ -361,15 +370,20 @@ class GraphedTrainStep:
         n = example_x.shape[0]
         self.static_flip = self.static_crop = None
         self._host_flip = self._host_crop = None
+        self._host_slot, self._staged = 0, None
         if preprocess is not None:
             self.static_flip = torch.zeros(n, dtype=torch.uint8, device=example_x.device)
             self.static_crop = torch.full((n, 2), int(preprocess.pad), dtype=torch.int32, device=example_x.device)
-            self._host_flip = torch.zeros(n, dtype=torch.uint8).pin_memory()
-            self._host_crop = torch.full((n, 2), int(preprocess.pad), dtype=torch.int32).pin_memory()
+            self._host_flip = [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._host_crop = [torch.full((n, 2), int(preprocess.pad), dtype=torch.int32).pin_memory() for _ in range(2)]
         self.graph = torch.cuda.CUDAGraph()
         self.static_losses: 'OrderedDict[str, torch.Tensor]' = OrderedDict()
         self.static_loss = None
-        self._drawn, self._loss_pack, self._loss_host = None, None, None
+        self._drawn = None
+        self._loss_pack = torch.empty(len(self.losses), dtype=torch.float32, device=example_x.device)
+        self._loss_host = torch.empty(len(self.losses), dtype=torch.float32).pin_memory()
+        self._loss_event = torch.cuda.Event(external=True)   # an event-record NODE of the captured graph, waited for by the host
+        self._loss_stream = torch.cuda.Stream(device=example_x.device) if os.environ.get('DCV_LOSS_INLINE') is None else None
         inner = model.module if isinstance(model, DataParallelModel) else model
         self.flat: Optional[FlatParameters] = getattr(optimizer, '_flat', None) or getattr(inner, '_flat_parameters', None)
         if isinstance(optimizer, FlatAdamW) and optimizer._flat is None and self.flat is not None:
@@ -485,56 +499,81 @@ class GraphedTrainStep:
         for name, fn in self.losses.items():
             self.static_losses[name] = fn(y_pred, self.static_y)
         loss = self.static_loss = self.static_losses[MAIN_TRAINING_LOSS_NAME]
+        # The loss terms leave for the host HERE, before backward: a device -> pinned-host copy and an EXTERNAL event inside the captured step. The host's
+        # one synchronisation per step (`read_losses`, the reference's `.item()`) then returns while backward is still running, and everything the
+        # host does until the next replay — engine bookkeeping, next batch, graph launch — hides under it: the device never waits for the host.
+        vals = [v.detach() for v in self.static_losses.values()]
+        if len(vals) > 1:
+            torch.stack(vals, out=self._loss_pack)
+        main = torch.cuda.current_stream()
+        if self._loss_stream is not None:   # the copy and the event are a side branch of the captured graph: backward does not queue behind a memcpy node
+            self._loss_stream.wait_stream(main)
+        with torch.cuda.stream(self._loss_stream if self._loss_stream is not None else main):
+            self._loss_host.copy_(vals[0].reshape(1) if len(vals) == 1 else self._loss_pack, non_blocking=True)
+            self._loss_event.record()
         self.optimizer.zero_grad()
         torch.autograd.backward(loss, grad_tensors=[ops.unit_grad(loss.device)])   # = loss.backward() without the ones_like fill kernel / the multiplication by one
         self.ctx.join_side()
+        if self._loss_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._loss_stream)
         if isinstance(self.model, DataParallelModel):
             self.model.finish_gradient_reduction()
         self.optimizer.step(refresh_lr=False)
         return loss
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        if x.data_ptr() != self.static_x.data_ptr():
-            self.static_x.copy_(x, non_blocking=True)
-        if y.data_ptr() != self.static_y.data_ptr():
-            self.static_y.copy_(y, non_blocking=True)
+        if self._staged != (x.data_ptr(), y.data_ptr()):   # else: `stage_next` already copied this very batch into the static buffers
+            if x.data_ptr() != self.static_x.data_ptr():
+                self.static_x.copy_(x, non_blocking=True)
+            if y.data_ptr() != self.static_y.data_ptr():
+                self.static_y.copy_(y, non_blocking=True)
+        self._staged = None
         if self.preprocess is not None:
             if not self._drawn:
                 self.prepare_next()
-            if self._drawn == 'params':
-                self.static_flip.copy_(self._host_flip, non_blocking=True)
-                self.static_crop.copy_(self._host_crop, non_blocking=True)
             self._drawn = None
         self.optimizer.set_lr_device()
         self.graph.replay()
         return self.static_loss
 
     def prepare_next(self) -> None:
-        """ Draws the NEXT step's per-sample augmentation parameters into the pinned staging buffers (host work that may run while the device executes
-        the current step; the draw order of the generator is unchanged). """
+        """ Draws the NEXT step's per-sample augmentation parameters (the draw order of the generator is unchanged) and enqueues their host -> device copy
+        into the static buffers. Called right after a step has been launched, all of it hides under that step's device time: the copies are ordered
+        behind the running step on the stream (it still reads the buffers), and the host has nothing left to do between that step's loss read and
+        the next replay. Two pinned staging buffers alternate: the previous copy may not have executed yet (one synchronisation per step). """
         if self.preprocess is None or self._drawn:
             return
         self.preprocess.train()   # the captured step is a TRAINING step (reference :246 `model.train()`): an evaluation pass in between must not freeze the draws
         flip, crop = self.preprocess.draw(self.static_x.shape[0])
         if flip is not None:
-            self._host_flip.copy_(flip)
-            self._host_crop.copy_(crop)
-            self._drawn = 'params'
-        else:
-            self._drawn = 'none'
+            self._host_slot ^= 1
+            host_flip, host_crop = self._host_flip[self._host_slot], self._host_crop[self._host_slot]
+            host_flip.copy_(flip)
+            host_crop.copy_(crop)
+            self.static_flip.copy_(host_flip, non_blocking=True)
+            self.static_crop.copy_(host_crop, non_blocking=True)
+        self._drawn = 'staged'
+
+    def stage_next(self, x: torch.Tensor, y: torch.Tensor, ready: Optional[torch.cuda.Event] = None) -> bool:
+        """ Copies the NEXT batch (device tensors, e.g. the batch a prefetching loader has in flight; `ready`: the event of its arrival) into the static
+        input buffers now — behind the step that is running — so that `step(x, y)` with these tensors only replays the graph. False (and nothing
+        done) when the tensors do not match the captured shapes. """
+        if not (isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor) and x.is_cuda and y.is_cuda and x.shape == self.static_x.shape and x.dtype == self.static_x.dtype
+                and y.shape == self.static_y.shape and y.dtype == self.static_y.dtype):
+            return False
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        if y.data_ptr() != self.static_y.data_ptr():
+            self.static_y.copy_(y, non_blocking=True)
+        self._staged = (x.data_ptr(), y.data_ptr())
+        return True
 
     def read_losses(self) -> List[float]:
-        """ The loss terms of the step just replayed, as floats: ONE device -> host copy (the step's only synchronisation, the reference's `.item()`). """
-        vals = list(self.static_losses.values())
-        if self._loss_pack is None or self._loss_pack.numel() != len(vals):
-            self._loss_pack = torch.empty(len(vals), dtype=torch.float32, device=vals[0].device)
-            self._loss_host = torch.empty(len(vals), dtype=torch.float32).pin_memory()
-        if len(vals) == 1:
-            self._loss_host.copy_(vals[0].reshape(1), non_blocking=True)
-        else:
-            torch.stack(vals, out=self._loss_pack)
-            self._loss_host.copy_(self._loss_pack, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        """ The loss terms of the step just replayed, as floats (the step's only synchronisation, the reference's `.item()`): waits for the forward
+        pass of that step, not for its backward / optimizer kernels. """
+        self._loss_event.synchronize()   # recorded inside the replayed graph right after the losses' device -> host copy (see `_eager_step`)
         return self._loss_host.tolist()
 
 
