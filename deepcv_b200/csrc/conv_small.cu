@@ -817,9 +817,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_wgrad_kernel(const WgradArgs
       *reinterpret_cast<float2*>(d0 + 8 * ND) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
     }
   __syncthreads();
-  const int total = a.k_out * KS * KS * a.c_src;
-  for (int i = tid; i < total; i += kWgThreads) {
-    const int c = i % a.c_src, tap = (i / a.c_src) % (KS * KS), o = i / (a.c_src * KS * KS), r = tap / KS, s_ = tap % KS;
+  const int total = a.k_out * KS * KS * CI;   // compile-time divisors (see sc_bwd_kernel); tile channels beyond c_src are skipped
+  for (int j = tid; j < total; j += kWgThreads) {
+    const int c = j % CI, tap = (j / CI) % (KS * KS), o = j / (CI * KS * KS), r = tap / KS, s_ = tap % KS;
+    if (c >= a.c_src) continue;
+    const int i = (o * KS * KS + tap) * a.c_src + c;
     float v = 0.f;
     if (G::PAIR) {   // dw[s] = D[(r, s' = s, c)][(par 0, o)] + D[(r, s' = s + 1, c)][(par 1, o)]
 #pragma unroll
@@ -1008,9 +1010,13 @@ __global__ void __launch_bounds__(kWgThreads, 2) sc_bwd_kernel(const BwdArgs a) 
       *reinterpret_cast<float2*>(d0 + 8 * ND) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
     }
   __syncthreads();
-  const int total = a.k_out * KS * KS * a.c_in;
-  for (int i = tid; i < total; i += kWgThreads) {
-    const int c = i % a.c_in, tap = (i / a.c_in) % (KS * KS), o = i / (a.c_in * KS * KS), r = tap / KS, s_ = tap % KS;
+  // walk the (output channel, tap, TILE channel) index space: every divisor is a compile-time constant (dividing by the runtime channel count cost three
+  // integer divisions per element: 11.6 % of this kernel's instructions in the ncu source view); tile channels beyond c_in are skipped
+  const int total = a.k_out * KS * KS * CI;
+  for (int j = tid; j < total; j += kWgThreads) {
+    const int c = j % CI, tap = (j / CI) % (KS * KS), o = j / (CI * KS * KS), r = tap / KS, s_ = tap % KS;
+    if (c >= a.c_in) continue;
+    const int i = (o * KS * KS + tap) * a.c_in + c;
     float v = 0.f;
     if (WG::PAIR) {
 #pragma unroll
