@@ -300,6 +300,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
 _SIDE_WGRAD = os.environ.get('DCV_SIDE_WGRAD') == '1'   # opt-in: weight-gradient kernels on a second stream (measured: 6.377 -> 6.323 ms on the ImageNet-shaped step — they compete with the normalisation passes for HBM — not worth a second stream inside the captured step by default)
+_ONE_IMAGE_BN = os.environ.get('DCV_ONE_IMAGE_BN') == '1'   # opt-in: BatchNorm-only blocks hand the batch to the finalize / apply kernels as ONE image (k coefficients instead of n*k). Measured on the ImageNet-shaped step: 6.27 -> 6.58 ms (the streaming kernels' row partition is tuned for many images), so off by default
 _POOLED_BWD = os.environ.get('DCV_NO_POOLED_BWD') is None   # tuning aid: DCV_NO_POOLED_BWD=1 materialises the full-resolution gradient behind a fused normalise + pool
 _LAZY_APPLY = os.environ.get('DCV_NO_LAZY_APPLY') is None   # tuning aid: DCV_NO_LAZY_APPLY=1 always runs the stand-alone normalisation apply pass
 _USE_PAIRS = os.environ.get('DCV_NO_PAIRS') is None     # tuning aid: DCV_NO_PAIRS=1 sends stride-2 few-channel layers to the gather kernels instead of the pixel-pair ones
@@ -394,25 +395,32 @@ class _ConvBlock(torch.autograd.Function):
                 check(lib.dcv_copy_channels_in(_ptr(w_op), _ptr(w_col), k, rsc, kpad, 0, dt, st), 'copy_channels_in(weight)')
                 col = torch.empty((n, p, q, kpad), dtype=x.dtype, device=dev)
                 check(lib.dcv_im2col(ctypes.byref(shape), _ptr(x), _ptr(col), kpad, dt, st), 'im2col')
-                check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz, st), 'conv2d_fwd(im2col)')
+                check(lib.dcv_conv2d_fwd(ctypes.byref(gemm_shape), _ptr(col), _ptr(w_col), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz | totals, st), 'conv2d_fwd(im2col)')
                 x = col   # what the weight gradient needs; the data gradient only needs dy and the weights
         else:
             check(lib.dcv_conv2d_fwd(ctypes.byref(shape), _ptr(x), _ptr(w_op), _ptr(bias), _ptr(y), _ptr(stats), act, slope, dt, algo, pz | totals, st), 'conv2d_fwd')
         saved = None
         out = y
+        # BatchNorm-only block whose statistics came out as channel totals (tensor-core paths): to the finalize / apply kernels the batch IS one image of
+        # n*p*q pixels (same arithmetic: BatchNorm reduces over (N, H, W)) — coefficient tables of k entries instead of n*k, finalize kernels that do not
+        # walk n rows of zeros
+        one_image = bool(totals & 2) and n > 1 and n * p * q < (1 << 31) and _ONE_IMAGE_BN and \
+            bool(gathered or gemm_shape is not None or (algo != ALGO_DIRECT and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 0)))
+        ne, hwe = (1, n * p * q) if one_image else (n, p * q)
         if cfg.any:
             groups = cfg.gn_groups if cfg.use_gn else 1
-            saved = torch.empty((int(lib.dcv_norm_saved_floats(n, k, groups)),), dtype=torch.float32, device=dev)
-            ab = torch.empty((n, k, 2), dtype=torch.float32, device=dev)
-            prm = _norm_params(cfg, n, k, p * q, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
+            saved = torch.empty((int(lib.dcv_norm_saved_floats(ne, k, groups)),), dtype=torch.float32, device=dev)
+            ab = torch.empty((ne, k, 2), dtype=torch.float32, device=dev)
+            prm = _norm_params(cfg, ne, k, hwe, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
             check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(ab), _ptr(saved), st), 'norm_fwd_finalize')
             if not defer_apply:
                 out = empty_nhwc(n, k, p, q, x.dtype, dev)
-                check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, p * q, k, dt, st), 'norm_apply_fwd')
+                check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), ne, hwe, k, dt, st), 'norm_apply_fwd')
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
         # the fp32 master weight, when it already is [K][R][S][C] in memory: the data-gradient operand is packed straight from it in backward
         ctx.w_master = weight.detach() if (weight.dtype == torch.float32 and weight.permute(0, 2, 3, 1).is_contiguous()) else None
         ctx.cfg = (shape, act, slope, cfg, training, algo, bias is not None, grad_out, tuple(weight.shape), gemm_shape, gathered, sctx)
+        ctx.one_image = one_image
         if defer_apply and cfg.any:
             # the RAW output goes on with its coefficients (`PendingNorm`): the consumer applies z = A*y + B inside its own pass (`_ApplyNorm*`) and hands
             # back dz — the gradient w.r.t. the normalised output, exactly what this backward expects — as the "gradient" of y
@@ -444,7 +452,8 @@ class _ConvBlock(torch.autograd.Function):
                 check(lib.dcv_norm_bwd_reduce_pooled(_ptr(dzp), _ptr(y), _ptr(s_nc), n, p, q, k, dt, pz | totals, st), 'norm_bwd_reduce_pooled')
             else:
                 check(lib.dcv_norm_bwd_reduce(_ptr(dz), _ptr(y), _ptr(s_nc), n, p * q, k, dt, pz | totals, st), 'norm_bwd_reduce')
-            pqr = torch.empty((n, k, 3), **f32)
+            ne, hwe = (1, n * p * q) if ctx.one_image else (n, p * q)
+            pqr = torch.empty((ne, k, 3), **f32)
             if cfg.use_bn and bn_w is not None:
                 d_bn_w, d_bn_b = targets.get('bn_w', None), targets.get('bn_b', None)
                 d_bn_w = torch.empty((k,), **f32) if d_bn_w is None else d_bn_w
@@ -453,7 +462,7 @@ class _ConvBlock(torch.autograd.Function):
                 d_gn_w, d_gn_b = targets.get('gn_w', None), targets.get('gn_b', None)
                 d_gn_w = torch.empty((k,), **f32) if d_gn_w is None else d_gn_w
                 d_gn_b = torch.empty((k,), **f32) if d_gn_b is None else d_gn_b
-            prm = _norm_params(cfg, n, k, p * q, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
+            prm = _norm_params(cfg, ne, k, hwe, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
             check(lib.dcv_norm_bwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(s_nc), _ptr(saved), _ptr(pqr),
                                             _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'norm_bwd_finalize')
         need_dy_pass = cfg.any or act != ACT_NONE or has_bias
@@ -464,10 +473,13 @@ class _ConvBlock(torch.autograd.Function):
             if has_bias:
                 dbias = targets.get('bias', None)
                 dbias = _acc_empty((k,), dev, sctx) if dbias is None else dbias
+            one = cfg.any and ctx.one_image   # the coefficient table has one row: the batch is one image of n*p rows
             if dzp is not None:
-                check(lib.dcv_act_norm_bwd_apply_pooled(_ptr(dzp), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p, q, k, dt, pz, st), 'act_norm_bwd_apply_pooled')
+                check(lib.dcv_act_norm_bwd_apply_pooled(_ptr(dzp), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, 1 if one else n, n * p if one else p, q, k, dt, pz, st),
+                      'act_norm_bwd_apply_pooled')
             else:
-                check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, n, p * q, k, dt, pz, st), 'act_norm_bwd_apply')
+                check(lib.dcv_act_norm_bwd_apply(_ptr(dz), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, 1 if one else n, n * p * q if one else p * q, k, dt, pz, st),
+                      'act_norm_bwd_apply')
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(n, shape.c, shape.h, shape.w, y.dtype, dev)
@@ -604,15 +616,17 @@ class _ApplyNorm(torch.autograd.Function):
         n, c, h, w = y.shape
         ctx.geom, ctx.pool, ctx.has_other, ctx.link = (n, c, h, w), pool, other is not None, link
         st, dt = _stream(), _dt(y)
+        one = ab.shape[0] == 1 and n > 1   # BatchNorm-only block: one row of coefficients, the batch is one image of n*h rows (h even when pooled: image
+        ne, he = (1, n * h) if one else (n, h)   # boundaries fall on even rows)
         if pool:
             out = empty_nhwc(n, c, h // 2, w // 2, y.dtype, y.device)
-            check(lib.dcv_norm_apply_pool_fwd(_ptr(y), _ptr(ab), _ptr(out), n, h, w, c, dt, st), 'norm_apply_pool_fwd')
+            check(lib.dcv_norm_apply_pool_fwd(_ptr(y), _ptr(ab), _ptr(out), ne, he, w, c, dt, st), 'norm_apply_pool_fwd')
         elif other is not None:
             out = empty_nhwc(n, c, h, w, y.dtype, y.device)
-            check(lib.dcv_norm_apply_add_fwd(_ptr(y), _ptr(ab), _ptr(other), _ptr(out), n, h * w, c, dt, st), 'norm_apply_add_fwd')
+            check(lib.dcv_norm_apply_add_fwd(_ptr(y), _ptr(ab), _ptr(other), _ptr(out), ne, he * w, c, dt, st), 'norm_apply_add_fwd')
         else:
             out = empty_nhwc(n, c, h, w, y.dtype, y.device)
-            check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), n, h * w, c, dt, st), 'norm_apply_fwd')
+            check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), ne, he * w, c, dt, st), 'norm_apply_fwd')
         return out
 
     @staticmethod
