@@ -684,6 +684,7 @@ static void finalize_grid(const dcv_norm_params* prm, int* cpb, int* blocks) {
   const int cg = prm->use_gn ? prm->c / prm->gn_groups : 1;
   int per = 512 / (prm->n > 0 ? prm->n : 1);
   if (per < 1) per = 1;
+  if (per > 32) per = 32;   // one warp per channel and pass: a handful of images (or a whole batch handed over as ONE image) must not end up in a single CTA
   per = (per + cg - 1) / cg * cg;
   while ((prm->c + per - 1) / per > dcv::kNumSMs) per += cg;
   *cpb = per;

@@ -300,7 +300,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
 _SIDE_WGRAD = os.environ.get('DCV_SIDE_WGRAD') == '1'   # opt-in: weight-gradient kernels on a second stream (measured: 6.377 -> 6.323 ms on the ImageNet-shaped step — they compete with the normalisation passes for HBM — not worth a second stream inside the captured step by default)
-_ONE_IMAGE_BN = os.environ.get('DCV_ONE_IMAGE_BN') == '1'   # opt-in: BatchNorm-only blocks hand the batch to the finalize / apply kernels as ONE image (k coefficients instead of n*k). Measured on the ImageNet-shaped step: 6.27 -> 6.58 ms (the streaming kernels' row partition is tuned for many images), so off by default
+_ONE_IMAGE_BN = os.environ.get('DCV_NO_ONE_IMAGE_BN') is None   # tuning aid: DCV_NO_ONE_IMAGE_BN=1 keeps per-image coefficient tables for BatchNorm-only blocks
 _POOLED_BWD = os.environ.get('DCV_NO_POOLED_BWD') is None   # tuning aid: DCV_NO_POOLED_BWD=1 materialises the full-resolution gradient behind a fused normalise + pool
 _LAZY_APPLY = os.environ.get('DCV_NO_LAZY_APPLY') is None   # tuning aid: DCV_NO_LAZY_APPLY=1 always runs the stand-alone normalisation apply pass
 _USE_PAIRS = os.environ.get('DCV_NO_PAIRS') is None     # tuning aid: DCV_NO_PAIRS=1 sends stride-2 few-channel layers to the gather kernels instead of the pixel-pair ones
