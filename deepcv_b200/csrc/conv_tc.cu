@@ -1682,6 +1682,7 @@ struct WgradParams {
   int tw, th, tn, tiles_w, tiles_h, tiles_n, pixel_tiles;
   int k_tiles, c_tiles, splits;
   int chan_taps;   // 1: the S_TAPS atoms of the B operand are consecutive 64-channel blocks of x (1x1 filters: c >= 128), not column taps
+  int row_pairs, r_units;   // row_pairs: layers with at most 64 output channels — a unit owns filter rows (rr, rr + 1), see the kernel; r_units = units along r
   float* dw;
 };
 
@@ -1711,7 +1712,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
   int u = blockIdx.x;
   const int split = u % prm.splits; u /= prm.splits;
   const int ct = u % prm.c_tiles; u /= prm.c_tiles;
-  const int rr = u % prm.r; const int kt = u / prm.r;
+  const int rr = (u % prm.r_units) * (prm.row_pairs ? 2 : 1); const int kt = u / prm.r_units;
   const int my_tiles = split < prm.pixel_tiles ? (prm.pixel_tiles - split + prm.splits - 1) / prm.splits : 0;
 
   if (threadIdx.x == 0) {
@@ -1726,8 +1727,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
   }
   // Output channels 64..127 of this k tile: when the layer has only 64 of them the second MN atom of the dy operand is all zeros. It is zeroed here once
   // instead of being zero-filled by a second TMA box per pixel tile (16 KB of shared-memory writes per tile for nothing).
+  // Row pairs (at most 64 output channels): the second atom is not wasted on zeros but holds the SAME dy tile one image row up (a second TMA box at p0 - 1,
+  // rows outside the image zero-filled): accumulator rows 64..127 then are sum_p dy[p - 1][k] * x[p + rr - pad][c] = the gradient of filter row rr + 1.
+  // One unit does two filter rows with a full M = 128 (the pixel-tile grid covers one extra row so that the shifted copy reaches the last dy row).
   const bool second_atom = prm.k > kt * 128 + 64;
-  if (!second_atom) {
+  const bool pair = prm.row_pairs && !second_atom && rr + 1 < prm.r;
+  if (!second_atom && !pair) {
     for (int i = threadIdx.x; i < WG_NA * (WG_SLAB / 16); i += kThreads) {
       const int slot = i / (WG_SLAB / 16), off = i - slot * (WG_SLAB / 16);
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_a + slot * A_BYTES + WG_SLAB + off * 16), "r"(0) : "memory");
@@ -1753,9 +1758,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
         const int ph = pt % prm.tiles_h; const int pn = pt / prm.tiles_h;
         const int q0 = pw * prm.tw, p0 = ph * prm.th, n0 = pn * prm.tn;
         mbar_wait(aempty(as), aph ^ 1u);
-        mbar_expect_tx(afull(as), second_atom ? A_BYTES : WG_SLAB);
+        mbar_expect_tx(afull(as), (second_atom || pair) ? A_BYTES : WG_SLAB);
         tma_load_4d(smem_a + as * A_BYTES, &map_dy, afull(as), kt * 128, q0, p0, n0);
         if (second_atom) tma_load_4d(smem_a + as * A_BYTES + WG_SLAB, &map_dy, afull(as), kt * 128 + 64, q0, p0, n0);
+        else if (pair) tma_load_4d(smem_a + as * A_BYTES + WG_SLAB, &map_dy, afull(as), kt * 128, q0, p0 - 1, n0);
         if (++as == WG_NA) { as = 0; aph ^= 1u; }
         mbar_wait(bempty(bs), bph ^ 1u);
         mbar_expect_tx(bfull(bs), B_BYTES);
@@ -1794,7 +1800,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
     }
   } else if (my_tiles > 0) {
     const int quarter = warp & 3;
-    const int krow = kt * 128 + quarter * 32 + lane;
+    const int arow = quarter * 32 + lane;                              // accumulator row
+    const int krow = kt * 128 + (pair ? (arow & 63) : arow);           // output channel; a row pair's rows 64..127 are the channels again, for filter row rr + 1
+    const int frow = rr + (pair ? (arow >> 6) : 0);
     mbar_wait(done, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -1804,9 +1812,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + ss * 64 + c0, v);
-        if (krow < prm.k) {
-          float* dst = prm.chan_taps ? prm.dw + (((size_t)krow * prm.r + rr) * prm.s) * prm.c + (ct * S_TAPS + ss) * 64 + c0
-                                     : prm.dw + (((size_t)krow * prm.r + rr) * prm.s + ss) * prm.c + ct * 64 + c0;
+        if (krow < prm.k && (pair || arow < 64 || second_atom)) {
+          float* dst = prm.chan_taps ? prm.dw + (((size_t)krow * prm.r + frow) * prm.s) * prm.c + (ct * S_TAPS + ss) * 64 + c0
+                                     : prm.dw + (((size_t)krow * prm.r + frow) * prm.s + ss) * prm.c + ct * 64 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic operations
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
@@ -1849,8 +1857,12 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
   DCV_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0), "conv2d_wgrad (tcgen05): pointers must be 16-byte aligned");
   WgradParams prm{};
   prm.n = s->n; prm.h = s->h; prm.w = s->w; prm.c = s->c; prm.k = s->k; prm.r = s->r; prm.s = s->s; prm.pad_h = s->pad_h; prm.pad_w = s->pad_w; prm.p = s->p; prm.q = s->q;
-  pick_pixel_tile(s->q, s->p, s->n, &prm.tw, &prm.th, &prm.tn);
-  prm.tiles_w = (s->q + prm.tw - 1) / prm.tw; prm.tiles_h = (s->p + prm.th - 1) / prm.th; prm.tiles_n = (s->n + prm.tn - 1) / prm.tn;
+  // at most 64 output channels (M = 128 would be half zero-fill): a unit takes two filter rows, the second through a dy tile shifted by one image row;
+  // the pixel tiles then cover p = 0 .. P (one extra row: the shifted copy of the last dy row)
+  prm.row_pairs = (s->k <= 64 && s->r >= 2 && s->s > 1 && getenv("DCV_WGRAD_NO_ROW_PAIRS") == nullptr) ? 1 : 0;
+  const int p_cover = s->p + prm.row_pairs;
+  pick_pixel_tile(s->q, p_cover, s->n, &prm.tw, &prm.th, &prm.tn);
+  prm.tiles_w = (s->q + prm.tw - 1) / prm.tw; prm.tiles_h = (p_cover + prm.th - 1) / prm.th; prm.tiles_n = (s->n + prm.tn - 1) / prm.tn;
   const long long ptiles = (long long)prm.tiles_w * prm.tiles_h * prm.tiles_n;
   DCV_REQUIRE(ptiles < (1ll << 30), "conv2d_wgrad (tcgen05): too many pixel tiles");
   prm.pixel_tiles = (int)ptiles;
@@ -1861,7 +1873,9 @@ int conv_wgrad_tc(const dcv_conv_shape* s, const void* x, const void* dy, float*
     taps = prm.c_tiles % 3 == 0 ? 3 : (prm.c_tiles % 2 == 0 ? 2 : 1);
     if (taps > 1) { prm.chan_taps = 1; prm.c_tiles /= taps; }
   }
-  const int units = prm.k_tiles * s->r * prm.c_tiles;
+  if (prm.chan_taps) prm.row_pairs = 0;
+  prm.r_units = prm.row_pairs ? (s->r + 1) / 2 : s->r;
+  const int units = prm.k_tiles * prm.r_units * prm.c_tiles;
   // One CTA per SM fits (192 KB of shared memory): pick the pixel split that minimises (waves of CTAs) x (pixel tiles per CTA + fixed cost) — e.g.
   // 3 units x 49 splits = 147 CTAs in one wave, never 297 CTAs in two waves plus a one-CTA tail.
   int splits = 1;
