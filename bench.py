@@ -462,7 +462,7 @@ def measure_workload(name, args, dev, world, rank, local_rank, peaks):
 
     # ---- end to end through the public API: Engine.run over a loader of pinned host uint8 batches; per step H2D of images / labels / augmentation
     # parameters (+ learning rate when it changes), the graph replay, and the D2H read of the loss (`process_function` returns floats)
-    e2e_steps = max(10, steps // 2)
+    e2e_steps = max(10, steps)   # as many steps as the device-resident measurement: a single host hiccup (one slow iteration) weighs less
     losses_seen = []
     trainer.add_event_handler(__import__('deepcv_b200.meta.ignite_training', fromlist=['Events']).Events.ITERATION_COMPLETED, lambda e: losses_seen.append(e.state.output['main_loss']))
 
