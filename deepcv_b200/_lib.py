@@ -109,6 +109,7 @@ SYMBOLS = {
     'dcv_norm_bwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P, P, P, P, P, P]),
     'dcv_act_norm_bwd_apply': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_bwd_pooled_supported': (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    'dcv_act_bn_bwd_apply_fold': (c_int, [P, c_int, P, P, P, c_int, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_bwd_reduce_pooled': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_act_norm_bwd_apply_pooled': (c_int, [P, P, P, P, P, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_avgpool2d_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -310,9 +310,21 @@ template <int ACT> __device__ __forceinline__ float act_grad_t(float y, float sl
   return 1.f;
 }
 
-template <typename T, int VE, int ACT, bool POOL = false>
+// FOLD (BatchNorm-only block whose batch is handed over as ONE image): the coefficients P, Q, R come out of the prologue — a few fp64 operations per thread
+// on the channel totals {sum dz, sum dz*y} (`fold.s`) and the forward's saved mean / rstd / alpha — and the CTAs of the first row range write the
+// BatchNorm parameter gradients: the bwd_finalize launch in between (6-8 us of latency per layer) is gone. Same arithmetic as bwd_finalize_kernel.
+struct BnFold {
+  const float* s;       // [c][2] channel totals of the backward reduce
+  const float* saved;   // forward finalize: [0,2c) mean,rstd | [2c,4c) alpha,beta
+  float* d_w; float* d_b;
+  double inv_m;         // 1 / (N*H*W)
+  int c, training;
+};
+
+template <typename T, int VE, int ACT, bool POOL = false, bool FOLD = false>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ pqr,
-                                                        T* __restrict__ dy, float* __restrict__ dbias, float slope, const NcGeom g, const FastDiv div_w = FastDiv(), uint32_t w = 0) {
+                                                        T* __restrict__ dy, float* __restrict__ dbias, float slope, const NcGeom g, const FastDiv div_w = FastDiv(), uint32_t w = 0,
+                                                        const BnFold fold = BnFold()) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
   float acc[1][VE];   // bias-gradient partial sums, kept over all the CTA's images
@@ -321,7 +333,21 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dz
   if (colg < g.cv) {
     for_each_segment(g, [&](int img, int p0, int p1) {
       float P[VE], Q[VE], R[VE];
-      if (pqr) {
+      if constexpr (FOLD) {
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          const int ch = chan_of(g, colg, VE, e);
+          const double mu = (double)__ldg(fold.saved + 2 * ch), rc = (double)__ldg(fold.saved + 2 * ch + 1), al = (double)__ldg(fold.saved + 2 * fold.c + 2 * ch);
+          const double u1 = (double)__ldg(fold.s + kBwdSums * ch), u2 = rc * ((double)__ldg(fold.s + kBwdSums * ch + 1) - mu * u1);
+          P[e] = (float)al;
+          Q[e] = fold.training ? (float)(-al * rc * u2 * fold.inv_m) : 0.f;
+          R[e] = fold.training ? (float)(al * (-u1 * fold.inv_m + mu * rc * u2 * fold.inv_m)) : 0.f;
+          if (blockIdx.x == 0 && row == 0 && (g.pack <= 1 || e < g.c)) {
+            if (fold.d_w) fold.d_w[ch] = (float)u2;
+            if (fold.d_b) fold.d_b[ch] = (float)u1;
+          }
+        }
+      } else if (pqr) {
 #pragma unroll
         for (int e = 0; e < VE; ++e) {
           const float* t = pqr + ((size_t)img * g.c + chan_of(g, colg, VE, e)) * 3;
@@ -840,6 +866,38 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
   }
 #undef DCV_BWD_APPLY
   DCV_LAUNCH_CHECK("bwd_apply_kernel");
+  return 0;
+}
+
+int dcv_act_bn_bwd_apply_fold(const void* dz, int pooled, const void* y, const float* s_c, const float* saved, int bn_training, float* d_bn_weight, float* d_bn_bias,
+                              void* dy, float* dbias_c, int act, float slope, int rows, int w, int c, int dtype, int acc_prezeroed, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(dz && y && dy && s_c && saved, "act_bn_bwd_apply_fold: null pointer");
+  DCV_REQUIRE(rows > 0 && w > 0 && c > 0 && (long long)rows * w < (1ll << 31), "act_bn_bwd_apply_fold: bad shape");
+  DCV_REQUIRE(!pooled || dcv_norm_bwd_pooled_supported(1, rows, w, c, dtype), "act_bn_bwd_apply_fold: pooled gradient needs even rows / width and whole 16-byte channel vectors");
+  cudaStream_t st = as_stream(stream);
+  zero_accumulator(dbias_c, (size_t)c * sizeof(float), st, acc_prezeroed != 0);
+  const int hw = rows * w;
+  BnFold fold{s_c, saved, d_bn_weight, d_bn_bias, 1.0 / (double)hw, c, bn_training};
+  dim3 grid; int block;
+#define DCV_FOLD_LAUNCH(ACT_, POOL_)                                                                                                                          \
+  DCV_DISPATCH_DTYPE(dtype, T, {                                                                                                                              \
+    constexpr int VE = 16 / sizeof(T);                                                                                                                        \
+    DCV_REQUIRE(c % VE == 0 && vec_ok(dz, y, dy, 1, hw, c, VE), "act_bn_bwd_apply_fold: channels must be whole 16-byte vectors at 16-byte aligned pointers");  \
+    static const int occ = streaming_ctas_per_sm((const void*)bwd_apply_kernel<T, VE, ACT_, POOL_, true>);                                                  \
+    NcGeom g = make_geom<VE>(1, hw, c, occ, &grid, &block, dbias_c ? 8 : 2);                                                                                  \
+    bwd_apply_kernel<T, VE, ACT_, POOL_, true><<<grid, block, 0, st>>>((const T*)dz, (const T*)y, nullptr, (T*)dy, dbias_c, slope, g, FastDiv((uint32_t)w), (uint32_t)w, fold); \
+  })
+#define DCV_FOLD_ACT(ACT_) do { if (pooled) { DCV_FOLD_LAUNCH(ACT_, true); } else { DCV_FOLD_LAUNCH(ACT_, false); } } while (0)
+  switch (act) {
+    case DCV_ACT_RELU: DCV_FOLD_ACT(DCV_ACT_RELU); break;
+    case DCV_ACT_LEAKY_RELU: DCV_FOLD_ACT(DCV_ACT_LEAKY_RELU); break;
+    case DCV_ACT_SIGMOID: DCV_FOLD_ACT(DCV_ACT_SIGMOID); break;
+    default: DCV_FOLD_ACT(DCV_ACT_NONE); break;
+  }
+#undef DCV_FOLD_ACT
+#undef DCV_FOLD_LAUNCH
+  DCV_LAUNCH_CHECK("bwd_apply_kernel(fold)");
   return 0;
 }
 

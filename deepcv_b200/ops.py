@@ -300,6 +300,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
 _SIDE_WGRAD = os.environ.get('DCV_SIDE_WGRAD') == '1'   # opt-in: weight-gradient kernels on a second stream (measured: 6.377 -> 6.323 ms on the ImageNet-shaped step — they compete with the normalisation passes for HBM — not worth a second stream inside the captured step by default)
+_FOLD_BWD_FINALIZE = os.environ.get('DCV_NO_FOLD_BWD_FINALIZE') is None   # tuning aid: DCV_NO_FOLD_BWD_FINALIZE=1 keeps the stand-alone backward finalize launch of BatchNorm-only blocks
 _ONE_IMAGE_BN = os.environ.get('DCV_NO_ONE_IMAGE_BN') is None   # tuning aid: DCV_NO_ONE_IMAGE_BN=1 keeps per-image coefficient tables for BatchNorm-only blocks
 _POOLED_BWD = os.environ.get('DCV_NO_POOLED_BWD') is None   # tuning aid: DCV_NO_POOLED_BWD=1 materialises the full-resolution gradient behind a fused normalise + pool
 _LAZY_APPLY = os.environ.get('DCV_NO_LAZY_APPLY') is None   # tuning aid: DCV_NO_LAZY_APPLY=1 always runs the stand-alone normalisation apply pass
@@ -462,9 +463,12 @@ class _ConvBlock(torch.autograd.Function):
                 d_gn_w, d_gn_b = targets.get('gn_w', None), targets.get('gn_b', None)
                 d_gn_w = torch.empty((k,), **f32) if d_gn_w is None else d_gn_w
                 d_gn_b = torch.empty((k,), **f32) if d_gn_b is None else d_gn_b
-            prm = _norm_params(cfg, ne, k, hwe, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
-            check(lib.dcv_norm_bwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(s_nc), _ptr(saved), _ptr(pqr),
-                                            _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'norm_bwd_finalize')
+            # BatchNorm-only block handed over as one image: P, Q, R and the BatchNorm parameter gradients come out of the apply kernel's prologue (no finalize launch)
+            fold = ctx.one_image and cfg.use_bn and not cfg.use_gn and _FOLD_BWD_FINALIZE and k % (16 // y.element_size()) == 0
+            if not fold:
+                prm = _norm_params(cfg, ne, k, hwe, training, bn_w, bn_b, rm, rv, None, gn_w, gn_b)
+                check(lib.dcv_norm_bwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(s_nc), _ptr(saved), _ptr(pqr),
+                                                _ptr(d_bn_w), _ptr(d_bn_b), _ptr(d_gn_w), _ptr(d_gn_b), st), 'norm_bwd_finalize')
         need_dy_pass = cfg.any or act != ACT_NONE or has_bias
         dy = dz
         dbias = None
@@ -474,7 +478,11 @@ class _ConvBlock(torch.autograd.Function):
                 dbias = targets.get('bias', None)
                 dbias = _acc_empty((k,), dev, sctx) if dbias is None else dbias
             one = cfg.any and ctx.one_image   # the coefficient table has one row: the batch is one image of n*p rows
-            if dzp is not None:
+            if cfg.any and fold:
+                bn_training = bool(training or rm is None or rv is None)
+                check(lib.dcv_act_bn_bwd_apply_fold(_ptr(dzp if dzp is not None else dz), int(dzp is not None), _ptr(y), _ptr(s_nc), _ptr(saved), int(bn_training),
+                                                    _ptr(d_bn_w), _ptr(d_bn_b), _ptr(dy), _ptr(dbias), act, slope, n * p, q, k, dt, pz, st), 'act_bn_bwd_apply_fold')
+            elif dzp is not None:
                 check(lib.dcv_act_norm_bwd_apply_pooled(_ptr(dzp), _ptr(y), _ptr(pqr), _ptr(dy), _ptr(dbias), act, slope, 1 if one else n, n * p if one else p, q, k, dt, pz, st),
                       'act_norm_bwd_apply_pooled')
             else:

@@ -243,6 +243,12 @@ int dcv_act_norm_bwd_apply(const void* dz, const void* y, const float* pqr_nc, v
  * POOLED gradient [n][h/2][w/2][c]; the gradient of a pixel is a quarter of its pooled pixel's, read in place — the full-resolution dz is never
  * written. c a whole number of 16-byte vectors, h and w even (dcv_norm_bwd_pooled_supported). Bit-identical to dcv_avgpool2d_bwd followed by the
  * plain passes. */
+/* BatchNorm-only block, batch handed over as ONE image of rows x w pixels (rows = N*H): dcv_norm_bwd_finalize + dcv_act_norm_bwd_apply[_pooled] in one
+ * launch. `s_c` = [c][2] channel totals {sum dz, sum dz*y} of dcv_norm_bwd_reduce[_pooled] (DCV_STATS_CHANNEL_TOTALS), `saved` = what dcv_norm_fwd_finalize
+ * wrote for n = 1; P, Q, R are computed in the kernel's prologue, d_bn_weight / d_bn_bias (may be NULL) written by it. `pooled`: dz is the pooled gradient
+ * [rows/2][w/2][c]. c a whole number of 16-byte vectors. */
+int dcv_act_bn_bwd_apply_fold(const void* dz, int pooled, const void* y, const float* s_c, const float* saved, int bn_training, float* d_bn_weight, float* d_bn_bias,
+                              void* dy, float* dbias_c, int act, float slope, int rows, int w, int c, int dtype, int acc_prezeroed, void* stream);
 int dcv_norm_bwd_pooled_supported(int n, int h, int w, int c, int dtype);
 int dcv_norm_bwd_reduce_pooled(const void* dzp, const void* y, float* s_nc, int n, int h, int w, int c, int dtype, int acc_prezeroed, void* stream);
 int dcv_act_norm_bwd_apply_pooled(const void* dzp, const void* y, const float* pqr_nc, void* dy, float* dbias_c, int act, float slope,
