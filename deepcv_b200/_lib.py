@@ -94,6 +94,7 @@ SYMBOLS = {
     'dcv_norm_fwd_finalize': (c_int, [POINTER(NormParams), P, P, P, P]),
     'dcv_norm_apply_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_apply_add_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dcv_bn_apply_fold_fwd': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_float, c_float, c_int, P, c_int, c_int, c_int, c_int, P]),
     'dcv_norm_apply_pool_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dcv_conv2d_gather_supported': (c_int, [POINTER(ConvShape), P, c_int, c_int]),
     'dcv_gather_pack_weight': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -189,18 +189,70 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ y, flo
   });
 }
 
+// Forward counterpart of BnFold: a BatchNorm-only block whose batch is ONE image — the consumer of the raw output (apply / apply + residual sum / apply + pool)
+// computes alpha = gamma * rstd, beta = bias - mean * alpha from the channel totals {sum y, sum y^2} itself; the CTAs of the first row range also write what
+// the backward needs (`saved`: mean, rstd | alpha, beta) and update the running statistics. Same arithmetic as fwd_finalize_kernel, minus its launch.
+struct BnFwdFold {
+  const float* stats;   // [c][2]
+  const float* gamma; const float* beta;
+  float* run_mean; float* run_var; long long* nbt;
+  float* saved;
+  double m, eps, momentum;
+  int c, training;
+};
+
+__device__ __forceinline__ void bn_fwd_coeffs(const BnFwdFold& f, int ch, bool owner, float& A, float& B) {
+  const double gamma = f.gamma ? (double)__ldg(f.gamma + ch) : 1.0, bias = f.beta ? (double)__ldg(f.beta + ch) : 0.0;
+  const bool run = f.run_mean && f.run_var;
+  double mean, var;
+  if (f.training) {
+    mean = (double)__ldg(f.stats + 2 * ch) / f.m;
+    var = (double)__ldg(f.stats + 2 * ch + 1) / f.m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (owner && run) {
+      const double unbiased = f.m > 1.0 ? var * f.m / (f.m - 1.0) : var;
+      f.run_mean[ch] = (float)((1.0 - f.momentum) * (double)f.run_mean[ch] + f.momentum * mean);
+      f.run_var[ch] = (float)((1.0 - f.momentum) * (double)f.run_var[ch] + f.momentum * unbiased);
+    }
+  } else {
+    mean = (double)f.run_mean[ch]; var = (double)f.run_var[ch];
+  }
+  // only the owner (one thread per channel) pays for the fp64 reciprocal square root; everybody else: fp32 rsqrt + one Newton step on the fp64 variance
+  // (relative error ~1e-7 on alpha / beta: below the bf16 / fp32 rounding of the tensor they are applied to)
+  if (owner) {
+    const double rstd = rsqrt(var + f.eps), alpha = gamma * rstd, beta = bias - mean * alpha;
+    f.saved[2 * ch] = (float)mean; f.saved[2 * ch + 1] = (float)rstd;
+    f.saved[2 * f.c + 2 * ch] = (float)alpha; f.saved[2 * f.c + 2 * ch + 1] = (float)beta;
+    A = (float)alpha; B = (float)beta;
+  } else {
+    const float v = (float)(var + f.eps);
+    float r = rsqrtf(v);
+    r = r * (1.5f - 0.5f * v * r * r);
+    const float alpha = (float)gamma * r;
+    A = alpha; B = (float)bias - (float)mean * alpha;
+  }
+}
+
 // ---- forward apply: z = A*y + B
-template <typename T, int VE, bool ADD = false>
-__global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ z, const NcGeom g, const T* __restrict__ other = nullptr) {
+template <typename T, int VE, bool ADD = false, bool FOLD = false>
+__global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ z, const NcGeom g, const T* __restrict__ other = nullptr,
+                                                        const BnFwdFold fold = BnFwdFold()) {
   const int col = threadIdx.x % g.cols_per_block, row = threadIdx.x / g.cols_per_block;
   const int colg = blockIdx.z * g.cols_per_block + col;
+  if constexpr (FOLD) {
+    if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0 && fold.training && fold.nbt) *fold.nbt += 1;
+  }
   if (colg >= g.cv) return;
   for_each_segment(g, [&](int img, int p0, int p1) {
     float A[VE], B[VE];
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
-      const float2 t = __ldg(reinterpret_cast<const float2*>(ab) + (size_t)img * g.c + chan_of(g, colg, VE, e));
-      A[e] = t.x; B[e] = t.y;
+      if constexpr (FOLD) {
+        bn_fwd_coeffs(fold, chan_of(g, colg, VE, e), blockIdx.x == 0 && row == 0 && (g.pack <= 1 || e < g.c), A[e], B[e]);
+      } else {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(ab) + (size_t)img * g.c + chan_of(g, colg, VE, e));
+        A[e] = t.x; B[e] = t.y;
+      }
     }
     const size_t base = ((size_t)img * g.hwv) * g.span + (size_t)colg * VE;
     for (int p = p0 + row; p < p1; p += UNR * g.rows) {
@@ -230,10 +282,20 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
 
 // ---- forward apply fused with the 2x2 / stride-2 average pooling that follows the block: zp = A * avgpool(y) + B (= avgpool(A*y + B)); the normalised
 // full-resolution tensor is never written. One thread per (pooled pixel, channel vector).
-template <typename T, int VE>
+template <typename T, int VE, bool FOLD = false>
 __global__ void __launch_bounds__(256) apply_pool_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ab, T* __restrict__ zp, int h, int w, int c, uint32_t total,
-                                                             const FastDiv div_cv, const FastDiv div_q, const FastDiv div_p) {
+                                                             const FastDiv div_cv, const FastDiv div_q, const FastDiv div_p, const BnFwdFold fold = BnFwdFold()) {
   const int cv = c / VE, q = w >> 1;
+  extern __shared__ float2 sh_ab[];   // FOLD: the c coefficient pairs, computed by every CTA from the channel totals
+  if constexpr (FOLD) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && fold.training && fold.nbt) *fold.nbt += 1;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      float A, B;
+      bn_fwd_coeffs(fold, ch, blockIdx.x == 0, A, B);
+      sh_ab[ch] = make_float2(A, B);
+    }
+    __syncthreads();
+  }
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const uint32_t t = div_cv.div(idx);
     const int cc = (int)(idx - t * cv);
@@ -243,10 +305,10 @@ __global__ void __launch_bounds__(256) apply_pool_fwd_kernel(const T* __restrict
     const T* src = y + (((size_t)row * 2) * w + (size_t)ox * 2) * c + (size_t)cc * VE;   // (img*p + oy) * 2 == img*h + 2*oy
     float v0[VE], v1[VE], v2[VE], v3[VE], out[VE];
     load_vec<T, VE>(src, v0); load_vec<T, VE>(src + c, v1); load_vec<T, VE>(src + (size_t)w * c, v2); load_vec<T, VE>(src + (size_t)(w + 1) * c, v3);
-    const float2* abp = reinterpret_cast<const float2*>(ab) + (size_t)img * c + (size_t)cc * VE;
+    const float2* abp = FOLD ? sh_ab + (size_t)cc * VE : reinterpret_cast<const float2*>(ab) + (size_t)img * c + (size_t)cc * VE;
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
-      const float2 k = __ldg(abp + e);
+      const float2 k = FOLD ? abp[e] : __ldg(abp + e);
       out[e] = fmaf(k.x, ((v0[e] + v1[e]) + (v2[e] + v3[e])) * 0.25f, k.y);
     }
     store_vec<T, VE>(zp + (size_t)idx * VE, out);
@@ -736,6 +798,39 @@ int dcv_norm_fwd_finalize(const dcv_norm_params* prm, const float* stats_nc, flo
   finalize_grid(prm, &cpb, &blocks);
   fwd_finalize_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(*prm, stats_nc, ab_nc, saved, cpb);
   DCV_LAUNCH_CHECK("fwd_finalize_kernel");
+  return 0;
+}
+
+int dcv_bn_apply_fold_fwd(const void* y, const void* other, int pool, void* out, const float* stats_c, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float eps, float momentum, int bn_training, float* saved, int rows, int w, int c, int dtype, void* stream) {
+  using namespace dcv;
+  DCV_REQUIRE(y && out && stats_c && saved, "bn_apply_fold_fwd: null pointer");
+  DCV_REQUIRE(rows > 0 && w > 0 && c > 0 && (long long)rows * w < (1ll << 31) && momentum >= 0.f, "bn_apply_fold_fwd: bad arguments (momentum = None is served by dcv_norm_fwd_finalize)");
+  DCV_REQUIRE(bn_training || (running_mean && running_var), "bn_apply_fold_fwd: eval-mode BatchNorm needs running statistics");
+  DCV_REQUIRE(!(pool && other), "bn_apply_fold_fwd: pooling and a residual operand are exclusive");
+  cudaStream_t st = as_stream(stream);
+  const int hw = rows * w;
+  BnFwdFold fold{stats_c, gamma, beta, running_mean, running_var, num_batches_tracked, saved, (double)hw, (double)eps, (double)momentum, c, bn_training};
+  dim3 grid; int block;
+  DCV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VE = 16 / sizeof(T);
+    DCV_REQUIRE(c % VE == 0 && vec_ok(y, out, other, 1, hw, c, VE), "bn_apply_fold_fwd: channels must be whole 16-byte vectors at 16-byte aligned pointers");
+    if (pool) {
+      DCV_REQUIRE(rows % 2 == 0 && w % 2 == 0 && c <= 4096, "bn_apply_fold_fwd: the 2x2 / stride-2 windows must tile the input (and c <= 4096)");
+      const int p = rows / 2, q = w / 2;
+      const uint32_t total = (uint32_t)((size_t)p * q * (c / VE));
+      apply_pool_fwd_kernel<T, VE, true><<<grid_for(total, 256), 256, (size_t)c * sizeof(float2), st>>>((const T*)y, nullptr, (T*)out, rows, w, c, total, FastDiv(c / VE), FastDiv(q), FastDiv(p), fold);
+    } else if (other) {
+      static const int occ = streaming_ctas_per_sm((const void*)apply_fwd_kernel<T, VE, true, true>);
+      NcGeom g = make_geom<VE>(1, hw, c, occ, &grid, &block);
+      apply_fwd_kernel<T, VE, true, true><<<grid, block, 0, st>>>((const T*)y, nullptr, (T*)out, g, (const T*)other, fold);
+    } else {
+      static const int occ = streaming_ctas_per_sm((const void*)apply_fwd_kernel<T, VE, false, true>);
+      NcGeom g = make_geom<VE>(1, hw, c, occ, &grid, &block);
+      apply_fwd_kernel<T, VE, false, true><<<grid, block, 0, st>>>((const T*)y, nullptr, (T*)out, g, nullptr, fold);
+    }
+  });
+  DCV_LAUNCH_CHECK("bn_apply_fold_fwd");
   return 0;
 }
 

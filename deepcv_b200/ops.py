@@ -300,6 +300,7 @@ def _acc_empty(shape, device, sctx: Optional['StepContext'] = None) -> torch.Ten
 _FUSE_STATS = os.environ.get('DCV_FUSED_STATS') == '1'
 _CHANNEL_TOTALS = os.environ.get('DCV_NO_CHANNEL_TOTALS') is None   # A/B switch: per-(image, channel) sums even for BatchNorm-only blocks
 _SIDE_WGRAD = os.environ.get('DCV_SIDE_WGRAD') == '1'   # opt-in: weight-gradient kernels on a second stream (measured: 6.377 -> 6.323 ms on the ImageNet-shaped step — they compete with the normalisation passes for HBM — not worth a second stream inside the captured step by default)
+_FOLD_FWD_FINALIZE = os.environ.get('DCV_NO_FOLD_FWD_FINALIZE') is None   # tuning aid: DCV_NO_FOLD_FWD_FINALIZE=1 keeps the stand-alone forward finalize launch of BatchNorm-only blocks
 _FOLD_BWD_FINALIZE = os.environ.get('DCV_NO_FOLD_BWD_FINALIZE') is None   # tuning aid: DCV_NO_FOLD_BWD_FINALIZE=1 keeps the stand-alone backward finalize launch of BatchNorm-only blocks
 _ONE_IMAGE_BN = os.environ.get('DCV_NO_ONE_IMAGE_BN') is None   # tuning aid: DCV_NO_ONE_IMAGE_BN=1 keeps per-image coefficient tables for BatchNorm-only blocks
 _POOLED_BWD = os.environ.get('DCV_NO_POOLED_BWD') is None   # tuning aid: DCV_NO_POOLED_BWD=1 materialises the full-resolution gradient behind a fused normalise + pool
@@ -344,6 +345,12 @@ def _norm_params(cfg: NormConfig, n: int, c: int, hw: int, training: bool, bn_w,
     return NormParams(n, c, hw, int(cfg.use_bn), int(bn_training), cfg.bn_eps, cfg.bn_momentum,
                       _ptr(bn_w), _ptr(bn_b), _ptr(rm), _ptr(rv), _ptr(nbt),
                       int(cfg.use_gn), cfg.gn_groups, cfg.gn_eps, _ptr(gn_w), _ptr(gn_b))
+
+
+def _bn_apply_fold(fold, y, other, pool: bool, out, rows: int, w: int, c: int, dt: int, st) -> None:
+    stats, bn_w, bn_b, rm, rv, nbt, eps, momentum, bn_training, saved = fold
+    check(lib.dcv_bn_apply_fold_fwd(_ptr(y), _ptr(other), int(pool), _ptr(out), _ptr(stats), _ptr(bn_w), _ptr(bn_b), _ptr(rm), _ptr(rv), _ptr(nbt), eps, momentum, bn_training,
+                                    _ptr(saved), rows, w, c, dt, st), 'bn_apply_fold_fwd')
 
 
 class _ConvBlock(torch.autograd.Function):
@@ -408,15 +415,28 @@ class _ConvBlock(torch.autograd.Function):
         one_image = bool(totals & 2) and n > 1 and n * p * q < (1 << 31) and _ONE_IMAGE_BN and \
             bool(gathered or gemm_shape is not None or (algo != ALGO_DIRECT and lib.dcv_conv2d_tc_supported(ctypes.byref(shape), dt, 0)))
         ne, hwe = (1, n * p * q) if one_image else (n, p * q)
+        fold = None
         if cfg.any:
             groups = cfg.gn_groups if cfg.use_gn else 1
             saved = torch.empty((int(lib.dcv_norm_saved_floats(ne, k, groups)),), dtype=torch.float32, device=dev)
-            ab = torch.empty((ne, k, 2), dtype=torch.float32, device=dev)
-            prm = _norm_params(cfg, ne, k, hwe, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
-            check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(ab), _ptr(saved), st), 'norm_fwd_finalize')
-            if not defer_apply:
-                out = empty_nhwc(n, k, p, q, x.dtype, dev)
-                check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), ne, hwe, k, dt, st), 'norm_apply_fwd')
+            # BatchNorm-only block handed over as one image: no finalize launch — the kernel that applies the normalisation (here, or the consumer of the
+            # pending normalisation) computes the coefficients from the channel totals in its prologue and writes `saved` / the running statistics
+            if one_image and cfg.use_bn and not cfg.use_gn and cfg.bn_momentum >= 0. and _FOLD_FWD_FINALIZE and k % (16 // y.element_size()) == 0:
+                bn_training = bool(training or rm is None or rv is None)
+                fold = (stats, bn_w, bn_b, rm, rv, nbt, float(cfg.bn_eps), float(cfg.bn_momentum), int(bn_training), saved)
+                ab = saved   # what travels with a pending normalisation (`PendingNorm.ab`): the consumer finds the fold arguments in the link
+                if link is not None:
+                    link['fold'] = fold
+                if not defer_apply:
+                    out = empty_nhwc(n, k, p, q, x.dtype, dev)
+                    _bn_apply_fold(fold, y, None, False, out, n * p, q, k, dt, st)
+            else:
+                ab = torch.empty((ne, k, 2), dtype=torch.float32, device=dev)
+                prm = _norm_params(cfg, ne, k, hwe, training, bn_w, bn_b, rm, rv, nbt, gn_w, gn_b)
+                check(lib.dcv_norm_fwd_finalize(ctypes.byref(prm), _ptr(stats), _ptr(ab), _ptr(saved), st), 'norm_fwd_finalize')
+                if not defer_apply:
+                    out = empty_nhwc(n, k, p, q, x.dtype, dev)
+                    check(lib.dcv_norm_apply_fwd(_ptr(y), _ptr(ab), _ptr(out), ne, hwe, k, dt, st), 'norm_apply_fwd')
         ctx.save_for_backward(x, w_op, y, stats, saved, bn_w, bn_b, gn_w, gn_b, rm, rv)
         # the fp32 master weight, when it already is [K][R][S][C] in memory: the data-gradient operand is packed straight from it in backward
         ctx.w_master = weight.detach() if (weight.dtype == torch.float32 and weight.permute(0, 2, 3, 1).is_contiguous()) else None
@@ -624,8 +644,13 @@ class _ApplyNorm(torch.autograd.Function):
         n, c, h, w = y.shape
         ctx.geom, ctx.pool, ctx.has_other, ctx.link = (n, c, h, w), pool, other is not None, link
         st, dt = _stream(), _dt(y)
-        one = ab.shape[0] == 1 and n > 1   # BatchNorm-only block: one row of coefficients, the batch is one image of n*h rows (h even when pooled: image
-        ne, he = (1, n * h) if one else (n, h)   # boundaries fall on even rows)
+        fold = link.get('fold') if link is not None else None
+        if fold is not None:   # BatchNorm-only block, batch as one image: the coefficients are computed by this very kernel (no finalize launch)
+            out = empty_nhwc(n, c, h // 2, w // 2, y.dtype, y.device) if pool else empty_nhwc(n, c, h, w, y.dtype, y.device)
+            _bn_apply_fold(fold, y, other, pool, out, n * h, w, c, dt, st)
+            return out
+        one = ab.dim() == 3 and ab.shape[0] == 1 and n > 1   # BatchNorm-only block: one row of coefficients, the batch is one image of n*h rows (h even when
+        ne, he = (1, n * h) if one else (n, h)                # pooled: image boundaries fall on even rows)
         if pool:
             out = empty_nhwc(n, c, h // 2, w // 2, y.dtype, y.device)
             check(lib.dcv_norm_apply_pool_fwd(_ptr(y), _ptr(ab), _ptr(out), ne, he, w, c, dt, st), 'norm_apply_pool_fwd')

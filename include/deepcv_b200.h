@@ -227,6 +227,12 @@ int dcv_norm_apply_fwd(const void* y, const float* ab_nc, void* z, int n, int hw
  *          tensor is never written. Backward of both needs no kernel of its own: d/dy is what the block's backward already computes from dz
  *          (dz = the link's incoming gradient; dz = dcv_avgpool2d_bwd of the pooled gradient). */
 int dcv_norm_apply_add_fwd(const void* y, const float* ab_nc, const void* other, void* z, int n, int hw, int c, int dtype, void* stream);
+/* BatchNorm-only block, batch handed over as ONE image of rows x w pixels (rows = N*H): dcv_norm_fwd_finalize + one of the three apply passes in one launch.
+ * `stats_c` = [c][2] channel totals {sum y, sum y^2} (DCV_STATS_CHANNEL_TOTALS); the kernel computes alpha / beta itself, writes `saved` (4*c floats: what
+ * the backward reads) and updates the running statistics (momentum >= 0; momentum = None goes through dcv_norm_fwd_finalize). other != NULL: + residual
+ * sum; pool != 0: 2x2 / stride-2 average pooling of the result. c a whole number of 16-byte vectors. */
+int dcv_bn_apply_fold_fwd(const void* y, const void* other, int pool, void* out, const float* stats_c, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float eps, float momentum, int bn_training, float* saved, int rows, int w, int c, int dtype, void* stream);
 int dcv_norm_apply_pool_fwd(const void* y, const float* ab_nc, void* zp, int n, int h, int w, int c, int dtype, void* stream);
 /* s_nc[n][c][2] = { sum(dz), sum(dz*y) } (overwritten). */
 int dcv_norm_bwd_reduce(const void* dz, const void* y, float* s_nc, int n, int hw, int c, int dtype, int acc_prezeroed, void* stream);
