@@ -32,6 +32,7 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def assert_close(a, b, tol, what=''):
     e = rel_err(a, b)
+    print(f'[parity] {what}: relative error {e:.3e} (bound {tol:.1e})')   # shown with `pytest -s`: the margin under each bound
     assert e <= tol, f'{what}: relative error {e:.3e} > {tol:.1e}'
 
 
@@ -432,7 +433,7 @@ def test_default_net_against_golden(dev, golden_dir, default_hp, dtype):
 # oracle that rounds where the device stores bf16. The distance to the plain fp32 oracle is not hidden: it is measured, printed and held under a
 # recorded ceiling here (max over parameter tensors of max|g - g32| / max|g32|; ceilings = about 1.5x the value measured on B200, see the test log).
 DEFAULT_NET_BF16_GRAD_CEILING = 0.6    # measured on B200: 0.35 worst, 0.08 median (26 well-conditioned tensors)
-RESNET_BF16_GRAD_CEILING = 0.8         # measured on B200: 0.51 (96x96, batch 6) / 0.41 (224x224, batch 3) worst, 0.32 / 0.20 median
+RESNET_BF16_GRAD_CEILING = 1.0         # measured on B200 over repeated runs (fp32 atomics reorder the statistics sums): 0.56-0.62 (96x96, batch 6) / 0.39-0.66 (224x224, batch 3) worst, 0.32 / 0.20 median
 
 
 def _record_distance_to_fp32_oracle(what, model, plain, plain64, ceiling):
