@@ -19,6 +19,7 @@ into a CUDA graph on its first call. Prints ONE JSON line (rank 0):
 """
 import argparse
 import copy
+import gc
 import json
 import os
 import statistics
@@ -470,6 +471,8 @@ def measure_workload(name, args, dev, world, rank, local_rank, peaks):
         n = n_warm if warm else e2e_steps
         # `dataloader_prefetch_batches` (reference meta/data/datasets.py:76-115, what train() applies to a pinned loader): batch i + 1 is copied while step i runs
         trainer.run(dataloader_prefetch_batches([(pool_host[i % n_host], labels_host[i % n_host]) for i in range(n)], dev), max_epochs=trainer.state.epoch + 1)
+    gc.collect()   # garbage of an earlier workload (its captured graph, pinned pools) must not be collected — cudaFree synchronises — inside the timed loop
+    torch.cuda.synchronize()
     ms_e2e = timed(e2e_run, 3)
     e2e_value = world * batch * e2e_steps / (ms_e2e / 1e3)
     if os.environ.get('DCV_BENCH_PROFILE_E2E'):   # tuning aid: where the HOST time of the end-to-end loop goes (cProfile, printed to stderr, not timed)
@@ -534,7 +537,12 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     peaks = load_peaks()
     names = ['cifar', 'imagenet'] if args.workload == 'all' else [args.workload]
-    results = {name: measure_workload(name, args, dev, world, rank, local_rank, peaks) for name in names}
+    results = {}
+    for name in names:
+        results[name] = measure_workload(name, args, dev, world, rank, local_rank, peaks)
+        gc.collect()   # the workload's captured graph, pools and pinned batches go NOW (not in the middle of the next workload's timed loop)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
 
     def shutdown():
         # A captured CUDA graph that contains NCCL kernels keeps the communicator busy: destroy_process_group() was seen to hang on it.

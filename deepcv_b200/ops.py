@@ -359,6 +359,7 @@ class _ConvBlock(torch.autograd.Function):
         _require_cuda(x, weight)
         ctx.notify = notify
         ctx.link = link   # side channel from the consumer of a pending normalisation (see `_ApplyNorm.backward`)
+        ctx.set_materialize_grads(False)   # the coefficient table returned next to a deferred output has no gradient: no zero-fill kernel for it in backward
         shape = _conv_shape(x, weight, stride, padding, dilation)
         n, k, p, q = shape.n, shape.k, shape.p, shape.q
         dev, st = x.device, _stream()
@@ -460,6 +461,8 @@ class _ConvBlock(torch.autograd.Function):
         # placeholder of the right shape) and the two normalisation passes below read it in place
         dzp = ctx.link.pop('pooled_dz', None) if ctx.link is not None else None
         if dzp is None:
+            if dz is None:   # (gradients are not materialised: an output nobody differentiates through)
+                dz = torch.zeros_like(y)
             dz = as_nhwc(dz.detach(), y.dtype)
         f32 = dict(dtype=torch.float32, device=dev)
         # gradients go straight into the caller's bucket slices on the FIRST backward after `zero_grad`; a second backward through the same layer before the
