@@ -1042,25 +1042,26 @@ __global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(co
   const uint32_t bars = rows_base + (uint32_t)PR_ROW_BUFS * (uint32_t)prm.rows_bytes;
   auto full = [&](int i) { return bars + 8u * i; };
   auto empty = [&](int i) { return bars + 8u * (PR_FWD_STAGES + i); };
+  constexpr int NACC = 512 / N_TILE >= 4 ? 4 : 2;   // TMEM accumulator buffers: four tiles of output may be waiting for their (HBM-bound) stores
   auto tfull = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + i); };
-  auto tempty = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 2 + i); };
-  const uint32_t bres = bars + 8u * (2 * PR_FWD_STAGES + 4), tmem_slot = bars + 8u * (2 * PR_FWD_STAGES + 5);
-  auto rfull = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 6 + i); };
-  auto rempty = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 6 + PR_ROW_BUFS + i); };
+  auto tempty = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + NACC + i); };
+  const uint32_t bres = bars + 8u * (2 * PR_FWD_STAGES + 2 * NACC), tmem_slot = bars + 8u * (2 * PR_FWD_STAGES + 2 * NACC + 1);
+  auto rfull = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 2 * NACC + 2 + i); };
+  auto rempty = [&](int i) { return bars + 8u * (2 * PR_FWD_STAGES + 2 * NACC + 2 + PR_ROW_BUFS + i); };
   uint8_t* gen_base = smem_raw + (res_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const dcv_conv_shape& s = prm.s;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < PR_FWD_STAGES; ++i) { mbar_init(full(i), 2); mbar_init(empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 8); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 8); }
     mbar_init(bres, 1);
     for (int i = 0; i < PR_ROW_BUFS; ++i) { mbar_init(rfull(i), 1); mbar_init(rempty(i), 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * N_TILE) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(NACC * N_TILE) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // the line stages (chunks of filter rows >= R stay zero) and the row buffers (their margins are the horizontal padding) start as zeros
@@ -1113,7 +1114,7 @@ __global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(co
         umma_commit(empty(stage));
         umma_commit(tfull(as));
         if (++stage == PR_FWD_STAGES) { stage = 0; phase ^= 1u; }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (++as == NACC) { as = 0; aphase ^= 1u; }
       }
     }
   } else if (warp < 10) {
@@ -1143,7 +1144,7 @@ __global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == NACC) { as = 0; aphase ^= 1u; }
     }
   } else {
     // ===== producer warps 10..17: transpose the staged rows into pixel-pair lines
@@ -1167,7 +1168,7 @@ __global__ void __launch_bounds__(PR_FWD_THREADS, 1) conv_fwd_tc_pairs_kernel(co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N_TILE) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NACC * N_TILE) : "memory");
   }
 }
 
